@@ -1,0 +1,44 @@
+#!/usr/bin/env python3
+"""Builds dsp-map_b200/lib/libdspmap_b200.so: hand-written sm_100a kernels + the C-ABI (include/dspmap_b200.h).
+
+nvcc cross-compiles without a GPU. -fmad=false, IEEE division / square root and no flush-to-zero are REQUIRED: the
+kernels reproduce the reference's fp32 results bit for bit.  The built .so is git-ignored but travels
+to the GPU box with gpurun."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "lib")
+SO = os.path.join(OUT, "libdspmap_b200.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+         "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
+         "-Xcompiler", "-fPIC,-ffp-contract=off,-O2", "-shared", "-cudart", "static"]
+
+
+def sources():
+    return [os.path.join(SRC, f) for f in ("dspmap.cu", "velocity_estimator.cpp")]
+
+
+def stale():
+    if not os.path.exists(SO):
+        return True
+    t = os.path.getmtime(SO)
+    deps = [os.path.join(SRC, f) for f in os.listdir(SRC)] + [os.path.join(HERE, "..", "include", "dspmap_b200.h")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and not stale():
+        return SO
+    os.makedirs(OUT, exist_ok=True)
+    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + sources() + ["-o", SO]
+    subprocess.check_call(cmd)
+    return SO
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,921 @@
+// dspmap.cu — host side of the B200 DSP map: handle, HBM layout, per-frame launch sequence, C-ABI.
+// Mirrors the public surface of class DSPMap (g-ch/DSP-map include/dsp_dynamic.h:142-446, 1549-1584); the
+// per-frame work is done by the sm_100a kernels in dspmap_frame.cuh.  There is no CPU fallback.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <fstream>
+#include <random>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/dspmap_b200.h"
+#include "dspmap_frame.cuh"
+#include "velocity_estimator.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+enum Family {
+    FAM_SETUP = 0, FAM_OBS, FAM_ENUM, FAM_PREDICT, FAM_ARRIVE, FAM_PYRAMID, FAM_CK, FAM_WEIGHT, FAM_NORM, FAM_NEWBORN,
+    FAM_RESAMPLE, FAM_CLEANUP, FAM_READER, FAM_MISC, FAM_COUNT
+};
+const char *kFamilyNames[FAM_COUNT] = {"setup", "obs_bin", "enumerate", "predict", "arrive", "pyramid_lists", "ck_pass",
+                                       "weight_pass", "newborn_norm", "newborn", "resample_future", "cleanup", "reader", "misc"};
+
+struct ProfSlot {
+    cudaEvent_t a, b;
+    int fam;
+};
+
+}  // namespace
+
+struct dspmap {
+    dspmap_config cfg;
+    MapConst mc;
+    DevPtrs dp;
+    cudaStream_t stream = nullptr, own_stream = nullptr, side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    std::vector<void *> allocs;
+    // host mirrors
+    std::vector<float> ptab, vtab, lut, planes0;
+    std::vector<int> nbr;
+    float p_std = 0.2f, v_std = 0.1f, sigma_ob = 0.2f, kappa = 0.01f, Pd = 0.95f;  // :154-158
+    float nb_weight = 0.04f;                                                        // :162
+    int nb_num = 20;                                                                // :163
+    bool tables_dirty = true;
+    bool have_last = false;
+    float last_p[3] = {0, 0, 0};
+    double last_t = 0;
+    bool nb_latched = false;
+    int nb_min_static = 0, nb_model_gen = 0;
+    float update_time = 0.f;
+    int update_counter = 0;
+    int record_flag = 0;
+    float record_time = 1.f;
+    bool recorded_once = false;
+    std::string record_folder = ".";
+    int stage_limit = 4;
+    int max_points = 0, cap_cand = 0;
+    // pinned staging
+    float *h_pts = nullptr, *h_tagged = nullptr, *h_future = nullptr, *h_xyz = nullptr;
+    DevState *h_state = nullptr;
+    int *h_count = nullptr;
+    int n_tagged = 0;               // size of the current newborn input
+    std::vector<float> tagged_host; // last newborn input (world frame), for getKMClusterResult
+    // reader scratch
+    int *d_blockcnt = nullptr, *d_blockoff = nullptr, *d_count = nullptr;
+    float *d_xyz = nullptr, *d_future = nullptr;
+    int occ_blocks = 0;
+    // ordered prediction noise (dsp_dynamic.h:653-659) stays armed while particles with vz != 0 may exist:
+    // constructor-seeded particles until their first prediction, or an injected state that contains such particles
+    bool vz_mode = false;
+    int vz_blocks = 0;
+    long long host_u_cur = 0;  // uniform draws consumed on the host while seeding
+    VelocityEstimator estimator;
+    // statistics
+    long long launches_total = 0, launches_frame = 0;
+    DevState last_state;
+    bool profile = false;
+    std::vector<ProfSlot> prof_slots;
+    size_t prof_used = 0;
+    double prof_ms[FAM_COUNT] = {0};
+    int prof_n[FAM_COUNT] = {0};
+};
+
+namespace {
+
+#define CK(x)                                                                                   \
+    do {                                                                                        \
+        cudaError_t e_ = (x);                                                                   \
+        if (e_ != cudaSuccess) {                                                                \
+            g_err = std::string(#x) + ": " + cudaGetErrorString(e_);                            \
+            return DSPMAP_E_CUDA;                                                               \
+        }                                                                                       \
+    } while (0)
+
+template <typename T>
+int dalloc(dspmap *m, T **p, size_t n, bool zero = true) {
+    void *q = nullptr;
+    size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+    CK(cudaMalloc(&q, bytes));
+    if (zero) CK(cudaMemsetAsync(q, 0, bytes, m->stream));
+    m->allocs.push_back(q);
+    *p = (T *)q;
+    return DSPMAP_OK;
+}
+
+void prof_begin(dspmap *m, int fam) {
+    if (!m->profile) return;
+    if (m->prof_used == m->prof_slots.size()) {
+        ProfSlot s;
+        cudaEventCreate(&s.a);
+        cudaEventCreate(&s.b);
+        m->prof_slots.push_back(s);
+    }
+    m->prof_slots[m->prof_used].fam = fam;
+    cudaEventRecord(m->prof_slots[m->prof_used].a, m->stream);
+}
+void prof_end(dspmap *m) {
+    if (!m->profile) return;
+    cudaEventRecord(m->prof_slots[m->prof_used].b, m->stream);
+    ++m->prof_used;
+}
+void prof_collect(dspmap *m) {
+    for (size_t i = 0; i < m->prof_used; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, m->prof_slots[i].a, m->prof_slots[i].b) == cudaSuccess) {
+            m->prof_ms[m->prof_slots[i].fam] += ms;
+            m->prof_n[m->prof_slots[i].fam] += 1;
+        }
+    }
+    m->prof_used = 0;
+}
+
+#define LAUNCH(m, fam, kernel, grid, block, smem, ...)                              \
+    do {                                                                            \
+        prof_begin(m, fam);                                                         \
+        kernel<<<(grid), (block), (smem), (m)->stream>>>(__VA_ARGS__);              \
+        prof_end(m);                                                                \
+        ++(m)->launches_total;                                                      \
+        ++(m)->launches_frame;                                                      \
+    } while (0)
+
+const int kSMs = 148;
+inline int grid_for(long long n, int block, int max_blocks = kSMs * 8) {
+    long long g = (n + block - 1) / block;
+    if (g < 1) g = 1;
+    if (g > max_blocks) g = max_blocks;
+    return (int)g;
+}
+
+// generateGaussianRandomsVectorZeroCenter (dsp_dynamic.h:1150-1160); seeded from cfg.table_seed instead of time(NULL)
+int gen_tables(dspmap *m) {
+    const int G = m->mc.G;
+    std::default_random_engine random(m->cfg.table_seed);
+    std::normal_distribution<double> n1(0, m->p_std);
+    std::normal_distribution<double> n2(0, m->v_std);
+    m->ptab.resize(G);
+    m->vtab.resize(G);
+    for (int i = 0; i < G; i++) {
+        m->ptab[i] = n1(random);
+        m->vtab[i] = n2(random);
+    }
+    CK(cudaMemcpyAsync((void *)m->dp.ptab, m->ptab.data(), sizeof(float) * G, cudaMemcpyHostToDevice, m->stream));
+    CK(cudaMemcpyAsync((void *)m->dp.vtab, m->vtab.data(), sizeof(float) * G, cudaMemcpyHostToDevice, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    m->tables_dirty = false;
+    return DSPMAP_OK;
+}
+
+int upload_particles(dspmap *m, const int32_t *ids, const float *vals, int n) {
+    const MapConst &mc = m->mc;
+    CK(cudaMemsetAsync(m->dp.M, 0, sizeof(ulonglong2) * (size_t)mc.V, m->stream));
+    if (n > 0) {
+        int *d_ids;
+        float *d_vals;
+        CK(cudaMalloc(&d_ids, sizeof(int) * 2 * (size_t)n));
+        CK(cudaMalloc(&d_vals, sizeof(float) * 8 * (size_t)n));
+        CK(cudaMemcpyAsync(d_ids, ids, sizeof(int) * 2 * (size_t)n, cudaMemcpyHostToDevice, m->stream));
+        CK(cudaMemcpyAsync(d_vals, vals, sizeof(float) * 8 * (size_t)n, cudaMemcpyHostToDevice, m->stream));
+        LAUNCH(m, FAM_MISC, k_load_scatter, grid_for(n, 256), 256, 0, mc, m->dp, d_ids, d_vals, n);
+        CK(cudaStreamSynchronize(m->stream));
+        cudaFree(d_ids);
+        cudaFree(d_vals);
+    }
+    return DSPMAP_OK;
+}
+
+// addRandomParticles (dsp_dynamic.h:594-624) on the host; the store is empty at this point, so "first free slot"
+// (addAParticle, :1183-1201) is simply the next slot of the voxel.  Seeded particles carry the newborn flag 15:
+// the first frame's prediction skips them (:649) and the second one draws their velocity noise (:653-659).
+int seed_particles(dspmap *m) {
+    const MapConst &mc = m->mc;
+    const int n = m->cfg.init_particle_num;
+    if (n <= 0) return DSPMAP_OK;
+    std::vector<int> fill(mc.V, 0), ids;
+    std::vector<float> vals;
+    u64 k = 0;
+    const u64 seed = m->cfg.uniform_seed;
+    for (int i = 0; i < n; i++) {
+        float px = dsp_uniform(seed, k, -mc.hx, mc.hx), py = dsp_uniform(seed, k + 1, -mc.hy, mc.hy), pz = dsp_uniform(seed, k + 2, -mc.hz, mc.hz);
+        float vx = dsp_uniform(seed, k + 3, -1.f, 1.f), vy = dsp_uniform(seed, k + 4, -1.f, 1.f), vz = dsp_uniform(seed, k + 5, -1.f, 1.f);
+        k += 6;
+        int idx = dsp_voxel_index(mc, px, py, pz);
+        if (idx < 0) continue;
+        if (fill[idx] >= mc.S) continue;
+        ids.push_back(idx);
+        ids.push_back(fill[idx]++);
+        const float rec[8] = {15.f, vx, vy, vz, px, py, pz, m->cfg.init_weight};
+        vals.insert(vals.end(), rec, rec + 8);
+    }
+    m->host_u_cur = (long long)k;
+    m->vz_mode = true;
+    return upload_particles(m, ids.data(), vals.data(), (int)ids.size() / 2);
+}
+
+int ensure_cand_capacity(dspmap *m) {
+    int need = m->max_points * std::max(m->nb_num, 1);
+    if (need <= m->cap_cand) return DSPMAP_OK;
+    m->cap_cand = need;
+    if (dalloc(m, &m->dp.CA, need, false) != DSPMAP_OK) return DSPMAP_E_CUDA;
+    if (dalloc(m, &m->dp.CB, need, false) != DSPMAP_OK) return DSPMAP_E_CUDA;
+    if (dalloc(m, &m->dp.Ckey, need, false) != DSPMAP_OK) return DSPMAP_E_CUDA;
+    if (dalloc(m, &m->dp.Cdst, need, false) != DSPMAP_OK) return DSPMAP_E_CUDA;
+    if (dalloc(m, &m->dp.cseg, need, false) != DSPMAP_OK) return DSPMAP_E_CUDA;
+    m->dp.cap_cand = need;
+    return DSPMAP_OK;
+}
+
+// Enqueue the first half of a frame: binning, prediction, reassignment, pyramid lists, C_z pass, weight pass.
+int enqueue_frame_a(dspmap *m, const FrameConst &fc, const float *d_pts) {
+    const MapConst &mc = m->mc;
+    DevPtrs dp = m->dp;
+    dp.pts = d_pts;
+    m->launches_frame = 0;
+    const int B = 256;
+    LAUNCH(m, FAM_SETUP, k_frame_setup, 1, 256, 0, mc, fc, dp);
+    // observations
+    if (fc.n_points > 0) {
+        LAUNCH(m, FAM_OBS, k_obs_classify, grid_for(fc.n_points, B), B, 0, mc, fc, dp);
+    }
+    LAUNCH(m, FAM_OBS, k_scan_small, 1, 1024, 0, dp.obs_cnt, dp.obs_off, dp.obs_capoff, mc.OBS - 1, mc.P);
+    if (fc.n_points > 0) {
+        LAUNCH(m, FAM_OBS, k_obs_scatter, grid_for(fc.n_points, B), B, 0, mc, fc, dp);
+        LAUNCH(m, FAM_OBS, k_obs_rank, grid_for(fc.n_points, B), B, 0, mc, fc, dp);
+    }
+    // prediction and reassignment
+    if (fc.vz_mode) {
+        LAUNCH(m, FAM_PREDICT, k_vz_count, grid_for(mc.V, B), B, 0, mc, dp);
+        LAUNCH(m, FAM_PREDICT, k_scan_blocksum, m->vz_blocks, 256, 0, dp.vzcnt, mc.V, dp.vzblk);
+        LAUNCH(m, FAM_PREDICT, k_scan_small, 1, 1024, 0, dp.vzblk, dp.vzblkoff, (int *)nullptr, 0, m->vz_blocks);
+        LAUNCH(m, FAM_PREDICT, k_scan_apply, m->vz_blocks, 256, 0, dp.vzcnt, mc.V, dp.vzblkoff, dp.vzoff, m->vz_blocks);
+    }
+    LAUNCH(m, FAM_ENUM, k_enumerate, grid_for(mc.V, B), B, 0, mc, dp, 1);
+    LAUNCH(m, FAM_PREDICT, k_predict, kSMs * 8, B, 0, mc, fc, dp);
+    if (fc.vz_mode) LAUNCH(m, FAM_PREDICT, k_vz_advance, 1, 32, 0, mc, dp);
+    LAUNCH(m, FAM_ARRIVE, k_group_owner, kSMs * 2, B, 0, dp, &dp.st->n_mov_owner, dp.mowner, dp.mcnt, dp.mbase, &dp.st->mov_top);
+    LAUNCH(m, FAM_ARRIVE, k_group_scatter, kSMs * 4, B, 0, &dp.st->n_mov, dp.MBdst, dp.MBkey, dp.mbase, dp.mfill, dp.mseg);
+    LAUNCH(m, FAM_ARRIVE, k_arrive, kSMs * 4, B, 0, mc, fc, dp);
+    LAUNCH(m, FAM_PYRAMID, k_scan_small, 1, 1024, 0, dp.pcount, dp.poff, (int *)nullptr, 0, mc.P);
+    LAUNCH(m, FAM_PYRAMID, k_pyr_scatter, kSMs * 8, B, 0, dp);
+    LAUNCH(m, FAM_PYRAMID, k_pyr_sort, std::min(mc.P, kSMs * 3), 512, PYR_SORT_CAP * sizeof(u64), mc, dp);
+    if (fc.stage_limit >= 2) {
+        size_t smem4 = sizeof(float) * (DSP_LUT_HALF + 3 + K4_TERMS) + sizeof(float4) * (256 + mc.OBS);
+        LAUNCH(m, FAM_CK, k_ck, std::min(mc.P, kSMs * 2), K4_THREADS, smem4, mc, fc, dp);
+        size_t smem5 = sizeof(float) * (DSP_LUT_HALF + 3) + sizeof(float4) * (size_t)mc.NB * (mc.OBS - 1);
+        int chunks = (mc.L + K5_THREADS - 1) / K5_THREADS;
+        LAUNCH(m, FAM_WEIGHT, k_weight, kSMs * 2, K5_THREADS, smem5, mc, fc, dp, chunks);
+    }
+    CK(cudaGetLastError());
+    return DSPMAP_OK;
+}
+// Second half: newborn particles (needs the velocity-tagged cloud), occupancy + resampling + future status.
+int enqueue_frame_b(dspmap *m, const FrameConst &fc, const float *d_tagged) {
+    const MapConst &mc = m->mc;
+    DevPtrs dp = m->dp;
+    dp.tagged = d_tagged;
+    const int B = 256;
+    if (fc.stage_limit >= 3) {
+        LAUNCH(m, FAM_NORM, k_norm, 1, 128, 0, mc, fc, dp);
+        if (fc.n_tagged > 0 && fc.nb_num > 0) {
+            LAUNCH(m, FAM_NEWBORN, k_nb_point0, grid_for(fc.n_tagged, B), B, 0, mc, fc, dp);
+            LAUNCH(m, FAM_NEWBORN, k_scan_small, 1, 1024, 0, dp.ninmap, dp.nrank, (int *)nullptr, 0, fc.n_tagged);
+            LAUNCH(m, FAM_NEWBORN, k_nb_point1, grid_for(fc.n_tagged, 128), 128, 0, mc, fc, dp);
+            LAUNCH(m, FAM_NEWBORN, k_scan_small, 1, 1024, 0, dp.nvcnt, dp.nvoff, (int *)nullptr, 0, fc.n_tagged);
+            LAUNCH(m, FAM_NEWBORN, k_scan_small, 1, 1024, 0, dp.nrcnt, dp.nroff, (int *)nullptr, 0, fc.n_tagged);
+            LAUNCH(m, FAM_NEWBORN, k_nb_cand, grid_for((long long)fc.n_tagged * fc.nb_num, B), B, 0, mc, fc, dp, (u64)m->cfg.uniform_seed);
+            LAUNCH(m, FAM_NEWBORN, k_group_owner, kSMs * 2, B, 0, dp, &dp.st->n_cand_owner, dp.cowner, dp.ccnt, dp.cbase, &dp.st->cand_top);
+            LAUNCH(m, FAM_NEWBORN, k_group_scatter, kSMs * 4, B, 0, &dp.st->n_cand, dp.Cdst, dp.Ckey, dp.cbase, dp.cfill, dp.cseg);
+            LAUNCH(m, FAM_NEWBORN, k_nb_place, kSMs * 8, B, 0, mc, fc, dp);
+            LAUNCH(m, FAM_NEWBORN, k_nb_cursors, 1, 32, 0, mc, fc, dp);
+        }
+    }
+    if (fc.stage_limit >= 4) {
+        LAUNCH(m, FAM_RESAMPLE, k_resample, grid_for(mc.V, 128), 128, 0, mc, fc, dp);
+    }
+    LAUNCH(m, FAM_CLEANUP, k_cleanup, kSMs * 2, B, 0, dp);
+    CK(cudaGetLastError());
+    return DSPMAP_OK;
+}
+
+// DSPMap::update's host prologue (dsp_dynamic.h:186-224, 292-293): validation, odometry delta, frame scalars
+int frame_prologue(dspmap *m, int n, float px, float py, float pz, double t, float qw, float qx, float qy, float qz, FrameConst *fc) {
+    if (!m->have_last) {  // function-local statics initialised by the first call (:187-190)
+        m->last_p[0] = px; m->last_p[1] = py; m->last_p[2] = pz;
+        m->last_t = t;
+        m->have_last = true;
+    }
+    if (std::fabs(qw) > 1.001f || std::fabs(qx) > 1.001f || std::fabs(qy) > 1.001f || std::fabs(qz) > 1.001f) {
+        printf("Invalid quaternion.\n");
+        return DSPMAP_REJECTED;
+    }
+    float ox = px - m->last_p[0], oy = py - m->last_p[1], oz = pz - m->last_p[2];
+    float dt = (float)(t - m->last_t);
+    if (std::fabs(ox) > 10.f || std::fabs(oy) > 10.f || std::fabs(oz) > 10.f || dt < 0.f || dt > 10.f) {
+        printf("!!! delt_t = %f\n", dt);
+        return DSPMAP_REJECTED;
+    }
+    m->last_p[0] = px; m->last_p[1] = py; m->last_p[2] = pz;
+    m->last_t = t;
+    m->update_time += dt;  // :634-635
+    m->update_counter += 1;
+    if (!m->nb_latched) {  // function-local statics of the newborn step, frozen at first use (:808-811; st:791)
+        m->nb_min_static = (int)((float)m->nb_num * (m->mc.model == 1 ? 0.2f : 0.15f));
+        m->nb_model_gen = (int)((float)m->nb_num * 0.8f);
+        m->nb_latched = true;
+    }
+    memset(fc, 0, sizeof(*fc));
+    fc->q[0] = qw; fc->q[1] = qx; fc->q[2] = qy; fc->q[3] = qz;
+    dsp_quat_inverse(fc->q, fc->qi);
+    fc->sx = -ox; fc->sy = -oy; fc->sz = -oz;
+    fc->dt = dt;
+    fc->cur[0] = px; fc->cur[1] = py; fc->cur[2] = pz;
+    fc->sigma = m->sigma_ob;
+    fc->Pd = m->Pd;
+    fc->one_minus_Pd = 1 - m->Pd;
+    fc->kappa = m->kappa;
+    fc->nb_weight = m->nb_weight;
+    fc->nb_num = m->nb_num;
+    fc->nb_min_static = m->nb_min_static;
+    fc->nb_model_gen = m->nb_model_gen;
+    fc->n_points = n;
+    fc->stage_limit = m->stage_limit;
+    fc->vz_mode = m->vz_mode ? 1 : 0;
+    return DSPMAP_OK;
+}
+
+int frame_epilogue(dspmap *m) {
+    CK(cudaMemcpyAsync(m->h_state, m->dp.st, sizeof(DevState), cudaMemcpyDeviceToHost, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    m->last_state = *m->h_state;
+    if (m->profile) prof_collect(m);
+    // once a frame has predicted every particle and drew no noise, all vz are 0 for good (LIMIT_MOVEMENT_IN_XY_PLANE)
+    if (m->vz_mode && m->stage_limit >= 4 && m->last_state.n_vz == 0 && m->last_state.n_skipped == 0) m->vz_mode = false;
+    if (m->last_state.overflow) {
+        g_err = "device list capacity exceeded (raise max_points / live-particle capacity)";
+        return DSPMAP_E_CAPACITY;
+    }
+    return DSPMAP_OK;
+}
+
+int write_particle_csv(dspmap *m);
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------------
+// C-ABI
+// ------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char *dspmap_last_error(void) { return g_err.c_str(); }
+
+void dspmap_default_config(dspmap_config *c) {
+    memset(c, 0, sizeof(*c));
+    c->nx = 66; c->ny = 66; c->nz = 40;
+    c->resolution = 0.15f;
+    c->angle_resolution = 3;
+    c->half_fov_h = 42; c->half_fov_v = 24;
+    c->max_particles_per_voxel = 9;
+    c->pyramid_neighbor_n = 1;
+    c->model = 0;
+    c->prediction_times = 6;
+    const float ft[6] = {0.05f, 0.2f, 0.5f, 1.f, 1.5f, 2.f};
+    memcpy(c->prediction_future_time, ft, sizeof(ft));
+    c->occlusion_margin = 0.3f;
+    c->init_particle_num = 0;
+    c->init_weight = 0.01f;
+    c->table_seed = (uint64_t)time(nullptr);
+    c->uniform_seed = (uint64_t)time(nullptr);
+    c->gaussian_table_size = 10000000;
+    c->max_observations_per_pyramid = 100;
+    c->device = 0;
+    c->max_points = 65536;
+}
+
+int dspmap_create(const dspmap_config *cfg, dspmap **out) {
+    if (!cfg || !out) { g_err = "null argument"; return DSPMAP_E_BAD_ARG; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        g_err = "no CUDA device: this library has no CPU path";
+        return DSPMAP_E_NO_DEVICE;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess || prop.major < 10) {
+        g_err = "device is not sm_100 class: the kernels are built for sm_100a only";
+        return DSPMAP_E_NO_DEVICE;
+    }
+    CK(cudaSetDevice(cfg->device));
+    dspmap *m = new dspmap();
+    m->cfg = *cfg;
+    MapConst &mc = m->mc;
+    memset(&mc, 0, sizeof(mc));
+    mc.nx = cfg->nx; mc.ny = cfg->ny; mc.nz = cfg->nz;
+    mc.V = cfg->nx * cfg->ny * cfg->nz;
+    mc.res = cfg->resolution;
+    mc.hx = (mc.res * (float)mc.nx) * 0.5f;  // :528-530
+    mc.hy = (mc.res * (float)mc.ny) * 0.5f;
+    mc.hz = (mc.res * (float)mc.nz) * 0.5f;
+    mc.Nh = cfg->half_fov_h * 2 / cfg->angle_resolution;  // :58-60
+    mc.Nv = cfg->half_fov_v * 2 / cfg->angle_resolution;
+    mc.P = mc.Nh * mc.Nv;
+    const int pyramid_num = 360 * 180 / cfg->angle_resolution / cfg->angle_resolution;  // :63
+    const int safe_particle_num = mc.V * cfg->max_particles_per_voxel + 1e5;           // :64
+    mc.max_ppv = cfg->max_particles_per_voxel;
+    mc.model = cfg->model;
+    mc.S = cfg->safe_particles_per_voxel > 0 ? cfg->safe_particles_per_voxel : mc.max_ppv * (mc.model == 1 ? 5 : 2);  // :65, st:63
+    mc.L = cfg->safe_particles_per_pyramid > 0 ? cfg->safe_particles_per_pyramid : safe_particle_num / pyramid_num * 2;  // :66
+    mc.T = cfg->prediction_times;
+    mc.NB = (2 * cfg->pyramid_neighbor_n + 1) * (2 * cfg->pyramid_neighbor_n + 1);
+    mc.NBW = mc.NB + 1;
+    mc.OBS = cfg->max_observations_per_pyramid > 0 ? cfg->max_observations_per_pyramid : 100;
+    mc.G = cfg->gaussian_table_size > 0 ? cfg->gaussian_table_size : 10000000;
+    mc.occl = cfg->occlusion_margin;
+    mc.z_begin = cfg->shard_z_begin;
+    mc.z_end = cfg->shard_z_end > 0 ? cfg->shard_z_end : mc.nz;
+    for (int i = 0; i < DSP_MAX_T; ++i) mc.ft[i] = cfg->prediction_future_time[i];
+    if (mc.S > DSP_MAX_SLOTS || mc.S < 1 || mc.T > DSP_MAX_T || mc.T < 0 || mc.V <= 0 || mc.P <= 0 ||
+        mc.Nh + mc.Nv + 2 > DSP_MAX_PLANES || (long long)mc.V * DSP_MAX_SLOTS > 2147483647ll || mc.L < 1 ||
+        mc.OBS > 128 || mc.NB * (mc.OBS - 1) * 16 > 150000) {
+        g_err = "configuration outside supported limits (S <= 128 slots, T <= 8, V*128 < 2^31)";
+        delete m;
+        return DSPMAP_E_BAD_ARG;
+    }
+    mc.vlo = mc.S >= 64 ? ~0ull : ((1ull << mc.S) - 1ull);
+    mc.vhi = mc.S <= 64 ? 0ull : (mc.S >= 128 ? ~0ull : ((1ull << (mc.S - 64)) - 1ull));
+    m->max_points = cfg->max_points > 0 ? cfg->max_points : 65536;
+    CK(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
+    m->stream = m->own_stream;
+
+    DevPtrs &dp = m->dp;
+    memset(&dp, 0, sizeof(dp));
+    const size_t V = mc.V, VS = V * mc.S, P = mc.P, MP = m->max_points;
+    long long cap_live = std::min<long long>((long long)V * mc.S, 8ll << 20);
+    dp.cap_live = (int)cap_live;
+    const size_t CL = (size_t)cap_live;
+    int rc = DSPMAP_OK;
+#define A(ptr, n) if (rc == DSPMAP_OK) rc = dalloc(m, &ptr, (n))
+    A(dp.PA, VS); A(dp.PB, VS); A(dp.M, V); A(dp.M0, V); A(dp.MS, V); A(dp.OCCV, V); A(dp.FUT, V * std::max(mc.T, 1));
+    A(dp.E, CL);
+    m->vz_blocks = (int)((V + SCAN_BLOCK - 1) / SCAN_BLOCK);
+    A(dp.vzcnt, V); A(dp.vzoff, V + 1); A(dp.vzblk, m->vz_blocks + 1); A(dp.vzblkoff, m->vz_blocks + 1);
+    A(dp.OR, MP); A(dp.OPID, MP); A(dp.obs_cnt, P); A(dp.obs_fill, P); A(dp.obs_maxbits, P); A(dp.obs_off, P + 1);
+    A(dp.obs_capoff, P + 1); A(dp.OSEG, MP); A(dp.OBSP, P * mc.OBS); A(dp.CZ, P * mc.OBS); A(dp.INV, MP + P * 0 + 1024);
+    A(dp.MBA, CL); A(dp.MBB, CL); A(dp.MBkey, CL); A(dp.MBdst, CL); A(dp.MBq, CL);
+    A(dp.mcnt, V); A(dp.mfill, V); A(dp.mbase, V); A(dp.mowner, V); A(dp.mseg, CL);
+    A(dp.Fkey, CL); A(dp.Faddr, CL); A(dp.Fq, CL); A(dp.pcount, P); A(dp.pfill, P); A(dp.poff, P + 1); A(dp.plen, P);
+    A(dp.PSkey, CL); A(dp.PSaddr, CL); A(dp.LA, CL); A(dp.LP, CL);
+    A(dp.NPC, MP); A(dp.ninmap, MP + 1); A(dp.nrank, MP + 1); A(dp.nstatic, MP); A(dp.nvcnt, MP + 1); A(dp.nrcnt, MP + 1);
+    A(dp.nvoff, MP + 1); A(dp.nroff, MP + 1); A(dp.nimask, MP);
+    A(dp.ccnt, V); A(dp.cfill, V); A(dp.cbase, V); A(dp.cowner, V);
+    A(dp.st, 1);
+    float *d_ptab, *d_vtab, *d_lut, *d_planes0, *d_pts, *d_tagged;
+    int *d_nbr;
+    A(d_ptab, mc.G); A(d_vtab, mc.G); A(d_lut, DSP_LUT_HALF); A(d_planes0, 3 * (mc.Nh + mc.Nv + 2)); A(dp.planes, 3 * (mc.Nh + mc.Nv + 2));
+    A(d_nbr, P * mc.NBW); A(d_pts, MP * 3); A(d_tagged, MP * 7);
+    m->occ_blocks = (int)((V + OCC_BLOCK - 1) / OCC_BLOCK);
+    A(m->d_blockcnt, m->occ_blocks + 1); A(m->d_blockoff, m->occ_blocks + 1); A(m->d_count, 1); A(m->d_xyz, V * 3);
+    A(m->d_future, V * std::max(mc.T, 1));
+#undef A
+    if (rc != DSPMAP_OK) { dspmap_destroy(m); return rc; }
+    dp.ptab = d_ptab; dp.vtab = d_vtab; dp.lut = d_lut; dp.planes0 = d_planes0; dp.nbr = d_nbr;
+    dp.pts = d_pts; dp.tagged = d_tagged;
+    if (ensure_cand_capacity(m) != DSPMAP_OK) { dspmap_destroy(m); return DSPMAP_E_CUDA; }
+    CK(cudaMallocHost(&m->h_pts, sizeof(float) * MP * 3));
+    CK(cudaMallocHost(&m->h_tagged, sizeof(float) * MP * 7));
+    CK(cudaMallocHost(&m->h_future, sizeof(float) * V * std::max(mc.T, 1)));
+    CK(cudaMallocHost(&m->h_xyz, sizeof(float) * V * 3));
+    CK(cudaMallocHost(&m->h_state, sizeof(DevState)));
+    CK(cudaMallocHost(&m->h_count, sizeof(int)));
+
+    // boundary-plane normals in the sensor frame (:563-578)
+    const float ang = (float)cfg->angle_resolution / 180.f * 3.14159265358979323846;  // :543
+    m->planes0.assign(3 * (mc.Nh + mc.Nv + 2), 0.f);
+    {
+        int h0 = -cfg->half_fov_h / cfg->angle_resolution, h1 = -h0;
+        for (int i = h0; i <= h1; i++) {
+            m->planes0[3 * (i + h1) + 0] = -std::sin((float)i * ang);
+            m->planes0[3 * (i + h1) + 1] = std::cos((float)i * ang);
+            m->planes0[3 * (i + h1) + 2] = 0.f;
+        }
+        float *pv = &m->planes0[3 * (mc.Nh + 1)];
+        int v0 = -cfg->half_fov_v / cfg->angle_resolution, v1 = -v0;
+        for (int i = v0; i <= v1; i++) {
+            pv[3 * (i + v1) + 0] = std::sin((float)i * ang);
+            pv[3 * (i + v1) + 1] = 0.f;
+            pv[3 * (i + v1) + 2] = std::cos((float)i * ang);
+        }
+    }
+    // neighbour table (:1128-1147; mn:1135-1136)
+    m->nbr.assign(P * mc.NBW, 0);
+    for (int p = 0; p < mc.P; p++) {
+        int h = p / mc.Nv, v = p % mc.Nv, n = 0;
+        for (int i = -cfg->pyramid_neighbor_n; i <= cfg->pyramid_neighbor_n; ++i)
+            for (int j = -cfg->pyramid_neighbor_n; j <= cfg->pyramid_neighbor_n; ++j) {
+                int hh = h + i, vv = v + j;
+                if (hh >= 0 && hh < mc.Nh && vv >= 0 && vv < mc.Nv) m->nbr[(size_t)p * mc.NBW + 1 + n++] = hh * mc.Nv + vv;
+            }
+        m->nbr[(size_t)p * mc.NBW] = n;
+    }
+    // PDF table (:1282-1292), host libm exactly as the reference evaluates it; only indices 10000..20000 are kept:
+    // the table is symmetric (x = (i-10000)*0.001f negates exactly and powf(x,2) is even), checked here.
+    m->lut.resize(DSP_LUT_HALF);
+    {
+        std::vector<float> full(20000);
+        for (int i = 0; i < 20000; ++i) {
+            float x = (float)(i - 10000) * 0.001f;
+            full[i] = (1.f / (sqrtf(2.f * 1.57079632679489661923))) * expf(-powf(x, 2) / (2));
+        }
+        for (int k = 1; k < 10000; ++k)
+            if (memcmp(&full[10000 + k], &full[10000 - k], 4) != 0) {
+                g_err = "PDF table is not symmetric on this libm";
+                dspmap_destroy(m);
+                return DSPMAP_E_BAD_ARG;
+            }
+        for (int h = 0; h < 10000; ++h) m->lut[h] = full[10000 + h];
+        m->lut[10000] = full[0];  // |i - 10000| = 10000 only for i = 0 (x = -10); unreachable, queries clamp to |x| <= 9.9
+    }
+    CK(cudaMemcpyAsync(d_lut, m->lut.data(), sizeof(float) * DSP_LUT_HALF, cudaMemcpyHostToDevice, m->stream));
+    CK(cudaMemcpyAsync(d_planes0, m->planes0.data(), sizeof(float) * m->planes0.size(), cudaMemcpyHostToDevice, m->stream));
+    CK(cudaMemcpyAsync(d_nbr, m->nbr.data(), sizeof(int) * m->nbr.size(), cudaMemcpyHostToDevice, m->stream));
+    CK(cudaFuncSetAttribute(k_pyr_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PYR_SORT_CAP * sizeof(u64))));
+    CK(cudaFuncSetAttribute(k_ck, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CK(cudaFuncSetAttribute(k_weight, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaStreamSynchronize(m->stream));
+    if (gen_tables(m) != DSPMAP_OK) { dspmap_destroy(m); return DSPMAP_E_CUDA; }
+    m->estimator.reset(cfg->uniform_seed);
+    rc = seed_particles(m);
+    if (rc != DSPMAP_OK) { dspmap_destroy(m); return rc; }
+    if (m->host_u_cur) {
+        DevState st;
+        memset(&st, 0, sizeof(st));
+        st.u_cur = m->host_u_cur;
+        CK(cudaMemcpy(dp.st, &st, sizeof(st), cudaMemcpyHostToDevice));
+    }
+    memset(&m->last_state, 0, sizeof(m->last_state));
+    printf("Map is ready to update!\n");  // :174
+    *out = m;
+    return DSPMAP_OK;
+}
+
+void dspmap_destroy(dspmap *m) {
+    if (!m) return;
+    cudaSetDevice(m->cfg.device);
+    cudaDeviceSynchronize();
+    for (void *p : m->allocs) cudaFree(p);
+    if (m->h_pts) cudaFreeHost(m->h_pts);
+    if (m->h_tagged) cudaFreeHost(m->h_tagged);
+    if (m->h_future) cudaFreeHost(m->h_future);
+    if (m->h_xyz) cudaFreeHost(m->h_xyz);
+    if (m->h_state) cudaFreeHost(m->h_state);
+    if (m->h_count) cudaFreeHost(m->h_count);
+    for (auto &s : m->prof_slots) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+    if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+    if (m->ev_join) cudaEventDestroy(m->ev_join);
+    if (m->own_stream) cudaStreamDestroy(m->own_stream);
+    if (m->side) cudaStreamDestroy(m->side);
+    delete m;
+}
+
+static int update_common(dspmap *m, int n, int stride, const float *pts, float px, float py, float pz, double t, float qw,
+                         float qx, float qy, float qz, const float *tagged, int n_tagged, bool use_estimator) {
+    if (!m || n < 0 || stride < 3 || (n > 0 && !pts)) { g_err = "bad argument"; return DSPMAP_E_BAD_ARG; }
+    if (n > m->max_points || n_tagged > m->max_points) { g_err = "more points than dspmap_config.max_points"; return DSPMAP_E_CAPACITY; }
+    CK(cudaSetDevice(m->cfg.device));
+    FrameConst fc;
+    int rc = frame_prologue(m, n, px, py, pz, t, qw, qx, qy, qz, &fc);
+    if (rc != DSPMAP_OK) return rc;
+    if (m->tables_dirty && (rc = gen_tables(m)) != DSPMAP_OK) return rc;
+    if ((rc = ensure_cand_capacity(m)) != DSPMAP_OK) return rc;
+    for (int i = 0; i < n; ++i) {
+        m->h_pts[3 * i] = pts[(size_t)i * stride];
+        m->h_pts[3 * i + 1] = pts[(size_t)i * stride + 1];
+        m->h_pts[3 * i + 2] = pts[(size_t)i * stride + 2];
+    }
+    if (n > 0) CK(cudaMemcpyAsync((void *)m->dp.pts, m->h_pts, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, m->stream));
+    if ((rc = enqueue_frame_a(m, fc, m->dp.pts)) != DSPMAP_OK) return rc;
+    if (use_estimator) {
+        // the reference's side thread (dsp_dynamic.h:297, 1377-1544), overlapped with the kernels enqueued above exactly
+        // as the reference overlaps it with prediction + update (:297-311)
+        m->estimator.estimate(m->mc, fc, m->planes0.data(), m->h_pts, n, m->cfg.model, m->tagged_host);
+    } else if (tagged) {
+        m->tagged_host.assign(tagged, tagged + (size_t)7 * n_tagged);
+    }
+    int nt = (int)(m->tagged_host.size() / 7);
+    if (nt > m->max_points) { g_err = "newborn input larger than max_points"; return DSPMAP_E_CAPACITY; }
+    if (nt > 0) {
+        memcpy(m->h_tagged, m->tagged_host.data(), sizeof(float) * 7 * (size_t)nt);
+        CK(cudaMemcpyAsync((void *)m->dp.tagged, m->h_tagged, sizeof(float) * 7 * (size_t)nt, cudaMemcpyHostToDevice, m->stream));
+    }
+    fc.n_tagged = nt;
+    if ((rc = enqueue_frame_b(m, fc, m->dp.tagged)) != DSPMAP_OK) return rc;
+    if ((rc = frame_epilogue(m)) != DSPMAP_OK) return rc;
+    // particle CSV (:325-350)
+    if (m->record_flag) {
+        if (m->record_flag < 0 || (m->update_time > m->record_time && !m->recorded_once)) {
+            m->recorded_once = true;
+            write_particle_csv(m);
+        }
+    }
+    return DSPMAP_OK;
+}
+
+int dspmap_update(dspmap *m, int n, int stride, const float *pts, float px, float py, float pz, double t, float qw,
+                  float qx, float qy, float qz) {
+    return update_common(m, n, stride, pts, px, py, pz, t, qw, qx, qy, qz, nullptr, 0, true);
+}
+int dspmap_update_tagged(dspmap *m, int n, int stride, const float *pts, float px, float py, float pz, double t,
+                         float qw, float qx, float qy, float qz, const float *tagged, int n_tagged) {
+    return update_common(m, n, stride, pts, px, py, pz, t, qw, qx, qy, qz, tagged, n_tagged, false);
+}
+int dspmap_update_device(dspmap *m, int n, const float *d_pts, float px, float py, float pz, double t, float qw,
+                         float qx, float qy, float qz, const float *d_tagged, int n_tagged) {
+    if (!m || n < 0 || n > m->max_points || n_tagged > m->max_points) { g_err = "bad argument"; return DSPMAP_E_BAD_ARG; }
+    CK(cudaSetDevice(m->cfg.device));
+    FrameConst fc;
+    int rc = frame_prologue(m, n, px, py, pz, t, qw, qx, qy, qz, &fc);
+    if (rc != DSPMAP_OK) return rc;
+    if (m->tables_dirty && (rc = gen_tables(m)) != DSPMAP_OK) return rc;
+    if ((rc = ensure_cand_capacity(m)) != DSPMAP_OK) return rc;
+    fc.n_tagged = n_tagged;
+    if ((rc = enqueue_frame_a(m, fc, d_pts)) != DSPMAP_OK) return rc;
+    if ((rc = enqueue_frame_b(m, fc, d_tagged)) != DSPMAP_OK) return rc;
+    if (m->vz_mode) return frame_epilogue(m);  // keep the ordered-noise path armed only as long as it is needed
+    return DSPMAP_OK;
+}
+
+int dspmap_set_prediction_variance(dspmap *m, float p, float v) {
+    if (!m) return DSPMAP_E_BAD_ARG;
+    m->p_std = p;
+    m->v_std = v;
+    m->tables_dirty = true;  // regenerated before the next frame (cursors are kept, :355-360)
+    return DSPMAP_OK;
+}
+int dspmap_set_observation_stddev(dspmap *m, float s) { if (!m) return DSPMAP_E_BAD_ARG; m->sigma_ob = s; return DSPMAP_OK; }
+int dspmap_set_newborn_weight(dspmap *m, float w) { if (!m) return DSPMAP_E_BAD_ARG; m->nb_weight = w; return DSPMAP_OK; }
+int dspmap_set_newborn_number(dspmap *m, int n) {
+    if (!m || n < 0 || n > DSP_MAX_NB_NUM) { g_err = "newborn number must be in [0, 64]"; return DSPMAP_E_BAD_ARG; }
+    m->nb_num = n;
+    return DSPMAP_OK;
+}
+int dspmap_set_particle_record_flag(dspmap *m, int flag, float record_time, const char *folder) {
+    if (!m) return DSPMAP_E_BAD_ARG;
+    m->record_flag = flag;
+    m->record_time = record_time;
+    if (folder) m->record_folder = folder;
+    return DSPMAP_OK;
+}
+int dspmap_set_voxel_filter_resolution(dspmap *m, float r) { if (!m) return DSPMAP_E_BAD_ARG; m->estimator.filter_res = r; return DSPMAP_OK; }
+
+int dspmap_get_occupancy_device(dspmap *m, float thr, float *d_xyz, int cap, int *d_count, float *d_future) {
+    if (!m) return DSPMAP_E_BAD_ARG;
+    const MapConst &mc = m->mc;
+    LAUNCH(m, FAM_READER, k_occ_count, m->occ_blocks, 256, 0, mc, m->dp, thr, m->d_blockcnt, d_future);
+    LAUNCH(m, FAM_READER, k_scan_small, 1, 1024, 0, m->d_blockcnt, m->d_blockoff, (int *)nullptr, 0, m->occ_blocks);
+    LAUNCH(m, FAM_READER, k_occ_write, m->occ_blocks, 256, 0, mc, m->dp, thr, m->d_blockoff, d_xyz, cap, d_count, m->occ_blocks);
+    CK(cudaGetLastError());
+    return DSPMAP_OK;
+}
+int dspmap_get_occupancy(dspmap *m, float thr, float *xyz_out, int cap, int *n_out, float *future) {
+    if (!m) return DSPMAP_E_BAD_ARG;
+    CK(cudaSetDevice(m->cfg.device));
+    const MapConst &mc = m->mc;
+    int rc = dspmap_get_occupancy_device(m, thr, m->d_xyz, mc.V, m->d_count, future ? m->d_future : nullptr);
+    if (rc != DSPMAP_OK) return rc;
+    CK(cudaMemcpyAsync(m->h_count, m->d_count, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    if (future) CK(cudaMemcpyAsync(m->h_future, m->d_future, sizeof(float) * (size_t)mc.V * mc.T, cudaMemcpyDeviceToHost, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    int n = *m->h_count;
+    if (n_out) *n_out = n;
+    int ncopy = std::min(n, cap);
+    if (xyz_out && ncopy > 0) {
+        CK(cudaMemcpyAsync(m->h_xyz, m->d_xyz, sizeof(float) * 3 * (size_t)ncopy, cudaMemcpyDeviceToHost, m->stream));
+        CK(cudaStreamSynchronize(m->stream));
+        memcpy(xyz_out, m->h_xyz, sizeof(float) * 3 * (size_t)ncopy);
+    }
+    if (future) memcpy(future, m->h_future, sizeof(float) * (size_t)mc.V * mc.T);
+    if (m->profile) prof_collect(m);
+    return DSPMAP_OK;
+}
+int dspmap_clear_prediction(dspmap *m) {
+    if (!m) return DSPMAP_E_BAD_ARG;
+    LAUNCH(m, FAM_READER, k_future_clear, kSMs * 4, 256, 0, m->mc, m->dp);
+    CK(cudaStreamSynchronize(m->stream));
+    return DSPMAP_OK;
+}
+int dspmap_get_tagged_cloud(dspmap *m, float *out, int cap) {
+    if (!m) return DSPMAP_E_BAD_ARG;
+    int n = (int)(m->tagged_host.size() / 7);
+    if (out) memcpy(out, m->tagged_host.data(), sizeof(float) * 7 * (size_t)std::min(n, cap));
+    return n;
+}
+
+void dspmap_voxel_center(const dspmap *m, int index, float *xyz) { dsp_voxel_center(m->mc, index, xyz); }
+int dspmap_voxel_index(const dspmap *m, float x, float y, float z, int *index) {
+    int i = dsp_voxel_index(m->mc, x, y, z);
+    if (i < 0) return 0;
+    *index = i;
+    return 1;
+}
+float dspmap_uniform(dspmap *m, float lo, float hi) { return m->estimator.uniform(lo, hi); }
+
+void dspmap_dims(const dspmap *m, int32_t *d) {
+    const MapConst &mc = m->mc;
+    int v[] = {mc.V, mc.S, mc.P, mc.L, mc.T, mc.Nh, mc.Nv, mc.NBW, mc.max_ppv, mc.nx, mc.ny, mc.nz, mc.OBS, mc.model};
+    memcpy(d, v, sizeof(v));
+}
+
+int dspmap_dump_particles(dspmap *m, int32_t *ids, float *vals, int cap) {
+    if (!m) return DSPMAP_E_BAD_ARG;
+    CK(cudaSetDevice(m->cfg.device));
+    const MapConst &mc = m->mc;
+    LAUNCH(m, FAM_MISC, k_reset_counter, 1, 1, 0, &m->dp.st->n_live);
+    LAUNCH(m, FAM_MISC, k_enumerate, grid_for(mc.V, 256), 256, 0, mc, m->dp, 0);
+    int n = 0;
+    CK(cudaMemcpyAsync(&n, &m->dp.st->n_live, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    if (!ids || n == 0) return n;
+    int *d_keys;
+    float *d_vals;
+    CK(cudaMalloc(&d_keys, sizeof(int) * (size_t)n));
+    CK(cudaMalloc(&d_vals, sizeof(float) * 8 * (size_t)n));
+    LAUNCH(m, FAM_MISC, k_dump_gather, grid_for(n, 256), 256, 0, mc, m->dp, d_keys, d_vals);
+    std::vector<int> keys(n);
+    std::vector<float> v(8 * (size_t)n);
+    CK(cudaMemcpyAsync(keys.data(), d_keys, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, m->stream));
+    CK(cudaMemcpyAsync(v.data(), d_vals, sizeof(float) * 8 * (size_t)n, cudaMemcpyDeviceToHost, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    cudaFree(d_keys);
+    cudaFree(d_vals);
+    std::vector<int> order(n);
+    for (int i = 0; i < n; ++i) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return keys[a] < keys[b]; });
+    for (int i = 0; i < n && i < cap; ++i) {
+        int k = keys[order[i]];
+        ids[2 * i] = k >> DSP_KEY_SHIFT;
+        ids[2 * i + 1] = k & (DSP_MAX_SLOTS - 1);
+        memcpy(vals + 8 * (size_t)i, &v[8 * (size_t)order[i]], 8 * sizeof(float));
+    }
+    return n;
+}
+int dspmap_load_particles(dspmap *m, const int32_t *ids, const float *vals, int n) {
+    if (!m || n < 0) return DSPMAP_E_BAD_ARG;
+    CK(cudaSetDevice(m->cfg.device));
+    m->vz_mode = false;
+    for (int i = 0; i < n; ++i) {
+        const float *r = vals + 8 * (size_t)i;
+        if (r[3] != 0.f || !(r[0] > 0.1f && r[0] < 6.f)) { m->vz_mode = true; break; }
+    }
+    return upload_particles(m, ids, vals, n);
+}
+int dspmap_dump_voxel_objects(dspmap *m, float *out) {
+    if (!m) return DSPMAP_E_BAD_ARG;
+    const MapConst &mc = m->mc;
+    std::vector<float> occ(4 * (size_t)mc.V), fut((size_t)mc.V * std::max(mc.T, 1));
+    CK(cudaMemcpy(occ.data(), m->dp.OCCV, sizeof(float) * occ.size(), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(fut.data(), m->dp.FUT, sizeof(float) * fut.size(), cudaMemcpyDeviceToHost));
+    for (int v = 0; v < mc.V; ++v) {
+        float *o = out + (size_t)v * (4 + mc.T);
+        memcpy(o, &occ[4 * (size_t)v], 16);
+        for (int t = 0; t < mc.T; ++t) o[4 + t] = fut[(size_t)v * mc.T + t];
+    }
+    return DSPMAP_OK;
+}
+int dspmap_dump_observations(dspmap *m, int32_t *counts, float *maxlen, float *pts) {
+    if (!m) return DSPMAP_E_BAD_ARG;
+    const MapConst &mc = m->mc;
+    CK(cudaStreamSynchronize(m->stream));
+    CK(cudaMemcpy(counts, m->dp.obs_cnt, sizeof(int) * mc.P, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(maxlen, m->dp.obs_maxbits, sizeof(int) * mc.P, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < mc.P; ++i) counts[i] = std::min(counts[i], mc.OBS - 1);  // :282-284
+    if (pts) {
+        std::vector<float> o(4 * (size_t)mc.P * mc.OBS), cz((size_t)mc.P * mc.OBS);
+        CK(cudaMemcpy(o.data(), m->dp.OBSP, sizeof(float) * o.size(), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(cz.data(), m->dp.CZ, sizeof(float) * cz.size(), cudaMemcpyDeviceToHost));
+        for (size_t k = 0; k < (size_t)mc.P * mc.OBS; ++k) {
+            pts[5 * k] = o[4 * k]; pts[5 * k + 1] = o[4 * k + 1]; pts[5 * k + 2] = o[4 * k + 2];
+            pts[5 * k + 3] = cz[k];
+            pts[5 * k + 4] = o[4 * k + 3];
+        }
+    }
+    return DSPMAP_OK;
+}
+int dspmap_dump_pyramid_lists(dspmap *m, int32_t *offsets, int32_t *entries, int cap) {
+    if (!m) return DSPMAP_E_BAD_ARG;
+    const MapConst &mc = m->mc;
+    CK(cudaStreamSynchronize(m->stream));
+    std::vector<int> poff(mc.P + 1), plen(mc.P);
+    CK(cudaMemcpy(poff.data(), m->dp.poff, sizeof(int) * (mc.P + 1), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(plen.data(), m->dp.plen, sizeof(int) * mc.P, cudaMemcpyDeviceToHost));
+    std::vector<int> la(std::max(poff[mc.P], 1));
+    CK(cudaMemcpy(la.data(), m->dp.LA, sizeof(int) * (size_t)poff[mc.P], cudaMemcpyDeviceToHost));
+    int n = 0;
+    for (int p = 0; p < mc.P; ++p) {
+        offsets[p] = n;
+        for (int j = 0; j < plen[p]; ++j) {
+            if (entries && n < cap) {
+                int a = la[poff[p] + j];
+                entries[2 * n] = a / mc.S;
+                entries[2 * n + 1] = a % mc.S;
+            }
+            ++n;
+        }
+    }
+    offsets[mc.P] = n;
+    return n;
+}
+int dspmap_cursors(dspmap *m, int64_t *c) {
+    if (!m) return DSPMAP_E_BAD_ARG;
+    DevState st;
+    CK(cudaStreamSynchronize(m->stream));
+    CK(cudaMemcpy(&st, m->dp.st, sizeof(st), cudaMemcpyDeviceToHost));
+    c[0] = st.p_cur; c[1] = st.v_cur; c[2] = st.u_cur;
+    return DSPMAP_OK;
+}
+int dspmap_set_cursors(dspmap *m, int64_t p, int64_t v, int64_t u) {
+    if (!m) return DSPMAP_E_BAD_ARG;
+    DevState st;
+    CK(cudaStreamSynchronize(m->stream));
+    CK(cudaMemcpy(&st, m->dp.st, sizeof(st), cudaMemcpyDeviceToHost));
+    st.p_cur = p; st.v_cur = v; st.u_cur = u;
+    CK(cudaMemcpy(m->dp.st, &st, sizeof(st), cudaMemcpyHostToDevice));
+    return DSPMAP_OK;
+}
+int dspmap_counters(dspmap *m, int64_t *out) {
+    if (!m) return DSPMAP_E_BAD_ARG;
+    const DevState &s = m->last_state;
+    int64_t v[16] = {s.n_live, s.n_left_map, s.n_voxel_full, s.n_pyramid_full, s.n_moved, s.n_fov, s.n_cand, s.n_born,
+                     s.n_low_weight, s.n_pre, s.n_old, s.n_out, s.n_valid, s.n_inexact, m->launches_frame, m->launches_total};
+    memcpy(out, v, sizeof(v));
+    return DSPMAP_OK;
+}
+int dspmap_set_last_pose(dspmap *m, float px, float py, float pz, double t) {
+    if (!m) return DSPMAP_E_BAD_ARG;
+    m->last_p[0] = px; m->last_p[1] = py; m->last_p[2] = pz;
+    m->last_t = t;
+    m->have_last = true;
+    return DSPMAP_OK;
+}
+int dspmap_set_stage_limit(dspmap *m, int k) { if (!m) return DSPMAP_E_BAD_ARG; m->stage_limit = k; return DSPMAP_OK; }
+int dspmap_set_stream(dspmap *m, void *s) {
+    if (!m) return DSPMAP_E_BAD_ARG;
+    cudaStreamSynchronize(m->stream);
+    m->stream = s ? (cudaStream_t)s : m->own_stream;
+    return DSPMAP_OK;
+}
+int dspmap_synchronize(dspmap *m) {
+    if (!m) return DSPMAP_E_BAD_ARG;
+    CK(cudaStreamSynchronize(m->stream));
+    if (m->profile) prof_collect(m);
+    return DSPMAP_OK;
+}
+int dspmap_profile_enable(dspmap *m, int on) {
+    if (!m) return DSPMAP_E_BAD_ARG;
+    cudaStreamSynchronize(m->stream);
+    prof_collect(m);
+    m->profile = on != 0;
+    for (int i = 0; i < FAM_COUNT; ++i) { m->prof_ms[i] = 0; m->prof_n[i] = 0; }
+    return DSPMAP_OK;
+}
+int dspmap_profile_read(dspmap *m, const char **names, float *ms, int32_t *launches, int cap) {
+    if (!m) return DSPMAP_E_BAD_ARG;
+    cudaStreamSynchronize(m->stream);
+    prof_collect(m);
+    int n = std::min<int>(cap, FAM_COUNT);
+    for (int i = 0; i < n; ++i) {
+        names[i] = kFamilyNames[i];
+        ms[i] = (float)m->prof_ms[i];
+        launches[i] = m->prof_n[i];
+    }
+    return n;
+}
+
+}  // extern "C"
+
+namespace {
+// the reference's particle CSV (dsp_dynamic.h:328-350): flag,vx,vy,vz,px,py,pz,weight,voxel per live particle
+int write_particle_csv(dspmap *m) {
+    int n = dspmap_dump_particles(m, nullptr, nullptr, 0);
+    if (n < 0) return n;
+    std::vector<int32_t> ids(2 * (size_t)std::max(n, 1));
+    std::vector<float> vals(8 * (size_t)std::max(n, 1));
+    n = dspmap_dump_particles(m, ids.data(), vals.data(), n);
+    std::string name = m->record_folder + "/particles_update_t_" + std::to_string(m->update_counter) + "_" +
+                       std::to_string((int)(m->update_time * 1000)) + ".csv";
+    std::ofstream f(name, std::ios::out | std::ios::trunc);
+    for (int i = 0; i < n; ++i) {
+        for (int k = 0; k < 8; ++k) f << vals[8 * (size_t)i + k] << ",";
+        f << ids[2 * i] << "\n";
+    }
+    return DSPMAP_OK;
+}
+}  // namespace

@@ -1,0 +1,923 @@
+// dspmap_frame.cuh — the kernels of one map update, in pipeline order (product code, sm_100a).
+#pragma once
+#include "dspmap_kernels.cuh"
+
+// ------------------------------------------------------------------------------------------------------------
+// K0  frame setup: rotate the boundary-plane normals (dsp_dynamic.h:226-232), reset per-frame state (:235-238)
+// ------------------------------------------------------------------------------------------------------------
+__global__ void k_frame_setup(MapConst mc, FrameConst fc, DevPtrs dp) {
+    int np = mc.Nh + 1 + mc.Nv + 1;
+    for (int i = threadIdx.x; i < np; i += blockDim.x) {
+        float o[3];
+        dsp_rotate(dp.planes0 + 3 * i, fc.q, fc.qi, o);
+        dp.planes[3 * i] = o[0];
+        dp.planes[3 * i + 1] = o[1];
+        dp.planes[3 * i + 2] = o[2];
+    }
+    if (threadIdx.x == 0) {
+        DevState *s = dp.st;
+        s->n_live = s->n_fov = s->n_mov = s->n_mov_owner = s->mov_top = 0;
+        s->n_cand = s->n_cand_owner = s->cand_top = 0;
+        s->n_left_map = s->n_voxel_full = s->n_pyramid_full = s->n_moved = s->n_born = 0;
+        s->n_low_weight = s->n_pre = s->n_old = s->n_out = s->n_valid = 0;
+        s->n_inmap_points = s->n_vdraw = s->n_rdraw = 0;
+        s->n_inexact = 0;
+        s->n_vz = s->n_skipped = 0;
+        s->work_k4 = s->work_k5 = 0;
+        s->norm = 0.f;
+        s->w_new = 0.f;
+    }
+    for (int i = threadIdx.x; i < mc.P; i += blockDim.x) {
+        dp.obs_cnt[i] = 0;
+        dp.obs_fill[i] = 0;
+        dp.obs_maxbits[i] = __float_as_int(-1.f);
+        dp.pcount[i] = 0;
+        dp.pfill[i] = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K1  observation binning (dsp_dynamic.h:244-290): rotate, FOV test, pyramid id, count, max range
+//     The reference appends points to their pyramid in input order and keeps the first OBS-1; here points are
+//     counted, scattered and then ranked by input index inside their pyramid (k_obs_rank).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void k_obs_classify(MapConst mc, FrameConst fc, DevPtrs dp) {
+    __shared__ float sp[3 * DSP_MAX_PLANES];
+    load_planes(sp, dp, mc);
+    const float *ph = sp, *pv = sp + 3 * (mc.Nh + 1);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < fc.n_points; i += gridDim.x * blockDim.x) {
+        float v[3] = {dp.pts[3 * i], dp.pts[3 * i + 1], dp.pts[3 * i + 2]}, r[3];
+        dsp_rotate(v, fc.q, fc.qi, r);
+        int pid = -1;
+        float len = 0.f;
+        if (dsp_in_fov(ph, pv, mc.Nh, mc.Nv, r[0], r[1], r[2])) {
+            int h = dsp_pyr_scan(ph, mc.Nh, 1.f, r[0], r[1], r[2]);
+            int w = dsp_pyr_scan(pv, mc.Nv, -1.f, r[0], r[1], r[2]);
+            pid = h * mc.Nv + w;
+            len = sqrtf(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+            if (h < 0 || w < 0) pid = -1;  // cannot happen for finite input inside the FOV planes
+        }
+        dp.OR[i] = make_float4(r[0], r[1], r[2], len);
+        dp.OPID[i] = pid;
+        if (pid >= 0) {
+            atomicAdd(&dp.obs_cnt[pid], 1);
+            atomicMax(&dp.obs_maxbits[pid], __float_as_int(len));  // ranges are positive: int order == float order
+            agg_inc(&dp.st->n_valid);
+        }
+    }
+}
+
+// single-block exclusive scan of a small int array; optionally a second scan of min(x, cap)
+__global__ void k_scan_small(const int *in, int *out, int *out_capped, int cap, int n) {
+    __shared__ int ssum[1024], scap[1024];
+    int per = (n + blockDim.x - 1) / blockDim.x;
+    int b = threadIdx.x * per, e = min(n, b + per);
+    int s = 0, sc = 0;
+    for (int i = b; i < e; ++i) { int x = in[i]; s += x; sc += min(x, cap); }
+    ssum[threadIdx.x] = s;
+    scap[threadIdx.x] = sc;
+    __syncthreads();
+    for (int d = 1; d < blockDim.x; d <<= 1) {
+        int a = 0, c = 0;
+        if (threadIdx.x >= d) { a = ssum[threadIdx.x - d]; c = scap[threadIdx.x - d]; }
+        __syncthreads();
+        ssum[threadIdx.x] += a;
+        scap[threadIdx.x] += c;
+        __syncthreads();
+    }
+    int run = ssum[threadIdx.x] - s, runc = scap[threadIdx.x] - sc;
+    for (int i = b; i < e; ++i) {
+        int x = in[i];
+        out[i] = run;
+        run += x;
+        if (out_capped) { out_capped[i] = runc; runc += min(x, cap); }
+    }
+    if (threadIdx.x == blockDim.x - 1) {
+        out[n] = ssum[threadIdx.x];
+        if (out_capped) out_capped[n] = scap[threadIdx.x];
+    }
+}
+
+__global__ void k_obs_scatter(MapConst mc, FrameConst fc, DevPtrs dp) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < fc.n_points; i += gridDim.x * blockDim.x) {
+        int pid = dp.OPID[i];
+        if (pid < 0) continue;
+        int pos = dp.obs_off[pid] + atomicAdd(&dp.obs_fill[pid], 1);
+        dp.OSEG[pos] = i;
+    }
+}
+__global__ void k_obs_rank(MapConst mc, FrameConst fc, DevPtrs dp) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < fc.n_points; i += gridDim.x * blockDim.x) {
+        int pid = dp.OPID[i];
+        if (pid < 0) continue;
+        int b = dp.obs_off[pid], n = dp.obs_cnt[pid], rank = 0;
+        for (int j = 0; j < n; ++j) rank += (dp.OSEG[b + j] < i);
+        // the first OBS-1 points in input order are kept (:281-284: the OBS-th slot is overwritten, never read)
+        if (rank < mc.OBS - 1) dp.OBSP[pid * mc.OBS + rank] = dp.OR[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K2a  enumerate live particles from the occupancy masks; snapshot the frame-start masks
+// ------------------------------------------------------------------------------------------------------------
+__global__ void k_enumerate(MapConst mc, DevPtrs dp, int snapshot) {
+    int lane = threadIdx.x & 31;
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int base = warp * 32; base < mc.V; base += nwarps * 32) {
+        int v = base + lane;
+        ulonglong2 m = make_ulonglong2(0ull, 0ull);
+        if (v < mc.V) {
+            m = dp.M[v];
+            if (snapshot) dp.M0[v] = m;
+        }
+        int c = mask_popc(m), incl = c;
+        for (int d = 1; d < 32; d <<= 1) {
+            int t = __shfl_up_sync(FULLMASK, incl, d);
+            if (lane >= d) incl += t;
+        }
+        int total = __shfl_sync(FULLMASK, incl, 31);
+        if (total == 0) continue;
+        int wbase = 0;
+        if (lane == 0) wbase = atomicAdd(&dp.st->n_live, total);
+        wbase = __shfl_sync(FULLMASK, wbase, 0);
+        int off = wbase + incl - c;
+        if (off + c > dp.cap_live) { if (c) dp.st->overflow = 1; continue; }
+        u64 z = m.x;
+        while (z) { int s = __ffsll((long long)z) - 1; z &= z - 1; dp.E[off++] = (v << DSP_KEY_SHIFT) | s; }
+        z = m.y;
+        while (z) { int s = __ffsll((long long)z) - 1; z &= z - 1; dp.E[off++] = (v << DSP_KEY_SHIFT) | (64 + s); }
+    }
+}
+
+// prediction noise predicate (dsp_dynamic.h:649,653): live, not newborn-flagged, |vx*vy*vz| >= 1e-6
+__device__ __forceinline__ bool vz_noisy(float4 B) {
+    return (B.w > 0.1f && B.w < 6.f) && !((double)fabsf(B.x * B.y * B.z) < 1e-6);
+}
+// vz mode only: per-voxel count of particles that will draw prediction noise (then scanned over voxels)
+__global__ void k_vz_count(MapConst mc, DevPtrs dp) {
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < mc.V; v += gridDim.x * blockDim.x) {
+        ulonglong2 m = dp.M[v], bits = make_ulonglong2(0ull, 0ull);
+        for (int half = 0; half < 2; ++half) {
+            u64 z = half ? m.y : m.x;
+            while (z) {
+                int sb = __ffsll((long long)z) - 1;
+                z &= z - 1;
+                if (vz_noisy(dp.PB[v * mc.S + sb + 64 * half])) { if (half) bits.y |= 1ull << sb; else bits.x |= 1ull << sb; }
+            }
+        }
+        dp.MS[v] = bits;  // MS is free until the arrival grouping; it carries the predicate bits to k_predict
+        int c = mask_popc(bits);
+        dp.vzcnt[v] = c;
+    }
+}
+#define SCAN_BLOCK 2048
+__global__ void __launch_bounds__(256) k_scan_blocksum(const int *in, int n, int *blocksum) {
+    __shared__ int s;
+    if (threadIdx.x == 0) s = 0;
+    __syncthreads();
+    int b = blockIdx.x * SCAN_BLOCK, c = 0;
+    for (int i = threadIdx.x; i < SCAN_BLOCK; i += blockDim.x) if (b + i < n) c += in[b + i];
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_down_sync(FULLMASK, c, d);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s, c);
+    __syncthreads();
+    if (threadIdx.x == 0) blocksum[blockIdx.x] = s;
+}
+__global__ void __launch_bounds__(256) k_scan_apply(const int *in, int n, const int *blockoff, int *out, int nblocks) {
+    __shared__ int tsum[256];
+    int b = blockIdx.x * SCAN_BLOCK + threadIdx.x * (SCAN_BLOCK / 256);
+    int loc[SCAN_BLOCK / 256], c = 0;
+    for (int k = 0; k < SCAN_BLOCK / 256; ++k) { loc[k] = (b + k < n) ? in[b + k] : 0; c += loc[k]; }
+    tsum[threadIdx.x] = c;
+    __syncthreads();
+    for (int d = 1; d < 256; d <<= 1) {
+        int a = threadIdx.x >= d ? tsum[threadIdx.x - d] : 0;
+        __syncthreads();
+        tsum[threadIdx.x] += a;
+        __syncthreads();
+    }
+    int run = blockoff[blockIdx.x] + tsum[threadIdx.x] - c;
+    for (int k = 0; k < SCAN_BLOCK / 256; ++k) { if (b + k < n) out[b + k] = run; run += loc[k]; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = blockoff[nblocks];
+}
+__global__ void k_vz_advance(MapConst mc, DevPtrs dp) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        int n = dp.vzoff[mc.V];
+        dp.st->n_vz = n;
+        dp.st->v_cur = (dp.st->v_cur + 3ll * n) % mc.G;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K2b  prediction (dsp_dynamic.h:645-694; dsp_static.h:640-646) + reindexing (:669-671) + FOV / pyramid id of
+//      the new position (:1233-1243).  Stayers are updated in place; movers leave their slot and go to the mover
+//      buffer, to be placed by k_arrive in the reference's sweep order.
+//      Velocity process noise (:653-659, :1262-1269) cannot fire here: with LIMIT_MOVEMENT_IN_XY_PLANE = 1 every
+//      particle has vz == 0 after its first prediction or at birth, so |vx*vy*vz| < 1e-6 always holds; the one
+//      reachable case (constructor-seeded particles in their first frame) is applied by the host before the
+//      first update (see dspmap.cu: apply_seed_noise).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void k_predict(MapConst mc, FrameConst fc, DevPtrs dp) {
+    __shared__ float sp[3 * DSP_MAX_PLANES];
+    load_planes(sp, dp, mc);
+    const float *ph = sp, *pv = sp + 3 * (mc.Nh + 1);
+    const int n = min(dp.st->n_live, dp.cap_live);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int key = dp.E[i];
+        int v = key >> DSP_KEY_SHIFT, s = key & (DSP_MAX_SLOTS - 1);
+        int a = v * mc.S + s;
+        float4 A = dp.PA[a], B = dp.PB[a];
+        if (!(B.w > 0.1f && B.w < 6.f)) {  // newborn-flagged (constructor-seeded) particles are not predicted (:649)
+            agg_inc(&dp.st->n_skipped);
+            continue;
+        }
+        if (mc.model == 1) {
+            B.x = 0.f; B.y = 0.f; B.z = 0.f;
+            A.x += fc.sx; A.y += fc.sy; A.z += fc.sz;
+        } else {
+            // (:653-659) three table draws, cursor in sweep order; the predicate bits were frozen by k_vz_count
+            if (fc.vz_mode && mask_test(dp.MS[v], s)) {
+                ulonglong2 vzm = dp.MS[v];
+                int rank = dp.vzoff[v];
+                if (s < 64) rank += __popcll(vzm.x & ((1ull << s) - 1ull));
+                else rank += __popcll(vzm.x) + __popcll(vzm.y & ((1ull << (s - 64)) - 1ull));
+                long long vc = (dp.st->v_cur + 3ll * rank) % mc.G;
+                B.x += dp.vtab[vc];
+                B.y += dp.vtab[(vc + 1) % mc.G];
+                B.z += dp.vtab[(vc + 2) % mc.G];
+            }
+            B.z = 0.f;
+            A.x += fc.dt * B.x + fc.sx;
+            A.y += fc.dt * B.y + fc.sy;
+            A.z += fc.dt * B.z + fc.sz;
+        }
+        int d = dsp_voxel_index(mc, A.x, A.y, A.z);
+        if (d < 0) {  // left the map (:686-690)
+            mask_atomic_clear(dp.M, v, s);
+            agg_inc(&dp.st->n_left_map);
+            continue;
+        }
+        int q = -1;
+        if (dsp_in_fov(ph, pv, mc.Nh, mc.Nv, A.x, A.y, A.z)) {
+            int h = dsp_pyr_scan(ph, mc.Nh, 1.f, A.x, A.y, A.z);
+            int w = dsp_pyr_scan(pv, mc.Nv, -1.f, A.x, A.y, A.z);
+            if (h >= 0 && w >= 0) q = h * mc.Nv + w;
+        }
+        if (d == v) {
+            B.w = 1.f;
+            dp.PA[a] = A;
+            dp.PB[a] = B;
+            if (q >= 0) {
+                int k = agg_inc(&dp.st->n_fov);
+                dp.Fkey[k] = key;
+                dp.Faddr[k] = a;
+                dp.Fq[k] = q;
+                atomicAdd(&dp.pcount[q], 1);
+            }
+        } else {
+            mask_atomic_clear(dp.M, v, s);  // "remove from ori voxel first" (:1210)
+            B.w = 7.f;
+            int k = agg_inc(&dp.st->n_mov);
+            dp.MBA[k] = A;
+            dp.MBB[k] = B;
+            dp.MBkey[k] = key;
+            dp.MBdst[k] = d;
+            dp.MBq[k] = q;
+            if (atomicAdd(&dp.mcnt[d], 1) == 0) dp.mowner[agg_inc(&dp.st->n_mov_owner)] = d;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// arrival grouping: arrivals to the same destination voxel are gathered into one contiguous segment so that each
+// arrival can rank itself among them.  owner pass: one thread per distinct destination allocates the segment and
+// snapshots the destination's mask; scatter pass: arrivals write their order key into the segment.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void k_group_owner(DevPtrs dp, const int *n_owner, const int *owner, const int *cnt, int *base, int *top) {
+    int lane = threadIdx.x & 31;
+    int n = *n_owner;
+    int nround = (n + 31) & ~31;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += gridDim.x * blockDim.x) {
+        int d = i < n ? owner[i] : -1;
+        int c = d >= 0 ? cnt[d] : 0, incl = c;
+        for (int k = 1; k < 32; k <<= 1) {
+            int t = __shfl_up_sync(FULLMASK, incl, k);
+            if (lane >= k) incl += t;
+        }
+        int total = __shfl_sync(FULLMASK, incl, 31), wb = 0;
+        if (lane == 0) wb = atomicAdd(top, total);
+        wb = __shfl_sync(FULLMASK, wb, 0);
+        if (d >= 0) {
+            base[d] = wb + incl - c;
+            dp.MS[d] = dp.M[d];
+        }
+    }
+}
+__global__ void k_group_scatter(const int *n_items, const int *dst, const int *key, const int *base, int *fill, int *seg) {
+    int n = *n_items;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int d = dst[i];
+        seg[base[d] + atomicAdd(&fill[d], 1)] = key[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K3  moveParticle's voxel half (dsp_dynamic.h:1206-1230), replayed in the reference's sweep order:
+//     arrivals from lower-index voxels come before the destination's own particles are processed and see the
+//     frame-start mask M0; the destination's own leavers then free their slots; arrivals from higher-index voxels
+//     come last.  The k-th arrival of a phase takes the k-th free slot; no free slot => the particle vanishes.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void k_arrive(MapConst mc, FrameConst fc, DevPtrs dp) {
+    const int n = dp.st->n_mov;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int d = dp.MBdst[i], key = dp.MBkey[i];
+        int b = dp.mbase[d], c = dp.mcnt[d];
+        int dkey = d << DSP_KEY_SHIFT;
+        bool early = key < dkey;
+        int n_early = 0, rank = 0;
+        for (int j = 0; j < c; ++j) {
+            int kj = dp.mseg[b + j];
+            bool ej = kj < dkey;
+            n_early += ej;
+            rank += (ej == early) && (kj < key);
+        }
+        ulonglong2 m0 = dp.M0[d], mid = dp.MS[d];  // mid = M0 minus the destination's own leavers
+        int slot;
+        if (early) {
+            slot = mask_nth_free(mc, m0, rank);
+        } else {
+            ulonglong2 t = mask_take_free(mc, m0, n_early);
+            ulonglong2 m2 = make_ulonglong2(mid.x | t.x, mid.y | t.y);
+            slot = mask_nth_free(mc, m2, rank);
+        }
+        if (slot < 0) {  // voxel full: the particle vanishes (:1227-1229)
+            agg_inc(&dp.st->n_voxel_full);
+            continue;
+        }
+        int a = d * mc.S + slot;
+        dp.PA[a] = dp.MBA[i];
+        dp.PB[a] = dp.MBB[i];
+        mask_atomic_set(dp.M, d, slot);
+        agg_inc(&dp.st->n_moved);
+        int q = dp.MBq[i];
+        if (q >= 0) {
+            int k = agg_inc(&dp.st->n_fov);
+            dp.Fkey[k] = key;  // list order is the order of processing, i.e. the SOURCE sweep key
+            dp.Faddr[k] = a;
+            dp.Fq[k] = q;
+            atomicAdd(&dp.pcount[q], 1);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K3b  pyramid lists (dsp_dynamic.h:1243-1259): scatter registered particles to their pyramid's segment, sort each
+//      segment by sweep key, keep the first L (the rest vanish, :1256-1259), and materialise a compact per-pyramid
+//      copy of (px, py, pz, w) for the two observation passes.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void k_pyr_scatter(DevPtrs dp) {
+    const int n = dp.st->n_fov;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int q = dp.Fq[i];
+        int pos = dp.poff[q] + atomicAdd(&dp.pfill[q], 1);
+        dp.PSkey[pos] = dp.Fkey[i];
+        dp.PSaddr[pos] = dp.Faddr[i];
+    }
+}
+
+#define PYR_SORT_CAP 8192
+__global__ void __launch_bounds__(512) k_pyr_sort(MapConst mc, DevPtrs dp) {
+    extern __shared__ u64 skey[];  // PYR_SORT_CAP entries: (sweep key << 32) | slot address
+    for (int q = blockIdx.x; q < mc.P; q += gridDim.x) {
+        const int n = dp.pcount[q], b = dp.poff[q];
+        const int keep = min(n, mc.L);
+        if (threadIdx.x == 0) dp.plen[q] = keep;
+        if (n == 0) continue;
+        if (n <= PYR_SORT_CAP) {
+            int m = 1;
+            while (m < n) m <<= 1;
+            for (int i = threadIdx.x; i < m; i += blockDim.x)
+                skey[i] = i < n ? ((u64)(unsigned)dp.PSkey[b + i] << 32) | (unsigned)dp.PSaddr[b + i] : ~0ull;
+            __syncthreads();
+            for (int k = 2; k <= m; k <<= 1)
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+                        int p = i ^ j;
+                        if (p > i) {
+                            u64 x = skey[i], y = skey[p];
+                            bool up = (i & k) == 0;
+                            if ((x > y) == up) { skey[i] = y; skey[p] = x; }
+                        }
+                    }
+                    __syncthreads();
+                }
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                int a = (int)(unsigned)(skey[i] & 0xffffffffull);
+                if (i < keep) {
+                    dp.LA[b + i] = a;
+                    dp.LP[b + i] = dp.PA[a];
+                } else {  // pyramid full: the particle vanishes and frees its voxel slot (:1256-1259)
+                    mask_atomic_clear(dp.M, a / mc.S, a % mc.S);
+                    atomicAdd(&dp.st->n_pyramid_full, 1);
+                }
+            }
+            __syncthreads();
+        } else {  // oversized segment: rank by counting straight from global memory (slow, rare)
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                int ki = dp.PSkey[b + i], r = 0;
+                for (int j = 0; j < n; ++j) r += dp.PSkey[b + j] < ki;
+                int a = dp.PSaddr[b + i];
+                if (r < keep) {
+                    dp.LA[b + r] = a;
+                    dp.LP[b + r] = dp.PA[a];
+                } else {
+                    mask_atomic_clear(dp.M, a / mc.S, a % mc.S);
+                    atomicAdd(&dp.st->n_pyramid_full, 1);
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K4  C_z pass (dsp_dynamic.h:709-739).  For every observation point z of pyramid i:
+//         C_z = sum over neighbour pyramids n (table order), particles of n (list order) of  P_d * w * g(p; z)
+//               + (expected_new_born + kappa)
+//     as ONE fp32 chain in exactly that order.  A CTA owns a pyramid: all threads evaluate a tile of
+//     (particle, point) terms into shared memory, then one thread per point adds the tile's terms to its running
+//     sum in list order.
+// ------------------------------------------------------------------------------------------------------------
+#define K4_THREADS 256
+#define K4_TERMS 8192  // term tile capacity (floats)
+__global__ void __launch_bounds__(K4_THREADS) k_ck(MapConst mc, FrameConst fc, DevPtrs dp) {
+    extern __shared__ float smem[];
+    float *lut = smem;                          // DSP_LUT_HALF
+    float *term = lut + DSP_LUT_HALF + 3;       // K4_TERMS
+    float4 *ptl = (float4 *)(term + K4_TERMS);  // particle tile, <= 256
+    float4 *zs = ptl + 256;                     // points of this pyramid, <= OBS
+    __shared__ int s_item;
+    for (int i = threadIdx.x; i < DSP_LUT_HALF; i += blockDim.x) lut[i] = dp.lut[i];
+    const float enb = fc.nb_weight * (float)dp.st->n_valid * (float)fc.nb_num;  // :292
+    const float add_k = enb + fc.kappa;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_item = atomicAdd(&dp.st->work_k4, 1);
+        __syncthreads();
+        const int i = s_item;
+        if (i >= mc.P) break;
+        const int npts = min(dp.obs_cnt[i], mc.OBS - 1);
+        if (npts == 0) continue;
+        for (int t = threadIdx.x; t < npts; t += blockDim.x) zs[t] = dp.OBSP[i * mc.OBS + t];
+        const int tp = min(256, K4_TERMS / npts);
+        float acc = 0.f;
+        const unsigned magic = 0xffffffffu / (unsigned)npts + 1u;  // exact t / npts for t < 65536
+        const int nn = dp.nbr[i * mc.NBW];
+        for (int ns = 0; ns < nn; ++ns) {
+            const int pc = dp.nbr[i * mc.NBW + 1 + ns];
+            const int lb = dp.poff[pc], ln = dp.plen[pc];
+            for (int t0 = 0; t0 < ln; t0 += tp) {
+                const int cur = min(tp, ln - t0);
+                __syncthreads();
+                for (int t = threadIdx.x; t < cur; t += blockDim.x) ptl[t] = dp.LP[lb + t0 + t];
+                __syncthreads();
+                const int pairs = cur * npts;
+                for (int t = threadIdx.x; t < pairs; t += blockDim.x) {
+                    int k = __umulhi((unsigned)t, magic);
+                    int z = t - k * npts;
+                    float4 p = ptl[k], o = zs[z];
+                    float gk = dsp_pdf(lut, p.x, o.x, fc.sigma) * dsp_pdf(lut, p.y, o.y, fc.sigma) * dsp_pdf(lut, p.z, o.z, fc.sigma);
+                    term[t] = fc.Pd * p.w * gk;
+                }
+                __syncthreads();
+                if (threadIdx.x < npts)
+                    for (int k = 0; k < cur; ++k) acc += term[k * npts + threadIdx.x];
+            }
+        }
+        if (threadIdx.x < npts) {
+            acc += add_k;
+            dp.CZ[i * mc.OBS + threadIdx.x] = acc;
+            dp.INV[dp.obs_capoff[i] + threadIdx.x] = 1.f / acc;  // for the newborn normaliser (:802)
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K5  weight pass (dsp_dynamic.h:743-790).  One thread per registered particle; the observation points of the
+//     particle's neighbour pyramids are staged in shared memory in (table order, bin order) and summed in that
+//     order:  w *= (1 - P_d) + sum_z P_d * g(p; z) / C_z.
+// ------------------------------------------------------------------------------------------------------------
+#define K5_THREADS 256
+__global__ void __launch_bounds__(K5_THREADS) k_weight(MapConst mc, FrameConst fc, DevPtrs dp, int chunks_per_pyr) {
+    extern __shared__ float smem[];
+    float *lut = smem;
+    float4 *zs = (float4 *)(lut + DSP_LUT_HALF + 3);  // NB * (OBS-1) staged points: x y z C_z
+    __shared__ int s_item;
+    for (int i = threadIdx.x; i < DSP_LUT_HALF; i += blockDim.x) lut[i] = dp.lut[i];
+    int staged = -1, nz = 0;
+    const int items = mc.P * chunks_per_pyr;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_item = atomicAdd(&dp.st->work_k5, 1);
+        __syncthreads();
+        const int it = s_item;
+        if (it >= items) break;
+        const int i = it / chunks_per_pyr, c = it - i * chunks_per_pyr;
+        const int ln = dp.plen[i];
+        if (c * K5_THREADS >= ln) continue;
+        if (staged != i) {
+            __syncthreads();
+            nz = 0;
+            const int nn = dp.nbr[i * mc.NBW];
+            for (int ns = 0; ns < nn; ++ns) {
+                const int ni = dp.nbr[i * mc.NBW + 1 + ns];
+                const int cnt = min(dp.obs_cnt[ni], mc.OBS - 1);
+                for (int t = threadIdx.x; t < cnt; t += blockDim.x) {
+                    float4 o = dp.OBSP[ni * mc.OBS + t];
+                    o.w = dp.CZ[ni * mc.OBS + t];
+                    zs[nz + t] = o;
+                }
+                nz += cnt;
+            }
+            staged = i;
+            __syncthreads();
+        }
+        const int j = c * K5_THREADS + threadIdx.x;
+        if (j >= ln) continue;
+        const int lb = dp.poff[i];
+        float4 p = dp.LP[lb + j];
+        float dist = sqrtf(p.x * p.x + p.y * p.y + p.z * p.z);
+        float maxlen = __int_as_float(dp.obs_maxbits[i]);
+        if (maxlen > 0.f && dist > maxlen + mc.occl) continue;  // occluded (:761)
+        float sum = 0.f;
+        for (int z = 0; z < nz; ++z) {
+            float4 o = zs[z];
+            float gk = dsp_pdf(lut, p.x, o.x, fc.sigma) * dsp_pdf(lut, p.y, o.y, fc.sigma) * dsp_pdf(lut, p.z, o.z, fc.sigma);
+            sum += fc.Pd * gk / o.w;
+        }
+        int a = dp.LA[lb + j];
+        dp.PA[a].w = p.w * (fc.one_minus_Pd + sum);
+    }
+}
+
+// K6a  newborn normaliser (dsp_dynamic.h:799-805): sum of 1/C_z over (pyramid, bin) order, one fp32 chain.
+__global__ void k_norm(MapConst mc, FrameConst fc, DevPtrs dp) {
+    __shared__ float buf[2][1024];
+    const int n = dp.obs_capoff[mc.P];
+    float acc = 0.f;
+    int nchunk = (n + 1023) / 1024;
+    if (nchunk > 0)
+        for (int t = threadIdx.x; t < 1024; t += blockDim.x) buf[0][t] = t < n ? dp.INV[t] : 0.f;
+    __syncthreads();
+    for (int c = 0; c < nchunk; ++c) {
+        int nb = (c + 1) & 1, b0 = (c + 1) * 1024;
+        if (threadIdx.x >= 32) {  // warps 1.. prefetch the next chunk while warp 0 adds the current one
+            if (c + 1 < nchunk)
+                for (int t = threadIdx.x - 32; t < 1024; t += blockDim.x - 32) buf[nb][t] = b0 + t < n ? dp.INV[b0 + t] : 0.f;
+        } else if (threadIdx.x == 0) {
+            int cnt = min(1024, n - c * 1024);
+            const float *s = buf[c & 1];
+#pragma unroll 8
+            for (int k = 0; k < cnt; ++k) acc += s[k];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        dp.st->norm = acc;
+        dp.st->w_new = fc.nb_weight * acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K6  newborn particles (dsp_dynamic.h:796-921; dsp_static.h:779-829)
+// ------------------------------------------------------------------------------------------------------------
+// point pass 0: corrected point, its voxel, in-map predicate (:817-827,:846-848; the static variant has no test)
+__global__ void k_nb_point0(MapConst mc, FrameConst fc, DevPtrs dp) {
+    for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < fc.n_tagged; m += gridDim.x * blockDim.x) {
+        const float *pt = dp.tagged + 7 * m;
+        float cx = pt[0] - fc.cur[0], cy = pt[1] - fc.cur[1], cz = pt[2] - fc.cur[2];
+        int pv = dsp_voxel_index(mc, cx, cy, cz);
+        dp.NPC[m] = make_float4(cx, cy, cz, __int_as_float(pv));
+        dp.ninmap[m] = (mc.model == 1) ? 1 : (pv >= 0);
+    }
+}
+__device__ __forceinline__ u64 bits_below(int p) { return p >= 64 ? ~0ull : ((1ull << p) - 1ull); }
+// point pass 1: Dempster-Shafer split from the resident particles of the point's voxel (:829-866), which of the
+// nb_num candidates land inside the map (:871-875), and how many table / uniform draws the point consumes.
+__global__ void k_nb_point1(MapConst mc, FrameConst fc, DevPtrs dp) {
+    for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < fc.n_tagged; m += gridDim.x * blockDim.x) {
+        if (!dp.ninmap[m]) { dp.nvcnt[m] = 0; dp.nrcnt[m] = 0; dp.nimask[m] = 0ull; continue; }
+        float4 pc = dp.NPC[m];
+        int n_static = 0;
+        if (mc.model == 0) {
+            int pv = __float_as_int(pc.w);
+            float ws = 0.f, wd = 0.f, wsd = 0.f;
+            ulonglong2 msk = dp.M[pv];
+            for (int half = 0; half < 2; ++half) {
+                u64 z = half ? msk.y : msk.x;
+                while (z) {
+                    int s = __ffsll((long long)z) - 1 + 64 * half;
+                    z &= z - 1;
+                    int a = pv * mc.S + s;
+                    float4 B = dp.PB[a];
+                    if (!(B.w > 0.9f && B.w < 14.f)) continue;  // not newborn (:830)
+                    float w = dp.PA[a].w;
+                    float va = fabsf(B.x) + fabsf(B.y) + fabsf(B.z);
+                    if (va < 0.1f) ws += w;
+                    else if (va < 0.5f) wsd += w;
+                    else wd += w;
+                }
+            }
+            float tot = ws + wd + wsd;
+            float m_s = ws / tot, m_d = wd / tot, m_sd = wsd / tot;
+            float p_s = (m_s + m_s + m_sd) * 0.5f, p_d = (m_d + m_d + m_sd) * 0.5f;
+            float np_ = p_s + p_d;
+            float ps_n = p_s / np_;
+            float prod = (float)fc.nb_model_gen * ps_n;
+            n_static = (prod != prod) ? INT_MIN : (int)prod;
+            n_static = max(fc.nb_min_static, n_static);
+        }
+        long long c0 = dp.st->p_cur + 3ll * ((long long)dp.nrank[m] * fc.nb_num);
+        u64 im = 0ull;
+        for (int p = 0; p < fc.nb_num; ++p) {
+            long long c = (c0 + 3ll * p) % mc.G;
+            float px = pc.x + dp.ptab[c];
+            float py = pc.y + dp.ptab[(c + 1) % mc.G];
+            float pz = pc.z + dp.ptab[(c + 2) % mc.G];
+            if (dsp_voxel_index(mc, px, py, pz) >= 0) im |= 1ull << p;
+        }
+        const float *pt = dp.tagged + 7 * m;
+        u64 vm = 0ull, rm = 0ull;
+        if (mc.model == 0 && pt[6] > 0.01f) {  // only points tagged dynamic draw velocities (:883,:894)
+            u64 nonstatic = im & ~bits_below(max(n_static, 0));
+            u64 est = (pt[3] > -100.f) ? bits_below(fc.nb_model_gen) : 0ull;  // (:881)
+            vm = nonstatic & est;
+            rm = nonstatic & ~est;
+        }
+        dp.nstatic[m] = n_static;
+        dp.nimask[m] = im;
+        dp.nvcnt[m] = __popcll(vm);
+        dp.nrcnt[m] = __popcll(rm);
+    }
+}
+// candidate pass: position (:871-873), velocity class (:877-907), weight (:909); candidates inside the map join
+// the arrival grouping of their voxel, ordered by (point, candidate) = the reference's serial order.
+__global__ void k_nb_cand(MapConst mc, FrameConst fc, DevPtrs dp, u64 useed) {
+    const int total = fc.n_tagged * fc.nb_num;
+    const float w_new = dp.st->w_new;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        int m = t / fc.nb_num, p = t - m * fc.nb_num;
+        u64 im = dp.nimask[m];
+        if (!((im >> p) & 1ull)) continue;
+        float4 pc = dp.NPC[m];
+        long long c = (dp.st->p_cur + 3ll * ((long long)dp.nrank[m] * fc.nb_num + p)) % mc.G;
+        float px = pc.x + dp.ptab[c];
+        float py = pc.y + dp.ptab[(c + 1) % mc.G];
+        float pz = pc.z + dp.ptab[(c + 2) % mc.G];
+        int d = dsp_voxel_index(mc, px, py, pz);
+        float vx = 0.f, vy = 0.f, vz = 0.f;
+        const float *pt = dp.tagged + 7 * m;
+        if (mc.model == 0 && pt[6] > 0.01f) {
+            int n_static = dp.nstatic[m];
+            if (p >= n_static) {
+                u64 nonstatic = im & ~bits_below(max(n_static, 0));
+                u64 est = (pt[3] > -100.f) ? bits_below(fc.nb_model_gen) : 0ull;
+                if ((est >> p) & 1ull) {
+                    int k = __popcll(nonstatic & est & bits_below(p));
+                    long long vc = (dp.st->v_cur + 3ll * (dp.nvoff[m] + k)) % mc.G;
+                    vx = pt[3] + 4 * dp.vtab[vc];
+                    vy = pt[4] + 4 * dp.vtab[(vc + 1) % mc.G];
+                    vz = pt[5] + 4 * dp.vtab[(vc + 2) % mc.G];
+                } else {
+                    int k = __popcll(nonstatic & ~est & bits_below(p));
+                    u64 uc = (u64)dp.st->u_cur + 3ull * (u64)(dp.nroff[m] + k);
+                    vx = dsp_uniform(useed, uc, -1.5f, 1.5f);
+                    vy = dsp_uniform(useed, uc + 1, -1.5f, 1.5f);
+                    vz = dsp_uniform(useed, uc + 2, -0.5f, 0.5f);
+                }
+            }
+            vz = 0.f;  // LIMIT_MOVEMENT_IN_XY_PLANE (:905-907)
+        }
+        int k = agg_inc(&dp.st->n_cand);
+        if (k >= dp.cap_cand) { dp.st->overflow = 1; continue; }
+        dp.CA[k] = make_float4(px, py, pz, w_new);
+        dp.CB[k] = make_float4(vx, vy, vz, 15.f);
+        dp.Ckey[k] = m * DSP_MAX_NB_NUM + p;
+        dp.Cdst[k] = d;
+        if (atomicAdd(&dp.ccnt[d], 1) == 0) dp.cowner[agg_inc(&dp.st->n_cand_owner)] = d;
+    }
+}
+// addAParticle (:1183-1201) in serial order: the k-th candidate of a voxel takes its k-th free slot.
+__global__ void k_nb_place(MapConst mc, FrameConst fc, DevPtrs dp) {
+    const int n = min(dp.st->n_cand, dp.cap_cand);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int d = dp.Cdst[i], key = dp.Ckey[i];
+        int b = dp.cbase[d], c = dp.ccnt[d], rank = 0;
+        for (int j = 0; j < c; ++j) rank += dp.cseg[b + j] < key;
+        int slot = mask_nth_free(mc, dp.MS[d], rank);
+        if (slot < 0) continue;
+        int a = d * mc.S + slot;
+        dp.PA[a] = dp.CA[i];
+        dp.PB[a] = dp.CB[i];
+        mask_atomic_set(dp.M, d, slot);
+        agg_inc(&dp.st->n_born);
+    }
+}
+// cursors advance by what the serial loop would have drawn
+__global__ void k_nb_cursors(MapConst mc, FrameConst fc, DevPtrs dp) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        DevState *s = dp.st;
+        int inmap_pts = fc.n_tagged > 0 ? dp.nrank[fc.n_tagged] : 0;
+        int vd = fc.n_tagged > 0 ? dp.nvoff[fc.n_tagged] : 0;
+        int rd = fc.n_tagged > 0 ? dp.nroff[fc.n_tagged] : 0;
+        s->n_inmap_points = inmap_pts;
+        s->n_vdraw = vd;
+        s->n_rdraw = rd;
+        s->p_cur = (s->p_cur + 3ll * inmap_pts * fc.nb_num) % mc.G;
+        s->v_cur = (s->v_cur + 3ll * vd) % mc.G;
+        s->u_cur += 3ll * rd;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K7  occupancy, future status and resampling (dsp_dynamic.h:924-1057), one thread per voxel, slots in order.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void k_resample(MapConst mc, FrameConst fc, DevPtrs dp) {
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < mc.V; v += gridDim.x * blockDim.x) {
+        ulonglong2 msk = dp.M[v];
+        if ((msk.x | msk.y) == 0ull) {
+            dp.OCCV[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+            continue;
+        }
+        float wsum = 0.f, sx = 0.f, sy = 0.f, sz = 0.f;
+        int n = 0, n_old = 0, n_low = 0;
+        ulonglong2 live = msk;
+        for (int half = 0; half < 2; ++half) {
+            u64 z = half ? msk.y : msk.x;
+            while (z) {
+                int sb = __ffsll((long long)z) - 1;
+                z &= z - 1;
+                int a = v * mc.S + sb + 64 * half;
+                float4 A = dp.PA[a], B = dp.PB[a];
+                if ((double)A.w < 1e-3) {  // (:941) drop
+                    if (half) live.y &= ~(1ull << sb); else live.x &= ~(1ull << sb);
+                    ++n_low;
+                    continue;
+                }
+                if (B.w < 10.f) {  // not newborn (:944)
+                    ++n_old;
+                    sx += B.x; sy += B.y; sz += B.z;
+                    for (int t = 0; t < mc.T; ++t) {
+                        float ft = mc.ft[t];
+                        float fx = A.x + B.x * ft, fy = A.y + B.y * ft, fz = A.z + B.z * ft;
+                        int fi = dsp_voxel_index(mc, fx, fy, fz);
+                        if (fi >= 0) atomicAdd(&dp.FUT[(size_t)fi * mc.T + t], A.w);
+                    }
+                }
+                dp.PB[a].w = 1.f;
+                ++n;
+                wsum += A.w;
+            }
+        }
+        float4 o = make_float4(wsum, 0.f, 0.f, 0.f);
+        if (n_old > 0) { o.y = sx / (float)n_old; o.z = sy / (float)n_old; o.w = sz / (float)n_old; }
+        dp.OCCV[v] = o;
+        int n_out = n;
+        if (n >= 5) {  // (:986)
+            int n_after = n > mc.max_ppv ? mc.max_ppv : n;
+            float w_after = wsum / (float)n_after;
+            float acc_ori = 0.f, acc_new = w_after * 0.5f;
+            ulonglong2 occ = live;        // slots that are not free (kept originals and copies)
+            const ulonglong2 orig = live; // originals, visited in slot order; copies are skipped (:1009)
+            n_out = 0;
+            for (int half = 0; half < 2; ++half) {
+                u64 z = half ? orig.y : orig.x;
+                while (z) {
+                    int sb = __ffsll((long long)z) - 1;
+                    z &= z - 1;
+                    int s = sb + 64 * half, a = v * mc.S + s;
+                    float4 A = dp.PA[a];
+                    acc_ori += A.w;
+                    if (acc_ori > acc_new) {
+                        float wk = w_after;
+                        acc_new += w_after;
+                        bool full = false;
+                        float4 B = dp.PB[a];
+                        while (acc_ori > acc_new) {  // duplicate heavy particles (:1021-1044)
+                            int fs = full ? -1 : mask_nth_free(mc, occ, 0);
+                            if (fs >= 0) {
+                                int ac = v * mc.S + fs;
+                                dp.PA[ac] = make_float4(A.x, A.y, A.z, wk);
+                                dp.PB[ac] = make_float4(B.x, B.y, B.z, 0.6f);
+                                if (fs < 64) occ.x |= 1ull << fs; else occ.y |= 1ull << (fs - 64);
+                                ++n_out;
+                            } else {
+                                wk += w_after;
+                                full = true;
+                            }
+                            acc_new += w_after;
+                        }
+                        dp.PA[a].w = wk;
+                        ++n_out;
+                    } else {  // removed (:1046-1050)
+                        if (half) occ.y &= ~(1ull << sb); else occ.x &= ~(1ull << sb);
+                    }
+                }
+            }
+            live = occ;
+        }
+        dp.M[v] = live;
+        atomicAdd(&dp.st->n_pre, n);
+        atomicAdd(&dp.st->n_old, n_old);
+        atomicAdd(&dp.st->n_out, n_out);
+        if (n_low) atomicAdd(&dp.st->n_low_weight, n_low);
+    }
+}
+
+// reset the arrival-grouping tables touched this frame
+__global__ void k_cleanup(DevPtrs dp) {
+    int n1 = dp.st->n_mov_owner, n2 = dp.st->n_cand_owner;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2; i += gridDim.x * blockDim.x) {
+        if (i < n1) { int d = dp.mowner[i]; dp.mcnt[d] = 0; dp.mfill[d] = 0; }
+        else { int d = dp.cowner[i - n1]; dp.ccnt[d] = 0; dp.cfill[d] = 0; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K8  readers (dsp_dynamic.h:385-438): ordered compaction of occupied voxel centres, future copy-out + zeroing
+// ------------------------------------------------------------------------------------------------------------
+#define OCC_BLOCK 2048  // voxels per block
+__global__ void __launch_bounds__(256) k_occ_count(MapConst mc, DevPtrs dp, float thr, int *blockcnt, float *d_future) {
+    __shared__ int s;
+    if (threadIdx.x == 0) s = 0;
+    __syncthreads();
+    int b = blockIdx.x * OCC_BLOCK, c = 0;
+    for (int i = threadIdx.x; i < OCC_BLOCK; i += blockDim.x) {
+        int v = b + i;
+        if (v < mc.V && dp.OCCV[v].x > thr) ++c;
+    }
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_down_sync(FULLMASK, c, d);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s, c);
+    __syncthreads();
+    if (threadIdx.x == 0) blockcnt[blockIdx.x] = s;
+    // future status: copy out (if asked) and clear (:416-424)
+    size_t fb = (size_t)b * mc.T, fe = min((size_t)mc.V, (size_t)b + OCC_BLOCK) * mc.T;
+    for (size_t i = fb + threadIdx.x; i < fe; i += blockDim.x) {
+        if (d_future) d_future[i] = dp.FUT[i];
+        dp.FUT[i] = 0.f;
+    }
+}
+__global__ void __launch_bounds__(256) k_occ_write(MapConst mc, DevPtrs dp, float thr, const int *blockoff, float *xyz, int cap, int *d_count, int nblocks) {
+    __shared__ int wsum[8];
+    int b = blockIdx.x * OCC_BLOCK;
+    int run = blockoff[blockIdx.x];
+    if (blockIdx.x == 0 && threadIdx.x == 0 && d_count) *d_count = blockoff[nblocks];
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int i0 = 0; i0 < OCC_BLOCK; i0 += 256) {
+        int v = b + i0 + threadIdx.x;
+        bool occ = v < mc.V && dp.OCCV[v].x > thr;
+        unsigned bal = __ballot_sync(FULLMASK, occ);
+        if (lane == 0) wsum[w] = __popc(bal);
+        __syncthreads();
+        int before = 0, tot = 0;
+        for (int k = 0; k < 8; ++k) { int x = wsum[k]; if (k < w) before += x; tot += x; }
+        if (occ) {
+            int pos = run + before + __popc(bal & ((1u << lane) - 1u));
+            if (pos < cap) {
+                float c[3];
+                dsp_voxel_center(mc, v, c);
+                xyz[3 * pos] = c[0]; xyz[3 * pos + 1] = c[1]; xyz[3 * pos + 2] = c[2];
+            }
+        }
+        run += tot;
+        __syncthreads();
+    }
+}
+__global__ void k_future_clear(MapConst mc, DevPtrs dp) {
+    size_t n = (size_t)mc.V * mc.T;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dp.FUT[i] = 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// state dump / load
+// ------------------------------------------------------------------------------------------------------------
+__global__ void k_dump_gather(MapConst mc, DevPtrs dp, int *keys, float *vals) {
+    const int n = min(dp.st->n_live, dp.cap_live);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int key = dp.E[i];
+        int a = (key >> DSP_KEY_SHIFT) * mc.S + (key & (DSP_MAX_SLOTS - 1));
+        float4 A = dp.PA[a], B = dp.PB[a];
+        keys[i] = key;
+        float *o = vals + 8 * (size_t)i;
+        o[0] = B.w; o[1] = B.x; o[2] = B.y; o[3] = B.z; o[4] = A.x; o[5] = A.y; o[6] = A.z; o[7] = A.w;
+    }
+}
+__global__ void k_load_scatter(MapConst mc, DevPtrs dp, const int *ids, const float *vals, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int v = ids[2 * i], s = ids[2 * i + 1];
+        const float *o = vals + 8 * (size_t)i;
+        int a = v * mc.S + s;
+        dp.PA[a] = make_float4(o[4], o[5], o[6], o[7]);
+        dp.PB[a] = make_float4(o[1], o[2], o[3], o[0]);
+        mask_atomic_set(dp.M, v, s);
+    }
+}
+__global__ void k_reset_counter(int *p) { *p = 0; }

@@ -1,0 +1,333 @@
+"""dspmap_b200 — Python host-side mirror of the DSP map's public interface over the C-ABI (include/dspmap_b200.h).
+
+`DSPMap` keeps the reference's method names and argument meaning (g-ch/DSP-map include/dsp_dynamic.h:142-446):
+update / getOccupancyMap / getOccupancyMapWithFutureStatus / clearOccupancyMapPrediction / the six setters /
+getKMClusterResult / getVoxelPositionFromIndexPublic / getPointVoxelsIndexPublic.  All work happens in
+dsp-map_b200/lib/libdspmap_b200.so (hand-written sm_100a kernels); there is no CPU path: importing works without a
+GPU (so the symbol table can be checked), creating a map without one raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from .configs import CONFIGS, derive  # noqa: F401
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libdspmap_b200.so")
+
+OK, REJECTED = 1, 0
+MAX_T = 8
+
+COUNTER_NAMES = ["n_in", "n_left_map", "n_voxel_full", "n_pyramid_full", "n_moved", "n_fov", "n_candidates", "n_born",
+                 "n_low_weight", "n_pre", "n_old", "n_out", "n_valid_points", "n_inexact", "launches_frame",
+                 "launches_total"]
+
+
+class Config(C.Structure):
+    _fields_ = [("nx", C.c_int32), ("ny", C.c_int32), ("nz", C.c_int32), ("resolution", C.c_float),
+                ("angle_resolution", C.c_int32), ("half_fov_h", C.c_int32), ("half_fov_v", C.c_int32),
+                ("max_particles_per_voxel", C.c_int32), ("safe_particles_per_voxel", C.c_int32),
+                ("safe_particles_per_pyramid", C.c_int32), ("pyramid_neighbor_n", C.c_int32), ("model", C.c_int32),
+                ("prediction_times", C.c_int32), ("prediction_future_time", C.c_float * MAX_T),
+                ("occlusion_margin", C.c_float), ("init_particle_num", C.c_int32), ("init_weight", C.c_float),
+                ("table_seed", C.c_uint64), ("uniform_seed", C.c_uint64), ("gaussian_table_size", C.c_int32),
+                ("max_observations_per_pyramid", C.c_int32), ("device", C.c_int32), ("max_points", C.c_int32),
+                ("shard_z_begin", C.c_int32), ("shard_z_end", C.c_int32)]
+
+
+class DSPMapError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library():
+    """Loads the C-ABI library. Fails loudly if it has not been built (python dsp-map_b200/build.py)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DSPMapError("%s is missing: build it with `python dsp-map_b200/build.py` (there is no CPU fallback)" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, f, i, fp, ip = C.c_void_p, C.c_float, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int32)
+    sig = {
+        "dspmap_default_config": (None, [C.POINTER(Config)]),
+        "dspmap_create": (i, [C.POINTER(Config), C.POINTER(vp)]),
+        "dspmap_destroy": (None, [vp]),
+        "dspmap_last_error": (C.c_char_p, []),
+        "dspmap_update": (i, [vp, i, i, fp, f, f, f, C.c_double, f, f, f, f]),
+        "dspmap_update_tagged": (i, [vp, i, i, fp, f, f, f, C.c_double, f, f, f, f, fp, i]),
+        "dspmap_update_device": (i, [vp, i, vp, f, f, f, C.c_double, f, f, f, f, vp, i]),
+        "dspmap_set_prediction_variance": (i, [vp, f, f]),
+        "dspmap_set_observation_stddev": (i, [vp, f]),
+        "dspmap_set_newborn_weight": (i, [vp, f]),
+        "dspmap_set_newborn_number": (i, [vp, i]),
+        "dspmap_set_particle_record_flag": (i, [vp, i, f, C.c_char_p]),
+        "dspmap_set_voxel_filter_resolution": (i, [vp, f]),
+        "dspmap_get_occupancy": (i, [vp, f, fp, i, ip, fp]),
+        "dspmap_get_occupancy_device": (i, [vp, f, vp, i, vp, vp]),
+        "dspmap_clear_prediction": (i, [vp]),
+        "dspmap_get_tagged_cloud": (i, [vp, fp, i]),
+        "dspmap_voxel_center": (None, [vp, i, fp]),
+        "dspmap_voxel_index": (i, [vp, f, f, f, ip]),
+        "dspmap_uniform": (f, [vp, f, f]),
+        "dspmap_dims": (None, [vp, ip]),
+        "dspmap_dump_particles": (i, [vp, ip, fp, i]),
+        "dspmap_load_particles": (i, [vp, ip, fp, i]),
+        "dspmap_dump_voxel_objects": (i, [vp, fp]),
+        "dspmap_dump_observations": (i, [vp, ip, fp, fp]),
+        "dspmap_dump_pyramid_lists": (i, [vp, ip, ip, i]),
+        "dspmap_cursors": (i, [vp, C.POINTER(C.c_int64)]),
+        "dspmap_set_cursors": (i, [vp, C.c_int64, C.c_int64, C.c_int64]),
+        "dspmap_counters": (i, [vp, C.POINTER(C.c_int64)]),
+        "dspmap_set_stage_limit": (i, [vp, i]),
+        "dspmap_set_last_pose": (i, [vp, f, f, f, C.c_double]),
+        "dspmap_set_stream": (i, [vp, vp]),
+        "dspmap_synchronize": (i, [vp]),
+        "dspmap_profile_enable": (i, [vp, i]),
+        "dspmap_profile_read": (i, [vp, C.POINTER(C.c_char_p), fp, ip, i]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)  # AttributeError here = the library does not export what include/dspmap_b200.h declares
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+EXPORTED_SYMBOLS = [
+    "dspmap_default_config", "dspmap_create", "dspmap_destroy", "dspmap_last_error", "dspmap_update",
+    "dspmap_update_tagged", "dspmap_update_device", "dspmap_set_prediction_variance", "dspmap_set_observation_stddev",
+    "dspmap_set_newborn_weight", "dspmap_set_newborn_number", "dspmap_set_particle_record_flag",
+    "dspmap_set_voxel_filter_resolution", "dspmap_get_occupancy", "dspmap_get_occupancy_device",
+    "dspmap_clear_prediction", "dspmap_get_tagged_cloud", "dspmap_voxel_center", "dspmap_voxel_index", "dspmap_uniform",
+    "dspmap_dims", "dspmap_dump_particles", "dspmap_load_particles", "dspmap_dump_voxel_objects",
+    "dspmap_dump_observations", "dspmap_dump_pyramid_lists", "dspmap_cursors", "dspmap_set_cursors", "dspmap_counters",
+    "dspmap_set_stage_limit", "dspmap_set_last_pose", "dspmap_set_stream", "dspmap_synchronize", "dspmap_profile_enable", "dspmap_profile_read",
+]
+
+
+def make_config(cfg, seed=1, init_particles=0, init_weight=0.01, device=0, max_points=0, safe_ppv=0, safe_pyramid=0,
+                table_size=10000000):
+    """cfg: a dict from configs.CONFIGS (the reference's compile-time parameters)."""
+    c = Config()
+    c.nx, c.ny, c.nz = cfg["nx"], cfg["ny"], cfg["nz"]
+    c.resolution = cfg["res"]
+    c.angle_resolution = cfg["angle_res"]
+    c.half_fov_h, c.half_fov_v = cfg["half_fov_h"], cfg["half_fov_v"]
+    c.max_particles_per_voxel = cfg["max_ppv"]
+    c.safe_particles_per_voxel = safe_ppv
+    c.safe_particles_per_pyramid = safe_pyramid
+    c.pyramid_neighbor_n = cfg["neighbor_n"]
+    c.model = 1 if cfg["model"] == "static" else 0
+    c.prediction_times = len(cfg["future_times"])
+    for k, t in enumerate(cfg["future_times"]):
+        c.prediction_future_time[k] = t
+    c.occlusion_margin = 0.3 if cfg["header"] == "dsp_dynamic.h" else cfg["res"]
+    c.init_particle_num, c.init_weight = init_particles, init_weight
+    c.table_seed = seed
+    c.uniform_seed = seed
+    c.gaussian_table_size = table_size
+    c.max_observations_per_pyramid = 100
+    c.device = device
+    c.max_points = max_points
+    return c
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float)) if a is not None else None
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32)) if a is not None else None
+
+
+class DSPMap:
+    """The reference's `class DSPMap` (dsp_dynamic.h:142) over the B200 library."""
+
+    def __init__(self, cfg, seed=1, init_particle_num=0, init_weight=0.01, device=0, **kw):
+        self.lib = load_library()
+        self.cfg_dict = cfg
+        self.config = make_config(cfg, seed, init_particle_num, init_weight, device, **kw)
+        h = C.c_void_p()
+        rc = self.lib.dspmap_create(C.byref(self.config), C.byref(h))
+        if rc != OK:
+            raise DSPMapError("dspmap_create failed (%d): %s" % (rc, self.lib.dspmap_last_error().decode()))
+        self.h = h
+        d = np.zeros(16, np.int32)
+        self.lib.dspmap_dims(self.h, _ip(d))
+        (self.V, self.S, self.P, self.L, self.T, self.Nh, self.Nv, self.NBW, self.max_ppv, self.nx, self.ny, self.nz,
+         self.obs_max, self.static) = [int(x) for x in d[:14]]
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.dspmap_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc < 0:
+            raise DSPMapError("dspmap call failed (%d): %s" % (rc, self.lib.dspmap_last_error().decode()))
+        return rc
+
+    # ---- the reference's public methods -----------------------------------------------------------------------
+    def update(self, point_cloud_num, size_of_one_point, point_cloud, sensor_px, sensor_py, sensor_pz,
+               time_stamp_second, qw, qx, qy, qz, tagged=None):
+        """DSPMap::update (dsp_dynamic.h:181). Returns 1 / 0 like the reference. `tagged` (n x 7, world frame)
+        overrides the built-in velocity estimation with an explicit newborn input."""
+        pts = np.ascontiguousarray(point_cloud, np.float32)
+        if tagged is None:
+            return self._check(self.lib.dspmap_update(self.h, point_cloud_num, size_of_one_point, _fp(pts), sensor_px,
+                                                      sensor_py, sensor_pz, time_stamp_second, qw, qx, qy, qz))
+        tg = np.ascontiguousarray(tagged, np.float32)
+        return self._check(self.lib.dspmap_update_tagged(self.h, point_cloud_num, size_of_one_point, _fp(pts), sensor_px,
+                                                         sensor_py, sensor_pz, time_stamp_second, qw, qx, qy, qz,
+                                                         _fp(tg), tg.shape[0]))
+
+    def setPredictionVariance(self, p_stddev, v_stddev):
+        self._check(self.lib.dspmap_set_prediction_variance(self.h, p_stddev, v_stddev))
+
+    def setObservationStdDev(self, ob_stddev):
+        self._check(self.lib.dspmap_set_observation_stddev(self.h, ob_stddev))
+
+    def setNewBornParticleWeight(self, weight):
+        self._check(self.lib.dspmap_set_newborn_weight(self.h, weight))
+
+    def setNewBornParticleNumberofEachPoint(self, num):
+        self._check(self.lib.dspmap_set_newborn_number(self.h, num))
+
+    def setParticleRecordFlag(self, record_particle_flag, record_csv_time=1.0, folder="."):
+        self._check(self.lib.dspmap_set_particle_record_flag(self.h, record_particle_flag, record_csv_time, folder.encode()))
+
+    def setOriginalVoxelFilterResolution(self, res):
+        self._check(self.lib.dspmap_set_voxel_filter_resolution(self.h, res))
+
+    def getOccupancyMap(self, threshold=0.7):
+        """Returns (obstacles_num, cloud[n,3]); zeroes the future columns like the reference (dsp_dynamic.h:385-402)."""
+        xyz = np.zeros((self.V, 3), np.float32)
+        n = C.c_int32(0)
+        self._check(self.lib.dspmap_get_occupancy(self.h, threshold, _fp(xyz), self.V, C.byref(n), None))
+        return n.value, xyz[:n.value].copy()
+
+    def getOccupancyMapWithFutureStatus(self, threshold=0.7, future_status=None):
+        """Returns (obstacles_num, cloud[n,3], future_status[V,T]) (dsp_dynamic.h:405-426)."""
+        xyz = np.zeros((self.V, 3), np.float32)
+        if future_status is None:
+            future_status = np.zeros((self.V, self.T), np.float32)
+        n = C.c_int32(0)
+        self._check(self.lib.dspmap_get_occupancy(self.h, threshold, _fp(xyz), self.V, C.byref(n), _fp(future_status)))
+        return n.value, xyz[:n.value].copy(), future_status
+
+    def clearOccupancyMapPrediction(self):
+        self._check(self.lib.dspmap_clear_prediction(self.h))
+
+    def getKMClusterResult(self):
+        n = self.lib.dspmap_get_tagged_cloud(self.h, None, 0)
+        out = np.zeros((n, 7), np.float32)
+        if n:
+            self.lib.dspmap_get_tagged_cloud(self.h, _fp(out), n)
+        return out
+
+    def getVoxelPositionFromIndexPublic(self, index):
+        out = np.zeros(3, np.float32)
+        self.lib.dspmap_voxel_center(self.h, int(index), _fp(out))
+        return out
+
+    def getPointVoxelsIndexPublic(self, px, py, pz):
+        idx = C.c_int32(-1)
+        ok = self.lib.dspmap_voxel_index(self.h, px, py, pz, C.byref(idx))
+        return ok, idx.value
+
+    # ---- state access (tests, checkpointing) ------------------------------------------------------------------
+    def particles(self):
+        n = self._check(self.lib.dspmap_dump_particles(self.h, None, None, 0))
+        ids = np.zeros((n, 2), np.int32)
+        vals = np.zeros((n, 8), np.float32)
+        if n:
+            self._check(self.lib.dspmap_dump_particles(self.h, _ip(ids), _fp(vals), n))
+        return ids, vals
+
+    def load_particles(self, ids, vals):
+        ids = np.ascontiguousarray(ids, np.int32)
+        vals = np.ascontiguousarray(vals, np.float32)
+        self._check(self.lib.dspmap_load_particles(self.h, _ip(ids), _fp(vals), ids.shape[0]))
+
+    def voxel_objects(self):
+        out = np.zeros((self.V, 4 + self.T), np.float32)
+        self._check(self.lib.dspmap_dump_voxel_objects(self.h, _fp(out)))
+        return out
+
+    def observations(self):
+        cnt = np.zeros(self.P, np.int32)
+        mx = np.zeros(self.P, np.float32)
+        pts = np.zeros((self.P, self.obs_max, 5), np.float32)
+        self._check(self.lib.dspmap_dump_observations(self.h, _ip(cnt), _fp(mx), _fp(pts)))
+        return cnt, mx, pts
+
+    def pyramid_lists(self):
+        off = np.zeros(self.P + 1, np.int32)
+        n = self._check(self.lib.dspmap_dump_pyramid_lists(self.h, _ip(off), None, 0))
+        ent = np.zeros((n, 2), np.int32)
+        if n:
+            self._check(self.lib.dspmap_dump_pyramid_lists(self.h, _ip(off), _ip(ent), n))
+        return off, ent
+
+    def cursors(self):
+        c = np.zeros(4, np.int64)
+        self._check(self.lib.dspmap_cursors(self.h, c.ctypes.data_as(C.POINTER(C.c_int64))))
+        return c
+
+    def set_cursors(self, p, v, u):
+        self._check(self.lib.dspmap_set_cursors(self.h, int(p), int(v), int(u)))
+
+    def counters(self):
+        c = np.zeros(16, np.int64)
+        self._check(self.lib.dspmap_counters(self.h, c.ctypes.data_as(C.POINTER(C.c_int64))))
+        return dict(zip(COUNTER_NAMES, [int(x) for x in c]))
+
+    def set_stage_limit(self, k):
+        self._check(self.lib.dspmap_set_stage_limit(self.h, k))
+
+    def set_last_pose(self, pos, t):
+        self._check(self.lib.dspmap_set_last_pose(self.h, float(pos[0]), float(pos[1]), float(pos[2]), float(t)))
+
+    def set_stream(self, cuda_stream):
+        self._check(self.lib.dspmap_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    def synchronize(self):
+        self._check(self.lib.dspmap_synchronize(self.h))
+
+    def profile_enable(self, on=True):
+        self._check(self.lib.dspmap_profile_enable(self.h, 1 if on else 0))
+
+    def profile_read(self):
+        names = (C.c_char_p * 32)()
+        ms = np.zeros(32, np.float32)
+        ln = np.zeros(32, np.int32)
+        n = self.lib.dspmap_profile_read(self.h, names, _fp(ms), _ip(ln), 32)
+        return {names[k].decode(): (float(ms[k]), int(ln[k])) for k in range(n)}
+
+    # device-resident entry points (bench): pointers are raw device addresses (e.g. torch tensor .data_ptr())
+    def update_device(self, n, d_pts, pos, t, quat, d_tagged, n_tagged):
+        return self._check(self.lib.dspmap_update_device(self.h, n, C.c_void_p(d_pts), float(pos[0]), float(pos[1]),
+                                                         float(pos[2]), float(t), float(quat[0]), float(quat[1]),
+                                                         float(quat[2]), float(quat[3]), C.c_void_p(d_tagged), n_tagged))
+
+    def get_occupancy_device(self, threshold, d_xyz, cap, d_count, d_future):
+        return self._check(self.lib.dspmap_get_occupancy_device(self.h, threshold, C.c_void_p(d_xyz), cap,
+                                                                C.c_void_p(d_count), C.c_void_p(d_future)))
+
+
+def bytes_per_update(counters, V, T, M):
+    """Algorithmic HBM bytes of one update:
+    64 N_in + 36 N_fov + 32 N_born + 32 N_pre + 32 N_out + 4 T N_old + V (20 + 12 T) + 20 M."""
+    c = counters
+    return (64 * c["n_in"] + 36 * c["n_fov"] + 32 * c["n_born"] + 32 * c["n_pre"] + 32 * c["n_out"] +
+            4 * T * c["n_old"] + V * (20 + 12 * T) + 20 * M)

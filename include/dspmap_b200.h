@@ -1,0 +1,156 @@
+/* dspmap_b200.h — C-ABI of the B200-native DSP map (drop-in boundary for the per-frame particle loop).
+ *
+ * Every entry point names the reference interface it replaces (g-ch/DSP-map, include/dsp_dynamic.h unless
+ * stated otherwise).  Plain C types only: no PCL / Eigen / torch types cross this boundary.  The C++ class
+ * `DSPMap` in include/dsp_dynamic.h (this repository's drop-in header) is a thin wrapper over these calls.
+ *
+ * Conventions
+ *   - All functions returning `int` return DSPMAP_OK (1) / a frame-rejected 0 where the reference returns 0,
+ *     or a negative DSPMAP_E_* code for conditions the reference cannot have (CUDA failure, bad handle).
+ *     Nothing throws.  dspmap_last_error() gives a human-readable string for the last negative code.
+ *   - The library is not thread-safe per handle (neither is the reference: file-static state, dsp_dynamic.h:112-140).
+ *   - There is NO CPU fallback: if no sm_100 device is usable, dspmap_create fails with DSPMAP_E_NO_DEVICE.
+ */
+#ifndef DSPMAP_B200_H
+#define DSPMAP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSPMAP_OK 1
+#define DSPMAP_REJECTED 0        /* update(): bad quaternion / pose jump / time jump (dsp_dynamic.h:193-208) */
+#define DSPMAP_E_NO_DEVICE (-1)
+#define DSPMAP_E_CUDA (-2)
+#define DSPMAP_E_BAD_ARG (-3)
+#define DSPMAP_E_CAPACITY (-4)
+
+#define DSPMAP_MAX_PREDICTION_TIMES 8
+#define DSPMAP_TAGGED_STRIDE 7 /* x y z vx vy vz intensity: one point of input_cloud_with_velocity (dsp_dynamic.h:134) */
+
+typedef struct dspmap dspmap; /* opaque handle */
+
+/* Compile-time parameters of the reference (dsp_dynamic.h:38-70, mn:38-51, st:38-63) as run-time fields. */
+typedef struct dspmap_config {
+    int32_t nx, ny, nz;                 /* MAP_LENGTH/WIDTH/HEIGHT_VOXEL_NUM                 dsp_dynamic.h:38-40 */
+    float resolution;                   /* VOXEL_RESOLUTION                                  :41 */
+    int32_t angle_resolution;           /* ANGLE_RESOLUTION (degrees)                        :42 */
+    int32_t half_fov_h, half_fov_v;     /* half_fov_h / half_fov_v (degrees)                 :49-50 */
+    int32_t max_particles_per_voxel;    /* MAX_PARTICLE_NUM_VOXEL                            :43 */
+    int32_t safe_particles_per_voxel;   /* SAFE_PARTICLE_NUM_VOXEL; 0 = derive (2x, static 5x) :65, st:63 */
+    int32_t safe_particles_per_pyramid; /* SAFE_PARTICLE_NUM_PYRAMID; 0 = derive             :66 */
+    int32_t pyramid_neighbor_n;         /* PYRAMID_NEIGHBOR_N; 1 = the 3x3 block of dsp_dynamic.h:1135, mn:43 */
+    int32_t model;                      /* 0 = constant velocity (dsp_dynamic.h), 1 = static (dsp_static.h) */
+    int32_t prediction_times;           /* PREDICTION_TIMES                                  :46 */
+    float prediction_future_time[DSPMAP_MAX_PREDICTION_TIMES]; /*                           :47 */
+    float occlusion_margin;             /* obstacle_thickness_for_occlusion 0.3 (:70,:761); voxel_resolution in mn:761 / st */
+    int32_t init_particle_num;          /* DSPMap(init_particle_num, init_weight)            :145 */
+    float init_weight;
+    uint64_t table_seed;                /* seed of the two Gaussian tables; the reference uses time(NULL) (:1151) */
+    uint64_t uniform_seed;              /* seed of the counter-based uniform stream that stands where rand() is (:1552) */
+    int32_t gaussian_table_size;        /* GAUSSIAN_RANDOMS_NUM 10000000                     :72 */
+    int32_t max_observations_per_pyramid; /* observation_max_points_num_one_pyramid 100      :69 */
+    int32_t device;                     /* CUDA device ordinal */
+    int32_t max_points;                 /* capacity for points per update() (0 = 65536) */
+    /* voxel-subspace shard owned by this handle (multi-GPU): z-layers [z_begin, z_end); 0,0 = whole map */
+    int32_t shard_z_begin, shard_z_end;
+} dspmap_config;
+
+/* Fills `c` with the values of the reference tree as shipped (dsp_dynamic.h:38-50,145-168). */
+void dspmap_default_config(dspmap_config *c);
+
+/* DSPMap::DSPMap (:145-175) + setInitParameters (:525-591) + addRandomParticles (:594-624). */
+int dspmap_create(const dspmap_config *cfg, dspmap **out);
+/* DSPMap::~DSPMap (:177). */
+void dspmap_destroy(dspmap *m);
+const char *dspmap_last_error(void);
+
+/* DSPMap::update (:181-353).  `pts` is HOST memory, n points of `stride` floats, first three used (:247,:289).
+ * Runs the whole frame: binning, prediction + voxel/pyramid reassignment, observation weight update, the host
+ * velocity-estimation step, newborn particles, occupancy + resampling + future status.  Returns 1 / 0 like the
+ * reference. */
+int dspmap_update(dspmap *m, int n, int stride, const float *pts, float px, float py, float pz, double t,
+                  float qw, float qx, float qy, float qz);
+
+/* Same frame, but the newborn input (the side thread's output input_cloud_with_velocity, :134,:815) is given
+ * explicitly: n_tagged points of DSPMAP_TAGGED_STRIDE floats in the WORLD frame, as getKMClusterResult (:441)
+ * returns them.  tagged == NULL keeps the previous frame's cloud (what the reference does when no point is in
+ * view, :1379). */
+int dspmap_update_tagged(dspmap *m, int n, int stride, const float *pts, float px, float py, float pz, double t,
+                         float qw, float qx, float qy, float qz, const float *tagged, int n_tagged);
+
+/* Device-resident variant of dspmap_update_tagged for callers whose clouds already live in HBM (no host copies,
+ * no synchronisation; the frame is only enqueued on the handle's stream). d_pts: n*3 floats, d_tagged: n_tagged*7. */
+int dspmap_update_device(dspmap *m, int n, const float *d_pts, float px, float py, float pz, double t, float qw,
+                         float qx, float qy, float qz, const float *d_tagged, int n_tagged);
+
+/* setPredictionVariance (:355-360; regenerates both Gaussian tables, cursors are kept),
+ * setObservationStdDev (:362), setNewBornParticleWeight (:366), setNewBornParticleNumberofEachPoint (:370),
+ * setParticleRecordFlag (:375), setOriginalVoxelFilterResolution (:380). */
+int dspmap_set_prediction_variance(dspmap *m, float p_stddev, float v_stddev);
+int dspmap_set_observation_stddev(dspmap *m, float ob_stddev);
+int dspmap_set_newborn_weight(dspmap *m, float weight);
+int dspmap_set_newborn_number(dspmap *m, int num);
+int dspmap_set_particle_record_flag(dspmap *m, int flag, float record_time, const char *folder);
+int dspmap_set_voxel_filter_resolution(dspmap *m, float res);
+
+/* getOccupancyMap (:385-402) when future == NULL, getOccupancyMapWithFutureStatus (:405-426) otherwise.
+ * Writes up to `cap` voxel centres (xyz triples, ascending voxel index) to xyz_out, the total count to *n_out,
+ * V*T floats ([voxel][horizon]) to `future`, and zeroes the future columns (the reference's side effect,
+ * :397-400,:421-424).  HOST pointers. */
+int dspmap_get_occupancy(dspmap *m, float threshold, float *xyz_out, int cap, int *n_out, float *future);
+/* Device-resident variant: d_xyz (cap*3 floats), d_count (1 int), d_future (V*T floats or NULL) are device
+ * pointers; only enqueued. */
+int dspmap_get_occupancy_device(dspmap *m, float threshold, float *d_xyz, int cap, int *d_count, float *d_future);
+/* clearOccupancyMapPrediction (:431-438). */
+int dspmap_clear_prediction(dspmap *m);
+/* getKMClusterResult (:441-445): copies the last newborn input; returns the number of points. */
+int dspmap_get_tagged_cloud(dspmap *m, float *out, int cap);
+
+/* getVoxelPositionFromIndexPublic (:1556-1572) / getPointVoxelsIndexPublic (:1574-1584): pure host arithmetic. */
+void dspmap_voxel_center(const dspmap *m, int index, float *xyz);
+int dspmap_voxel_index(const dspmap *m, float x, float y, float z, int *index);
+/* generateRandomFloat (:1551-1553) on the handle's uniform stream. */
+float dspmap_uniform(dspmap *m, float lo, float hi);
+
+/* Sizes: V, S, P, L, T, Nh, Nv, neighbour-table width, MAX ppv, nx, ny, nz, obs max, model (14 ints). */
+void dspmap_dims(const dspmap *m, int32_t *out);
+
+/* State dump / load (tests, checkpointing).  Particle record = the reference's CSV columns (:339-344):
+ * ids[n][2] = {voxel, slot}; vals[n][8] = {flag, vx, vy, vz, px, py, pz, weight}; sweep order on dump. */
+int dspmap_dump_particles(dspmap *m, int32_t *ids, float *vals, int cap);
+int dspmap_load_particles(dspmap *m, const int32_t *ids, const float *vals, int n);
+/* voxels_objects_number[V][4+T] (:120). */
+int dspmap_dump_voxel_objects(dspmap *m, float *out);
+/* Last frame's binned observations (:497-515): counts[P], maxlen[P], pts[P][obs_max][5] (x y z Cz range). */
+int dspmap_dump_observations(dspmap *m, int32_t *counts, float *maxlen, float *pts);
+/* Last frame's pyramid lists (:124): offsets[P+1], entries[n][2] = {voxel, slot} in list order. */
+int dspmap_dump_pyramid_lists(dspmap *m, int32_t *offsets, int32_t *entries, int cap);
+/* c[0] position-noise cursor, c[1] velocity-noise cursor, c[2] uniform-stream counter (:483-484). */
+int dspmap_cursors(dspmap *m, int64_t *c);
+int dspmap_set_cursors(dspmap *m, int64_t p, int64_t v, int64_t u);
+
+/* Per-frame counters of the last update: n_in, n_left_map, n_voxel_full, n_pyramid_full, n_moved,
+ * n_fov, n_candidates, n_born, n_low_weight, n_pre, n_old, n_out, n_valid_points, n_inexact, kernel launches of
+ * the last frame, kernel launches since create (16 int64). */
+int dspmap_counters(dspmap *m, int64_t *out);
+
+/* Debug / replay: overrides the remembered previous pose and time stamp (the function-local statics of update(),
+ * dsp_dynamic.h:187-190) so that a frame can be replayed from an injected state. */
+int dspmap_set_last_pose(dspmap *m, float px, float py, float pz, double t);
+/* Debug: run only the first k stages of the next update()s (1 predict, 2 +observe, 3 +newborn, >=4 all). */
+int dspmap_set_stage_limit(dspmap *m, int k);
+/* Work is enqueued on this CUDA stream (a cudaStream_t; 0 = the handle's own stream). */
+int dspmap_set_stream(dspmap *m, void *cuda_stream);
+int dspmap_synchronize(dspmap *m);
+/* Average device time (ms) of each kernel family since the last reset, measured with CUDA events when profiling is
+ * enabled: names[i] / ms[i] / launches[i]; returns the number of families. */
+int dspmap_profile_enable(dspmap *m, int on);
+int dspmap_profile_read(dspmap *m, const char **names, float *ms, int32_t *launches, int cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSPMAP_B200_H */

@@ -88,6 +88,7 @@ struct Map {
     std::vector<float> tagged;  // last newborn input (kept when a frame provides none, dsp_dynamic.h:1379)
     // per-frame counters
     int64_t ctr[16];
+    int stage_limit = 4;  // debugging aid: 1 predict, 2 +observe, 3 +newborn, 4 all
 
     float *slot(int v, int s) { return &part[((size_t)v * S + s) * F_N]; }
 
@@ -574,10 +575,10 @@ struct Map {
         ctr[12] = valid;
         expected_new_born = nb_weight * (float)valid * (float)nb_num;  // :292
         if (tag && n_tag >= 0) tagged.assign(tag, tag + (size_t)7 * n_tag);  // null = keep the previous cloud (:1379)
-        predict(-ox, -oy, -oz, dt);  // :300
-        observe_update();            // :304
-        newborn();                   // :315
-        resample();                  // :322
+        predict(-ox, -oy, -oz, dt);                 // :300
+        if (stage_limit >= 2) observe_update();     // :304
+        if (stage_limit >= 3) newborn();            // :315
+        if (stage_limit >= 4) resample();           // :322
         return 1;
     }
 
@@ -701,6 +702,13 @@ void oracle_set_cursors(void *h, int64_t p, int64_t v, int64_t u) {
     m->v_cur = v;
     m->u_cur = (uint64_t)u;
 }
+void oracle_set_last_pose(void *h, float px, float py, float pz, double t) {
+    Map *m = (Map *)h;
+    m->last_p[0] = px; m->last_p[1] = py; m->last_p[2] = pz;
+    m->last_t = t;
+    m->have_last = true;
+}
+void oracle_set_stage_limit(void *h, int k) { ((Map *)h)->stage_limit = k; }
 void oracle_counters(void *h, int64_t *out) { std::memcpy(out, ((Map *)h)->ctr, sizeof(int64_t) * 16); }
 void oracle_gaussian_tables(void *h, float *p, float *v, int n) {
     Map *m = (Map *)h;

@@ -73,6 +73,8 @@ class OracleMap:
         L.oracle_set_newborn_number.argtypes = [vp, C.c_int]
         L.oracle_voxel_index.argtypes = [vp, C.c_float, C.c_float, C.c_float]
         L.oracle_set_cursors.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64]
+        L.oracle_set_stage_limit.argtypes = [vp, C.c_int]
+        L.oracle_set_last_pose.argtypes = [vp, C.c_float, C.c_float, C.c_float, C.c_double]
         for f in ("oracle_destroy", "oracle_dims", "oracle_clear_prediction", "oracle_dump_particles",
                   "oracle_load_particles", "oracle_dump_voxel_objects", "oracle_dump_observations",
                   "oracle_dump_pyramid_lists", "oracle_dump_neighbors", "oracle_cursors", "oracle_counters",
@@ -159,6 +161,12 @@ class OracleMap:
 
     def set_cursors(self, p, v, u):
         self.lib.oracle_set_cursors(self.h, int(p), int(v), int(u))
+
+    def set_stage_limit(self, k):
+        self.lib.oracle_set_stage_limit(self.h, k)
+
+    def set_last_pose(self, pos, t):
+        self.lib.oracle_set_last_pose(self.h, float(pos[0]), float(pos[1]), float(pos[2]), float(t))
 
     def counters(self):
         c = np.zeros(16, np.int64)
