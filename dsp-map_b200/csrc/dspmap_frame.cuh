@@ -469,7 +469,7 @@ __global__ void __launch_bounds__(K4_THREADS) k_ck(MapConst mc, FrameConst fc, D
         for (int t = threadIdx.x; t < npts; t += blockDim.x) zs[t] = dp.OBSP[i * mc.OBS + t];
         const int tp = min(256, K4_TERMS / npts);
         float acc = 0.f;
-        const unsigned magic = 0xffffffffu / (unsigned)npts + 1u;  // exact t / npts for t < 65536
+        const unsigned magic = npts > 1 ? 0xffffffffu / (unsigned)npts + 1u : 0u;  // exact t / npts for t < 65536
         const int nn = dp.nbr[i * mc.NBW];
         for (int ns = 0; ns < nn; ++ns) {
             const int pc = dp.nbr[i * mc.NBW + 1 + ns];
@@ -481,7 +481,7 @@ __global__ void __launch_bounds__(K4_THREADS) k_ck(MapConst mc, FrameConst fc, D
                 __syncthreads();
                 const int pairs = cur * npts;
                 for (int t = threadIdx.x; t < pairs; t += blockDim.x) {
-                    int k = __umulhi((unsigned)t, magic);
+                    int k = npts > 1 ? (int)__umulhi((unsigned)t, magic) : t;
                     int z = t - k * npts;
                     float4 p = ptl[k], o = zs[z];
                     float gk = dsp_pdf(lut, p.x, o.x, fc.sigma) * dsp_pdf(lut, p.y, o.y, fc.sigma) * dsp_pdf(lut, p.z, o.z, fc.sigma);
