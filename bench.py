@@ -1,0 +1,345 @@
+#!/usr/bin/env python3
+"""bench.py — map updates/s of the DSP-Dynamic per-frame particle loop on B200 (BASELINE.json metric).
+
+One "step" = DSPMap::update() + getOccupancyMapWithFutureStatus() on one frame of a deterministic synthetic
+depth-cloud + pose stream.  Default workload = BASELINE.json configs[1]: DSP-Dynamic 66x66x40 voxels
+@0.15 m, 24 particles/voxel, 90x60 deg FOV, 10 k-point cloud.
+
+  python bench.py --gpus N --steps K --warmup W            # this repository's CUDA path
+  python bench.py --impl reference --steps K --warmup W    # the unmodified reference header (oracle/_ref) on host cores
+
+JSON line keys: see DESIGN.md "Measurement".  `value` = frames/s with clouds already resident in HBM (device-resident
+C-ABI entry points, CUDA events, L2 flushed between steps); `e2e` = the same frames through the host-pointer C-ABI
+(dspmap_update + dspmap_get_occupancy: H2D of the cloud, host velocity estimation, D2H of the occupied-voxel list and
+the V x T future grid inside the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "dsp-map_b200"))
+
+import numpy as np  # noqa: E402
+
+THRESHOLD = 0.2   # occupancy threshold used by the example app (src/map_sim_example.cpp:378)
+PREROLL = 25      # untimed frames to reach the steady particle population (discard >= 20)
+SETTERS = dict(p_std=0.05, v_std=0.05, ob_std=0.1, newborn_num=20, newborn_weight=1e-4, filter_res=0.1)  # ex:522-526
+
+
+def apply_setters(m):
+    m.setPredictionVariance(SETTERS["p_std"], SETTERS["v_std"])
+    m.setObservationStdDev(SETTERS["ob_std"])
+    m.setNewBornParticleNumberofEachPoint(SETTERS["newborn_num"])
+    m.setNewBornParticleWeight(SETTERS["newborn_weight"])
+    m.setOriginalVoxelFilterResolution(SETTERS["filter_res"])
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for k, nme in enumerate(names):
+                if len(r) > 4 + k and r[4 + k].lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def reference_arm(args, cfg_name, cfg):
+    """Times the reference's own CPU implementation (unmodified header, oracle/_ref) on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from dspmap_b200.streams import make_stream
+    import refmap
+    if not refmap.available(cfg_name):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libdspref_%s.so not built" % cfg_name}))
+        return 0
+    pre = 8  # the reference needs ~8 frames to reach its steady particle population (1 s each at cfg2)
+    F = pre + args.warmup + args.steps
+    st = make_stream(cfg, seed=1, frames=F)
+    r = refmap.RefMap(cfg_name, seed=1, **SETTERS)
+    fut = np.zeros((r.V, r.T), np.float32)
+    times = []
+    for f in range(F):
+        s, _ = r.timed_frame(st["points"][f], st["pos"][f], st["t"][f], st["quat"][f], THRESHOLD, fut)
+        if f >= pre + args.warmup:
+            times.append(s)
+    total = float(np.sum(times))
+    val = len(times) / total
+    line = {"impl": "reference", "metric": "map_updates_per_s", "value": val, "unit": "updates/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(cfg_name, cfg, "cpu"),
+            "cpu_baseline": {"value": val, "unit": "updates/s", "cores": 2, "kind": "reference",
+                             "sample": "%d frames of the same stream after %d untimed frames; unmodified reference header, "
+                                       "g++ -O2, 1 thread + its 1 helper thread of %d host cores" % (len(times), pre + args.warmup, os.cpu_count())},
+            "e2e": {"value": val, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(cfg_name, cfg, where):
+    return {"workload": "%s: DSP-%s %dx%dx%d vox @%.2f m, %d ppv, FOV %dx%d deg, %d-pt synthetic depth cloud, update()+getOccupancyMapWithFutureStatus()"
+                        % (cfg_name, "Static" if cfg["model"] == "static" else "Dynamic", cfg["nx"], cfg["ny"], cfg["nz"], cfg["res"],
+                           cfg["max_ppv"], 2 * cfg["half_fov_h"], 2 * cfg["half_fov_v"], cfg["points"]),
+            "horizons": cfg["future_times"], "neighbors": (2 * cfg["neighbor_n"] + 1) ** 2, "where": where}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--config", default="cfg2")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-flush", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    import dspmap_b200 as dm
+    from dspmap_b200.streams import make_stream
+    cfg_name = args.config
+    cfg = dm.CONFIGS[cfg_name]
+    if args.impl == "reference":
+        return reference_arm(args, cfg_name, cfg)
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    K, W = args.steps, args.warmup
+    F = PREROLL + W + K          # device-resident pass
+    PROF = min(K, 20)            # frames of the per-kernel profiling pass
+    F2 = F + PROF + W + K        # + profiling pass + end-to-end pass on the following frames
+    st = make_stream(cfg, seed=1 + rank, frames=F2)
+    M = int(st["n"][0])
+
+    # newborn inputs for the device-resident pass: the library's own host velocity estimator, pre-computed
+    est = dm.VelocityEstimator(cfg, seed=1, filter_res=SETTERS["filter_res"])
+    tagged, last = [], np.zeros((0, 7), np.float32)
+    for f in range(F):
+        t = est.estimate(st["points"][f], st["pos"][f], st["t"][f], st["quat"][f])
+        last = t if t is not None else last
+        tagged.append(last)
+    nt_max = max(len(t) for t in tagged)
+    d_pts = torch.from_numpy(st["points"][:F]).to(dev)
+    tg = np.zeros((F, max(nt_max, 1), 7), np.float32)
+    for f, t in enumerate(tagged):
+        tg[f, :len(t)] = t
+    d_tag = torch.from_numpy(tg).to(dev)
+
+    m = dm.DSPMap(cfg, seed=1, device=local, max_points=max(M, nt_max, 1024))
+    apply_setters(m)
+    stream = torch.cuda.Stream(device=dev)  # a real (non-default) stream shared by torch's events and the library's kernels
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    m.set_stream(stream.cuda_stream)
+    d_xyz = torch.empty((m.V, 3), dtype=torch.float32, device=dev)
+    d_cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+    d_fut = torch.empty((m.V, m.T), dtype=torch.float32, device=dev)
+    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step_device(f):
+        m.update_device(M, d_pts[f].data_ptr(), st["pos"][f], st["t"][f], st["quat"][f], d_tag[f].data_ptr(), len(tagged[f]))
+        m.get_occupancy_device(THRESHOLD, d_xyz.data_ptr(), m.V, d_cnt.data_ptr(), d_fut.data_ptr())
+
+    for f in range(PREROLL + W):
+        step_device(f)
+    m.synchronize()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches0 = m.counters()["launches_total"]
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ncu = os.environ.get("DSPMAP_NCU") == "1"  # under `ncu --profile-from-start off` only the timed region is captured
+    if ncu:
+        torch.cuda.profiler.start()
+    e0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    e1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ctr_sum = None
+    for k in range(K):
+        if flush is not None:
+            flush.zero_()
+        e0[k].record(stream)
+        step_device(PREROLL + W + k)
+        e1[k].record(stream)
+    torch.cuda.synchronize()
+    m.synchronize()
+    if ncu:
+        torch.cuda.profiler.stop()
+    if world > 1:
+        dist.barrier()
+    dev_ms = sum(a.elapsed_time(b) for a, b in zip(e0, e1))
+    launches = m.counters()["launches_total"] - launches0
+    tt = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dev_ms_max = float(tt.item())
+    value = world * K / (dev_ms_max * 1e-3)
+
+    # per-family kernel times (CUDA events on the launching stream) over the same kind of frames, and the frame counters
+    # that define the algorithmic bytes
+    m.profile_enable(True)
+    P = PROF
+    agg = {}
+    for k in range(P):
+        f = PREROLL + W + K - P + k  # replaying already-seen inputs is fine: kernel work depends on the map state
+        if flush is not None:
+            flush.zero_()
+        m.update(M, 3, st["points"][F + k], *map(float, st["pos"][F + k]), float(st["t"][F + k]), *map(float, st["quat"][F + k]),
+                 tagged=est.estimate(st["points"][F + k], st["pos"][F + k], st["t"][F + k], st["quat"][F + k]))
+        c = m.counters()
+        for kk, vv in c.items():
+            agg[kk] = agg.get(kk, 0) + vv
+        m.get_occupancy_device(THRESHOLD, d_xyz.data_ptr(), m.V, d_cnt.data_ptr(), d_fut.data_ptr())
+    m.synchronize()
+    prof = m.profile_read()
+    m.profile_enable(False)
+    ctr = {kk: vv / P for kk, vv in agg.items()}
+    fam_ms = {n: (ms / P) for n, (ms, ln) in prof.items() if ln}
+    fam_launches = {n: ln / P for n, (ms, ln) in prof.items() if ln}
+
+    # end-to-end: host buffers in, host buffers out, through the reference-facing calls
+    fut_host = np.zeros((m.V, m.T), np.float32)
+    e2e_t = []
+    h2d = d2h = 0
+    for k in range(W + K):
+        f = F + P + k
+        pts, pos, t, q = st["points"][f], st["pos"][f], st["t"][f], st["quat"][f]
+        if flush is not None:
+            flush.zero_()
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        rc = m.update(M, 3, pts, float(pos[0]), float(pos[1]), float(pos[2]), float(t), float(q[0]), float(q[1]), float(q[2]), float(q[3]))
+        n_occ, xyz, _ = m.getOccupancyMapWithFutureStatus(THRESHOLD, fut_host)
+        t1 = time.perf_counter()
+        if k >= W and rc == 1:
+            e2e_t.append(t1 - t0)
+            h2d += pts.nbytes + 28 * len(m.getKMClusterResult())
+            d2h += 4 + 12 * n_occ + fut_host.nbytes + 160
+    tt = torch.tensor([sum(e2e_t)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    e2e_val = world * len(e2e_t) / float(tt.item())
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = measured_peak()
+    T, V = m.T, m.V
+    b_frame = dm.bytes_per_update(ctr, V, T, M)
+    # dominant kernel = the family with the largest device time; its algorithmic bytes (DESIGN.md "Kernels")
+    top = max(fam_ms, key=fam_ms.get)
+    fam_bytes = {
+        "ck_pass": 16 * ctr["n_fov"] + 20 * M,             # read px,py,pz,w per registered particle; read point, write C_z
+        "weight_pass": 20 * ctr["n_fov"] + 20 * M,         # read px,py,pz,w + write w; read point + C_z
+        "predict": 64 * ctr["n_in"],
+        "newborn": 32 * ctr["n_born"] + 28 * M,
+        "resample_future": 32 * ctr["n_pre"] + 32 * ctr["n_out"] + 4 * T * ctr["n_old"] + V * (16 + 16),
+        "reader": V * (4 + 12 * T),
+        "pyramid_lists": 28 * ctr["n_fov"],
+        "arrive": 64 * ctr["n_moved"],
+        "obs_bin": 32 * M,
+        "enumerate": 32 * V + 4 * ctr["n_in"],
+    }
+    top_ms = fam_ms[top]  # device ms per update spent in that family (one launch per update for the two observation passes)
+    achieved = fam_bytes.get(top, b_frame) / (top_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(top)
+    line = {
+        "metric": "map_updates_per_s", "value": value, "unit": "updates/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": dict(workload_config(cfg_name, cfg, "hbm-resident"), parallelism="replicas x%d" % world if world > 1 else "single",
+                       l2_flush_between_steps=flush is not None, preroll_frames=PREROLL),
+        "e2e": {"value": e2e_val, "unit": "updates/s", "h2d_bytes_per_step": h2d // max(len(e2e_t), 1),
+                "d2h_bytes_per_step": d2h // max(len(e2e_t), 1), "ms_per_step": 1e3 * float(np.mean(e2e_t))},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": fam_bytes.get(top),
+                     "kernel_ms": top_ms},
+        "roofline_frame": {"bound": "hbm", "algorithmic_bytes_per_update": b_frame, "achieved": b_frame / (dev_ms_max / K * 1e-3) / 1e9,
+                           "peak": peak, "unit": "GB/s", "frac": b_frame / (dev_ms_max / K * 1e-3) / 1e9 / peak},
+        "kernel_ms_per_update": {k_: round(v_, 5) for k_, v_ in sorted(fam_ms.items(), key=lambda kv: -kv[1])},
+        "counters_per_update": {k_: round(v_, 1) for k_, v_ in ctr.items() if k_ not in ("launches_total",)},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import refmap
+        if refmap.available(cfg_name):
+            pre, n_t = 8, 5
+            r = refmap.RefMap(cfg_name, seed=1, **SETTERS)
+            futr = np.zeros((r.V, r.T), np.float32)
+            ts = []
+            for f in range(pre + n_t):
+                s, _ = r.timed_frame(st["points"][f], st["pos"][f], st["t"][f], st["quat"][f], THRESHOLD, futr)
+                if f >= pre:
+                    ts.append(s)
+            line["cpu_baseline"] = {"value": len(ts) / float(np.sum(ts)), "unit": "updates/s", "cores": 2, "kind": "reference",
+                                    "sample": "frames %d..%d of the same stream; unmodified reference header (oracle/_ref), g++ -O2, "
+                                              "1 thread + its 1 helper thread of %d host cores" % (pre, pre + n_t - 1, os.cpu_count())}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

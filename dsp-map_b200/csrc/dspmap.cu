@@ -367,6 +367,25 @@ int frame_epilogue(dspmap *m) {
 
 int write_particle_csv(dspmap *m);
 
+// pyramid boundary-plane normals when the sensor has no rotation (dsp_dynamic.h:563-578)
+void make_planes0(const dspmap_config *cfg, int Nh, int Nv, std::vector<float> &planes0) {
+    const float ang = (float)cfg->angle_resolution / 180.f * 3.14159265358979323846;  // :543
+    planes0.assign(3 * (Nh + Nv + 2), 0.f);
+    int h0 = -cfg->half_fov_h / cfg->angle_resolution, h1 = -h0;
+    for (int i = h0; i <= h1; i++) {
+        planes0[3 * (i + h1) + 0] = -std::sin((float)i * ang);
+        planes0[3 * (i + h1) + 1] = std::cos((float)i * ang);
+        planes0[3 * (i + h1) + 2] = 0.f;
+    }
+    float *pv = &planes0[3 * (Nh + 1)];
+    int v0 = -cfg->half_fov_v / cfg->angle_resolution, v1 = -v0;
+    for (int i = v0; i <= v1; i++) {
+        pv[3 * (i + v1) + 0] = std::sin((float)i * ang);
+        pv[3 * (i + v1) + 1] = 0.f;
+        pv[3 * (i + v1) + 2] = std::cos((float)i * ang);
+    }
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------------------
@@ -497,24 +516,7 @@ int dspmap_create(const dspmap_config *cfg, dspmap **out) {
     CK(cudaMallocHost(&m->h_state, sizeof(DevState)));
     CK(cudaMallocHost(&m->h_count, sizeof(int)));
 
-    // boundary-plane normals in the sensor frame (:563-578)
-    const float ang = (float)cfg->angle_resolution / 180.f * 3.14159265358979323846;  // :543
-    m->planes0.assign(3 * (mc.Nh + mc.Nv + 2), 0.f);
-    {
-        int h0 = -cfg->half_fov_h / cfg->angle_resolution, h1 = -h0;
-        for (int i = h0; i <= h1; i++) {
-            m->planes0[3 * (i + h1) + 0] = -std::sin((float)i * ang);
-            m->planes0[3 * (i + h1) + 1] = std::cos((float)i * ang);
-            m->planes0[3 * (i + h1) + 2] = 0.f;
-        }
-        float *pv = &m->planes0[3 * (mc.Nh + 1)];
-        int v0 = -cfg->half_fov_v / cfg->angle_resolution, v1 = -v0;
-        for (int i = v0; i <= v1; i++) {
-            pv[3 * (i + v1) + 0] = std::sin((float)i * ang);
-            pv[3 * (i + v1) + 1] = 0.f;
-            pv[3 * (i + v1) + 2] = std::cos((float)i * ang);
-        }
-    }
+    make_planes0(cfg, mc.Nh, mc.Nv, m->planes0);  // boundary-plane normals in the sensor frame (:563-578)
     // neighbour table (:1128-1147; mn:1135-1136)
     m->nbr.assign(P * mc.NBW, 0);
     for (int p = 0; p < mc.P; p++) {
@@ -897,6 +899,47 @@ int dspmap_profile_read(dspmap *m, const char **names, float *ms, int32_t *launc
         launches[i] = m->prof_n[i];
     }
     return n;
+}
+
+struct dspmap_estimator {
+    MapConst mc;
+    int model;
+    std::vector<float> planes0, tagged;
+    VelocityEstimator est;
+};
+dspmap_estimator *dspmap_estimator_create(const dspmap_config *cfg, float filter_res) {
+    dspmap_estimator *e = new dspmap_estimator();
+    memset(&e->mc, 0, sizeof(e->mc));
+    e->mc.Nh = cfg->half_fov_h * 2 / cfg->angle_resolution;
+    e->mc.Nv = cfg->half_fov_v * 2 / cfg->angle_resolution;
+    e->model = cfg->model;
+    make_planes0(cfg, e->mc.Nh, e->mc.Nv, e->planes0);
+    e->est.reset(cfg->uniform_seed);
+    e->est.filter_res = filter_res;
+    return e;
+}
+void dspmap_estimator_destroy(dspmap_estimator *e) { delete e; }
+int dspmap_estimator_estimate(dspmap_estimator *e, int n, const float *pts, float px, float py, float pz, float dt,
+                              float qw, float qx, float qy, float qz, float *out, int cap) {
+    FrameConst fc;
+    memset(&fc, 0, sizeof(fc));
+    fc.q[0] = qw; fc.q[1] = qx; fc.q[2] = qy; fc.q[3] = qz;
+    dsp_quat_inverse(fc.q, fc.qi);
+    fc.cur[0] = px; fc.cur[1] = py; fc.cur[2] = pz;
+    fc.dt = dt;
+    size_t before = e->tagged.size();
+    std::vector<float> prev;
+    prev.swap(e->tagged);
+    e->tagged.assign(1, -12345.f);  // sentinel: estimate() leaves the vector untouched when nothing is in view
+    e->est.estimate(e->mc, fc, e->planes0.data(), pts, n, e->model, e->tagged);
+    if (e->tagged.size() == 1 && e->tagged[0] == -12345.f) {
+        e->tagged.swap(prev);
+        (void)before;
+        return -1;
+    }
+    int nt = (int)(e->tagged.size() / 7);
+    if (out) memcpy(out, e->tagged.data(), sizeof(float) * 7 * (size_t)std::min(nt, cap));
+    return nt;
 }
 
 }  // extern "C"

@@ -88,6 +88,9 @@ def load_library():
         "dspmap_synchronize": (i, [vp]),
         "dspmap_profile_enable": (i, [vp, i]),
         "dspmap_profile_read": (i, [vp, C.POINTER(C.c_char_p), fp, ip, i]),
+        "dspmap_estimator_create": (vp, [C.POINTER(Config), f]),
+        "dspmap_estimator_destroy": (None, [vp]),
+        "dspmap_estimator_estimate": (i, [vp, i, fp, f, f, f, f, f, f, f, f, fp, i]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)  # AttributeError here = the library does not export what include/dspmap_b200.h declares
@@ -106,6 +109,7 @@ EXPORTED_SYMBOLS = [
     "dspmap_dims", "dspmap_dump_particles", "dspmap_load_particles", "dspmap_dump_voxel_objects",
     "dspmap_dump_observations", "dspmap_dump_pyramid_lists", "dspmap_cursors", "dspmap_set_cursors", "dspmap_counters",
     "dspmap_set_stage_limit", "dspmap_set_last_pose", "dspmap_set_stream", "dspmap_synchronize", "dspmap_profile_enable", "dspmap_profile_read",
+    "dspmap_estimator_create", "dspmap_estimator_destroy", "dspmap_estimator_estimate",
 ]
 
 
@@ -323,6 +327,34 @@ class DSPMap:
     def get_occupancy_device(self, threshold, d_xyz, cap, d_count, d_future):
         return self._check(self.lib.dspmap_get_occupancy_device(self.h, threshold, C.c_void_p(d_xyz), cap,
                                                                 C.c_void_p(d_count), C.c_void_p(d_future)))
+
+
+class VelocityEstimator:
+    """Host-only velocity estimation (the reference's side thread, dsp_dynamic.h:1377-1544); needs no GPU."""
+
+    def __init__(self, cfg, seed=1, filter_res=0.1):
+        self.lib = load_library()
+        self.config = make_config(cfg, seed)
+        self.h = C.c_void_p(self.lib.dspmap_estimator_create(C.byref(self.config), filter_res))
+        self.last_t = None
+        self.cap = 1 << 16
+
+    def estimate(self, pts, pos, t, quat):
+        """Returns the tagged cloud (n x 7) of this frame, or None when no point is in view."""
+        pts = np.ascontiguousarray(pts, np.float32)
+        dt = np.float32(0.0) if self.last_t is None else np.float32(float(t) - float(self.last_t))
+        self.last_t = t
+        out = np.zeros((max(len(pts), 1), 7), np.float32)
+        n = self.lib.dspmap_estimator_estimate(self.h, len(pts), _fp(pts), float(pos[0]), float(pos[1]), float(pos[2]),
+                                               float(dt), float(quat[0]), float(quat[1]), float(quat[2]), float(quat[3]),
+                                               _fp(out), out.shape[0])
+        return None if n < 0 else out[:n].copy()
+
+    def __del__(self):
+        try:
+            self.lib.dspmap_estimator_destroy(self.h)
+        except Exception:
+            pass
 
 
 def bytes_per_update(counters, V, T, M):

@@ -150,6 +150,17 @@ int dspmap_synchronize(dspmap *m);
 int dspmap_profile_enable(dspmap *m, int on);
 int dspmap_profile_read(dspmap *m, const char **names, float *ms, int32_t *launches, int cap);
 
+/* Host-only access to the velocity-estimation step (the reference's side thread, dsp_dynamic.h:1377-1544; static variant
+ * dsp_static.h:1285-1309) without a map or a GPU: used to pre-compute newborn inputs for device-resident streams and
+ * by the CPU tests.  `estimate` consumes one frame (n x 3 points, sensor frame) and writes the tagged cloud (7 floats
+ * per point, world frame); it returns the number of points, or -1 when nothing is in view (the previous cloud stays
+ * valid, :1379). */
+typedef struct dspmap_estimator dspmap_estimator;
+dspmap_estimator *dspmap_estimator_create(const dspmap_config *cfg, float voxel_filter_resolution);
+void dspmap_estimator_destroy(dspmap_estimator *e);
+int dspmap_estimator_estimate(dspmap_estimator *e, int n, const float *pts, float px, float py, float pz, float dt,
+                              float qw, float qx, float qy, float qz, float *out, int cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -61,6 +61,8 @@ def build(name):
     so = os.path.join(OUT, "libdspref_%s.so" % name)
     V = cfg["nx"] * cfg["ny"] * cfg["nz"]
     cmd = ["g++", "-std=c++14", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-Wl,-Bsymbolic", "-w",
+           # function-local statics of the reference's inline methods must stay private to each loaded copy
+           "-fno-gnu-unique",
            "-I", os.path.join(ROOT, "oracle", "shim"), '-DREF_HEADER="%s"' % gen]
     if cfg["model"] == "static":
         cmd.append("-DREF_STATIC")

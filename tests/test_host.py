@@ -1,0 +1,83 @@
+"""CPU tests of the host side: the C-ABI library loads and exports everything include/dspmap_b200.h declares, the
+config derivation matches the reference's compile-time arithmetic, and the host velocity estimator reproduces the
+reference's side thread.  No GPU compute calls here."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import dspmap_b200 as dm
+import refmap
+from common import make_stream
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "dspmap_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(dspmap_[a-z_0-9]+)\s*\(", hdr)))
+    assert len(declared) >= 35
+    L = dm.load_library()
+    for s in declared:
+        assert hasattr(L, s), "library does not export %s" % s
+    assert set(dm.EXPORTED_SYMBOLS) <= set(declared)
+
+
+def test_no_cpu_fallback():
+    from conftest import HAS_GPU
+    if HAS_GPU:
+        pytest.skip("GPU present")
+    with pytest.raises(dm.DSPMapError):
+        dm.DSPMap(dm.CONFIGS["tiny_dyn"])
+
+
+def test_product_does_not_touch_the_oracle():
+    for base, _, files in os.walk(os.path.join(ROOT, "dsp-map_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(base, f)).read()
+                for pat in (r"import\s+oracle", r"from\s+oracle", r"refmap", r"liboracle", r"oracle/", r"dsp_oracle", r"_ref\b"):
+                    assert not re.search(pat, src), "%s uses the oracle (%s)" % (f, pat)
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3", "cfg5", "tiny_mn"])
+def test_derived_sizes_match_reference_arithmetic(name):
+    d = dm.derive(dm.CONFIGS[name])
+    expect = {"cfg1": (4000, 40, 504, 36), "cfg2": (174240, 48, 600, 1188), "cfg3": (174240, 48, 5400, 132),
+              "cfg5": (1393920, 72, 600, 13966), "tiny_mn": (2560, 12, 84 * 54, 2)}[name]
+    assert (d["V"], d["S"], d["P"], d["L"]) == expect
+    if refmap.available(name) and name != "cfg5":
+        r = refmap.RefMap(name, seed=1)
+        assert (r.V, r.S, r.P, r.L, r.T) == (d["V"], d["S"], d["P"], d["L"], d["T"])
+
+
+@pytest.mark.parametrize("name,frames", [("tiny_dyn", 10), ("tiny_static", 3), ("cfg1", 3), ("ref_default", 3)])
+def test_host_velocity_estimator_equals_reference_side_thread(name, frames):
+    if not refmap.available(name):
+        pytest.skip("oracle/_ref not built")
+    cfg = dm.CONFIGS[name]
+    st = make_stream(cfg, seed=3, frames=frames)
+    r = refmap.RefMap(name, seed=7)
+    e = dm.VelocityEstimator(cfg, seed=7, filter_res=0.1)
+    dyn = 0
+    for f in range(frames):
+        r.update(st["points"][f], st["pos"][f], st["t"][f], st["quat"][f])
+        a = r.tagged_cloud()
+        b = e.estimate(st["points"][f], st["pos"][f], st["t"][f], st["quat"][f])
+        assert a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32)), "frame %d" % f
+        dyn += int((a[:, 6] > 0.01).sum())
+    if name == "tiny_dyn":
+        assert dyn > 0  # the stream really exercises clustering + matching
+
+
+def test_estimator_keeps_previous_cloud_when_nothing_in_view():
+    cfg = dm.CONFIGS["tiny_dyn"]
+    e = dm.VelocityEstimator(cfg, seed=1)
+    behind = np.array([[-1.0, 0.0, 0.0], [-2.0, 0.1, 0.0]], np.float32)
+    assert e.estimate(behind, (0, 0, 0), 0.0, (1, 0, 0, 0)) is None            # dsp_dynamic.h:1379
+    ahead = np.array([[1.0, 0.0, 0.0]], np.float32)
+    out = e.estimate(ahead, (0.5, 0, 0), 0.1, (1, 0, 0, 0))                   # z <= filter resolution: "ground", static
+    assert out.shape == (1, 7) and np.allclose(out[0], [1.5, 0.0, 0.0, 0, 0, 0, 0])
+    lone = e.estimate(ahead, (0, 0, 1.0), 0.2, (1, 0, 0, 0))                  # above ground, cluster of 1 < 5: dropped
+    assert lone.shape == (0, 7)
