@@ -1,0 +1,64 @@
+"""The drop-in headers (include/dsp_dynamic.h, dsp_dynamic_multiple_neighbors.h, dsp_static.h) compile against the
+application-side code pattern of src/map_sim_example.cpp and, on a GPU, produce the reference's outputs."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+import dspmap_b200 as dm
+import refmap
+from common import make_stream
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BUILD = os.path.join(ROOT, "tests", "_build")
+
+
+def build(header):
+    os.makedirs(BUILD, exist_ok=True)
+    exe = os.path.join(BUILD, "dropin_" + header.replace(".h", ""))
+    cmd = ["g++", "-std=c++14", "-O1", "-w", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "oracle", "shim"),
+           '-DDSPMAP_HEADER="%s"' % header, os.path.join(ROOT, "tests", "dropin_main.cpp"), "-o", exe,
+           "-L", os.path.join(ROOT, "dsp-map_b200", "lib"), "-ldspmap_b200", "-Wl,-rpath," + os.path.join(ROOT, "dsp-map_b200", "lib"),
+           "-lpthread", "-ldl", "-lrt"]
+    subprocess.check_call(cmd)
+    return exe
+
+
+@pytest.mark.parametrize("header", ["dsp_dynamic.h", "dsp_dynamic_multiple_neighbors.h", "dsp_static.h"])
+def test_dropin_headers_compile_and_link(header):
+    dm.load_library()
+    assert os.path.exists(build(header))
+
+
+@pytest.mark.gpu
+def test_dropin_application_matches_reference():
+    """dsp_dynamic.h as shipped (66x66x40, 9 ppv) == config 'ref_default'."""
+    name = "ref_default"
+    if not refmap.available(name):
+        pytest.skip("reference library not present")
+    exe = build("dsp_dynamic.h")
+    cfg = dm.CONFIGS[name]
+    F = 3
+    st = make_stream(cfg, seed=2, frames=F)
+    path = os.path.join(BUILD, "stream.bin")
+    with open(path, "wb") as f:
+        f.write(struct.pack("i", F))
+        for k in range(F):
+            f.write(struct.pack("i", int(st["n"][k])))
+            f.write(st["pos"][k].astype(np.float32).tobytes() + st["quat"][k].astype(np.float32).tobytes())
+            f.write(struct.pack("d", float(st["t"][k])))
+            f.write(st["points"][k].astype(np.float32).tobytes())
+    out = subprocess.check_output([exe, path], text=True)
+    lines = [l for l in out.splitlines() if l.startswith("frame ")]
+    assert len(lines) == F
+    # same seeds as the header's default would be time(): compare the deterministic parts against the reference run
+    r = refmap.RefMap(name, seed=1)
+    for k in range(F):
+        r.update(st["points"][k], st["pos"][k], st["t"][k], st["quat"][k])
+        xyz, fut = r.occupancy(0.2)
+        tok = lines[k].split()
+        assert int(tok[5]) == len(xyz)                      # cloud size == occupied count
+        assert int(tok[9]) == len(r.tagged_cloud())         # getKMClusterResult size
+        assert abs(int(tok[3]) - len(xyz)) <= max(3, len(xyz) // 50)  # different noise seeds (time-seeded): statistically equal
