@@ -50,6 +50,9 @@ struct dspmap {
     float nb_weight = 0.04f;                                                        // :162
     int nb_num = 20;                                                                // :163
     bool tables_dirty = true;
+    bool sigma_dirty = true;  // the fast division by sigma must be re-verified
+    int fast_sigma = 0;
+    int *d_bad = nullptr;
     bool have_last = false;
     float last_p[3] = {0, 0, 0};
     double last_t = 0;
@@ -220,6 +223,22 @@ int seed_particles(dspmap *m) {
     return upload_particles(m, ids.data(), vals.data(), (int)ids.size() / 2);
 }
 
+// Enables dsp_div_known for divisor b only if it equals IEEE division bit for bit on every float in [-amax, amax].
+int verify_fast_div(dspmap *m, float b, float amax, int *ok) {
+    *ok = 0;
+    if (!(b > 0.f) || !(amax > 0.f) || !std::isfinite(b) || !std::isfinite(amax)) return DSPMAP_OK;
+    unsigned max_bits;
+    memcpy(&max_bits, &amax, 4);
+    const float r = 1.f / b;
+    CK(cudaMemsetAsync(m->d_bad, 0, sizeof(int), m->stream));
+    k_verify_div<<<kSMs * 16, 256, 0, m->stream>>>(b, r, max_bits, m->d_bad);
+    int bad = 1;
+    CK(cudaMemcpyAsync(&bad, m->d_bad, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    *ok = bad == 0;
+    return DSPMAP_OK;
+}
+
 int ensure_cand_capacity(dspmap *m) {
     int need = m->max_points * std::max(m->nb_num, 1);
     if (need <= m->cap_cand) return DSPMAP_OK;
@@ -245,7 +264,7 @@ int enqueue_frame_a(dspmap *m, const FrameConst &fc, const float *d_pts) {
     if (fc.n_points > 0) {
         LAUNCH(m, FAM_OBS, k_obs_classify, grid_for(fc.n_points, B), B, 0, mc, fc, dp);
     }
-    LAUNCH(m, FAM_OBS, k_scan_small, 1, 1024, 0, dp.obs_cnt, dp.obs_off, dp.obs_capoff, mc.OBS - 1, mc.P);
+    LAUNCH(m, FAM_OBS, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{dp.obs_cnt, dp.obs_off, dp.obs_capoff, mc.OBS - 1, mc.P}, ScanJob{}, ScanJob{}}});
     if (fc.n_points > 0) {
         LAUNCH(m, FAM_OBS, k_obs_scatter, grid_for(fc.n_points, B), B, 0, mc, fc, dp);
         LAUNCH(m, FAM_OBS, k_obs_rank, grid_for(fc.n_points, B), B, 0, mc, fc, dp);
@@ -254,7 +273,7 @@ int enqueue_frame_a(dspmap *m, const FrameConst &fc, const float *d_pts) {
     if (fc.vz_mode) {
         LAUNCH(m, FAM_PREDICT, k_vz_count, grid_for(mc.V, B), B, 0, mc, dp);
         LAUNCH(m, FAM_PREDICT, k_scan_blocksum, m->vz_blocks, 256, 0, dp.vzcnt, mc.V, dp.vzblk);
-        LAUNCH(m, FAM_PREDICT, k_scan_small, 1, 1024, 0, dp.vzblk, dp.vzblkoff, (int *)nullptr, 0, m->vz_blocks);
+        LAUNCH(m, FAM_PREDICT, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{dp.vzblk, dp.vzblkoff, nullptr, 0, m->vz_blocks}, ScanJob{}, ScanJob{}}});
         LAUNCH(m, FAM_PREDICT, k_scan_apply, m->vz_blocks, 256, 0, dp.vzcnt, mc.V, dp.vzblkoff, dp.vzoff, m->vz_blocks);
     }
     LAUNCH(m, FAM_ENUM, k_enumerate, grid_for(mc.V, B), B, 0, mc, dp, 1);
@@ -263,15 +282,30 @@ int enqueue_frame_a(dspmap *m, const FrameConst &fc, const float *d_pts) {
     LAUNCH(m, FAM_ARRIVE, k_group_owner, kSMs * 2, B, 0, dp, &dp.st->n_mov_owner, dp.mowner, dp.mcnt, dp.mbase, &dp.st->mov_top);
     LAUNCH(m, FAM_ARRIVE, k_group_scatter, kSMs * 4, B, 0, &dp.st->n_mov, dp.MBdst, dp.MBkey, dp.mbase, dp.mfill, dp.mseg);
     LAUNCH(m, FAM_ARRIVE, k_arrive, kSMs * 4, B, 0, mc, fc, dp);
-    LAUNCH(m, FAM_PYRAMID, k_scan_small, 1, 1024, 0, dp.pcount, dp.poff, (int *)nullptr, 0, mc.P);
+    LAUNCH(m, FAM_PYRAMID, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{dp.pcount, dp.poff, nullptr, 0, mc.P}, ScanJob{}, ScanJob{}}});
     LAUNCH(m, FAM_PYRAMID, k_pyr_scatter, kSMs * 8, B, 0, dp);
-    LAUNCH(m, FAM_PYRAMID, k_pyr_sort, std::min(mc.P, kSMs * 3), 512, PYR_SORT_CAP * sizeof(u64), mc, dp);
+    LAUNCH(m, FAM_PYRAMID, k_pyr_sort, std::min(mc.P, kSMs * 3), 512, PYR_SORT_CAP * sizeof(u64), mc, dp, fc.Pd);
     if (fc.stage_limit >= 2) {
+        LAUNCH(m, FAM_CK, k_pair_prep, grid_for(mc.P, B), B, 0, mc, dp);
+        LAUNCH(m, FAM_CK, k_scan_small, 2, 1024, 0, ScanJobs{{ScanJob{dp.pairs, dp.rowbase, nullptr, 0, mc.P}, ScanJob{dp.chunks, dp.chunk_off, nullptr, 0, mc.P}, ScanJob{}}});
+        LAUNCH(m, FAM_CK, k_pair_decide, 1, 32, 0, mc, dp);
+        LAUNCH(m, FAM_CK, k_pair_eval, kSMs * 2, EVAL_THREADS, sizeof(float) * (DSP_LUT_HALF + 3 + (EVAL_THREADS / 32) * 32 * TILE_LD), mc, fc, dp);
+        LAUNCH(m, FAM_CK, k_cz_chain, std::min(mc.P, kSMs * 6), CZ_THREADS, 0, mc, fc, dp);
         size_t smem4 = sizeof(float) * (DSP_LUT_HALF + 3 + K4_TERMS) + sizeof(float4) * (256 + mc.OBS);
-        LAUNCH(m, FAM_CK, k_ck, std::min(mc.P, kSMs * 2), K4_THREADS, smem4, mc, fc, dp);
+        LAUNCH(m, FAM_CK, k_ck, std::min(mc.P, kSMs * 2), K4_THREADS, smem4, mc, fc, dp);  // fallback: returns at once when the pair buffer is used
+        if (fc.stage_limit >= 3) {  // the newborn normaliser is one long serial chain: run it beside the weight pass
+            CK(cudaEventRecord(m->ev_fork, m->stream));
+            CK(cudaStreamWaitEvent(m->side, m->ev_fork, 0));
+            k_norm<<<1, 128, 0, m->side>>>(mc, fc, dp);
+            ++m->launches_total;
+            ++m->launches_frame;
+            CK(cudaEventRecord(m->ev_join, m->side));
+        }
+        LAUNCH(m, FAM_WEIGHT, k_weight2, kSMs * 6, W2_THREADS, 0, mc, fc, dp);
         size_t smem5 = sizeof(float) * (DSP_LUT_HALF + 3) + sizeof(float4) * (size_t)mc.NB * (mc.OBS - 1);
         int chunks = (mc.L + K5_THREADS - 1) / K5_THREADS;
-        LAUNCH(m, FAM_WEIGHT, k_weight, kSMs * 2, K5_THREADS, smem5, mc, fc, dp, chunks);
+        LAUNCH(m, FAM_WEIGHT, k_weight, kSMs * 2, K5_THREADS, smem5, mc, fc, dp, chunks);  // fallback
+        if (fc.stage_limit >= 3) CK(cudaStreamWaitEvent(m->stream, m->ev_join, 0));
     }
     CK(cudaGetLastError());
     return DSPMAP_OK;
@@ -283,13 +317,12 @@ int enqueue_frame_b(dspmap *m, const FrameConst &fc, const float *d_tagged) {
     dp.tagged = d_tagged;
     const int B = 256;
     if (fc.stage_limit >= 3) {
-        LAUNCH(m, FAM_NORM, k_norm, 1, 128, 0, mc, fc, dp);
         if (fc.n_tagged > 0 && fc.nb_num > 0) {
             LAUNCH(m, FAM_NEWBORN, k_nb_point0, grid_for(fc.n_tagged, B), B, 0, mc, fc, dp);
-            LAUNCH(m, FAM_NEWBORN, k_scan_small, 1, 1024, 0, dp.ninmap, dp.nrank, (int *)nullptr, 0, fc.n_tagged);
+            LAUNCH(m, FAM_NEWBORN, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{dp.ninmap, dp.nrank, nullptr, 0, fc.n_tagged}, ScanJob{}, ScanJob{}}});
+            LAUNCH(m, FAM_NEWBORN, k_nb_mask, grid_for((long long)fc.n_tagged * fc.nb_num, B), B, 0, mc, fc, dp);
             LAUNCH(m, FAM_NEWBORN, k_nb_point1, grid_for(fc.n_tagged, 128), 128, 0, mc, fc, dp);
-            LAUNCH(m, FAM_NEWBORN, k_scan_small, 1, 1024, 0, dp.nvcnt, dp.nvoff, (int *)nullptr, 0, fc.n_tagged);
-            LAUNCH(m, FAM_NEWBORN, k_scan_small, 1, 1024, 0, dp.nrcnt, dp.nroff, (int *)nullptr, 0, fc.n_tagged);
+            LAUNCH(m, FAM_NEWBORN, k_scan_small, 2, 1024, 0, ScanJobs{{ScanJob{dp.nvcnt, dp.nvoff, nullptr, 0, fc.n_tagged}, ScanJob{dp.nrcnt, dp.nroff, nullptr, 0, fc.n_tagged}, ScanJob{}}});
             LAUNCH(m, FAM_NEWBORN, k_nb_cand, grid_for((long long)fc.n_tagged * fc.nb_num, B), B, 0, mc, fc, dp, (u64)m->cfg.uniform_seed);
             LAUNCH(m, FAM_NEWBORN, k_group_owner, kSMs * 2, B, 0, dp, &dp.st->n_cand_owner, dp.cowner, dp.ccnt, dp.cbase, &dp.st->cand_top);
             LAUNCH(m, FAM_NEWBORN, k_group_scatter, kSMs * 4, B, 0, &dp.st->n_cand, dp.Cdst, dp.Ckey, dp.cbase, dp.cfill, dp.cseg);
@@ -298,7 +331,8 @@ int enqueue_frame_b(dspmap *m, const FrameConst &fc, const float *d_tagged) {
         }
     }
     if (fc.stage_limit >= 4) {
-        LAUNCH(m, FAM_RESAMPLE, k_resample, grid_for(mc.V, 128), 128, 0, mc, fc, dp);
+        LAUNCH(m, FAM_RESAMPLE, k_voxel_list, grid_for(mc.V, B), B, 0, mc, dp);
+        LAUNCH(m, FAM_RESAMPLE, k_resample, kSMs * 8, 256, 0, mc, fc, dp);
     }
     LAUNCH(m, FAM_CLEANUP, k_cleanup, kSMs * 2, B, 0, dp);
     CK(cudaGetLastError());
@@ -338,6 +372,8 @@ int frame_prologue(dspmap *m, int n, float px, float py, float pz, double t, flo
     fc->dt = dt;
     fc->cur[0] = px; fc->cur[1] = py; fc->cur[2] = pz;
     fc->sigma = m->sigma_ob;
+    fc->sigma_r = 1.f / m->sigma_ob;
+    fc->fast_sigma = m->fast_sigma;
     fc->Pd = m->Pd;
     fc->one_minus_Pd = 1 - m->Pd;
     fc->kappa = m->kappa;
@@ -492,11 +528,14 @@ int dspmap_create(const dspmap_config *cfg, dspmap **out) {
     A(dp.MBA, CL); A(dp.MBB, CL); A(dp.MBkey, CL); A(dp.MBdst, CL); A(dp.MBq, CL);
     A(dp.mcnt, V); A(dp.mfill, V); A(dp.mbase, V); A(dp.mowner, V); A(dp.mseg, CL);
     A(dp.Fkey, CL); A(dp.Faddr, CL); A(dp.Fq, CL); A(dp.pcount, P); A(dp.pfill, P); A(dp.poff, P + 1); A(dp.plen, P);
-    A(dp.PSkey, CL); A(dp.PSaddr, CL); A(dp.LA, CL); A(dp.LP, CL);
+    A(dp.PSkey, CL); A(dp.PSaddr, CL); A(dp.LA, CL); A(dp.LP, CL); A(dp.PW, CL);
+    mc.cap_pairs = 128ll << 20;  // 512 MB of fp32 pair terms; larger frames fall back to the recompute kernels
+    A(dp.G, (size_t)mc.cap_pairs); A(dp.cum, P * mc.NBW); A(dp.totlen, P); A(dp.pairs, P + 1); A(dp.rowbase, P + 1);
+    A(dp.chunks, P + 1); A(dp.chunk_off, P + 1);
     A(dp.NPC, MP); A(dp.ninmap, MP + 1); A(dp.nrank, MP + 1); A(dp.nstatic, MP); A(dp.nvcnt, MP + 1); A(dp.nrcnt, MP + 1);
     A(dp.nvoff, MP + 1); A(dp.nroff, MP + 1); A(dp.nimask, MP);
     A(dp.ccnt, V); A(dp.cfill, V); A(dp.cbase, V); A(dp.cowner, V);
-    A(dp.st, 1);
+    A(dp.st, 1); A(m->d_bad, 1);
     float *d_ptab, *d_vtab, *d_lut, *d_planes0, *d_pts, *d_tagged;
     int *d_nbr;
     A(d_ptab, mc.G); A(d_vtab, mc.G); A(d_lut, DSP_LUT_HALF); A(d_planes0, 3 * (mc.Nh + mc.Nv + 2)); A(dp.planes, 3 * (mc.Nh + mc.Nv + 2));
@@ -551,9 +590,16 @@ int dspmap_create(const dspmap_config *cfg, dspmap **out) {
     CK(cudaMemcpyAsync(d_nbr, m->nbr.data(), sizeof(int) * m->nbr.size(), cudaMemcpyHostToDevice, m->stream));
     CK(cudaFuncSetAttribute(k_pyr_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PYR_SORT_CAP * sizeof(u64))));
     CK(cudaFuncSetAttribute(k_ck, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CK(cudaFuncSetAttribute(k_pair_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     CK(cudaFuncSetAttribute(k_weight, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaStreamSynchronize(m->stream));
     if (gen_tables(m) != DSPMAP_OK) { dspmap_destroy(m); return DSPMAP_E_CUDA; }
+    {   // (p + half) / res with p inside the map: dividends lie in (0, 2*half)
+        mc.res_r = 1.f / mc.res;
+        int ok = 0;
+        if (verify_fast_div(m, mc.res, 2.f * std::max(mc.hx, std::max(mc.hy, mc.hz)) * 1.0001f, &ok) != DSPMAP_OK) { dspmap_destroy(m); return DSPMAP_E_CUDA; }
+        mc.fast_res = ok;
+    }
     m->estimator.reset(cfg->uniform_seed);
     rc = seed_particles(m);
     if (rc != DSPMAP_OK) { dspmap_destroy(m); return rc; }
@@ -597,6 +643,11 @@ static int update_common(dspmap *m, int n, int stride, const float *pts, float p
     int rc = frame_prologue(m, n, px, py, pz, t, qw, qx, qy, qz, &fc);
     if (rc != DSPMAP_OK) return rc;
     if (m->tables_dirty && (rc = gen_tables(m)) != DSPMAP_OK) return rc;
+    if (m->sigma_dirty) {  // queries are clamped to |x - mu| / sigma <= 9.9: beyond 16 sigma both divisions clamp alike
+        if ((rc = verify_fast_div(m, m->sigma_ob, 16.f * m->sigma_ob, &m->fast_sigma)) != DSPMAP_OK) return rc;
+        m->sigma_dirty = false;
+        fc.fast_sigma = m->fast_sigma;
+    }
     if ((rc = ensure_cand_capacity(m)) != DSPMAP_OK) return rc;
     for (int i = 0; i < n; ++i) {
         m->h_pts[3 * i] = pts[(size_t)i * stride];
@@ -647,6 +698,11 @@ int dspmap_update_device(dspmap *m, int n, const float *d_pts, float px, float p
     int rc = frame_prologue(m, n, px, py, pz, t, qw, qx, qy, qz, &fc);
     if (rc != DSPMAP_OK) return rc;
     if (m->tables_dirty && (rc = gen_tables(m)) != DSPMAP_OK) return rc;
+    if (m->sigma_dirty) {  // queries are clamped to |x - mu| / sigma <= 9.9: beyond 16 sigma both divisions clamp alike
+        if ((rc = verify_fast_div(m, m->sigma_ob, 16.f * m->sigma_ob, &m->fast_sigma)) != DSPMAP_OK) return rc;
+        m->sigma_dirty = false;
+        fc.fast_sigma = m->fast_sigma;
+    }
     if ((rc = ensure_cand_capacity(m)) != DSPMAP_OK) return rc;
     fc.n_tagged = n_tagged;
     if ((rc = enqueue_frame_a(m, fc, d_pts)) != DSPMAP_OK) return rc;
@@ -662,7 +718,12 @@ int dspmap_set_prediction_variance(dspmap *m, float p, float v) {
     m->tables_dirty = true;  // regenerated before the next frame (cursors are kept, :355-360)
     return DSPMAP_OK;
 }
-int dspmap_set_observation_stddev(dspmap *m, float s) { if (!m) return DSPMAP_E_BAD_ARG; m->sigma_ob = s; return DSPMAP_OK; }
+int dspmap_set_observation_stddev(dspmap *m, float s) {
+    if (!m) return DSPMAP_E_BAD_ARG;
+    m->sigma_ob = s;
+    m->sigma_dirty = true;
+    return DSPMAP_OK;
+}
 int dspmap_set_newborn_weight(dspmap *m, float w) { if (!m) return DSPMAP_E_BAD_ARG; m->nb_weight = w; return DSPMAP_OK; }
 int dspmap_set_newborn_number(dspmap *m, int n) {
     if (!m || n < 0 || n > DSP_MAX_NB_NUM) { g_err = "newborn number must be in [0, 64]"; return DSPMAP_E_BAD_ARG; }
@@ -682,7 +743,7 @@ int dspmap_get_occupancy_device(dspmap *m, float thr, float *d_xyz, int cap, int
     if (!m) return DSPMAP_E_BAD_ARG;
     const MapConst &mc = m->mc;
     LAUNCH(m, FAM_READER, k_occ_count, m->occ_blocks, 256, 0, mc, m->dp, thr, m->d_blockcnt, d_future);
-    LAUNCH(m, FAM_READER, k_scan_small, 1, 1024, 0, m->d_blockcnt, m->d_blockoff, (int *)nullptr, 0, m->occ_blocks);
+    LAUNCH(m, FAM_READER, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{m->d_blockcnt, m->d_blockoff, nullptr, 0, m->occ_blocks}, ScanJob{}, ScanJob{}}});
     LAUNCH(m, FAM_READER, k_occ_write, m->occ_blocks, 256, 0, mc, m->dp, thr, m->d_blockoff, d_xyz, cap, d_count, m->occ_blocks);
     CK(cudaGetLastError());
     return DSPMAP_OK;

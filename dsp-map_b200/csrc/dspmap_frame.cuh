@@ -1,5 +1,6 @@
 // dspmap_frame.cuh — the kernels of one map update, in pipeline order (product code, sm_100a).
 #pragma once
+#include <cuda_pipeline.h>
 #include "dspmap_kernels.cuh"
 
 // ------------------------------------------------------------------------------------------------------------
@@ -23,6 +24,10 @@ __global__ void k_frame_setup(MapConst mc, FrameConst fc, DevPtrs dp) {
         s->n_inmap_points = s->n_vdraw = s->n_rdraw = 0;
         s->n_inexact = 0;
         s->n_vz = s->n_skipped = 0;
+        s->n_occ_voxels = 0;
+        s->work_eval = s->work_w2 = 0;
+        s->total_pairs = 0ull;
+        s->use_store = 0;
         s->work_k4 = s->work_k5 = 0;
         s->norm = 0.f;
         s->w_new = 0.f;
@@ -67,34 +72,42 @@ __global__ void k_obs_classify(MapConst mc, FrameConst fc, DevPtrs dp) {
     }
 }
 
-// single-block exclusive scan of a small int array; optionally a second scan of min(x, cap)
-__global__ void k_scan_small(const int *in, int *out, int *out_capped, int cap, int n) {
-    __shared__ int ssum[1024], scap[1024];
-    int per = (n + blockDim.x - 1) / blockDim.x;
-    int b = threadIdx.x * per, e = min(n, b + per);
+// single-block exclusive scans of small int arrays (one array per block; blockIdx.x selects the job); optionally a
+// second scan of min(x, cap) of the same input
+struct ScanJob { const int *in; int *out; int *out_capped; int cap; int n; };
+struct ScanJobs { ScanJob j[3]; };
+__global__ void __launch_bounds__(1024) k_scan_small(ScanJobs jobs) {
+    __shared__ int wsum[32], wcap[32];
+    const ScanJob J = jobs.j[blockIdx.x];
+    const int n = J.n, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int per = (n + blockDim.x - 1) / blockDim.x;
+    const int b = threadIdx.x * per, e = min(n, b + per);
     int s = 0, sc = 0;
-    for (int i = b; i < e; ++i) { int x = in[i]; s += x; sc += min(x, cap); }
-    ssum[threadIdx.x] = s;
-    scap[threadIdx.x] = sc;
+    for (int i = b; i < e; ++i) { int x = J.in[i]; s += x; sc += min(x, J.cap); }
+    int incl = s, inclc = sc;
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(FULLMASK, incl, d), tc = __shfl_up_sync(FULLMASK, inclc, d);
+        if (lane >= d) { incl += t; inclc += tc; }
+    }
+    if (lane == 31) { wsum[wid] = incl; wcap[wid] = inclc; }
     __syncthreads();
-    for (int d = 1; d < blockDim.x; d <<= 1) {
-        int a = 0, c = 0;
-        if (threadIdx.x >= d) { a = ssum[threadIdx.x - d]; c = scap[threadIdx.x - d]; }
-        __syncthreads();
-        ssum[threadIdx.x] += a;
-        scap[threadIdx.x] += c;
-        __syncthreads();
+    if (wid == 0) {
+        int x = wsum[lane], xc = wcap[lane], y = x, yc = xc;
+        for (int d = 1; d < 32; d <<= 1) {
+            int t = __shfl_up_sync(FULLMASK, y, d), tc = __shfl_up_sync(FULLMASK, yc, d);
+            if (lane >= d) { y += t; yc += tc; }
+        }
+        wsum[lane] = y - x;  // exclusive prefix of the warp totals
+        wcap[lane] = yc - xc;
+        if (lane == 31) { J.out[n] = y; if (J.out_capped) J.out_capped[n] = yc; }
     }
-    int run = ssum[threadIdx.x] - s, runc = scap[threadIdx.x] - sc;
+    __syncthreads();
+    int run = wsum[wid] + incl - s, runc = wcap[wid] + inclc - sc;
     for (int i = b; i < e; ++i) {
-        int x = in[i];
-        out[i] = run;
+        int x = J.in[i];
+        J.out[i] = run;
         run += x;
-        if (out_capped) { out_capped[i] = runc; runc += min(x, cap); }
-    }
-    if (threadIdx.x == blockDim.x - 1) {
-        out[n] = ssum[threadIdx.x];
-        if (out_capped) out_capped[n] = scap[threadIdx.x];
+        if (J.out_capped) { J.out_capped[i] = runc; runc += min(x, J.cap); }
     }
 }
 
@@ -385,7 +398,7 @@ __global__ void k_pyr_scatter(DevPtrs dp) {
 }
 
 #define PYR_SORT_CAP 8192
-__global__ void __launch_bounds__(512) k_pyr_sort(MapConst mc, DevPtrs dp) {
+__global__ void __launch_bounds__(512) k_pyr_sort(MapConst mc, DevPtrs dp, float Pd) {
     extern __shared__ u64 skey[];  // PYR_SORT_CAP entries: (sweep key << 32) | slot address
     for (int q = blockIdx.x; q < mc.P; q += gridDim.x) {
         const int n = dp.pcount[q], b = dp.poff[q];
@@ -413,8 +426,10 @@ __global__ void __launch_bounds__(512) k_pyr_sort(MapConst mc, DevPtrs dp) {
             for (int i = threadIdx.x; i < n; i += blockDim.x) {
                 int a = (int)(unsigned)(skey[i] & 0xffffffffull);
                 if (i < keep) {
+                    const float4 pa = dp.PA[a];
                     dp.LA[b + i] = a;
-                    dp.LP[b + i] = dp.PA[a];
+                    dp.LP[b + i] = pa;
+                    dp.PW[b + i] = Pd * pa.w;
                 } else {  // pyramid full: the particle vanishes and frees its voxel slot (:1256-1259)
                     mask_atomic_clear(dp.M, a / mc.S, a % mc.S);
                     atomicAdd(&dp.st->n_pyramid_full, 1);
@@ -427,8 +442,10 @@ __global__ void __launch_bounds__(512) k_pyr_sort(MapConst mc, DevPtrs dp) {
                 for (int j = 0; j < n; ++j) r += dp.PSkey[b + j] < ki;
                 int a = dp.PSaddr[b + i];
                 if (r < keep) {
+                    const float4 pa = dp.PA[a];
                     dp.LA[b + r] = a;
-                    dp.LP[b + r] = dp.PA[a];
+                    dp.LP[b + r] = pa;
+                    dp.PW[b + r] = Pd * pa.w;
                 } else {
                     mask_atomic_clear(dp.M, a / mc.S, a % mc.S);
                     atomicAdd(&dp.st->n_pyramid_full, 1);
@@ -455,6 +472,7 @@ __global__ void __launch_bounds__(K4_THREADS) k_ck(MapConst mc, FrameConst fc, D
     float4 *ptl = (float4 *)(term + K4_TERMS);  // particle tile, <= 256
     float4 *zs = ptl + 256;                     // points of this pyramid, <= OBS
     __shared__ int s_item;
+    if (dp.st->use_store) return;  // the pair-buffer kernels handle this frame
     for (int i = threadIdx.x; i < DSP_LUT_HALF; i += blockDim.x) lut[i] = dp.lut[i];
     const float enb = fc.nb_weight * (float)dp.st->n_valid * (float)fc.nb_num;  // :292
     const float add_k = enb + fc.kappa;
@@ -511,6 +529,7 @@ __global__ void __launch_bounds__(K5_THREADS) k_weight(MapConst mc, FrameConst f
     float *lut = smem;
     float4 *zs = (float4 *)(lut + DSP_LUT_HALF + 3);  // NB * (OBS-1) staged points: x y z C_z
     __shared__ int s_item;
+    if (dp.st->use_store) return;  // the pair-buffer kernels handle this frame
     for (int i = threadIdx.x; i < DSP_LUT_HALF; i += blockDim.x) lut[i] = dp.lut[i];
     int staged = -1, nz = 0;
     const int items = mc.P * chunks_per_pyr;
@@ -558,9 +577,222 @@ __global__ void __launch_bounds__(K5_THREADS) k_weight(MapConst mc, FrameConst f
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Pair-buffer observation passes.  Every (particle, point) pair with the point's pyramid among the particle's pyramid's
+// neighbours is evaluated ONCE (k_pair_eval) into G; the C_z pass (k_cz_chain) and the weight pass (k_weight2) then add
+// their terms in exactly the reference's order (dsp_dynamic.h:709-739, 743-790).
+//   layout  G[rowbase[i] + z * totlen[i] + j],  i = pyramid of the point, z = its bin index, j = position of the
+//           particle in the concatenation of i's neighbour lists (neighbour-table order, list order)
+//   k_cz_chain reads a row sequentially (j); k_weight2 reads it with consecutive lanes = consecutive particles.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void k_pair_prep(MapConst mc, DevPtrs dp) {
+    unsigned long long local = 0ull;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < mc.P; i += gridDim.x * blockDim.x) {
+        const int np = min(dp.obs_cnt[i], mc.OBS - 1), nn = dp.nbr[i * mc.NBW];
+        int c = 0;
+        for (int ns = 0; ns < nn; ++ns) {
+            dp.cum[i * mc.NBW + ns] = c;
+            c += dp.plen[dp.nbr[i * mc.NBW + 1 + ns]];
+        }
+        dp.totlen[i] = c;
+        const unsigned long long pr = (unsigned long long)np * (unsigned long long)c;
+        dp.pairs[i] = pr > 0x3fffffffull ? 0x3fffffff : (int)pr;
+        local += pr;
+        dp.chunks[i] = (dp.plen[i] + 31) >> 5;
+    }
+    if (local) atomicAdd(&dp.st->total_pairs, local);
+}
+__global__ void k_pair_decide(MapConst mc, DevPtrs dp) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) dp.st->use_store = dp.st->total_pairs <= (unsigned long long)mc.cap_pairs ? 1 : 0;
+}
+// position of pyramid a inside pyramid b's neighbour list (the relation is symmetric)
+__device__ __forceinline__ int nb_index_of(const MapConst &mc, const DevPtrs &dp, int b, int a) {
+    const int nn = dp.nbr[b * mc.NBW];
+    for (int k = 0; k < nn; ++k)
+        if (dp.nbr[b * mc.NBW + 1 + k] == a) return k;
+    return -1;
+}
+__device__ __forceinline__ int chunk_to_pyramid(const int *chunk_off, int P, int c) {  // last a with chunk_off[a] <= c
+    int lo = 0, hi = P;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (chunk_off[mid] <= c) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+#define EVAL_THREADS 512
+#define TILE_LD 33  // per-warp 32 x 32 staging tile, padded
+__global__ void __launch_bounds__(EVAL_THREADS) k_pair_eval(MapConst mc, FrameConst fc, DevPtrs dp) {
+    extern __shared__ float sm[];
+    float *lut = sm;
+    float *tile = sm + (DSP_LUT_HALF + 3) + (threadIdx.x >> 5) * (32 * TILE_LD);
+    if (!dp.st->use_store) return;
+    for (int i = threadIdx.x; i < DSP_LUT_HALF; i += blockDim.x) lut[i] = dp.lut[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int nchunks = dp.chunk_off[mc.P];
+    const int items = nchunks * mc.NB;
+    for (;;) {
+        int it = 0;
+        if (lane == 0) it = atomicAdd(&dp.st->work_eval, 1);
+        it = __shfl_sync(FULLMASK, it, 0);
+        if (it >= items) break;
+        const int c = it / mc.NB, ns = it - c * mc.NB;
+        const int a = chunk_to_pyramid(dp.chunk_off, mc.P, c);
+        if (ns >= dp.nbr[a * mc.NBW]) continue;
+        const int i = dp.nbr[a * mc.NBW + 1 + ns];  // a point pyramid that sees pyramid a
+        const int np = min(dp.obs_cnt[i], mc.OBS - 1);
+        if (np == 0) continue;
+        const int k0 = (c - dp.chunk_off[a]) << 5;
+        const int ln = dp.plen[a];
+        const int nrows = min(32, ln - k0);
+        const float4 p = lane < nrows ? dp.LP[dp.poff[a] + k0 + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+        float *gb = dp.G + (size_t)dp.rowbase[i] + (size_t)(dp.cum[i * mc.NBW + nb_index_of(mc, dp, i, a)] + k0) * np;
+        const float4 *zs = dp.OBSP + (size_t)i * mc.OBS;
+        for (int z0 = 0; z0 < np; z0 += 32) {
+            const int nsub = min(32, np - z0);
+            for (int zl = 0; zl < nsub; ++zl) {
+                const float4 o = zs[z0 + zl];
+                tile[lane * TILE_LD + zl] = dsp_pdf_f(lut, p.x, o.x, fc) * dsp_pdf_f(lut, p.y, o.y, fc) * dsp_pdf_f(lut, p.z, o.z, fc);
+            }
+            __syncwarp();
+            if (lane < nsub)
+                for (int r = 0; r < nrows; ++r) gb[(size_t)r * np + z0 + lane] = tile[r * TILE_LD + lane];
+            __syncwarp();
+        }
+    }
+}
+// C_z (dsp_dynamic.h:709-739): a CTA per point pyramid streams the pyramid's contiguous block of G through shared
+// memory (double-buffered cp.async); thread z < np adds its column in list order: one fp32 chain per point.
+#define CZ_THREADS 128
+#define CZ_TILE 4096
+__global__ void __launch_bounds__(CZ_THREADS) k_cz_chain(MapConst mc, FrameConst fc, DevPtrs dp) {
+    __shared__ float tile[2][CZ_TILE];
+    __shared__ float pws[2][64];
+    __shared__ int s_item;
+    if (!dp.st->use_store) return;
+    const float enb = fc.nb_weight * (float)dp.st->n_valid * (float)fc.nb_num;  // :292
+    const float add_k = enb + fc.kappa;
+    const int tid = threadIdx.x;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_item = atomicAdd(&dp.st->work_k4, 1);
+        __syncthreads();
+        const int i = s_item;
+        if (i >= mc.P) break;
+        const int np = min(dp.obs_cnt[i], mc.OBS - 1);
+        if (np == 0) continue;
+        const int nn = dp.nbr[i * mc.NBW];
+        const int JT = min(64, CZ_TILE / np);
+        const float *gsrc = dp.G + (size_t)dp.rowbase[i];
+        // tile iterator over (neighbour ns, particle offset k0); "issue" state runs one tile ahead of "consume" state
+        int ins = 0, ik0 = 0, iln = nn > 0 ? dp.plen[dp.nbr[i * mc.NBW + 1]] : 0;
+        const float *ig = gsrc;
+        auto issue = [&](int buf) -> int {  // returns the number of particle rows of the issued tile, 0 when exhausted
+            while (ins < nn && ik0 >= iln) {
+                ++ins;
+                ik0 = 0;
+                iln = ins < nn ? dp.plen[dp.nbr[i * mc.NBW + 1 + ins]] : 0;
+            }
+            if (ins >= nn) return 0;
+            const int cur = min(JT, iln - ik0), nfl = cur * np;
+            for (int f = tid; f < nfl; f += CZ_THREADS) __pipeline_memcpy_async(&tile[buf][f], ig + f, 4);
+            if (tid < cur) __pipeline_memcpy_async(&pws[buf][tid], dp.PW + dp.poff[dp.nbr[i * mc.NBW + 1 + ins]] + ik0 + tid, 4);
+            ig += nfl;
+            ik0 += cur;
+            return cur;
+        };
+        float acc = 0.f;
+        int cur = issue(0);
+        __pipeline_commit();
+        int buf = 0;
+        while (cur > 0) {
+            const int nxt = issue(buf ^ 1);
+            __pipeline_commit();
+            __pipeline_wait_prior(1);
+            __syncthreads();
+            if (tid < np) {
+                const float *t = tile[buf] + tid;
+                const float *w = pws[buf];
+#pragma unroll 4
+                for (int jj = 0; jj < cur; ++jj) acc += w[jj] * t[jj * np];
+            }
+            __syncthreads();
+            cur = nxt;
+            buf ^= 1;
+        }
+        __pipeline_wait_prior(0);
+        if (tid < np) {
+            acc += add_k;
+            dp.CZ[i * mc.OBS + tid] = acc;
+            dp.INV[dp.obs_capoff[i] + tid] = 1.f / acc;  // for the newborn normaliser (:802)
+        }
+    }
+}
+// weights (dsp_dynamic.h:743-790): one warp per 32 particles of a pyramid, lanes = particles; the 32 x 32 sub-tiles of G
+// are read as coalesced rows into a per-warp staging tile.
+#define W2_THREADS 256
+__global__ void __launch_bounds__(W2_THREADS) k_weight2(MapConst mc, FrameConst fc, DevPtrs dp) {
+    __shared__ float tiles[(W2_THREADS / 32) * 32 * TILE_LD];
+    if (!dp.st->use_store) return;
+    float *tile = tiles + (threadIdx.x >> 5) * (32 * TILE_LD);
+    const int lane = threadIdx.x & 31;
+    const int nchunks = dp.chunk_off[mc.P];
+    for (;;) {
+        int c = 0;
+        if (lane == 0) c = atomicAdd(&dp.st->work_w2, 1);
+        c = __shfl_sync(FULLMASK, c, 0);
+        if (c >= nchunks) break;
+        const int a = chunk_to_pyramid(dp.chunk_off, mc.P, c);
+        const int k0 = (c - dp.chunk_off[a]) << 5;
+        const int ln = dp.plen[a], lb = dp.poff[a];
+        const int nrows = min(32, ln - k0);
+        bool act = lane < nrows;
+        const float4 p = act ? dp.LP[lb + k0 + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool mine = act;
+        if (act) {
+            const float dist = sqrtf(p.x * p.x + p.y * p.y + p.z * p.z);
+            const float maxlen = __int_as_float(dp.obs_maxbits[a]);
+            if (maxlen > 0.f && dist > maxlen + mc.occl) act = false;  // occluded (:761): weight unchanged
+        }
+        float sum = 0.f;
+        const int nn = dp.nbr[a * mc.NBW];
+        for (int ns = 0; ns < nn; ++ns) {
+            const int b = dp.nbr[a * mc.NBW + 1 + ns];
+            const int np = min(dp.obs_cnt[b], mc.OBS - 1);
+            if (np == 0) continue;
+            const float *gb = dp.G + (size_t)dp.rowbase[b] + (size_t)(dp.cum[b * mc.NBW + nb_index_of(mc, dp, b, a)] + k0) * np;
+            const float *cz = dp.CZ + (size_t)b * mc.OBS;
+            for (int z0 = 0; z0 < np; z0 += 32) {
+                const int nsub = min(32, np - z0);
+                if (lane < nsub)
+                    for (int r = 0; r < nrows; ++r) tile[r * TILE_LD + lane] = gb[(size_t)r * np + z0 + lane];
+                __syncwarp();
+                if (act)
+                    for (int zl = 0; zl < nsub; ++zl) sum += fc.Pd * tile[lane * TILE_LD + zl] / cz[z0 + zl];
+                __syncwarp();
+            }
+        }
+        if (mine && act) dp.PA[dp.LA[lb + k0 + lane]].w = p.w * (fc.one_minus_Pd + sum);
+    }
+}
+// Exhaustive check of dsp_div_known against IEEE division for ONE divisor over every non-negative float up to max_bits
+// (the quotient is odd in the dividend, so the negative half follows).
+__global__ void k_verify_div(float b, float r, unsigned max_bits, int *bad) {
+    int local = 0;
+    for (unsigned long long u = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; u <= max_bits; u += (unsigned long long)gridDim.x * blockDim.x) {
+        const float a = __uint_as_float((unsigned)u);
+        const float q = a / b;
+        const float f = dsp_div_known(a, b, r);
+        const float qn = (-a) / b, fn = dsp_div_known(-a, b, r);
+        if (__float_as_uint(q) != __float_as_uint(f) || __float_as_uint(qn) != __float_as_uint(fn)) ++local;
+    }
+    if (local) atomicAdd(bad, local);
+}
+
 // K6a  newborn normaliser (dsp_dynamic.h:799-805): sum of 1/C_z over (pyramid, bin) order, one fp32 chain.
 __global__ void k_norm(MapConst mc, FrameConst fc, DevPtrs dp) {
-    __shared__ float buf[2][1024];
+    __shared__ __align__(16) float buf[2][1024];
     const int n = dp.obs_capoff[mc.P];
     float acc = 0.f;
     int nchunk = (n + 1023) / 1024;
@@ -574,9 +806,14 @@ __global__ void k_norm(MapConst mc, FrameConst fc, DevPtrs dp) {
                 for (int t = threadIdx.x - 32; t < 1024; t += blockDim.x - 32) buf[nb][t] = b0 + t < n ? dp.INV[b0 + t] : 0.f;
         } else if (threadIdx.x == 0) {
             int cnt = min(1024, n - c * 1024);
-            const float *s = buf[c & 1];
-#pragma unroll 8
-            for (int k = 0; k < cnt; ++k) acc += s[k];
+            const float4 *s4 = reinterpret_cast<const float4 *>(buf[c & 1]);
+            const int c4 = cnt >> 2;
+#pragma unroll 4
+            for (int k = 0; k < c4; ++k) {
+                float4 x = s4[k];
+                acc += x.x; acc += x.y; acc += x.z; acc += x.w;
+            }
+            for (int k = c4 << 2; k < cnt; ++k) acc += buf[c & 1][k];
         }
         __syncthreads();
     }
@@ -597,14 +834,29 @@ __global__ void k_nb_point0(MapConst mc, FrameConst fc, DevPtrs dp) {
         int pv = dsp_voxel_index(mc, cx, cy, cz);
         dp.NPC[m] = make_float4(cx, cy, cz, __int_as_float(pv));
         dp.ninmap[m] = (mc.model == 1) ? 1 : (pv >= 0);
+        dp.nimask[m] = 0ull;
     }
 }
 __device__ __forceinline__ u64 bits_below(int p) { return p >= 64 ? ~0ull : ((1ull << p) - 1ull); }
+// which of a point's nb_num candidates land inside the map (:871-875): one thread per candidate
+__global__ void k_nb_mask(MapConst mc, FrameConst fc, DevPtrs dp) {
+    const int total = fc.n_tagged * fc.nb_num;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        int m = t / fc.nb_num, p = t - m * fc.nb_num;
+        if (!dp.ninmap[m]) continue;
+        float4 pc = dp.NPC[m];
+        long long c = (dp.st->p_cur + 3ll * ((long long)dp.nrank[m] * fc.nb_num + p)) % mc.G;
+        float px = pc.x + dp.ptab[c];
+        float py = pc.y + dp.ptab[(c + 1) % mc.G];
+        float pz = pc.z + dp.ptab[(c + 2) % mc.G];
+        if (dsp_voxel_index(mc, px, py, pz) >= 0) atomicOr(&dp.nimask[m], 1ull << p);
+    }
+}
 // point pass 1: Dempster-Shafer split from the resident particles of the point's voxel (:829-866), which of the
 // nb_num candidates land inside the map (:871-875), and how many table / uniform draws the point consumes.
 __global__ void k_nb_point1(MapConst mc, FrameConst fc, DevPtrs dp) {
     for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < fc.n_tagged; m += gridDim.x * blockDim.x) {
-        if (!dp.ninmap[m]) { dp.nvcnt[m] = 0; dp.nrcnt[m] = 0; dp.nimask[m] = 0ull; continue; }
+        if (!dp.ninmap[m]) { dp.nvcnt[m] = 0; dp.nrcnt[m] = 0; continue; }
         float4 pc = dp.NPC[m];
         int n_static = 0;
         if (mc.model == 0) {
@@ -635,15 +887,7 @@ __global__ void k_nb_point1(MapConst mc, FrameConst fc, DevPtrs dp) {
             n_static = (prod != prod) ? INT_MIN : (int)prod;
             n_static = max(fc.nb_min_static, n_static);
         }
-        long long c0 = dp.st->p_cur + 3ll * ((long long)dp.nrank[m] * fc.nb_num);
-        u64 im = 0ull;
-        for (int p = 0; p < fc.nb_num; ++p) {
-            long long c = (c0 + 3ll * p) % mc.G;
-            float px = pc.x + dp.ptab[c];
-            float py = pc.y + dp.ptab[(c + 1) % mc.G];
-            float pz = pc.z + dp.ptab[(c + 2) % mc.G];
-            if (dsp_voxel_index(mc, px, py, pz) >= 0) im |= 1ull << p;
-        }
+        const u64 im = dp.nimask[m];
         const float *pt = dp.tagged + 7 * m;
         u64 vm = 0ull, rm = 0ull;
         if (mc.model == 0 && pt[6] > 0.01f) {  // only points tagged dynamic draw velocities (:883,:894)
@@ -653,7 +897,6 @@ __global__ void k_nb_point1(MapConst mc, FrameConst fc, DevPtrs dp) {
             rm = nonstatic & ~est;
         }
         dp.nstatic[m] = n_static;
-        dp.nimask[m] = im;
         dp.nvcnt[m] = __popcll(vm);
         dp.nrcnt[m] = __popcll(rm);
     }
@@ -710,9 +953,12 @@ __global__ void k_nb_place(MapConst mc, FrameConst fc, DevPtrs dp) {
     const int n = min(dp.st->n_cand, dp.cap_cand);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         int d = dp.Cdst[i], key = dp.Ckey[i];
+        const ulonglong2 ms = dp.MS[d];
+        const int nfree = mask_free(mc, ms);
         int b = dp.cbase[d], c = dp.ccnt[d], rank = 0;
         for (int j = 0; j < c; ++j) rank += dp.cseg[b + j] < key;
-        int slot = mask_nth_free(mc, dp.MS[d], rank);
+        if (rank >= nfree) continue;
+        int slot = mask_nth_free(mc, ms, rank);
         if (slot < 0) continue;
         int a = d * mc.S + slot;
         dp.PA[a] = dp.CA[i];
@@ -738,97 +984,163 @@ __global__ void k_nb_cursors(MapConst mc, FrameConst fc, DevPtrs dp) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// K7  occupancy, future status and resampling (dsp_dynamic.h:924-1057), one thread per voxel, slots in order.
+// K7a list of occupied voxels (balances K7: occupied voxels are x-adjacent, so a strided sweep would hand one warp up
+//     to 32 of them); empty voxels get their zero occupancy here.
 // ------------------------------------------------------------------------------------------------------------
-__global__ void k_resample(MapConst mc, FrameConst fc, DevPtrs dp) {
-    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < mc.V; v += gridDim.x * blockDim.x) {
-        ulonglong2 msk = dp.M[v];
-        if ((msk.x | msk.y) == 0ull) {
-            dp.OCCV[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-            continue;
+__global__ void k_voxel_list(MapConst mc, DevPtrs dp) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int base = warp * 32; base < mc.V; base += nwarps * 32) {
+        const int v = base + lane;
+        bool occ = false;
+        if (v < mc.V) {
+            const ulonglong2 m = dp.M[v];
+            occ = (m.x | m.y) != 0ull;
+            if (!occ) dp.OCCV[v] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        float wsum = 0.f, sx = 0.f, sy = 0.f, sz = 0.f;
-        int n = 0, n_old = 0, n_low = 0;
-        ulonglong2 live = msk;
-        for (int half = 0; half < 2; ++half) {
-            u64 z = half ? msk.y : msk.x;
-            while (z) {
-                int sb = __ffsll((long long)z) - 1;
-                z &= z - 1;
-                int a = v * mc.S + sb + 64 * half;
-                float4 A = dp.PA[a], B = dp.PB[a];
-                if ((double)A.w < 1e-3) {  // (:941) drop
-                    if (half) live.y &= ~(1ull << sb); else live.x &= ~(1ull << sb);
-                    ++n_low;
-                    continue;
+        const unsigned b = __ballot_sync(FULLMASK, occ);
+        if (b == 0u) continue;
+        int wb = 0;
+        if (lane == 0) wb = atomicAdd(&dp.st->n_occ_voxels, __popc(b));
+        wb = __shfl_sync(FULLMASK, wb, 0);
+        if (occ) dp.E[wb + __popc(b & ((1u << lane) - 1u))] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K7  occupancy, future status and resampling (dsp_dynamic.h:924-1057).  One WARP per occupied voxel: lane l owns
+//     slots l, l+32, l+64, l+96 (coalesced row loads); the order-dependent parts — the fp32 sums in slot order and the
+//     systematic-resampling state machine — are executed warp-uniformly on values broadcast by shuffles.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_resample(MapConst mc, FrameConst fc, DevPtrs dp) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int R = (mc.S + 31) >> 5;
+    int c_pre = 0, c_old = 0, c_out = 0, c_low = 0;
+    const int nocc = dp.st->n_occ_voxels;
+    for (int item = warp; item < nocc; item += nwarps) {
+        {
+            const int v = dp.E[item];  // E is free after prediction: it carries the occupied-voxel list (k_voxel_list)
+            const ulonglong2 mv = dp.M[v];
+            const u64 mx = mv.x, my = mv.y;
+            float4 A[4], B[4];
+            unsigned keep[4], old[4], surv[4];
+            int n_low = 0;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const unsigned live = r < 2 ? (unsigned)(mx >> (32 * r)) : (unsigned)(my >> (32 * (r - 2)));
+                A[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+                B[r] = A[r];
+                const bool mine = r < R && ((live >> lane) & 1u);
+                if (mine) {
+                    const int a = v * mc.S + 32 * r + lane;
+                    A[r] = dp.PA[a];
+                    B[r] = dp.PB[a];
                 }
-                if (B.w < 10.f) {  // not newborn (:944)
-                    ++n_old;
-                    sx += B.x; sy += B.y; sz += B.z;
+                const bool kp = mine && !((double)A[r].w < 1e-3);  // (:941) particles below 1e-3 are dropped
+                keep[r] = __ballot_sync(FULLMASK, kp);
+                old[r] = __ballot_sync(FULLMASK, kp && B[r].w < 10.f);  // not newborn (:944)
+                surv[r] = keep[r];
+                n_low += __popc(live) - __popc(keep[r]);
+            }
+            // sums in slot order (:938-973)
+            float wsum = 0.f, sx = 0.f, sy = 0.f, sz = 0.f;
+            int n = 0, n_old = 0;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                unsigned k = keep[r];
+                n += __popc(k);
+                n_old += __popc(old[r]);
+                while (k) {
+                    const int l = __ffs(k) - 1;
+                    k &= k - 1;
+                    const float w = __shfl_sync(FULLMASK, A[r].w, l);
+                    if ((old[r] >> l) & 1u) {
+                        sx += __shfl_sync(FULLMASK, B[r].x, l);
+                        sy += __shfl_sync(FULLMASK, B[r].y, l);
+                        sz += __shfl_sync(FULLMASK, B[r].z, l);
+                    }
+                    wsum += w;
+                }
+            }
+            // future status of the old particles (:950-964): each lane scatters its own
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                if ((old[r] >> lane) & 1u)
                     for (int t = 0; t < mc.T; ++t) {
-                        float ft = mc.ft[t];
-                        float fx = A.x + B.x * ft, fy = A.y + B.y * ft, fz = A.z + B.z * ft;
-                        int fi = dsp_voxel_index(mc, fx, fy, fz);
-                        if (fi >= 0) atomicAdd(&dp.FUT[(size_t)fi * mc.T + t], A.w);
+                        const float ft = mc.ft[t];
+                        const float fx = A[r].x + B[r].x * ft, fy = A[r].y + B[r].y * ft, fz = A[r].z + B[r].z * ft;
+                        const int fi = dsp_voxel_index(mc, fx, fy, fz);
+                        if (fi >= 0) atomicAdd(&dp.FUT[(size_t)fi * mc.T + t], A[r].w);
                     }
-                }
-                dp.PB[a].w = 1.f;
-                ++n;
-                wsum += A.w;
+            if (lane == 0) {
+                float4 o = make_float4(wsum, 0.f, 0.f, 0.f);
+                if (n_old > 0) { o.y = sx / (float)n_old; o.z = sy / (float)n_old; o.w = sz / (float)n_old; }
+                dp.OCCV[v] = o;
             }
-        }
-        float4 o = make_float4(wsum, 0.f, 0.f, 0.f);
-        if (n_old > 0) { o.y = sx / (float)n_old; o.z = sy / (float)n_old; o.w = sz / (float)n_old; }
-        dp.OCCV[v] = o;
-        int n_out = n;
-        if (n >= 5) {  // (:986)
-            int n_after = n > mc.max_ppv ? mc.max_ppv : n;
-            float w_after = wsum / (float)n_after;
-            float acc_ori = 0.f, acc_new = w_after * 0.5f;
-            ulonglong2 occ = live;        // slots that are not free (kept originals and copies)
-            const ulonglong2 orig = live; // originals, visited in slot order; copies are skipped (:1009)
-            n_out = 0;
-            for (int half = 0; half < 2; ++half) {
-                u64 z = half ? orig.y : orig.x;
-                while (z) {
-                    int sb = __ffsll((long long)z) - 1;
-                    z &= z - 1;
-                    int s = sb + 64 * half, a = v * mc.S + s;
-                    float4 A = dp.PA[a];
-                    acc_ori += A.w;
-                    if (acc_ori > acc_new) {
-                        float wk = w_after;
-                        acc_new += w_after;
-                        bool full = false;
-                        float4 B = dp.PB[a];
-                        while (acc_ori > acc_new) {  // duplicate heavy particles (:1021-1044)
-                            int fs = full ? -1 : mask_nth_free(mc, occ, 0);
-                            if (fs >= 0) {
-                                int ac = v * mc.S + fs;
-                                dp.PA[ac] = make_float4(A.x, A.y, A.z, wk);
-                                dp.PB[ac] = make_float4(B.x, B.y, B.z, 0.6f);
-                                if (fs < 64) occ.x |= 1ull << fs; else occ.y |= 1ull << (fs - 64);
-                                ++n_out;
-                            } else {
-                                wk += w_after;
-                                full = true;
-                            }
+            ulonglong2 occ = make_ulonglong2((u64)keep[0] | ((u64)keep[1] << 32), (u64)keep[2] | ((u64)keep[3] << 32));
+            float nw[4] = {A[0].w, A[1].w, A[2].w, A[3].w};
+            if (n >= 5) {  // (:986) systematic resampling to at most MAX particles, offset 0.5 * w_after, slot order
+                const int n_after = n > mc.max_ppv ? mc.max_ppv : n;
+                const float w_after = wsum / (float)n_after;
+                float acc_ori = 0.f, acc_new = w_after * 0.5f;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    unsigned k = keep[r];
+                    while (k) {
+                        const int l = __ffs(k) - 1;
+                        k &= k - 1;
+                        acc_ori += __shfl_sync(FULLMASK, A[r].w, l);
+                        if (acc_ori > acc_new) {
+                            float wk = w_after;
                             acc_new += w_after;
+                            bool full = false;
+                            while (acc_ori > acc_new) {  // duplicate heavy particles into the first free slot (:1021-1044)
+                                const int fs = full ? -1 : mask_nth_free(mc, occ, 0);
+                                if (fs >= 0) {
+                                    const float x = __shfl_sync(FULLMASK, A[r].x, l), y = __shfl_sync(FULLMASK, A[r].y, l),
+                                                z = __shfl_sync(FULLMASK, A[r].z, l);
+                                    const float vx = __shfl_sync(FULLMASK, B[r].x, l), vy = __shfl_sync(FULLMASK, B[r].y, l),
+                                                vz = __shfl_sync(FULLMASK, B[r].z, l);
+                                    if (lane == 0) {
+                                        dp.PA[v * mc.S + fs] = make_float4(x, y, z, wk);
+                                        dp.PB[v * mc.S + fs] = make_float4(vx, vy, vz, 0.6f);
+                                    }
+                                    if (fs < 64) occ.x |= 1ull << fs; else occ.y |= 1ull << (fs - 64);
+                                } else {
+                                    wk += w_after;
+                                    full = true;
+                                }
+                                acc_new += w_after;
+                            }
+                            if (lane == l) nw[r] = wk;
+                        } else {  // removed (:1046-1050)
+                            const int sl = 32 * r + l;
+                            if (sl < 64) occ.x &= ~(1ull << sl); else occ.y &= ~(1ull << (sl - 64));
+                            surv[r] &= ~(1u << l);
                         }
-                        dp.PA[a].w = wk;
-                        ++n_out;
-                    } else {  // removed (:1046-1050)
-                        if (half) occ.y &= ~(1ull << sb); else occ.x &= ~(1ull << sb);
                     }
                 }
             }
-            live = occ;
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                if ((surv[r] >> lane) & 1u) {
+                    const int a = v * mc.S + 32 * r + lane;
+                    if (nw[r] != A[r].w) dp.PA[a].w = nw[r];
+                    if (B[r].w != 1.f) dp.PB[a].w = 1.f;  // newborn / moved flags become "valid" (:968)
+                }
+            if (lane == 0) dp.M[v] = occ;
+            c_pre += n;
+            c_old += n_old;
+            c_out += mask_popc(occ);
+            c_low += n_low;
         }
-        dp.M[v] = live;
-        atomicAdd(&dp.st->n_pre, n);
-        atomicAdd(&dp.st->n_old, n_old);
-        atomicAdd(&dp.st->n_out, n_out);
-        if (n_low) atomicAdd(&dp.st->n_low_weight, n_low);
+    }
+    if (lane == 0 && (c_pre | c_low)) {
+        atomicAdd(&dp.st->n_pre, c_pre);
+        atomicAdd(&dp.st->n_old, c_old);
+        atomicAdd(&dp.st->n_out, c_out);
+        if (c_low) atomicAdd(&dp.st->n_low_weight, c_low);
     }
 }
 
@@ -844,7 +1156,7 @@ __global__ void k_cleanup(DevPtrs dp) {
 // ------------------------------------------------------------------------------------------------------------
 // K8  readers (dsp_dynamic.h:385-438): ordered compaction of occupied voxel centres, future copy-out + zeroing
 // ------------------------------------------------------------------------------------------------------------
-#define OCC_BLOCK 2048  // voxels per block
+#define OCC_BLOCK 512  // voxels per block
 __global__ void __launch_bounds__(256) k_occ_count(MapConst mc, DevPtrs dp, float thr, int *blockcnt, float *d_future) {
     __shared__ int s;
     if (threadIdx.x == 0) s = 0;

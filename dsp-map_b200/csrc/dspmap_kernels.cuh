@@ -40,6 +40,10 @@ struct DevPtrs {
     int *PSkey, *PSaddr;
     int *LA;            // per-pyramid sorted list: slot address
     float4 *LP;         // per-pyramid sorted list: px py pz weight (post-prediction)
+    float *PW;          // per-pyramid sorted list: P_d * weight
+    // pair buffer: G[rowbase[i] + z * totlen[i] + j] = g(particle j of pyramid i's concatenated neighbour lists; point z of i)
+    float *G;
+    int *cum, *totlen, *pairs, *rowbase, *chunks, *chunk_off;
     // newborn
     const float *tagged;  // n_tagged x 7, world frame
     float4 *NPC;          // corrected point + voxel id
@@ -102,10 +106,32 @@ __device__ __forceinline__ int dsp_pyr_scan(const float *pl, int n, float seed, 
     }
     return -1;
 }
+// Correctly rounded a / b for a divisor known in advance: r = RN(1/b), one product and two fused corrections.
+// It is used ONLY after k_verify_div has compared it bit for bit with IEEE division over every float of the reachable
+// argument range for that particular divisor (dspmap.cu: verify_fast_div); otherwise the callers divide.
+__host__ __device__ __forceinline__ float dsp_div_known(float a, float b, float r) {
+#ifdef __CUDA_ARCH__
+    const float q0 = a * r;
+    const float e = __fmaf_rn(-q0, b, a);
+    return __fmaf_rn(e, r, q0);
+#else
+    (void)r;
+    return a / b;
+#endif
+}
 // getParticleVoxelsIndex (:1076-1088) with ifParticleIsOut (:1118-1125); -1 when outside
 __host__ __device__ __forceinline__ int dsp_voxel_index(const MapConst &mc, float x, float y, float z) {
     if (x >= mc.hx || x <= -mc.hx || y >= mc.hy || y <= -mc.hy || z >= mc.hz || z <= -mc.hz) return -1;
-    int ix = (int)((x + mc.hx) / mc.res), iy = (int)((y + mc.hy) / mc.res), iz = (int)((z + mc.hz) / mc.res);
+    int ix, iy, iz;
+    if (mc.fast_res) {
+        ix = (int)dsp_div_known(x + mc.hx, mc.res, mc.res_r);
+        iy = (int)dsp_div_known(y + mc.hy, mc.res, mc.res_r);
+        iz = (int)dsp_div_known(z + mc.hz, mc.res, mc.res_r);
+    } else {
+        ix = (int)((x + mc.hx) / mc.res);
+        iy = (int)((y + mc.hy) / mc.res);
+        iz = (int)((z + mc.hz) / mc.res);
+    }
     int idx = iz * mc.ny * mc.nx + iy * mc.nx + ix;
     if (idx < 0 || idx >= mc.V) return -1;
     return idx;
@@ -121,6 +147,14 @@ __host__ __device__ __forceinline__ void dsp_voxel_center(const MapConst &mc, in
 // queryNormalPDF (:1294-1301) against the half table: lut[|i - 10000|] == standard_gaussian_pdf[i]
 __device__ __forceinline__ float dsp_pdf(const float *lut, float x, float mu, float sigma) {
     float cx = (x - mu) / sigma;
+    if (cx > 9.9f) cx = 9.9f;
+    else if (cx < -9.9f) cx = -9.9f;
+    int i = (int)(cx * 1000 + 10000) - 10000;
+    return lut[i < 0 ? -i : i];
+}
+// same, with the exhaustively verified exact division by sigma
+__device__ __forceinline__ float dsp_pdf_f(const float *lut, float x, float mu, const FrameConst &fc) {
+    float cx = fc.fast_sigma ? dsp_div_known(x - mu, fc.sigma, fc.sigma_r) : (x - mu) / fc.sigma;
     if (cx > 9.9f) cx = 9.9f;
     else if (cx < -9.9f) cx = -9.9f;
     int i = (int)(cx * 1000 + 10000) - 10000;

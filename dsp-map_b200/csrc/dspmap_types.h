@@ -17,6 +17,9 @@ struct MapConst {
     float hx, hy, hz, res, occl;
     float ft[DSP_MAX_T];
     u64 vlo, vhi;  // valid slot bits (slot < S)
+    float res_r;   // RN(1/res); used only when fast_res (exhaustively verified at create time, see k_verify_div)
+    int fast_res;
+    long long cap_pairs;  // capacity of the pair buffer G
 };
 
 // Per-frame scalars. Passed to kernels by value.
@@ -31,6 +34,8 @@ struct FrameConst {
     int nb_num, nb_min_static, nb_model_gen;
     int n_points, n_tagged;
     int stage_limit;
+    float sigma_r;  // RN(1/sigma), used only when fast_sigma (exhaustively verified, see k_verify_div)
+    int fast_sigma;
     int vz_mode;  // some particle may still carry vz != 0 (constructor-seeded): ordered prediction noise is active
 };
 
@@ -45,6 +50,10 @@ struct DevState {
     int n_inexact;   // events whose exact serial semantics are not reproduced
     int overflow;    // a device list ran out of capacity
     int work_k4, work_k5;  // dynamic work queues
+    int n_occ_voxels;      // occupied-voxel work list of the resampling kernel
+    int work_eval, work_w2;  // work queues of the pair-buffer kernels
+    unsigned long long total_pairs;  // (particle, point) pairs of this frame
+    int use_store;         // total_pairs fits the pair buffer: the pair-buffer kernels run, else the recompute kernels
     float norm;      // sum of 1/C_z               (dsp_dynamic.h:799-805)
     float w_new;     // newborn particle weight    (dsp_dynamic.h:805)
     long long p_cur, v_cur, u_cur;  // noise-table cursors and uniform-stream counter (dsp_dynamic.h:483-484)

@@ -54,9 +54,14 @@ public:
         if (dspmap_create(&c, &map_) != DSPMAP_OK) {
             cout << "DSPMap: " << dspmap_last_error() << endl;
             map_ = nullptr;
+        } else {
+            instances().push_back(map_);
+            dspmap_set_voxel_filter_resolution(map_, filter_resolution());
         }
     }
     ~DSPMap() {  // :177
+        for (size_t i = 0; i < instances().size(); ++i)
+            if (instances()[i] == map_) { instances().erase(instances().begin() + i); break; }
         dspmap_destroy(map_);
         cout << "\n See you ;)" << endl;
     }
@@ -133,15 +138,6 @@ private:
             cloud.push_back(p);
         }
     }
-    struct Init {
-        Init(DSPMap *m) {
-            if (m->map_) {
-                instances().push_back(m->map_);
-                dspmap_set_voxel_filter_resolution(m->map_, filter_resolution());
-            }
-        }
-    };
     dspmap *map_ = nullptr;
     std::vector<float> xyz_;
-    Init init_{this};
 };
