@@ -72,6 +72,8 @@ struct dspmap {
     int *h_count = nullptr;
     int n_tagged = 0;               // size of the current newborn input
     std::vector<float> tagged_host; // last newborn input (world frame), for getKMClusterResult
+    void *pinned_user = nullptr;  // caller buffer registered with dspmap_pin_host_buffer
+    size_t pinned_bytes = 0;
     // reader scratch
     int *d_blockcnt = nullptr, *d_blockoff = nullptr, *d_count = nullptr;
     float *d_xyz = nullptr, *d_future = nullptr;
@@ -80,6 +82,8 @@ struct dspmap {
     // constructor-seeded particles until their first prediction, or an injected state that contains such particles
     bool vz_mode = false;
     int vz_blocks = 0;
+    // the recompute kernels (k_ck / k_weight) are launched only while the pair buffer may overflow
+    bool fallback_armed = true;
     long long host_u_cur = 0;  // uniform draws consumed on the host while seeding
     VelocityEstimator estimator;
     // statistics
@@ -248,6 +252,7 @@ int ensure_cand_capacity(dspmap *m) {
     if (dalloc(m, &m->dp.Ckey, need, false) != DSPMAP_OK) return DSPMAP_E_CUDA;
     if (dalloc(m, &m->dp.Cdst, need, false) != DSPMAP_OK) return DSPMAP_E_CUDA;
     if (dalloc(m, &m->dp.cseg, need, false) != DSPMAP_OK) return DSPMAP_E_CUDA;
+    if (dalloc(m, &m->dp.csegi, need, false) != DSPMAP_OK) return DSPMAP_E_CUDA;
     m->dp.cap_cand = need;
     return DSPMAP_OK;
 }
@@ -280,7 +285,7 @@ int enqueue_frame_a(dspmap *m, const FrameConst &fc, const float *d_pts) {
     LAUNCH(m, FAM_PREDICT, k_predict, kSMs * 8, B, 0, mc, fc, dp);
     if (fc.vz_mode) LAUNCH(m, FAM_PREDICT, k_vz_advance, 1, 32, 0, mc, dp);
     LAUNCH(m, FAM_ARRIVE, k_group_owner, kSMs * 2, B, 0, dp, &dp.st->n_mov_owner, dp.mowner, dp.mcnt, dp.mbase, &dp.st->mov_top);
-    LAUNCH(m, FAM_ARRIVE, k_group_scatter, kSMs * 4, B, 0, &dp.st->n_mov, dp.MBdst, dp.MBkey, dp.mbase, dp.mfill, dp.mseg);
+    LAUNCH(m, FAM_ARRIVE, k_group_scatter, kSMs * 4, B, 0, &dp.st->n_mov, dp.MBdst, dp.MBkey, dp.mbase, dp.mfill, dp.mseg, (int *)nullptr);
     LAUNCH(m, FAM_ARRIVE, k_arrive, kSMs * 4, B, 0, mc, fc, dp);
     LAUNCH(m, FAM_PYRAMID, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{dp.pcount, dp.poff, nullptr, 0, mc.P}, ScanJob{}, ScanJob{}}});
     LAUNCH(m, FAM_PYRAMID, k_pyr_scatter, kSMs * 8, B, 0, dp);
@@ -288,11 +293,10 @@ int enqueue_frame_a(dspmap *m, const FrameConst &fc, const float *d_pts) {
     if (fc.stage_limit >= 2) {
         LAUNCH(m, FAM_CK, k_pair_prep, grid_for(mc.P, B), B, 0, mc, dp);
         LAUNCH(m, FAM_CK, k_scan_small, 2, 1024, 0, ScanJobs{{ScanJob{dp.pairs, dp.rowbase, nullptr, 0, mc.P}, ScanJob{dp.chunks, dp.chunk_off, nullptr, 0, mc.P}, ScanJob{}}});
-        LAUNCH(m, FAM_CK, k_pair_decide, 1, 32, 0, mc, dp);
         LAUNCH(m, FAM_CK, k_pair_eval, kSMs * 2, EVAL_THREADS, sizeof(float) * (DSP_LUT_HALF + 3 + (EVAL_THREADS / 32) * 32 * TILE_LD), mc, fc, dp);
-        LAUNCH(m, FAM_CK, k_cz_chain, std::min(mc.P, kSMs * 6), CZ_THREADS, 0, mc, fc, dp);
+        LAUNCH(m, FAM_CK, k_cz_chain, std::min(mc.P, kSMs * 3), CZ_THREADS, sizeof(float) * (2 * CZ_TILE + 2 * CZ_JT), mc, fc, dp);
         size_t smem4 = sizeof(float) * (DSP_LUT_HALF + 3 + K4_TERMS) + sizeof(float4) * (256 + mc.OBS);
-        LAUNCH(m, FAM_CK, k_ck, std::min(mc.P, kSMs * 2), K4_THREADS, smem4, mc, fc, dp);  // fallback: returns at once when the pair buffer is used
+        if (m->fallback_armed) LAUNCH(m, FAM_CK, k_ck, std::min(mc.P, kSMs * 2), K4_THREADS, smem4, mc, fc, dp);  // returns at once when the pair buffer is used
         if (fc.stage_limit >= 3) {  // the newborn normaliser is one long serial chain: run it beside the weight pass
             CK(cudaEventRecord(m->ev_fork, m->stream));
             CK(cudaStreamWaitEvent(m->side, m->ev_fork, 0));
@@ -304,7 +308,7 @@ int enqueue_frame_a(dspmap *m, const FrameConst &fc, const float *d_pts) {
         LAUNCH(m, FAM_WEIGHT, k_weight2, kSMs * 6, W2_THREADS, 0, mc, fc, dp);
         size_t smem5 = sizeof(float) * (DSP_LUT_HALF + 3) + sizeof(float4) * (size_t)mc.NB * (mc.OBS - 1);
         int chunks = (mc.L + K5_THREADS - 1) / K5_THREADS;
-        LAUNCH(m, FAM_WEIGHT, k_weight, kSMs * 2, K5_THREADS, smem5, mc, fc, dp, chunks);  // fallback
+        if (m->fallback_armed) LAUNCH(m, FAM_WEIGHT, k_weight, kSMs * 2, K5_THREADS, smem5, mc, fc, dp, chunks);
         if (fc.stage_limit >= 3) CK(cudaStreamWaitEvent(m->stream, m->ev_join, 0));
     }
     CK(cudaGetLastError());
@@ -316,25 +320,28 @@ int enqueue_frame_b(dspmap *m, const FrameConst &fc, const float *d_tagged) {
     DevPtrs dp = m->dp;
     dp.tagged = d_tagged;
     const int B = 256;
+    int newborn_ran = 0;
     if (fc.stage_limit >= 3) {
         if (fc.n_tagged > 0 && fc.nb_num > 0) {
             LAUNCH(m, FAM_NEWBORN, k_nb_point0, grid_for(fc.n_tagged, B), B, 0, mc, fc, dp);
             LAUNCH(m, FAM_NEWBORN, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{dp.ninmap, dp.nrank, nullptr, 0, fc.n_tagged}, ScanJob{}, ScanJob{}}});
             LAUNCH(m, FAM_NEWBORN, k_nb_mask, grid_for((long long)fc.n_tagged * fc.nb_num, B), B, 0, mc, fc, dp);
-            LAUNCH(m, FAM_NEWBORN, k_nb_point1, grid_for(fc.n_tagged, 128), 128, 0, mc, fc, dp);
+            LAUNCH(m, FAM_NEWBORN, k_nb_point1, grid_for((long long)fc.n_tagged * 32, B), B, 0, mc, fc, dp);
             LAUNCH(m, FAM_NEWBORN, k_scan_small, 2, 1024, 0, ScanJobs{{ScanJob{dp.nvcnt, dp.nvoff, nullptr, 0, fc.n_tagged}, ScanJob{dp.nrcnt, dp.nroff, nullptr, 0, fc.n_tagged}, ScanJob{}}});
             LAUNCH(m, FAM_NEWBORN, k_nb_cand, grid_for((long long)fc.n_tagged * fc.nb_num, B), B, 0, mc, fc, dp, (u64)m->cfg.uniform_seed);
             LAUNCH(m, FAM_NEWBORN, k_group_owner, kSMs * 2, B, 0, dp, &dp.st->n_cand_owner, dp.cowner, dp.ccnt, dp.cbase, &dp.st->cand_top);
-            LAUNCH(m, FAM_NEWBORN, k_group_scatter, kSMs * 4, B, 0, &dp.st->n_cand, dp.Cdst, dp.Ckey, dp.cbase, dp.cfill, dp.cseg);
+            LAUNCH(m, FAM_NEWBORN, k_group_scatter, kSMs * 4, B, 0, &dp.st->n_cand, dp.Cdst, dp.Ckey, dp.cbase, dp.cfill, dp.cseg, dp.csegi);
             LAUNCH(m, FAM_NEWBORN, k_nb_place, kSMs * 8, B, 0, mc, fc, dp);
-            LAUNCH(m, FAM_NEWBORN, k_nb_cursors, 1, 32, 0, mc, fc, dp);
+            newborn_ran = 1;
         }
     }
     if (fc.stage_limit >= 4) {
         LAUNCH(m, FAM_RESAMPLE, k_voxel_list, grid_for(mc.V, B), B, 0, mc, dp);
         LAUNCH(m, FAM_RESAMPLE, k_resample, kSMs * 8, 256, 0, mc, fc, dp);
     }
-    LAUNCH(m, FAM_CLEANUP, k_cleanup, kSMs * 2, B, 0, dp);
+    LAUNCH(m, FAM_CLEANUP, k_cleanup, kSMs * 2, B, 0, mc, fc, dp, newborn_ran, m->fallback_armed ? 1 : 0);
+    // the (possibly one frame old) state steers which optional kernels the next frame launches
+    CK(cudaMemcpyAsync(m->h_state, m->dp.st, sizeof(DevState), cudaMemcpyDeviceToHost, m->stream));
     CK(cudaGetLastError());
     return DSPMAP_OK;
 }
@@ -384,6 +391,8 @@ int frame_prologue(dspmap *m, int n, float px, float py, float pz, double t, flo
     fc->n_points = n;
     fc->stage_limit = m->stage_limit;
     fc->vz_mode = m->vz_mode ? 1 : 0;
+    if (m->update_counter > 2)  // h_state is refreshed by every frame; a stale value is fine, growth is gradual
+        m->fallback_armed = m->h_state->total_pairs * 2ull > (unsigned long long)m->mc.cap_pairs;
     return DSPMAP_OK;
 }
 
@@ -591,6 +600,7 @@ int dspmap_create(const dspmap_config *cfg, dspmap **out) {
     CK(cudaFuncSetAttribute(k_pyr_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PYR_SORT_CAP * sizeof(u64))));
     CK(cudaFuncSetAttribute(k_ck, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CK(cudaFuncSetAttribute(k_pair_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    CK(cudaFuncSetAttribute(k_cz_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
     CK(cudaFuncSetAttribute(k_weight, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaStreamSynchronize(m->stream));
     if (gen_tables(m) != DSPMAP_OK) { dspmap_destroy(m); return DSPMAP_E_CUDA; }
@@ -619,6 +629,7 @@ void dspmap_destroy(dspmap *m) {
     if (!m) return;
     cudaSetDevice(m->cfg.device);
     cudaDeviceSynchronize();
+    if (m->pinned_user) cudaHostUnregister(m->pinned_user);
     for (void *p : m->allocs) cudaFree(p);
     if (m->h_pts) cudaFreeHost(m->h_pts);
     if (m->h_tagged) cudaFreeHost(m->h_tagged);
@@ -755,7 +766,10 @@ int dspmap_get_occupancy(dspmap *m, float thr, float *xyz_out, int cap, int *n_o
     int rc = dspmap_get_occupancy_device(m, thr, m->d_xyz, mc.V, m->d_count, future ? m->d_future : nullptr);
     if (rc != DSPMAP_OK) return rc;
     CK(cudaMemcpyAsync(m->h_count, m->d_count, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
-    if (future) CK(cudaMemcpyAsync(m->h_future, m->d_future, sizeof(float) * (size_t)mc.V * mc.T, cudaMemcpyDeviceToHost, m->stream));
+    const size_t fbytes = sizeof(float) * (size_t)mc.V * mc.T;
+    const bool direct = future && m->pinned_user && (char *)future >= (char *)m->pinned_user &&
+                        (char *)future + fbytes <= (char *)m->pinned_user + m->pinned_bytes;
+    if (future) CK(cudaMemcpyAsync(direct ? future : m->h_future, m->d_future, fbytes, cudaMemcpyDeviceToHost, m->stream));
     CK(cudaStreamSynchronize(m->stream));
     int n = *m->h_count;
     if (n_out) *n_out = n;
@@ -765,8 +779,25 @@ int dspmap_get_occupancy(dspmap *m, float thr, float *xyz_out, int cap, int *n_o
         CK(cudaStreamSynchronize(m->stream));
         memcpy(xyz_out, m->h_xyz, sizeof(float) * 3 * (size_t)ncopy);
     }
-    if (future) memcpy(future, m->h_future, sizeof(float) * (size_t)mc.V * mc.T);
+    if (future && !direct) memcpy(future, m->h_future, fbytes);
     if (m->profile) prof_collect(m);
+    return DSPMAP_OK;
+}
+int dspmap_pin_host_buffer(dspmap *m, void *ptr, size_t bytes) {
+    if (!m) return DSPMAP_E_BAD_ARG;
+    if (m->pinned_user) {
+        cudaHostUnregister(m->pinned_user);
+        m->pinned_user = nullptr;
+        m->pinned_bytes = 0;
+    }
+    if (ptr && bytes) {
+        if (cudaHostRegister(ptr, bytes, cudaHostRegisterPortable) != cudaSuccess) {
+            cudaGetLastError();  // not fatal: the staged path stays in use
+            return DSPMAP_REJECTED;
+        }
+        m->pinned_user = ptr;
+        m->pinned_bytes = bytes;
+    }
     return DSPMAP_OK;
 }
 int dspmap_clear_prediction(dspmap *m) {

@@ -4,6 +4,12 @@
 #include "dspmap_kernels.cuh"
 
 // ------------------------------------------------------------------------------------------------------------
+// (helper) the pair buffer is used when the frame's pairs fit it; otherwise the recompute kernels (k_ck / k_weight) take the frame
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool use_pair_buffer(const MapConst &mc, const DevPtrs &dp) {
+    return dp.st->total_pairs <= (unsigned long long)mc.cap_pairs;
+}
+// ------------------------------------------------------------------------------------------------------------
 // K0  frame setup: rotate the boundary-plane normals (dsp_dynamic.h:226-232), reset per-frame state (:235-238)
 // ------------------------------------------------------------------------------------------------------------
 __global__ void k_frame_setup(MapConst mc, FrameConst fc, DevPtrs dp) {
@@ -78,37 +84,41 @@ struct ScanJob { const int *in; int *out; int *out_capped; int cap; int n; };
 struct ScanJobs { ScanJob j[3]; };
 __global__ void __launch_bounds__(1024) k_scan_small(ScanJobs jobs) {
     __shared__ int wsum[32], wcap[32];
+    __shared__ int carry[2];
     const ScanJob J = jobs.j[blockIdx.x];
     const int n = J.n, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int per = (n + blockDim.x - 1) / blockDim.x;
-    const int b = threadIdx.x * per, e = min(n, b + per);
-    int s = 0, sc = 0;
-    for (int i = b; i < e; ++i) { int x = J.in[i]; s += x; sc += min(x, J.cap); }
-    int incl = s, inclc = sc;
-    for (int d = 1; d < 32; d <<= 1) {
-        int t = __shfl_up_sync(FULLMASK, incl, d), tc = __shfl_up_sync(FULLMASK, inclc, d);
-        if (lane >= d) { incl += t; inclc += tc; }
-    }
-    if (lane == 31) { wsum[wid] = incl; wcap[wid] = inclc; }
+    if (threadIdx.x == 0) { carry[0] = 0; carry[1] = 0; }
     __syncthreads();
-    if (wid == 0) {
-        int x = wsum[lane], xc = wcap[lane], y = x, yc = xc;
+    for (int base = 0; base < n; base += 1024) {  // rounds of 1024 consecutive elements: coalesced loads and stores
+        const int i = base + threadIdx.x;
+        const int x = i < n ? J.in[i] : 0, xc = min(x, J.cap);
+        int incl = x, inclc = xc;
         for (int d = 1; d < 32; d <<= 1) {
-            int t = __shfl_up_sync(FULLMASK, y, d), tc = __shfl_up_sync(FULLMASK, yc, d);
-            if (lane >= d) { y += t; yc += tc; }
+            int t = __shfl_up_sync(FULLMASK, incl, d), tc = __shfl_up_sync(FULLMASK, inclc, d);
+            if (lane >= d) { incl += t; inclc += tc; }
         }
-        wsum[lane] = y - x;  // exclusive prefix of the warp totals
-        wcap[lane] = yc - xc;
-        if (lane == 31) { J.out[n] = y; if (J.out_capped) J.out_capped[n] = yc; }
+        if (lane == 31) { wsum[wid] = incl; wcap[wid] = inclc; }
+        __syncthreads();
+        if (wid == 0) {
+            int y0 = wsum[lane], yc0 = wcap[lane], y = y0, yc = yc0;
+            for (int d = 1; d < 32; d <<= 1) {
+                int t = __shfl_up_sync(FULLMASK, y, d), tc = __shfl_up_sync(FULLMASK, yc, d);
+                if (lane >= d) { y += t; yc += tc; }
+            }
+            wsum[lane] = y - y0;  // exclusive prefix of the warp totals
+            wcap[lane] = yc - yc0;
+        }
+        __syncthreads();
+        const int c0 = carry[0], c1 = carry[1];
+        if (i < n) {
+            J.out[i] = c0 + wsum[wid] + incl - x;
+            if (J.out_capped) J.out_capped[i] = c1 + wcap[wid] + inclc - xc;
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) { carry[0] = c0 + wsum[wid] + incl; carry[1] = c1 + wcap[wid] + inclc; }
+        __syncthreads();
     }
-    __syncthreads();
-    int run = wsum[wid] + incl - s, runc = wcap[wid] + inclc - sc;
-    for (int i = b; i < e; ++i) {
-        int x = J.in[i];
-        J.out[i] = run;
-        run += x;
-        if (J.out_capped) { J.out_capped[i] = runc; runc += min(x, J.cap); }
-    }
+    if (threadIdx.x == 0) { J.out[n] = carry[0]; if (J.out_capped) J.out_capped[n] = carry[1]; }
 }
 
 __global__ void k_obs_scatter(MapConst mc, FrameConst fc, DevPtrs dp) {
@@ -325,11 +335,13 @@ __global__ void k_group_owner(DevPtrs dp, const int *n_owner, const int *owner, 
         }
     }
 }
-__global__ void k_group_scatter(const int *n_items, const int *dst, const int *key, const int *base, int *fill, int *seg) {
+__global__ void k_group_scatter(const int *n_items, const int *dst, const int *key, const int *base, int *fill, int *seg, int *segi) {
     int n = *n_items;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         int d = dst[i];
-        seg[base[d] + atomicAdd(&fill[d], 1)] = key[i];
+        const int pos = base[d] + atomicAdd(&fill[d], 1);
+        seg[pos] = key[i];
+        if (segi) segi[pos] = i;
     }
 }
 
@@ -472,7 +484,7 @@ __global__ void __launch_bounds__(K4_THREADS) k_ck(MapConst mc, FrameConst fc, D
     float4 *ptl = (float4 *)(term + K4_TERMS);  // particle tile, <= 256
     float4 *zs = ptl + 256;                     // points of this pyramid, <= OBS
     __shared__ int s_item;
-    if (dp.st->use_store) return;  // the pair-buffer kernels handle this frame
+    if (use_pair_buffer(mc, dp)) return;  // the pair-buffer kernels handle this frame
     for (int i = threadIdx.x; i < DSP_LUT_HALF; i += blockDim.x) lut[i] = dp.lut[i];
     const float enb = fc.nb_weight * (float)dp.st->n_valid * (float)fc.nb_num;  // :292
     const float add_k = enb + fc.kappa;
@@ -529,7 +541,7 @@ __global__ void __launch_bounds__(K5_THREADS) k_weight(MapConst mc, FrameConst f
     float *lut = smem;
     float4 *zs = (float4 *)(lut + DSP_LUT_HALF + 3);  // NB * (OBS-1) staged points: x y z C_z
     __shared__ int s_item;
-    if (dp.st->use_store) return;  // the pair-buffer kernels handle this frame
+    if (use_pair_buffer(mc, dp)) return;  // the pair-buffer kernels handle this frame
     for (int i = threadIdx.x; i < DSP_LUT_HALF; i += blockDim.x) lut[i] = dp.lut[i];
     int staged = -1, nz = 0;
     const int items = mc.P * chunks_per_pyr;
@@ -602,9 +614,6 @@ __global__ void k_pair_prep(MapConst mc, DevPtrs dp) {
     }
     if (local) atomicAdd(&dp.st->total_pairs, local);
 }
-__global__ void k_pair_decide(MapConst mc, DevPtrs dp) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) dp.st->use_store = dp.st->total_pairs <= (unsigned long long)mc.cap_pairs ? 1 : 0;
-}
 // position of pyramid a inside pyramid b's neighbour list (the relation is symmetric)
 __device__ __forceinline__ int nb_index_of(const MapConst &mc, const DevPtrs &dp, int b, int a) {
     const int nn = dp.nbr[b * mc.NBW];
@@ -626,7 +635,7 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_pair_eval(MapConst mc, FrameCo
     extern __shared__ float sm[];
     float *lut = sm;
     float *tile = sm + (DSP_LUT_HALF + 3) + (threadIdx.x >> 5) * (32 * TILE_LD);
-    if (!dp.st->use_store) return;
+    if (!use_pair_buffer(mc, dp)) return;
     for (int i = threadIdx.x; i < DSP_LUT_HALF; i += blockDim.x) lut[i] = dp.lut[i];
     __syncthreads();
     const int lane = threadIdx.x & 31;
@@ -656,21 +665,26 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_pair_eval(MapConst mc, FrameCo
                 tile[lane * TILE_LD + zl] = dsp_pdf_f(lut, p.x, o.x, fc) * dsp_pdf_f(lut, p.y, o.y, fc) * dsp_pdf_f(lut, p.z, o.z, fc);
             }
             __syncwarp();
-            if (lane < nsub)
-                for (int r = 0; r < nrows; ++r) gb[(size_t)r * np + z0 + lane] = tile[r * TILE_LD + lane];
+            if (lane < nsub) {
+                float *dst = gb + z0 + lane;
+#pragma unroll 8
+                for (int r = 0; r < nrows; ++r) dst[(size_t)r * np] = tile[r * TILE_LD + lane];
+            }
             __syncwarp();
         }
     }
 }
 // C_z (dsp_dynamic.h:709-739): a CTA per point pyramid streams the pyramid's contiguous block of G through shared
 // memory (double-buffered cp.async); thread z < np adds its column in list order: one fp32 chain per point.
-#define CZ_THREADS 128
-#define CZ_TILE 4096
+#define CZ_THREADS 256
+#define CZ_TILE 8192   // floats per buffer (dynamic shared memory: 2 buffers)
+#define CZ_JT 128
 __global__ void __launch_bounds__(CZ_THREADS) k_cz_chain(MapConst mc, FrameConst fc, DevPtrs dp) {
-    __shared__ float tile[2][CZ_TILE];
-    __shared__ float pws[2][64];
+    extern __shared__ float czsm[];
+    float *tile0 = czsm, *tile1 = czsm + CZ_TILE;
+    float *pws0 = czsm + 2 * CZ_TILE, *pws1 = pws0 + CZ_JT;
     __shared__ int s_item;
-    if (!dp.st->use_store) return;
+    if (!use_pair_buffer(mc, dp)) return;
     const float enb = fc.nb_weight * (float)dp.st->n_valid * (float)fc.nb_num;  // :292
     const float add_k = enb + fc.kappa;
     const int tid = threadIdx.x;
@@ -683,9 +697,9 @@ __global__ void __launch_bounds__(CZ_THREADS) k_cz_chain(MapConst mc, FrameConst
         const int np = min(dp.obs_cnt[i], mc.OBS - 1);
         if (np == 0) continue;
         const int nn = dp.nbr[i * mc.NBW];
-        const int JT = min(64, CZ_TILE / np);
+        const int JT = min(CZ_JT, CZ_TILE / np);
         const float *gsrc = dp.G + (size_t)dp.rowbase[i];
-        // tile iterator over (neighbour ns, particle offset k0); "issue" state runs one tile ahead of "consume" state
+        // tile iterator over (neighbour ns, particle offset k0); the "issue" state runs one tile ahead of the consumer
         int ins = 0, ik0 = 0, iln = nn > 0 ? dp.plen[dp.nbr[i * mc.NBW + 1]] : 0;
         const float *ig = gsrc;
         auto issue = [&](int buf) -> int {  // returns the number of particle rows of the issued tile, 0 when exhausted
@@ -696,8 +710,9 @@ __global__ void __launch_bounds__(CZ_THREADS) k_cz_chain(MapConst mc, FrameConst
             }
             if (ins >= nn) return 0;
             const int cur = min(JT, iln - ik0), nfl = cur * np;
-            for (int f = tid; f < nfl; f += CZ_THREADS) __pipeline_memcpy_async(&tile[buf][f], ig + f, 4);
-            if (tid < cur) __pipeline_memcpy_async(&pws[buf][tid], dp.PW + dp.poff[dp.nbr[i * mc.NBW + 1 + ins]] + ik0 + tid, 4);
+            float *t = buf ? tile1 : tile0;
+            for (int f = tid; f < nfl; f += CZ_THREADS) __pipeline_memcpy_async(t + f, ig + f, 4);
+            if (tid < cur) __pipeline_memcpy_async((buf ? pws1 : pws0) + tid, dp.PW + dp.poff[dp.nbr[i * mc.NBW + 1 + ins]] + ik0 + tid, 4);
             ig += nfl;
             ik0 += cur;
             return cur;
@@ -711,11 +726,18 @@ __global__ void __launch_bounds__(CZ_THREADS) k_cz_chain(MapConst mc, FrameConst
             __pipeline_commit();
             __pipeline_wait_prior(1);
             __syncthreads();
-            if (tid < np) {
-                const float *t = tile[buf] + tid;
-                const float *w = pws[buf];
-#pragma unroll 4
-                for (int jj = 0; jj < cur; ++jj) acc += w[jj] * t[jj * np];
+            if (tid < np) {  // the chain: (P_d * w) * g added in list order, one fp32 add per term
+                const float *t = (buf ? tile1 : tile0) + tid;
+                const float *w = buf ? pws1 : pws0;
+                int jj = 0;
+                for (; jj + 8 <= cur; jj += 8) {
+                    float g0 = t[jj * np], g1 = t[(jj + 1) * np], g2 = t[(jj + 2) * np], g3 = t[(jj + 3) * np];
+                    float g4 = t[(jj + 4) * np], g5 = t[(jj + 5) * np], g6 = t[(jj + 6) * np], g7 = t[(jj + 7) * np];
+                    const float4 wa = *reinterpret_cast<const float4 *>(w + jj), wb = *reinterpret_cast<const float4 *>(w + jj + 4);
+                    g0 *= wa.x; g1 *= wa.y; g2 *= wa.z; g3 *= wa.w; g4 *= wb.x; g5 *= wb.y; g6 *= wb.z; g7 *= wb.w;
+                    acc += g0; acc += g1; acc += g2; acc += g3; acc += g4; acc += g5; acc += g6; acc += g7;
+                }
+                for (; jj < cur; ++jj) acc += w[jj] * t[jj * np];
             }
             __syncthreads();
             cur = nxt;
@@ -729,13 +751,16 @@ __global__ void __launch_bounds__(CZ_THREADS) k_cz_chain(MapConst mc, FrameConst
         }
     }
 }
-// weights (dsp_dynamic.h:743-790): one warp per 32 particles of a pyramid, lanes = particles; the 32 x 32 sub-tiles of G
-// are read as coalesced rows into a per-warp staging tile.
+// weights (dsp_dynamic.h:743-790): one warp per 32 particles of a pyramid, lanes = particles.  The 32 x 32 sub-tiles of G
+// are read as coalesced rows (lane = point) into registers one sub-tile AHEAD of the one being consumed, staged through a
+// per-warp shared tile, and each lane adds its particle's row in (neighbour-table, bin) order.
 #define W2_THREADS 256
-__global__ void __launch_bounds__(W2_THREADS) k_weight2(MapConst mc, FrameConst fc, DevPtrs dp) {
+__global__ void __launch_bounds__(W2_THREADS, 3) k_weight2(MapConst mc, FrameConst fc, DevPtrs dp) {
     __shared__ float tiles[(W2_THREADS / 32) * 32 * TILE_LD];
-    if (!dp.st->use_store) return;
+    __shared__ float czall[(W2_THREADS / 32) * 32];
+    if (!use_pair_buffer(mc, dp)) return;
     float *tile = tiles + (threadIdx.x >> 5) * (32 * TILE_LD);
+    float *czs = czall + (threadIdx.x >> 5) * 32;
     const int lane = threadIdx.x & 31;
     const int nchunks = dp.chunk_off[mc.P];
     for (;;) {
@@ -749,31 +774,57 @@ __global__ void __launch_bounds__(W2_THREADS) k_weight2(MapConst mc, FrameConst 
         const int nrows = min(32, ln - k0);
         bool act = lane < nrows;
         const float4 p = act ? dp.LP[lb + k0 + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
-        const bool mine = act;
         if (act) {
             const float dist = sqrtf(p.x * p.x + p.y * p.y + p.z * p.z);
             const float maxlen = __int_as_float(dp.obs_maxbits[a]);
             if (maxlen > 0.f && dist > maxlen + mc.occl) act = false;  // occluded (:761): weight unchanged
         }
-        float sum = 0.f;
         const int nn = dp.nbr[a * mc.NBW];
-        for (int ns = 0; ns < nn; ++ns) {
-            const int b = dp.nbr[a * mc.NBW + 1 + ns];
-            const int np = min(dp.obs_cnt[b], mc.OBS - 1);
-            if (np == 0) continue;
-            const float *gb = dp.G + (size_t)dp.rowbase[b] + (size_t)(dp.cum[b * mc.NBW + nb_index_of(mc, dp, b, a)] + k0) * np;
-            const float *cz = dp.CZ + (size_t)b * mc.OBS;
-            for (int z0 = 0; z0 < np; z0 += 32) {
-                const int nsub = min(32, np - z0);
-                if (lane < nsub)
-                    for (int r = 0; r < nrows; ++r) tile[r * TILE_LD + lane] = gb[(size_t)r * np + z0 + lane];
-                __syncwarp();
-                if (act)
-                    for (int zl = 0; zl < nsub; ++zl) sum += fc.Pd * tile[lane * TILE_LD + zl] / cz[z0 + zl];
-                __syncwarp();
+        // sub-tile iterator over (neighbour ns, point block z0)
+        int ns = -1, z0 = 0, np = 0;
+        const float *gb = nullptr, *cz = nullptr;
+        auto advance = [&]() -> int {  // moves to the next sub-tile; returns its number of points, 0 when done
+            z0 += 32;
+            while (ns < 0 || z0 >= np) {
+                if (++ns >= nn) return 0;
+                const int b = dp.nbr[a * mc.NBW + 1 + ns];
+                np = min(dp.obs_cnt[b], mc.OBS - 1);
+                z0 = 0;
+                if (np == 0) continue;
+                gb = dp.G + (size_t)dp.rowbase[b] + (size_t)(dp.cum[b * mc.NBW + nb_index_of(mc, dp, b, a)] + k0) * np;
+                cz = dp.CZ + (size_t)b * mc.OBS;
             }
+            return min(32, np - z0);
+        };
+        float v[32], czv = 1.f;
+        auto prefetch = [&](int nsub) {
+            if (lane < nsub) {
+                const float *src = gb + z0 + lane;
+#pragma unroll
+                for (int r = 0; r < 32; ++r) v[r] = r < nrows ? __ldg(src + (size_t)r * np) : 0.f;
+                czv = cz[z0 + lane];
+            }
+        };
+        float sum = 0.f;
+        int nsub = advance();
+        if (nsub) prefetch(nsub);
+        while (nsub) {
+            if (lane < nsub) {
+#pragma unroll
+                for (int r = 0; r < 32; ++r) tile[r * TILE_LD + lane] = v[r];
+                czs[lane] = czv;
+            }
+            __syncwarp();
+            const int cur = nsub;
+            nsub = advance();
+            if (nsub) prefetch(nsub);  // in flight while the current sub-tile is consumed
+            if (act) {
+#pragma unroll 4
+                for (int zl = 0; zl < cur; ++zl) sum += fc.Pd * tile[lane * TILE_LD + zl] / czs[zl];
+            }
+            __syncwarp();
         }
-        if (mine && act) dp.PA[dp.LA[lb + k0 + lane]].w = p.w * (fc.one_minus_Pd + sum);
+        if (act) dp.PA[dp.LA[lb + k0 + lane]].w = p.w * (fc.one_minus_Pd + sum);
     }
 }
 // Exhaustive check of dsp_div_known against IEEE division for ONE divisor over every non-negative float up to max_bits
@@ -852,53 +903,72 @@ __global__ void k_nb_mask(MapConst mc, FrameConst fc, DevPtrs dp) {
         if (dsp_voxel_index(mc, px, py, pz) >= 0) atomicOr(&dp.nimask[m], 1ull << p);
     }
 }
-// point pass 1: Dempster-Shafer split from the resident particles of the point's voxel (:829-866), which of the
-// nb_num candidates land inside the map (:871-875), and how many table / uniform draws the point consumes.
-__global__ void k_nb_point1(MapConst mc, FrameConst fc, DevPtrs dp) {
-    for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < fc.n_tagged; m += gridDim.x * blockDim.x) {
-        if (!dp.ninmap[m]) { dp.nvcnt[m] = 0; dp.nrcnt[m] = 0; continue; }
-        float4 pc = dp.NPC[m];
+// point pass 1: Dempster-Shafer split from the resident particles of the point's voxel (:829-866) — one warp per point,
+// lanes = slots, the three weight sums added in slot order — and how many table / uniform draws the point consumes.
+__global__ void __launch_bounds__(256) k_nb_point1(MapConst mc, FrameConst fc, DevPtrs dp) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int R = (mc.S + 31) >> 5;
+    for (int m = warp; m < fc.n_tagged; m += nwarps) {
+        if (!dp.ninmap[m]) {
+            if (lane == 0) { dp.nvcnt[m] = 0; dp.nrcnt[m] = 0; }
+            continue;
+        }
         int n_static = 0;
         if (mc.model == 0) {
-            int pv = __float_as_int(pc.w);
+            const int pv = __float_as_int(dp.NPC[m].w);
+            const ulonglong2 msk = dp.M[pv];
             float ws = 0.f, wd = 0.f, wsd = 0.f;
-            ulonglong2 msk = dp.M[pv];
-            for (int half = 0; half < 2; ++half) {
-                u64 z = half ? msk.y : msk.x;
-                while (z) {
-                    int s = __ffsll((long long)z) - 1 + 64 * half;
-                    z &= z - 1;
-                    int a = pv * mc.S + s;
-                    float4 B = dp.PB[a];
-                    if (!(B.w > 0.9f && B.w < 14.f)) continue;  // not newborn (:830)
-                    float w = dp.PA[a].w;
-                    float va = fabsf(B.x) + fabsf(B.y) + fabsf(B.z);
-                    if (va < 0.1f) ws += w;
-                    else if (va < 0.5f) wsd += w;
-                    else wd += w;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                if (r >= R) break;
+                const unsigned live = r < 2 ? (unsigned)(msk.x >> (32 * r)) : (unsigned)(msk.y >> (32 * (r - 2)));
+                if (live == 0u) continue;
+                float w = 0.f;
+                int cls = 3;
+                if ((live >> lane) & 1u) {
+                    const int a = pv * mc.S + 32 * r + lane;
+                    const float4 B = dp.PB[a];
+                    if (B.w > 0.9f && B.w < 14.f) {  // not newborn (:830)
+                        w = dp.PA[a].w;
+                        const float va = fabsf(B.x) + fabsf(B.y) + fabsf(B.z);
+                        cls = va < 0.1f ? 0 : (va < 0.5f ? 1 : 2);
+                    }
+                }
+                unsigned k = __ballot_sync(FULLMASK, cls != 3);
+                while (k) {
+                    const int l = __ffs(k) - 1;
+                    k &= k - 1;
+                    const float wv = __shfl_sync(FULLMASK, w, l);
+                    const int cl = __shfl_sync(FULLMASK, cls, l);
+                    if (cl == 0) ws += wv;
+                    else if (cl == 1) wsd += wv;
+                    else wd += wv;
                 }
             }
-            float tot = ws + wd + wsd;
-            float m_s = ws / tot, m_d = wd / tot, m_sd = wsd / tot;
-            float p_s = (m_s + m_s + m_sd) * 0.5f, p_d = (m_d + m_d + m_sd) * 0.5f;
-            float np_ = p_s + p_d;
-            float ps_n = p_s / np_;
-            float prod = (float)fc.nb_model_gen * ps_n;
+            const float tot = ws + wd + wsd;
+            const float m_s = ws / tot, m_d = wd / tot, m_sd = wsd / tot;
+            const float p_s = (m_s + m_s + m_sd) * 0.5f, p_d = (m_d + m_d + m_sd) * 0.5f;
+            const float np_ = p_s + p_d;
+            const float ps_n = p_s / np_;
+            const float prod = (float)fc.nb_model_gen * ps_n;
             n_static = (prod != prod) ? INT_MIN : (int)prod;
             n_static = max(fc.nb_min_static, n_static);
         }
-        const u64 im = dp.nimask[m];
-        const float *pt = dp.tagged + 7 * m;
-        u64 vm = 0ull, rm = 0ull;
-        if (mc.model == 0 && pt[6] > 0.01f) {  // only points tagged dynamic draw velocities (:883,:894)
-            u64 nonstatic = im & ~bits_below(max(n_static, 0));
-            u64 est = (pt[3] > -100.f) ? bits_below(fc.nb_model_gen) : 0ull;  // (:881)
-            vm = nonstatic & est;
-            rm = nonstatic & ~est;
+        if (lane == 0) {
+            const u64 im = dp.nimask[m];
+            const float *pt = dp.tagged + 7 * m;
+            u64 vm = 0ull, rm = 0ull;
+            if (mc.model == 0 && pt[6] > 0.01f) {  // only points tagged dynamic draw velocities (:883,:894)
+                u64 nonstatic = im & ~bits_below(max(n_static, 0));
+                u64 est = (pt[3] > -100.f) ? bits_below(fc.nb_model_gen) : 0ull;  // (:881)
+                vm = nonstatic & est;
+                rm = nonstatic & ~est;
+            }
+            dp.nstatic[m] = n_static;
+            dp.nvcnt[m] = __popcll(vm);
+            dp.nrcnt[m] = __popcll(rm);
         }
-        dp.nstatic[m] = n_static;
-        dp.nvcnt[m] = __popcll(vm);
-        dp.nrcnt[m] = __popcll(rm);
     }
 }
 // candidate pass: position (:871-873), velocity class (:877-907), weight (:909); candidates inside the map join
@@ -948,41 +1018,54 @@ __global__ void k_nb_cand(MapConst mc, FrameConst fc, DevPtrs dp, u64 useed) {
         if (atomicAdd(&dp.ccnt[d], 1) == 0) dp.cowner[agg_inc(&dp.st->n_cand_owner)] = d;
     }
 }
-// addAParticle (:1183-1201) in serial order: the k-th candidate of a voxel takes its k-th free slot.
-__global__ void k_nb_place(MapConst mc, FrameConst fc, DevPtrs dp) {
-    const int n = min(dp.st->n_cand, dp.cap_cand);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        int d = dp.Cdst[i], key = dp.Ckey[i];
-        const ulonglong2 ms = dp.MS[d];
-        const int nfree = mask_free(mc, ms);
-        int b = dp.cbase[d], c = dp.ccnt[d], rank = 0;
-        for (int j = 0; j < c; ++j) rank += dp.cseg[b + j] < key;
-        if (rank >= nfree) continue;
-        int slot = mask_nth_free(mc, ms, rank);
-        if (slot < 0) continue;
-        int a = d * mc.S + slot;
-        dp.PA[a] = dp.CA[i];
-        dp.PB[a] = dp.CB[i];
-        mask_atomic_set(dp.M, d, slot);
-        agg_inc(&dp.st->n_born);
+// addAParticle (:1183-1201) in serial order: the k-th candidate of a voxel (in (point, candidate) order) takes its k-th
+// free slot.  One warp per destination voxel: it extracts the next-smallest key as many times as the voxel has free
+// slots (lanes scan the voxel's segment, a shuffle reduction picks the minimum), then the winners are copied in parallel.
+__global__ void __launch_bounds__(256) k_nb_place(MapConst mc, FrameConst fc, DevPtrs dp) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int nown = dp.st->n_cand_owner;
+    int born = 0;
+    for (int o = warp; o < nown; o += nwarps) {
+        const int d = dp.cowner[o];
+        const int b = dp.cbase[d], c = dp.ccnt[d];
+        ulonglong2 msk = dp.M[d];
+        const int nfree = min(mask_free(mc, msk), c);
+        long long last = -1;
+        int my_slot[4] = {-1, -1, -1, -1}, my_cand[4] = {0, 0, 0, 0};
+        for (int r = 0; r < nfree; ++r) {
+            u64 best = ~0ull;  // (key << 32) | position
+            for (int j = lane; j < c; j += 32) {
+                const long long kj = dp.cseg[b + j];
+                if (kj > last) best = min(best, ((u64)kj << 32) | (unsigned)j);
+            }
+            for (int sft = 16; sft > 0; sft >>= 1) best = min(best, __shfl_xor_sync(FULLMASK, best, sft));
+            last = (long long)(best >> 32);
+            const int slot = mask_nth_free(mc, msk, 0);
+            if (slot < 64) msk.x |= 1ull << slot; else msk.y |= 1ull << (slot - 64);
+            if (lane == (r & 31)) {
+                const int q = r >> 5;
+                const int cand = dp.csegi[b + (int)(best & 0xffffffffull)];
+                if (q == 0) { my_slot[0] = slot; my_cand[0] = cand; }
+                else if (q == 1) { my_slot[1] = slot; my_cand[1] = cand; }
+                else if (q == 2) { my_slot[2] = slot; my_cand[2] = cand; }
+                else { my_slot[3] = slot; my_cand[3] = cand; }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (my_slot[q] >= 0) {
+                const int a = d * mc.S + my_slot[q];
+                dp.PA[a] = dp.CA[my_cand[q]];
+                dp.PB[a] = dp.CB[my_cand[q]];
+            }
+        if (lane == 0) {
+            dp.M[d] = msk;
+            born += nfree;
+        }
     }
+    if (lane == 0 && born) atomicAdd(&dp.st->n_born, born);
 }
-// cursors advance by what the serial loop would have drawn
-__global__ void k_nb_cursors(MapConst mc, FrameConst fc, DevPtrs dp) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        DevState *s = dp.st;
-        int inmap_pts = fc.n_tagged > 0 ? dp.nrank[fc.n_tagged] : 0;
-        int vd = fc.n_tagged > 0 ? dp.nvoff[fc.n_tagged] : 0;
-        int rd = fc.n_tagged > 0 ? dp.nroff[fc.n_tagged] : 0;
-        s->n_inmap_points = inmap_pts;
-        s->n_vdraw = vd;
-        s->n_rdraw = rd;
-        s->p_cur = (s->p_cur + 3ll * inmap_pts * fc.nb_num) % mc.G;
-        s->v_cur = (s->v_cur + 3ll * vd) % mc.G;
-        s->u_cur += 3ll * rd;
-    }
-}
-
 // ------------------------------------------------------------------------------------------------------------
 // K7a list of occupied voxels (balances K7: occupied voxels are x-adjacent, so a strided sweep would hand one warp up
 //     to 32 of them); empty voxels get their zero occupancy here.
@@ -1144,12 +1227,27 @@ __global__ void __launch_bounds__(256) k_resample(MapConst mc, FrameConst fc, De
     }
 }
 
-// reset the arrival-grouping tables touched this frame
-__global__ void k_cleanup(DevPtrs dp) {
+// end of frame: reset the arrival-grouping tables touched this frame; advance the noise cursors by what the reference's
+// serial newborn loop would have drawn (dsp_dynamic.h:1162-1178); flag a frame no observation kernel handled
+__global__ void k_cleanup(MapConst mc, FrameConst fc, DevPtrs dp, int newborn_ran, int fallback_launched) {
     int n1 = dp.st->n_mov_owner, n2 = dp.st->n_cand_owner;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2; i += gridDim.x * blockDim.x) {
         if (i < n1) { int d = dp.mowner[i]; dp.mcnt[d] = 0; dp.mfill[d] = 0; }
         else { int d = dp.cowner[i - n1]; dp.ccnt[d] = 0; dp.cfill[d] = 0; }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        DevState *s = dp.st;
+        if (newborn_ran) {
+            const int inmap_pts = dp.nrank[fc.n_tagged], vd = dp.nvoff[fc.n_tagged], rd = dp.nroff[fc.n_tagged];
+            s->n_inmap_points = inmap_pts;
+            s->n_vdraw = vd;
+            s->n_rdraw = rd;
+            s->p_cur = (s->p_cur + 3ll * inmap_pts * fc.nb_num) % mc.G;
+            s->v_cur = (s->v_cur + 3ll * vd) % mc.G;
+            s->u_cur += 3ll * rd;
+        }
+        s->use_store = use_pair_buffer(mc, dp) ? 1 : 0;
+        if (!s->use_store && !fallback_launched && fc.stage_limit >= 2) s->overflow = 1;
     }
 }
 

@@ -51,7 +51,7 @@ struct DevPtrs {
     u64 *nimask;
     float4 *CA, *CB;
     int *Ckey, *Cdst;
-    int *ccnt, *cfill, *cbase, *cowner, *cseg;
+    int *ccnt, *cfill, *cbase, *cowner, *cseg, *csegi;
     // tables
     const float *ptab, *vtab, *lut;
     const float *planes0;  // boundary-plane normals, sensor frame: (Nh+1) + (Nv+1) vectors

@@ -52,39 +52,72 @@ struct Grid {  // open-addressing hash from integer cell to the head of a linked
 }  // namespace
 
 void euclidean_clusters(const float *xyz, int n, float tol, int min_size, int max_size, std::vector<std::vector<int>> &out) {
+    // Connected components of the graph "d2 <= tol^2" through a union-find over grid cells.  The cell edge is below
+    // tol / sqrt(3), so all points of one cell are mutually linked; links between cells up to two cells apart need one
+    // witness pair.  Cost is linear in the points for the dense clouds a nearby surface produces (a per-point
+    // neighbourhood search is quadratic there).  Components do not depend on the traversal, so the result is identical.
     out.clear();
     if (n == 0 || !(tol > 0.f)) return;
     const float tol2 = tol * tol;
+    const float edge = tol * 0.57f;
     std::vector<int64_t> cells(3 * (size_t)n);
     for (int i = 0; i < n; ++i)
-        for (int k = 0; k < 3; ++k) cells[3 * i + k] = (int64_t)std::floor(xyz[3 * i + k] / tol);
+        for (int k = 0; k < 3; ++k) cells[3 * i + k] = (int64_t)std::floor(xyz[3 * i + k] / edge);
     Grid g;
     g.build(cells, n);
-    std::vector<char> seen(n, 0);
-    std::vector<int> queue;
-    for (int s = 0; s < n; ++s) {
-        if (seen[s]) continue;
-        queue.clear();
-        queue.push_back(s);
-        seen[s] = 1;
-        for (size_t h = 0; h < queue.size(); ++h) {
-            const int i = queue[h];
-            const float px = xyz[3 * i], py = xyz[3 * i + 1], pz = xyz[3 * i + 2];
-            for (int64_t a = cells[3 * i] - 1; a <= cells[3 * i] + 1; ++a)
-                for (int64_t b = cells[3 * i + 1] - 1; b <= cells[3 * i + 1] + 1; ++b)
-                    for (int64_t c = cells[3 * i + 2] - 1; c <= cells[3 * i + 2] + 1; ++c)
-                        for (int j = g.find(a, b, c); j >= 0; j = g.next[j]) {
-                            if (seen[j]) continue;
-                            float dx = xyz[3 * j] - px, dy = xyz[3 * j + 1] - py, dz = xyz[3 * j + 2] - pz;
-                            float d2 = dx * dx + dy * dy + dz * dz;
-                            if (d2 <= tol2) { seen[j] = 1; queue.push_back(j); }
-                        }
-        }
-        if ((int)queue.size() >= min_size && (int)queue.size() <= max_size) {
-            out.push_back(queue);
-            std::sort(out.back().begin(), out.back().end());
-        }
+    // one representative point per occupied cell (the head of its list), cells numbered in order of first appearance
+    std::vector<int> cell_of(n, -1), rep;
+    for (int i = 0; i < n; ++i) {
+        const int h = g.find(cells[3 * i], cells[3 * i + 1], cells[3 * i + 2]);  // smallest index in the cell
+        if (h == i) { cell_of[i] = (int)rep.size(); rep.push_back(i); }
     }
+    for (int i = 0; i < n; ++i)
+        if (cell_of[i] < 0) cell_of[i] = cell_of[g.find(cells[3 * i], cells[3 * i + 1], cells[3 * i + 2])];
+    const int nc = (int)rep.size();
+    std::vector<int> parent(nc);
+    for (int c = 0; c < nc; ++c) parent[c] = c;
+    auto root = [&](int c) {
+        while (parent[c] != c) { parent[c] = parent[parent[c]]; c = parent[c]; }
+        return c;
+    };
+    auto linked = [&](int ha, int hb) {  // is there a pair (i in cell a, j in cell b) within tol?
+        for (int i = ha; i >= 0; i = g.next[i]) {
+            const float px = xyz[3 * i], py = xyz[3 * i + 1], pz = xyz[3 * i + 2];
+            for (int j = hb; j >= 0; j = g.next[j]) {
+                const float dx = xyz[3 * j] - px, dy = xyz[3 * j + 1] - py, dz = xyz[3 * j + 2] - pz;
+                if (dx * dx + dy * dy + dz * dz <= tol2) return true;
+            }
+        }
+        return false;
+    };
+    for (int pass = 1; pass <= 2; ++pass)  // adjacent cells first: most far links are then already implied
+        for (int c = 0; c < nc; ++c) {
+            const int i = rep[c];
+            const int64_t cx = cells[3 * i], cy = cells[3 * i + 1], cz = cells[3 * i + 2];
+            for (int64_t a = -2; a <= 2; ++a)
+                for (int64_t b = -2; b <= 2; ++b)
+                    for (int64_t d = -2; d <= 2; ++d) {
+                        const int64_t m = std::max(std::max(a < 0 ? -a : a, b < 0 ? -b : b), d < 0 ? -d : d);
+                        if (m != pass) continue;
+                        const int hb = g.find(cx + a, cy + b, cz + d);
+                        if (hb < 0) continue;
+                        const int cb = cell_of[hb];
+                        if (cb < c) continue;  // each unordered pair once
+                        int ra = root(c), rb = root(cb);
+                        if (ra == rb) continue;
+                        if (linked(i, hb)) parent[std::max(ra, rb)] = std::min(ra, rb);
+                    }
+        }
+    // gather components; a component is discovered at its smallest point index, like a seeded flood fill would
+    std::vector<int> comp_of_root(nc, -1);
+    std::vector<std::vector<int>> comps;
+    for (int i = 0; i < n; ++i) {
+        const int r = root(cell_of[i]);
+        if (comp_of_root[r] < 0) { comp_of_root[r] = (int)comps.size(); comps.emplace_back(); }
+        comps[comp_of_root[r]].push_back(i);  // ascending indices by construction
+    }
+    for (auto &c : comps)
+        if ((int)c.size() >= min_size && (int)c.size() <= max_size) out.push_back(std::move(c));
     std::stable_sort(out.begin(), out.end(), [](const std::vector<int> &a, const std::vector<int> &b) { return a.size() > b.size(); });
 }
 

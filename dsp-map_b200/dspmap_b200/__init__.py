@@ -69,6 +69,7 @@ def load_library():
         "dspmap_get_occupancy": (i, [vp, f, fp, i, ip, fp]),
         "dspmap_get_occupancy_device": (i, [vp, f, vp, i, vp, vp]),
         "dspmap_clear_prediction": (i, [vp]),
+        "dspmap_pin_host_buffer": (i, [vp, vp, C.c_size_t]),
         "dspmap_get_tagged_cloud": (i, [vp, fp, i]),
         "dspmap_voxel_center": (None, [vp, i, fp]),
         "dspmap_voxel_index": (i, [vp, f, f, f, ip]),
@@ -105,7 +106,7 @@ EXPORTED_SYMBOLS = [
     "dspmap_update_tagged", "dspmap_update_device", "dspmap_set_prediction_variance", "dspmap_set_observation_stddev",
     "dspmap_set_newborn_weight", "dspmap_set_newborn_number", "dspmap_set_particle_record_flag",
     "dspmap_set_voxel_filter_resolution", "dspmap_get_occupancy", "dspmap_get_occupancy_device",
-    "dspmap_clear_prediction", "dspmap_get_tagged_cloud", "dspmap_voxel_center", "dspmap_voxel_index", "dspmap_uniform",
+    "dspmap_clear_prediction", "dspmap_pin_host_buffer", "dspmap_get_tagged_cloud", "dspmap_voxel_center", "dspmap_voxel_index", "dspmap_uniform",
     "dspmap_dims", "dspmap_dump_particles", "dspmap_load_particles", "dspmap_dump_voxel_objects",
     "dspmap_dump_observations", "dspmap_dump_pyramid_lists", "dspmap_cursors", "dspmap_set_cursors", "dspmap_counters",
     "dspmap_set_stage_limit", "dspmap_set_last_pose", "dspmap_set_stream", "dspmap_synchronize", "dspmap_profile_enable", "dspmap_profile_read",
@@ -167,6 +168,9 @@ class DSPMap:
 
     def close(self):
         if getattr(self, "h", None):
+            if getattr(self, "_pinned", None) is not None:
+                self.lib.dspmap_pin_host_buffer(self.h, None, 0)
+                self._pinned = None
             self.lib.dspmap_destroy(self.h)
             self.h = None
 
@@ -228,6 +232,11 @@ class DSPMap:
         n = C.c_int32(0)
         self._check(self.lib.dspmap_get_occupancy(self.h, threshold, _fp(xyz), self.V, C.byref(n), _fp(future_status)))
         return n.value, xyz[:n.value].copy(), future_status
+
+    def pin_host_buffer(self, arr):
+        """Page-locks a numpy array used as future_status so the reader DMAs straight into it; keep `arr` alive."""
+        self._pinned = arr
+        return self.lib.dspmap_pin_host_buffer(self.h, C.c_void_p(arr.ctypes.data if arr is not None else 0), arr.nbytes if arr is not None else 0)
 
     def clearOccupancyMapPrediction(self):
         self._check(self.lib.dspmap_clear_prediction(self.h))

@@ -14,6 +14,7 @@
 #ifndef DSPMAP_B200_H
 #define DSPMAP_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -104,6 +105,10 @@ int dspmap_get_occupancy(dspmap *m, float threshold, float *xyz_out, int cap, in
 /* Device-resident variant: d_xyz (cap*3 floats), d_count (1 int), d_future (V*T floats or NULL) are device
  * pointers; only enqueued. */
 int dspmap_get_occupancy_device(dspmap *m, float threshold, float *d_xyz, int cap, int *d_count, float *d_future);
+/* Optional: page-locks a caller-owned output buffer (e.g. the application's static future_status array) so that
+ * dspmap_get_occupancy can DMA straight into it instead of staging + memcpy. The buffer must outlive the handle or be
+ * released with bytes == 0. */
+int dspmap_pin_host_buffer(dspmap *m, void *ptr, size_t bytes);
 /* clearOccupancyMapPrediction (:431-438). */
 int dspmap_clear_prediction(dspmap *m);
 /* getKMClusterResult (:441-445): copies the last newborn input; returns the number of points. */

@@ -129,6 +129,10 @@ private:
     static float &filter_resolution() { static float r = 0.15f; return r; }  // voxel_filtered_resolution (:132)
     void read(int &obstacles_num, pcl::PointCloud<pcl::PointXYZ> &cloud, float *future_status, float threshold) {
         if (xyz_.empty()) xyz_.resize((size_t)3 * VOXEL_NUM);
+        if (future_status && future_status != pinned_) {  // the application's array is static (ex:371): pin it once
+            dspmap_pin_host_buffer(map_, future_status, sizeof(float) * (size_t)VOXEL_NUM * PREDICTION_TIMES);
+            pinned_ = future_status;
+        }
         int n = 0;
         dspmap_get_occupancy(map_, threshold, xyz_.data(), VOXEL_NUM, &n, future_status);
         obstacles_num = n;
@@ -140,4 +144,5 @@ private:
     }
     dspmap *map_ = nullptr;
     std::vector<float> xyz_;
+    float *pinned_ = nullptr;
 };
