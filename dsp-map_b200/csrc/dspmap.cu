@@ -228,14 +228,14 @@ int seed_particles(dspmap *m) {
 }
 
 // Enables dsp_div_known for divisor b only if it equals IEEE division bit for bit on every float in [-amax, amax].
-int verify_fast_div(dspmap *m, float b, float amax, int *ok) {
+int verify_fast_div(dspmap *m, float b, float amax, int mode, int *ok) {
     *ok = 0;
     if (!(b > 0.f) || !(amax > 0.f) || !std::isfinite(b) || !std::isfinite(amax)) return DSPMAP_OK;
     unsigned max_bits;
     memcpy(&max_bits, &amax, 4);
     const float r = 1.f / b;
     CK(cudaMemsetAsync(m->d_bad, 0, sizeof(int), m->stream));
-    k_verify_div<<<kSMs * 16, 256, 0, m->stream>>>(b, r, max_bits, m->d_bad);
+    k_verify_div<<<kSMs * 16, 256, 0, m->stream>>>(b, r, max_bits, mode, m->d_bad);
     int bad = 1;
     CK(cudaMemcpyAsync(&bad, m->d_bad, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
     CK(cudaStreamSynchronize(m->stream));
@@ -607,7 +607,7 @@ int dspmap_create(const dspmap_config *cfg, dspmap **out) {
     {   // (p + half) / res with p inside the map: dividends lie in (0, 2*half)
         mc.res_r = 1.f / mc.res;
         int ok = 0;
-        if (verify_fast_div(m, mc.res, 2.f * std::max(mc.hx, std::max(mc.hy, mc.hz)) * 1.0001f, &ok) != DSPMAP_OK) { dspmap_destroy(m); return DSPMAP_E_CUDA; }
+        if (verify_fast_div(m, mc.res, 2.f * std::max(mc.hx, std::max(mc.hy, mc.hz)) * 1.0001f, 0, &ok) != DSPMAP_OK) { dspmap_destroy(m); return DSPMAP_E_CUDA; }
         mc.fast_res = ok;
     }
     m->estimator.reset(cfg->uniform_seed);
@@ -655,7 +655,7 @@ static int update_common(dspmap *m, int n, int stride, const float *pts, float p
     if (rc != DSPMAP_OK) return rc;
     if (m->tables_dirty && (rc = gen_tables(m)) != DSPMAP_OK) return rc;
     if (m->sigma_dirty) {  // queries are clamped to |x - mu| / sigma <= 9.9: beyond 16 sigma both divisions clamp alike
-        if ((rc = verify_fast_div(m, m->sigma_ob, 16.f * m->sigma_ob, &m->fast_sigma)) != DSPMAP_OK) return rc;
+        if ((rc = verify_fast_div(m, m->sigma_ob, 16.f * m->sigma_ob, 1, &m->fast_sigma)) != DSPMAP_OK) return rc;
         m->sigma_dirty = false;
         fc.fast_sigma = m->fast_sigma;
     }
@@ -710,7 +710,7 @@ int dspmap_update_device(dspmap *m, int n, const float *d_pts, float px, float p
     if (rc != DSPMAP_OK) return rc;
     if (m->tables_dirty && (rc = gen_tables(m)) != DSPMAP_OK) return rc;
     if (m->sigma_dirty) {  // queries are clamped to |x - mu| / sigma <= 9.9: beyond 16 sigma both divisions clamp alike
-        if ((rc = verify_fast_div(m, m->sigma_ob, 16.f * m->sigma_ob, &m->fast_sigma)) != DSPMAP_OK) return rc;
+        if ((rc = verify_fast_div(m, m->sigma_ob, 16.f * m->sigma_ob, 1, &m->fast_sigma)) != DSPMAP_OK) return rc;
         m->sigma_dirty = false;
         fc.fast_sigma = m->fast_sigma;
     }
@@ -824,7 +824,7 @@ float dspmap_uniform(dspmap *m, float lo, float hi) { return m->estimator.unifor
 
 void dspmap_dims(const dspmap *m, int32_t *d) {
     const MapConst &mc = m->mc;
-    int v[] = {mc.V, mc.S, mc.P, mc.L, mc.T, mc.Nh, mc.Nv, mc.NBW, mc.max_ppv, mc.nx, mc.ny, mc.nz, mc.OBS, mc.model};
+    int v[] = {mc.V, mc.S, mc.P, mc.L, mc.T, mc.Nh, mc.Nv, mc.NBW, mc.max_ppv, mc.nx, mc.ny, mc.nz, mc.OBS, mc.model, mc.fast_res, m->fast_sigma};
     memcpy(d, v, sizeof(v));
 }
 

@@ -827,16 +827,22 @@ __global__ void __launch_bounds__(W2_THREADS, 3) k_weight2(MapConst mc, FrameCon
         if (act) dp.PA[dp.LA[lb + k0 + lane]].w = p.w * (fc.one_minus_Pd + sum);
     }
 }
-// Exhaustive check of dsp_div_known against IEEE division for ONE divisor over every non-negative float up to max_bits
-// (the quotient is odd in the dividend, so the negative half follows).
-__global__ void k_verify_div(float b, float r, unsigned max_bits, int *bad) {
+// Exhaustive check of dsp_div_known for ONE divisor over every float a with |a| <= max (both signs).  What has to be
+// identical to IEEE division is the integer the quotient is turned into, so that is what is compared:
+//   mode 0: (int)(a / b)                                   voxel coordinates (dsp_dynamic.h:1078-1080)
+//   mode 1: (int)(clamp(a / b, +-9.9) * 1000 + 10000)      PDF table index   (dsp_dynamic.h:1296-1300)
+__device__ __forceinline__ int verify_index(float q, int mode) {
+    if (mode == 0) return (int)q;
+    if (q > 9.9f) q = 9.9f;
+    else if (q < -9.9f) q = -9.9f;
+    return (int)(q * 1000 + 10000);
+}
+__global__ void k_verify_div(float b, float r, unsigned max_bits, int mode, int *bad) {
     int local = 0;
     for (unsigned long long u = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; u <= max_bits; u += (unsigned long long)gridDim.x * blockDim.x) {
         const float a = __uint_as_float((unsigned)u);
-        const float q = a / b;
-        const float f = dsp_div_known(a, b, r);
-        const float qn = (-a) / b, fn = dsp_div_known(-a, b, r);
-        if (__float_as_uint(q) != __float_as_uint(f) || __float_as_uint(qn) != __float_as_uint(fn)) ++local;
+        if (verify_index(a / b, mode) != verify_index(dsp_div_known(a, b, r), mode)) ++local;
+        if (verify_index((-a) / b, mode) != verify_index(dsp_div_known(-a, b, r), mode)) ++local;
     }
     if (local) atomicAdd(bad, local);
 }

@@ -305,6 +305,12 @@ class DSPMap:
         self._check(self.lib.dspmap_counters(self.h, c.ctypes.data_as(C.POINTER(C.c_int64))))
         return dict(zip(COUNTER_NAMES, [int(x) for x in c]))
 
+    def fast_paths(self):
+        """(fast_res, fast_sigma): whether the exhaustively verified exact fast divisions are enabled (sigma: after the next update)."""
+        d = np.zeros(16, np.int32)
+        self.lib.dspmap_dims(self.h, _ip(d))
+        return int(d[14]), int(d[15])
+
     def set_stage_limit(self, k):
         self._check(self.lib.dspmap_set_stage_limit(self.h, k))
 

@@ -120,7 +120,8 @@ int dspmap_voxel_index(const dspmap *m, float x, float y, float z, int *index);
 /* generateRandomFloat (:1551-1553) on the handle's uniform stream. */
 float dspmap_uniform(dspmap *m, float lo, float hi);
 
-/* Sizes: V, S, P, L, T, Nh, Nv, neighbour-table width, MAX ppv, nx, ny, nz, obs max, model (14 ints). */
+/* Sizes: V, S, P, L, T, Nh, Nv, neighbour-table width, MAX ppv, nx, ny, nz, obs max, model, then two flags: exact fast
+ * division verified for the voxel size / for sigma (16 ints). */
 void dspmap_dims(const dspmap *m, int32_t *out);
 
 /* State dump / load (tests, checkpointing).  Particle record = the reference's CSV columns (:339-344):
