@@ -305,7 +305,7 @@ int enqueue_frame_a(dspmap *m, const FrameConst &fc, const float *d_pts) {
             ++m->launches_frame;
             CK(cudaEventRecord(m->ev_join, m->side));
         }
-        LAUNCH(m, FAM_WEIGHT, k_weight2, kSMs * 6, W2_THREADS, 0, mc, fc, dp);
+        LAUNCH(m, FAM_WEIGHT, k_weight2, kSMs * 8, W2_THREADS, 0, mc, fc, dp);
         size_t smem5 = sizeof(float) * (DSP_LUT_HALF + 3) + sizeof(float4) * (size_t)mc.NB * (mc.OBS - 1);
         int chunks = (mc.L + K5_THREADS - 1) / K5_THREADS;
         if (m->fallback_armed) LAUNCH(m, FAM_WEIGHT, k_weight, kSMs * 2, K5_THREADS, smem5, mc, fc, dp, chunks);

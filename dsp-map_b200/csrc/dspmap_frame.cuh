@@ -751,80 +751,75 @@ __global__ void __launch_bounds__(CZ_THREADS) k_cz_chain(MapConst mc, FrameConst
         }
     }
 }
-// weights (dsp_dynamic.h:743-790): one warp per 32 particles of a pyramid, lanes = particles.  The 32 x 32 sub-tiles of G
-// are read as coalesced rows (lane = point) into registers one sub-tile AHEAD of the one being consumed, staged through a
-// per-warp shared tile, and each lane adds its particle's row in (neighbour-table, bin) order.
-#define W2_THREADS 256
-__global__ void __launch_bounds__(W2_THREADS, 3) k_weight2(MapConst mc, FrameConst fc, DevPtrs dp) {
-    __shared__ float tiles[(W2_THREADS / 32) * 32 * TILE_LD];
-    __shared__ float czall[(W2_THREADS / 32) * 32];
+// weights (dsp_dynamic.h:743-790): a CTA per 32 particles of a pyramid.  For one neighbour pyramid at a time, ALL threads
+// turn the chunk's contiguous 32 x np tile of G into quotient terms (P_d * g) / C_z (flat, coalesced loads); then warp 0,
+// lane = particle, adds its row in bin order.  Neighbours are visited in table order, so each particle's sum is one fp32
+// chain in the reference's order.  Two term buffers let the next neighbour's divisions overlap the current chain.
+#define W2_THREADS 128
+#define W2_NP 100  // padded row length (np <= 99; odd stride: no bank conflicts in the chain)
+__global__ void __launch_bounds__(W2_THREADS) k_weight2(MapConst mc, FrameConst fc, DevPtrs dp) {
+    __shared__ float terms[2][32 * (W2_NP + 1)];
+    __shared__ float czs[2][W2_NP];
+    __shared__ int s_item;
     if (!use_pair_buffer(mc, dp)) return;
-    float *tile = tiles + (threadIdx.x >> 5) * (32 * TILE_LD);
-    float *czs = czall + (threadIdx.x >> 5) * 32;
-    const int lane = threadIdx.x & 31;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int nchunks = dp.chunk_off[mc.P];
     for (;;) {
-        int c = 0;
-        if (lane == 0) c = atomicAdd(&dp.st->work_w2, 1);
-        c = __shfl_sync(FULLMASK, c, 0);
+        __syncthreads();
+        if (tid == 0) s_item = atomicAdd(&dp.st->work_w2, 1);
+        __syncthreads();
+        const int c = s_item;
         if (c >= nchunks) break;
         const int a = chunk_to_pyramid(dp.chunk_off, mc.P, c);
         const int k0 = (c - dp.chunk_off[a]) << 5;
         const int ln = dp.plen[a], lb = dp.poff[a];
         const int nrows = min(32, ln - k0);
-        bool act = lane < nrows;
-        const float4 p = act ? dp.LP[lb + k0 + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
-        if (act) {
+        const int nn = dp.nbr[a * mc.NBW];
+        // chain state lives in warp 0 (lane = particle)
+        bool act = false;
+        float pw = 0.f, sum = 0.f;
+        if (wid == 0 && lane < nrows) {
+            const float4 p = dp.LP[lb + k0 + lane];
+            pw = p.w;
             const float dist = sqrtf(p.x * p.x + p.y * p.y + p.z * p.z);
             const float maxlen = __int_as_float(dp.obs_maxbits[a]);
-            if (maxlen > 0.f && dist > maxlen + mc.occl) act = false;  // occluded (:761): weight unchanged
+            act = !(maxlen > 0.f && dist > maxlen + mc.occl);  // occluded particles keep their weight (:761)
         }
-        const int nn = dp.nbr[a * mc.NBW];
-        // sub-tile iterator over (neighbour ns, point block z0)
-        int ns = -1, z0 = 0, np = 0;
-        const float *gb = nullptr, *cz = nullptr;
-        auto advance = [&]() -> int {  // moves to the next sub-tile; returns its number of points, 0 when done
-            z0 += 32;
-            while (ns < 0 || z0 >= np) {
-                if (++ns >= nn) return 0;
+        int buf = 0, prev_np = 0, prev_ld = 1;
+        for (int ns = 0; ns <= nn; ++ns) {
+            // phase 1 (warps 1..3): quotient terms of neighbour ns into terms[buf], while warp 0 runs the previous chain
+            int np = 0, ld = 1;
+            if (ns < nn) {
                 const int b = dp.nbr[a * mc.NBW + 1 + ns];
                 np = min(dp.obs_cnt[b], mc.OBS - 1);
-                z0 = 0;
-                if (np == 0) continue;
-                gb = dp.G + (size_t)dp.rowbase[b] + (size_t)(dp.cum[b * mc.NBW + nb_index_of(mc, dp, b, a)] + k0) * np;
-                cz = dp.CZ + (size_t)b * mc.OBS;
+                ld = np | 1;
+                if (np > 0 && wid > 0) {
+                    const int t96 = tid - 32;
+                    const float *gb = dp.G + (size_t)dp.rowbase[b] + (size_t)(dp.cum[b * mc.NBW + nb_index_of(mc, dp, b, a)] + k0) * np;
+                    const float *cz = dp.CZ + (size_t)b * mc.OBS;
+                    for (int z = t96; z < np; z += W2_THREADS - 32) czs[buf][z] = cz[z];
+                    asm volatile("bar.sync 1, 96;" ::: "memory");  // only the three producer warps
+                    const int nfl = nrows * np;
+                    const unsigned magic = np > 1 ? 0xffffffffu / (unsigned)np + 1u : 0u;  // exact f / np for f < 65536
+                    for (int f = t96; f < nfl; f += W2_THREADS - 32) {
+                        const int r = np > 1 ? (int)__umulhi((unsigned)f, magic) : f;
+                        const int z = f - r * np;
+                        terms[buf][r * ld + z] = fc.Pd * __ldg(gb + f) / czs[buf][z];
+                    }
+                }
             }
-            return min(32, np - z0);
-        };
-        float v[32], czv = 1.f;
-        auto prefetch = [&](int nsub) {
-            if (lane < nsub) {
-                const float *src = gb + z0 + lane;
-#pragma unroll
-                for (int r = 0; r < 32; ++r) v[r] = r < nrows ? __ldg(src + (size_t)r * np) : 0.f;
-                czv = cz[z0 + lane];
+            // phase 2 (warp 0): add the previous neighbour's terms, particle rows in bin order
+            if (wid == 0 && act && prev_np > 0) {
+                const float *t = terms[buf ^ 1] + lane * prev_ld;
+#pragma unroll 8
+                for (int z = 0; z < prev_np; ++z) sum += t[z];
             }
-        };
-        float sum = 0.f;
-        int nsub = advance();
-        if (nsub) prefetch(nsub);
-        while (nsub) {
-            if (lane < nsub) {
-#pragma unroll
-                for (int r = 0; r < 32; ++r) tile[r * TILE_LD + lane] = v[r];
-                czs[lane] = czv;
-            }
-            __syncwarp();
-            const int cur = nsub;
-            nsub = advance();
-            if (nsub) prefetch(nsub);  // in flight while the current sub-tile is consumed
-            if (act) {
-#pragma unroll 4
-                for (int zl = 0; zl < cur; ++zl) sum += fc.Pd * tile[lane * TILE_LD + zl] / czs[zl];
-            }
-            __syncwarp();
+            __syncthreads();
+            prev_np = np;
+            prev_ld = ld;
+            buf ^= 1;
         }
-        if (act) dp.PA[dp.LA[lb + k0 + lane]].w = p.w * (fc.one_minus_Pd + sum);
+        if (wid == 0 && lane < nrows && act) dp.PA[dp.LA[lb + k0 + lane]].w = pw * (fc.one_minus_Pd + sum);
     }
 }
 // Exhaustive check of dsp_div_known for ONE divisor over every float a with |a| <= max (both signs).  What has to be
@@ -1039,13 +1034,30 @@ __global__ void __launch_bounds__(256) k_nb_place(MapConst mc, FrameConst fc, De
         const int nfree = min(mask_free(mc, msk), c);
         long long last = -1;
         int my_slot[4] = {-1, -1, -1, -1}, my_cand[4] = {0, 0, 0, 0};
+        const bool in_regs = c <= 256;  // the usual case: the segment's keys live in registers for all rounds
+        u64 K[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int j = q * 32 + lane;
+            K[q] = (in_regs && j < c) ? (((u64)(unsigned)dp.cseg[b + j] << 32) | (unsigned)j) : ~0ull;
+        }
         for (int r = 0; r < nfree; ++r) {
             u64 best = ~0ull;  // (key << 32) | position
-            for (int j = lane; j < c; j += 32) {
-                const long long kj = dp.cseg[b + j];
-                if (kj > last) best = min(best, ((u64)kj << 32) | (unsigned)j);
+            if (in_regs) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) best = min(best, K[q]);
+            } else {
+                for (int j = lane; j < c; j += 32) {
+                    const long long kj = dp.cseg[b + j];
+                    if (kj > last) best = min(best, ((u64)kj << 32) | (unsigned)j);
+                }
             }
             for (int sft = 16; sft > 0; sft >>= 1) best = min(best, __shfl_xor_sync(FULLMASK, best, sft));
+            if (in_regs) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (K[q] == best) K[q] = ~0ull;
+            }
             last = (long long)(best >> 32);
             const int slot = mask_nth_free(mc, msk, 0);
             if (slot < 64) msk.x |= 1ull << slot; else msk.y |= 1ull << (slot - 64);
