@@ -84,6 +84,7 @@ struct dspmap {
     int vz_blocks = 0;
     // the recompute kernels (k_ck / k_weight) are launched only while the pair buffer may overflow
     bool fallback_armed = true;
+    FrameConst shard_fc;  // frame scalars carried across the phases of a sharded frame
     long long host_u_cur = 0;  // uniform draws consumed on the host while seeding
     VelocityEstimator estimator;
     // statistics
@@ -326,7 +327,7 @@ int enqueue_frame_b(dspmap *m, const FrameConst &fc, const float *d_tagged) {
             LAUNCH(m, FAM_NEWBORN, k_nb_point0, grid_for(fc.n_tagged, B), B, 0, mc, fc, dp);
             LAUNCH(m, FAM_NEWBORN, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{dp.ninmap, dp.nrank, nullptr, 0, fc.n_tagged}, ScanJob{}, ScanJob{}}});
             LAUNCH(m, FAM_NEWBORN, k_nb_mask, grid_for((long long)fc.n_tagged * fc.nb_num, B), B, 0, mc, fc, dp);
-            LAUNCH(m, FAM_NEWBORN, k_nb_point1, grid_for((long long)fc.n_tagged * 32, B), B, 0, mc, fc, dp);
+            LAUNCH(m, FAM_NEWBORN, k_nb_point1, grid_for((long long)fc.n_tagged * 32, B), B, 0, mc, fc, dp, 0);
             LAUNCH(m, FAM_NEWBORN, k_scan_small, 2, 1024, 0, ScanJobs{{ScanJob{dp.nvcnt, dp.nvoff, nullptr, 0, fc.n_tagged}, ScanJob{dp.nrcnt, dp.nroff, nullptr, 0, fc.n_tagged}, ScanJob{}}});
             LAUNCH(m, FAM_NEWBORN, k_nb_cand, grid_for((long long)fc.n_tagged * fc.nb_num, B), B, 0, mc, fc, dp, (u64)m->cfg.uniform_seed);
             LAUNCH(m, FAM_NEWBORN, k_group_owner, kSMs * 2, B, 0, dp, &dp.st->n_cand_owner, dp.cowner, dp.ccnt, dp.cbase, &dp.st->cand_top);
@@ -501,8 +502,9 @@ int dspmap_create(const dspmap_config *cfg, dspmap **out) {
     mc.OBS = cfg->max_observations_per_pyramid > 0 ? cfg->max_observations_per_pyramid : 100;
     mc.G = cfg->gaussian_table_size > 0 ? cfg->gaussian_table_size : 10000000;
     mc.occl = cfg->occlusion_margin;
-    mc.z_begin = cfg->shard_z_begin;
-    mc.z_end = cfg->shard_z_end > 0 ? cfg->shard_z_end : mc.nz;
+    mc.z_begin = 0;
+    mc.z_end = mc.nz;
+    mc.sharded = 0; mc.rank = 0; mc.nranks = 1; mc.z_per_rank = mc.nz; mc.v_lo = 0; mc.v_hi = mc.V;
     for (int i = 0; i < DSP_MAX_T; ++i) mc.ft[i] = cfg->prediction_future_time[i];
     if (mc.S > DSP_MAX_SLOTS || mc.S < 1 || mc.T > DSP_MAX_T || mc.T < 0 || mc.V <= 0 || mc.P <= 0 ||
         mc.Nh + mc.Nv + 2 > DSP_MAX_PLANES || (long long)mc.V * DSP_MAX_SLOTS > 2147483647ll || mc.L < 1 ||
@@ -536,7 +538,7 @@ int dspmap_create(const dspmap_config *cfg, dspmap **out) {
     A(dp.obs_capoff, P + 1); A(dp.OSEG, MP); A(dp.OBSP, P * mc.OBS); A(dp.CZ, P * mc.OBS); A(dp.INV, MP + P * 0 + 1024);
     A(dp.MBA, CL); A(dp.MBB, CL); A(dp.MBkey, CL); A(dp.MBdst, CL); A(dp.MBq, CL);
     A(dp.mcnt, V); A(dp.mfill, V); A(dp.mbase, V); A(dp.mowner, V); A(dp.mseg, CL);
-    A(dp.Fkey, CL); A(dp.Faddr, CL); A(dp.Fq, CL); A(dp.pcount, P); A(dp.pfill, P); A(dp.poff, P + 1); A(dp.plen, P);
+    A(dp.Fkey, CL); A(dp.Faddr, CL); A(dp.Fq, CL); A(dp.FP, CL); A(dp.PSpay, CL); A(dp.pcount, P); A(dp.pfill, P); A(dp.poff, P + 1); A(dp.plen, P);
     A(dp.PSkey, CL); A(dp.PSaddr, CL); A(dp.LA, CL); A(dp.LP, CL); A(dp.PW, CL);
     mc.cap_pairs = 128ll << 20;  // 512 MB of fp32 pair terms; larger frames fall back to the recompute kernels
     A(dp.G, (size_t)mc.cap_pairs); A(dp.cum, P * mc.NBW); A(dp.totlen, P); A(dp.pairs, P + 1); A(dp.rowbase, P + 1);
@@ -719,6 +721,121 @@ int dspmap_update_device(dspmap *m, int n, const float *d_pts, float px, float p
     if ((rc = enqueue_frame_a(m, fc, d_pts)) != DSPMAP_OK) return rc;
     if ((rc = enqueue_frame_b(m, fc, d_tagged)) != DSPMAP_OK) return rc;
     if (m->vz_mode) return frame_epilogue(m);  // keep the ordered-noise path armed only as long as it is needed
+    return DSPMAP_OK;
+}
+
+int dspmap_shard_config(dspmap *m, int rank, int nranks, float *xsend, float *xrecv, int cap_x, float *gsend, float *grecv,
+                        int cap_g, int32_t *nst) {
+    if (!m || nranks < 1 || rank < 0 || rank >= nranks || cap_x < 1 || cap_g < 1 || !xsend || !xrecv || !gsend || !grecv || !nst) {
+        g_err = "bad shard configuration";
+        return DSPMAP_E_BAD_ARG;
+    }
+    MapConst &mc = m->mc;
+    mc.sharded = 1;
+    mc.rank = rank;
+    mc.nranks = nranks;
+    mc.z_per_rank = (mc.nz + nranks - 1) / nranks;
+    const int z0 = std::min(mc.nz, rank * mc.z_per_rank), z1 = std::min(mc.nz, (rank + 1) * mc.z_per_rank);
+    mc.z_begin = z0;
+    mc.z_end = z1;
+    mc.v_lo = z0 * mc.nx * mc.ny;
+    mc.v_hi = z1 * mc.nx * mc.ny;
+    mc.cap_x = cap_x;
+    mc.cap_g = cap_g;
+    m->dp.xsend = xsend; m->dp.xrecv = xrecv; m->dp.gsend = gsend; m->dp.grecv = grecv; m->dp.nst_shared = nst;
+    m->fallback_armed = false;  // sharded frames always use the pair buffer (checked: overflow flag otherwise)
+    return DSPMAP_OK;
+}
+
+int dspmap_shard_phase(dspmap *m, int phase, int n, const float *d_pts, float px, float py, float pz, double t, float qw,
+                       float qx, float qy, float qz, const float *d_tagged, int n_tagged) {
+    if (!m || !m->mc.sharded) { g_err = "handle is not sharded"; return DSPMAP_E_BAD_ARG; }
+    CK(cudaSetDevice(m->cfg.device));
+    const MapConst &mc = m->mc;
+    const int B = 256;
+    int rc;
+    if (phase == 0) {
+        if (n < 0 || n > m->max_points || n_tagged > m->max_points) { g_err = "bad argument"; return DSPMAP_E_BAD_ARG; }
+        FrameConst fc;
+        rc = frame_prologue(m, n, px, py, pz, t, qw, qx, qy, qz, &fc);
+        if (rc != DSPMAP_OK) return rc;
+        if (m->tables_dirty && (rc = gen_tables(m)) != DSPMAP_OK) return rc;
+        if (m->sigma_dirty) {
+            if ((rc = verify_fast_div(m, m->sigma_ob, 16.f * m->sigma_ob, 1, &m->fast_sigma)) != DSPMAP_OK) return rc;
+            m->sigma_dirty = false;
+            fc.fast_sigma = m->fast_sigma;
+        }
+        if ((rc = ensure_cand_capacity(m)) != DSPMAP_OK) return rc;
+        fc.n_tagged = n_tagged;
+        m->fallback_armed = false;
+        m->shard_fc = fc;
+    }
+    const FrameConst &fc = m->shard_fc;
+    DevPtrs dp = m->dp;
+    if (phase == 0) {
+        dp.pts = d_pts;
+        m->launches_frame = 0;
+        LAUNCH(m, FAM_SETUP, k_frame_setup, 1, 256, 0, mc, fc, dp);
+        if (fc.n_points > 0) LAUNCH(m, FAM_OBS, k_obs_classify, grid_for(fc.n_points, B), B, 0, mc, fc, dp);
+        LAUNCH(m, FAM_OBS, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{dp.obs_cnt, dp.obs_off, dp.obs_capoff, mc.OBS - 1, mc.P}, ScanJob{}, ScanJob{}}});
+        if (fc.n_points > 0) {
+            LAUNCH(m, FAM_OBS, k_obs_scatter, grid_for(fc.n_points, B), B, 0, mc, fc, dp);
+            LAUNCH(m, FAM_OBS, k_obs_rank, grid_for(fc.n_points, B), B, 0, mc, fc, dp);
+        }
+        if (fc.vz_mode) {
+            LAUNCH(m, FAM_PREDICT, k_vz_count, grid_for(mc.V, B), B, 0, mc, dp);
+            LAUNCH(m, FAM_PREDICT, k_scan_blocksum, m->vz_blocks, 256, 0, dp.vzcnt, mc.V, dp.vzblk);
+            LAUNCH(m, FAM_PREDICT, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{dp.vzblk, dp.vzblkoff, nullptr, 0, m->vz_blocks}, ScanJob{}, ScanJob{}}});
+            LAUNCH(m, FAM_PREDICT, k_scan_apply, m->vz_blocks, 256, 0, dp.vzcnt, mc.V, dp.vzblkoff, dp.vzoff, m->vz_blocks);
+        }
+        LAUNCH(m, FAM_ENUM, k_enumerate, grid_for(mc.V, B), B, 0, mc, dp, 1);
+        LAUNCH(m, FAM_PREDICT, k_predict, kSMs * 8, B, 0, mc, fc, dp);
+        if (fc.vz_mode) LAUNCH(m, FAM_PREDICT, k_vz_advance, 1, 32, 0, mc, dp);
+    } else if (phase == 1) {
+        LAUNCH(m, FAM_ARRIVE, k_shard_import, grid_for((long long)mc.nranks * mc.cap_x, B), B, 0, mc, dp);
+        LAUNCH(m, FAM_ARRIVE, k_group_owner, kSMs * 2, B, 0, dp, &dp.st->n_mov_owner, dp.mowner, dp.mcnt, dp.mbase, &dp.st->mov_top);
+        LAUNCH(m, FAM_ARRIVE, k_group_scatter, kSMs * 4, B, 0, &dp.st->n_mov, dp.MBdst, dp.MBkey, dp.mbase, dp.mfill, dp.mseg, (int *)nullptr);
+        LAUNCH(m, FAM_ARRIVE, k_arrive, kSMs * 4, B, 0, mc, fc, dp);
+        LAUNCH(m, FAM_PYRAMID, k_shard_pack_fov, kSMs * 4, B, 0, mc, dp);
+    } else if (phase == 2) {
+        dp.tagged = d_tagged;
+        LAUNCH(m, FAM_PYRAMID, k_shard_fov_gathered, kSMs * 8, B, 0, mc, dp, 0);
+        LAUNCH(m, FAM_PYRAMID, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{dp.pcount, dp.poff, nullptr, 0, mc.P}, ScanJob{}, ScanJob{}}});
+        LAUNCH(m, FAM_PYRAMID, k_shard_fov_gathered, kSMs * 8, B, 0, mc, dp, 1);
+        LAUNCH(m, FAM_PYRAMID, k_pyr_sort, std::min(mc.P, kSMs * 3), 512, PYR_SORT_CAP * sizeof(u64), mc, dp, fc.Pd);
+        LAUNCH(m, FAM_CK, k_pair_prep, grid_for(mc.P, B), B, 0, mc, dp);
+        LAUNCH(m, FAM_CK, k_scan_small, 2, 1024, 0, ScanJobs{{ScanJob{dp.pairs, dp.rowbase, nullptr, 0, mc.P}, ScanJob{dp.chunks, dp.chunk_off, nullptr, 0, mc.P}, ScanJob{}}});
+        LAUNCH(m, FAM_CK, k_pair_eval, kSMs * 2, EVAL_THREADS, sizeof(float) * (DSP_LUT_HALF + 3 + (EVAL_THREADS / 32) * 32 * TILE_LD), mc, fc, dp);
+        LAUNCH(m, FAM_CK, k_cz_chain, std::min(mc.P, kSMs * 3), CZ_THREADS, sizeof(float) * (2 * CZ_TILE + 2 * CZ_JT), mc, fc, dp);
+        LAUNCH(m, FAM_WEIGHT, k_weight2, kSMs * 8, W2_THREADS, 0, mc, fc, dp);
+        LAUNCH(m, FAM_NORM, k_norm, 1, 128, 0, mc, fc, dp);
+        if (fc.n_tagged > 0 && fc.nb_num > 0) {
+            LAUNCH(m, FAM_NEWBORN, k_nb_point0, grid_for(fc.n_tagged, B), B, 0, mc, fc, dp);
+            LAUNCH(m, FAM_NEWBORN, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{dp.ninmap, dp.nrank, nullptr, 0, fc.n_tagged}, ScanJob{}, ScanJob{}}});
+            LAUNCH(m, FAM_NEWBORN, k_nb_mask, grid_for((long long)fc.n_tagged * fc.nb_num, B), B, 0, mc, fc, dp);
+            LAUNCH(m, FAM_NEWBORN, k_nb_point1, grid_for((long long)fc.n_tagged * 32, B), B, 0, mc, fc, dp, 1);
+        }
+    } else if (phase == 3) {
+        dp.tagged = d_tagged;
+        int newborn_ran = 0;
+        if (fc.n_tagged > 0 && fc.nb_num > 0) {
+            LAUNCH(m, FAM_NEWBORN, k_nb_point1, grid_for((long long)fc.n_tagged * 32, B), B, 0, mc, fc, dp, 2);
+            LAUNCH(m, FAM_NEWBORN, k_scan_small, 2, 1024, 0, ScanJobs{{ScanJob{dp.nvcnt, dp.nvoff, nullptr, 0, fc.n_tagged}, ScanJob{dp.nrcnt, dp.nroff, nullptr, 0, fc.n_tagged}, ScanJob{}}});
+            LAUNCH(m, FAM_NEWBORN, k_nb_cand, grid_for((long long)fc.n_tagged * fc.nb_num, B), B, 0, mc, fc, dp, (u64)m->cfg.uniform_seed);
+            LAUNCH(m, FAM_NEWBORN, k_group_owner, kSMs * 2, B, 0, dp, &dp.st->n_cand_owner, dp.cowner, dp.ccnt, dp.cbase, &dp.st->cand_top);
+            LAUNCH(m, FAM_NEWBORN, k_group_scatter, kSMs * 4, B, 0, &dp.st->n_cand, dp.Cdst, dp.Ckey, dp.cbase, dp.cfill, dp.cseg, dp.csegi);
+            LAUNCH(m, FAM_NEWBORN, k_nb_place, kSMs * 8, B, 0, mc, fc, dp);
+            newborn_ran = 1;
+        }
+        LAUNCH(m, FAM_RESAMPLE, k_voxel_list, grid_for(mc.V, B), B, 0, mc, dp);
+        LAUNCH(m, FAM_RESAMPLE, k_resample, kSMs * 8, 256, 0, mc, fc, dp);
+        LAUNCH(m, FAM_CLEANUP, k_cleanup, kSMs * 2, B, 0, mc, fc, dp, newborn_ran, 0);
+        CK(cudaMemcpyAsync(m->h_state, m->dp.st, sizeof(DevState), cudaMemcpyDeviceToHost, m->stream));
+    } else {
+        g_err = "phase must be 0..3";
+        return DSPMAP_E_BAD_ARG;
+    }
+    CK(cudaGetLastError());
     return DSPMAP_OK;
 }
 
@@ -970,6 +1087,7 @@ int dspmap_synchronize(dspmap *m) {
     if (!m) return DSPMAP_E_BAD_ARG;
     CK(cudaStreamSynchronize(m->stream));
     if (m->profile) prof_collect(m);
+    if (m->update_counter > 0) m->last_state = *m->h_state;  // every frame ends with an async copy of the device state
     return DSPMAP_OK;
 }
 int dspmap_profile_enable(dspmap *m, int on) {

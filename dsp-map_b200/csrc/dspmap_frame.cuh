@@ -38,6 +38,10 @@ __global__ void k_frame_setup(MapConst mc, FrameConst fc, DevPtrs dp) {
         s->norm = 0.f;
         s->w_new = 0.f;
     }
+    if (mc.sharded) {
+        for (int r = threadIdx.x; r < mc.nranks; r += blockDim.x) reinterpret_cast<int *>(dp.xsend + (size_t)r * (SLAB_HDR + mc.cap_x * XREC))[0] = 0;
+        if (threadIdx.x == 0) reinterpret_cast<int *>(dp.gsend)[0] = 0;
+    }
     for (int i = threadIdx.x; i < mc.P; i += blockDim.x) {
         dp.obs_cnt[i] = 0;
         dp.obs_fill[i] = 0;
@@ -294,11 +298,24 @@ __global__ void k_predict(MapConst mc, FrameConst fc, DevPtrs dp) {
                 dp.Fkey[k] = key;
                 dp.Faddr[k] = a;
                 dp.Fq[k] = q;
-                atomicAdd(&dp.pcount[q], 1);
+                dp.FP[k] = A;
+                if (!mc.sharded) atomicAdd(&dp.pcount[q], 1);
             }
         } else {
             mask_atomic_clear(dp.M, v, s);  // "remove from ori voxel first" (:1210)
             B.w = 7.f;
+            if (mc.sharded && (d < mc.v_lo || d >= mc.v_hi)) {  // crosses into another rank's voxel subspace
+                float *slab = dp.xsend + (size_t)dsp_owner(mc, d) * (SLAB_HDR + mc.cap_x * XREC);
+                int k = atomicAdd(reinterpret_cast<int *>(slab), 1);
+                if (k >= mc.cap_x) { dp.st->overflow = 1; continue; }
+                float *rec = slab + SLAB_HDR + (size_t)k * XREC;
+                *reinterpret_cast<float4 *>(rec) = A;
+                *reinterpret_cast<float4 *>(rec + 4) = B;
+                reinterpret_cast<int *>(rec)[8] = key;
+                reinterpret_cast<int *>(rec)[9] = d;
+                reinterpret_cast<int *>(rec)[10] = q;
+                continue;
+            }
             int k = agg_inc(&dp.st->n_mov);
             dp.MBA[k] = A;
             dp.MBB[k] = B;
@@ -389,7 +406,68 @@ __global__ void k_arrive(MapConst mc, FrameConst fc, DevPtrs dp) {
             dp.Fkey[k] = key;  // list order is the order of processing, i.e. the SOURCE sweep key
             dp.Faddr[k] = a;
             dp.Fq[k] = q;
+            dp.FP[k] = dp.MBA[i];
+            if (!mc.sharded) atomicAdd(&dp.pcount[q], 1);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Sharded mode (multi-GPU, voxel subspaces = z slabs).  After the all-to-all, movers that crossed into this rank's slab
+// join the local mover list; their sweep keys are global, so k_arrive replays them in the reference's order.  After the
+// arrival pass every rank contributes its registered particles to an all-gather, and all ranks build identical global
+// pyramid lists (slot addresses are only meaningful on the owner; -1 elsewhere).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void k_shard_import(MapConst mc, DevPtrs dp) {
+    const int slab = SLAB_HDR + mc.cap_x * XREC;
+    const int total = mc.nranks * mc.cap_x;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const int src = t / mc.cap_x, j = t - src * mc.cap_x;
+        if (src == mc.rank) continue;
+        const float *sl = dp.xrecv + (size_t)src * slab;
+        if (j >= min(reinterpret_cast<const int *>(sl)[0], mc.cap_x)) continue;
+        const float *rec = sl + SLAB_HDR + (size_t)j * XREC;
+        const int d = reinterpret_cast<const int *>(rec)[9];
+        int k = agg_inc(&dp.st->n_mov);
+        dp.MBA[k] = *reinterpret_cast<const float4 *>(rec);
+        dp.MBB[k] = *reinterpret_cast<const float4 *>(rec + 4);
+        dp.MBkey[k] = reinterpret_cast<const int *>(rec)[8];
+        dp.MBdst[k] = d;
+        dp.MBq[k] = reinterpret_cast<const int *>(rec)[10];
+        if (atomicAdd(&dp.mcnt[d], 1) == 0) dp.mowner[agg_inc(&dp.st->n_mov_owner)] = d;
+    }
+}
+__global__ void k_shard_pack_fov(MapConst mc, DevPtrs dp) {
+    const int n = dp.st->n_fov;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        reinterpret_cast<int *>(dp.gsend)[0] = min(n, mc.cap_g);
+        if (n > mc.cap_g) dp.st->overflow = 1;
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < min(n, mc.cap_g); i += gridDim.x * blockDim.x) {
+        float *rec = dp.gsend + SLAB_HDR + (size_t)i * GREC;
+        reinterpret_cast<int *>(rec)[0] = dp.Fkey[i];
+        reinterpret_cast<int *>(rec)[1] = dp.Fq[i];
+        reinterpret_cast<int *>(rec)[2] = dp.Faddr[i];
+        *reinterpret_cast<float4 *>(rec + 4) = dp.FP[i];
+    }
+}
+// pass 0 counts per pyramid, pass 1 scatters (after the scan of the counts)
+__global__ void k_shard_fov_gathered(MapConst mc, DevPtrs dp, int pass) {
+    const int slab = SLAB_HDR + mc.cap_g * GREC;
+    const int total = mc.nranks * mc.cap_g;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const int src = t / mc.cap_g, j = t - src * mc.cap_g;
+        const float *sl = dp.grecv + (size_t)src * slab;
+        if (j >= reinterpret_cast<const int *>(sl)[0]) continue;
+        const float *rec = sl + SLAB_HDR + (size_t)j * GREC;
+        const int q = reinterpret_cast<const int *>(rec)[1];
+        if (pass == 0) {
             atomicAdd(&dp.pcount[q], 1);
+        } else {
+            const int pos = dp.poff[q] + atomicAdd(&dp.pfill[q], 1);
+            dp.PSkey[pos] = reinterpret_cast<const int *>(rec)[0];
+            dp.PSaddr[pos] = src == mc.rank ? reinterpret_cast<const int *>(rec)[2] : -1;
+            dp.PSpay[pos] = *reinterpret_cast<const float4 *>(rec + 4);
         }
     }
 }
@@ -421,7 +499,7 @@ __global__ void __launch_bounds__(512) k_pyr_sort(MapConst mc, DevPtrs dp, float
             int m = 1;
             while (m < n) m <<= 1;
             for (int i = threadIdx.x; i < m; i += blockDim.x)
-                skey[i] = i < n ? ((u64)(unsigned)dp.PSkey[b + i] << 32) | (unsigned)dp.PSaddr[b + i] : ~0ull;
+                skey[i] = i < n ? ((u64)(unsigned)dp.PSkey[b + i] << 32) | (unsigned)(mc.sharded ? i : dp.PSaddr[b + i]) : ~0ull;
             __syncthreads();
             for (int k = 2; k <= m; k <<= 1)
                 for (int j = k >> 1; j > 0; j >>= 1) {
@@ -437,12 +515,18 @@ __global__ void __launch_bounds__(512) k_pyr_sort(MapConst mc, DevPtrs dp, float
                 }
             for (int i = threadIdx.x; i < n; i += blockDim.x) {
                 int a = (int)(unsigned)(skey[i] & 0xffffffffull);
+                float4 pa;
+                if (mc.sharded) {  // the low word is the position inside the segment: address and payload come from there
+                    pa = dp.PSpay[b + a];
+                    a = dp.PSaddr[b + a];
+                } else {
+                    pa = dp.PA[a];
+                }
                 if (i < keep) {
-                    const float4 pa = dp.PA[a];
                     dp.LA[b + i] = a;
                     dp.LP[b + i] = pa;
                     dp.PW[b + i] = Pd * pa.w;
-                } else {  // pyramid full: the particle vanishes and frees its voxel slot (:1256-1259)
+                } else if (a >= 0) {  // pyramid full: the particle vanishes and frees its voxel slot (:1256-1259)
                     mask_atomic_clear(dp.M, a / mc.S, a % mc.S);
                     atomicAdd(&dp.st->n_pyramid_full, 1);
                 }
@@ -454,11 +538,11 @@ __global__ void __launch_bounds__(512) k_pyr_sort(MapConst mc, DevPtrs dp, float
                 for (int j = 0; j < n; ++j) r += dp.PSkey[b + j] < ki;
                 int a = dp.PSaddr[b + i];
                 if (r < keep) {
-                    const float4 pa = dp.PA[a];
+                    const float4 pa = mc.sharded ? dp.PSpay[b + i] : dp.PA[a];
                     dp.LA[b + r] = a;
                     dp.LP[b + r] = pa;
                     dp.PW[b + r] = Pd * pa.w;
-                } else {
+                } else if (a >= 0) {
                     mask_atomic_clear(dp.M, a / mc.S, a % mc.S);
                     atomicAdd(&dp.st->n_pyramid_full, 1);
                 }
@@ -585,7 +669,7 @@ __global__ void __launch_bounds__(K5_THREADS) k_weight(MapConst mc, FrameConst f
             sum += fc.Pd * gk / o.w;
         }
         int a = dp.LA[lb + j];
-        dp.PA[a].w = p.w * (fc.one_minus_Pd + sum);
+        if (a >= 0) dp.PA[a].w = p.w * (fc.one_minus_Pd + sum);
     }
 }
 
@@ -775,10 +859,14 @@ __global__ void __launch_bounds__(W2_THREADS) k_weight2(MapConst mc, FrameConst 
         const int ln = dp.plen[a], lb = dp.poff[a];
         const int nrows = min(32, ln - k0);
         const int nn = dp.nbr[a * mc.NBW];
+        if (mc.sharded) {  // only the owner of a particle updates its weight: skip chunks without local rows
+            const int mine = (tid < nrows && dp.LA[lb + k0 + tid] >= 0) ? 1 : 0;
+            if (!__syncthreads_or(mine)) continue;
+        }
         // chain state lives in warp 0 (lane = particle)
         bool act = false;
         float pw = 0.f, sum = 0.f;
-        if (wid == 0 && lane < nrows) {
+        if (wid == 0 && lane < nrows && dp.LA[lb + k0 + lane] >= 0) {
             const float4 p = dp.LP[lb + k0 + lane];
             pw = p.w;
             const float dist = sqrtf(p.x * p.x + p.y * p.y + p.z * p.z);
@@ -906,18 +994,28 @@ __global__ void k_nb_mask(MapConst mc, FrameConst fc, DevPtrs dp) {
 }
 // point pass 1: Dempster-Shafer split from the resident particles of the point's voxel (:829-866) — one warp per point,
 // lanes = slots, the three weight sums added in slot order — and how many table / uniform draws the point consumes.
-__global__ void __launch_bounds__(256) k_nb_point1(MapConst mc, FrameConst fc, DevPtrs dp) {
+// phase 0: single GPU (split + counts); phase 1: sharded, split by the owner of the point's voxel only; phase 2: sharded, counts
+__global__ void __launch_bounds__(256) k_nb_point1(MapConst mc, FrameConst fc, DevPtrs dp, int phase) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     const int R = (mc.S + 31) >> 5;
     for (int m = warp; m < fc.n_tagged; m += nwarps) {
         if (!dp.ninmap[m]) {
-            if (lane == 0) { dp.nvcnt[m] = 0; dp.nrcnt[m] = 0; }
+            if (lane == 0) {
+                if (phase != 1) { dp.nvcnt[m] = 0; dp.nrcnt[m] = 0; }
+                else dp.nst_shared[m] = 0;
+            }
             continue;
         }
         int n_static = 0;
-        if (mc.model == 0) {
-            const int pv = __float_as_int(dp.NPC[m].w);
+        if (phase == 2) n_static = dp.nst_shared[m];  // summed over ranks: exactly one owner contributed
+        const int pv0 = __float_as_int(dp.NPC[m].w);
+        if (phase == 1 && (mc.model != 0 || pv0 < mc.v_lo || pv0 >= mc.v_hi)) {  // not this rank's voxel
+            if (lane == 0) dp.nst_shared[m] = 0;
+            continue;
+        }
+        if (mc.model == 0 && phase != 2) {
+            const int pv = pv0;
             const ulonglong2 msk = dp.M[pv];
             float ws = 0.f, wd = 0.f, wsd = 0.f;
 #pragma unroll
@@ -956,6 +1054,10 @@ __global__ void __launch_bounds__(256) k_nb_point1(MapConst mc, FrameConst fc, D
             n_static = (prod != prod) ? INT_MIN : (int)prod;
             n_static = max(fc.nb_min_static, n_static);
         }
+        if (phase == 1) {
+            if (lane == 0) dp.nst_shared[m] = n_static;
+            continue;
+        }
         if (lane == 0) {
             const u64 im = dp.nimask[m];
             const float *pt = dp.tagged + 7 * m;
@@ -987,6 +1089,7 @@ __global__ void k_nb_cand(MapConst mc, FrameConst fc, DevPtrs dp, u64 useed) {
         float py = pc.y + dp.ptab[(c + 1) % mc.G];
         float pz = pc.z + dp.ptab[(c + 2) % mc.G];
         int d = dsp_voxel_index(mc, px, py, pz);
+        if (mc.sharded && (d < mc.v_lo || d >= mc.v_hi)) continue;  // another rank places this candidate
         float vx = 0.f, vy = 0.f, vz = 0.f;
         const float *pt = dp.tagged + 7 * m;
         if (mc.model == 0 && pt[6] > 0.01f) {

@@ -36,6 +36,12 @@ struct DevPtrs {
     int *mcnt, *mfill, *mbase, *mowner, *mseg;
     // particles registered in FOV pyramids
     int *Fkey, *Faddr, *Fq;
+    float4 *FP;         // position + weight of the registered particle (payload for the sharded all-gather)
+    float4 *PSpay;      // payload scattered with PSkey / PSaddr (sharded mode)
+    // sharded mode exchange buffers (caller-owned device memory, see dspmap_shard_config)
+    float *xsend, *xrecv;  // [nranks][4 + cap_x * 12]: header {count}, then boundary-crossing movers
+    float *gsend, *grecv;  // gsend [4 + cap_g * 8], grecv [nranks][4 + cap_g * 8]: registered particles
+    int *nst_shared;       // [max_points] per-point static newborn count, summed over ranks
     int *pcount, *pfill, *poff, *plen;
     int *PSkey, *PSaddr;
     int *LA;            // per-pyramid sorted list: slot address
@@ -213,6 +219,15 @@ __device__ __forceinline__ void mask_atomic_set(ulonglong2 *M, int v, int s) {
     u64 *w = reinterpret_cast<u64 *>(M + v) + (s >> 6);
     atomicOr(w, 1ull << (s & 63));
 }
+
+// owner rank of a voxel under z-slab sharding
+__host__ __device__ __forceinline__ int dsp_owner(const MapConst &mc, int voxel) {
+    int r = (voxel / (mc.nx * mc.ny)) / mc.z_per_rank;
+    return r < mc.nranks ? r : mc.nranks - 1;
+}
+#define XREC 12  // words per boundary-crosser record: A(4) B(4) key dst q pad
+#define GREC 8   // words per registered-particle record: key q addr pad px py pz w
+#define SLAB_HDR 4
 
 // warp-aggregated counter increment; returns this thread's index
 __device__ __forceinline__ int agg_inc(int *ctr) {

@@ -20,6 +20,9 @@ struct MapConst {
     float res_r;   // RN(1/res); used only when fast_res (exhaustively verified at create time, see k_verify_div)
     int fast_res;
     long long cap_pairs;  // capacity of the pair buffer G
+    // voxel-subspace sharding (multi-GPU): this handle owns voxels [v_lo, v_hi) = z layers [rank * z_per_rank, ...)
+    int sharded, rank, nranks, z_per_rank, v_lo, v_hi;
+    int cap_x, cap_g;  // records per exchange slab (boundary crossers / registered particles)
 };
 
 // Per-frame scalars. Passed to kernels by value.

@@ -89,6 +89,8 @@ def load_library():
         "dspmap_synchronize": (i, [vp]),
         "dspmap_profile_enable": (i, [vp, i]),
         "dspmap_profile_read": (i, [vp, C.POINTER(C.c_char_p), fp, ip, i]),
+        "dspmap_shard_config": (i, [vp, i, i, vp, vp, i, vp, vp, i, vp]),
+        "dspmap_shard_phase": (i, [vp, i, i, vp, f, f, f, C.c_double, f, f, f, f, vp, i]),
         "dspmap_estimator_create": (vp, [C.POINTER(Config), f]),
         "dspmap_estimator_destroy": (None, [vp]),
         "dspmap_estimator_estimate": (i, [vp, i, fp, f, f, f, f, f, f, f, f, fp, i]),
@@ -111,6 +113,7 @@ EXPORTED_SYMBOLS = [
     "dspmap_dump_observations", "dspmap_dump_pyramid_lists", "dspmap_cursors", "dspmap_set_cursors", "dspmap_counters",
     "dspmap_set_stage_limit", "dspmap_set_last_pose", "dspmap_set_stream", "dspmap_synchronize", "dspmap_profile_enable", "dspmap_profile_read",
     "dspmap_estimator_create", "dspmap_estimator_destroy", "dspmap_estimator_estimate",
+    "dspmap_shard_config", "dspmap_shard_phase",
 ]
 
 
@@ -338,6 +341,15 @@ class DSPMap:
         return self._check(self.lib.dspmap_update_device(self.h, n, C.c_void_p(d_pts), float(pos[0]), float(pos[1]),
                                                          float(pos[2]), float(t), float(quat[0]), float(quat[1]),
                                                          float(quat[2]), float(quat[3]), C.c_void_p(d_tagged), n_tagged))
+
+    def shard_config(self, rank, nranks, xsend, xrecv, cap_x, gsend, grecv, cap_g, nst):
+        return self._check(self.lib.dspmap_shard_config(self.h, rank, nranks, C.c_void_p(xsend), C.c_void_p(xrecv), cap_x,
+                                                        C.c_void_p(gsend), C.c_void_p(grecv), cap_g, C.c_void_p(nst)))
+
+    def shard_phase(self, phase, n, d_pts, pos, t, quat, d_tagged, n_tagged):
+        return self._check(self.lib.dspmap_shard_phase(self.h, phase, n, C.c_void_p(d_pts), float(pos[0]), float(pos[1]),
+                                                       float(pos[2]), float(t), float(quat[0]), float(quat[1]), float(quat[2]),
+                                                       float(quat[3]), C.c_void_p(d_tagged), n_tagged))
 
     def get_occupancy_device(self, threshold, d_xyz, cap, d_count, d_future):
         return self._check(self.lib.dspmap_get_occupancy_device(self.h, threshold, C.c_void_p(d_xyz), cap,

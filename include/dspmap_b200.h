@@ -156,6 +156,24 @@ int dspmap_synchronize(dspmap *m);
 int dspmap_profile_enable(dspmap *m, int on);
 int dspmap_profile_read(dspmap *m, const char **names, float *ms, int32_t *launches, int cap);
 
+/* ---- voxel-subspace sharding over the GPUs of one box (one handle per GPU / rank) -----------------------------------
+ * The map's z layers are cut into `nranks` equal slabs; handle `rank` owns the particles of its slab.  A frame is
+ * enqueued in four phases with three collectives between them, issued by the caller on the same stream
+ * (dsp-map_b200/dspmap_b200/sharded.py does it with torch.distributed / NCCL):
+ *   phase 0  binning, prediction; movers that leave the slab are written to xsend[dest rank]
+ *            -> all-to-all of the fixed-size slabs xsend -> xrecv                       (the boundary exchange)
+ *   phase 1  imported movers join the ordered arrival replay; registered particles are packed into gsend
+ *            -> all-gather gsend -> grecv
+ *   phase 2  identical global pyramid lists on every rank, C_z, weights of own particles, newborn split of own voxels
+ *            -> all-reduce(sum) of nst (int32 per tagged point)
+ *   phase 3  newborn candidates that land in the slab, occupancy + resampling + future status of the slab
+ * Buffers are device memory owned by the caller: xsend/xrecv hold nranks slabs of (4 + cap_x*12) floats, gsend one and
+ * grecv nranks slabs of (4 + cap_g*8) floats, nst max_points int32.  Results are bit-identical to a single handle. */
+int dspmap_shard_config(dspmap *m, int rank, int nranks, float *xsend, float *xrecv, int cap_x, float *gsend, float *grecv,
+                        int cap_g, int32_t *nst);
+int dspmap_shard_phase(dspmap *m, int phase, int n, const float *d_pts, float px, float py, float pz, double t, float qw,
+                       float qx, float qy, float qz, const float *d_tagged, int n_tagged);
+
 /* Host-only access to the velocity-estimation step (the reference's side thread, dsp_dynamic.h:1377-1544; static variant
  * dsp_static.h:1285-1309) without a map or a GPU: used to pre-compute newborn inputs for device-resident streams and
  * by the CPU tests.  `estimate` consumes one frame (n x 3 points, sensor frame) and writes the tagged cloud (7 floats

@@ -1,0 +1,55 @@
+"""GPU tests of voxel-subspace sharding: N shards of one map (LocalCluster: the library's sharded code path, collectives
+done as tensor copies on one GPU) must reproduce an unsharded map bit for bit, frame after frame."""
+import numpy as np
+import pytest
+
+import dspmap_b200 as dm
+from common import SET, gpu_map, gpu_update, make_stream
+from dspmap_b200.sharded import LocalCluster
+from parity import same
+
+pytestmark = pytest.mark.gpu
+
+
+def setters(g):
+    g.setPredictionVariance(SET["p_std"], SET["v_std"])
+    g.setObservationStdDev(SET["ob_std"])
+    g.setNewBornParticleNumberofEachPoint(SET["newborn_num"])
+    g.setNewBornParticleWeight(SET["newborn_weight"])
+
+
+@pytest.mark.parametrize("name,nranks,frames", [("tiny_dyn", 2, 10), ("tiny_dyn", 3, 8), ("tiny_static", 2, 6), ("cfg1", 2, 5), ("cfg2", 4, 4)])
+def test_sharded_equals_single_gpu(name, nranks, frames):
+    cfg = dm.CONFIGS[name]
+    st = make_stream(cfg, seed=8, frames=frames)
+    est = dm.VelocityEstimator(cfg, seed=4, filter_res=0.1)
+    one = gpu_map(name, seed=4, max_points=cfg["points"])
+    cl = LocalCluster(cfg, nranks, seed=4, max_points=cfg["points"], setters=setters)
+    crossed = 0
+    for f in range(frames):
+        pts, pos, t, q = st["points"][f], st["pos"][f], st["t"][f], st["quat"][f]
+        tc = est.estimate(pts, pos, t, q)
+        assert gpu_update(one, pts, pos, t, q, tagged=tc) == 1
+        assert cl.update(pts, pos, t, q, tc) == 1
+        ids, vals = one.particles()
+        sids, svals = cl.particles()
+        assert same(ids, sids), "frame %d: particle (voxel, slot) sets" % f
+        assert same(vals, svals), "frame %d: particle fields" % f
+        vo, svo = one.voxel_objects(), cl.voxel_objects()
+        assert same(vo[:, :4], svo[:, :4]), "frame %d: occupancy / mean velocity" % f
+        assert np.array_equal(vo[:, 4:] != 0, svo[:, 4:] != 0) and np.allclose(vo[:, 4:], svo[:, 4:], rtol=4e-6, atol=0)
+        c1 = one.cursors()
+        for c in cl.cursors():
+            assert np.array_equal(c[:3], c1[:3]), "frame %d: cursors" % f
+        cs = cl.counters()
+        assert sum(c["n_out"] for c in cs) == one.counters()["n_out"] and all(c["n_inexact"] == 0 for c in cs)
+        # every shard only holds particles of its own voxel subspace
+        for s in cl.shards:
+            pid, _ = s.map.particles()
+            assert len(pid) == 0 or (pid[:, 0].min() >= s.v_lo and pid[:, 0].max() < s.v_hi)
+        if f % 2 == 1:
+            n, xyz, fut = one.getOccupancyMapWithFutureStatus(0.2)
+            sxyz, sfut = cl.occupancy(0.2)
+            assert same(xyz, sxyz) and np.allclose(fut, sfut, rtol=4e-6, atol=0)
+    one.close()
+    cl.close()
