@@ -126,6 +126,163 @@ def workload_config(cfg_name, cfg, where):
             "horizons": cfg["future_times"], "neighbors": (2 * cfg["neighbor_n"] + 1) ** 2, "where": where}
 
 
+def main_sharded(args, cfg_name, cfg, dm, make_stream):
+    """--gpus N > 1: ONE map, its voxel subspaces (z slabs) sharded over the N GPUs (one process per GPU, NCCL):
+    all-to-all of boundary crossers, all-gather of registered particles, all-reduce of the newborn split per frame,
+    plus the reader's all-reduce of the future grid and gather of the occupied-voxel lists.  Strong scaling."""
+    import torch
+    import torch.distributed as dist
+    from dspmap_b200.sharded import NcclComm, ShardedDSPMap, sharded_update
+    rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    K, W = args.steps, args.warmup
+    PROF = min(K, 10)
+    F = PREROLL + W + K + PROF + W + K
+    st = make_stream(cfg, seed=1, frames=F)     # the same stream on every rank: the cloud and the pose are replicated
+    M = int(st["n"][0])
+    est = dm.VelocityEstimator(cfg, seed=1, filter_res=SETTERS["filter_res"])
+    F1 = PREROLL + W + K + PROF
+    tagged, last = [], np.zeros((0, 7), np.float32)
+    for f in range(F1):
+        t = est.estimate(st["points"][f], st["pos"][f], st["t"][f], st["quat"][f])
+        last = t if t is not None else last
+        tagged.append(last)
+    nt_max = max(max(len(t) for t in tagged), 1)
+    d_pts = torch.from_numpy(st["points"][:F1]).to(dev)
+    tg = np.zeros((F1, nt_max, 7), np.float32)
+    for f, t in enumerate(tagged):
+        tg[f, :len(t)] = t
+    d_tag = torch.from_numpy(tg).to(dev)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    sm = ShardedDSPMap(cfg, rank, world, device=local, seed=1, max_points=max(M, nt_max, 1024))
+    m = sm.map
+    m.set_stream(stream.cuda_stream)
+    apply_setters(m)
+    comm = NcclComm()
+    cap_occ = 32768
+    d_xyz = torch.zeros((m.V, 3), dtype=torch.float32, device=dev)
+    d_cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+    d_fut = torch.zeros((m.V, m.T), dtype=torch.float32, device=dev)
+    g_xyz = torch.zeros((world, cap_occ, 3), dtype=torch.float32, device=dev)
+    g_cnt = torch.zeros(world, dtype=torch.int32, device=dev)
+    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step(f, d_p, d_t, nt):
+        sharded_update(sm, comm, M, d_p, st["pos"][f], st["t"][f], st["quat"][f], d_t, nt)
+        m.get_occupancy_device(THRESHOLD, d_xyz.data_ptr(), m.V, d_cnt.data_ptr(), d_fut.data_ptr())
+        dist.all_reduce(d_fut)                                        # future contributions land in any rank's voxels
+        dist.all_gather_into_tensor(g_xyz.view(-1), d_xyz[:cap_occ].reshape(-1))   # slab lists concatenate in voxel order
+        dist.all_gather_into_tensor(g_cnt, d_cnt)
+
+    for f in range(PREROLL + W):
+        step(f, d_pts[f].data_ptr(), d_tag[f].data_ptr(), len(tagged[f]))
+    torch.cuda.synchronize()
+    dist.barrier()
+    m.synchronize()
+    launches0 = m.counters()["launches_total"]
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    e1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    for k in range(K):
+        f = PREROLL + W + k
+        if flush is not None:
+            flush.zero_()
+        e0[k].record(stream)
+        step(f, d_pts[f].data_ptr(), d_tag[f].data_ptr(), len(tagged[f]))
+        e1[k].record(stream)
+    torch.cuda.synchronize()
+    dist.barrier()
+    m.synchronize()
+    dev_ms = sum(a.elapsed_time(b) for a, b in zip(e0, e1))
+    launches = m.counters()["launches_total"] - launches0
+    tt = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dev_ms_max = float(tt.item())
+    value = K / (dev_ms_max * 1e-3)        # one map: every frame is ONE update, whatever the number of GPUs
+    # per-family kernel times on this rank + frame counters summed over ranks
+    m.profile_enable(True)
+    agg = {}
+    for k in range(PROF):
+        f = PREROLL + W + K + k
+        if flush is not None:
+            flush.zero_()
+        step(f, d_pts[f].data_ptr(), d_tag[f].data_ptr(), len(tagged[f]))
+        m.synchronize()
+        for kk, vv in m.counters().items():
+            agg[kk] = agg.get(kk, 0) + vv
+    prof = m.profile_read()
+    m.profile_enable(False)
+    names = sorted(agg)
+    ct = torch.tensor([agg[k_] for k_ in names], dtype=torch.float64, device=dev)
+    dist.all_reduce(ct)
+    ctr = {k_: float(v_) / PROF for k_, v_ in zip(names, ct.tolist())}
+    fam_ms = {n: (ms / PROF) for n, (ms, ln) in prof.items() if ln}
+    # end to end: host cloud in, host results out on rank 0
+    fut_host = torch.zeros((m.V, m.T), dtype=torch.float32).pin_memory()
+    xyz_host = torch.zeros((world, cap_occ, 3), dtype=torch.float32).pin_memory()
+    e2e_t, h2d, d2h = [], 0, 0
+    for k in range(W + K):
+        f = F1 + k
+        pts, pos, t, q = st["points"][f], st["pos"][f], st["t"][f], st["quat"][f]
+        if flush is not None:
+            flush.zero_()
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        dp_ = torch.from_numpy(pts).to(dev, non_blocking=True)
+        tc = est.estimate(pts, pos, t, q)
+        last = tc if tc is not None else last
+        dt_ = torch.from_numpy(last if len(last) else np.zeros((1, 7), np.float32)).to(dev, non_blocking=True)
+        step(f, dp_.data_ptr(), dt_.data_ptr(), len(last))
+        if rank == 0:
+            fut_host.copy_(d_fut, non_blocking=True)
+            xyz_host.copy_(g_xyz, non_blocking=True)
+            n_occ = int(g_cnt.sum().item())
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        if k >= W:
+            e2e_t.append(t1 - t0)
+            h2d += pts.nbytes + last.nbytes
+            d2h += (fut_host.numel() + xyz_host.numel()) * 4 + 4 if rank == 0 else 0
+    tt = torch.tensor([sum(e2e_t)], dtype=torch.float64, device=dev)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    e2e_val = len(e2e_t) / float(tt.item())
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        b_frame = dm.bytes_per_update(ctr, m.V, m.T, M)
+        top = max(fam_ms, key=fam_ms.get)
+        line = {
+            "metric": "map_updates_per_s", "value": value, "unit": "updates/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": dict(workload_config(cfg_name, cfg, "hbm-resident"), parallelism="voxel z-slabs x%d (one map)" % world,
+                           collectives_per_update=["all_to_all(boundary crossers)", "all_gather(registered particles)",
+                                                   "all_reduce(newborn split)", "all_reduce(future grid)", "all_gather(occupied lists)"],
+                           l2_flush_between_steps=flush is not None, preroll_frames=PREROLL),
+            "e2e": {"value": e2e_val, "unit": "updates/s", "h2d_bytes_per_step": h2d // max(len(e2e_t), 1),
+                    "d2h_bytes_per_step": d2h // max(len(e2e_t), 1), "ms_per_step": 1e3 * float(np.mean(e2e_t))},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": top, "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
+                         "peak_source": peak_src, "kernel_ms": fam_ms[top], "note": "rank 0's share; see the N=1 line for the per-kernel roofline"},
+            "roofline_frame": {"bound": "hbm", "algorithmic_bytes_per_update": b_frame,
+                               "achieved": b_frame / (dev_ms_max / K * 1e-3) / 1e9, "peak": peak * world, "unit": "GB/s",
+                               "frac": b_frame / (dev_ms_max / K * 1e-3) / 1e9 / (peak * world)},
+            "kernel_ms_per_update_rank0": {k_: round(v_, 5) for k_, v_ in sorted(fam_ms.items(), key=lambda kv: -kv[1])},
+            "counters_per_update": {k_: round(v_, 1) for k_, v_ in ctr.items() if k_ not in ("launches_total", "launches_frame")},
+        }
+        print(json.dumps(line))
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -135,6 +292,7 @@ def main():
     ap.add_argument("--config", default="cfg2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--replicas", action="store_true", help="N > 1: N independent maps instead of one sharded map")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -144,6 +302,9 @@ def main():
     cfg = dm.CONFIGS[cfg_name]
     if args.impl == "reference":
         return reference_arm(args, cfg_name, cfg)
+
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and not args.replicas:
+        return main_sharded(args, cfg_name, cfg, dm, make_stream)
 
     import torch
     import torch.distributed as dist
