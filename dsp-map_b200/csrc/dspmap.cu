@@ -41,7 +41,8 @@ struct dspmap {
     MapConst mc;
     DevPtrs dp;
     cudaStream_t stream = nullptr, own_stream = nullptr, side = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_state = nullptr;
+    bool state_event_recorded = false;
     std::vector<void *> allocs;
     // host mirrors
     std::vector<float> ptab, vtab, lut, planes0;
@@ -341,8 +342,10 @@ int enqueue_frame_b(dspmap *m, const FrameConst &fc, const float *d_tagged) {
         LAUNCH(m, FAM_RESAMPLE, k_resample, kSMs * 8, 256, 0, mc, fc, dp);
     }
     LAUNCH(m, FAM_CLEANUP, k_cleanup, kSMs * 2, B, 0, mc, fc, dp, newborn_ran, m->fallback_armed ? 1 : 0);
-    // the (possibly one frame old) state steers which optional kernels the next frame launches
+    // the state copy steers which optional kernels the next frame launches
     CK(cudaMemcpyAsync(m->h_state, m->dp.st, sizeof(DevState), cudaMemcpyDeviceToHost, m->stream));
+    CK(cudaEventRecord(m->ev_state, m->stream));
+    m->state_event_recorded = true;
     CK(cudaGetLastError());
     return DSPMAP_OK;
 }
@@ -392,8 +395,13 @@ int frame_prologue(dspmap *m, int n, float px, float py, float pz, double t, flo
     fc->n_points = n;
     fc->stage_limit = m->stage_limit;
     fc->vz_mode = m->vz_mode ? 1 : 0;
-    if (m->update_counter > 2)  // h_state is refreshed by every frame; a stale value is fine, growth is gradual
+    // The recompute kernels are left out only when the host KNOWS the previous frame's pair count (its state copy has
+    // completed) and it is below half the buffer; growth from one frame to the next is gradual.
+    m->fallback_armed = true;
+    if (m->update_counter > 2 && m->state_event_recorded && cudaEventQuery(m->ev_state) == cudaSuccess)
         m->fallback_armed = m->h_state->total_pairs * 2ull > (unsigned long long)m->mc.cap_pairs;
+    else
+        cudaGetLastError();  // cudaErrorNotReady is not an error here
     return DSPMAP_OK;
 }
 
@@ -405,7 +413,11 @@ int frame_epilogue(dspmap *m) {
     // once a frame has predicted every particle and drew no noise, all vz are 0 for good (LIMIT_MOVEMENT_IN_XY_PLANE)
     if (m->vz_mode && m->stage_limit >= 4 && m->last_state.n_vz == 0 && m->last_state.n_skipped == 0) m->vz_mode = false;
     if (m->last_state.overflow) {
-        g_err = "device list capacity exceeded (raise max_points / live-particle capacity)";
+        char buf[256];
+        snprintf(buf, sizeof(buf), "device capacity exceeded: code %d (1 live list, 2 newborn candidates, 4 pair buffer without fallback, "
+                 "8 shard crossers, 16 shard gather); pairs this frame %llu, capacity %lld", m->last_state.overflow,
+                 m->last_state.total_pairs, m->mc.cap_pairs);
+        g_err = buf;
         return DSPMAP_E_CAPACITY;
     }
     return DSPMAP_OK;
@@ -520,6 +532,7 @@ int dspmap_create(const dspmap_config *cfg, dspmap **out) {
     CK(cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&m->ev_state, cudaEventDisableTiming));
     m->stream = m->own_stream;
 
     DevPtrs &dp = m->dp;
@@ -540,7 +553,7 @@ int dspmap_create(const dspmap_config *cfg, dspmap **out) {
     A(dp.mcnt, V); A(dp.mfill, V); A(dp.mbase, V); A(dp.mowner, V); A(dp.mseg, CL);
     A(dp.Fkey, CL); A(dp.Faddr, CL); A(dp.Fq, CL); A(dp.FP, CL); A(dp.PSpay, CL); A(dp.pcount, P); A(dp.pfill, P); A(dp.poff, P + 1); A(dp.plen, P);
     A(dp.PSkey, CL); A(dp.PSaddr, CL); A(dp.LA, CL); A(dp.LP, CL); A(dp.PW, CL);
-    mc.cap_pairs = 128ll << 20;  // 512 MB of fp32 pair terms; larger frames fall back to the recompute kernels
+    mc.cap_pairs = 512ll << 20;  // 2 GB of fp32 pair terms (of 180 GB); larger frames fall back to the recompute kernels
     A(dp.G, (size_t)mc.cap_pairs); A(dp.cum, P * mc.NBW); A(dp.totlen, P); A(dp.pairs, P + 1); A(dp.rowbase, P + 1);
     A(dp.chunks, P + 1); A(dp.chunk_off, P + 1);
     A(dp.NPC, MP); A(dp.ninmap, MP + 1); A(dp.nrank, MP + 1); A(dp.nstatic, MP); A(dp.nvcnt, MP + 1); A(dp.nrcnt, MP + 1);
@@ -642,6 +655,7 @@ void dspmap_destroy(dspmap *m) {
     for (auto &s : m->prof_slots) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     if (m->ev_fork) cudaEventDestroy(m->ev_fork);
     if (m->ev_join) cudaEventDestroy(m->ev_join);
+    if (m->ev_state) cudaEventDestroy(m->ev_state);
     if (m->own_stream) cudaStreamDestroy(m->own_stream);
     if (m->side) cudaStreamDestroy(m->side);
     delete m;

@@ -168,7 +168,7 @@ __global__ void k_enumerate(MapConst mc, DevPtrs dp, int snapshot) {
         if (lane == 0) wbase = atomicAdd(&dp.st->n_live, total);
         wbase = __shfl_sync(FULLMASK, wbase, 0);
         int off = wbase + incl - c;
-        if (off + c > dp.cap_live) { if (c) dp.st->overflow = 1; continue; }
+        if (off + c > dp.cap_live) { if (c) atomicOr(&dp.st->overflow, 1); continue; }
         u64 z = m.x;
         while (z) { int s = __ffsll((long long)z) - 1; z &= z - 1; dp.E[off++] = (v << DSP_KEY_SHIFT) | s; }
         z = m.y;
@@ -307,7 +307,7 @@ __global__ void k_predict(MapConst mc, FrameConst fc, DevPtrs dp) {
             if (mc.sharded && (d < mc.v_lo || d >= mc.v_hi)) {  // crosses into another rank's voxel subspace
                 float *slab = dp.xsend + (size_t)dsp_owner(mc, d) * (SLAB_HDR + mc.cap_x * XREC);
                 int k = atomicAdd(reinterpret_cast<int *>(slab), 1);
-                if (k >= mc.cap_x) { dp.st->overflow = 1; continue; }
+                if (k >= mc.cap_x) { atomicOr(&dp.st->overflow, 8); continue; }
                 float *rec = slab + SLAB_HDR + (size_t)k * XREC;
                 *reinterpret_cast<float4 *>(rec) = A;
                 *reinterpret_cast<float4 *>(rec + 4) = B;
@@ -441,7 +441,7 @@ __global__ void k_shard_pack_fov(MapConst mc, DevPtrs dp) {
     const int n = dp.st->n_fov;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         reinterpret_cast<int *>(dp.gsend)[0] = min(n, mc.cap_g);
-        if (n > mc.cap_g) dp.st->overflow = 1;
+        if (n > mc.cap_g) atomicOr(&dp.st->overflow, 16);
     }
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < min(n, mc.cap_g); i += gridDim.x * blockDim.x) {
         float *rec = dp.gsend + SLAB_HDR + (size_t)i * GREC;
@@ -1114,7 +1114,7 @@ __global__ void k_nb_cand(MapConst mc, FrameConst fc, DevPtrs dp, u64 useed) {
             vz = 0.f;  // LIMIT_MOVEMENT_IN_XY_PLANE (:905-907)
         }
         int k = agg_inc(&dp.st->n_cand);
-        if (k >= dp.cap_cand) { dp.st->overflow = 1; continue; }
+        if (k >= dp.cap_cand) { atomicOr(&dp.st->overflow, 2); continue; }
         dp.CA[k] = make_float4(px, py, pz, w_new);
         dp.CB[k] = make_float4(vx, vy, vz, 15.f);
         dp.Ckey[k] = m * DSP_MAX_NB_NUM + p;
@@ -1368,7 +1368,7 @@ __global__ void k_cleanup(MapConst mc, FrameConst fc, DevPtrs dp, int newborn_ra
             s->u_cur += 3ll * rd;
         }
         s->use_store = use_pair_buffer(mc, dp) ? 1 : 0;
-        if (!s->use_store && !fallback_launched && fc.stage_limit >= 2) s->overflow = 1;
+        if (!s->use_store && !fallback_launched && fc.stage_limit >= 2) atomicOr(&s->overflow, 4);
     }
 }
 
