@@ -101,3 +101,17 @@ def make_stream(cfg, seed=1, frames=100, points=None, dt=0.1, speed=0.2, n_boxes
         quat[f] = q.astype(np.float32)
         ts[f] = t
     return dict(points=out_p, n=np.full(frames, M, np.int32), pos=pos, quat=quat, t=ts)
+
+
+def write_stream(path, stream, frames=None):
+    """Binary stream file read by dsp-map_b200/tools/dspmap_replay.cpp and tests/dropin_main.cpp."""
+    import struct
+    F = len(stream["t"]) if frames is None else frames
+    with open(path, "wb") as f:
+        f.write(struct.pack("i", F))
+        for k in range(F):
+            n = int(stream["n"][k])
+            f.write(struct.pack("i", n))
+            f.write(stream["pos"][k].astype(np.float32).tobytes() + stream["quat"][k].astype(np.float32).tobytes())
+            f.write(struct.pack("d", float(stream["t"][k])))
+            f.write(stream["points"][k][:n].astype(np.float32).tobytes())

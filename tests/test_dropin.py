@@ -62,3 +62,28 @@ def test_dropin_application_matches_reference():
         assert int(tok[5]) == int(tok[3])                   # the cloud got exactly the occupied voxels
         assert int(tok[9]) == len(r.tagged_cloud())         # getKMClusterResult size
         assert abs(int(tok[3]) - len(xyz)) <= max(5, len(xyz) // 8)  # noise seeds differ (time-seeded): statistically equal
+
+
+def test_replay_tool_compiles():
+    os.makedirs(BUILD, exist_ok=True)
+    exe = os.path.join(BUILD, "dspmap_replay")
+    subprocess.check_call(["g++", "-std=c++14", "-O1", "-w", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "oracle", "shim"),
+                           os.path.join(ROOT, "dsp-map_b200", "tools", "dspmap_replay.cpp"), "-o", exe,
+                           "-L", os.path.join(ROOT, "dsp-map_b200", "lib"), "-ldspmap_b200",
+                           "-Wl,-rpath," + os.path.join(ROOT, "dsp-map_b200", "lib"), "-lpthread", "-ldl", "-lrt"])
+    assert os.path.exists(exe)
+
+
+@pytest.mark.gpu
+def test_replay_tool_runs_and_writes_outputs():
+    test_replay_tool_compiles()
+    from dspmap_b200.streams import write_stream
+    cfg = dm.CONFIGS["ref_default"]
+    st = make_stream(cfg, seed=2, frames=4)
+    path = os.path.join(BUILD, "replay_stream.bin")
+    write_stream(path, st)
+    out = subprocess.check_output([os.path.join(BUILD, "dspmap_replay"), path, "--out", os.path.join(BUILD, "rp"), "--future"], text=True)
+    assert out.count("occupied voxels") == 4
+    occ = np.fromfile(os.path.join(BUILD, "rp_frame0003.occ"), np.float32).reshape(-1, 3)
+    fut = np.fromfile(os.path.join(BUILD, "rp_frame0003.fut"), np.float32)
+    assert len(occ) > 100 and fut.size == cfg["nx"] * cfg["ny"] * cfg["nz"] * 6 and fut.sum() > 0
