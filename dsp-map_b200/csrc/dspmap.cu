@@ -86,6 +86,7 @@ struct dspmap {
     // the recompute kernels (k_ck / k_weight) are launched only while the pair buffer may overflow
     bool fallback_armed = true;
     FrameConst shard_fc;  // frame scalars carried across the phases of a sharded frame
+    int shard_cap_g = 0;
     long long host_u_cur = 0;  // uniform draws consumed on the host while seeding
     VelocityEstimator estimator;
     // statistics
@@ -295,8 +296,8 @@ int enqueue_frame_a(dspmap *m, const FrameConst &fc, const float *d_pts) {
     if (fc.stage_limit >= 2) {
         LAUNCH(m, FAM_CK, k_pair_prep, grid_for(mc.P, B), B, 0, mc, dp);
         LAUNCH(m, FAM_CK, k_scan_small, 2, 1024, 0, ScanJobs{{ScanJob{dp.pairs, dp.rowbase, nullptr, 0, mc.P}, ScanJob{dp.chunks, dp.chunk_off, nullptr, 0, mc.P}, ScanJob{}}});
-        LAUNCH(m, FAM_CK, k_pair_eval, kSMs * 2, EVAL_THREADS, sizeof(float) * (DSP_LUT_HALF + 3 + (EVAL_THREADS / 32) * 32 * TILE_LD), mc, fc, dp);
-        LAUNCH(m, FAM_CK, k_cz_chain, std::min(mc.P, kSMs * 3), CZ_THREADS, sizeof(float) * (2 * CZ_TILE + 2 * CZ_JT), mc, fc, dp);
+        LAUNCH(m, FAM_CK, k_pair_eval, kSMs * 2, EVAL_THREADS, sizeof(float) * (DSP_LUT_HALF + 3 + (EVAL_THREADS / 32) * 32 * TILE_LD), mc, fc, dp, 0);
+        LAUNCH(m, FAM_CK, k_cz_chain, std::min(mc.P, kSMs * 3), CZ_THREADS, sizeof(float) * (2 * (CZ_TILE + 8) + 2 * CZ_JT), mc, fc, dp);
         size_t smem4 = sizeof(float) * (DSP_LUT_HALF + 3 + K4_TERMS) + sizeof(float4) * (256 + mc.OBS);
         if (m->fallback_armed) LAUNCH(m, FAM_CK, k_ck, std::min(mc.P, kSMs * 2), K4_THREADS, smem4, mc, fc, dp);  // returns at once when the pair buffer is used
         if (fc.stage_limit >= 3) {  // the newborn normaliser is one long serial chain: run it beside the weight pass
@@ -308,6 +309,7 @@ int enqueue_frame_a(dspmap *m, const FrameConst &fc, const float *d_pts) {
             CK(cudaEventRecord(m->ev_join, m->side));
         }
         LAUNCH(m, FAM_WEIGHT, k_weight2, kSMs * 8, W2_THREADS, 0, mc, fc, dp);
+        LAUNCH(m, FAM_WEIGHT, k_weight2w, kSMs * 6, W2W_THREADS, 0, mc, fc, dp);
         size_t smem5 = sizeof(float) * (DSP_LUT_HALF + 3) + sizeof(float4) * (size_t)mc.NB * (mc.OBS - 1);
         int chunks = (mc.L + K5_THREADS - 1) / K5_THREADS;
         if (m->fallback_armed) LAUNCH(m, FAM_WEIGHT, k_weight, kSMs * 2, K5_THREADS, smem5, mc, fc, dp, chunks);
@@ -554,7 +556,7 @@ int dspmap_create(const dspmap_config *cfg, dspmap **out) {
     A(dp.Fkey, CL); A(dp.Faddr, CL); A(dp.Fq, CL); A(dp.FP, CL); A(dp.PSpay, CL); A(dp.pcount, P); A(dp.pfill, P); A(dp.poff, P + 1); A(dp.plen, P);
     A(dp.PSkey, CL); A(dp.PSaddr, CL); A(dp.LA, CL); A(dp.LP, CL); A(dp.PW, CL);
     mc.cap_pairs = 512ll << 20;  // 2 GB of fp32 pair terms (of 180 GB); larger frames fall back to the recompute kernels
-    A(dp.G, (size_t)mc.cap_pairs); A(dp.cum, P * mc.NBW); A(dp.totlen, P); A(dp.pairs, P + 1); A(dp.rowbase, P + 1);
+    A(dp.G, (size_t)mc.cap_pairs + 64); A(dp.cum, P * mc.NBW); A(dp.totlen, P); A(dp.pairs, P + 1); A(dp.rowbase, P + 1);
     A(dp.chunks, P + 1); A(dp.chunk_off, P + 1);
     A(dp.NPC, MP); A(dp.ninmap, MP + 1); A(dp.nrank, MP + 1); A(dp.nstatic, MP); A(dp.nvcnt, MP + 1); A(dp.nrcnt, MP + 1);
     A(dp.nvoff, MP + 1); A(dp.nroff, MP + 1); A(dp.nimask, MP);
@@ -739,12 +741,13 @@ int dspmap_update_device(dspmap *m, int n, const float *d_pts, float px, float p
 }
 
 int dspmap_shard_config(dspmap *m, int rank, int nranks, float *xsend, float *xrecv, int cap_x, float *gsend, float *grecv,
-                        int cap_g, int32_t *nst) {
-    if (!m || nranks < 1 || rank < 0 || rank >= nranks || cap_x < 1 || cap_g < 1 || !xsend || !xrecv || !gsend || !grecv || !nst) {
+                        int cap_g, float *czinv, float *shared) {
+    if (!m || nranks < 1 || rank < 0 || rank >= nranks || cap_x < 1 || cap_g < 1 || !xsend || !xrecv || !gsend || !grecv || !czinv || !shared) {
         g_err = "bad shard configuration";
         return DSPMAP_E_BAD_ARG;
     }
     MapConst &mc = m->mc;
+    if ((long long)nranks * cap_g > m->dp.cap_live) { g_err = "nranks * cap_g exceeds the live-particle capacity"; return DSPMAP_E_BAD_ARG; }
     mc.sharded = 1;
     mc.rank = rank;
     mc.nranks = nranks;
@@ -756,8 +759,19 @@ int dspmap_shard_config(dspmap *m, int rank, int nranks, float *xsend, float *xr
     mc.v_hi = z1 * mc.nx * mc.ny;
     mc.cap_x = cap_x;
     mc.cap_g = cap_g;
-    m->dp.xsend = xsend; m->dp.xrecv = xrecv; m->dp.gsend = gsend; m->dp.grecv = grecv; m->dp.nst_shared = nst;
+    m->shard_cap_g = cap_g;
+    DevPtrs &dp = m->dp;
+    dp.xsend = xsend; dp.xrecv = xrecv; dp.gsend = gsend; dp.grecv = grecv;
+    dp.CZ = czinv;                                   // C_z and 1/C_z live in the caller's buffer: merged by all-reduce
+    dp.INV = czinv + (size_t)mc.P * mc.OBS;
+    dp.nst_shared = shared;                          // newborn split first, then the new weights by global list index
+    dp.NW = shared + m->max_points;
     m->fallback_armed = false;  // sharded frames always use the pair buffer (checked: overflow flag otherwise)
+    return DSPMAP_OK;
+}
+int dspmap_shard_gather_records(dspmap *m, int records) {
+    if (!m || !m->mc.sharded || records < 1 || records > m->shard_cap_g) { g_err = "bad gather size"; return DSPMAP_E_BAD_ARG; }
+    m->mc.cap_g = records;
     return DSPMAP_OK;
 }
 
@@ -765,11 +779,11 @@ int dspmap_shard_phase(dspmap *m, int phase, int n, const float *d_pts, float px
                        float qx, float qy, float qz, const float *d_tagged, int n_tagged) {
     if (!m || !m->mc.sharded) { g_err = "handle is not sharded"; return DSPMAP_E_BAD_ARG; }
     CK(cudaSetDevice(m->cfg.device));
-    const MapConst &mc = m->mc;
     const int B = 256;
     int rc;
     if (phase == 0) {
         if (n < 0 || n > m->max_points || n_tagged > m->max_points) { g_err = "bad argument"; return DSPMAP_E_BAD_ARG; }
+        m->mc.cap_g = m->shard_cap_g;  // the pack kernel may fill the whole slab; the frame's stride is set after phase 1
         FrameConst fc;
         rc = frame_prologue(m, n, px, py, pz, t, qw, qx, qy, qz, &fc);
         if (rc != DSPMAP_OK) return rc;
@@ -784,6 +798,7 @@ int dspmap_shard_phase(dspmap *m, int phase, int n, const float *d_pts, float px
         m->fallback_armed = false;
         m->shard_fc = fc;
     }
+    const MapConst &mc = m->mc;
     const FrameConst &fc = m->shard_fc;
     DevPtrs dp = m->dp;
     if (phase == 0) {
@@ -812,24 +827,33 @@ int dspmap_shard_phase(dspmap *m, int phase, int n, const float *d_pts, float px
         LAUNCH(m, FAM_ARRIVE, k_arrive, kSMs * 4, B, 0, mc, fc, dp);
         LAUNCH(m, FAM_PYRAMID, k_shard_pack_fov, kSMs * 4, B, 0, mc, dp);
     } else if (phase == 2) {
-        dp.tagged = d_tagged;
         LAUNCH(m, FAM_PYRAMID, k_shard_fov_gathered, kSMs * 8, B, 0, mc, dp, 0);
         LAUNCH(m, FAM_PYRAMID, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{dp.pcount, dp.poff, nullptr, 0, mc.P}, ScanJob{}, ScanJob{}}});
         LAUNCH(m, FAM_PYRAMID, k_shard_fov_gathered, kSMs * 8, B, 0, mc, dp, 1);
         LAUNCH(m, FAM_PYRAMID, k_pyr_sort, std::min(mc.P, kSMs * 3), 512, PYR_SORT_CAP * sizeof(u64), mc, dp, fc.Pd);
         LAUNCH(m, FAM_CK, k_pair_prep, grid_for(mc.P, B), B, 0, mc, dp);
         LAUNCH(m, FAM_CK, k_scan_small, 2, 1024, 0, ScanJobs{{ScanJob{dp.pairs, dp.rowbase, nullptr, 0, mc.P}, ScanJob{dp.chunks, dp.chunk_off, nullptr, 0, mc.P}, ScanJob{}}});
-        LAUNCH(m, FAM_CK, k_pair_eval, kSMs * 2, EVAL_THREADS, sizeof(float) * (DSP_LUT_HALF + 3 + (EVAL_THREADS / 32) * 32 * TILE_LD), mc, fc, dp);
-        LAUNCH(m, FAM_CK, k_cz_chain, std::min(mc.P, kSMs * 3), CZ_THREADS, sizeof(float) * (2 * CZ_TILE + 2 * CZ_JT), mc, fc, dp);
+        LAUNCH(m, FAM_CK, k_shard_zero, kSMs * 2, B, 0, mc, fc, dp, 0);
+        LAUNCH(m, FAM_CK, k_pair_eval, kSMs * 2, EVAL_THREADS, sizeof(float) * (DSP_LUT_HALF + 3 + (EVAL_THREADS / 32) * 32 * TILE_LD), mc, fc, dp, 1);
+        LAUNCH(m, FAM_CK, k_cz_chain, std::min(mc.P, kSMs * 3), CZ_THREADS, sizeof(float) * (2 * (CZ_TILE + 8) + 2 * CZ_JT), mc, fc, dp);
+    } else if (phase == 3) {
+        dp.tagged = d_tagged;
+        LAUNCH(m, FAM_WEIGHT, k_shard_zero, kSMs * 2, B, 0, mc, fc, dp, 1);
+        LAUNCH(m, FAM_WEIGHT, k_pair_eval, kSMs * 2, EVAL_THREADS, sizeof(float) * (DSP_LUT_HALF + 3 + (EVAL_THREADS / 32) * 32 * TILE_LD), mc, fc, dp, 2);
         LAUNCH(m, FAM_WEIGHT, k_weight2, kSMs * 8, W2_THREADS, 0, mc, fc, dp);
+        LAUNCH(m, FAM_WEIGHT, k_weight2w, kSMs * 6, W2W_THREADS, 0, mc, fc, dp);
+    } else if (phase == 4) {  // owners take their new weights; the newborn split reads them (dsp_dynamic.h:829-866)
+        dp.tagged = d_tagged;
+        LAUNCH(m, FAM_WEIGHT, k_shard_apply_weights, kSMs * 4, B, 0, mc, dp);
         LAUNCH(m, FAM_NORM, k_norm, 1, 128, 0, mc, fc, dp);
         if (fc.n_tagged > 0 && fc.nb_num > 0) {
+            LAUNCH(m, FAM_NEWBORN, k_shard_zero, kSMs, B, 0, mc, fc, dp, 2);
             LAUNCH(m, FAM_NEWBORN, k_nb_point0, grid_for(fc.n_tagged, B), B, 0, mc, fc, dp);
             LAUNCH(m, FAM_NEWBORN, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{dp.ninmap, dp.nrank, nullptr, 0, fc.n_tagged}, ScanJob{}, ScanJob{}}});
             LAUNCH(m, FAM_NEWBORN, k_nb_mask, grid_for((long long)fc.n_tagged * fc.nb_num, B), B, 0, mc, fc, dp);
             LAUNCH(m, FAM_NEWBORN, k_nb_point1, grid_for((long long)fc.n_tagged * 32, B), B, 0, mc, fc, dp, 1);
         }
-    } else if (phase == 3) {
+    } else if (phase == 5) {
         dp.tagged = d_tagged;
         int newborn_ran = 0;
         if (fc.n_tagged > 0 && fc.nb_num > 0) {
@@ -845,8 +869,10 @@ int dspmap_shard_phase(dspmap *m, int phase, int n, const float *d_pts, float px
         LAUNCH(m, FAM_RESAMPLE, k_resample, kSMs * 8, 256, 0, mc, fc, dp);
         LAUNCH(m, FAM_CLEANUP, k_cleanup, kSMs * 2, B, 0, mc, fc, dp, newborn_ran, 0);
         CK(cudaMemcpyAsync(m->h_state, m->dp.st, sizeof(DevState), cudaMemcpyDeviceToHost, m->stream));
+        CK(cudaEventRecord(m->ev_state, m->stream));
+        m->state_event_recorded = true;
     } else {
-        g_err = "phase must be 0..3";
+        g_err = "phase must be 0..5";
         return DSPMAP_E_BAD_ARG;
     }
     CK(cudaGetLastError());

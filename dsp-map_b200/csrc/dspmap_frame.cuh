@@ -31,7 +31,7 @@ __global__ void k_frame_setup(MapConst mc, FrameConst fc, DevPtrs dp) {
         s->n_inexact = 0;
         s->n_vz = s->n_skipped = 0;
         s->n_occ_voxels = 0;
-        s->work_eval = s->work_w2 = 0;
+        s->work_eval = s->work_eval2 = s->work_w2 = 0;
         s->total_pairs = 0ull;
         s->use_store = 0;
         s->work_k4 = s->work_k5 = 0;
@@ -472,6 +472,26 @@ __global__ void k_shard_fov_gathered(MapConst mc, DevPtrs dp, int pass) {
     }
 }
 
+// zero the buffers that are merged with all-reduce(sum): exactly one rank writes each element
+__global__ void k_shard_zero(MapConst mc, FrameConst fc, DevPtrs dp, int which) {
+    const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+    if (which == 0) {  // C_z [P][OBS] and, right behind it, 1/C_z in bin order
+        const size_t n = (size_t)mc.P * mc.OBS + fc.n_points;
+        for (size_t i = tid; i < n; i += nth) dp.CZ[i] = 0.f;
+    } else if (which == 1) {  // new weights by global list index
+        const size_t n = (size_t)dp.poff[mc.P];
+        for (size_t i = tid; i < n; i += nth) dp.NW[i] = 0.f;
+    } else {                  // newborn split per tagged point
+        for (size_t i = tid; i < (size_t)fc.n_tagged; i += nth) dp.nst_shared[i] = 0.f;
+    }
+}
+__global__ void k_shard_apply_weights(MapConst mc, DevPtrs dp) {
+    const int n = dp.poff[mc.P];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int a = dp.LA[i];
+        if (a >= 0) dp.PA[a].w = dp.NW[i];
+    }
+}
 // ------------------------------------------------------------------------------------------------------------
 // K3b  pyramid lists (dsp_dynamic.h:1243-1259): scatter registered particles to their pyramid's segment, sort each
 //      segment by sweep key, keep the first L (the rest vanish, :1256-1259), and materialise a compact per-pyramid
@@ -715,7 +735,9 @@ __device__ __forceinline__ int chunk_to_pyramid(const int *chunk_off, int P, int
 }
 #define EVAL_THREADS 512
 #define TILE_LD 33  // per-warp 32 x 32 staging tile, padded
-__global__ void __launch_bounds__(EVAL_THREADS) k_pair_eval(MapConst mc, FrameConst fc, DevPtrs dp) {
+// mode 0: all items; sharded: mode 1 = rows of the point pyramids this rank computes C_z for (i % nranks == rank),
+// mode 2 = rows of the particle chunks this rank computes weights for (chunk % nranks == rank)
+__global__ void __launch_bounds__(EVAL_THREADS) k_pair_eval(MapConst mc, FrameConst fc, DevPtrs dp, int mode) {
     extern __shared__ float sm[];
     float *lut = sm;
     float *tile = sm + (DSP_LUT_HALF + 3) + (threadIdx.x >> 5) * (32 * TILE_LD);
@@ -727,13 +749,15 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_pair_eval(MapConst mc, FrameCo
     const int items = nchunks * mc.NB;
     for (;;) {
         int it = 0;
-        if (lane == 0) it = atomicAdd(&dp.st->work_eval, 1);
+        if (lane == 0) it = atomicAdd(mode == 2 ? &dp.st->work_eval2 : &dp.st->work_eval, 1);
         it = __shfl_sync(FULLMASK, it, 0);
         if (it >= items) break;
         const int c = it / mc.NB, ns = it - c * mc.NB;
+        if (mode == 2 && c % mc.nranks != mc.rank) continue;
         const int a = chunk_to_pyramid(dp.chunk_off, mc.P, c);
         if (ns >= dp.nbr[a * mc.NBW]) continue;
         const int i = dp.nbr[a * mc.NBW + 1 + ns];  // a point pyramid that sees pyramid a
+        if (mode == 1 && i % mc.nranks != mc.rank) continue;
         const int np = min(dp.obs_cnt[i], mc.OBS - 1);
         if (np == 0) continue;
         const int k0 = (c - dp.chunk_off[a]) << 5;
@@ -765,8 +789,8 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_pair_eval(MapConst mc, FrameCo
 #define CZ_JT 128
 __global__ void __launch_bounds__(CZ_THREADS) k_cz_chain(MapConst mc, FrameConst fc, DevPtrs dp) {
     extern __shared__ float czsm[];
-    float *tile0 = czsm, *tile1 = czsm + CZ_TILE;
-    float *pws0 = czsm + 2 * CZ_TILE, *pws1 = pws0 + CZ_JT;
+    float *tile0 = czsm, *tile1 = czsm + CZ_TILE + 8;  // + room for the alignment phase
+    float *pws0 = czsm + 2 * (CZ_TILE + 8), *pws1 = pws0 + CZ_JT;
     __shared__ int s_item;
     if (!use_pair_buffer(mc, dp)) return;
     const float enb = fc.nb_weight * (float)dp.st->n_valid * (float)fc.nb_num;  // :292
@@ -780,11 +804,13 @@ __global__ void __launch_bounds__(CZ_THREADS) k_cz_chain(MapConst mc, FrameConst
         if (i >= mc.P) break;
         const int np = min(dp.obs_cnt[i], mc.OBS - 1);
         if (np == 0) continue;
+        if (mc.sharded && i % mc.nranks != mc.rank) continue;  // another rank computes this pyramid's C_z
         const int nn = dp.nbr[i * mc.NBW];
         const int JT = min(CZ_JT, CZ_TILE / np);
         const float *gsrc = dp.G + (size_t)dp.rowbase[i];
         // tile iterator over (neighbour ns, particle offset k0); the "issue" state runs one tile ahead of the consumer
         int ins = 0, ik0 = 0, iln = nn > 0 ? dp.plen[dp.nbr[i * mc.NBW + 1]] : 0;
+        int ph0 = 0, ph1 = 0;
         const float *ig = gsrc;
         auto issue = [&](int buf) -> int {  // returns the number of particle rows of the issued tile, 0 when exhausted
             while (ins < nn && ik0 >= iln) {
@@ -795,7 +821,12 @@ __global__ void __launch_bounds__(CZ_THREADS) k_cz_chain(MapConst mc, FrameConst
             if (ins >= nn) return 0;
             const int cur = min(JT, iln - ik0), nfl = cur * np;
             float *t = buf ? tile1 : tile0;
-            for (int f = tid; f < nfl; f += CZ_THREADS) __pipeline_memcpy_async(t + f, ig + f, 4);
+            // 16-byte copies: start at the 16 B boundary below the tile and keep the source's phase inside the buffer
+            const int ph = (int)((reinterpret_cast<size_t>(ig) >> 2) & 3);
+            const float *src = ig - ph;
+            const int nq = (ph + nfl + 3) >> 2;
+            for (int q = tid; q < nq; q += CZ_THREADS) __pipeline_memcpy_async(t + 4 * q, src + 4 * q, 16);
+            if (buf) ph1 = ph; else ph0 = ph;
             if (tid < cur) __pipeline_memcpy_async((buf ? pws1 : pws0) + tid, dp.PW + dp.poff[dp.nbr[i * mc.NBW + 1 + ins]] + ik0 + tid, 4);
             ig += nfl;
             ik0 += cur;
@@ -811,7 +842,7 @@ __global__ void __launch_bounds__(CZ_THREADS) k_cz_chain(MapConst mc, FrameConst
             __pipeline_wait_prior(1);
             __syncthreads();
             if (tid < np) {  // the chain: (P_d * w) * g added in list order, one fp32 add per term
-                const float *t = (buf ? tile1 : tile0) + tid;
+                const float *t = (buf ? tile1 : tile0) + (buf ? ph1 : ph0) + tid;
                 const float *w = buf ? pws1 : pws0;
                 int jj = 0;
                 for (; jj + 8 <= cur; jj += 8) {
@@ -839,6 +870,7 @@ __global__ void __launch_bounds__(CZ_THREADS) k_cz_chain(MapConst mc, FrameConst
 // turn the chunk's contiguous 32 x np tile of G into quotient terms (P_d * g) / C_z (flat, coalesced loads); then warp 0,
 // lane = particle, adds its row in bin order.  Neighbours are visited in table order, so each particle's sum is one fp32
 // chain in the reference's order.  Two term buffers let the next neighbour's divisions overlap the current chain.
+#define W2_SWITCH 4096  // chunks of 32 particles: below, CTA-per-chunk (k_weight2); from here on, warp-per-chunk (k_weight2w)
 #define W2_THREADS 128
 #define W2_NP 100  // padded row length (np <= 99; odd stride: no bank conflicts in the chain)
 __global__ void __launch_bounds__(W2_THREADS) k_weight2(MapConst mc, FrameConst fc, DevPtrs dp) {
@@ -848,6 +880,7 @@ __global__ void __launch_bounds__(W2_THREADS) k_weight2(MapConst mc, FrameConst 
     if (!use_pair_buffer(mc, dp)) return;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int nchunks = dp.chunk_off[mc.P];
+    if (nchunks >= W2_SWITCH) return;  // many chunks: k_weight2w takes the frame
     for (;;) {
         __syncthreads();
         if (tid == 0) s_item = atomicAdd(&dp.st->work_w2, 1);
@@ -859,14 +892,11 @@ __global__ void __launch_bounds__(W2_THREADS) k_weight2(MapConst mc, FrameConst 
         const int ln = dp.plen[a], lb = dp.poff[a];
         const int nrows = min(32, ln - k0);
         const int nn = dp.nbr[a * mc.NBW];
-        if (mc.sharded) {  // only the owner of a particle updates its weight: skip chunks without local rows
-            const int mine = (tid < nrows && dp.LA[lb + k0 + tid] >= 0) ? 1 : 0;
-            if (!__syncthreads_or(mine)) continue;
-        }
+        if (mc.sharded && c % mc.nranks != mc.rank) continue;  // chunks are dealt round-robin, whoever owns the particles
         // chain state lives in warp 0 (lane = particle)
         bool act = false;
         float pw = 0.f, sum = 0.f;
-        if (wid == 0 && lane < nrows && dp.LA[lb + k0 + lane] >= 0) {
+        if (wid == 0 && lane < nrows) {
             const float4 p = dp.LP[lb + k0 + lane];
             pw = p.w;
             const float dist = sqrtf(p.x * p.x + p.y * p.y + p.z * p.z);
@@ -907,9 +937,96 @@ __global__ void __launch_bounds__(W2_THREADS) k_weight2(MapConst mc, FrameConst 
             prev_ld = ld;
             buf ^= 1;
         }
-        if (wid == 0 && lane < nrows && act) dp.PA[dp.LA[lb + k0 + lane]].w = pw * (fc.one_minus_Pd + sum);
+        if (wid == 0 && lane < nrows) {
+            const float w_new = act ? pw * (fc.one_minus_Pd + sum) : pw;
+            if (mc.sharded) dp.NW[lb + k0 + lane] = w_new;  // merged over ranks, applied by the particle's owner
+            else if (act) dp.PA[dp.LA[lb + k0 + lane]].w = w_new;
+        }
     }
 }
+// weights (dsp_dynamic.h:743-790), variant for MANY chunks (>= W2_SWITCH): one warp per 32 particles, lanes = particles.  The 32 x 32 sub-tiles of G
+// are read as coalesced rows (lane = point) into registers one sub-tile AHEAD of the one being consumed, staged through a
+// per-warp shared tile, and each lane adds its particle's row in (neighbour-table, bin) order.
+#define W2W_THREADS 256
+__global__ void __launch_bounds__(W2W_THREADS, 3) k_weight2w(MapConst mc, FrameConst fc, DevPtrs dp) {
+    __shared__ float tiles[(W2W_THREADS / 32) * 32 * TILE_LD];
+    __shared__ float czall[(W2W_THREADS / 32) * 32];
+    if (!use_pair_buffer(mc, dp)) return;
+    if (dp.chunk_off[mc.P] < W2_SWITCH) return;  // few chunks: the CTA-per-chunk kernel has more parallelism
+    float *tile = tiles + (threadIdx.x >> 5) * (32 * TILE_LD);
+    float *czs = czall + (threadIdx.x >> 5) * 32;
+    const int lane = threadIdx.x & 31;
+    const int nchunks = dp.chunk_off[mc.P];
+    for (;;) {
+        int c = 0;
+        if (lane == 0) c = atomicAdd(&dp.st->work_w2, 1);
+        c = __shfl_sync(FULLMASK, c, 0);
+        if (c >= nchunks) break;
+        if (mc.sharded && c % mc.nranks != mc.rank) continue;  // chunks are dealt round-robin over the ranks
+        const int a = chunk_to_pyramid(dp.chunk_off, mc.P, c);
+        const int k0 = (c - dp.chunk_off[a]) << 5;
+        const int ln = dp.plen[a], lb = dp.poff[a];
+        const int nrows = min(32, ln - k0);
+        bool act = lane < nrows;
+        const float4 p = act ? dp.LP[lb + k0 + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (act) {
+            const float dist = sqrtf(p.x * p.x + p.y * p.y + p.z * p.z);
+            const float maxlen = __int_as_float(dp.obs_maxbits[a]);
+            if (maxlen > 0.f && dist > maxlen + mc.occl) act = false;  // occluded (:761): weight unchanged
+        }
+        const int nn = dp.nbr[a * mc.NBW];
+        // sub-tile iterator over (neighbour ns, point block z0)
+        int ns = -1, z0 = 0, np = 0;
+        const float *gb = nullptr, *cz = nullptr;
+        auto advance = [&]() -> int {  // moves to the next sub-tile; returns its number of points, 0 when done
+            z0 += 32;
+            while (ns < 0 || z0 >= np) {
+                if (++ns >= nn) return 0;
+                const int b = dp.nbr[a * mc.NBW + 1 + ns];
+                np = min(dp.obs_cnt[b], mc.OBS - 1);
+                z0 = 0;
+                if (np == 0) continue;
+                gb = dp.G + (size_t)dp.rowbase[b] + (size_t)(dp.cum[b * mc.NBW + nb_index_of(mc, dp, b, a)] + k0) * np;
+                cz = dp.CZ + (size_t)b * mc.OBS;
+            }
+            return min(32, np - z0);
+        };
+        float v[32], czv = 1.f;
+        auto prefetch = [&](int nsub) {
+            if (lane < nsub) {
+                const float *src = gb + z0 + lane;
+#pragma unroll
+                for (int r = 0; r < 32; ++r) v[r] = r < nrows ? __ldg(src + (size_t)r * np) : 0.f;
+                czv = cz[z0 + lane];
+            }
+        };
+        float sum = 0.f;
+        int nsub = advance();
+        if (nsub) prefetch(nsub);
+        while (nsub) {
+            if (lane < nsub) {
+#pragma unroll
+                for (int r = 0; r < 32; ++r) tile[r * TILE_LD + lane] = v[r];
+                czs[lane] = czv;
+            }
+            __syncwarp();
+            const int cur = nsub;
+            nsub = advance();
+            if (nsub) prefetch(nsub);  // in flight while the current sub-tile is consumed
+            if (act) {
+#pragma unroll 4
+                for (int zl = 0; zl < cur; ++zl) sum += fc.Pd * tile[lane * TILE_LD + zl] / czs[zl];
+            }
+            __syncwarp();
+        }
+        if (lane < nrows) {
+            const float w_new = act ? p.w * (fc.one_minus_Pd + sum) : p.w;
+            if (mc.sharded) dp.NW[lb + k0 + lane] = w_new;  // merged over ranks, applied by the particle's owner
+            else if (act) dp.PA[dp.LA[lb + k0 + lane]].w = w_new;
+        }
+    }
+}
+
 // Exhaustive check of dsp_div_known for ONE divisor over every float a with |a| <= max (both signs).  What has to be
 // identical to IEEE division is the integer the quotient is turned into, so that is what is compared:
 //   mode 0: (int)(a / b)                                   voxel coordinates (dsp_dynamic.h:1078-1080)
@@ -1003,16 +1120,14 @@ __global__ void __launch_bounds__(256) k_nb_point1(MapConst mc, FrameConst fc, D
         if (!dp.ninmap[m]) {
             if (lane == 0) {
                 if (phase != 1) { dp.nvcnt[m] = 0; dp.nrcnt[m] = 0; }
-                else dp.nst_shared[m] = 0;
             }
             continue;
         }
         int n_static = 0;
-        if (phase == 2) n_static = dp.nst_shared[m];  // summed over ranks: exactly one owner contributed
+        if (phase == 2) n_static = (int)dp.nst_shared[m];  // summed over ranks: exactly one owner contributed
         const int pv0 = __float_as_int(dp.NPC[m].w);
         if (phase == 1 && (mc.model != 0 || pv0 < mc.v_lo || pv0 >= mc.v_hi)) {  // not this rank's voxel
-            if (lane == 0) dp.nst_shared[m] = 0;
-            continue;
+            continue;  // nst_shared was zeroed: another rank (or nobody) contributes
         }
         if (mc.model == 0 && phase != 2) {
             const int pv = pv0;
@@ -1055,7 +1170,7 @@ __global__ void __launch_bounds__(256) k_nb_point1(MapConst mc, FrameConst fc, D
             n_static = max(fc.nb_min_static, n_static);
         }
         if (phase == 1) {
-            if (lane == 0) dp.nst_shared[m] = n_static;
+            if (lane == 0) dp.nst_shared[m] = (float)n_static;
             continue;
         }
         if (lane == 0) {

@@ -41,7 +41,8 @@ struct DevPtrs {
     // sharded mode exchange buffers (caller-owned device memory, see dspmap_shard_config)
     float *xsend, *xrecv;  // [nranks][4 + cap_x * 12]: header {count}, then boundary-crossing movers
     float *gsend, *grecv;  // gsend [4 + cap_g * 8], grecv [nranks][4 + cap_g * 8]: registered particles
-    int *nst_shared;       // [max_points] per-point static newborn count, summed over ranks
+    float *nst_shared;     // [max_points] per-point static newborn count (as float), summed over ranks
+    float *NW;             // [nranks * cap_g] new weights by global list index, summed over ranks (one writer each)
     int *pcount, *pfill, *poff, *plen;
     int *PSkey, *PSaddr;
     int *LA;            // per-pyramid sorted list: slot address

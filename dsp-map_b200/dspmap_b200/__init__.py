@@ -89,7 +89,8 @@ def load_library():
         "dspmap_synchronize": (i, [vp]),
         "dspmap_profile_enable": (i, [vp, i]),
         "dspmap_profile_read": (i, [vp, C.POINTER(C.c_char_p), fp, ip, i]),
-        "dspmap_shard_config": (i, [vp, i, i, vp, vp, i, vp, vp, i, vp]),
+        "dspmap_shard_config": (i, [vp, i, i, vp, vp, i, vp, vp, i, vp, vp]),
+        "dspmap_shard_gather_records": (i, [vp, i]),
         "dspmap_shard_phase": (i, [vp, i, i, vp, f, f, f, C.c_double, f, f, f, f, vp, i]),
         "dspmap_estimator_create": (vp, [C.POINTER(Config), f]),
         "dspmap_estimator_destroy": (None, [vp]),
@@ -113,7 +114,7 @@ EXPORTED_SYMBOLS = [
     "dspmap_dump_observations", "dspmap_dump_pyramid_lists", "dspmap_cursors", "dspmap_set_cursors", "dspmap_counters",
     "dspmap_set_stage_limit", "dspmap_set_last_pose", "dspmap_set_stream", "dspmap_synchronize", "dspmap_profile_enable", "dspmap_profile_read",
     "dspmap_estimator_create", "dspmap_estimator_destroy", "dspmap_estimator_estimate",
-    "dspmap_shard_config", "dspmap_shard_phase",
+    "dspmap_shard_config", "dspmap_shard_gather_records", "dspmap_shard_phase",
 ]
 
 
@@ -342,9 +343,13 @@ class DSPMap:
                                                          float(pos[2]), float(t), float(quat[0]), float(quat[1]),
                                                          float(quat[2]), float(quat[3]), C.c_void_p(d_tagged), n_tagged))
 
-    def shard_config(self, rank, nranks, xsend, xrecv, cap_x, gsend, grecv, cap_g, nst):
+    def shard_config(self, rank, nranks, xsend, xrecv, cap_x, gsend, grecv, cap_g, czinv, shared):
         return self._check(self.lib.dspmap_shard_config(self.h, rank, nranks, C.c_void_p(xsend), C.c_void_p(xrecv), cap_x,
-                                                        C.c_void_p(gsend), C.c_void_p(grecv), cap_g, C.c_void_p(nst)))
+                                                        C.c_void_p(gsend), C.c_void_p(grecv), cap_g, C.c_void_p(czinv),
+                                                        C.c_void_p(shared)))
+
+    def shard_gather_records(self, records):
+        return self._check(self.lib.dspmap_shard_gather_records(self.h, records))
 
     def shard_phase(self, phase, n, d_pts, pos, t, quat, d_tagged, n_tagged):
         return self._check(self.lib.dspmap_shard_phase(self.h, phase, n, C.c_void_p(d_pts), float(pos[0]), float(pos[1]),

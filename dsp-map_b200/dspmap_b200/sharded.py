@@ -1,12 +1,15 @@
 """Voxel-subspace sharding of one DSP map over several GPUs (include/dspmap_b200.h "sharding").
 
-The map's z layers are cut into `nranks` slabs; rank r owns the particles whose voxel lies in its slab.  One frame is four
-library phases with three collectives between them:
+The map's z layers are cut into `nranks` slabs; rank r owns the particles whose voxel lies in its slab.  One frame is six
+library phases with five collectives between them:
 
     phase 0  -> all-to-all   boundary-crossing movers (fixed-size slabs, no host round trip)
-    phase 1  -> all-gather   particles registered in FOV pyramids (every rank builds identical global pyramid lists)
-    phase 2  -> all-reduce   per-point newborn split (computed by the owner of the point's voxel)
-    phase 3
+    phase 1  -> all-gather   particles registered in FOV pyramids: 16-byte headers first (one small host sync to size the
+                             payload), then only the used part of the slabs; every rank builds identical pyramid lists
+    phase 2  -> all-reduce   C_z, computed for point pyramids i % nranks == rank   (zero-initialised, one writer: exact)
+    phase 3  -> all-reduce   new weights of particle chunks c % nranks == rank (whoever owns the particles)
+    phase 4  -> all-reduce   owners apply their weights; newborn split of the points whose voxel the rank owns
+    phase 5
 
 `NcclComm` runs them with torch.distributed (one process per GPU, NCCL over NVLink); `LocalCluster` drives N handles in
 one process on one GPU and performs the same data movement with tensor copies — the library code path is identical, which
@@ -18,6 +21,7 @@ import torch
 from . import DSPMap, derive
 
 XREC, GREC, HDR = 12, 8, 4
+GATHER_ROUND = 1024
 
 
 def slab_plan(nz, nranks):
@@ -29,20 +33,27 @@ def slab_plan(nz, nranks):
 def default_caps(cfg, nranks):
     d = derive(cfg)
     cap_live = min(d["V"] * d["S"], 8 << 20)
-    cap_g = max(1024, min(cap_live // nranks, 2 << 20))
-    cap_x = max(1024, min(cap_g // 4, 1 << 18))
+    cap_g = max(GATHER_ROUND, min(cap_live // nranks, 1 << 20) // GATHER_ROUND * GATHER_ROUND)
+    cap_x = 8192   # boundary crossers per (source, destination) pair and frame
     return cap_x, cap_g
 
 
+def gather_size(counts, cap_g):
+    """Records per rank moved by the all-gather: the largest count, rounded up, at most the slab capacity."""
+    g = (max(max(counts), 1) + GATHER_ROUND - 1) // GATHER_ROUND * GATHER_ROUND
+    return min(g, cap_g)
+
+
 class ShardBuffers:
-    def __init__(self, nranks, cap_x, cap_g, max_points, device):
+    def __init__(self, nranks, cap_x, cap_g, max_points, P, obs_max, device):
         self.xs = HDR + cap_x * XREC
         self.gs = HDR + cap_g * GREC
-        self.xsend = torch.zeros(nranks * self.xs, dtype=torch.float32, device=device)
-        self.xrecv = torch.zeros(nranks * self.xs, dtype=torch.float32, device=device)
-        self.gsend = torch.zeros(self.gs, dtype=torch.float32, device=device)
-        self.grecv = torch.zeros(nranks * self.gs, dtype=torch.float32, device=device)
-        self.nst = torch.zeros(max_points, dtype=torch.int32, device=device)
+        z = lambda n, dt=torch.float32: torch.zeros(n, dtype=dt, device=device)  # noqa: E731
+        self.xsend, self.xrecv = z(nranks * self.xs), z(nranks * self.xs)
+        self.gsend, self.grecv = z(self.gs), z(nranks * self.gs)
+        self.hdr = z(nranks * HDR)
+        self.czinv = z(P * obs_max + max_points)
+        self.shared = z(max_points + nranks * cap_g)
 
 
 class ShardedDSPMap:
@@ -52,13 +63,15 @@ class ShardedDSPMap:
         self.cfg, self.rank, self.nranks = cfg, rank, nranks
         dx, dg = default_caps(cfg, nranks)
         self.cap_x, self.cap_g = cap_x or dx, cap_g or dg
-        self.map = DSPMap(cfg, seed=seed, device=device, max_points=max_points, **kw)
-        mp = max_points or 65536
-        self.buf = ShardBuffers(nranks, self.cap_x, self.cap_g, mp, torch.device("cuda", device))
-        self.map.shard_config(rank, nranks, self.buf.xsend.data_ptr(), self.buf.xrecv.data_ptr(), self.cap_x,
-                              self.buf.gsend.data_ptr(), self.buf.grecv.data_ptr(), self.cap_g, self.buf.nst.data_ptr())
+        self.max_points = max_points or 65536
+        self.map = DSPMap(cfg, seed=seed, device=device, max_points=self.max_points, **kw)
+        m = self.map
+        self.buf = b = ShardBuffers(nranks, self.cap_x, self.cap_g, self.max_points, m.P, m.obs_max, torch.device("cuda", device))
+        m.shard_config(rank, nranks, b.xsend.data_ptr(), b.xrecv.data_ptr(), self.cap_x, b.gsend.data_ptr(), b.grecv.data_ptr(),
+                       self.cap_g, b.czinv.data_ptr(), b.shared.data_ptr())
         self.z0, self.z1 = slab_plan(cfg["nz"], nranks)[rank]
         self.v_lo, self.v_hi = self.z0 * cfg["nx"] * cfg["ny"], self.z1 * cfg["nx"] * cfg["ny"]
+        self.P_obs = m.P * m.obs_max
 
     def phase(self, k, n, d_pts, pos, t, quat, d_tagged, n_tagged):
         return self.map.shard_phase(k, n, d_pts, pos, t, quat, d_tagged, n_tagged)
@@ -74,7 +87,7 @@ class ShardedDSPMap:
 
 
 class NcclComm:
-    """The three collectives of a sharded frame over torch.distributed (backend nccl; gloo works too for tests)."""
+    """The collectives of a sharded frame over torch.distributed (backend nccl; gloo works too, for the CPU tests)."""
 
     def __init__(self, group=None):
         import torch.distributed as dist
@@ -105,16 +118,26 @@ class NcclComm:
 
 def sharded_update(sm, comm, n, d_pts, pos, t, quat, d_tagged, n_tagged):
     """One frame on this rank (all ranks call it with the same cloud, pose and newborn input)."""
+    b, N = sm.buf, sm.nranks
     rc = sm.phase(0, n, d_pts, pos, t, quat, d_tagged, n_tagged)
     if rc != 1:
         return rc
-    comm.all_to_all(sm.buf.xrecv, sm.buf.xsend, sm.nranks)
+    comm.all_to_all(b.xrecv, b.xsend, N)
     sm.phase(1, n, d_pts, pos, t, quat, d_tagged, n_tagged)
-    comm.all_gather(sm.buf.grecv, sm.buf.gsend, sm.nranks)
+    comm.all_gather(b.hdr, b.gsend[:HDR], N)                      # counts of registered particles per rank
+    counts = b.hdr.view(torch.int32)[::HDR].tolist()              # the one host synchronisation of a sharded frame
+    g = gather_size(counts, sm.cap_g)
+    sm.map.shard_gather_records(g)
+    gs = HDR + g * GREC
+    comm.all_gather(b.grecv[:N * gs], b.gsend[:gs], N)
     sm.phase(2, n, d_pts, pos, t, quat, d_tagged, n_tagged)
-    if n_tagged > 0:
-        comm.all_reduce_sum(sm.buf.nst[:n_tagged])
+    comm.all_reduce_sum(b.czinv[:sm.P_obs + n])
     sm.phase(3, n, d_pts, pos, t, quat, d_tagged, n_tagged)
+    comm.all_reduce_sum(b.shared[sm.max_points:sm.max_points + sum(counts)])   # new weights
+    sm.phase(4, n, d_pts, pos, t, quat, d_tagged, n_tagged)
+    if n_tagged > 0:
+        comm.all_reduce_sum(b.shared[:n_tagged])                               # newborn split
+    sm.phase(5, n, d_pts, pos, t, quat, d_tagged, n_tagged)
     return 1
 
 
@@ -137,39 +160,55 @@ class LocalCluster:
             s.map.synchronize()
         torch.cuda.synchronize()
 
+    def _each(self, k, args):
+        for s in self.shards:
+            s.phase(k, *args)
+        self._sync()
+
     def update(self, pts, pos, t, quat, tagged):
         """pts [n,3], tagged [m,7]: host arrays; the same inputs go to every shard."""
         d_pts = torch.from_numpy(np.ascontiguousarray(pts, np.float32)).to(self.dev)
         tg = np.ascontiguousarray(tagged, np.float32).reshape(-1, 7)
         d_tag = torch.from_numpy(tg if len(tg) else np.zeros((1, 7), np.float32)).to(self.dev)
-        n, nt, N = len(pts), len(tg), self.nranks
-        rcs = [s.phase(0, n, d_pts.data_ptr(), pos, t, quat, d_tag.data_ptr(), nt) for s in self.shards]
+        n, nt, N, sh = len(pts), len(tg), self.nranks, self.shards
+        args = (n, d_pts.data_ptr(), pos, t, quat, d_tag.data_ptr(), nt)
+        rcs = [s.phase(0, *args) for s in sh]
         if any(rc != 1 for rc in rcs):
             return rcs[0]
         self._sync()
-        xs = self.shards[0].buf.xs
-        for r, dst in enumerate(self.shards):   # all-to-all: slab r of every sender goes to rank r
-            for s, src in enumerate(self.shards):
+        xs = sh[0].buf.xs
+        for r, dst in enumerate(sh):   # all-to-all: slab r of every sender goes to rank r
+            for s, src in enumerate(sh):
                 dst.buf.xrecv[s * xs:(s + 1) * xs].copy_(src.buf.xsend[r * xs:(r + 1) * xs])
         self._sync()
-        for s in self.shards:
-            s.phase(1, n, d_pts.data_ptr(), pos, t, quat, d_tag.data_ptr(), nt)
+        self._each(1, args)
+        counts = [int(s.buf.gsend[:1].view(torch.int32).item()) for s in sh]
+        g = gather_size(counts, sh[0].cap_g)
+        gs = HDR + g * GREC
+        gathered = torch.cat([s.buf.gsend[:gs] for s in sh])   # all-gather of the used part of the slabs
+        for s in sh:
+            s.map.shard_gather_records(g)
+            s.buf.grecv[:N * gs].copy_(gathered)
         self._sync()
-        g = torch.cat([s.buf.gsend for s in self.shards])   # all-gather
-        for s in self.shards:
-            s.buf.grecv.copy_(g)
+        self._each(2, args)
+        k = sh[0].P_obs + n
+        tot = torch.stack([s.buf.czinv[:k] for s in sh]).sum(0)   # all-reduce: one non-zero contributor per element
+        for s in sh:
+            s.buf.czinv[:k].copy_(tot)
         self._sync()
-        for s in self.shards:
-            s.phase(2, n, d_pts.data_ptr(), pos, t, quat, d_tag.data_ptr(), nt)
+        self._each(3, args)
+        k0, k1 = sh[0].max_points, sh[0].max_points + sum(counts)
+        tot = torch.stack([s.buf.shared[k0:k1] for s in sh]).sum(0)
+        for s in sh:
+            s.buf.shared[k0:k1].copy_(tot)
         self._sync()
+        self._each(4, args)
         if nt:
-            tot = torch.stack([s.buf.nst[:nt] for s in self.shards]).sum(0, dtype=torch.int32)   # all-reduce
-            for s in self.shards:
-                s.buf.nst[:nt].copy_(tot)
+            tot = torch.stack([s.buf.shared[:nt] for s in sh]).sum(0)
+            for s in sh:
+                s.buf.shared[:nt].copy_(tot)
         self._sync()
-        for s in self.shards:
-            s.phase(3, n, d_pts.data_ptr(), pos, t, quat, d_tag.data_ptr(), nt)
-        self._sync()
+        self._each(5, args)
         return 1
 
     # ---- assembled state (for parity checks against an unsharded map) ------------------------------------------

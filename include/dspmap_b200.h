@@ -158,19 +158,27 @@ int dspmap_profile_read(dspmap *m, const char **names, float *ms, int32_t *launc
 
 /* ---- voxel-subspace sharding over the GPUs of one box (one handle per GPU / rank) -----------------------------------
  * The map's z layers are cut into `nranks` equal slabs; handle `rank` owns the particles of its slab.  A frame is
- * enqueued in four phases with three collectives between them, issued by the caller on the same stream
+ * enqueued in six phases with five collectives between them, issued by the caller on the same stream
  * (dsp-map_b200/dspmap_b200/sharded.py does it with torch.distributed / NCCL):
  *   phase 0  binning, prediction; movers that leave the slab are written to xsend[dest rank]
  *            -> all-to-all of the fixed-size slabs xsend -> xrecv                       (the boundary exchange)
  *   phase 1  imported movers join the ordered arrival replay; registered particles are packed into gsend
- *            -> all-gather gsend -> grecv
- *   phase 2  identical global pyramid lists on every rank, C_z, weights of own particles, newborn split of own voxels
- *            -> all-reduce(sum) of nst (int32 per tagged point)
- *   phase 3  newborn candidates that land in the slab, occupancy + resampling + future status of the slab
+ *            -> all-gather of the slab headers (counts), dspmap_shard_gather_records(max count), all-gather gsend -> grecv
+ *   phase 2  identical global pyramid lists on every rank; C_z of the point pyramids i with i % nranks == rank
+ *            -> all-reduce(sum) of czinv (zero-initialised, one writer per element: exact)
+ *   phase 3  weights of the particle chunks c with c % nranks == rank (whoever owns the particles)
+ *            -> all-reduce(sum) of the weight part of `shared`
+ *   phase 4  owners apply the new weights; newborn split of the points whose voxel this rank owns
+ *            -> all-reduce(sum) of the split part of `shared`
+ *   phase 5  newborn candidates that land in the slab; occupancy, resampling, future status
  * Buffers are device memory owned by the caller: xsend/xrecv hold nranks slabs of (4 + cap_x*12) floats, gsend one and
- * grecv nranks slabs of (4 + cap_g*8) floats, nst max_points int32.  Results are bit-identical to a single handle. */
+ * grecv nranks slabs of (4 + cap_g*8) floats, czinv P*obs_max + max_points floats, shared max_points + nranks*cap_g
+ * floats.  Results are bit-identical to a single handle. */
 int dspmap_shard_config(dspmap *m, int rank, int nranks, float *xsend, float *xrecv, int cap_x, float *gsend, float *grecv,
-                        int cap_g, int32_t *nst);
+                        int cap_g, float *czinv, float *shared);
+/* Records per rank actually moved by this frame's all-gather (>= the largest count, <= cap_g): sets the slab stride of
+ * grecv for phases 2..4. */
+int dspmap_shard_gather_records(dspmap *m, int records);
 int dspmap_shard_phase(dspmap *m, int phase, int n, const float *d_pts, float px, float py, float pz, double t, float qw,
                        float qx, float qy, float qz, const float *d_tagged, int n_tagged);
 

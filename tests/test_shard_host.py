@@ -10,7 +10,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from dspmap_b200 import CONFIGS
-from dspmap_b200.sharded import GREC, HDR, XREC, NcclComm, default_caps, slab_plan
+from dspmap_b200.sharded import GREC, HDR, XREC, NcclComm, default_caps, gather_size, slab_plan
 
 
 def test_slab_plan_covers_the_map_once():
@@ -25,7 +25,8 @@ def test_slab_plan_covers_the_map_once():
                 r = min(n - 1, z // zpr)
                 assert plan[r][0] <= z < plan[r][1]
     cx, cg = default_caps(CONFIGS["cfg5"], 8)
-    assert cx >= 1024 and cg * 8 <= 8 << 20
+    assert cx >= 1024 and cg * 8 <= 8 << 20 and cg % 1024 == 0
+    assert gather_size([5, 3000, 70], cg) == 3072 and gather_size([0, 0], cg) == 1024 and gather_size([10 ** 9], cg) == cg
 
 
 def _free_port():
@@ -56,10 +57,11 @@ def _worker(rank, world, port, q):
     gr = torch.zeros(world * gs)
     comm.all_gather(gr, g, world)
     ok = ok and all(torch.all(gr[s * gs:(s + 1) * gs] == s + 1) for s in range(world))
-    # all-reduce of the per-point newborn split: exactly one owner contributes a non-zero value per point
-    nst = torch.tensor([3 if (i % world) == rank else 0 for i in range(10)], dtype=torch.int32)
+    # all-reduce of a zero-initialised buffer with exactly one writer per element reproduces the writers' bits
+    vals = torch.tensor([0.1 * (i + 1) for i in range(10)], dtype=torch.float32)
+    nst = torch.where(torch.arange(10) % world == rank, vals, torch.zeros(10))
     comm.all_reduce_sum(nst)
-    ok = ok and bool(torch.all(nst == 3))
+    ok = ok and bool(torch.equal(nst, vals))
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 
