@@ -1192,6 +1192,16 @@ int dspmap_estimator_estimate(dspmap_estimator *e, int n, const float *pts, floa
     return nt;
 }
 
+int dspmap_euclidean_clusters(const float *xyz, int n, float tolerance, int min_size, int max_size, int path, int *labels) {
+    if (n < 0 || (n > 0 && (!xyz || !labels))) return DSPMAP_E_BAD_ARG;
+    std::vector<std::vector<int>> cl;
+    if (!euclidean_clusters_path(xyz, n, tolerance, min_size, max_size, path, cl)) return DSPMAP_E_CAPACITY;
+    for (int i = 0; i < n; ++i) labels[i] = -1;
+    for (size_t c = 0; c < cl.size(); ++c)
+        for (int idx : cl[c]) labels[idx] = (int)c;
+    return (int)cl.size();
+}
+
 }  // extern "C"
 
 namespace {

@@ -3,7 +3,10 @@
 #include "velocity_estimator.h"
 
 #include <algorithm>
+#include <climits>
 #include <cmath>
+#include <cstdint>
+#include <cstring>
 #include <limits>
 
 #include "dspmap_hostmath.h"
@@ -51,13 +54,9 @@ struct Grid {  // open-addressing hash from integer cell to the head of a linked
 };
 }  // namespace
 
-void euclidean_clusters(const float *xyz, int n, float tol, int min_size, int max_size, std::vector<std::vector<int>> &out) {
-    // Connected components of the graph "d2 <= tol^2" through a union-find over grid cells.  The cell edge is below
-    // tol / sqrt(3), so all points of one cell are mutually linked; links between cells up to two cells apart need one
-    // witness pair.  Cost is linear in the points for the dense clouds a nearby surface produces (a per-point
-    // neighbourhood search is quadratic there).  Components do not depend on the traversal, so the result is identical.
-    out.clear();
-    if (n == 0 || !(tol > 0.f)) return;
+namespace {
+// Hash-grid path for clouds whose bounding box is too large for the dense grid (same components).
+void hashed_clusters(const float *xyz, int n, float tol, int min_size, int max_size, std::vector<std::vector<int>> &out) {
     const float tol2 = tol * tol;
     const float edge = tol * 0.57f;
     std::vector<int64_t> cells(3 * (size_t)n);
@@ -118,7 +117,194 @@ void euclidean_clusters(const float *xyz, int n, float tol, int min_size, int ma
     }
     for (auto &c : comps)
         if ((int)c.size() >= min_size && (int)c.size() <= max_size) out.push_back(std::move(c));
+}
+}  // namespace
+
+namespace {
+// Scratch of the dense-grid clustering path, reused from frame to frame (no allocation in steady state).
+struct ClusterScratch {
+    std::vector<int> grid;  // padded dense cell grid -> compact cell number; all -1 between calls
+    std::vector<float> box;
+    std::vector<unsigned char> bits;
+    std::vector<int> cell_of, next, rep, tail, cell_lin, parent, croot, comp_of_root, comp_size;
+};
+const long long kDenseCells = 1ll << 23;  // 32 MB of int; larger bounding boxes take the hash-grid path
+
+// Connected components on a dense cell grid over the cloud's bounding box.  Returns false when the box is too large.
+bool dense_clusters(const float *xyz, int n, float tol, int min_size, int max_size, std::vector<std::vector<int>> &out) {
+    static thread_local ClusterScratch S;
+    const float tol2 = tol * tol;
+    const float inv_edge = 1.f / (tol * 0.57f);  // cells only need edge < tol / sqrt(3) up to rounding (1.3 % slack)
+    auto cell = [inv_edge](float v) {
+        const float f = v * inv_edge;
+        int c = (int)f;
+        return c - (int)(f < (float)c);  // floor
+    };
+    // bounding box first (floor is monotone, so the extreme cells are the cells of the extreme coordinates)
+    float fl[3] = {xyz[0], xyz[1], xyz[2]}, fh[3] = {xyz[0], xyz[1], xyz[2]};
+    for (int i = 1; i < n; ++i)
+        for (int k = 0; k < 3; ++k) {
+            const float v = xyz[3 * i + k];
+            fl[k] = v < fl[k] ? v : fl[k];
+            fh[k] = v > fh[k] ? v : fh[k];
+        }
+    int lo[3];
+    long long dim[3];
+    for (int k = 0; k < 3; ++k) {
+        if (!(fl[k] * inv_edge > -1e9f && fh[k] * inv_edge < 1e9f)) return false;  // also rejects NaN extremes
+        lo[k] = cell(fl[k]);
+        dim[k] = (long long)cell(fh[k]) - lo[k] + 5;  // 2 cells of padding on each side
+    }
+    const long long dx = dim[0], dy = dim[1], dz = dim[2];
+    if (dx * dy > kDenseCells || dx * dy * dz > kDenseCells) return false;
+    const size_t vol = (size_t)(dx * dy * dz);
+    if (S.grid.size() < vol) S.grid.resize(vol, -1);
+    if (S.bits.size() < vol / 8 + 16) S.bits.resize(vol / 8 + 16, 0);
+    int *grid = S.grid.data();
+    unsigned char *bits = S.bits.data();  // one occupancy bit per cell: the neighbour scan below stays in L1
+    S.cell_of.resize(n); S.next.resize(n);
+    S.rep.clear(); S.tail.clear(); S.cell_lin.clear(); S.box.clear();
+    // cells numbered in order of first appearance; each cell's point list ascends by index, its head is rep[c]
+    const int ox = 2 - lo[0], oy = 2 - lo[1], oz = 2 - lo[2];
+    for (int i = 0; i < n; ++i) {
+        const int cx = cell(xyz[3 * i]) + ox, cy = cell(xyz[3 * i + 1]) + oy, cz = cell(xyz[3 * i + 2]) + oz;
+        if ((unsigned)cx >= (unsigned)dx || (unsigned)cy >= (unsigned)dy || (unsigned)cz >= (unsigned)dz) {  // a NaN coordinate
+            for (size_t c = 0; c < S.cell_lin.size(); ++c) { grid[S.cell_lin[c]] = -1; bits[S.cell_lin[c] >> 3] = 0; }
+            return false;
+        }
+        const int l = (int)(((long long)cz * dy + cy) * dx + cx);
+        int c = grid[l];
+        const float x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+        if (c < 0) {
+            c = (int)S.rep.size();
+            grid[l] = c;
+            bits[l >> 3] |= (unsigned char)(1u << (l & 7));
+            S.rep.push_back(i); S.tail.push_back(i); S.cell_lin.push_back(l);
+            const float b6[6] = {x, y, z, x, y, z};
+            S.box.insert(S.box.end(), b6, b6 + 6);
+        } else {
+            S.next[S.tail[c]] = i;
+            S.tail[c] = i;
+            float *bb = &S.box[6 * (size_t)c];  // the cell's points' bounding box: a cheap lower bound for linked()
+            bb[0] = std::min(bb[0], x); bb[1] = std::min(bb[1], y); bb[2] = std::min(bb[2], z);
+            bb[3] = std::max(bb[3], x); bb[4] = std::max(bb[4], y); bb[5] = std::max(bb[5], z);
+        }
+        S.next[i] = -1;
+        S.cell_of[i] = c;
+    }
+    const int nc = (int)S.rep.size();
+    const float *box = S.box.data();
+    auto apart = [&](int ca, int cb) {  // no pair of the two cells can be within tol
+        const float *A = box + 6 * (size_t)ca, *B = box + 6 * (size_t)cb;
+        float d2 = 0.f;
+        for (int k = 0; k < 3; ++k) {
+            const float g = std::max(std::max(B[k] - A[k + 3], A[k] - B[k + 3]), 0.f);
+            d2 += g * g;
+        }
+        return d2 > tol2 * 1.0001f;  // margin: the bound is evaluated in a different rounding than the pair test
+    };
+    S.parent.resize(nc);
+    int *parent = S.parent.data();
+    for (int c = 0; c < nc; ++c) parent[c] = c;
+    auto root = [&](int c) {
+        while (parent[c] != c) { parent[c] = parent[parent[c]]; c = parent[c]; }
+        return c;
+    };
+    const int *next = S.next.data();
+    auto linked = [&](int ha, int hb) {  // is there a pair (i in cell a, j in cell b) within tol?
+        for (int i = ha; i >= 0; i = next[i]) {
+            const float px = xyz[3 * i], py = xyz[3 * i + 1], pz = xyz[3 * i + 2];
+            for (int j = hb; j >= 0; j = next[j]) {
+                const float ddx = xyz[3 * j] - px, ddy = xyz[3 * j + 1] - py, ddz = xyz[3 * j + 2] - pz;
+                if (ddx * ddx + ddy * ddy + ddz * ddz <= tol2) return true;
+            }
+        }
+        return false;
+    };
+    // Each unordered pair of cells once: the lexicographically positive half of the 5 x 5 x 5 neighbourhood, scanned as
+    // rows of five x-adjacent cells (one cache line; an all-empty row is skipped with one test).  Adjacent cells (pass 0)
+    // before cells two apart (pass 1): most of the far links are then already implied.
+    struct Row { int off; int amask; };  // bit (a + 2) set: offset a of this row belongs to the pass
+    Row rows[2][13];
+    int nrows[2] = {0, 0};
+    for (int d = 0; d <= 2; ++d)
+        for (int b = -2; b <= 2; ++b) {
+            if (d == 0 && b < 0) continue;
+            int m[2] = {0, 0};
+            for (int a = -2; a <= 2; ++a) {
+                if (d == 0 && b == 0 && a <= 0) continue;
+                const int ch = std::max(std::max(a < 0 ? -a : a, b < 0 ? -b : b), d);
+                m[ch - 1] |= 1 << (a + 2);
+            }
+            for (int ps = 0; ps < 2; ++ps)
+                if (m[ps]) rows[ps][nrows[ps]++] = Row{(int)((d * dy + b) * dx), m[ps]};
+        }
+    for (int pass = 0; pass < 2; ++pass)
+        for (int c = 0; c < nc; ++c) {
+            const int base = S.cell_lin[c];
+            const int hc = S.rep[c];
+            for (int k = 0; k < nrows[pass]; ++k) {
+                const int pos = base + rows[pass][k].off - 2;  // >= 0: the grid is padded by two cells
+                uint64_t w;
+                memcpy(&w, bits + (pos >> 3), 8);
+                unsigned occ = (unsigned)(w >> (pos & 7)) & (unsigned)rows[pass][k].amask;
+                while (occ) {
+                    const int a = __builtin_ctz(occ);
+                    occ &= occ - 1;
+                    const int cb = grid[pos + a];
+                    const int ra = root(c), rb = root(cb);
+                    if (ra == rb) continue;
+                    if (!apart(c, cb) && linked(hc, S.rep[cb])) parent[std::max(ra, rb)] = std::min(ra, rb);
+                }
+            }
+        }
+    for (int c = 0; c < nc; ++c) { grid[S.cell_lin[c]] = -1; bits[S.cell_lin[c] >> 3] = 0; }  // leave the grid clean for the next call
+    // gather components; a component is discovered at its smallest point index, like a seeded flood fill would
+    S.croot.resize(nc);
+    for (int c = 0; c < nc; ++c) S.croot[c] = root(c);
+    S.comp_of_root.assign(nc, -1);
+    S.comp_size.clear();
+    for (int i = 0; i < n; ++i) {
+        const int r = S.croot[S.cell_of[i]];
+        if (S.comp_of_root[r] < 0) { S.comp_of_root[r] = (int)S.comp_size.size(); S.comp_size.push_back(0); }
+        ++S.comp_size[S.comp_of_root[r]];
+    }
+    const int ncomp = (int)S.comp_size.size();
+    std::vector<int> slot(ncomp, -1);
+    for (int k = 0; k < ncomp; ++k)
+        if (S.comp_size[k] >= min_size && S.comp_size[k] <= max_size) {
+            slot[k] = (int)out.size();
+            out.emplace_back();
+            out.back().reserve(S.comp_size[k]);
+        }
+    for (int i = 0; i < n; ++i) {
+        const int s = slot[S.comp_of_root[S.croot[S.cell_of[i]]]];
+        if (s >= 0) out[s].push_back(i);  // ascending indices by construction
+    }
+    return true;
+}
+}  // namespace
+
+void euclidean_clusters(const float *xyz, int n, float tol, int min_size, int max_size, std::vector<std::vector<int>> &out) {
+    // Connected components of the graph "d2 <= tol^2" through a union-find over grid cells.  The cell edge is below
+    // tol / sqrt(3), so all points of one cell are mutually linked; links between cells up to two cells apart need one
+    // witness pair.  Cost is linear in the points for the dense clouds a nearby surface produces (a per-point
+    // neighbourhood search is quadratic there).  Components do not depend on the traversal, so the result is identical.
+    euclidean_clusters_path(xyz, n, tol, min_size, max_size, 0, out);
+}
+
+bool euclidean_clusters_path(const float *xyz, int n, float tol, int min_size, int max_size, int path, std::vector<std::vector<int>> &out) {
+    out.clear();
+    if (n == 0 || !(tol > 0.f)) return true;
+    bool done = false;
+    if (path != 1) {
+        done = dense_clusters(xyz, n, tol, min_size, max_size, out);
+        if (!done) out.clear();
+        if (!done && path == 2) return false;
+    }
+    if (!done) hashed_clusters(xyz, n, tol, min_size, max_size, out);
     std::stable_sort(out.begin(), out.end(), [](const std::vector<int> &a, const std::vector<int> &b) { return a.size() > b.size(); });
+    return true;
 }
 
 void hungarian(const std::vector<float> &cost, int R, int C, std::vector<int> &assign) {
@@ -161,38 +347,95 @@ void hungarian(const std::vector<float> &cost, int R, int C, std::vector<int> &a
         if (p[j] >= 1 && p[j] <= R && j <= C) assign[p[j] - 1] = j - 1;
 }
 
+namespace {
+typedef float vf8 __attribute__((vector_size(32)));
+typedef int vi8 __attribute__((vector_size(32)));
+
+// Rotates n sensor-frame points into the world-aligned frame and keeps those inside the four outer FOV planes
+// (dsp_dynamic.h:226-257), eight points per step.  Every lane evaluates dsp_rotate's expressions in dsp_rotate's order
+// (no contraction: the file is compiled with -ffp-contract=off and neither target has FMA enabled), so the kept points are
+// bit-identical to the scalar helper's.  nrm = the four rotated plane normals (h first, h last, v first, v last).
+__attribute__((target_clones("avx2", "default")))
+int rotate_in_view(const float *pts, int n, const float *q, const float *qi, const float *nrm, float *kept) {
+    const float aw = q[0], ax = q[1], ay = q[2], az = q[3];
+    const float iw = qi[0], ix = qi[1], iy = qi[2], iz = qi[3];
+    int nk = 0;
+    for (int i0 = 0; i0 < n; i0 += 8) {
+        alignas(32) float sx[8], sy[8], sz[8];
+        const int m = std::min(8, n - i0);
+        for (int l = 0; l < m; ++l) {
+            sx[l] = pts[3 * (size_t)(i0 + l)];
+            sy[l] = pts[3 * (size_t)(i0 + l) + 1];
+            sz[l] = pts[3 * (size_t)(i0 + l) + 2];
+        }
+        for (int l = m; l < 8; ++l) sx[l] = sy[l] = sz[l] = 0.f;
+        const vf8 bx = *(const vf8 *)sx, by = *(const vf8 *)sy, bz = *(const vf8 *)sz;
+        const vf8 bw = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // scalar component of the pure quaternion (0, v)
+        const vf8 tw = aw * bw - ax * bx - ay * by - az * bz;
+        const vf8 tx = aw * bx + ax * bw + ay * bz - az * by;
+        const vf8 ty = aw * by + ay * bw + az * bx - ax * bz;
+        const vf8 tz = aw * bz + az * bw + ax * by - ay * bx;
+        const vf8 rx = tw * ix + tx * iw + ty * iz - tz * iy;
+        const vf8 ry = tw * iy + ty * iw + tz * ix - tx * iz;
+        const vf8 rz = tw * iz + tz * iw + tx * iy - ty * ix;
+        const vf8 d0 = rx * nrm[0] + ry * nrm[1] + rz * nrm[2];
+        const vf8 d1 = rx * nrm[3] + ry * nrm[4] + rz * nrm[5];
+        const vf8 d2 = rx * nrm[6] + ry * nrm[7] + rz * nrm[8];
+        const vf8 d3 = rx * nrm[9] + ry * nrm[10] + rz * nrm[11];
+        const vi8 in = (d0 >= 0.f) & (d1 <= 0.f) & (d2 <= 0.f) & (d3 >= 0.f);
+        for (int l = 0; l < m; ++l)
+            if (in[l]) {
+                kept[3 * (size_t)nk] = rx[l];
+                kept[3 * (size_t)nk + 1] = ry[l];
+                kept[3 * (size_t)nk + 2] = rz[l];
+                ++nk;
+            }
+    }
+    return nk;
+}
+}  // namespace
+
 void VelocityEstimator::estimate(const MapConst &mc, const FrameConst &fc, const float *planes0, const float *pts, int n,
                                  int model, std::vector<float> &out) {
-    // rotated boundary planes and the in-view rotated cloud, same arithmetic as the device (dsp_dynamic.h:226-257)
-    const int np = mc.Nh + mc.Nv + 2;
-    std::vector<float> planes(3 * (size_t)np);
-    for (int i = 0; i < np; ++i) dsp_rotate(planes0 + 3 * i, fc.q, fc.qi, &planes[3 * i]);
-    const float *ph = planes.data(), *pv = ph + 3 * (mc.Nh + 1);
-    auto dot = [](const float *nn, float x, float y, float z) { return x * nn[0] + y * nn[1] + z * nn[2]; };
-    rotated.clear();
-    for (int i = 0; i < n; ++i) {
-        float r[3];
-        dsp_rotate(pts + 3 * (size_t)i, fc.q, fc.qi, r);
-        if (dot(ph, r[0], r[1], r[2]) >= 0.f && dot(ph + 3 * mc.Nh, r[0], r[1], r[2]) <= 0.f && dot(pv, r[0], r[1], r[2]) <= 0.f &&
-            dot(pv + 3 * mc.Nv, r[0], r[1], r[2]) >= 0.f)
-            rotated.insert(rotated.end(), r, r + 3);
-    }
-    const int nv = (int)rotated.size() / 3;
+    // rotated outer boundary planes and the in-view rotated cloud, same arithmetic as the device (dsp_dynamic.h:226-257)
+    float nrm[12];
+    dsp_rotate(planes0, fc.q, fc.qi, nrm);
+    dsp_rotate(planes0 + 3 * mc.Nh, fc.q, fc.qi, nrm + 3);
+    dsp_rotate(planes0 + 3 * (mc.Nh + 1), fc.q, fc.qi, nrm + 6);
+    dsp_rotate(planes0 + 3 * (mc.Nh + 1 + mc.Nv), fc.q, fc.qi, nrm + 9);
+    rotated.resize(3 * (size_t)n);
+    const int nv = rotate_in_view(pts, n, fc.q, fc.qi, nrm, rotated.data());
     if (nv == 0) return;  // :1379 — the previous cloud is kept
-    out.clear();
+    out.resize(7 * (size_t)nv);  // every in-view point is written at most once
+    size_t no = 0;
+    float *o = out.data();
     auto push = [&](float x, float y, float z, float vx, float vy, float vz, float inten) {
-        const float rec[7] = {x, y, z, vx, vy, vz, inten};
-        out.insert(out.end(), rec, rec + 7);
+        o[no] = x; o[no + 1] = y; o[no + 2] = z; o[no + 3] = vx; o[no + 4] = vy; o[no + 5] = vz; o[no + 6] = inten;
+        no += 7;
     };
     if (model == 1) {  // dsp_static.h:1285-1309
         for (int i = 0; i < nv; ++i) push(rotated[3 * i] + fc.cur[0], rotated[3 * i + 1] + fc.cur[1], rotated[3 * i + 2] + fc.cur[2], 0.f, 0.f, 0.f, 0.f);
         return;
     }
-    std::vector<float> statics, nonground;  // xyz triples, world frame (:1387-1398)
-    for (int i = 0; i < nv; ++i) {
-        float x = rotated[3 * i] + fc.cur[0], y = rotated[3 * i + 1] + fc.cur[1], z = rotated[3 * i + 2] + fc.cur[2];
-        std::vector<float> &dst = (z > filter_res) ? nonground : statics;
-        dst.push_back(x); dst.push_back(y); dst.push_back(z);
+    // ground / non-ground split, xyz triples in the world frame (:1387-1398).  Both destinations are written and only
+    // one cursor advances: the side a point falls on is data-dependent, a branch here mispredicts
+    statics.resize(3 * (size_t)nv + 3);
+    nonground.resize(3 * (size_t)nv + 3);
+    {
+        float *sp = statics.data(), *gp = nonground.data();
+        const float cx = fc.cur[0], cy = fc.cur[1], cz = fc.cur[2];
+        for (int i = 0; i < nv; ++i) {
+            const float x = rotated[3 * i] + cx, y = rotated[3 * i + 1] + cy, z = rotated[3 * i + 2] + cz;
+            sp[0] = x; sp[1] = y; sp[2] = z;
+            gp[0] = x; gp[1] = y; gp[2] = z;
+            const int ng = z > filter_res;
+            gp += 3 * ng;
+            sp += 3 * (1 - ng);
+        }
+        const size_t ns = sp - statics.data(), ngr = gp - nonground.data();
+        statics.resize(ns);
+        nonground.resize(ngr);
+        statics.reserve(3 * (size_t)nv);  // clusters reclassified as static are appended below
     }
     std::vector<ClusterFeature> cur;
     if (!nonground.empty()) {
@@ -257,5 +500,6 @@ void VelocityEstimator::estimate(const MapConst &mc, const FrameConst &fc, const
         }
     }
     for (size_t i = 0; i < statics.size() / 3; ++i) push(statics[3 * i], statics[3 * i + 1], statics[3 * i + 2], 0.f, 0.f, 0.f, 0.f);  // :1529-1540
+    out.resize(no);
     last = cur;  // :1542 (only reached when non-ground points exist in the reference too? no: assigned unconditionally)
 }

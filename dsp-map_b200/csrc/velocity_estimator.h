@@ -21,6 +21,7 @@ struct VelocityEstimator {
     u64 seed = 0, draws = 0;   // helper uniform stream (cluster colours, :1422)
     std::vector<ClusterFeature> last;
     std::vector<float> rotated;  // scratch: in-FOV rotated points (cloud_in_current_view_rotated, :130)
+    std::vector<float> statics, nonground;  // scratch: world-frame xyz triples of the ground / non-ground split
 
     void reset(u64 s) { seed = s ^ 0xA5A5A5A5DEADBEEFull; draws = 0; last.clear(); }
     float uniform(float lo, float hi);
@@ -32,5 +33,8 @@ struct VelocityEstimator {
 // Euclidean clustering: connected components of "squared distance <= tol^2", sizes in [min_size, max_size], member
 // indices ascending, clusters by size descending (ties: smallest member index first).
 void euclidean_clusters(const float *xyz, int n, float tol, int min_size, int max_size, std::vector<std::vector<int>> &out);
+// path: 0 = automatic (dense grid when the bounding box allows, else hash grid), 1 = hash grid, 2 = dense grid; false when
+// the requested path cannot take the cloud.  Both paths return the same clusters.
+bool euclidean_clusters_path(const float *xyz, int n, float tol, int min_size, int max_size, int path, std::vector<std::vector<int>> &out);
 // Minimum-cost assignment of an R x C cost matrix padded to square with its maximum; assign[r] = column or -1.
 void hungarian(const std::vector<float> &cost, int R, int C, std::vector<int> &assign);

@@ -95,6 +95,7 @@ def load_library():
         "dspmap_estimator_create": (vp, [C.POINTER(Config), f]),
         "dspmap_estimator_destroy": (None, [vp]),
         "dspmap_estimator_estimate": (i, [vp, i, fp, f, f, f, f, f, f, f, f, fp, i]),
+        "dspmap_euclidean_clusters": (i, [fp, i, f, i, i, i, ip]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)  # AttributeError here = the library does not export what include/dspmap_b200.h declares
@@ -113,7 +114,7 @@ EXPORTED_SYMBOLS = [
     "dspmap_dims", "dspmap_dump_particles", "dspmap_load_particles", "dspmap_dump_voxel_objects",
     "dspmap_dump_observations", "dspmap_dump_pyramid_lists", "dspmap_cursors", "dspmap_set_cursors", "dspmap_counters",
     "dspmap_set_stage_limit", "dspmap_set_last_pose", "dspmap_set_stream", "dspmap_synchronize", "dspmap_profile_enable", "dspmap_profile_read",
-    "dspmap_estimator_create", "dspmap_estimator_destroy", "dspmap_estimator_estimate",
+    "dspmap_estimator_create", "dspmap_estimator_destroy", "dspmap_estimator_estimate", "dspmap_euclidean_clusters",
     "dspmap_shard_config", "dspmap_shard_gather_records", "dspmap_shard_phase",
 ]
 
@@ -387,6 +388,16 @@ class VelocityEstimator:
             self.lib.dspmap_estimator_destroy(self.h)
         except Exception:
             pass
+
+
+def euclidean_clusters(xyz, tolerance, min_size=1, max_size=1 << 30, path=0):
+    """The estimator's clustering on its own: (cluster count, int32 label per point, -1 = not in a kept cluster)."""
+    xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+    labels = np.full(len(xyz), -1, np.int32)
+    n = load_library().dspmap_euclidean_clusters(_fp(xyz), len(xyz), float(tolerance), int(min_size), int(max_size), int(path), _ip(labels))
+    if n < 0:
+        raise DSPMapError("dspmap_euclidean_clusters: path %d cannot take this cloud (%d)" % (path, n))
+    return n, labels
 
 
 def bytes_per_update(counters, V, T, M):

@@ -193,6 +193,12 @@ void dspmap_estimator_destroy(dspmap_estimator *e);
 int dspmap_estimator_estimate(dspmap_estimator *e, int n, const float *pts, float px, float py, float pz, float dt,
                               float qw, float qx, float qy, float qz, float *out, int cap);
 
+/* The estimator's Euclidean clustering on its own (stand-in for pcl::EuclideanClusterExtraction as the side thread uses
+ * it, dsp_dynamic.h:1407-1417): labels[i] = index of point i's cluster in the output order (size descending, ties by
+ * smallest member index), or -1 when its component is outside [min_size, max_size].  path: 0 = automatic, 1 = hash
+ * grid, 2 = dense grid (fails with DSPMAP_E_CAPACITY when the bounding box is too large).  Returns the cluster count. */
+int dspmap_euclidean_clusters(const float *xyz, int n, float tolerance, int min_size, int max_size, int path, int *labels);
+
 #ifdef __cplusplus
 }
 #endif

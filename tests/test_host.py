@@ -52,7 +52,7 @@ def test_derived_sizes_match_reference_arithmetic(name):
         assert (r.V, r.S, r.P, r.L, r.T) == (d["V"], d["S"], d["P"], d["L"], d["T"])
 
 
-@pytest.mark.parametrize("name,frames", [("tiny_dyn", 10), ("tiny_static", 3), ("cfg1", 3), ("ref_default", 3)])
+@pytest.mark.parametrize("name,frames", [("tiny_dyn", 10), ("tiny_static", 3), ("cfg1", 3), ("ref_default", 3), ("cfg2", 3)])
 def test_host_velocity_estimator_equals_reference_side_thread(name, frames):
     if not refmap.available(name):
         pytest.skip("oracle/_ref not built")
@@ -69,6 +69,55 @@ def test_host_velocity_estimator_equals_reference_side_thread(name, frames):
         dyn += int((a[:, 6] > 0.01).sum())
     if name == "tiny_dyn":
         assert dyn > 0  # the stream really exercises clustering + matching
+
+
+def _brute_force_clusters(xyz, tol, min_size, max_size):
+    """O(n^2) connected components of 'distance <= tol' in fp32, PCL's output order (size descending, then smallest member)."""
+    n = len(xyz)
+    d = xyz[:, None, :] - xyz[None, :, :]
+    d2 = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]   # the estimator's fp32 expression
+    adj = d2 <= np.float32(tol) * np.float32(tol)
+    label = -np.ones(n, np.int64)
+    comps = []
+    for s in range(n):
+        if label[s] >= 0:
+            continue
+        stack, members = [s], []
+        label[s] = len(comps)
+        while stack:
+            i = stack.pop()
+            members.append(i)
+            for j in np.nonzero(adj[i] & (label < 0))[0]:
+                label[j] = len(comps)
+                stack.append(j)
+        comps.append(sorted(members))
+    kept = [c for c in comps if min_size <= len(c) <= max_size]
+    kept.sort(key=lambda c: (-len(c), c[0]))
+    out = -np.ones(n, np.int32)
+    for k, c in enumerate(kept):
+        out[c] = k
+    return len(kept), out
+
+
+@pytest.mark.parametrize("seed,n,spread", [(1, 600, 1.0), (2, 1500, 3.0), (3, 900, 0.4), (4, 5, 0.1), (5, 1, 0.1)])
+def test_clustering_paths_agree_with_brute_force(seed, n, spread):
+    rng = np.random.default_rng(seed)
+    centres = rng.uniform(-spread, spread, (12, 3)).astype(np.float32)
+    xyz = (centres[rng.integers(0, 12, n)] + rng.normal(0, 0.12, (n, 3))).astype(np.float32)
+    xyz[: n // 4] = rng.uniform(-spread - 1, spread + 1, (n // 4, 3)).astype(np.float32)      # scattered outliers
+    tol = 0.2
+    want = _brute_force_clusters(xyz, tol, 5, 400)
+    for path in (1, 2, 0):
+        got = dm.euclidean_clusters(xyz, tol, 5, 400, path=path)
+        assert got[0] == want[0] and np.array_equal(got[1], want[1]), "path %d" % path
+
+
+def test_clustering_falls_back_to_the_hash_grid_for_huge_extents():
+    xyz = np.array([[0, 0, 0], [0.05, 0, 0], [1e6, 1e6, 1e6], [1e6 + 0.05, 1e6, 1e6], [np.nan, 0, 0]], np.float32)[:4]
+    with pytest.raises(dm.DSPMapError):
+        dm.euclidean_clusters(xyz, 0.2, 1, 10, path=2)
+    n, labels = dm.euclidean_clusters(xyz, 0.2, 1, 10, path=0)
+    assert n == 2 and list(labels) == [0, 0, 1, 1]
 
 
 def test_estimator_keeps_previous_cloud_when_nothing_in_view():
