@@ -20,7 +20,7 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
 
 
 def sources():
-    return [os.path.join(SRC, f) for f in ("dspmap.cu", "velocity_estimator.cpp")]
+    return [os.path.join(SRC, f) for f in ("dspmap.cu", "prefilter.cu", "velocity_estimator.cpp")]
 
 
 def stale():

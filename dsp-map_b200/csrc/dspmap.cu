@@ -79,6 +79,18 @@ struct dspmap {
     int *d_blockcnt = nullptr, *d_blockoff = nullptr, *d_count = nullptr;
     float *d_xyz = nullptr, *d_future = nullptr;
     int occ_blocks = 0;
+    int occ_guess = 4096;  // occupied voxels copied along with the count (twice the last count): one round trip, not two
+    // pipelined reader (dspmap_get_occupancy_async): two result slots, copies on their own stream
+    struct ReaderSlot {
+        float *d_xyz = nullptr, *d_future = nullptr, *h_xyz = nullptr, *h_future = nullptr;
+        int *d_count = nullptr, *h_count = nullptr;
+        cudaEvent_t done = nullptr;
+        int copied = 0;
+        bool with_future = false, pending = false;
+    } rslot[2];
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_reader = nullptr;
+    int next_slot = 0;
     // ordered prediction noise (dsp_dynamic.h:653-659) stays armed while particles with vz != 0 may exist:
     // constructor-seeded particles until their first prediction, or an injected state that contains such particles
     bool vz_mode = false;
@@ -658,6 +670,14 @@ void dspmap_destroy(dspmap *m) {
     if (m->ev_fork) cudaEventDestroy(m->ev_fork);
     if (m->ev_join) cudaEventDestroy(m->ev_join);
     if (m->ev_state) cudaEventDestroy(m->ev_state);
+    for (auto &s : m->rslot) {
+        if (s.done) cudaEventDestroy(s.done);
+        if (s.h_xyz) cudaFreeHost(s.h_xyz);
+        if (s.h_future) cudaFreeHost(s.h_future);
+        if (s.h_count) cudaFreeHost(s.h_count);
+    }
+    if (m->ev_reader) cudaEventDestroy(m->ev_reader);
+    if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
     if (m->own_stream) cudaStreamDestroy(m->own_stream);
     if (m->side) cudaStreamDestroy(m->side);
     delete m;
@@ -923,6 +943,9 @@ int dspmap_get_occupancy(dspmap *m, float thr, float *xyz_out, int cap, int *n_o
     int rc = dspmap_get_occupancy_device(m, thr, m->d_xyz, mc.V, m->d_count, future ? m->d_future : nullptr);
     if (rc != DSPMAP_OK) return rc;
     CK(cudaMemcpyAsync(m->h_count, m->d_count, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    // the occupied-voxel list travels with its count: as many records as the last frames suggest, the rest (rare) after
+    const int guess = xyz_out ? std::min(std::min(m->occ_guess, cap), mc.V) : 0;
+    if (guess > 0) CK(cudaMemcpyAsync(m->h_xyz, m->d_xyz, sizeof(float) * 3 * (size_t)guess, cudaMemcpyDeviceToHost, m->stream));
     const size_t fbytes = sizeof(float) * (size_t)mc.V * mc.T;
     const bool direct = future && m->pinned_user && (char *)future >= (char *)m->pinned_user &&
                         (char *)future + fbytes <= (char *)m->pinned_user + m->pinned_bytes;
@@ -931,12 +954,73 @@ int dspmap_get_occupancy(dspmap *m, float thr, float *xyz_out, int cap, int *n_o
     int n = *m->h_count;
     if (n_out) *n_out = n;
     int ncopy = std::min(n, cap);
+    m->occ_guess = std::max(4096, 2 * n);
     if (xyz_out && ncopy > 0) {
-        CK(cudaMemcpyAsync(m->h_xyz, m->d_xyz, sizeof(float) * 3 * (size_t)ncopy, cudaMemcpyDeviceToHost, m->stream));
-        CK(cudaStreamSynchronize(m->stream));
+        if (ncopy > guess) {
+            CK(cudaMemcpyAsync(m->h_xyz + 3 * (size_t)guess, m->d_xyz + 3 * (size_t)guess, sizeof(float) * 3 * (size_t)(ncopy - guess),
+                               cudaMemcpyDeviceToHost, m->stream));
+            CK(cudaStreamSynchronize(m->stream));
+        }
         memcpy(xyz_out, m->h_xyz, sizeof(float) * 3 * (size_t)ncopy);
     }
     if (future && !direct) memcpy(future, m->h_future, fbytes);
+    if (m->profile) prof_collect(m);
+    return DSPMAP_OK;
+}
+// Pipelined reader: the reader kernels run on the map's stream, the device-to-host copies on a second stream, so they
+// overlap the next update.  Two result slots alternate; a slot's host pointers stay valid until it is reused.
+int dspmap_get_occupancy_async(dspmap *m, float thr, int with_future, int *ticket) {
+    if (!m || !ticket) return DSPMAP_E_BAD_ARG;
+    CK(cudaSetDevice(m->cfg.device));
+    const MapConst &mc = m->mc;
+    const size_t fcount = (size_t)mc.V * std::max(mc.T, 1);
+    if (!m->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&m->ev_reader, cudaEventDisableTiming));
+        for (auto &s : m->rslot) {
+            if (dalloc(m, &s.d_xyz, (size_t)mc.V * 3, false) != DSPMAP_OK || dalloc(m, &s.d_future, fcount, false) != DSPMAP_OK ||
+                dalloc(m, &s.d_count, 1) != DSPMAP_OK)
+                return DSPMAP_E_CUDA;
+            CK(cudaMallocHost(&s.h_xyz, sizeof(float) * 3 * (size_t)mc.V));
+            CK(cudaMallocHost(&s.h_future, sizeof(float) * fcount));
+            CK(cudaMallocHost(&s.h_count, sizeof(int)));
+            CK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+        }
+    }
+    const int k = m->next_slot;
+    m->next_slot ^= 1;
+    auto &s = m->rslot[k];
+    if (s.pending) CK(cudaStreamWaitEvent(m->stream, s.done, 0));  // the slot's previous copies must have left the device buffers
+    int rc = dspmap_get_occupancy_device(m, thr, s.d_xyz, mc.V, s.d_count, with_future ? s.d_future : nullptr);
+    if (rc != DSPMAP_OK) return rc;
+    CK(cudaEventRecord(m->ev_reader, m->stream));
+    CK(cudaStreamWaitEvent(m->copy_stream, m->ev_reader, 0));
+    s.copied = std::min(m->occ_guess, mc.V);
+    s.with_future = with_future != 0;
+    CK(cudaMemcpyAsync(s.h_count, s.d_count, sizeof(int), cudaMemcpyDeviceToHost, m->copy_stream));
+    CK(cudaMemcpyAsync(s.h_xyz, s.d_xyz, sizeof(float) * 3 * (size_t)s.copied, cudaMemcpyDeviceToHost, m->copy_stream));
+    if (with_future) CK(cudaMemcpyAsync(s.h_future, s.d_future, sizeof(float) * (size_t)mc.V * mc.T, cudaMemcpyDeviceToHost, m->copy_stream));
+    CK(cudaEventRecord(s.done, m->copy_stream));
+    s.pending = true;
+    *ticket = k;
+    return DSPMAP_OK;
+}
+int dspmap_wait_occupancy(dspmap *m, int ticket, const float **xyz, int *n_out, const float **future) {
+    if (!m || ticket < 0 || ticket > 1 || !m->rslot[ticket].pending) { g_err = "no such pending reader ticket"; return DSPMAP_E_BAD_ARG; }
+    CK(cudaSetDevice(m->cfg.device));
+    auto &s = m->rslot[ticket];
+    CK(cudaEventSynchronize(s.done));
+    const int n = *s.h_count;
+    if (n > s.copied) {  // more occupied voxels than the speculative copy carried
+        CK(cudaMemcpyAsync(s.h_xyz + 3 * (size_t)s.copied, s.d_xyz + 3 * (size_t)s.copied, sizeof(float) * 3 * (size_t)(n - s.copied),
+                           cudaMemcpyDeviceToHost, m->copy_stream));
+        CK(cudaStreamSynchronize(m->copy_stream));
+        s.copied = n;
+    }
+    m->occ_guess = std::max(4096, 2 * n);
+    if (n_out) *n_out = n;
+    if (xyz) *xyz = s.h_xyz;
+    if (future) *future = s.with_future ? s.h_future : nullptr;
     if (m->profile) prof_collect(m);
     return DSPMAP_OK;
 }

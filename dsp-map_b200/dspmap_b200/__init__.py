@@ -68,6 +68,8 @@ def load_library():
         "dspmap_set_voxel_filter_resolution": (i, [vp, f]),
         "dspmap_get_occupancy": (i, [vp, f, fp, i, ip, fp]),
         "dspmap_get_occupancy_device": (i, [vp, f, vp, i, vp, vp]),
+        "dspmap_get_occupancy_async": (i, [vp, f, i, ip]),
+        "dspmap_wait_occupancy": (i, [vp, i, C.POINTER(fp), ip, C.POINTER(fp)]),
         "dspmap_clear_prediction": (i, [vp]),
         "dspmap_pin_host_buffer": (i, [vp, vp, C.c_size_t]),
         "dspmap_get_tagged_cloud": (i, [vp, fp, i]),
@@ -96,6 +98,14 @@ def load_library():
         "dspmap_estimator_destroy": (None, [vp]),
         "dspmap_estimator_estimate": (i, [vp, i, fp, f, f, f, f, f, f, f, f, fp, i]),
         "dspmap_euclidean_clusters": (i, [fp, i, f, i, i, i, ip]),
+        "dspmap_prefilter_create": (i, [i, i, i, C.c_longlong, C.POINTER(vp)]),
+        "dspmap_prefilter_destroy": (None, [vp]),
+        "dspmap_prefilter_set_stream": (i, [vp, vp]),
+        "dspmap_prefilter_last_error": (C.c_char_p, []),
+        "dspmap_prefilter_launches": (C.c_longlong, [vp]),
+        "dspmap_prefilter_run": (i, [vp, i, i, fp, f, fp, fp, fp, i, ip]),
+        "dspmap_prefilter_run_device": (i, [vp, i, i, vp, f, fp, fp, vp, i, vp]),
+        "dspmap_update_raw": (i, [vp, vp, i, i, fp, f, fp, fp, f, f, f, C.c_double, f, f, f, f, ip]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)  # AttributeError here = the library does not export what include/dspmap_b200.h declares
@@ -110,11 +120,14 @@ EXPORTED_SYMBOLS = [
     "dspmap_update_tagged", "dspmap_update_device", "dspmap_set_prediction_variance", "dspmap_set_observation_stddev",
     "dspmap_set_newborn_weight", "dspmap_set_newborn_number", "dspmap_set_particle_record_flag",
     "dspmap_set_voxel_filter_resolution", "dspmap_get_occupancy", "dspmap_get_occupancy_device",
+    "dspmap_get_occupancy_async", "dspmap_wait_occupancy",
     "dspmap_clear_prediction", "dspmap_pin_host_buffer", "dspmap_get_tagged_cloud", "dspmap_voxel_center", "dspmap_voxel_index", "dspmap_uniform",
     "dspmap_dims", "dspmap_dump_particles", "dspmap_load_particles", "dspmap_dump_voxel_objects",
     "dspmap_dump_observations", "dspmap_dump_pyramid_lists", "dspmap_cursors", "dspmap_set_cursors", "dspmap_counters",
     "dspmap_set_stage_limit", "dspmap_set_last_pose", "dspmap_set_stream", "dspmap_synchronize", "dspmap_profile_enable", "dspmap_profile_read",
     "dspmap_estimator_create", "dspmap_estimator_destroy", "dspmap_estimator_estimate", "dspmap_euclidean_clusters",
+    "dspmap_prefilter_create", "dspmap_prefilter_destroy", "dspmap_prefilter_set_stream", "dspmap_prefilter_last_error",
+    "dspmap_prefilter_launches", "dspmap_prefilter_run", "dspmap_prefilter_run_device", "dspmap_update_raw",
     "dspmap_shard_config", "dspmap_shard_gather_records", "dspmap_shard_phase",
 ]
 
@@ -362,6 +375,22 @@ class DSPMap:
                                                                 C.c_void_p(d_count), C.c_void_p(d_future)))
 
 
+    def get_occupancy_async(self, threshold, with_future=True):
+        """Pipelined reader: enqueues the reader kernels + the copies on a second stream; returns a ticket."""
+        t = C.c_int32(-1)
+        self._check(self.lib.dspmap_get_occupancy_async(self.h, threshold, 1 if with_future else 0, C.byref(t)))
+        return t.value
+
+    def wait_occupancy(self, ticket):
+        """(count, (count, 3) voxel centres, (V, T) future status or None): zero-copy views of the library's page-locked
+        slot, valid until the second get_occupancy_async call after the one that returned `ticket`."""
+        xyz, fut, n = C.POINTER(C.c_float)(), C.POINTER(C.c_float)(), C.c_int32(0)
+        self._check(self.lib.dspmap_wait_occupancy(self.h, ticket, C.byref(xyz), C.byref(n), C.byref(fut)))
+        a = np.ctypeslib.as_array(xyz, shape=(max(n.value, 1), 3))[:n.value]
+        f_ = np.ctypeslib.as_array(fut, shape=(self.V, self.T)) if fut else None
+        return n.value, a, f_
+
+
 class VelocityEstimator:
     """Host-only velocity estimation (the reference's side thread, dsp_dynamic.h:1377-1544); needs no GPU."""
 
@@ -388,6 +417,69 @@ class VelocityEstimator:
             self.lib.dspmap_estimator_destroy(self.h)
         except Exception:
             pass
+
+
+class Prefilter:
+    """The application's preprocessing (map_sim_example.cpp:305-336: VoxelGrid, axis swap, crop, cut) on the GPU."""
+
+    def __init__(self, max_raw_points=640 * 480, max_stride=4, max_out_points=5000, max_leaves=0, device=0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.dspmap_prefilter_create(device, max_raw_points * max_stride, max_out_points, max_leaves, C.byref(h))
+        if rc != OK:
+            raise DSPMapError("dspmap_prefilter_create failed (%d): %s" % (rc, self.lib.dspmap_prefilter_last_error().decode()))
+        self.h, self.cap = h, max_out_points
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.dspmap_prefilter_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc < 0:
+            raise DSPMapError("prefilter call failed (%d): %s" % (rc, self.lib.dspmap_prefilter_last_error().decode()))
+        return rc
+
+    def set_stream(self, cuda_stream):
+        self._check(self.lib.dspmap_prefilter_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    def launches(self):
+        return int(self.lib.dspmap_prefilter_launches(self.h))
+
+    def run(self, pts, leaf, range_min, range_max, cap=None):
+        """pts (n, stride) float32 host array, camera frame -> (m, 3) float32 cloud for DSPMap.update."""
+        pts = np.ascontiguousarray(pts, np.float32)
+        pts = pts.reshape(-1, 3) if pts.ndim == 1 else pts
+        cap = self.cap if cap is None else min(cap, self.cap)
+        lo, hi = np.ascontiguousarray(range_min, np.float32), np.ascontiguousarray(range_max, np.float32)
+        out, n = np.zeros((cap, 3), np.float32), C.c_int32(0)
+        self._check(self.lib.dspmap_prefilter_run(self.h, pts.shape[0], pts.shape[1], _fp(pts), float(leaf), _fp(lo), _fp(hi),
+                                                  _fp(out), cap, C.byref(n)))
+        return out[:n.value]
+
+    def run_device(self, n, stride, d_pts, leaf, range_min, range_max, d_out, cap, d_n_out):
+        lo, hi = np.ascontiguousarray(range_min, np.float32), np.ascontiguousarray(range_max, np.float32)
+        return self._check(self.lib.dspmap_prefilter_run_device(self.h, n, stride, C.c_void_p(d_pts), float(leaf), _fp(lo), _fp(hi),
+                                                                C.c_void_p(d_out), cap, C.c_void_p(d_n_out)))
+
+    def update_raw(self, m, pts, leaf, range_min, range_max, pos, t, quat):
+        """dspmap_update_raw: preprocessing + DSPMap.update in one call. Returns (update's return code, filtered count)."""
+        pts = np.ascontiguousarray(pts, np.float32)
+        lo, hi = np.ascontiguousarray(range_min, np.float32), np.ascontiguousarray(range_max, np.float32)
+        nf = C.c_int32(0)
+        rc = self.lib.dspmap_update_raw(m.h, self.h, pts.shape[0], pts.shape[1], _fp(pts), float(leaf), _fp(lo), _fp(hi),
+                                        float(pos[0]), float(pos[1]), float(pos[2]), float(t), float(quat[0]), float(quat[1]),
+                                        float(quat[2]), float(quat[3]), C.byref(nf))
+        if rc < 0:
+            raise DSPMapError("dspmap_update_raw failed (%d): %s / %s" % (rc, self.lib.dspmap_prefilter_last_error().decode(),
+                                                                         self.lib.dspmap_last_error().decode()))
+        return rc, nf.value
 
 
 def euclidean_clusters(xyz, tolerance, min_size=1, max_size=1 << 30, path=0):

@@ -103,6 +103,34 @@ def make_stream(cfg, seed=1, frames=100, points=None, dt=0.1, speed=0.2, n_boxes
     return dict(points=out_p, n=np.full(frames, M, np.int32), pos=pos, quat=quat, t=ts)
 
 
+def make_depth_cloud(width=640, height=480, seed=1, hfov_deg=90.0, max_range=9.0, invalid=0.08, stride=3):
+    """A raw depth-camera cloud as the application receives it (map_sim_example.cpp:305-309): one point per pixel in the
+    CAMERA frame (x right, y down, z forward), raster order, invalid pixels NaN.  Scene: floor, back wall, a few boxes.
+    Returns (height*width, stride) float32; columns past 2 are padding, like the 16-byte points of a PointCloud2."""
+    rng = np.random.default_rng(seed)
+    f = 0.5 * width / np.tan(np.radians(hfov_deg) / 2)
+    u, v = np.meshgrid(np.arange(width, dtype=np.float64) - width / 2 + 0.5, np.arange(height, dtype=np.float64) - height / 2 + 0.5)
+    dx, dy = u / f, v / f                                  # ray direction (dx, dy, 1)
+    depth = np.full(u.shape, max_range * 1.2)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        floor = np.where(dy > 1e-6, 1.0 / dy, np.inf)       # floor 1 m below the camera (y down)
+    depth = np.minimum(depth, floor)
+    depth = np.minimum(depth, 6.0 + 0.3 * np.sin(3 * dx))  # gently curved back wall
+    for _ in range(5):                                     # boxes: axis-aligned slabs in front of the wall
+        cx, cy, cz = rng.uniform(-2.5, 2.5), rng.uniform(-0.8, 0.9), rng.uniform(1.0, 5.0)
+        hx, hy = rng.uniform(0.15, 0.6), rng.uniform(0.2, 0.9)
+        hit = (np.abs(dx * cz - cx) < hx) & (np.abs(dy * cz - cy) < hy)
+        depth = np.where(hit, np.minimum(depth, cz), depth)
+    depth = depth + rng.normal(0, 0.004, depth.shape) * depth
+    bad = (depth > max_range) | (rng.random(depth.shape) < invalid)
+    pts = np.zeros((height * width, stride), np.float32)
+    pts[:, 0] = (dx * depth).ravel()
+    pts[:, 1] = (dy * depth).ravel()
+    pts[:, 2] = depth.ravel()
+    pts[bad.ravel(), :3] = np.nan
+    return pts
+
+
 def write_stream(path, stream, frames=None):
     """Binary stream file read by dsp-map_b200/tools/dspmap_replay.cpp and tests/dropin_main.cpp."""
     import struct

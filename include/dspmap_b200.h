@@ -105,6 +105,15 @@ int dspmap_get_occupancy(dspmap *m, float threshold, float *xyz_out, int cap, in
 /* Device-resident variant: d_xyz (cap*3 floats), d_count (1 int), d_future (V*T floats or NULL) are device
  * pointers; only enqueued. */
 int dspmap_get_occupancy_device(dspmap *m, float threshold, float *d_xyz, int cap, int *d_count, float *d_future);
+/* Pipelined reader (zero-copy readers): same results and the same side effect as dspmap_get_occupancy with
+ * xyz capacity V, but the call only enqueues — the reader kernels on the map's stream, the device-to-host copies on a second
+ * stream into page-locked buffers owned by the library — and returns a ticket (0 or 1; two result slots alternate).
+ * dspmap_wait_occupancy blocks until that ticket's copies have landed and hands out HOST pointers into the slot: *n voxel
+ * centres in xyz, V*T floats in future (NULL if with_future was 0).  They stay valid until the slot is reused, i.e. until the
+ * second dspmap_get_occupancy_async call after this one.  Typical loop: update(k); get_async(k); wait(k-1); consume(k-1) — the
+ * 4 B * V * T copy of frame k-1 overlaps update(k). */
+int dspmap_get_occupancy_async(dspmap *m, float threshold, int with_future, int *ticket);
+int dspmap_wait_occupancy(dspmap *m, int ticket, const float **xyz, int *n, const float **future);
 /* Optional: page-locks a caller-owned output buffer (e.g. the application's static future_status array) so that
  * dspmap_get_occupancy can DMA straight into it instead of staging + memcpy. The buffer must outlive the handle or be
  * released with bytes == 0. */
@@ -192,6 +201,32 @@ dspmap_estimator *dspmap_estimator_create(const dspmap_config *cfg, float voxel_
 void dspmap_estimator_destroy(dspmap_estimator *e);
 int dspmap_estimator_estimate(dspmap_estimator *e, int n, const float *pts, float px, float py, float pz, float dt,
                               float qw, float qx, float qy, float qz, float *out, int cap);
+
+/* Application-side preprocessing on the GPU: what src/map_sim_example.cpp:305-336 does per depth frame
+ * before DSPMap::update — pcl::VoxelGrid down-sampling with leaf size `leaf` (ex:312-316), the camera -> map axis swap
+ * x = z, y = -x, z = -y (ex:320-322), the open-interval crop to (range_min, range_max) (ex:325) and the cut at `cap`
+ * points (ex:332-334) — so that a raw depth cloud crosses PCIe once.  Leaf membership and output order (ascending PCL leaf
+ * index) are exact; a leaf's centroid is accumulated exactly in 2^-24 m fixed point and rounded once (PCL's own fp32 running
+ * sum follows an unstable sort, i.e. is only defined up to its rounding error; see prefilter.cu).
+ *   max_raw_floats: capacity of the raw staging buffer (points x stride); max_out_points: capacity of the result;
+ *   max_leaves: capacity of the leaf grid over the cloud's bounding box (0 = 2^22; 28 B of HBM each).
+ * dspmap_prefilter_run: HOST pointers; `pts` = n points `stride` floats apart (camera frame, NaN / inf allowed and skipped);
+ * writes *n_out <= cap points to `out`.  DSPMAP_E_CAPACITY when the bounding box needs more than max_leaves leaves.
+ * dspmap_prefilter_run_device: DEVICE pointers, enqueue only; *d_n_out = -1 signals the capacity error.
+ * dspmap_update_raw = dspmap_prefilter_run + dspmap_update on the result (no intermediate copy to caller memory). */
+typedef struct dspmap_prefilter dspmap_prefilter;
+int dspmap_prefilter_create(int device, int max_raw_floats, int max_out_points, long long max_leaves, dspmap_prefilter **out);
+void dspmap_prefilter_destroy(dspmap_prefilter *p);
+int dspmap_prefilter_set_stream(dspmap_prefilter *p, void *cuda_stream);
+const char *dspmap_prefilter_last_error(void);
+long long dspmap_prefilter_launches(const dspmap_prefilter *p);
+int dspmap_prefilter_run(dspmap_prefilter *p, int n, int stride, const float *pts, float leaf, const float *range_min,
+                         const float *range_max, float *out, int cap, int *n_out);
+int dspmap_prefilter_run_device(dspmap_prefilter *p, int n, int stride, const float *d_pts, float leaf, const float *range_min,
+                                const float *range_max, float *d_out, int cap, int *d_n_out);
+int dspmap_update_raw(dspmap *m, dspmap_prefilter *p, int n, int stride, const float *raw, float leaf, const float *range_min,
+                      const float *range_max, float px, float py, float pz, double t, float qw, float qx, float qy, float qz,
+                      int *n_filtered);
 
 /* The estimator's Euclidean clustering on its own (stand-in for pcl::EuclideanClusterExtraction as the side thread uses
  * it, dsp_dynamic.h:1407-1417): labels[i] = index of point i's cluster in the output order (size descending, ties by

@@ -154,6 +154,42 @@ def test_readers_threshold_variants_clear_and_state_round_trip():
     g2.close()
 
 
+@pytest.mark.parametrize("name,frames", [("tiny_dyn", 8), ("cfg2", 6)])
+def test_pipelined_reader_equals_blocking_reader(name, frames):
+    """dspmap_get_occupancy_async / dspmap_wait_occupancy (copies overlapped with the next update) return what the
+    reference-facing blocking reader returns, frame for frame, including the zeroing of the future columns."""
+    cfg = dm.CONFIGS[name]
+    st = make_stream(cfg, seed=4, frames=frames)
+    a, b = gpu_map(name, seed=3), gpu_map(name, seed=3)
+    est = dm.VelocityEstimator(cfg, seed=3)
+    fut = np.zeros((a.V, a.T), np.float32)
+    want, got, ticket = [], [], None
+    for f in range(frames):
+        tc = est.estimate(st["points"][f], st["pos"][f], st["t"][f], st["quat"][f])
+        for m in (a, b):
+            gpu_update(m, st["points"][f], st["pos"][f], st["t"][f], st["quat"][f], tagged=tc)
+        n, xyz, _ = a.getOccupancyMapWithFutureStatus(0.2, fut)
+        want.append((n, xyz.copy(), fut.copy()))
+        prev, ticket = ticket, b.get_occupancy_async(0.2, with_future=(f % 3 != 2))
+        if prev is not None:   # frame f-1's results are collected while frame f's copies are in flight
+            n2, x2, f2 = b.wait_occupancy(prev)
+            got.append((n2, x2.copy(), None if f2 is None else f2.copy()))
+    n2, x2, f2 = b.wait_occupancy(ticket)
+    got.append((n2, x2.copy(), None if f2 is None else f2.copy()))
+    assert len(got) == frames
+    for f, ((n, xyz, fu), (n2, x2, f2)) in enumerate(zip(want, got)):
+        assert n == n2 and same(xyz, x2), "frame %d" % f
+        assert (f2 is None) == (f % 3 == 2)
+        if f2 is not None:
+            # fp32 atomics: identical support, values to rounding (DESIGN.md "Result contract")
+            assert np.array_equal(fu != 0, f2 != 0) and np.allclose(fu, f2, rtol=2e-6, atol=0), "future status, frame %d" % f
+    assert not b.voxel_objects()[:, 4:].any()
+    with pytest.raises(dm.DSPMapError):
+        b.wait_occupancy(5)
+    a.close()
+    b.close()
+
+
 @pytest.mark.parametrize("name,frames", [("cfg2", 30), ("cfg5", 4)])
 def test_full_size_properties(name, frames):
     """BASELINE.json sizes, no oracle in the loop: invariants every reference state satisfies."""

@@ -37,7 +37,7 @@ def test_product_does_not_touch_the_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 src = open(os.path.join(base, f)).read()
-                for pat in (r"import\s+oracle", r"from\s+oracle", r"refmap", r"liboracle", r"oracle/", r"dsp_oracle", r"_ref\b"):
+                for pat in (r"import\s+oracle", r"from\s+oracle", r"refmap", r"liboracle", r"oracle/", r"dsp_oracle", r"prefilter_oracle", r"_ref\b"):
                     assert not re.search(pat, src), "%s uses the oracle (%s)" % (f, pat)
 
 
