@@ -294,7 +294,7 @@ int dspmap_prefilter_create(int device, int max_raw_floats, int max_out_points, 
     PCK(cudaSetDevice(device));
     dspmap_prefilter *p = new dspmap_prefilter();
     p->device = device;
-    p->cap_leaves = max_leaves > 0 ? max_leaves : (1ll << 22);
+    p->cap_leaves = std::min<long long>(max_leaves > 0 ? max_leaves : (1ll << 22), 1ll << 30);  // leaf indices are int32
     p->cap_raw_floats = max_raw_floats;
     p->cap_out = max_out_points;
     p->nblocks = (int)((p->cap_leaves + PF_SCAN_BLOCK - 1) / PF_SCAN_BLOCK);

@@ -62,7 +62,15 @@ def make_stream(cfg, seed=1, frames=100, points=None, dt=0.1, speed=0.2, n_boxes
         q = _quat(0.02 * np.sin(0.7 * t), 0.03 * np.sin(0.4 * t), 0.15 * np.sin(0.2 * t))
         R = _rot(q)
         pts = np.zeros((0, 3))
+        rounds, skip = 0, np.zeros(n_boxes, bool)
         while pts.shape[0] < M:
+            rounds += 1
+            if rounds == 20:   # the sensor has flown into an obstacle (every return is nearer than 0.2 m): see through it
+                cxy = np.stack([bx + bv[:, 0] * t, by + bv[:, 1] * t], 1)
+                skip = np.all(np.abs(cxy - s[:2]) < bs + 0.5, axis=1)
+                pts = np.zeros((0, 3))
+            if rounds > 200:
+                raise RuntimeError("make_stream: frame %d has no valid returns (%d of %d points)" % (f, pts.shape[0], M))
             n = 2 * M
             az = rng.uniform(-hfov, hfov, n)
             ev = rng.uniform(-vfov, vfov, n)
@@ -83,6 +91,8 @@ def make_stream(cfg, seed=1, frames=100, points=None, dt=0.1, speed=0.2, n_boxes
                     ty[(ty <= 0)] = np.inf
                     rng_hit = np.minimum(rng_hit, ty)
                 for k in range(n_boxes):
+                    if skip[k]:
+                        continue
                     c = np.array([bx[k] + bv[k, 0] * t, by[k] + bv[k, 1] * t])
                     lo = np.array([c[0] - bs[k, 0], c[1] - bs[k, 1], 0.0])
                     hi = np.array([c[0] + bs[k, 0], c[1] + bs[k, 1], bh[k]])

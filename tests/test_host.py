@@ -120,6 +120,12 @@ def test_clustering_falls_back_to_the_hash_grid_for_huge_extents():
     assert n == 2 and list(labels) == [0, 0, 1, 1]
 
 
+def test_stream_generator_never_hangs_when_the_sensor_enters_an_obstacle():
+    # bench.py consumes 210 frames of this stream; at frame 160 the sensor flies into a box and every return is < 0.2 m
+    st = make_stream(dm.CONFIGS["cfg2"], seed=1, frames=170, points=2000)
+    assert st["points"].shape == (170, 2000, 3) and np.isfinite(st["points"]).all()
+
+
 def test_estimator_keeps_previous_cloud_when_nothing_in_view():
     cfg = dm.CONFIGS["tiny_dyn"]
     e = dm.VelocityEstimator(cfg, seed=1)
