@@ -88,41 +88,39 @@ struct ScanJob { const int *in; int *out; int *out_capped; int cap; int n; };
 struct ScanJobs { ScanJob j[3]; };
 __global__ void __launch_bounds__(1024) k_scan_small(ScanJobs jobs) {
     __shared__ int wsum[32], wcap[32];
-    __shared__ int carry[2];
     const ScanJob J = jobs.j[blockIdx.x];
     const int n = J.n, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (threadIdx.x == 0) { carry[0] = 0; carry[1] = 0; }
-    __syncthreads();
-    for (int base = 0; base < n; base += 1024) {  // rounds of 1024 consecutive elements: coalesced loads and stores
-        const int i = base + threadIdx.x;
-        const int x = i < n ? J.in[i] : 0, xc = min(x, J.cap);
-        int incl = x, inclc = xc;
-        for (int d = 1; d < 32; d <<= 1) {
-            int t = __shfl_up_sync(FULLMASK, incl, d), tc = __shfl_up_sync(FULLMASK, inclc, d);
-            if (lane >= d) { incl += t; inclc += tc; }
-        }
-        if (lane == 31) { wsum[wid] = incl; wcap[wid] = inclc; }
-        __syncthreads();
-        if (wid == 0) {
-            int y0 = wsum[lane], yc0 = wcap[lane], y = y0, yc = yc0;
-            for (int d = 1; d < 32; d <<= 1) {
-                int t = __shfl_up_sync(FULLMASK, y, d), tc = __shfl_up_sync(FULLMASK, yc, d);
-                if (lane >= d) { y += t; yc += tc; }
-            }
-            wsum[lane] = y - y0;  // exclusive prefix of the warp totals
-            wcap[lane] = yc - yc0;
-        }
-        __syncthreads();
-        const int c0 = carry[0], c1 = carry[1];
-        if (i < n) {
-            J.out[i] = c0 + wsum[wid] + incl - x;
-            if (J.out_capped) J.out_capped[i] = c1 + wcap[wid] + inclc - xc;
-        }
-        __syncthreads();
-        if (threadIdx.x == 1023) { carry[0] = c0 + wsum[wid] + incl; carry[1] = c1 + wcap[wid] + inclc; }
-        __syncthreads();
+    // one pass: every thread owns `per` consecutive elements (the arrays are a few tens of KB and sit in L2 / L1, so the
+    // strided access costs nothing next to the block-wide synchronisations a round-per-1024-elements loop pays)
+    const int per = (n + 1023) >> 10;
+    const int b0 = min(n, threadIdx.x * per), b1 = min(n, b0 + per);
+    int s = 0, sc = 0;
+    for (int i = b0; i < b1; ++i) { const int x = J.in[i]; s += x; sc += min(x, J.cap); }
+    int incl = s, inclc = sc;
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(FULLMASK, incl, d), tc = __shfl_up_sync(FULLMASK, inclc, d);
+        if (lane >= d) { incl += t; inclc += tc; }
     }
-    if (threadIdx.x == 0) { J.out[n] = carry[0]; if (J.out_capped) J.out_capped[n] = carry[1]; }
+    if (lane == 31) { wsum[wid] = incl; wcap[wid] = inclc; }
+    __syncthreads();
+    if (wid == 0) {
+        int y0 = wsum[lane], yc0 = wcap[lane], y = y0, yc = yc0;
+        for (int d = 1; d < 32; d <<= 1) {
+            int t = __shfl_up_sync(FULLMASK, y, d), tc = __shfl_up_sync(FULLMASK, yc, d);
+            if (lane >= d) { y += t; yc += tc; }
+        }
+        wsum[lane] = y - y0;  // exclusive prefix of the warp totals
+        wcap[lane] = yc - yc0;
+    }
+    __syncthreads();
+    int run = wsum[wid] + incl - s, runc = wcap[wid] + inclc - sc;
+    for (int i = b0; i < b1; ++i) {
+        const int x = J.in[i];
+        J.out[i] = run;
+        run += x;
+        if (J.out_capped) { J.out_capped[i] = runc; runc += min(x, J.cap); }
+    }
+    if (threadIdx.x == 1023) { J.out[n] = run; if (J.out_capped) J.out_capped[n] = runc; }
 }
 
 __global__ void k_obs_scatter(MapConst mc, FrameConst fc, DevPtrs dp) {

@@ -71,7 +71,7 @@ def test_gpu_prefilter_reproduces_fixture_and_restatement():
 
 @pytest.mark.gpu
 def test_gpu_prefilter_edge_cases():
-    pf = dm.Prefilter(max_raw_points=4096, max_stride=4, max_out_points=64, max_leaves=1 << 16)
+    pf = dm.Prefilter(max_raw_points=4096, max_stride=4, max_out_points=64, max_leaves=1 << 20)
     assert pf.run(np.zeros((0, 3), np.float32), LEAF, LO, HI).shape == (0, 3)                 # empty cloud
     assert pf.run(np.full((100, 3), np.nan, np.float32), LEAF, LO, HI).shape == (0, 3)        # nothing finite
     one = np.array([[0.5, -0.25, 2.0]], np.float32)
@@ -83,7 +83,7 @@ def test_gpu_prefilter_edge_cases():
     assert same(pf.run(raw, LEAF, LO, HI, cap=10), want[:10])
     assert same(pf.run(raw, LEAF, (0, 0, 0), (3, 3, 3)), po.preprocess(raw, LEAF, (0, 0, 0), (3, 3, 3), 64))
     far = np.array([[0, 0, 1], [500, 500, 500]], np.float32)                                   # bounding box of 1.25e11 leaves
-    assert po.leaf_volume(far, LEAF) > (1 << 16)
+    assert po.leaf_volume(far, LEAF) > (1 << 20) > po.leaf_volume(raw, LEAF)
     with pytest.raises(dm.DSPMapError):
         pf.run(far, LEAF, LO, HI)
     assert same(pf.run(raw, LEAF, LO, HI), want[:64])                                         # and the grid is still clean afterwards
