@@ -97,6 +97,7 @@ struct dspmap {
     int vz_blocks = 0;
     // the recompute kernels (k_ck / k_weight) are launched only while the pair buffer may overflow
     bool fallback_armed = true;
+    bool cz_wide = true;
     FrameConst shard_fc;  // frame scalars carried across the phases of a sharded frame
     int shard_cap_g = 0;
     long long host_u_cur = 0;  // uniform draws consumed on the host while seeding
@@ -170,6 +171,9 @@ void prof_collect(dspmap *m) {
     } while (0)
 
 const int kSMs = 148;
+// the two configurations of the C_z chain kernel (threads, floats per tile, rows per tile)
+const auto k_cz_narrow = &k_cz_chain<128, 4096, 128>;
+const auto k_cz_wide = &k_cz_chain<256, 8192, 128>;
 inline int grid_for(long long n, int block, int max_blocks = kSMs * 8) {
     long long g = (n + block - 1) / block;
     if (g < 1) g = 1;
@@ -309,7 +313,8 @@ int enqueue_frame_a(dspmap *m, const FrameConst &fc, const float *d_pts) {
         LAUNCH(m, FAM_CK, k_pair_prep, grid_for(mc.P, B), B, 0, mc, dp);
         LAUNCH(m, FAM_CK, k_scan_small, 2, 1024, 0, ScanJobs{{ScanJob{dp.pairs, dp.rowbase, nullptr, 0, mc.P}, ScanJob{dp.chunks, dp.chunk_off, nullptr, 0, mc.P}, ScanJob{}}});
         LAUNCH(m, FAM_CK, k_pair_eval, kSMs * 2, EVAL_THREADS, sizeof(float) * (DSP_LUT_HALF + 3 + (EVAL_THREADS / 32) * 32 * TILE_LD), mc, fc, dp, 0);
-        LAUNCH(m, FAM_CK, k_cz_chain, std::min(mc.P, kSMs * 3), CZ_THREADS, sizeof(float) * (2 * (CZ_TILE + 8) + 2 * CZ_JT), mc, fc, dp);
+        if (m->cz_wide) LAUNCH(m, FAM_CK, k_cz_wide, std::min(mc.P, kSMs * 3), 256, sizeof(float) * (2 * (8192 + 8) + 2 * 128), mc, fc, dp);
+        else LAUNCH(m, FAM_CK, k_cz_narrow, std::min(mc.P, kSMs * 6), 128, sizeof(float) * (2 * (4096 + 8) + 2 * 128), mc, fc, dp);
         size_t smem4 = sizeof(float) * (DSP_LUT_HALF + 3 + K4_TERMS) + sizeof(float4) * (256 + mc.OBS);
         if (m->fallback_armed) LAUNCH(m, FAM_CK, k_ck, std::min(mc.P, kSMs * 2), K4_THREADS, smem4, mc, fc, dp);  // returns at once when the pair buffer is used
         if (fc.stage_limit >= 3) {  // the newborn normaliser is one long serial chain: run it beside the weight pass
@@ -629,7 +634,8 @@ int dspmap_create(const dspmap_config *cfg, dspmap **out) {
     CK(cudaFuncSetAttribute(k_pyr_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PYR_SORT_CAP * sizeof(u64))));
     CK(cudaFuncSetAttribute(k_ck, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CK(cudaFuncSetAttribute(k_pair_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-    CK(cudaFuncSetAttribute(k_cz_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    CK(cudaFuncSetAttribute(k_cz_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    m->cz_wide = getenv("DSPMAP_CZ_NARROW") == nullptr;  // experiment switch: DSPMAP_CZ_NARROW selects the 128-thread / 32 KB configuration
     CK(cudaFuncSetAttribute(k_weight, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaStreamSynchronize(m->stream));
     if (gen_tables(m) != DSPMAP_OK) { dspmap_destroy(m); return DSPMAP_E_CUDA; }
@@ -855,7 +861,8 @@ int dspmap_shard_phase(dspmap *m, int phase, int n, const float *d_pts, float px
         LAUNCH(m, FAM_CK, k_scan_small, 2, 1024, 0, ScanJobs{{ScanJob{dp.pairs, dp.rowbase, nullptr, 0, mc.P}, ScanJob{dp.chunks, dp.chunk_off, nullptr, 0, mc.P}, ScanJob{}}});
         LAUNCH(m, FAM_CK, k_shard_zero, kSMs * 2, B, 0, mc, fc, dp, 0);
         LAUNCH(m, FAM_CK, k_pair_eval, kSMs * 2, EVAL_THREADS, sizeof(float) * (DSP_LUT_HALF + 3 + (EVAL_THREADS / 32) * 32 * TILE_LD), mc, fc, dp, 1);
-        LAUNCH(m, FAM_CK, k_cz_chain, std::min(mc.P, kSMs * 3), CZ_THREADS, sizeof(float) * (2 * (CZ_TILE + 8) + 2 * CZ_JT), mc, fc, dp);
+        if (m->cz_wide) LAUNCH(m, FAM_CK, k_cz_wide, std::min(mc.P, kSMs * 3), 256, sizeof(float) * (2 * (8192 + 8) + 2 * 128), mc, fc, dp);
+        else LAUNCH(m, FAM_CK, k_cz_narrow, std::min(mc.P, kSMs * 6), 128, sizeof(float) * (2 * (4096 + 8) + 2 * 128), mc, fc, dp);
     } else if (phase == 3) {
         dp.tagged = d_tagged;
         LAUNCH(m, FAM_WEIGHT, k_shard_zero, kSMs * 2, B, 0, mc, fc, dp, 1);

@@ -497,11 +497,23 @@ __global__ void k_shard_apply_weights(MapConst mc, DevPtrs dp) {
 // ------------------------------------------------------------------------------------------------------------
 __global__ void k_pyr_scatter(DevPtrs dp) {
     const int n = dp.st->n_fov;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        int q = dp.Fq[i];
-        int pos = dp.poff[q] + atomicAdd(&dp.pfill[q], 1);
-        dp.PSkey[pos] = dp.Fkey[i];
-        dp.PSaddr[pos] = dp.Faddr[i];
+    // neighbouring particles mostly fall in the same pyramid: lanes that share one are counted together and their
+    // leader reserves the block of slots with a single atomic (the order inside a segment is fixed by k_pyr_sort)
+    const int lane = threadIdx.x & 31;
+    const int stride = gridDim.x * blockDim.x;
+    for (int i0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < n; i0 += stride) {
+        const int i = i0 + lane;
+        const int q = i < n ? dp.Fq[i] : -1;
+        const unsigned peers = __match_any_sync(FULLMASK, q);
+        const int leader = __ffs(peers) - 1;
+        int base = 0;
+        if (lane == leader && q >= 0) base = atomicAdd(&dp.pfill[q], __popc(peers));
+        base = __shfl_sync(FULLMASK, base, leader);
+        if (q >= 0) {
+            const int pos = dp.poff[q] + base + __popc(peers & ((1u << lane) - 1u));
+            dp.PSkey[pos] = dp.Fkey[i];
+            dp.PSaddr[pos] = dp.Faddr[i];
+        }
     }
 }
 
@@ -782,9 +794,9 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_pair_eval(MapConst mc, FrameCo
 }
 // C_z (dsp_dynamic.h:709-739): a CTA per point pyramid streams the pyramid's contiguous block of G through shared
 // memory (double-buffered cp.async); thread z < np adds its column in list order: one fp32 chain per point.
-#define CZ_THREADS 256
-#define CZ_TILE 8192   // floats per buffer (dynamic shared memory: 2 buffers)
-#define CZ_JT 128
+// Measured on B200 (cfg2): 256 threads with 2 x 32 KB tiles (3 CTAs / SM) 54 us, 128 threads with 2 x 16 KB tiles
+// (6 CTAs / SM, every pyramid resident at once) 64 us — the longer tiles amortise the per-tile barrier better.
+template <int CZ_THREADS, int CZ_TILE, int CZ_JT>
 __global__ void __launch_bounds__(CZ_THREADS) k_cz_chain(MapConst mc, FrameConst fc, DevPtrs dp) {
     extern __shared__ float czsm[];
     float *tile0 = czsm, *tile1 = czsm + CZ_TILE + 8;  // + room for the alignment phase
@@ -917,10 +929,24 @@ __global__ void __launch_bounds__(W2_THREADS) k_weight2(MapConst mc, FrameConst 
                     asm volatile("bar.sync 1, 96;" ::: "memory");  // only the three producer warps
                     const int nfl = nrows * np;
                     const unsigned magic = np > 1 ? 0xffffffffu / (unsigned)np + 1u : 0u;  // exact f / np for f < 65536
-                    for (int f = t96; f < nfl; f += W2_THREADS - 32) {
-                        const int r = np > 1 ? (int)__umulhi((unsigned)f, magic) : f;
-                        const int z = f - r * np;
-                        terms[buf][r * ld + z] = fc.Pd * __ldg(gb + f) / czs[buf][z];
+                    // eight loads in flight per thread before the first division: the tile comes from L2 (or HBM), and a
+                    // load-divide-store loop with one outstanding load per thread is pure latency
+                    for (int f0 = t96; f0 < nfl; f0 += 8 * (W2_THREADS - 32)) {
+                        float g[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int f = f0 + u * (W2_THREADS - 32);
+                            g[u] = f < nfl ? __ldg(gb + f) : 0.f;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int f = f0 + u * (W2_THREADS - 32);
+                            if (f < nfl) {
+                                const int r = np > 1 ? (int)__umulhi((unsigned)f, magic) : f;
+                                const int z = f - r * np;
+                                terms[buf][r * ld + z] = fc.Pd * g[u] / czs[buf][z];
+                            }
+                        }
                     }
                 }
             }
