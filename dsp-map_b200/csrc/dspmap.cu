@@ -9,6 +9,7 @@
 #include <ctime>
 #include <fstream>
 #include <random>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -32,6 +33,7 @@ const char *kFamilyNames[FAM_COUNT] = {"setup", "obs_bin", "enumerate", "predict
 struct ProfSlot {
     cudaEvent_t a, b;
     int fam;
+    const char *kernel;
 };
 
 }  // namespace
@@ -110,6 +112,7 @@ struct dspmap {
     size_t prof_used = 0;
     double prof_ms[FAM_COUNT] = {0};
     int prof_n[FAM_COUNT] = {0};
+    std::map<std::string, std::pair<double, int>> prof_kernel;  // per kernel name: summed ms, launches
 };
 
 namespace {
@@ -134,7 +137,7 @@ int dalloc(dspmap *m, T **p, size_t n, bool zero = true) {
     return DSPMAP_OK;
 }
 
-void prof_begin(dspmap *m, int fam) {
+void prof_begin(dspmap *m, int fam, const char *kernel) {
     if (!m->profile) return;
     if (m->prof_used == m->prof_slots.size()) {
         ProfSlot s;
@@ -143,6 +146,7 @@ void prof_begin(dspmap *m, int fam) {
         m->prof_slots.push_back(s);
     }
     m->prof_slots[m->prof_used].fam = fam;
+    m->prof_slots[m->prof_used].kernel = kernel;
     cudaEventRecord(m->prof_slots[m->prof_used].a, m->stream);
 }
 void prof_end(dspmap *m) {
@@ -156,6 +160,9 @@ void prof_collect(dspmap *m) {
         if (cudaEventElapsedTime(&ms, m->prof_slots[i].a, m->prof_slots[i].b) == cudaSuccess) {
             m->prof_ms[m->prof_slots[i].fam] += ms;
             m->prof_n[m->prof_slots[i].fam] += 1;
+            auto &k = m->prof_kernel[m->prof_slots[i].kernel];
+            k.first += ms;
+            k.second += 1;
         }
     }
     m->prof_used = 0;
@@ -163,7 +170,7 @@ void prof_collect(dspmap *m) {
 
 #define LAUNCH(m, fam, kernel, grid, block, smem, ...)                              \
     do {                                                                            \
-        prof_begin(m, fam);                                                         \
+        prof_begin(m, fam, #kernel);                                                \
         kernel<<<(grid), (block), (smem), (m)->stream>>>(__VA_ARGS__);              \
         prof_end(m);                                                                \
         ++(m)->launches_total;                                                      \
@@ -1227,6 +1234,7 @@ int dspmap_profile_enable(dspmap *m, int on) {
     prof_collect(m);
     m->profile = on != 0;
     for (int i = 0; i < FAM_COUNT; ++i) { m->prof_ms[i] = 0; m->prof_n[i] = 0; }
+    m->prof_kernel.clear();
     return DSPMAP_OK;
 }
 int dspmap_profile_read(dspmap *m, const char **names, float *ms, int32_t *launches, int cap) {
@@ -1238,6 +1246,22 @@ int dspmap_profile_read(dspmap *m, const char **names, float *ms, int32_t *launc
         names[i] = kFamilyNames[i];
         ms[i] = (float)m->prof_ms[i];
         launches[i] = m->prof_n[i];
+    }
+    return n;
+}
+
+// Same measurement per kernel name (the name as written at the launch site): names[i] stays valid until the next call.
+int dspmap_profile_read_kernels(dspmap *m, const char **names, float *ms, int32_t *launches, int cap) {
+    if (!m) return DSPMAP_E_BAD_ARG;
+    cudaStreamSynchronize(m->stream);
+    prof_collect(m);
+    int n = 0;
+    for (auto &kv : m->prof_kernel) {
+        if (n >= cap) break;
+        names[n] = kv.first.c_str();
+        ms[n] = (float)kv.second.first;
+        launches[n] = kv.second.second;
+        ++n;
     }
     return n;
 }

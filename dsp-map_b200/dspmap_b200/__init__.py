@@ -91,6 +91,7 @@ def load_library():
         "dspmap_synchronize": (i, [vp]),
         "dspmap_profile_enable": (i, [vp, i]),
         "dspmap_profile_read": (i, [vp, C.POINTER(C.c_char_p), fp, ip, i]),
+        "dspmap_profile_read_kernels": (i, [vp, C.POINTER(C.c_char_p), fp, ip, i]),
         "dspmap_shard_config": (i, [vp, i, i, vp, vp, i, vp, vp, i, vp, vp]),
         "dspmap_shard_gather_records": (i, [vp, i]),
         "dspmap_shard_phase": (i, [vp, i, i, vp, f, f, f, C.c_double, f, f, f, f, vp, i]),
@@ -124,7 +125,7 @@ EXPORTED_SYMBOLS = [
     "dspmap_clear_prediction", "dspmap_pin_host_buffer", "dspmap_get_tagged_cloud", "dspmap_voxel_center", "dspmap_voxel_index", "dspmap_uniform",
     "dspmap_dims", "dspmap_dump_particles", "dspmap_load_particles", "dspmap_dump_voxel_objects",
     "dspmap_dump_observations", "dspmap_dump_pyramid_lists", "dspmap_cursors", "dspmap_set_cursors", "dspmap_counters",
-    "dspmap_set_stage_limit", "dspmap_set_last_pose", "dspmap_set_stream", "dspmap_synchronize", "dspmap_profile_enable", "dspmap_profile_read",
+    "dspmap_set_stage_limit", "dspmap_set_last_pose", "dspmap_set_stream", "dspmap_synchronize", "dspmap_profile_enable", "dspmap_profile_read", "dspmap_profile_read_kernels",
     "dspmap_estimator_create", "dspmap_estimator_destroy", "dspmap_estimator_estimate", "dspmap_euclidean_clusters",
     "dspmap_prefilter_create", "dspmap_prefilter_destroy", "dspmap_prefilter_set_stream", "dspmap_prefilter_last_error",
     "dspmap_prefilter_launches", "dspmap_prefilter_run", "dspmap_prefilter_run_device", "dspmap_update_raw",
@@ -349,6 +350,14 @@ class DSPMap:
         ms = np.zeros(32, np.float32)
         ln = np.zeros(32, np.int32)
         n = self.lib.dspmap_profile_read(self.h, names, _fp(ms), _ip(ln), 32)
+        return {names[k].decode(): (float(ms[k]), int(ln[k])) for k in range(n)}
+
+    def profile_read_kernels(self):
+        """{kernel name: (summed ms, launches)} measured with CUDA events on the launching stream while profiling is on."""
+        names = (C.c_char_p * 96)()
+        ms = np.zeros(96, np.float32)
+        ln = np.zeros(96, np.int32)
+        n = self.lib.dspmap_profile_read_kernels(self.h, names, _fp(ms), _ip(ln), 96)
         return {names[k].decode(): (float(ms[k]), int(ln[k])) for k in range(n)}
 
     # device-resident entry points (bench): pointers are raw device addresses (e.g. torch tensor .data_ptr())

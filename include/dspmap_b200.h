@@ -164,6 +164,8 @@ int dspmap_synchronize(dspmap *m);
  * enabled: names[i] / ms[i] / launches[i]; returns the number of families. */
 int dspmap_profile_enable(dspmap *m, int on);
 int dspmap_profile_read(dspmap *m, const char **names, float *ms, int32_t *launches, int cap);
+/* The same event measurement per kernel (name as written at the launch site); returns the number of kernels. */
+int dspmap_profile_read_kernels(dspmap *m, const char **names, float *ms, int32_t *launches, int cap);
 
 /* ---- voxel-subspace sharding over the GPUs of one box (one handle per GPU / rank) -----------------------------------
  * The map's z layers are cut into `nranks` equal slabs; handle `rank` owns the particles of its slab.  A frame is
