@@ -43,7 +43,7 @@ struct dspmap {
     MapConst mc;
     DevPtrs dp;
     cudaStream_t stream = nullptr, own_stream = nullptr, side = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_state = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_state = nullptr, ev_fork_obs = nullptr, ev_join_obs = nullptr;
     bool state_event_recorded = false;
     std::vector<void *> allocs;
     // host mirrors
@@ -177,6 +177,19 @@ void prof_collect(dspmap *m) {
         ++(m)->launches_frame;                                                      \
     } while (0)
 
+// the same on an explicit stream (kernels of a forked branch of the frame); profiled on that stream
+#define LAUNCH_ON(m, fam, st, kernel, grid, block, smem, ...)                       \
+    do {                                                                            \
+        cudaStream_t keep_ = (m)->stream;                                           \
+        (m)->stream = (st);                                                         \
+        prof_begin(m, fam, #kernel);                                                \
+        kernel<<<(grid), (block), (smem), (st)>>>(__VA_ARGS__);                     \
+        prof_end(m);                                                                \
+        (m)->stream = keep_;                                                        \
+        ++(m)->launches_total;                                                      \
+        ++(m)->launches_frame;                                                      \
+    } while (0)
+
 const int kSMs = 148;
 // the two configurations of the C_z chain kernel (threads, floats per tile, rows per tile)
 const auto k_cz_narrow = &k_cz_chain<128, 4096, 128>;
@@ -291,15 +304,19 @@ int enqueue_frame_a(dspmap *m, const FrameConst &fc, const float *d_pts) {
     m->launches_frame = 0;
     const int B = 256;
     LAUNCH(m, FAM_SETUP, k_frame_setup, 1, 256, 0, mc, fc, dp);
-    // observations
+    // observations: binning touches nothing the prediction / reassignment chain reads, and both are chains of small
+    // latency-bound kernels, so they run side by side (joined before the pair preparation, the first consumer of the bins)
+    CK(cudaEventRecord(m->ev_fork_obs, m->stream));
+    CK(cudaStreamWaitEvent(m->side, m->ev_fork_obs, 0));
     if (fc.n_points > 0) {
-        LAUNCH(m, FAM_OBS, k_obs_classify, grid_for(fc.n_points, B), B, 0, mc, fc, dp);
+        LAUNCH_ON(m, FAM_OBS, m->side, k_obs_classify, grid_for(fc.n_points, B), B, 0, mc, fc, dp);
     }
-    LAUNCH(m, FAM_OBS, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{dp.obs_cnt, dp.obs_off, dp.obs_capoff, mc.OBS - 1, mc.P}, ScanJob{}, ScanJob{}}});
+    LAUNCH_ON(m, FAM_OBS, m->side, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{dp.obs_cnt, dp.obs_off, dp.obs_capoff, mc.OBS - 1, mc.P}, ScanJob{}, ScanJob{}}});
     if (fc.n_points > 0) {
-        LAUNCH(m, FAM_OBS, k_obs_scatter, grid_for(fc.n_points, B), B, 0, mc, fc, dp);
-        LAUNCH(m, FAM_OBS, k_obs_rank, grid_for(fc.n_points, B), B, 0, mc, fc, dp);
+        LAUNCH_ON(m, FAM_OBS, m->side, k_obs_scatter, grid_for(fc.n_points, B), B, 0, mc, fc, dp);
+        LAUNCH_ON(m, FAM_OBS, m->side, k_obs_rank, grid_for(fc.n_points, B), B, 0, mc, fc, dp);
     }
+    CK(cudaEventRecord(m->ev_join_obs, m->side));
     // prediction and reassignment
     if (fc.vz_mode) {
         LAUNCH(m, FAM_PREDICT, k_vz_count, grid_for(mc.V, B), B, 0, mc, dp);
@@ -316,6 +333,7 @@ int enqueue_frame_a(dspmap *m, const FrameConst &fc, const float *d_pts) {
     LAUNCH(m, FAM_PYRAMID, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{dp.pcount, dp.poff, nullptr, 0, mc.P}, ScanJob{}, ScanJob{}}});
     LAUNCH(m, FAM_PYRAMID, k_pyr_scatter, kSMs * 8, B, 0, dp);
     LAUNCH(m, FAM_PYRAMID, k_pyr_sort, std::min(mc.P, kSMs * 3), 512, PYR_SORT_CAP * sizeof(u64), mc, dp, fc.Pd);
+    CK(cudaStreamWaitEvent(m->stream, m->ev_join_obs, 0));
     if (fc.stage_limit >= 2) {
         LAUNCH(m, FAM_CK, k_pair_prep, grid_for(mc.P, B), B, 0, mc, dp);
         LAUNCH(m, FAM_CK, k_scan_small, 2, 1024, 0, ScanJobs{{ScanJob{dp.pairs, dp.rowbase, nullptr, 0, mc.P}, ScanJob{dp.chunks, dp.chunk_off, nullptr, 0, mc.P}, ScanJob{}}});
@@ -558,6 +576,8 @@ int dspmap_create(const dspmap_config *cfg, dspmap **out) {
     CK(cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&m->ev_fork_obs, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&m->ev_join_obs, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&m->ev_state, cudaEventDisableTiming));
     m->stream = m->own_stream;
 
@@ -682,6 +702,8 @@ void dspmap_destroy(dspmap *m) {
     for (auto &s : m->prof_slots) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     if (m->ev_fork) cudaEventDestroy(m->ev_fork);
     if (m->ev_join) cudaEventDestroy(m->ev_join);
+    if (m->ev_fork_obs) cudaEventDestroy(m->ev_fork_obs);
+    if (m->ev_join_obs) cudaEventDestroy(m->ev_join_obs);
     if (m->ev_state) cudaEventDestroy(m->ev_state);
     for (auto &s : m->rslot) {
         if (s.done) cudaEventDestroy(s.done);
