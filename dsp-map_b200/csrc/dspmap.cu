@@ -100,6 +100,7 @@ struct dspmap {
     // the recompute kernels (k_ck / k_weight) are launched only while the pair buffer may overflow
     bool fallback_armed = true;
     bool cz_wide = true;
+    bool nb_prefix_done = false;  // this frame's first newborn kernels already ran on the side branch
     FrameConst shard_fc;  // frame scalars carried across the phases of a sharded frame
     int shard_cap_g = 0;
     long long host_u_cur = 0;  // uniform draws consumed on the host while seeding
@@ -297,7 +298,7 @@ int ensure_cand_capacity(dspmap *m) {
 }
 
 // Enqueue the first half of a frame: binning, prediction, reassignment, pyramid lists, C_z pass, weight pass.
-int enqueue_frame_a(dspmap *m, const FrameConst &fc, const float *d_pts) {
+int enqueue_frame_a(dspmap *m, const FrameConst &fc, const float *d_pts, const float *d_tagged_early = nullptr) {
     const MapConst &mc = m->mc;
     DevPtrs dp = m->dp;
     dp.pts = d_pts;
@@ -315,6 +316,17 @@ int enqueue_frame_a(dspmap *m, const FrameConst &fc, const float *d_pts) {
     if (fc.n_points > 0) {
         LAUNCH_ON(m, FAM_OBS, m->side, k_obs_scatter, grid_for(fc.n_points, B), B, 0, mc, fc, dp);
         LAUNCH_ON(m, FAM_OBS, m->side, k_obs_rank, grid_for(fc.n_points, B), B, 0, mc, fc, dp);
+    }
+    // With a device-resident newborn input the first newborn kernels — they read only that cloud, the noise table and its
+    // cursor — follow on the same branch instead of waiting for the weight pass
+    m->nb_prefix_done = false;
+    if (d_tagged_early && fc.stage_limit >= 3 && fc.n_tagged > 0 && fc.nb_num > 0) {
+        DevPtrs dq = dp;
+        dq.tagged = d_tagged_early;
+        LAUNCH_ON(m, FAM_NEWBORN, m->side, k_nb_point0, grid_for(fc.n_tagged, B), B, 0, mc, fc, dq);
+        LAUNCH_ON(m, FAM_NEWBORN, m->side, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{dp.ninmap, dp.nrank, nullptr, 0, fc.n_tagged}, ScanJob{}, ScanJob{}}});
+        LAUNCH_ON(m, FAM_NEWBORN, m->side, k_nb_mask, grid_for((long long)fc.n_tagged * fc.nb_num, B), B, 0, mc, fc, dq);
+        m->nb_prefix_done = true;
     }
     CK(cudaEventRecord(m->ev_join_obs, m->side));
     // prediction and reassignment
@@ -369,9 +381,11 @@ int enqueue_frame_b(dspmap *m, const FrameConst &fc, const float *d_tagged) {
     int newborn_ran = 0;
     if (fc.stage_limit >= 3) {
         if (fc.n_tagged > 0 && fc.nb_num > 0) {
-            LAUNCH(m, FAM_NEWBORN, k_nb_point0, grid_for(fc.n_tagged, B), B, 0, mc, fc, dp);
-            LAUNCH(m, FAM_NEWBORN, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{dp.ninmap, dp.nrank, nullptr, 0, fc.n_tagged}, ScanJob{}, ScanJob{}}});
-            LAUNCH(m, FAM_NEWBORN, k_nb_mask, grid_for((long long)fc.n_tagged * fc.nb_num, B), B, 0, mc, fc, dp);
+            if (!m->nb_prefix_done) {
+                LAUNCH(m, FAM_NEWBORN, k_nb_point0, grid_for(fc.n_tagged, B), B, 0, mc, fc, dp);
+                LAUNCH(m, FAM_NEWBORN, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{dp.ninmap, dp.nrank, nullptr, 0, fc.n_tagged}, ScanJob{}, ScanJob{}}});
+                LAUNCH(m, FAM_NEWBORN, k_nb_mask, grid_for((long long)fc.n_tagged * fc.nb_num, B), B, 0, mc, fc, dp);
+            }
             LAUNCH(m, FAM_NEWBORN, k_nb_point1, grid_for((long long)fc.n_tagged * 32, B), B, 0, mc, fc, dp, 0);
             LAUNCH(m, FAM_NEWBORN, k_scan_small, 2, 1024, 0, ScanJobs{{ScanJob{dp.nvcnt, dp.nvoff, nullptr, 0, fc.n_tagged}, ScanJob{dp.nrcnt, dp.nroff, nullptr, 0, fc.n_tagged}, ScanJob{}}});
             LAUNCH(m, FAM_NEWBORN, k_nb_cand, grid_for((long long)fc.n_tagged * fc.nb_num, B), B, 0, mc, fc, dp, (u64)m->cfg.uniform_seed);
@@ -789,7 +803,7 @@ int dspmap_update_device(dspmap *m, int n, const float *d_pts, float px, float p
     }
     if ((rc = ensure_cand_capacity(m)) != DSPMAP_OK) return rc;
     fc.n_tagged = n_tagged;
-    if ((rc = enqueue_frame_a(m, fc, d_pts)) != DSPMAP_OK) return rc;
+    if ((rc = enqueue_frame_a(m, fc, d_pts, d_tagged)) != DSPMAP_OK) return rc;
     if ((rc = enqueue_frame_b(m, fc, d_tagged)) != DSPMAP_OK) return rc;
     if (m->vz_mode) return frame_epilogue(m);  // keep the ordered-noise path armed only as long as it is needed
     return DSPMAP_OK;

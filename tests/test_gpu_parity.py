@@ -154,6 +154,45 @@ def test_readers_threshold_variants_clear_and_state_round_trip():
     g2.close()
 
 
+@pytest.mark.parametrize("name,frames", [("tiny_dyn", 8), ("cfg2", 8)])
+def test_device_resident_update_equals_host_update(name, frames):
+    """dspmap_update_device (cloud and newborn input already in HBM, nothing synchronises, the first newborn kernels run on
+    the side branch) leaves the same map as dspmap_update_tagged with the same inputs — the path bench.py's `value` times."""
+    import torch
+    cfg = dm.CONFIGS[name]
+    st = make_stream(cfg, seed=8, frames=frames)
+    a, b = gpu_map(name, seed=4), gpu_map(name, seed=4)
+    est = dm.VelocityEstimator(cfg, seed=4)
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.Stream(device=dev)
+    b.set_stream(stream.cuda_stream)
+    last = np.zeros((0, 7), np.float32)
+    d_xyz = torch.zeros((b.V, 3), dtype=torch.float32, device=dev)
+    d_cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+    d_fut = torch.zeros((b.V, b.T), dtype=torch.float32, device=dev)
+    for f in range(frames):
+        pts, pos, t, q = st["points"][f], st["pos"][f], st["t"][f], st["quat"][f]
+        tc = est.estimate(pts, pos, t, q)
+        last = tc if tc is not None else last
+        assert gpu_update(a, pts, pos, t, q, tagged=last) == 1
+        with torch.cuda.stream(stream):
+            d_p = torch.from_numpy(np.ascontiguousarray(pts, np.float32)).to(dev)
+            d_t = torch.from_numpy(last if len(last) else np.zeros((1, 7), np.float32)).to(dev)
+            assert b.update_device(len(pts), d_p.data_ptr(), pos, t, q, d_t.data_ptr(), len(last)) == 1
+            if f % 2:
+                b.get_occupancy_device(0.2, d_xyz.data_ptr(), b.V, d_cnt.data_ptr(), d_fut.data_ptr())
+        stream.synchronize()
+        if f % 2:
+            n, xyz, _ = a.getOccupancyMapWithFutureStatus(0.2)
+            assert n == int(d_cnt.item()) and same(xyz, d_xyz[:n].cpu().numpy())
+        (ia, va), (ib, vb) = a.particles(), b.particles()
+        assert same(ia, ib) and same(va, vb), "frame %d" % f
+        assert np.array_equal(a.cursors(), b.cursors()), "cursors, frame %d" % f
+    assert len(ia) > 100
+    a.close()
+    b.close()
+
+
 @pytest.mark.parametrize("name,frames", [("tiny_dyn", 8), ("cfg2", 6)])
 def test_pipelined_reader_equals_blocking_reader(name, frames):
     """dspmap_get_occupancy_async / dspmap_wait_occupancy (copies overlapped with the next update) return what the
