@@ -101,6 +101,7 @@ struct dspmap {
     bool fallback_armed = true;
     bool cz_wide = true;
     bool nb_prefix_done = false;  // this frame's first newborn kernels already ran on the side branch
+    bool pdl = false;             // programmatic dependent launch of the frame's kernels (DSPMAP_PDL=1)
     FrameConst shard_fc;  // frame scalars carried across the phases of a sharded frame
     int shard_cap_g = 0;
     long long host_u_cur = 0;  // uniform draws consumed on the host while seeding
@@ -169,10 +170,33 @@ void prof_collect(dspmap *m) {
     m->prof_used = 0;
 }
 
+// One launch site for every kernel of a frame.  With dspmap::pdl the kernel is launched for programmatic dependent
+// launch (see pdl_enter in dspmap_kernels.cuh): its CTAs may become resident while the previous kernel of the stream
+// drains, which removes the launch gap between the ~30 short, dependent kernels of a frame.
+template <typename... KArgs, typename... Args>
+inline void launch_kernel(bool pdl, cudaStream_t st, void (*kernel)(KArgs...), int grid, int block, size_t smem, Args &&...args) {
+    if (!pdl) {
+        kernel<<<grid, block, smem, st>>>(static_cast<KArgs>(args)...);
+        return;
+    }
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof(lc));
+    lc.gridDim = dim3((unsigned)grid, 1, 1);
+    lc.blockDim = dim3((unsigned)block, 1, 1);
+    lc.dynamicSmemBytes = smem;
+    lc.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at;
+    lc.numAttrs = 1;
+    cudaLaunchKernelEx(&lc, kernel, static_cast<KArgs>(args)...);
+}
+
 #define LAUNCH(m, fam, kernel, grid, block, smem, ...)                              \
     do {                                                                            \
         prof_begin(m, fam, #kernel);                                                \
-        kernel<<<(grid), (block), (smem), (m)->stream>>>(__VA_ARGS__);              \
+        launch_kernel((m)->pdl, (m)->stream, kernel, (grid), (block), (smem), __VA_ARGS__); \
         prof_end(m);                                                                \
         ++(m)->launches_total;                                                      \
         ++(m)->launches_frame;                                                      \
@@ -184,7 +208,7 @@ void prof_collect(dspmap *m) {
         cudaStream_t keep_ = (m)->stream;                                           \
         (m)->stream = (st);                                                         \
         prof_begin(m, fam, #kernel);                                                \
-        kernel<<<(grid), (block), (smem), (st)>>>(__VA_ARGS__);                     \
+        launch_kernel((m)->pdl, (st), kernel, (grid), (block), (smem), __VA_ARGS__); \
         prof_end(m);                                                                \
         (m)->stream = keep_;                                                        \
         ++(m)->launches_total;                                                      \
@@ -357,7 +381,7 @@ int enqueue_frame_a(dspmap *m, const FrameConst &fc, const float *d_pts, const f
         if (fc.stage_limit >= 3) {  // the newborn normaliser is one long serial chain: run it beside the weight pass
             CK(cudaEventRecord(m->ev_fork, m->stream));
             CK(cudaStreamWaitEvent(m->side, m->ev_fork, 0));
-            k_norm<<<1, 128, 0, m->side>>>(mc, fc, dp);
+            launch_kernel(m->pdl, m->side, k_norm, 1, 128, 0, mc, fc, dp);
             ++m->launches_total;
             ++m->launches_frame;
             CK(cudaEventRecord(m->ev_join, m->side));
@@ -676,6 +700,10 @@ int dspmap_create(const dspmap_config *cfg, dspmap **out) {
     CK(cudaFuncSetAttribute(k_ck, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CK(cudaFuncSetAttribute(k_pair_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     CK(cudaFuncSetAttribute(k_cz_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    {   // experiment switch, off unless DSPMAP_PDL is set to something other than 0
+        const char *e = getenv("DSPMAP_PDL");
+        m->pdl = e && *e && strcmp(e, "0") != 0;
+    }
     m->cz_wide = getenv("DSPMAP_CZ_NARROW") == nullptr;  // experiment switch: DSPMAP_CZ_NARROW selects the 128-thread / 32 KB configuration
     CK(cudaFuncSetAttribute(k_weight, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaStreamSynchronize(m->stream));

@@ -13,6 +13,7 @@ __device__ __forceinline__ bool use_pair_buffer(const MapConst &mc, const DevPtr
 // K0  frame setup: rotate the boundary-plane normals (dsp_dynamic.h:226-232), reset per-frame state (:235-238)
 // ------------------------------------------------------------------------------------------------------------
 __global__ void k_frame_setup(MapConst mc, FrameConst fc, DevPtrs dp) {
+    pdl_enter();
     int np = mc.Nh + 1 + mc.Nv + 1;
     for (int i = threadIdx.x; i < np; i += blockDim.x) {
         float o[3];
@@ -57,6 +58,7 @@ __global__ void k_frame_setup(MapConst mc, FrameConst fc, DevPtrs dp) {
 //     counted, scattered and then ranked by input index inside their pyramid (k_obs_rank).
 // ------------------------------------------------------------------------------------------------------------
 __global__ void k_obs_classify(MapConst mc, FrameConst fc, DevPtrs dp) {
+    pdl_enter();
     __shared__ float sp[3 * DSP_MAX_PLANES];
     load_planes(sp, dp, mc);
     const float *ph = sp, *pv = sp + 3 * (mc.Nh + 1);
@@ -87,6 +89,7 @@ __global__ void k_obs_classify(MapConst mc, FrameConst fc, DevPtrs dp) {
 struct ScanJob { const int *in; int *out; int *out_capped; int cap; int n; };
 struct ScanJobs { ScanJob j[3]; };
 __global__ void __launch_bounds__(1024) k_scan_small(ScanJobs jobs) {
+    pdl_enter();
     __shared__ int wsum[32], wcap[32];
     const ScanJob J = jobs.j[blockIdx.x];
     const int n = J.n, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -124,6 +127,7 @@ __global__ void __launch_bounds__(1024) k_scan_small(ScanJobs jobs) {
 }
 
 __global__ void k_obs_scatter(MapConst mc, FrameConst fc, DevPtrs dp) {
+    pdl_enter();
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < fc.n_points; i += gridDim.x * blockDim.x) {
         int pid = dp.OPID[i];
         if (pid < 0) continue;
@@ -132,6 +136,7 @@ __global__ void k_obs_scatter(MapConst mc, FrameConst fc, DevPtrs dp) {
     }
 }
 __global__ void k_obs_rank(MapConst mc, FrameConst fc, DevPtrs dp) {
+    pdl_enter();
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < fc.n_points; i += gridDim.x * blockDim.x) {
         int pid = dp.OPID[i];
         if (pid < 0) continue;
@@ -146,6 +151,7 @@ __global__ void k_obs_rank(MapConst mc, FrameConst fc, DevPtrs dp) {
 // K2a  enumerate live particles from the occupancy masks; snapshot the frame-start masks
 // ------------------------------------------------------------------------------------------------------------
 __global__ void k_enumerate(MapConst mc, DevPtrs dp, int snapshot) {
+    pdl_enter();
     int lane = threadIdx.x & 31;
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     for (int base = warp * 32; base < mc.V; base += nwarps * 32) {
@@ -180,6 +186,7 @@ __device__ __forceinline__ bool vz_noisy(float4 B) {
 }
 // vz mode only: per-voxel count of particles that will draw prediction noise (then scanned over voxels)
 __global__ void k_vz_count(MapConst mc, DevPtrs dp) {
+    pdl_enter();
     for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < mc.V; v += gridDim.x * blockDim.x) {
         ulonglong2 m = dp.M[v], bits = make_ulonglong2(0ull, 0ull);
         for (int half = 0; half < 2; ++half) {
@@ -197,6 +204,7 @@ __global__ void k_vz_count(MapConst mc, DevPtrs dp) {
 }
 #define SCAN_BLOCK 2048
 __global__ void __launch_bounds__(256) k_scan_blocksum(const int *in, int n, int *blocksum) {
+    pdl_enter();
     __shared__ int s;
     if (threadIdx.x == 0) s = 0;
     __syncthreads();
@@ -208,6 +216,7 @@ __global__ void __launch_bounds__(256) k_scan_blocksum(const int *in, int n, int
     if (threadIdx.x == 0) blocksum[blockIdx.x] = s;
 }
 __global__ void __launch_bounds__(256) k_scan_apply(const int *in, int n, const int *blockoff, int *out, int nblocks) {
+    pdl_enter();
     __shared__ int tsum[256];
     int b = blockIdx.x * SCAN_BLOCK + threadIdx.x * (SCAN_BLOCK / 256);
     int loc[SCAN_BLOCK / 256], c = 0;
@@ -225,6 +234,7 @@ __global__ void __launch_bounds__(256) k_scan_apply(const int *in, int n, const 
     if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = blockoff[nblocks];
 }
 __global__ void k_vz_advance(MapConst mc, DevPtrs dp) {
+    pdl_enter();
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         int n = dp.vzoff[mc.V];
         dp.st->n_vz = n;
@@ -242,6 +252,7 @@ __global__ void k_vz_advance(MapConst mc, DevPtrs dp) {
 //      first update (see dspmap.cu: apply_seed_noise).
 // ------------------------------------------------------------------------------------------------------------
 __global__ void k_predict(MapConst mc, FrameConst fc, DevPtrs dp) {
+    pdl_enter();
     __shared__ float sp[3 * DSP_MAX_PLANES];
     load_planes(sp, dp, mc);
     const float *ph = sp, *pv = sp + 3 * (mc.Nh + 1);
@@ -331,6 +342,7 @@ __global__ void k_predict(MapConst mc, FrameConst fc, DevPtrs dp) {
 // snapshots the destination's mask; scatter pass: arrivals write their order key into the segment.
 // ------------------------------------------------------------------------------------------------------------
 __global__ void k_group_owner(DevPtrs dp, const int *n_owner, const int *owner, const int *cnt, int *base, int *top) {
+    pdl_enter();
     int lane = threadIdx.x & 31;
     int n = *n_owner;
     int nround = (n + 31) & ~31;
@@ -351,6 +363,7 @@ __global__ void k_group_owner(DevPtrs dp, const int *n_owner, const int *owner, 
     }
 }
 __global__ void k_group_scatter(const int *n_items, const int *dst, const int *key, const int *base, int *fill, int *seg, int *segi) {
+    pdl_enter();
     int n = *n_items;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         int d = dst[i];
@@ -367,6 +380,7 @@ __global__ void k_group_scatter(const int *n_items, const int *dst, const int *k
 //     come last.  The k-th arrival of a phase takes the k-th free slot; no free slot => the particle vanishes.
 // ------------------------------------------------------------------------------------------------------------
 __global__ void k_arrive(MapConst mc, FrameConst fc, DevPtrs dp) {
+    pdl_enter();
     const int n = dp.st->n_mov;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         int d = dp.MBdst[i], key = dp.MBkey[i];
@@ -417,6 +431,7 @@ __global__ void k_arrive(MapConst mc, FrameConst fc, DevPtrs dp) {
 // pyramid lists (slot addresses are only meaningful on the owner; -1 elsewhere).
 // ------------------------------------------------------------------------------------------------------------
 __global__ void k_shard_import(MapConst mc, DevPtrs dp) {
+    pdl_enter();
     const int slab = SLAB_HDR + mc.cap_x * XREC;
     const int total = mc.nranks * mc.cap_x;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
@@ -436,6 +451,7 @@ __global__ void k_shard_import(MapConst mc, DevPtrs dp) {
     }
 }
 __global__ void k_shard_pack_fov(MapConst mc, DevPtrs dp) {
+    pdl_enter();
     const int n = dp.st->n_fov;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         reinterpret_cast<int *>(dp.gsend)[0] = min(n, mc.cap_g);
@@ -451,6 +467,7 @@ __global__ void k_shard_pack_fov(MapConst mc, DevPtrs dp) {
 }
 // pass 0 counts per pyramid, pass 1 scatters (after the scan of the counts)
 __global__ void k_shard_fov_gathered(MapConst mc, DevPtrs dp, int pass) {
+    pdl_enter();
     const int slab = SLAB_HDR + mc.cap_g * GREC;
     const int total = mc.nranks * mc.cap_g;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
@@ -472,6 +489,7 @@ __global__ void k_shard_fov_gathered(MapConst mc, DevPtrs dp, int pass) {
 
 // zero the buffers that are merged with all-reduce(sum): exactly one rank writes each element
 __global__ void k_shard_zero(MapConst mc, FrameConst fc, DevPtrs dp, int which) {
+    pdl_enter();
     const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
     if (which == 0) {  // C_z [P][OBS] and, right behind it, 1/C_z in bin order
         const size_t n = (size_t)mc.P * mc.OBS + fc.n_points;
@@ -484,6 +502,7 @@ __global__ void k_shard_zero(MapConst mc, FrameConst fc, DevPtrs dp, int which) 
     }
 }
 __global__ void k_shard_apply_weights(MapConst mc, DevPtrs dp) {
+    pdl_enter();
     const int n = dp.poff[mc.P];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int a = dp.LA[i];
@@ -496,6 +515,7 @@ __global__ void k_shard_apply_weights(MapConst mc, DevPtrs dp) {
 //      copy of (px, py, pz, w) for the two observation passes.
 // ------------------------------------------------------------------------------------------------------------
 __global__ void k_pyr_scatter(DevPtrs dp) {
+    pdl_enter();
     const int n = dp.st->n_fov;
     // neighbouring particles mostly fall in the same pyramid: lanes that share one are counted together and their
     // leader reserves the block of slots with a single atomic (the order inside a segment is fixed by k_pyr_sort)
@@ -519,6 +539,7 @@ __global__ void k_pyr_scatter(DevPtrs dp) {
 
 #define PYR_SORT_CAP 8192
 __global__ void __launch_bounds__(512) k_pyr_sort(MapConst mc, DevPtrs dp, float Pd) {
+    pdl_enter();
     extern __shared__ u64 skey[];  // PYR_SORT_CAP entries: (sweep key << 32) | slot address
     for (int q = blockIdx.x; q < mc.P; q += gridDim.x) {
         const int n = dp.pcount[q], b = dp.poff[q];
@@ -592,6 +613,7 @@ __global__ void __launch_bounds__(512) k_pyr_sort(MapConst mc, DevPtrs dp, float
 #define K4_THREADS 256
 #define K4_TERMS 8192  // term tile capacity (floats)
 __global__ void __launch_bounds__(K4_THREADS) k_ck(MapConst mc, FrameConst fc, DevPtrs dp) {
+    pdl_enter();
     extern __shared__ float smem[];
     float *lut = smem;                          // DSP_LUT_HALF
     float *term = lut + DSP_LUT_HALF + 3;       // K4_TERMS
@@ -651,6 +673,7 @@ __global__ void __launch_bounds__(K4_THREADS) k_ck(MapConst mc, FrameConst fc, D
 // ------------------------------------------------------------------------------------------------------------
 #define K5_THREADS 256
 __global__ void __launch_bounds__(K5_THREADS) k_weight(MapConst mc, FrameConst fc, DevPtrs dp, int chunks_per_pyr) {
+    pdl_enter();
     extern __shared__ float smem[];
     float *lut = smem;
     float4 *zs = (float4 *)(lut + DSP_LUT_HALF + 3);  // NB * (OBS-1) staged points: x y z C_z
@@ -712,6 +735,7 @@ __global__ void __launch_bounds__(K5_THREADS) k_weight(MapConst mc, FrameConst f
 //   k_cz_chain reads a row sequentially (j); k_weight2 reads it with consecutive lanes = consecutive particles.
 // ------------------------------------------------------------------------------------------------------------
 __global__ void k_pair_prep(MapConst mc, DevPtrs dp) {
+    pdl_enter();
     unsigned long long local = 0ull;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < mc.P; i += gridDim.x * blockDim.x) {
         const int np = min(dp.obs_cnt[i], mc.OBS - 1), nn = dp.nbr[i * mc.NBW];
@@ -751,8 +775,10 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_pair_eval(MapConst mc, FrameCo
     extern __shared__ float sm[];
     float *lut = sm;
     float *tile = sm + (DSP_LUT_HALF + 3) + (threadIdx.x >> 5) * (32 * TILE_LD);
+    pdl_trigger();
+    for (int i = threadIdx.x; i < DSP_LUT_HALF; i += blockDim.x) lut[i] = dp.lut[i];  // constant after create: staged before the wait
+    pdl_wait();
     if (!use_pair_buffer(mc, dp)) return;
-    for (int i = threadIdx.x; i < DSP_LUT_HALF; i += blockDim.x) lut[i] = dp.lut[i];
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int nchunks = dp.chunk_off[mc.P];
@@ -798,6 +824,7 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_pair_eval(MapConst mc, FrameCo
 // (6 CTAs / SM, every pyramid resident at once) 64 us — the longer tiles amortise the per-tile barrier better.
 template <int CZ_THREADS, int CZ_TILE, int CZ_JT>
 __global__ void __launch_bounds__(CZ_THREADS) k_cz_chain(MapConst mc, FrameConst fc, DevPtrs dp) {
+    pdl_enter();
     extern __shared__ float czsm[];
     float *tile0 = czsm, *tile1 = czsm + CZ_TILE + 8;  // + room for the alignment phase
     float *pws0 = czsm + 2 * (CZ_TILE + 8), *pws1 = pws0 + CZ_JT;
@@ -884,6 +911,7 @@ __global__ void __launch_bounds__(CZ_THREADS) k_cz_chain(MapConst mc, FrameConst
 #define W2_THREADS 128
 #define W2_NP 100  // padded row length (np <= 99; odd stride: no bank conflicts in the chain)
 __global__ void __launch_bounds__(W2_THREADS) k_weight2(MapConst mc, FrameConst fc, DevPtrs dp) {
+    pdl_enter();
     __shared__ float terms[2][32 * (W2_NP + 1)];
     __shared__ float czs[2][W2_NP];
     __shared__ int s_item;
@@ -1010,6 +1038,7 @@ __global__ void __launch_bounds__(W2_THREADS) k_weight2(MapConst mc, FrameConst 
 // per-warp shared tile, and each lane adds its particle's row in (neighbour-table, bin) order.
 #define W2W_THREADS 256
 __global__ void __launch_bounds__(W2W_THREADS, 3) k_weight2w(MapConst mc, FrameConst fc, DevPtrs dp) {
+    pdl_enter();
     __shared__ float tiles[(W2W_THREADS / 32) * 32 * TILE_LD];
     __shared__ float czall[(W2W_THREADS / 32) * 32];
     if (!use_pair_buffer(mc, dp)) return;
@@ -1099,6 +1128,7 @@ __device__ __forceinline__ int verify_index(float q, int mode) {
     return (int)(q * 1000 + 10000);
 }
 __global__ void k_verify_div(float b, float r, unsigned max_bits, int mode, int *bad) {
+    pdl_enter();
     int local = 0;
     for (unsigned long long u = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; u <= max_bits; u += (unsigned long long)gridDim.x * blockDim.x) {
         const float a = __uint_as_float((unsigned)u);
@@ -1110,6 +1140,7 @@ __global__ void k_verify_div(float b, float r, unsigned max_bits, int mode, int 
 
 // K6a  newborn normaliser (dsp_dynamic.h:799-805): sum of 1/C_z over (pyramid, bin) order, one fp32 chain.
 __global__ void k_norm(MapConst mc, FrameConst fc, DevPtrs dp) {
+    pdl_enter();
     __shared__ __align__(16) float buf[2][1024];
     const int n = dp.obs_capoff[mc.P];
     float acc = 0.f;
@@ -1146,6 +1177,7 @@ __global__ void k_norm(MapConst mc, FrameConst fc, DevPtrs dp) {
 // ------------------------------------------------------------------------------------------------------------
 // point pass 0: corrected point, its voxel, in-map predicate (:817-827,:846-848; the static variant has no test)
 __global__ void k_nb_point0(MapConst mc, FrameConst fc, DevPtrs dp) {
+    pdl_enter();
     for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < fc.n_tagged; m += gridDim.x * blockDim.x) {
         const float *pt = dp.tagged + 7 * m;
         float cx = pt[0] - fc.cur[0], cy = pt[1] - fc.cur[1], cz = pt[2] - fc.cur[2];
@@ -1158,6 +1190,7 @@ __global__ void k_nb_point0(MapConst mc, FrameConst fc, DevPtrs dp) {
 __device__ __forceinline__ u64 bits_below(int p) { return p >= 64 ? ~0ull : ((1ull << p) - 1ull); }
 // which of a point's nb_num candidates land inside the map (:871-875): one thread per candidate
 __global__ void k_nb_mask(MapConst mc, FrameConst fc, DevPtrs dp) {
+    pdl_enter();
     const int total = fc.n_tagged * fc.nb_num;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
         int m = t / fc.nb_num, p = t - m * fc.nb_num;
@@ -1174,6 +1207,7 @@ __global__ void k_nb_mask(MapConst mc, FrameConst fc, DevPtrs dp) {
 // lanes = slots, the three weight sums added in slot order — and how many table / uniform draws the point consumes.
 // phase 0: single GPU (split + counts); phase 1: sharded, split by the owner of the point's voxel only; phase 2: sharded, counts
 __global__ void __launch_bounds__(256) k_nb_point1(MapConst mc, FrameConst fc, DevPtrs dp, int phase) {
+    pdl_enter();
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     const int R = (mc.S + 31) >> 5;
@@ -1253,6 +1287,7 @@ __global__ void __launch_bounds__(256) k_nb_point1(MapConst mc, FrameConst fc, D
 // candidate pass: position (:871-873), velocity class (:877-907), weight (:909); candidates inside the map join
 // the arrival grouping of their voxel, ordered by (point, candidate) = the reference's serial order.
 __global__ void k_nb_cand(MapConst mc, FrameConst fc, DevPtrs dp, u64 useed) {
+    pdl_enter();
     const int total = fc.n_tagged * fc.nb_num;
     const float w_new = dp.st->w_new;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
@@ -1302,6 +1337,7 @@ __global__ void k_nb_cand(MapConst mc, FrameConst fc, DevPtrs dp, u64 useed) {
 // free slot.  One warp per destination voxel: it extracts the next-smallest key as many times as the voxel has free
 // slots (lanes scan the voxel's segment, a shuffle reduction picks the minimum), then the winners are copied in parallel.
 __global__ void __launch_bounds__(256) k_nb_place(MapConst mc, FrameConst fc, DevPtrs dp) {
+    pdl_enter();
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     const int nown = dp.st->n_cand_owner;
@@ -1368,6 +1404,7 @@ __global__ void __launch_bounds__(256) k_nb_place(MapConst mc, FrameConst fc, De
 //     to 32 of them); empty voxels get their zero occupancy here.
 // ------------------------------------------------------------------------------------------------------------
 __global__ void k_voxel_list(MapConst mc, DevPtrs dp) {
+    pdl_enter();
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     for (int base = warp * 32; base < mc.V; base += nwarps * 32) {
@@ -1393,6 +1430,7 @@ __global__ void k_voxel_list(MapConst mc, DevPtrs dp) {
 //     systematic-resampling state machine — are executed warp-uniformly on values broadcast by shuffles.
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_resample(MapConst mc, FrameConst fc, DevPtrs dp) {
+    pdl_enter();
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     const int R = (mc.S + 31) >> 5;
@@ -1527,6 +1565,7 @@ __global__ void __launch_bounds__(256) k_resample(MapConst mc, FrameConst fc, De
 // end of frame: reset the arrival-grouping tables touched this frame; advance the noise cursors by what the reference's
 // serial newborn loop would have drawn (dsp_dynamic.h:1162-1178); flag a frame no observation kernel handled
 __global__ void k_cleanup(MapConst mc, FrameConst fc, DevPtrs dp, int newborn_ran, int fallback_launched) {
+    pdl_enter();
     int n1 = dp.st->n_mov_owner, n2 = dp.st->n_cand_owner;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2; i += gridDim.x * blockDim.x) {
         if (i < n1) { int d = dp.mowner[i]; dp.mcnt[d] = 0; dp.mfill[d] = 0; }
@@ -1553,6 +1592,7 @@ __global__ void k_cleanup(MapConst mc, FrameConst fc, DevPtrs dp, int newborn_ra
 // ------------------------------------------------------------------------------------------------------------
 #define OCC_BLOCK 512  // voxels per block
 __global__ void __launch_bounds__(256) k_occ_count(MapConst mc, DevPtrs dp, float thr, int *blockcnt, float *d_future) {
+    pdl_enter();
     __shared__ int s;
     if (threadIdx.x == 0) s = 0;
     __syncthreads();
@@ -1573,6 +1613,7 @@ __global__ void __launch_bounds__(256) k_occ_count(MapConst mc, DevPtrs dp, floa
     }
 }
 __global__ void __launch_bounds__(256) k_occ_write(MapConst mc, DevPtrs dp, float thr, const int *blockoff, float *xyz, int cap, int *d_count, int nblocks) {
+    pdl_enter();
     __shared__ int wsum[8];
     int b = blockIdx.x * OCC_BLOCK;
     int run = blockoff[blockIdx.x];
@@ -1599,6 +1640,7 @@ __global__ void __launch_bounds__(256) k_occ_write(MapConst mc, DevPtrs dp, floa
     }
 }
 __global__ void k_future_clear(MapConst mc, DevPtrs dp) {
+    pdl_enter();
     size_t n = (size_t)mc.V * mc.T;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dp.FUT[i] = 0.f;
 }
@@ -1607,6 +1649,7 @@ __global__ void k_future_clear(MapConst mc, DevPtrs dp) {
 // state dump / load
 // ------------------------------------------------------------------------------------------------------------
 __global__ void k_dump_gather(MapConst mc, DevPtrs dp, int *keys, float *vals) {
+    pdl_enter();
     const int n = min(dp.st->n_live, dp.cap_live);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         int key = dp.E[i];
@@ -1618,6 +1661,7 @@ __global__ void k_dump_gather(MapConst mc, DevPtrs dp, int *keys, float *vals) {
     }
 }
 __global__ void k_load_scatter(MapConst mc, DevPtrs dp, const int *ids, const float *vals, int n) {
+    pdl_enter();
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         int v = ids[2 * i], s = ids[2 * i + 1];
         const float *o = vals + 8 * (size_t)i;
@@ -1627,4 +1671,7 @@ __global__ void k_load_scatter(MapConst mc, DevPtrs dp, const int *ids, const fl
         mask_atomic_set(dp.M, v, s);
     }
 }
-__global__ void k_reset_counter(int *p) { *p = 0; }
+__global__ void k_reset_counter(int *p) {
+    pdl_enter();
+    *p = 0;
+}

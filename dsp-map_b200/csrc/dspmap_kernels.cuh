@@ -11,6 +11,19 @@
 
 #define FULLMASK 0xffffffffu
 
+// Programmatic dependent launch (griddepcontrol, sm_90+).  When the host launches the frame's kernels with
+// cudaLaunchAttributeProgrammaticStreamSerialization (dspmap.cu: launch_kernel, DSPMAP_PDL=1), kernel k+1 may be scheduled
+// while kernel k still runs; nothing the predecessor writes may be touched before pdl_wait(), which returns once every
+// prerequisite grid has completed and its memory is visible.  EVERY kernel executes the wait before it exits (also on its
+// early-return paths): the guarantee is transitive only through kernels that waited.  Launched without the attribute both
+// instructions are no-ops.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() {
+    pdl_trigger();
+    pdl_wait();
+}
+
 struct DevPtrs {
     // particle store, dense direct-addressed: slot address a = voxel * S + slot
     float4 *PA;       // px py pz weight

@@ -1,0 +1,184 @@
+#!/usr/bin/env python3
+"""A/B harness for the library's experiment switches (environment variables read by dspmap_create).
+
+For every switch set given on the command line (e.g. `DSPMAP_PDL=1` or `DSPMAP_PDL=1,DSPMAP_EST_THREAD=1`) it creates a
+baseline map (no switches) and a switched map with the same seeds, feeds both the same stream and requires the complete
+map state to be bit-identical after every frame (tests/parity.py: compare_state; the atomically accumulated future grid
+within rtol 2e-6); then it times the device-resident frame (update_device + get_occupancy_device, CUDA events, L2 flushed
+between steps) and the host-pointer frame (update + getOccupancyMapWithFutureStatus, wall clock) of both.
+
+    python tests/ab_toggles.py [--cfg cfg2] [--frames 10] [--steps 40] [--also cfg3:2] DSPMAP_PDL=1 ...
+
+Results are appended line by line to gpurun_out/ab_toggles.jsonl (flushed as it goes, so a run cut short keeps what it had).
+This is a measurement tool, not part of the test-suite (pytest does not collect it)."""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (os.path.join(ROOT, "dsp-map_b200"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+SWITCHES = ("DSPMAP_PDL", "DSPMAP_EST_THREAD", "DSPMAP_CZ_NARROW", "DSPMAP_NB_RANK", "DSPMAP_GRAPH")
+
+
+def make_map(dm, gpu_map, name, env, **kw):
+    for k in SWITCHES:
+        os.environ.pop(k, None)
+    os.environ.update(env)
+    g = gpu_map(name, seed=7, **kw)
+    for k in env:
+        os.environ.pop(k, None)
+    return g
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cfg", default="cfg2")
+    ap.add_argument("--frames", type=int, default=10, help="parity frames (host-pointer path)")
+    ap.add_argument("--steps", type=int, default=40, help="timed frames per path")
+    ap.add_argument("--also", default="", help="extra parity-only configs, name:frames[,name:frames]")
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "ab_toggles.jsonl"))
+    ap.add_argument("sets", nargs="+")
+    args = ap.parse_args()
+
+    import torch
+    import dspmap_b200 as dm
+    from common import gpu_map, gpu_update, make_stream
+    from parity import compare_state, same
+
+    os.makedirs(os.path.dirname(args.out), exist_ok=True)
+    out = open(args.out, "a")
+
+    def emit(rec):
+        out.write(json.dumps(rec) + "\n")
+        out.flush()
+        print(json.dumps(rec), flush=True)
+
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def parity(name, frames, env):
+        cfg = dm.CONFIGS[name]
+        st = make_stream(cfg, seed=3, frames=frames + 2)
+        est = dm.VelocityEstimator(cfg, seed=7, filter_res=0.1)
+        a = make_map(dm, gpu_map, name, {}, max_points=cfg["points"])
+        b = make_map(dm, gpu_map, name, env, max_points=cfg["points"])
+        bad = []
+        for f in range(frames):
+            pts, pos, t, q = st["points"][f], st["pos"][f], st["t"][f], st["quat"][f]
+            tc = est.estimate(pts, pos, t, q)
+            ra, rb = gpu_update(a, pts, pos, t, q, tagged=tc), gpu_update(b, pts, pos, t, q, tagged=tc)
+            if ra != rb:
+                bad.append("frame %d: return codes %d / %d" % (f, ra, rb))
+            bad += compare_state(a, b, label="frame %d:" % f)
+            if f % 3 == 2:
+                na, xa, fa = a.getOccupancyMapWithFutureStatus(0.2)
+                nb, xb, fb = b.getOccupancyMapWithFutureStatus(0.2)
+                if not same(xa, xb) or not np.allclose(fa, fb, rtol=2e-6, atol=0):
+                    bad.append("frame %d: reader output differs" % f)
+            if bad:
+                break
+        # the library's own estimator path (no explicit newborn input) on two more frames
+        if not bad:
+            for f in range(frames, frames + 2):
+                pts, pos, t, q = st["points"][f], st["pos"][f], st["t"][f], st["quat"][f]
+                ra, rb = gpu_update(a, pts, pos, t, q), gpu_update(b, pts, pos, t, q)
+                if ra != rb or not same(a.getKMClusterResult(), b.getKMClusterResult()):
+                    bad.append("estimator path frame %d: rc %d / %d or tagged cloud differs" % (f, ra, rb))
+                bad += compare_state(a, b, label="estimator path frame %d:" % f)
+        a.close()
+        b.close()
+        return bad
+
+    def timing(name, env, steps):
+        cfg = dm.CONFIGS[name]
+        pre, W = 25, 3
+        F = pre + W + steps
+        st = make_stream(cfg, seed=1, frames=2 * F)
+        M = int(st["n"][0])
+        est = dm.VelocityEstimator(cfg, seed=1, filter_res=0.1)
+        tagged, last = [], np.zeros((0, 7), np.float32)
+        for f in range(F):
+            t = est.estimate(st["points"][f], st["pos"][f], st["t"][f], st["quat"][f])
+            last = t if t is not None else last
+            tagged.append(last)
+        nt_max = max(max(len(t) for t in tagged), 1)
+        d_pts = torch.from_numpy(st["points"][:F]).to(dev)
+        tg = np.zeros((F, nt_max, 7), np.float32)
+        for f, t in enumerate(tagged):
+            tg[f, :len(t)] = t
+        d_tag = torch.from_numpy(tg).to(dev)
+        m = make_map(dm, gpu_map, name, env, max_points=max(M, nt_max, 1024))
+        m.set_stream(stream.cuda_stream)
+        d_xyz = torch.empty((m.V, 3), dtype=torch.float32, device=dev)
+        d_cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+        d_fut = torch.empty((m.V, m.T), dtype=torch.float32, device=dev)
+
+        def step(f):
+            m.update_device(M, d_pts[f].data_ptr(), st["pos"][f], st["t"][f], st["quat"][f], d_tag[f].data_ptr(), len(tagged[f]))
+            m.get_occupancy_device(0.2, d_xyz.data_ptr(), m.V, d_cnt.data_ptr(), d_fut.data_ptr())
+
+        for f in range(pre + W):
+            step(f)
+        m.synchronize()
+        torch.cuda.synchronize()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for k, (e0, e1) in enumerate(ev):
+            flush.zero_()
+            e0.record(stream)
+            step(pre + W + k)
+            e1.record(stream)
+        torch.cuda.synchronize()
+        m.synchronize()
+        dev_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+        fut_host = np.zeros((m.V, m.T), np.float32)
+        m.pin_host_buffer(fut_host)
+        ts = []
+        for k in range(W + steps):
+            f = F + k
+            pts, pos, t, q = st["points"][f], st["pos"][f], st["t"][f], st["quat"][f]
+            flush.zero_()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            gpu_update(m, pts, pos, t, q)
+            m.getOccupancyMapWithFutureStatus(0.2, fut_host)
+            if k >= W:
+                ts.append(time.perf_counter() - t0)
+        m.close()
+        return dev_ms, 1e3 * float(np.mean(ts))
+
+    for spec in args.sets:
+        env = dict(kv.split("=", 1) for kv in spec.split(",") if kv)
+        rec = {"switches": env, "cfg": args.cfg}
+        t0 = time.time()
+        bad = parity(args.cfg, args.frames, env)
+        rec["parity_frames"] = args.frames
+        rec["parity"] = "bit-identical" if not bad else bad[:6]
+        emit(dict(rec, stage="parity", seconds=round(time.time() - t0, 1)))
+        for extra in [e for e in args.also.split(",") if e]:
+            nme, fr = extra.split(":")
+            t0 = time.time()
+            bad2 = parity(nme, int(fr), env)
+            emit({"switches": env, "cfg": nme, "stage": "parity", "parity_frames": int(fr),
+                  "parity": "bit-identical" if not bad2 else bad2[:6], "seconds": round(time.time() - t0, 1)})
+        if args.steps > 0:
+            base_dev, base_host = timing(args.cfg, {}, args.steps)
+            sw_dev, sw_host = timing(args.cfg, env, args.steps)
+            emit({"switches": env, "cfg": args.cfg, "stage": "timing", "steps": args.steps,
+                  "device_ms_per_frame": {"baseline": base_dev, "switched": sw_dev},
+                  "host_api_ms_per_frame": {"baseline": base_host, "switched": sw_host},
+                  "updates_per_s_device": {"baseline": 1e3 / base_dev, "switched": 1e3 / sw_dev},
+                  "updates_per_s_host_api": {"baseline": 1e3 / base_host, "switched": 1e3 / sw_host}})
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
