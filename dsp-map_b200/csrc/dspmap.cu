@@ -18,6 +18,7 @@
 #include "../../include/dspmap_b200.h"
 #include "dspmap_frame.cuh"
 #include "velocity_estimator.h"
+#include "host_worker.h"
 
 namespace {
 
@@ -102,6 +103,8 @@ struct dspmap {
     bool cz_wide = true;
     bool nb_prefix_done = false;  // this frame's first newborn kernels already ran on the side branch
     bool pdl = false;             // programmatic dependent launch of the frame's kernels (DSPMAP_PDL=1)
+    bool est_thread = false;      // velocity estimation on the helper thread, beside the enqueueing of the frame (DSPMAP_EST_THREAD=1)
+    HostWorker worker;
     FrameConst shard_fc;  // frame scalars carried across the phases of a sharded frame
     int shard_cap_g = 0;
     long long host_u_cur = 0;  // uniform draws consumed on the host while seeding
@@ -703,6 +706,8 @@ int dspmap_create(const dspmap_config *cfg, dspmap **out) {
     {   // experiment switch, off unless DSPMAP_PDL is set to something other than 0
         const char *e = getenv("DSPMAP_PDL");
         m->pdl = e && *e && strcmp(e, "0") != 0;
+        e = getenv("DSPMAP_EST_THREAD");
+        m->est_thread = e && *e && strcmp(e, "0") != 0;
     }
     m->cz_wide = getenv("DSPMAP_CZ_NARROW") == nullptr;  // experiment switch: DSPMAP_CZ_NARROW selects the 128-thread / 32 KB configuration
     CK(cudaFuncSetAttribute(k_weight, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -731,6 +736,7 @@ int dspmap_create(const dspmap_config *cfg, dspmap **out) {
 
 void dspmap_destroy(dspmap *m) {
     if (!m) return;
+    m->worker.stop();
     cudaSetDevice(m->cfg.device);
     cudaDeviceSynchronize();
     if (m->pinned_user) cudaHostUnregister(m->pinned_user);
@@ -781,8 +787,16 @@ static int update_common(dspmap *m, int n, int stride, const float *pts, float p
         m->h_pts[3 * i + 2] = pts[(size_t)i * stride + 2];
     }
     if (n > 0) CK(cudaMemcpyAsync((void *)m->dp.pts, m->h_pts, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, m->stream));
-    if ((rc = enqueue_frame_a(m, fc, m->dp.pts)) != DSPMAP_OK) return rc;
-    if (use_estimator) {
+    const bool on_helper = use_estimator && m->est_thread;
+    if (on_helper) {  // the estimation starts now, on the helper thread, while this thread enqueues the frame (host_worker.h)
+        m->worker.start();
+        dspmap *mm = m;
+        m->worker.submit([mm, fc, n] { mm->estimator.estimate(mm->mc, fc, mm->planes0.data(), mm->h_pts, n, mm->cfg.model, mm->tagged_host); });
+    }
+    rc = enqueue_frame_a(m, fc, m->dp.pts);
+    if (on_helper) m->worker.wait();  // joined before the newborn step, like the reference's thread (:311)
+    if (rc != DSPMAP_OK) return rc;
+    if (use_estimator && !on_helper) {
         // the reference's side thread (dsp_dynamic.h:297, 1377-1544), overlapped with the kernels enqueued above exactly
         // as the reference overlaps it with prediction + update (:297-311)
         m->estimator.estimate(m->mc, fc, m->planes0.data(), m->h_pts, n, m->cfg.model, m->tagged_host);
@@ -1335,6 +1349,8 @@ struct dspmap_estimator {
     int model;
     std::vector<float> planes0, tagged;
     VelocityEstimator est;
+    bool threaded = false;
+    HostWorker worker;
 };
 dspmap_estimator *dspmap_estimator_create(const dspmap_config *cfg, float filter_res) {
     dspmap_estimator *e = new dspmap_estimator();
@@ -1348,6 +1364,12 @@ dspmap_estimator *dspmap_estimator_create(const dspmap_config *cfg, float filter
     return e;
 }
 void dspmap_estimator_destroy(dspmap_estimator *e) { delete e; }
+int dspmap_estimator_set_threaded(dspmap_estimator *e, int on) {
+    if (!e) return DSPMAP_E_BAD_ARG;
+    e->threaded = on != 0;
+    if (e->threaded) e->worker.start(); else e->worker.stop();
+    return DSPMAP_OK;
+}
 int dspmap_estimator_estimate(dspmap_estimator *e, int n, const float *pts, float px, float py, float pz, float dt,
                               float qw, float qx, float qy, float qz, float *out, int cap) {
     FrameConst fc;
@@ -1360,7 +1382,12 @@ int dspmap_estimator_estimate(dspmap_estimator *e, int n, const float *pts, floa
     std::vector<float> prev;
     prev.swap(e->tagged);
     e->tagged.assign(1, -12345.f);  // sentinel: estimate() leaves the vector untouched when nothing is in view
-    e->est.estimate(e->mc, fc, e->planes0.data(), pts, n, e->model, e->tagged);
+    if (e->threaded) {  // the same hand-over dspmap_update uses with DSPMAP_EST_THREAD=1
+        e->worker.submit([e, fc, pts, n] { e->est.estimate(e->mc, fc, e->planes0.data(), pts, n, e->model, e->tagged); });
+        e->worker.wait();
+    } else {
+        e->est.estimate(e->mc, fc, e->planes0.data(), pts, n, e->model, e->tagged);
+    }
     if (e->tagged.size() == 1 && e->tagged[0] == -12345.f) {
         e->tagged.swap(prev);
         (void)before;

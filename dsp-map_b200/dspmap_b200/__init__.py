@@ -98,6 +98,7 @@ def load_library():
         "dspmap_estimator_create": (vp, [C.POINTER(Config), f]),
         "dspmap_estimator_destroy": (None, [vp]),
         "dspmap_estimator_estimate": (i, [vp, i, fp, f, f, f, f, f, f, f, f, fp, i]),
+        "dspmap_estimator_set_threaded": (i, [vp, i]),
         "dspmap_euclidean_clusters": (i, [fp, i, f, i, i, i, ip]),
         "dspmap_prefilter_create": (i, [i, i, i, C.c_longlong, C.POINTER(vp)]),
         "dspmap_prefilter_destroy": (None, [vp]),
@@ -126,7 +127,8 @@ EXPORTED_SYMBOLS = [
     "dspmap_dims", "dspmap_dump_particles", "dspmap_load_particles", "dspmap_dump_voxel_objects",
     "dspmap_dump_observations", "dspmap_dump_pyramid_lists", "dspmap_cursors", "dspmap_set_cursors", "dspmap_counters",
     "dspmap_set_stage_limit", "dspmap_set_last_pose", "dspmap_set_stream", "dspmap_synchronize", "dspmap_profile_enable", "dspmap_profile_read", "dspmap_profile_read_kernels",
-    "dspmap_estimator_create", "dspmap_estimator_destroy", "dspmap_estimator_estimate", "dspmap_euclidean_clusters",
+    "dspmap_estimator_create", "dspmap_estimator_destroy", "dspmap_estimator_estimate", "dspmap_estimator_set_threaded",
+    "dspmap_euclidean_clusters",
     "dspmap_prefilter_create", "dspmap_prefilter_destroy", "dspmap_prefilter_set_stream", "dspmap_prefilter_last_error",
     "dspmap_prefilter_launches", "dspmap_prefilter_run", "dspmap_prefilter_run_device", "dspmap_update_raw",
     "dspmap_shard_config", "dspmap_shard_gather_records", "dspmap_shard_phase",
@@ -409,6 +411,10 @@ class VelocityEstimator:
         self.h = C.c_void_p(self.lib.dspmap_estimator_create(C.byref(self.config), filter_res))
         self.last_t = None
         self.cap = 1 << 16
+
+    def set_threaded(self, on=True):
+        """Runs estimate() on the library's persistent helper thread (same results; see include/dspmap_b200.h)."""
+        return self.lib.dspmap_estimator_set_threaded(self.h, 1 if on else 0)
 
     def estimate(self, pts, pos, t, quat):
         """Returns the tagged cloud (n x 7) of this frame, or None when no point is in view."""

@@ -203,6 +203,9 @@ dspmap_estimator *dspmap_estimator_create(const dspmap_config *cfg, float voxel_
 void dspmap_estimator_destroy(dspmap_estimator *e);
 int dspmap_estimator_estimate(dspmap_estimator *e, int n, const float *pts, float px, float py, float pz, float dt,
                               float qw, float qx, float qy, float qz, float *out, int cap);
+/* Runs `estimate` on a persistent helper thread (the hand-over dspmap_update uses when DSPMAP_EST_THREAD=1 moves the
+ * estimation off the enqueueing thread, like the reference's std::thread, dsp_dynamic.h:297-311); results are identical. */
+int dspmap_estimator_set_threaded(dspmap_estimator *e, int on);
 
 /* Application-side preprocessing on the GPU: what src/map_sim_example.cpp:305-336 does per depth frame
  * before DSPMap::update — pcl::VoxelGrid down-sampling with leaf size `leaf` (ex:312-316), the camera -> map axis swap

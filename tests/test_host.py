@@ -136,3 +136,33 @@ def test_estimator_keeps_previous_cloud_when_nothing_in_view():
     assert out.shape == (1, 7) and np.allclose(out[0], [1.5, 0.0, 0.0, 0, 0, 0, 0])
     lone = e.estimate(ahead, (0, 0, 1.0), 0.2, (1, 0, 0, 0))                  # above ground, cluster of 1 < 5: dropped
     assert lone.shape == (0, 7)
+
+
+def test_estimator_on_the_helper_thread_equals_the_calling_thread():
+    """DSPMAP_EST_THREAD=1 hands the estimation to a persistent helper thread (host_worker.h); the hand-over must not
+    change a bit, must survive being switched on and off, and must not lose a wake-up in either of its two waiting modes
+    (spinning right after a job, sleeping on the condition variable after 2 ms without one)."""
+    import time
+    cfg = dm.CONFIGS["tiny_dyn"]
+    st = make_stream(cfg, seed=3, frames=40)
+    a = dm.VelocityEstimator(cfg, seed=7, filter_res=0.1)
+    b = dm.VelocityEstimator(cfg, seed=7, filter_res=0.1)
+    assert b.set_threaded(True) == 1   # DSPMAP_OK
+    for f in range(40):
+        if f == 20:
+            b.set_threaded(False)
+        if f == 25:
+            b.set_threaded(True)
+        if f in (5, 30):
+            time.sleep(0.01)   # the helper has gone to sleep by now
+        x = a.estimate(st["points"][f], st["pos"][f], st["t"][f], st["quat"][f])
+        y = b.estimate(st["points"][f], st["pos"][f], st["t"][f], st["quat"][f])
+        assert (x is None) == (y is None)
+        if x is not None:
+            assert x.shape == y.shape and np.array_equal(x.view(np.uint32), y.view(np.uint32)), "frame %d" % f
+    # many short jobs back to back (the spinning hand-over) interleaved with idle gaps (the sleeping hand-over)
+    pts = st["points"][0][:32]
+    for k in range(3000):
+        b.estimate(pts, (0, 0, 0), 100.0 + 0.1 * k, (1, 0, 0, 0))
+        if k % 500 == 499:
+            time.sleep(0.005)
