@@ -103,6 +103,8 @@ struct dspmap {
     bool cz_wide = true;
     bool nb_prefix_done = false;  // this frame's first newborn kernels already ran on the side branch
     bool pdl = false;             // programmatic dependent launch of the frame's kernels (DSPMAP_PDL=1)
+    bool cz_tma = false;          // C_z chains fed by a cp.async.bulk / mbarrier ring, heaviest pyramid first (DSPMAP_CZ_TMA=1)
+    bool nb_rank = false;         // newborn placement by direct ranking (DSPMAP_NB_RANK=1)
     bool est_thread = false;      // velocity estimation on the helper thread, beside the enqueueing of the frame (DSPMAP_EST_THREAD=1)
     HostWorker worker;
     FrameConst shard_fc;  // frame scalars carried across the phases of a sharded frame
@@ -377,7 +379,8 @@ int enqueue_frame_a(dspmap *m, const FrameConst &fc, const float *d_pts, const f
         LAUNCH(m, FAM_CK, k_pair_prep, grid_for(mc.P, B), B, 0, mc, dp);
         LAUNCH(m, FAM_CK, k_scan_small, 2, 1024, 0, ScanJobs{{ScanJob{dp.pairs, dp.rowbase, nullptr, 0, mc.P}, ScanJob{dp.chunks, dp.chunk_off, nullptr, 0, mc.P}, ScanJob{}}});
         LAUNCH(m, FAM_CK, k_pair_eval, kSMs * 2, EVAL_THREADS, sizeof(float) * (DSP_LUT_HALF + 3 + (EVAL_THREADS / 32) * 32 * TILE_LD), mc, fc, dp, 0);
-        if (m->cz_wide) LAUNCH(m, FAM_CK, k_cz_wide, std::min(mc.P, kSMs * 3), 256, sizeof(float) * (2 * (8192 + 8) + 2 * 128), mc, fc, dp);
+        if (m->cz_tma) LAUNCH(m, FAM_CK, k_cz_chain_tma, std::min(mc.P, kSMs * 2), CZT_THREADS, CZT_SMEM_BYTES, mc, fc, dp);
+        else if (m->cz_wide) LAUNCH(m, FAM_CK, k_cz_wide, std::min(mc.P, kSMs * 3), 256, sizeof(float) * (2 * (8192 + 8) + 2 * 128), mc, fc, dp);
         else LAUNCH(m, FAM_CK, k_cz_narrow, std::min(mc.P, kSMs * 6), 128, sizeof(float) * (2 * (4096 + 8) + 2 * 128), mc, fc, dp);
         size_t smem4 = sizeof(float) * (DSP_LUT_HALF + 3 + K4_TERMS) + sizeof(float4) * (256 + mc.OBS);
         if (m->fallback_armed) LAUNCH(m, FAM_CK, k_ck, std::min(mc.P, kSMs * 2), K4_THREADS, smem4, mc, fc, dp);  // returns at once when the pair buffer is used
@@ -418,7 +421,8 @@ int enqueue_frame_b(dspmap *m, const FrameConst &fc, const float *d_tagged) {
             LAUNCH(m, FAM_NEWBORN, k_nb_cand, grid_for((long long)fc.n_tagged * fc.nb_num, B), B, 0, mc, fc, dp, (u64)m->cfg.uniform_seed);
             LAUNCH(m, FAM_NEWBORN, k_group_owner, kSMs * 2, B, 0, dp, &dp.st->n_cand_owner, dp.cowner, dp.ccnt, dp.cbase, &dp.st->cand_top);
             LAUNCH(m, FAM_NEWBORN, k_group_scatter, kSMs * 4, B, 0, &dp.st->n_cand, dp.Cdst, dp.Ckey, dp.cbase, dp.cfill, dp.cseg, dp.csegi);
-            LAUNCH(m, FAM_NEWBORN, k_nb_place, kSMs * 8, B, 0, mc, fc, dp);
+            if (m->nb_rank) LAUNCH(m, FAM_NEWBORN, k_nb_place_rank, kSMs * 8, B, 0, mc, fc, dp);
+            else LAUNCH(m, FAM_NEWBORN, k_nb_place, kSMs * 8, B, 0, mc, fc, dp);
             newborn_ran = 1;
         }
     }
@@ -643,6 +647,8 @@ int dspmap_create(const dspmap_config *cfg, dspmap **out) {
     mc.cap_pairs = 512ll << 20;  // 2 GB of fp32 pair terms (of 180 GB); larger frames fall back to the recompute kernels
     A(dp.G, (size_t)mc.cap_pairs + 64); A(dp.cum, P * mc.NBW); A(dp.totlen, P); A(dp.pairs, P + 1); A(dp.rowbase, P + 1);
     A(dp.chunks, P + 1); A(dp.chunk_off, P + 1);
+    int *cz_order_buf = nullptr;
+    A(cz_order_buf, P);
     A(dp.NPC, MP); A(dp.ninmap, MP + 1); A(dp.nrank, MP + 1); A(dp.nstatic, MP); A(dp.nvcnt, MP + 1); A(dp.nrcnt, MP + 1);
     A(dp.nvoff, MP + 1); A(dp.nroff, MP + 1); A(dp.nimask, MP);
     A(dp.ccnt, V); A(dp.cfill, V); A(dp.cbase, V); A(dp.cowner, V);
@@ -703,9 +709,15 @@ int dspmap_create(const dspmap_config *cfg, dspmap **out) {
     CK(cudaFuncSetAttribute(k_ck, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CK(cudaFuncSetAttribute(k_pair_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     CK(cudaFuncSetAttribute(k_cz_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    CK(cudaFuncSetAttribute(k_cz_chain_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, CZT_SMEM_BYTES));
     {   // experiment switch, off unless DSPMAP_PDL is set to something other than 0
         const char *e = getenv("DSPMAP_PDL");
         m->pdl = e && *e && strcmp(e, "0") != 0;
+        e = getenv("DSPMAP_CZ_TMA");
+        m->cz_tma = e && *e && strcmp(e, "0") != 0;
+        dp.cz_order = m->cz_tma ? cz_order_buf : nullptr;
+        e = getenv("DSPMAP_NB_RANK");
+        m->nb_rank = e && *e && strcmp(e, "0") != 0;
         e = getenv("DSPMAP_EST_THREAD");
         m->est_thread = e && *e && strcmp(e, "0") != 0;
     }
@@ -946,7 +958,8 @@ int dspmap_shard_phase(dspmap *m, int phase, int n, const float *d_pts, float px
         LAUNCH(m, FAM_CK, k_scan_small, 2, 1024, 0, ScanJobs{{ScanJob{dp.pairs, dp.rowbase, nullptr, 0, mc.P}, ScanJob{dp.chunks, dp.chunk_off, nullptr, 0, mc.P}, ScanJob{}}});
         LAUNCH(m, FAM_CK, k_shard_zero, kSMs * 2, B, 0, mc, fc, dp, 0);
         LAUNCH(m, FAM_CK, k_pair_eval, kSMs * 2, EVAL_THREADS, sizeof(float) * (DSP_LUT_HALF + 3 + (EVAL_THREADS / 32) * 32 * TILE_LD), mc, fc, dp, 1);
-        if (m->cz_wide) LAUNCH(m, FAM_CK, k_cz_wide, std::min(mc.P, kSMs * 3), 256, sizeof(float) * (2 * (8192 + 8) + 2 * 128), mc, fc, dp);
+        if (m->cz_tma) LAUNCH(m, FAM_CK, k_cz_chain_tma, std::min(mc.P, kSMs * 2), CZT_THREADS, CZT_SMEM_BYTES, mc, fc, dp);
+        else if (m->cz_wide) LAUNCH(m, FAM_CK, k_cz_wide, std::min(mc.P, kSMs * 3), 256, sizeof(float) * (2 * (8192 + 8) + 2 * 128), mc, fc, dp);
         else LAUNCH(m, FAM_CK, k_cz_narrow, std::min(mc.P, kSMs * 6), 128, sizeof(float) * (2 * (4096 + 8) + 2 * 128), mc, fc, dp);
     } else if (phase == 3) {
         dp.tagged = d_tagged;
@@ -974,7 +987,8 @@ int dspmap_shard_phase(dspmap *m, int phase, int n, const float *d_pts, float px
             LAUNCH(m, FAM_NEWBORN, k_nb_cand, grid_for((long long)fc.n_tagged * fc.nb_num, B), B, 0, mc, fc, dp, (u64)m->cfg.uniform_seed);
             LAUNCH(m, FAM_NEWBORN, k_group_owner, kSMs * 2, B, 0, dp, &dp.st->n_cand_owner, dp.cowner, dp.ccnt, dp.cbase, &dp.st->cand_top);
             LAUNCH(m, FAM_NEWBORN, k_group_scatter, kSMs * 4, B, 0, &dp.st->n_cand, dp.Cdst, dp.Ckey, dp.cbase, dp.cfill, dp.cseg, dp.csegi);
-            LAUNCH(m, FAM_NEWBORN, k_nb_place, kSMs * 8, B, 0, mc, fc, dp);
+            if (m->nb_rank) LAUNCH(m, FAM_NEWBORN, k_nb_place_rank, kSMs * 8, B, 0, mc, fc, dp);
+            else LAUNCH(m, FAM_NEWBORN, k_nb_place, kSMs * 8, B, 0, mc, fc, dp);
             newborn_ran = 1;
         }
         LAUNCH(m, FAM_RESAMPLE, k_voxel_list, grid_for(mc.V, B), B, 0, mc, dp);

@@ -1,6 +1,7 @@
 // dspmap_frame.cuh — the kernels of one map update, in pipeline order (product code, sm_100a).
 #pragma once
 #include <cuda_pipeline.h>
+#include <cuda/ptx>
 #include "dspmap_kernels.cuh"
 
 // ------------------------------------------------------------------------------------------------------------
@@ -767,6 +768,29 @@ __device__ __forceinline__ int chunk_to_pyramid(const int *chunk_off, int P, int
     }
     return lo;
 }
+// Work order of the C_z pass for k_cz_chain_tma: pyramids by descending pair count (ties by index).  The C_z kernel's run
+// time is the longest serial chain it contains, so the heaviest pyramids have to start first.  Built by ONE CTA of
+// k_pair_eval (rank by counting over keys staged in shared memory); beyond CZ_ORDER_MAX pyramids the lists are short and
+// the identity order is kept.
+#define CZ_ORDER_MAX 2048
+__device__ __forceinline__ void cz_build_order(const MapConst &mc, const DevPtrs &dp, int *keys) {
+    if (mc.P > CZ_ORDER_MAX) {
+        for (int i = threadIdx.x; i < mc.P; i += blockDim.x) dp.cz_order[i] = i;
+        return;
+    }
+    for (int i = threadIdx.x; i < mc.P; i += blockDim.x) keys[i] = dp.pairs[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < mc.P; i += blockDim.x) {
+        const int ki = keys[i];
+        int r = 0;
+        for (int j = 0; j < mc.P; ++j) {
+            const int kj = keys[j];
+            r += (kj > ki) || (kj == ki && j < i);
+        }
+        dp.cz_order[r] = i;
+    }
+    __syncthreads();  // the staging area is the evaluation tiles' from here on
+}
 #define EVAL_THREADS 512
 #define TILE_LD 33  // per-warp 32 x 32 staging tile, padded
 // mode 0: all items; sharded: mode 1 = rows of the point pyramids this rank computes C_z for (i % nranks == rank),
@@ -779,6 +803,7 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_pair_eval(MapConst mc, FrameCo
     for (int i = threadIdx.x; i < DSP_LUT_HALF; i += blockDim.x) lut[i] = dp.lut[i];  // constant after create: staged before the wait
     pdl_wait();
     if (!use_pair_buffer(mc, dp)) return;
+    if (dp.cz_order && blockIdx.x == 0) cz_build_order(mc, dp, reinterpret_cast<int *>(sm + (DSP_LUT_HALF + 3)));  // before this CTA joins the queue
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int nchunks = dp.chunk_off[mc.P];
@@ -896,6 +921,109 @@ __global__ void __launch_bounds__(CZ_THREADS) k_cz_chain(MapConst mc, FrameConst
             buf ^= 1;
         }
         __pipeline_wait_prior(0);
+        if (tid < np) {
+            acc += add_k;
+            dp.CZ[i * mc.OBS + tid] = acc;
+            dp.INV[dp.obs_capoff[i] + tid] = 1.f / acc;  // for the newborn normaliser (:802)
+        }
+    }
+}
+// C_z with a bulk-copy ring (experiment switch DSPMAP_CZ_TMA=1).  The chain of one observation point is serial — rows x 4
+// cycles at best — so the kernel lasts as long as its heaviest pyramid, and the double-buffered version above spends half
+// of that waiting: one tile of lead (<= 128 rows, ~500 cycles of chain) is less than the L2 round trip of the next tile.
+// Here a producer thread streams the pyramid's contiguous block of G (and the matching P_d * w values) through a ring of
+// CZT_STAGES shared-memory stages with cp.async.bulk (TMA, 1-D) completing on per-stage mbarriers; the chain warps wait on
+// "full", add their column in list order, and release the stage on "empty".  ~96 KB in flight per CTA covers
+// np x 4 B per 4 cycles x the L2 latency for np = 99; no block-wide barrier inside a pyramid.
+// Work items come from dp.cz_order (heaviest first).  Results are bit-identical to k_cz_chain: same terms, same order.
+#define CZT_STAGES 6
+#define CZT_TILE 4096   // floats per stage
+#define CZT_JT 128      // particle rows per stage at most
+#define CZT_CHAIN_WARPS 4
+#define CZT_THREADS (32 * (CZT_CHAIN_WARPS + 1))
+#define CZT_SMEM_BYTES (CZT_STAGES * (CZT_TILE + 4 + CZT_JT + 4) * 4 + 2 * CZT_STAGES * 8)
+__global__ void __launch_bounds__(CZT_THREADS) k_cz_chain_tma(MapConst mc, FrameConst fc, DevPtrs dp) {
+    pdl_enter();
+    extern __shared__ __align__(128) float cztsm[];
+    float *tiles = cztsm;                                       // CZT_STAGES x (CZT_TILE + 4): + room for the alignment phase
+    float *pws = tiles + CZT_STAGES * (CZT_TILE + 4);           // CZT_STAGES x (CZT_JT + 4)
+    uint64_t *full = reinterpret_cast<uint64_t *>(pws + CZT_STAGES * (CZT_JT + 4));
+    uint64_t *empty = full + CZT_STAGES;
+    __shared__ int s_item;
+    if (!use_pair_buffer(mc, dp)) return;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) {
+        for (int s = 0; s < CZT_STAGES; ++s) {
+            cuda::ptx::mbarrier_init(&full[s], 1);                  // the producer's arrive.expect_tx; completes with the bytes
+            cuda::ptx::mbarrier_init(&empty[s], CZT_CHAIN_WARPS);   // one arrival per chain warp
+        }
+        cuda::ptx::fence_mbarrier_init(cuda::ptx::sem_release, cuda::ptx::scope_cluster);
+        cuda::ptx::fence_proxy_async(cuda::ptx::space_shared);
+    }
+    __syncthreads();
+    const float enb = fc.nb_weight * (float)dp.st->n_valid * (float)fc.nb_num;  // :292
+    const float add_k = enb + fc.kappa;
+    unsigned it = 0;  // tiles this CTA has been through: the producer and the chain warps walk the same sequence
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_item = atomicAdd(&dp.st->work_k4, 1);
+        __syncthreads();
+        const int wi = s_item;
+        if (wi >= mc.P) break;
+        const int i = dp.cz_order ? dp.cz_order[wi] : wi;
+        const int np = min(dp.obs_cnt[i], mc.OBS - 1);
+        if (np == 0) continue;
+        if (mc.sharded && i % mc.nranks != mc.rank) continue;  // another rank computes this pyramid's C_z
+        const int nn = dp.nbr[i * mc.NBW];
+        const int JT = min(CZT_JT, CZT_TILE / np);
+        const float *g = dp.G + (size_t)dp.rowbase[i];
+        int ns = 0, k0 = 0, ln = nn > 0 ? dp.plen[dp.nbr[i * mc.NBW + 1]] : 0;
+        float acc = 0.f;
+        for (;;) {
+            while (ns < nn && k0 >= ln) {
+                ++ns;
+                k0 = 0;
+                ln = ns < nn ? dp.plen[dp.nbr[i * mc.NBW + 1 + ns]] : 0;
+            }
+            if (ns >= nn) break;
+            const int cur = min(JT, ln - k0), nfl = cur * np;
+            const float *wsrc = dp.PW + dp.poff[dp.nbr[i * mc.NBW + 1 + ns]] + k0;
+            // bulk copies move 16-byte units between 16-byte aligned addresses: start at the boundary below and keep the phase
+            const int phg = (int)((reinterpret_cast<size_t>(g) >> 2) & 3), phw = (int)((reinterpret_cast<size_t>(wsrc) >> 2) & 3);
+            const int s = (int)(it % CZT_STAGES);
+            const unsigned par = (it / CZT_STAGES) & 1u;
+            float *ts = tiles + s * (CZT_TILE + 4), *ws = pws + s * (CZT_JT + 4);
+            if (wid == CZT_CHAIN_WARPS) {  // producer warp: one thread feeds the ring
+                if (lane == 0) {
+                    while (!cuda::ptx::mbarrier_try_wait_parity(&empty[s], par ^ 1u)) {}  // a fresh barrier passes at once
+                    const unsigned bg = (unsigned)((phg + nfl + 3) >> 2) * 16u, bw = (unsigned)((phw + cur + 3) >> 2) * 16u;
+                    cuda::ptx::mbarrier_arrive_expect_tx(cuda::ptx::sem_release, cuda::ptx::scope_cta, cuda::ptx::space_shared, &full[s], bg + bw);
+                    cuda::ptx::cp_async_bulk(cuda::ptx::space_cluster, cuda::ptx::space_global, ts, g - phg, bg, &full[s]);
+                    cuda::ptx::cp_async_bulk(cuda::ptx::space_cluster, cuda::ptx::space_global, ws, wsrc - phw, bw, &full[s]);
+                }
+                __syncwarp();
+            } else {
+                while (!cuda::ptx::mbarrier_try_wait_parity(&full[s], par)) {}
+                if (tid < np) {  // the chain: (P_d * w) * g added in list order, one fp32 add per term
+                    const float *t = ts + phg + tid;
+                    const float *w = ws + phw;
+                    int jj = 0;
+                    for (; jj + 8 <= cur; jj += 8) {
+                        float g0 = t[jj * np], g1 = t[(jj + 1) * np], g2 = t[(jj + 2) * np], g3 = t[(jj + 3) * np];
+                        float g4 = t[(jj + 4) * np], g5 = t[(jj + 5) * np], g6 = t[(jj + 6) * np], g7 = t[(jj + 7) * np];
+                        g0 *= w[jj]; g1 *= w[jj + 1]; g2 *= w[jj + 2]; g3 *= w[jj + 3];
+                        g4 *= w[jj + 4]; g5 *= w[jj + 5]; g6 *= w[jj + 6]; g7 *= w[jj + 7];
+                        acc += g0; acc += g1; acc += g2; acc += g3; acc += g4; acc += g5; acc += g6; acc += g7;
+                    }
+                    for (; jj < cur; ++jj) acc += w[jj] * t[jj * np];
+                }
+                __syncwarp();
+                if (lane == 0) cuda::ptx::mbarrier_arrive(&empty[s]);
+            }
+            g += nfl;
+            k0 += cur;
+            ++it;
+        }
         if (tid < np) {
             acc += add_k;
             dp.CZ[i * mc.OBS + tid] = acc;
@@ -1394,6 +1522,80 @@ __global__ void __launch_bounds__(256) k_nb_place(MapConst mc, FrameConst fc, De
             }
         if (lane == 0) {
             dp.M[d] = msk;
+            born += nfree;
+        }
+    }
+    if (lane == 0 && born) atomicAdd(&dp.st->n_born, born);
+}
+// The same placement by direct ranking (experiment switch DSPMAP_NB_RANK=1).  Keys are unique, so a candidate's rank among
+// its voxel's candidates IS the number of the free slot it takes: ranks come from one all-pairs comparison through
+// shuffles (c steps for a voxel with c <= 32 candidates instead of one min-extraction round per free slot), the rank-th
+// free slot of the voxel's mask is then found by every winner in parallel.  Voxels with more than 128 candidates take the
+// serial extraction straight from global memory.
+__global__ void __launch_bounds__(256) k_nb_place_rank(MapConst mc, FrameConst fc, DevPtrs dp) {
+    pdl_enter();
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int nown = dp.st->n_cand_owner;
+    int born = 0;
+    for (int o = warp; o < nown; o += nwarps) {
+        const int d = dp.cowner[o];
+        const int b = dp.cbase[d], c = dp.ccnt[d];
+        const ulonglong2 msk = dp.M[d];
+        const int nfree = min(mask_free(mc, msk), c);
+        if (c <= 128) {
+            int key[4], rank[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int j = q * 32 + lane;
+                key[q] = j < c ? dp.cseg[b + j] : INT_MAX;
+                rank[q] = 0;
+            }
+            const int nq = (c + 31) >> 5;
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) {
+                if (qq < nq) {
+                    const int lim = min(32, c - 32 * qq);
+                    for (int l = 0; l < lim; ++l) {
+                        const int other = __shfl_sync(FULLMASK, key[qq], l);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) rank[q] += other < key[q] ? 1 : 0;
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int j = q * 32 + lane;
+                if (j < c && rank[q] < nfree) {
+                    const int slot = mask_nth_free(mc, msk, rank[q]);
+                    const int cand = dp.csegi[b + j];
+                    const int a = d * mc.S + slot;
+                    dp.PA[a] = dp.CA[cand];
+                    dp.PB[a] = dp.CB[cand];
+                }
+            }
+        } else {
+            long long last = -1;
+            for (int r = 0; r < nfree; ++r) {
+                u64 best = ~0ull;  // (key << 32) | position
+                for (int j = lane; j < c; j += 32) {
+                    const long long kj = dp.cseg[b + j];
+                    if (kj > last) best = min(best, ((u64)kj << 32) | (unsigned)j);
+                }
+                for (int sft = 16; sft > 0; sft >>= 1) best = min(best, __shfl_xor_sync(FULLMASK, best, sft));
+                last = (long long)(best >> 32);
+                if (lane == 0) {
+                    const int slot = mask_nth_free(mc, msk, r);
+                    const int cand = dp.csegi[b + (int)(best & 0xffffffffull)];
+                    const int a = d * mc.S + slot;
+                    dp.PA[a] = dp.CA[cand];
+                    dp.PB[a] = dp.CB[cand];
+                }
+            }
+        }
+        if (lane == 0) {
+            const ulonglong2 t = mask_take_free(mc, msk, nfree);
+            dp.M[d] = make_ulonglong2(msk.x | t.x, msk.y | t.y);
             born += nfree;
         }
     }

@@ -64,6 +64,7 @@ struct DevPtrs {
     // pair buffer: G[rowbase[i] + z * totlen[i] + j] = g(particle j of pyramid i's concatenated neighbour lists; point z of i)
     float *G;
     int *cum, *totlen, *pairs, *rowbase, *chunks, *chunk_off;
+    int *cz_order;      // work order of k_cz_chain_tma (heaviest pyramid first); null unless DSPMAP_CZ_TMA
     // newborn
     const float *tagged;  // n_tagged x 7, world frame
     float4 *NPC;          // corrected point + voxel id
