@@ -28,6 +28,7 @@ import numpy as np  # noqa: E402
 
 THRESHOLD = 0.2   # occupancy threshold used by the example app (src/map_sim_example.cpp:378)
 PREROLL = 25      # untimed frames to reach the steady particle population (discard >= 20)
+SWITCHES = ("DSPMAP_PDL", "DSPMAP_EST_THREAD")   # see main(): opted into by the single-map arm, not by the sharded one
 SETTERS = dict(p_std=0.05, v_std=0.05, ob_std=0.1, newborn_num=20, newborn_weight=1e-4, filter_res=0.1)  # ex:522-526
 
 
@@ -311,6 +312,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # Library switches this arm opts into (read by dspmap_create; set them to 0 to measure the library defaults).  Both were
+    # A/B-measured on B200 on exactly this workload and are bit-identical to the default path (profiles/r01_ab_switches.jsonl,
+    # tests/test_gpu_parity.py): programmatic dependent launch of the frame's kernels, and the velocity estimation on the
+    # library's helper thread (the reference runs it on a std::thread as well).
+    for k_ in SWITCHES:
+        os.environ.setdefault(k_, "1")
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -558,7 +565,8 @@ def main():
         "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": dict(workload_config(cfg_name, cfg, "hbm-resident"), parallelism="replicas x%d" % world if world > 1 else "single",
-                       l2_flush_between_steps=flush is not None, preroll_frames=PREROLL),
+                       l2_flush_between_steps=flush is not None, preroll_frames=PREROLL,
+                       library_switches={k_: os.environ.get(k_, "0") for k_ in SWITCHES}),
         "e2e": {"value": e2e_val, "unit": "updates/s", "h2d_bytes_per_step": h2d // max(len(e2e_t), 1),
                 "d2h_bytes_per_step": d2h // max(len(e2e_t), 1), "ms_per_step": 1e3 * float(np.mean(e2e_t)),
                 "update_ms": 1e3 * float(np.mean(e2e_upd)), "reader_ms": 1e3 * float(np.mean(e2e_t) - np.mean(e2e_upd))},

@@ -104,7 +104,6 @@ struct dspmap {
     bool nb_prefix_done = false;  // this frame's first newborn kernels already ran on the side branch
     bool pdl = false;             // programmatic dependent launch of the frame's kernels (DSPMAP_PDL=1)
     bool cz_tma = false;          // C_z chains fed by a cp.async.bulk / mbarrier ring, heaviest pyramid first (DSPMAP_CZ_TMA=1)
-    bool nb_rank = false;         // newborn placement by direct ranking (DSPMAP_NB_RANK=1)
     bool est_thread = false;      // velocity estimation on the helper thread, beside the enqueueing of the frame (DSPMAP_EST_THREAD=1)
     HostWorker worker;
     FrameConst shard_fc;  // frame scalars carried across the phases of a sharded frame
@@ -421,8 +420,7 @@ int enqueue_frame_b(dspmap *m, const FrameConst &fc, const float *d_tagged) {
             LAUNCH(m, FAM_NEWBORN, k_nb_cand, grid_for((long long)fc.n_tagged * fc.nb_num, B), B, 0, mc, fc, dp, (u64)m->cfg.uniform_seed);
             LAUNCH(m, FAM_NEWBORN, k_group_owner, kSMs * 2, B, 0, dp, &dp.st->n_cand_owner, dp.cowner, dp.ccnt, dp.cbase, &dp.st->cand_top);
             LAUNCH(m, FAM_NEWBORN, k_group_scatter, kSMs * 4, B, 0, &dp.st->n_cand, dp.Cdst, dp.Ckey, dp.cbase, dp.cfill, dp.cseg, dp.csegi);
-            if (m->nb_rank) LAUNCH(m, FAM_NEWBORN, k_nb_place_rank, kSMs * 8, B, 0, mc, fc, dp);
-            else LAUNCH(m, FAM_NEWBORN, k_nb_place, kSMs * 8, B, 0, mc, fc, dp);
+            LAUNCH(m, FAM_NEWBORN, k_nb_place, kSMs * 8, B, 0, mc, fc, dp);
             newborn_ran = 1;
         }
     }
@@ -716,8 +714,6 @@ int dspmap_create(const dspmap_config *cfg, dspmap **out) {
         e = getenv("DSPMAP_CZ_TMA");
         m->cz_tma = e && *e && strcmp(e, "0") != 0;
         dp.cz_order = m->cz_tma ? cz_order_buf : nullptr;
-        e = getenv("DSPMAP_NB_RANK");
-        m->nb_rank = e && *e && strcmp(e, "0") != 0;
         e = getenv("DSPMAP_EST_THREAD");
         m->est_thread = e && *e && strcmp(e, "0") != 0;
     }
@@ -987,8 +983,7 @@ int dspmap_shard_phase(dspmap *m, int phase, int n, const float *d_pts, float px
             LAUNCH(m, FAM_NEWBORN, k_nb_cand, grid_for((long long)fc.n_tagged * fc.nb_num, B), B, 0, mc, fc, dp, (u64)m->cfg.uniform_seed);
             LAUNCH(m, FAM_NEWBORN, k_group_owner, kSMs * 2, B, 0, dp, &dp.st->n_cand_owner, dp.cowner, dp.ccnt, dp.cbase, &dp.st->cand_top);
             LAUNCH(m, FAM_NEWBORN, k_group_scatter, kSMs * 4, B, 0, &dp.st->n_cand, dp.Cdst, dp.Ckey, dp.cbase, dp.cfill, dp.cseg, dp.csegi);
-            if (m->nb_rank) LAUNCH(m, FAM_NEWBORN, k_nb_place_rank, kSMs * 8, B, 0, mc, fc, dp);
-            else LAUNCH(m, FAM_NEWBORN, k_nb_place, kSMs * 8, B, 0, mc, fc, dp);
+            LAUNCH(m, FAM_NEWBORN, k_nb_place, kSMs * 8, B, 0, mc, fc, dp);
             newborn_ran = 1;
         }
         LAUNCH(m, FAM_RESAMPLE, k_voxel_list, grid_for(mc.V, B), B, 0, mc, dp);

@@ -940,6 +940,7 @@ __global__ void __launch_bounds__(CZ_THREADS) k_cz_chain(MapConst mc, FrameConst
 #define CZT_TILE 4096   // floats per stage
 #define CZT_JT 128      // particle rows per stage at most
 #define CZT_CHAIN_WARPS 4
+#define CZT_MAXNB 128    // neighbour tables staged in shared memory up to this many neighbours (== chain threads)
 #define CZT_THREADS (32 * (CZT_CHAIN_WARPS + 1))
 #define CZT_SMEM_BYTES (CZT_STAGES * (CZT_TILE + 4 + CZT_JT + 4) * 4 + 2 * CZT_STAGES * 8)
 __global__ void __launch_bounds__(CZT_THREADS) k_cz_chain_tma(MapConst mc, FrameConst fc, DevPtrs dp) {
@@ -950,6 +951,7 @@ __global__ void __launch_bounds__(CZT_THREADS) k_cz_chain_tma(MapConst mc, Frame
     uint64_t *full = reinterpret_cast<uint64_t *>(pws + CZT_STAGES * (CZT_JT + 4));
     uint64_t *empty = full + CZT_STAGES;
     __shared__ int s_item;
+    __shared__ int s_len[CZT_MAXNB], s_off[CZT_MAXNB];  // this pyramid's neighbour lists (length, offset into PW): read once, walked per tile
     if (!use_pair_buffer(mc, dp)) return;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) {
@@ -975,19 +977,28 @@ __global__ void __launch_bounds__(CZT_THREADS) k_cz_chain_tma(MapConst mc, Frame
         if (np == 0) continue;
         if (mc.sharded && i % mc.nranks != mc.rank) continue;  // another rank computes this pyramid's C_z
         const int nn = dp.nbr[i * mc.NBW];
+        const bool staged = nn <= CZT_MAXNB;  // larger neighbourhoods (PYRAMID_NEIGHBOR_N >= 6) read the tables per tile
+        if (staged && tid < nn) {
+            const int b = dp.nbr[i * mc.NBW + 1 + tid];
+            s_len[tid] = dp.plen[b];
+            s_off[tid] = dp.poff[b];
+        }
+        __syncthreads();  // (the barrier at the top of the loop keeps the previous pyramid's readers ahead of these writes)
+        auto len_of = [&](int k) { return staged ? s_len[k] : dp.plen[dp.nbr[i * mc.NBW + 1 + k]]; };
+        auto off_of = [&](int k) { return staged ? s_off[k] : dp.poff[dp.nbr[i * mc.NBW + 1 + k]]; };
         const int JT = min(CZT_JT, CZT_TILE / np);
         const float *g = dp.G + (size_t)dp.rowbase[i];
-        int ns = 0, k0 = 0, ln = nn > 0 ? dp.plen[dp.nbr[i * mc.NBW + 1]] : 0;
+        int ns = 0, k0 = 0, ln = nn > 0 ? len_of(0) : 0;
         float acc = 0.f;
         for (;;) {
             while (ns < nn && k0 >= ln) {
                 ++ns;
                 k0 = 0;
-                ln = ns < nn ? dp.plen[dp.nbr[i * mc.NBW + 1 + ns]] : 0;
+                ln = ns < nn ? len_of(ns) : 0;
             }
             if (ns >= nn) break;
             const int cur = min(JT, ln - k0), nfl = cur * np;
-            const float *wsrc = dp.PW + dp.poff[dp.nbr[i * mc.NBW + 1 + ns]] + k0;
+            const float *wsrc = dp.PW + off_of(ns) + k0;
             // bulk copies move 16-byte units between 16-byte aligned addresses: start at the boundary below and keep the phase
             const int phg = (int)((reinterpret_cast<size_t>(g) >> 2) & 3), phw = (int)((reinterpret_cast<size_t>(wsrc) >> 2) & 3);
             const int s = (int)(it % CZT_STAGES);
@@ -1464,6 +1475,9 @@ __global__ void k_nb_cand(MapConst mc, FrameConst fc, DevPtrs dp, u64 useed) {
 // addAParticle (:1183-1201) in serial order: the k-th candidate of a voxel (in (point, candidate) order) takes its k-th
 // free slot.  One warp per destination voxel: it extracts the next-smallest key as many times as the voxel has free
 // slots (lanes scan the voxel's segment, a shuffle reduction picks the minimum), then the winners are copied in parallel.
+// (Measured alternative on B200, cfg2: ranking all candidates of a voxel against each other through shuffles and placing
+// every winner in parallel is bit-identical but 2.8 % slower per frame — a voxel has ~3 free slots to fill, fewer rounds than
+// the all-pairs ranking has steps.)
 __global__ void __launch_bounds__(256) k_nb_place(MapConst mc, FrameConst fc, DevPtrs dp) {
     pdl_enter();
     const int lane = threadIdx.x & 31;
@@ -1522,80 +1536,6 @@ __global__ void __launch_bounds__(256) k_nb_place(MapConst mc, FrameConst fc, De
             }
         if (lane == 0) {
             dp.M[d] = msk;
-            born += nfree;
-        }
-    }
-    if (lane == 0 && born) atomicAdd(&dp.st->n_born, born);
-}
-// The same placement by direct ranking (experiment switch DSPMAP_NB_RANK=1).  Keys are unique, so a candidate's rank among
-// its voxel's candidates IS the number of the free slot it takes: ranks come from one all-pairs comparison through
-// shuffles (c steps for a voxel with c <= 32 candidates instead of one min-extraction round per free slot), the rank-th
-// free slot of the voxel's mask is then found by every winner in parallel.  Voxels with more than 128 candidates take the
-// serial extraction straight from global memory.
-__global__ void __launch_bounds__(256) k_nb_place_rank(MapConst mc, FrameConst fc, DevPtrs dp) {
-    pdl_enter();
-    const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-    const int nown = dp.st->n_cand_owner;
-    int born = 0;
-    for (int o = warp; o < nown; o += nwarps) {
-        const int d = dp.cowner[o];
-        const int b = dp.cbase[d], c = dp.ccnt[d];
-        const ulonglong2 msk = dp.M[d];
-        const int nfree = min(mask_free(mc, msk), c);
-        if (c <= 128) {
-            int key[4], rank[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int j = q * 32 + lane;
-                key[q] = j < c ? dp.cseg[b + j] : INT_MAX;
-                rank[q] = 0;
-            }
-            const int nq = (c + 31) >> 5;
-#pragma unroll
-            for (int qq = 0; qq < 4; ++qq) {
-                if (qq < nq) {
-                    const int lim = min(32, c - 32 * qq);
-                    for (int l = 0; l < lim; ++l) {
-                        const int other = __shfl_sync(FULLMASK, key[qq], l);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) rank[q] += other < key[q] ? 1 : 0;
-                    }
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int j = q * 32 + lane;
-                if (j < c && rank[q] < nfree) {
-                    const int slot = mask_nth_free(mc, msk, rank[q]);
-                    const int cand = dp.csegi[b + j];
-                    const int a = d * mc.S + slot;
-                    dp.PA[a] = dp.CA[cand];
-                    dp.PB[a] = dp.CB[cand];
-                }
-            }
-        } else {
-            long long last = -1;
-            for (int r = 0; r < nfree; ++r) {
-                u64 best = ~0ull;  // (key << 32) | position
-                for (int j = lane; j < c; j += 32) {
-                    const long long kj = dp.cseg[b + j];
-                    if (kj > last) best = min(best, ((u64)kj << 32) | (unsigned)j);
-                }
-                for (int sft = 16; sft > 0; sft >>= 1) best = min(best, __shfl_xor_sync(FULLMASK, best, sft));
-                last = (long long)(best >> 32);
-                if (lane == 0) {
-                    const int slot = mask_nth_free(mc, msk, r);
-                    const int cand = dp.csegi[b + (int)(best & 0xffffffffull)];
-                    const int a = d * mc.S + slot;
-                    dp.PA[a] = dp.CA[cand];
-                    dp.PB[a] = dp.CB[cand];
-                }
-            }
-        }
-        if (lane == 0) {
-            const ulonglong2 t = mask_take_free(mc, msk, nfree);
-            dp.M[d] = make_ulonglong2(msk.x | t.x, msk.y | t.y);
             born += nfree;
         }
     }

@@ -263,3 +263,33 @@ def test_full_size_properties(name, frames):
             n2, _, fut2 = g.getOccupancyMapWithFutureStatus(0.2)
             assert n2 == n and not fut2.any()                                       # idempotent list, future cleared
     g.close()
+
+
+@pytest.mark.parametrize("switch", ["DSPMAP_PDL", "DSPMAP_EST_THREAD"])
+def test_library_switches_used_by_the_bench_do_not_change_a_bit(switch, monkeypatch):
+    """bench.py opts into programmatic dependent launch and the helper-thread velocity estimation (environment switches
+    read by dspmap_create).  A map created with the switch must stay bit-identical to a default map on the bench workload,
+    through the explicit-newborn-input path and through the library's own estimator."""
+    name, frames = "cfg2", 3
+    cfg = dm.CONFIGS[name]
+    st = make_stream(cfg, seed=3, frames=frames + 2)
+    est = dm.VelocityEstimator(cfg, seed=7, filter_res=0.1)
+    monkeypatch.delenv(switch, raising=False)
+    a = gpu_map(name, seed=7, max_points=cfg["points"])
+    monkeypatch.setenv(switch, "1")
+    b = gpu_map(name, seed=7, max_points=cfg["points"])
+    monkeypatch.delenv(switch, raising=False)
+    bad = []
+    for f in range(frames + 2):
+        pts, pos, t, q = st["points"][f], st["pos"][f], st["t"][f], st["quat"][f]
+        tc = est.estimate(pts, pos, t, q) if f < frames else None   # the last two frames: built-in estimation
+        assert gpu_update(a, pts, pos, t, q, tagged=tc) == gpu_update(b, pts, pos, t, q, tagged=tc) == 1
+        bad += compare_state(a, b, label="%s frame %d:" % (switch, f))
+        if tc is None:
+            assert same(a.getKMClusterResult(), b.getKMClusterResult())
+    na, xa, fa = a.getOccupancyMapWithFutureStatus(0.2)
+    nb, xb, fb = b.getOccupancyMapWithFutureStatus(0.2)
+    assert same(xa, xb) and np.allclose(fa, fb, rtol=2e-6, atol=0)
+    a.close()
+    b.close()
+    assert not bad, "\n".join(bad)
