@@ -104,6 +104,8 @@ struct dspmap {
     bool nb_prefix_done = false;  // this frame's first newborn kernels already ran on the side branch
     bool pdl = false;             // programmatic dependent launch of the frame's kernels (DSPMAP_PDL=1)
     bool cz_tma = false;          // C_z chains fed by a cp.async.bulk / mbarrier ring, heaviest pyramid first (DSPMAP_CZ_TMA=1)
+    bool nb_redux = false;        // newborn placement with REDUX minima (DSPMAP_NB_REDUX=1)
+    bool quot_fast = false;       // weight pass: zero / tiny dividends bypass the IEEE division's slow path (DSPMAP_QUOT_FAST=1)
     bool est_thread = false;      // velocity estimation on the helper thread, beside the enqueueing of the frame (DSPMAP_EST_THREAD=1)
     HostWorker worker;
     FrameConst shard_fc;  // frame scalars carried across the phases of a sharded frame
@@ -221,6 +223,8 @@ inline void launch_kernel(bool pdl, cudaStream_t st, void (*kernel)(KArgs...), i
 
 const int kSMs = 148;
 // the two configurations of the C_z chain kernel (threads, floats per tile, rows per tile)
+const auto k_weight2 = &k_weight2_t<false>, k_weight2q = &k_weight2_t<true>;
+const auto k_weight2w = &k_weight2w_t<false>, k_weight2wq = &k_weight2w_t<true>;
 const auto k_cz_narrow = &k_cz_chain<128, 4096, 128>;
 const auto k_cz_wide = &k_cz_chain<256, 8192, 128>;
 inline int grid_for(long long n, int block, int max_blocks = kSMs * 8) {
@@ -391,8 +395,13 @@ int enqueue_frame_a(dspmap *m, const FrameConst &fc, const float *d_pts, const f
             ++m->launches_frame;
             CK(cudaEventRecord(m->ev_join, m->side));
         }
-        LAUNCH(m, FAM_WEIGHT, k_weight2, kSMs * 8, W2_THREADS, 0, mc, fc, dp);
-        LAUNCH(m, FAM_WEIGHT, k_weight2w, kSMs * 6, W2W_THREADS, 0, mc, fc, dp);
+        if (m->quot_fast) {
+            LAUNCH(m, FAM_WEIGHT, k_weight2q, kSMs * 8, W2_THREADS, 0, mc, fc, dp);
+            LAUNCH(m, FAM_WEIGHT, k_weight2wq, kSMs * 6, W2W_THREADS, 0, mc, fc, dp);
+        } else {
+            LAUNCH(m, FAM_WEIGHT, k_weight2, kSMs * 8, W2_THREADS, 0, mc, fc, dp);
+            LAUNCH(m, FAM_WEIGHT, k_weight2w, kSMs * 6, W2W_THREADS, 0, mc, fc, dp);
+        }
         size_t smem5 = sizeof(float) * (DSP_LUT_HALF + 3) + sizeof(float4) * (size_t)mc.NB * (mc.OBS - 1);
         int chunks = (mc.L + K5_THREADS - 1) / K5_THREADS;
         if (m->fallback_armed) LAUNCH(m, FAM_WEIGHT, k_weight, kSMs * 2, K5_THREADS, smem5, mc, fc, dp, chunks);
@@ -420,7 +429,8 @@ int enqueue_frame_b(dspmap *m, const FrameConst &fc, const float *d_tagged) {
             LAUNCH(m, FAM_NEWBORN, k_nb_cand, grid_for((long long)fc.n_tagged * fc.nb_num, B), B, 0, mc, fc, dp, (u64)m->cfg.uniform_seed);
             LAUNCH(m, FAM_NEWBORN, k_group_owner, kSMs * 2, B, 0, dp, &dp.st->n_cand_owner, dp.cowner, dp.ccnt, dp.cbase, &dp.st->cand_top);
             LAUNCH(m, FAM_NEWBORN, k_group_scatter, kSMs * 4, B, 0, &dp.st->n_cand, dp.Cdst, dp.Ckey, dp.cbase, dp.cfill, dp.cseg, dp.csegi);
-            LAUNCH(m, FAM_NEWBORN, k_nb_place, kSMs * 8, B, 0, mc, fc, dp);
+            if (m->nb_redux) LAUNCH(m, FAM_NEWBORN, k_nb_place_redux, kSMs * 8, B, 0, mc, fc, dp);
+            else LAUNCH(m, FAM_NEWBORN, k_nb_place, kSMs * 8, B, 0, mc, fc, dp);
             newborn_ran = 1;
         }
     }
@@ -714,6 +724,10 @@ int dspmap_create(const dspmap_config *cfg, dspmap **out) {
         e = getenv("DSPMAP_CZ_TMA");
         m->cz_tma = e && *e && strcmp(e, "0") != 0;
         dp.cz_order = m->cz_tma ? cz_order_buf : nullptr;
+        e = getenv("DSPMAP_NB_REDUX");
+        m->nb_redux = e && *e && strcmp(e, "0") != 0;
+        e = getenv("DSPMAP_QUOT_FAST");
+        m->quot_fast = e && *e && strcmp(e, "0") != 0;
         e = getenv("DSPMAP_EST_THREAD");
         m->est_thread = e && *e && strcmp(e, "0") != 0;
     }
@@ -961,8 +975,13 @@ int dspmap_shard_phase(dspmap *m, int phase, int n, const float *d_pts, float px
         dp.tagged = d_tagged;
         LAUNCH(m, FAM_WEIGHT, k_shard_zero, kSMs * 2, B, 0, mc, fc, dp, 1);
         LAUNCH(m, FAM_WEIGHT, k_pair_eval, kSMs * 2, EVAL_THREADS, sizeof(float) * (DSP_LUT_HALF + 3 + (EVAL_THREADS / 32) * 32 * TILE_LD), mc, fc, dp, 2);
-        LAUNCH(m, FAM_WEIGHT, k_weight2, kSMs * 8, W2_THREADS, 0, mc, fc, dp);
-        LAUNCH(m, FAM_WEIGHT, k_weight2w, kSMs * 6, W2W_THREADS, 0, mc, fc, dp);
+        if (m->quot_fast) {
+            LAUNCH(m, FAM_WEIGHT, k_weight2q, kSMs * 8, W2_THREADS, 0, mc, fc, dp);
+            LAUNCH(m, FAM_WEIGHT, k_weight2wq, kSMs * 6, W2W_THREADS, 0, mc, fc, dp);
+        } else {
+            LAUNCH(m, FAM_WEIGHT, k_weight2, kSMs * 8, W2_THREADS, 0, mc, fc, dp);
+            LAUNCH(m, FAM_WEIGHT, k_weight2w, kSMs * 6, W2W_THREADS, 0, mc, fc, dp);
+        }
     } else if (phase == 4) {  // owners take their new weights; the newborn split reads them (dsp_dynamic.h:829-866)
         dp.tagged = d_tagged;
         LAUNCH(m, FAM_WEIGHT, k_shard_apply_weights, kSMs * 4, B, 0, mc, dp);
@@ -983,7 +1002,8 @@ int dspmap_shard_phase(dspmap *m, int phase, int n, const float *d_pts, float px
             LAUNCH(m, FAM_NEWBORN, k_nb_cand, grid_for((long long)fc.n_tagged * fc.nb_num, B), B, 0, mc, fc, dp, (u64)m->cfg.uniform_seed);
             LAUNCH(m, FAM_NEWBORN, k_group_owner, kSMs * 2, B, 0, dp, &dp.st->n_cand_owner, dp.cowner, dp.ccnt, dp.cbase, &dp.st->cand_top);
             LAUNCH(m, FAM_NEWBORN, k_group_scatter, kSMs * 4, B, 0, &dp.st->n_cand, dp.Cdst, dp.Ckey, dp.cbase, dp.cfill, dp.cseg, dp.csegi);
-            LAUNCH(m, FAM_NEWBORN, k_nb_place, kSMs * 8, B, 0, mc, fc, dp);
+            if (m->nb_redux) LAUNCH(m, FAM_NEWBORN, k_nb_place_redux, kSMs * 8, B, 0, mc, fc, dp);
+            else LAUNCH(m, FAM_NEWBORN, k_nb_place, kSMs * 8, B, 0, mc, fc, dp);
             newborn_ran = 1;
         }
         LAUNCH(m, FAM_RESAMPLE, k_voxel_list, grid_for(mc.V, B), B, 0, mc, dp);

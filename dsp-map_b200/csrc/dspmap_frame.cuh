@@ -1049,7 +1049,8 @@ __global__ void __launch_bounds__(CZT_THREADS) k_cz_chain_tma(MapConst mc, Frame
 #define W2_SWITCH 4096  // chunks of 32 particles: below, CTA-per-chunk (k_weight2); from here on, warp-per-chunk (k_weight2w)
 #define W2_THREADS 128
 #define W2_NP 100  // padded row length (np <= 99; odd stride: no bank conflicts in the chain)
-__global__ void __launch_bounds__(W2_THREADS) k_weight2(MapConst mc, FrameConst fc, DevPtrs dp) {
+template <bool QF>  // QF: quotients through dsp_quot's fast path (DSPMAP_QUOT_FAST=1)
+__global__ void __launch_bounds__(W2_THREADS) k_weight2_t(MapConst mc, FrameConst fc, DevPtrs dp) {
     pdl_enter();
     __shared__ float terms[2][32 * (W2_NP + 1)];
     __shared__ float czs[2][W2_NP];
@@ -1130,7 +1131,7 @@ __global__ void __launch_bounds__(W2_THREADS) k_weight2(MapConst mc, FrameConst 
                         if (f < nfl) {
                             const int r = np > 1 ? (int)__umulhi((unsigned)f, magic) : f;
                             const int z = f - r * np;
-                            terms[buf][r * ld + z] = fc.Pd * gpre[u] / czs[buf][z];
+                            terms[buf][r * ld + z] = dsp_quot<QF>(fc.Pd * gpre[u], czs[buf][z]);
                         }
                     }
                     // tiles of more than 768 terms (np > 24): further batches of eight loads in flight per thread
@@ -1147,7 +1148,7 @@ __global__ void __launch_bounds__(W2_THREADS) k_weight2(MapConst mc, FrameConst 
                             if (f < nfl) {
                                 const int r = np > 1 ? (int)__umulhi((unsigned)f, magic) : f;
                                 const int z = f - r * np;
-                                terms[buf][r * ld + z] = fc.Pd * g[u] / czs[buf][z];
+                                terms[buf][r * ld + z] = dsp_quot<QF>(fc.Pd * g[u], czs[buf][z]);
                             }
                         }
                     }
@@ -1176,7 +1177,8 @@ __global__ void __launch_bounds__(W2_THREADS) k_weight2(MapConst mc, FrameConst 
 // are read as coalesced rows (lane = point) into registers one sub-tile AHEAD of the one being consumed, staged through a
 // per-warp shared tile, and each lane adds its particle's row in (neighbour-table, bin) order.
 #define W2W_THREADS 256
-__global__ void __launch_bounds__(W2W_THREADS, 3) k_weight2w(MapConst mc, FrameConst fc, DevPtrs dp) {
+template <bool QF>
+__global__ void __launch_bounds__(W2W_THREADS, 3) k_weight2w_t(MapConst mc, FrameConst fc, DevPtrs dp) {
     pdl_enter();
     __shared__ float tiles[(W2W_THREADS / 32) * 32 * TILE_LD];
     __shared__ float czall[(W2W_THREADS / 32) * 32];
@@ -1244,7 +1246,7 @@ __global__ void __launch_bounds__(W2W_THREADS, 3) k_weight2w(MapConst mc, FrameC
             if (nsub) prefetch(nsub);  // in flight while the current sub-tile is consumed
             if (act) {
 #pragma unroll 4
-                for (int zl = 0; zl < cur; ++zl) sum += fc.Pd * tile[lane * TILE_LD + zl] / czs[zl];
+                for (int zl = 0; zl < cur; ++zl) sum += dsp_quot<QF>(fc.Pd * tile[lane * TILE_LD + zl], czs[zl]);
             }
             __syncwarp();
         }
@@ -1534,6 +1536,89 @@ __global__ void __launch_bounds__(256) k_nb_place(MapConst mc, FrameConst fc, De
                 dp.PA[a] = dp.CA[my_cand[q]];
                 dp.PB[a] = dp.CB[my_cand[q]];
             }
+        if (lane == 0) {
+            dp.M[d] = msk;
+            born += nfree;
+        }
+    }
+    if (lane == 0 && born) atomicAdd(&dp.st->n_born, born);
+}
+// The same placement with the warp-wide minimum taken by one REDUX instruction (experiment switch DSPMAP_NB_REDUX=1).  At
+// cfg2 a destination voxel has ~100 candidates and ~20 free slots: k_nb_place spends each of its ~20 rounds in a five-step
+// 64-bit shuffle reduction (ten dependent SHFLs, ~250 cycles of latency) on (key, position) pairs.  Keys are unique 32-bit
+// integers, so the minimum key alone identifies the winner: __reduce_min_sync gives it to every lane at once, and the lane
+// that holds it keeps the slot for its own candidate (no position has to travel).  Voxels without a free slot are left
+// before their keys are loaded.  Same selection, same slots: bit-identical.
+__global__ void __launch_bounds__(256) k_nb_place_redux(MapConst mc, FrameConst fc, DevPtrs dp) {
+    pdl_enter();
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int nown = dp.st->n_cand_owner;
+    int born = 0;
+    for (int o = warp; o < nown; o += nwarps) {
+        const int d = dp.cowner[o];
+        const int b = dp.cbase[d], c = dp.ccnt[d];
+        ulonglong2 msk = dp.M[d];
+        const int nfree = min(mask_free(mc, msk), c);
+        if (nfree == 0) continue;
+        if (c <= 256) {  // the usual case: the segment's keys live in registers for all rounds
+            unsigned K[8];
+            int slot_q[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int j = q * 32 + lane;
+                K[q] = j < c ? (unsigned)dp.cseg[b + j] : 0xffffffffu;
+                slot_q[q] = -1;
+            }
+            for (int r = 0; r < nfree; ++r) {
+                unsigned loc = K[0];
+#pragma unroll
+                for (int q = 1; q < 8; ++q) loc = min(loc, K[q]);
+                const unsigned best = __reduce_min_sync(FULLMASK, loc);  // r < nfree <= c: a valid key is left
+                const int slot = mask_nth_free(mc, msk, 0);
+                if (slot < 64) msk.x |= 1ull << slot; else msk.y |= 1ull << (slot - 64);
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (K[q] == best) { slot_q[q] = slot; K[q] = 0xffffffffu; }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (slot_q[q] >= 0) {
+                    const int cand = dp.csegi[b + q * 32 + lane];
+                    const int a = d * mc.S + slot_q[q];
+                    dp.PA[a] = dp.CA[cand];
+                    dp.PB[a] = dp.CB[cand];
+                }
+        } else {  // oversized segment: every round rescans it in global memory (rare)
+            long long last = -1;
+            int my_slot[4] = {-1, -1, -1, -1}, my_cand[4] = {0, 0, 0, 0};
+            for (int r = 0; r < nfree; ++r) {
+                u64 best = ~0ull;  // (key << 32) | position
+                for (int j = lane; j < c; j += 32) {
+                    const long long kj = dp.cseg[b + j];
+                    if (kj > last) best = min(best, ((u64)kj << 32) | (unsigned)j);
+                }
+                for (int sft = 16; sft > 0; sft >>= 1) best = min(best, __shfl_xor_sync(FULLMASK, best, sft));
+                last = (long long)(best >> 32);
+                const int slot = mask_nth_free(mc, msk, 0);
+                if (slot < 64) msk.x |= 1ull << slot; else msk.y |= 1ull << (slot - 64);
+                if (lane == (r & 31)) {
+                    const int q = r >> 5;
+                    const int cand = dp.csegi[b + (int)(best & 0xffffffffull)];
+                    if (q == 0) { my_slot[0] = slot; my_cand[0] = cand; }
+                    else if (q == 1) { my_slot[1] = slot; my_cand[1] = cand; }
+                    else if (q == 2) { my_slot[2] = slot; my_cand[2] = cand; }
+                    else { my_slot[3] = slot; my_cand[3] = cand; }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (my_slot[q] >= 0) {
+                    const int a = d * mc.S + my_slot[q];
+                    dp.PA[a] = dp.CA[my_cand[q]];
+                    dp.PB[a] = dp.CB[my_cand[q]];
+                }
+        }
         if (lane == 0) {
             dp.M[d] = msk;
             born += nfree;
