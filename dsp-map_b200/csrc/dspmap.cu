@@ -101,6 +101,7 @@ struct dspmap {
     // the recompute kernels (k_ck / k_weight) are launched only while the pair buffer may overflow
     bool fallback_armed = true;
     bool cz_wide = true;
+    bool norm_join_pending = false;  // k_norm runs on the side stream and has not been joined yet
     bool nb_prefix_done = false;  // this frame's first newborn kernels already ran on the side branch
     bool pdl = false;             // programmatic dependent launch of the frame's kernels (DSPMAP_PDL=1)
     bool cz_tma = false;          // C_z chains fed by a cp.async.bulk / mbarrier ring, heaviest pyramid first (DSPMAP_CZ_TMA=1)
@@ -405,7 +406,13 @@ int enqueue_frame_a(dspmap *m, const FrameConst &fc, const float *d_pts, const f
         size_t smem5 = sizeof(float) * (DSP_LUT_HALF + 3) + sizeof(float4) * (size_t)mc.NB * (mc.OBS - 1);
         int chunks = (mc.L + K5_THREADS - 1) / K5_THREADS;
         if (m->fallback_armed) LAUNCH(m, FAM_WEIGHT, k_weight, kSMs * 2, K5_THREADS, smem5, mc, fc, dp, chunks);
-        if (fc.stage_limit >= 3) CK(cudaStreamWaitEvent(m->stream, m->ev_join, 0));
+        // the normaliser is first read by k_nb_cand (w_new).  With the fast weight pass it is the longer branch, so its join
+        // moves behind the newborn kernels that do not need it (enqueue_frame_b); otherwise it is joined here
+        m->norm_join_pending = fc.stage_limit >= 3;
+        if (m->norm_join_pending && !m->quot_fast) {
+            CK(cudaStreamWaitEvent(m->stream, m->ev_join, 0));
+            m->norm_join_pending = false;
+        }
     }
     CK(cudaGetLastError());
     return DSPMAP_OK;
@@ -426,6 +433,10 @@ int enqueue_frame_b(dspmap *m, const FrameConst &fc, const float *d_tagged) {
             }
             LAUNCH(m, FAM_NEWBORN, k_nb_point1, grid_for((long long)fc.n_tagged * 32, B), B, 0, mc, fc, dp, 0);
             LAUNCH(m, FAM_NEWBORN, k_scan_small, 2, 1024, 0, ScanJobs{{ScanJob{dp.nvcnt, dp.nvoff, nullptr, 0, fc.n_tagged}, ScanJob{dp.nrcnt, dp.nroff, nullptr, 0, fc.n_tagged}, ScanJob{}}});
+            if (m->norm_join_pending) {  // k_norm (side stream) wrote w_new, which k_nb_cand reads
+                CK(cudaStreamWaitEvent(m->stream, m->ev_join, 0));
+                m->norm_join_pending = false;
+            }
             LAUNCH(m, FAM_NEWBORN, k_nb_cand, grid_for((long long)fc.n_tagged * fc.nb_num, B), B, 0, mc, fc, dp, (u64)m->cfg.uniform_seed);
             LAUNCH(m, FAM_NEWBORN, k_group_owner, kSMs * 2, B, 0, dp, &dp.st->n_cand_owner, dp.cowner, dp.ccnt, dp.cbase, &dp.st->cand_top);
             LAUNCH(m, FAM_NEWBORN, k_group_scatter, kSMs * 4, B, 0, &dp.st->n_cand, dp.Cdst, dp.Ckey, dp.cbase, dp.cfill, dp.cseg, dp.csegi);
@@ -437,6 +448,10 @@ int enqueue_frame_b(dspmap *m, const FrameConst &fc, const float *d_tagged) {
     if (fc.stage_limit >= 4) {
         LAUNCH(m, FAM_RESAMPLE, k_voxel_list, grid_for(mc.V, B), B, 0, mc, dp);
         LAUNCH(m, FAM_RESAMPLE, k_resample, kSMs * 8, 256, 0, mc, fc, dp);
+    }
+    if (m->norm_join_pending) {  // no newborn kernels this frame: k_norm must still be over before the next frame resets its outputs
+        CK(cudaStreamWaitEvent(m->stream, m->ev_join, 0));
+        m->norm_join_pending = false;
     }
     LAUNCH(m, FAM_CLEANUP, k_cleanup, kSMs * 2, B, 0, mc, fc, dp, newborn_ran, m->fallback_armed ? 1 : 0);
     // the state copy steers which optional kernels the next frame launches
