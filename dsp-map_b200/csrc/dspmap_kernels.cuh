@@ -183,11 +183,13 @@ __device__ __forceinline__ float dsp_pdf_f(const float *lut, float x, float mu, 
 }
 // (P_d * g) / C_z, rounded exactly as the IEEE division the reference performs (dsp_dynamic.h:776), without the division's
 // slow path.  nvcc's a / b is 7 instructions plus FCHK; FCHK sends zero and subnormal dividends (and quotients that may be
-// subnormal) to a ~30-80 instruction subroutine, and the warp pays for it as soon as ONE lane needs it.  Here most
-// dividends are exactly that: g is a product of three table values down to 3e-22 each, so for a particle a metre or more
-// from the point in two axes it is subnormal, in three axes zero.  With FAST:
+// subnormal) to a ~30-80 instruction subroutine, and the warp pays for it as soon as ONE lane needs it.  g is a product of
+// three table values down to 3e-22 each: for a particle a metre or more from the point in two axes it is subnormal, in three
+// axes zero.  Measured on the reference's state at cfg2 (18 M pairs): 0.3 % zero, 3.2 % subnormal, 3.9 % below 2^-100 — rare
+// per pair, but two warps in three hold at least one such lane.  With FAST:
 //   a == 0           ->  +0 (b is a positive finite C_z), no division at all;
-//   a < 2^-100       ->  the division is done in double and rounded to float once more.  For the quotient of two floats
+//   a < 2^-96        ->  (the fast path's residual a - q*b would lose bits below ~2^-102, which is what FCHK guards)
+//                        the division is done in double and rounded to float once more.  For the quotient of two floats
 //                        this double rounding is innocuous (53 >= 2 * 24 + 2 bits: a quotient that is not itself a
 //                        midpoint of the float grid — normal or subnormal — lies further than 2^-49 relative from one),
 //                        and float subnormals are normal doubles, so the double division stays on its own fast path;
@@ -198,7 +200,7 @@ template <bool FAST>
 __device__ __forceinline__ float dsp_quot(float a, float b) {
     if (FAST) {
         if (a == 0.f) return 0.f;
-        if (a < 7.888609052210118e-31f) return (float)((double)a / (double)b);
+        if (a < 1.262177448e-29f) return (float)((double)a / (double)b);  // 2^-96
     }
     return a / b;
 }
