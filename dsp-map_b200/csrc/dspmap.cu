@@ -105,6 +105,7 @@ struct dspmap {
     bool nb_prefix_done = false;  // this frame's first newborn kernels already ran on the side branch
     bool pdl = false;             // programmatic dependent launch of the frame's kernels (DSPMAP_PDL=1)
     bool cz_tma = false;          // C_z chains fed by a cp.async.bulk / mbarrier ring, heaviest pyramid first (DSPMAP_CZ_TMA=1)
+    bool g_col = false;           // column-major pair buffer: k_pair_eval_col / k_cz_chain_col / k_weight2<.., COL> (DSPMAP_G_COL=1)
     bool nb_redux = false;        // newborn placement with REDUX minima (DSPMAP_NB_REDUX=1)
     bool quot_fast = false;       // weight pass: zero / tiny dividends bypass the IEEE division's slow path (DSPMAP_QUOT_FAST=1)
     bool est_thread = false;      // velocity estimation on the helper thread, beside the enqueueing of the frame (DSPMAP_EST_THREAD=1)
@@ -224,7 +225,8 @@ inline void launch_kernel(bool pdl, cudaStream_t st, void (*kernel)(KArgs...), i
 
 const int kSMs = 148;
 // the two configurations of the C_z chain kernel (threads, floats per tile, rows per tile)
-const auto k_weight2 = &k_weight2_t<false>, k_weight2q = &k_weight2_t<true>;
+const auto k_weight2 = &k_weight2_t<false, false>, k_weight2q = &k_weight2_t<true, false>;
+const auto k_weight2c = &k_weight2_t<false, true>, k_weight2qc = &k_weight2_t<true, true>;  // column-major pair buffer
 const auto k_weight2w = &k_weight2w_t<false>, k_weight2wq = &k_weight2w_t<true>;
 const auto k_cz_narrow = &k_cz_chain<128, 4096, 128>;
 const auto k_cz_wide = &k_cz_chain<256, 8192, 128>;
@@ -380,12 +382,17 @@ int enqueue_frame_a(dspmap *m, const FrameConst &fc, const float *d_pts, const f
     LAUNCH(m, FAM_PYRAMID, k_pyr_sort, std::min(mc.P, kSMs * 3), 512, PYR_SORT_CAP * sizeof(u64), mc, dp, fc.Pd);
     CK(cudaStreamWaitEvent(m->stream, m->ev_join_obs, 0));
     if (fc.stage_limit >= 2) {
-        LAUNCH(m, FAM_CK, k_pair_prep, grid_for(mc.P, B), B, 0, mc, dp);
+        LAUNCH(m, FAM_CK, k_pair_prep, grid_for(mc.P, B), B, 0, mc, dp, m->g_col ? 1 : 0);
         LAUNCH(m, FAM_CK, k_scan_small, 2, 1024, 0, ScanJobs{{ScanJob{dp.pairs, dp.rowbase, nullptr, 0, mc.P}, ScanJob{dp.chunks, dp.chunk_off, nullptr, 0, mc.P}, ScanJob{}}});
+        if (m->g_col) {
+            LAUNCH(m, FAM_CK, k_pair_eval_col, kSMs * 4, EVAL_THREADS, sizeof(float) * (DSP_LUT_HALF + 3 + EVALC_KEYS), mc, fc, dp, 0);
+            LAUNCH(m, FAM_CK, k_cz_chain_col, std::min(mc.P, kSMs * 2), CZC_THREADS, CZC_SMEM_BYTES, mc, fc, dp);
+        } else {
         LAUNCH(m, FAM_CK, k_pair_eval, kSMs * 2, EVAL_THREADS, sizeof(float) * (DSP_LUT_HALF + 3 + (EVAL_THREADS / 32) * 32 * TILE_LD), mc, fc, dp, 0);
         if (m->cz_tma) LAUNCH(m, FAM_CK, k_cz_chain_tma, std::min(mc.P, kSMs * 2), CZT_THREADS, CZT_SMEM_BYTES, mc, fc, dp);
         else if (m->cz_wide) LAUNCH(m, FAM_CK, k_cz_wide, std::min(mc.P, kSMs * 3), 256, sizeof(float) * (2 * (8192 + 8) + 2 * 128), mc, fc, dp);
         else LAUNCH(m, FAM_CK, k_cz_narrow, std::min(mc.P, kSMs * 6), 128, sizeof(float) * (2 * (4096 + 8) + 2 * 128), mc, fc, dp);
+        }
         size_t smem4 = sizeof(float) * (DSP_LUT_HALF + 3 + K4_TERMS) + sizeof(float4) * (256 + mc.OBS);
         if (m->fallback_armed) LAUNCH(m, FAM_CK, k_ck, std::min(mc.P, kSMs * 2), K4_THREADS, smem4, mc, fc, dp);  // returns at once when the pair buffer is used
         if (fc.stage_limit >= 3) {  // the newborn normaliser is one long serial chain: run it beside the weight pass
@@ -396,7 +403,10 @@ int enqueue_frame_a(dspmap *m, const FrameConst &fc, const float *d_pts, const f
             ++m->launches_frame;
             CK(cudaEventRecord(m->ev_join, m->side));
         }
-        if (m->quot_fast) {
+        if (m->g_col) {  // the CTA-per-chunk kernel takes every frame (the warp-per-chunk variant reads the row-major buffer)
+            if (m->quot_fast) LAUNCH(m, FAM_WEIGHT, k_weight2qc, kSMs * 8, W2_THREADS, 0, mc, fc, dp);
+            else LAUNCH(m, FAM_WEIGHT, k_weight2c, kSMs * 8, W2_THREADS, 0, mc, fc, dp);
+        } else if (m->quot_fast) {
             LAUNCH(m, FAM_WEIGHT, k_weight2q, kSMs * 8, W2_THREADS, 0, mc, fc, dp);
             LAUNCH(m, FAM_WEIGHT, k_weight2wq, kSMs * 6, W2W_THREADS, 0, mc, fc, dp);
         } else {
@@ -733,12 +743,16 @@ int dspmap_create(const dspmap_config *cfg, dspmap **out) {
     CK(cudaFuncSetAttribute(k_pair_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     CK(cudaFuncSetAttribute(k_cz_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
     CK(cudaFuncSetAttribute(k_cz_chain_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, CZT_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(k_cz_chain_col, cudaFuncAttributeMaxDynamicSharedMemorySize, CZC_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(k_pair_eval_col, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * (DSP_LUT_HALF + 3 + EVALC_KEYS))));
     {   // experiment switch, off unless DSPMAP_PDL is set to something other than 0
         const char *e = getenv("DSPMAP_PDL");
         m->pdl = e && *e && strcmp(e, "0") != 0;
         e = getenv("DSPMAP_CZ_TMA");
         m->cz_tma = e && *e && strcmp(e, "0") != 0;
-        dp.cz_order = m->cz_tma ? cz_order_buf : nullptr;
+        e = getenv("DSPMAP_G_COL");
+        m->g_col = e && *e && strcmp(e, "0") != 0;
+        dp.cz_order = (m->cz_tma || m->g_col) ? cz_order_buf : nullptr;
         e = getenv("DSPMAP_NB_REDUX");
         m->nb_redux = e && *e && strcmp(e, "0") != 0;
         e = getenv("DSPMAP_QUOT_FAST");
@@ -915,6 +929,7 @@ int dspmap_shard_config(dspmap *m, int rank, int nranks, float *xsend, float *xr
     dp.nst_shared = shared;                          // newborn split first, then the new weights by global list index
     dp.NW = shared + m->max_points;
     m->fallback_armed = false;  // sharded frames always use the pair buffer (checked: overflow flag otherwise)
+    m->g_col = false;           // the sharded phases launch the row-major observation kernels
     return DSPMAP_OK;
 }
 int dspmap_shard_gather_records(dspmap *m, int records) {
@@ -979,7 +994,7 @@ int dspmap_shard_phase(dspmap *m, int phase, int n, const float *d_pts, float px
         LAUNCH(m, FAM_PYRAMID, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{dp.pcount, dp.poff, nullptr, 0, mc.P}, ScanJob{}, ScanJob{}}});
         LAUNCH(m, FAM_PYRAMID, k_shard_fov_gathered, kSMs * 8, B, 0, mc, dp, 1);
         LAUNCH(m, FAM_PYRAMID, k_pyr_sort, std::min(mc.P, kSMs * 3), 512, PYR_SORT_CAP * sizeof(u64), mc, dp, fc.Pd);
-        LAUNCH(m, FAM_CK, k_pair_prep, grid_for(mc.P, B), B, 0, mc, dp);
+        LAUNCH(m, FAM_CK, k_pair_prep, grid_for(mc.P, B), B, 0, mc, dp, m->g_col ? 1 : 0);
         LAUNCH(m, FAM_CK, k_scan_small, 2, 1024, 0, ScanJobs{{ScanJob{dp.pairs, dp.rowbase, nullptr, 0, mc.P}, ScanJob{dp.chunks, dp.chunk_off, nullptr, 0, mc.P}, ScanJob{}}});
         LAUNCH(m, FAM_CK, k_shard_zero, kSMs * 2, B, 0, mc, fc, dp, 0);
         LAUNCH(m, FAM_CK, k_pair_eval, kSMs * 2, EVAL_THREADS, sizeof(float) * (DSP_LUT_HALF + 3 + (EVAL_THREADS / 32) * 32 * TILE_LD), mc, fc, dp, 1);

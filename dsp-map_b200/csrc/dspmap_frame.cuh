@@ -735,7 +735,9 @@ __global__ void __launch_bounds__(K5_THREADS) k_weight(MapConst mc, FrameConst f
 //           particle in the concatenation of i's neighbour lists (neighbour-table order, list order)
 //   k_cz_chain reads a row sequentially (j); k_weight2 reads it with consecutive lanes = consecutive particles.
 // ------------------------------------------------------------------------------------------------------------
-__global__ void k_pair_prep(MapConst mc, DevPtrs dp) {
+// col != 0 (DSPMAP_G_COL): pyramid i's block of G is column-major — np + 1 columns (its points, then P_d * w) of
+// tl = round-up-to-4(rows) floats each, so every column and every 8-row tile of it starts on a 16-byte boundary.
+__global__ void k_pair_prep(MapConst mc, DevPtrs dp, int col) {
     pdl_enter();
     unsigned long long local = 0ull;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < mc.P; i += gridDim.x * blockDim.x) {
@@ -746,7 +748,8 @@ __global__ void k_pair_prep(MapConst mc, DevPtrs dp) {
             c += dp.plen[dp.nbr[i * mc.NBW + 1 + ns]];
         }
         dp.totlen[i] = c;
-        const unsigned long long pr = (unsigned long long)np * (unsigned long long)c;
+        unsigned long long pr = (unsigned long long)np * (unsigned long long)c;
+        if (col) pr = np > 0 ? (unsigned long long)(np + 1) * (unsigned long long)((c + 3) & ~3) : 0ull;
         dp.pairs[i] = pr > 0x3fffffffull ? 0x3fffffff : (int)pr;
         local += pr;
         dp.chunks[i] = (dp.plen[i] + 31) >> 5;
@@ -928,6 +931,148 @@ __global__ void __launch_bounds__(CZ_THREADS) k_cz_chain(MapConst mc, FrameConst
         }
     }
 }
+// ------------------------------------------------------------------------------------------------------------
+// Column-major pair buffer (experiment switch DSPMAP_G_COL=1).  Pyramid i's block of G holds np + 1 columns of
+// tl = round-up-to-4(rows) floats: column z < np = g(particle j; point z) down the concatenation j of i's neighbour
+// lists, column np = P_d * w_j.  What it buys:
+//   * k_pair_eval_col: lanes are particles, so the 32 values of one point are one coalesced store — no transposing
+//     tile in shared memory (the row-major kernel spends a third of its shared-memory traffic on it);
+//   * k_cz_chain_col: every column is contiguous and 16-byte aligned, so the chain thread of point z streams ITS column
+//     through shared memory with cp.async.bulk and reads it four rows per LDS.128 — 10 instructions per 4 rows instead of
+//     ~22, which leaves the 4-cycle dependent FADD as the only limit of the longest chain (4 559 rows at cfg2);
+//   * k_weight2 (COL): a flat index is (point f / 32, particle f % 32): no division by np per element.
+// Sums are formed from the same terms in the same order: results are bit-identical.
+// ------------------------------------------------------------------------------------------------------------
+#define EVALC_KEYS 2048  // shared-memory room for cz_build_order (== CZ_ORDER_MAX)
+__global__ void __launch_bounds__(EVAL_THREADS) k_pair_eval_col(MapConst mc, FrameConst fc, DevPtrs dp, int mode) {
+    extern __shared__ float sm[];
+    float *lut = sm;
+    pdl_trigger();
+    for (int i = threadIdx.x; i < DSP_LUT_HALF; i += blockDim.x) lut[i] = dp.lut[i];  // constant after create: staged before the wait
+    pdl_wait();
+    if (!use_pair_buffer(mc, dp)) return;
+    if (dp.cz_order && blockIdx.x == 0) cz_build_order(mc, dp, reinterpret_cast<int *>(sm + (DSP_LUT_HALF + 3)));
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int nchunks = dp.chunk_off[mc.P];
+    const int items = nchunks * mc.NB;
+    for (;;) {
+        int it = 0;
+        if (lane == 0) it = atomicAdd(mode == 2 ? &dp.st->work_eval2 : &dp.st->work_eval, 1);
+        it = __shfl_sync(FULLMASK, it, 0);
+        if (it >= items) break;
+        const int c = it / mc.NB, ns = it - c * mc.NB;
+        if (mode == 2 && c % mc.nranks != mc.rank) continue;
+        const int a = chunk_to_pyramid(dp.chunk_off, mc.P, c);
+        if (ns >= dp.nbr[a * mc.NBW]) continue;
+        const int i = dp.nbr[a * mc.NBW + 1 + ns];  // a point pyramid that sees pyramid a
+        if (mode == 1 && i % mc.nranks != mc.rank) continue;
+        const int np = min(dp.obs_cnt[i], mc.OBS - 1);
+        if (np == 0) continue;
+        const int k0 = (c - dp.chunk_off[a]) << 5;
+        const int nrows = min(32, dp.plen[a] - k0);
+        const bool mine = lane < nrows;
+        const float4 p = mine ? dp.LP[dp.poff[a] + k0 + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const size_t tl = (size_t)((dp.totlen[i] + 3) & ~3);
+        float *gb = dp.G + (size_t)dp.rowbase[i] + (size_t)(dp.cum[i * mc.NBW + nb_index_of(mc, dp, i, a)] + k0) + lane;
+        if (mine) gb[(size_t)np * tl] = dp.PW[dp.poff[a] + k0 + lane];  // the weight column (P_d * w, as k_pyr_sort rounded it)
+        const float4 *zs = dp.OBSP + (size_t)i * mc.OBS;
+#pragma unroll 2
+        for (int z = 0; z < np; ++z) {
+            const float4 o = zs[z];
+            const float g = dsp_pdf_f(lut, p.x, o.x, fc) * dsp_pdf_f(lut, p.y, o.y, fc) * dsp_pdf_f(lut, p.z, o.z, fc);
+            if (mine) gb[(size_t)z * tl] = g;
+        }
+    }
+}
+#define CZC_STAGES 6
+#define CZC_TILE 4096   // floats per stage: (np + 1) columns of RT + 4
+#define CZC_RT_MAX 512
+#define CZC_CHAIN_WARPS 4
+#define CZC_THREADS (32 * (CZC_CHAIN_WARPS + 1))
+#define CZC_SMEM_BYTES (CZC_STAGES * CZC_TILE * 4 + 2 * CZC_STAGES * 8)
+__global__ void __launch_bounds__(CZC_THREADS) k_cz_chain_col(MapConst mc, FrameConst fc, DevPtrs dp) {
+    pdl_enter();
+    extern __shared__ __align__(128) float czcsm[];
+    float *stages = czcsm;
+    uint64_t *full = reinterpret_cast<uint64_t *>(stages + CZC_STAGES * CZC_TILE);
+    uint64_t *empty = full + CZC_STAGES;
+    __shared__ int s_item;
+    if (!use_pair_buffer(mc, dp)) return;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) {
+        for (int s = 0; s < CZC_STAGES; ++s) {
+            cuda::ptx::mbarrier_init(&full[s], 1);                  // the producer's arrive.expect_tx; completes with the bytes
+            cuda::ptx::mbarrier_init(&empty[s], CZC_CHAIN_WARPS);   // one arrival per chain warp
+        }
+        cuda::ptx::fence_mbarrier_init(cuda::ptx::sem_release, cuda::ptx::scope_cluster);
+        cuda::ptx::fence_proxy_async(cuda::ptx::space_shared);
+    }
+    __syncthreads();
+    const float enb = fc.nb_weight * (float)dp.st->n_valid * (float)fc.nb_num;  // :292
+    const float add_k = enb + fc.kappa;
+    unsigned it = 0;  // stages this CTA has been through: the producer warp and the chain warps walk the same sequence
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_item = atomicAdd(&dp.st->work_k4, 1);
+        __syncthreads();
+        const int wi = s_item;
+        if (wi >= mc.P) break;
+        const int i = dp.cz_order ? dp.cz_order[wi] : wi;
+        const int np = min(dp.obs_cnt[i], mc.OBS - 1);
+        if (np == 0) continue;
+        if (mc.sharded && i % mc.nranks != mc.rank) continue;  // another rank computes this pyramid's C_z
+        const int rows = dp.totlen[i];
+        const size_t tl = (size_t)((rows + 3) & ~3);
+        const int ncol = np + 1;
+        // rows per stage: a multiple of 8 with (RT + 4) / 4 odd, so that the LDS.128 of eight neighbouring columns fall into
+        // eight different 16-byte bank groups
+        const int RT = min(CZC_RT_MAX, (CZC_TILE / ncol - 4) & ~7);
+        const int stride = RT + 4;
+        const float *gsrc = dp.G + (size_t)dp.rowbase[i];
+        float acc = 0.f;
+        for (int j0 = 0; j0 < rows; j0 += RT, ++it) {
+            const int cur = min(RT, rows - j0), cur4 = (cur + 3) & ~3;
+            const int s = (int)(it % CZC_STAGES);
+            const unsigned par = (it / CZC_STAGES) & 1u;
+            float *st = stages + s * CZC_TILE;
+            if (wid == CZC_CHAIN_WARPS) {  // producer warp: lane c feeds columns c, c + 32, ...
+                if (lane == 0) {
+                    while (!cuda::ptx::mbarrier_try_wait_parity(&empty[s], par ^ 1u)) {}  // a fresh barrier passes at once
+                    cuda::ptx::mbarrier_arrive_expect_tx(cuda::ptx::sem_release, cuda::ptx::scope_cta, cuda::ptx::space_shared, &full[s],
+                                                         (unsigned)(ncol * cur4 * 4));
+                }
+                __syncwarp();
+                for (int c = lane; c < ncol; c += 32)
+                    cuda::ptx::cp_async_bulk(cuda::ptx::space_cluster, cuda::ptx::space_global, st + c * stride, gsrc + (size_t)c * tl + j0,
+                                             (unsigned)(cur4 * 4), &full[s]);
+                __syncwarp();
+            } else {
+                while (!cuda::ptx::mbarrier_try_wait_parity(&full[s], par)) {}
+                if (tid < np) {  // the chain: (P_d * w) * g added in list order, one fp32 add per term
+                    const float4 *g4 = reinterpret_cast<const float4 *>(st + tid * stride);
+                    const float4 *w4 = reinterpret_cast<const float4 *>(st + np * stride);
+                    const int nq = cur >> 2;
+#pragma unroll 4
+                    for (int q = 0; q < nq; ++q) {
+                        float4 g = g4[q];
+                        const float4 w = w4[q];
+                        g.x *= w.x; g.y *= w.y; g.z *= w.z; g.w *= w.w;
+                        acc += g.x; acc += g.y; acc += g.z; acc += g.w;
+                    }
+                    for (int jj = nq << 2; jj < cur; ++jj) acc += st[np * stride + jj] * st[tid * stride + jj];
+                }
+                __syncwarp();
+                if (lane == 0) cuda::ptx::mbarrier_arrive(&empty[s]);
+            }
+        }
+        if (tid < np) {
+            acc += add_k;
+            dp.CZ[i * mc.OBS + tid] = acc;
+            dp.INV[dp.obs_capoff[i] + tid] = 1.f / acc;  // for the newborn normaliser (:802)
+        }
+    }
+}
 // C_z with a bulk-copy ring (experiment switch DSPMAP_CZ_TMA=1).  The chain of one observation point is serial — rows x 4
 // cycles at best — so the kernel lasts as long as its heaviest pyramid, and the double-buffered version above spends half
 // of that waiting: one tile of lead (<= 128 rows, ~500 cycles of chain) is less than the L2 round trip of the next tile.
@@ -1049,7 +1194,9 @@ __global__ void __launch_bounds__(CZT_THREADS) k_cz_chain_tma(MapConst mc, Frame
 #define W2_SWITCH 4096  // chunks of 32 particles: below, CTA-per-chunk (k_weight2); from here on, warp-per-chunk (k_weight2w)
 #define W2_THREADS 128
 #define W2_NP 100  // padded row length (np <= 99; odd stride: no bank conflicts in the chain)
-template <bool QF>  // QF: quotients through dsp_quot's fast path (DSPMAP_QUOT_FAST=1)
+// QF: quotients through dsp_quot's fast path (DSPMAP_QUOT_FAST=1); COL: column-major pair buffer (DSPMAP_G_COL=1) — the
+// chunk's values for one point are 32 consecutive floats, a flat index f means (point f / 32, particle f % 32)
+template <bool QF, bool COL>
 __global__ void __launch_bounds__(W2_THREADS) k_weight2_t(MapConst mc, FrameConst fc, DevPtrs dp) {
     pdl_enter();
     __shared__ float terms[2][32 * (W2_NP + 1)];
@@ -1058,7 +1205,7 @@ __global__ void __launch_bounds__(W2_THREADS) k_weight2_t(MapConst mc, FrameCons
     if (!use_pair_buffer(mc, dp)) return;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int nchunks = dp.chunk_off[mc.P];
-    if (nchunks >= W2_SWITCH) return;  // many chunks: k_weight2w takes the frame
+    if (!COL && nchunks >= W2_SWITCH) return;  // many chunks: k_weight2w takes the frame (row-major buffer only)
     for (;;) {
         __syncthreads();
         if (tid == 0) s_item = atomicAdd(&dp.st->work_w2, 1);
@@ -1090,19 +1237,30 @@ __global__ void __launch_bounds__(W2_THREADS) k_weight2_t(MapConst mc, FrameCons
         const int PSTR = W2_THREADS - 32;
         float gpre[8], czpre0 = 1.f, czpre1 = 1.f;
         const float *gb_n = nullptr;
-        int nfl_n = 0;
+        int nfl_n = 0, tl_n = 0;
+        // address of flat element f of the tile at g (stride tl between the points' columns when COL); false: no such element
+        auto elem = [&](const float *g, int tl, int nfl, int f, const float *&addr) -> bool {
+            if (COL) {
+                addr = g + (size_t)(f >> 5) * tl + (f & 31);
+                return f < nfl && (f & 31) < nrows;
+            }
+            addr = g + f;
+            return f < nfl;
+        };
         auto prefetch = [&](int ns) {
             nfl_n = 0;
             if (ns >= nn) return;
             const int b = dp.nbr[a * mc.NBW + 1 + ns];
             const int np = min(dp.obs_cnt[b], mc.OBS - 1);
             if (np == 0) return;
-            gb_n = dp.G + (size_t)dp.rowbase[b] + (size_t)(dp.cum[b * mc.NBW + nb_index_of(mc, dp, b, a)] + k0) * np;
-            nfl_n = nrows * np;
+            const int jb = dp.cum[b * mc.NBW + nb_index_of(mc, dp, b, a)] + k0;
+            gb_n = dp.G + (size_t)dp.rowbase[b] + (COL ? (size_t)jb : (size_t)jb * np);
+            tl_n = COL ? ((dp.totlen[b] + 3) & ~3) : 0;
+            nfl_n = COL ? 32 * np : nrows * np;
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                const int f = t96 + u * PSTR;
-                gpre[u] = f < nfl_n ? __ldg(gb_n + f) : 0.f;
+                const float *ad;
+                gpre[u] = elem(gb_n, tl_n, nfl_n, t96 + u * PSTR, ad) ? __ldg(ad) : 0.f;
             }
             const float *cz = dp.CZ + (size_t)b * mc.OBS;
             czpre0 = t96 < np ? cz[t96] : 1.f;
@@ -1122,15 +1280,21 @@ __global__ void __launch_bounds__(W2_THREADS) k_weight2_t(MapConst mc, FrameCons
                     if (t96 < np) czs[buf][t96] = czpre0;
                     if (t96 + PSTR < np) czs[buf][t96 + PSTR] = czpre1;
                     const float *gb = gb_n;
-                    const int nfl = nfl_n;
+                    const int nfl = nfl_n, tl = tl_n;
                     asm volatile("bar.sync 1, 96;" ::: "memory");  // only the three producer warps
                     const unsigned magic = np > 1 ? 0xffffffffu / (unsigned)np + 1u : 0u;  // exact f / np for f < 65536
+                    // (particle row r, point z) of flat element f
+                    auto row_col = [&](int f, int &r, int &z) {
+                        if (COL) { r = f & 31; z = f >> 5; }
+                        else { r = np > 1 ? (int)__umulhi((unsigned)f, magic) : f; z = f - r * np; }
+                    };
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
                         const int f = t96 + u * PSTR;
-                        if (f < nfl) {
-                            const int r = np > 1 ? (int)__umulhi((unsigned)f, magic) : f;
-                            const int z = f - r * np;
+                        const float *ad;
+                        if (elem(gb, tl, nfl, f, ad)) {
+                            int r, z;
+                            row_col(f, r, z);
                             terms[buf][r * ld + z] = dsp_quot<QF>(fc.Pd * gpre[u], czs[buf][z]);
                         }
                     }
@@ -1139,15 +1303,16 @@ __global__ void __launch_bounds__(W2_THREADS) k_weight2_t(MapConst mc, FrameCons
                         float g[8];
 #pragma unroll
                         for (int u = 0; u < 8; ++u) {
-                            const int f = f0 + u * PSTR;
-                            g[u] = f < nfl ? __ldg(gb + f) : 0.f;
+                            const float *ad;
+                            g[u] = elem(gb, tl, nfl, f0 + u * PSTR, ad) ? __ldg(ad) : 0.f;
                         }
 #pragma unroll
                         for (int u = 0; u < 8; ++u) {
                             const int f = f0 + u * PSTR;
-                            if (f < nfl) {
-                                const int r = np > 1 ? (int)__umulhi((unsigned)f, magic) : f;
-                                const int z = f - r * np;
+                            const float *ad;
+                            if (elem(gb, tl, nfl, f, ad)) {
+                                int r, z;
+                                row_col(f, r, z);
                                 terms[buf][r * ld + z] = dsp_quot<QF>(fc.Pd * g[u], czs[buf][z]);
                             }
                         }
