@@ -105,6 +105,7 @@ struct dspmap {
     bool nb_prefix_done = false;  // this frame's first newborn kernels already ran on the side branch
     bool pdl = false;             // programmatic dependent launch of the frame's kernels (DSPMAP_PDL=1)
     bool cz_tma = false;          // C_z chains fed by a cp.async.bulk / mbarrier ring, heaviest pyramid first (DSPMAP_CZ_TMA=1)
+    bool cz_staged = false;       // k_cz_chain with the neighbour table staged per pyramid (DSPMAP_CZ_STAGED=1)
     bool g_col = false;           // column-major pair buffer: k_pair_eval_col / k_cz_chain_col / k_weight2<.., COL> (DSPMAP_G_COL=1)
     bool nb_redux = false;        // newborn placement with REDUX minima (DSPMAP_NB_REDUX=1)
     bool quot_fast = false;       // weight pass: zero / tiny dividends bypass the IEEE division's slow path (DSPMAP_QUOT_FAST=1)
@@ -230,6 +231,7 @@ const auto k_weight2c = &k_weight2_t<false, true>, k_weight2qc = &k_weight2_t<tr
 const auto k_weight2w = &k_weight2w_t<false>, k_weight2wq = &k_weight2w_t<true>;
 const auto k_cz_narrow = &k_cz_chain<128, 4096, 128>;
 const auto k_cz_wide = &k_cz_chain<256, 8192, 128>;
+const auto k_cz_wide_staged = &k_cz_chain<256, 8192, 128, true>;
 inline int grid_for(long long n, int block, int max_blocks = kSMs * 8) {
     long long g = (n + block - 1) / block;
     if (g < 1) g = 1;
@@ -390,6 +392,7 @@ int enqueue_frame_a(dspmap *m, const FrameConst &fc, const float *d_pts, const f
         } else {
         LAUNCH(m, FAM_CK, k_pair_eval, kSMs * 2, EVAL_THREADS, sizeof(float) * (DSP_LUT_HALF + 3 + (EVAL_THREADS / 32) * 32 * TILE_LD), mc, fc, dp, 0);
         if (m->cz_tma) LAUNCH(m, FAM_CK, k_cz_chain_tma, std::min(mc.P, kSMs * 2), CZT_THREADS, CZT_SMEM_BYTES, mc, fc, dp);
+        else if (m->cz_staged) LAUNCH(m, FAM_CK, k_cz_wide_staged, std::min(mc.P, kSMs * 3), 256, sizeof(float) * (2 * (8192 + 8) + 2 * 128), mc, fc, dp);
         else if (m->cz_wide) LAUNCH(m, FAM_CK, k_cz_wide, std::min(mc.P, kSMs * 3), 256, sizeof(float) * (2 * (8192 + 8) + 2 * 128), mc, fc, dp);
         else LAUNCH(m, FAM_CK, k_cz_narrow, std::min(mc.P, kSMs * 6), 128, sizeof(float) * (2 * (4096 + 8) + 2 * 128), mc, fc, dp);
         }
@@ -742,6 +745,7 @@ int dspmap_create(const dspmap_config *cfg, dspmap **out) {
     CK(cudaFuncSetAttribute(k_ck, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CK(cudaFuncSetAttribute(k_pair_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     CK(cudaFuncSetAttribute(k_cz_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    CK(cudaFuncSetAttribute(k_cz_wide_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
     CK(cudaFuncSetAttribute(k_cz_chain_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, CZT_SMEM_BYTES));
     CK(cudaFuncSetAttribute(k_cz_chain_col, cudaFuncAttributeMaxDynamicSharedMemorySize, CZC_SMEM_BYTES));
     CK(cudaFuncSetAttribute(k_pair_eval_col, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * (DSP_LUT_HALF + 3 + EVALC_KEYS))));
@@ -750,6 +754,8 @@ int dspmap_create(const dspmap_config *cfg, dspmap **out) {
         m->pdl = e && *e && strcmp(e, "0") != 0;
         e = getenv("DSPMAP_CZ_TMA");
         m->cz_tma = e && *e && strcmp(e, "0") != 0;
+        e = getenv("DSPMAP_CZ_STAGED");
+        m->cz_staged = e && *e && strcmp(e, "0") != 0;
         e = getenv("DSPMAP_G_COL");
         m->g_col = e && *e && strcmp(e, "0") != 0;
         dp.cz_order = (m->cz_tma || m->g_col) ? cz_order_buf : nullptr;
@@ -999,6 +1005,7 @@ int dspmap_shard_phase(dspmap *m, int phase, int n, const float *d_pts, float px
         LAUNCH(m, FAM_CK, k_shard_zero, kSMs * 2, B, 0, mc, fc, dp, 0);
         LAUNCH(m, FAM_CK, k_pair_eval, kSMs * 2, EVAL_THREADS, sizeof(float) * (DSP_LUT_HALF + 3 + (EVAL_THREADS / 32) * 32 * TILE_LD), mc, fc, dp, 1);
         if (m->cz_tma) LAUNCH(m, FAM_CK, k_cz_chain_tma, std::min(mc.P, kSMs * 2), CZT_THREADS, CZT_SMEM_BYTES, mc, fc, dp);
+        else if (m->cz_staged) LAUNCH(m, FAM_CK, k_cz_wide_staged, std::min(mc.P, kSMs * 3), 256, sizeof(float) * (2 * (8192 + 8) + 2 * 128), mc, fc, dp);
         else if (m->cz_wide) LAUNCH(m, FAM_CK, k_cz_wide, std::min(mc.P, kSMs * 3), 256, sizeof(float) * (2 * (8192 + 8) + 2 * 128), mc, fc, dp);
         else LAUNCH(m, FAM_CK, k_cz_narrow, std::min(mc.P, kSMs * 6), 128, sizeof(float) * (2 * (4096 + 8) + 2 * 128), mc, fc, dp);
     } else if (phase == 3) {

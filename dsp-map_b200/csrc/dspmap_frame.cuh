@@ -850,13 +850,18 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_pair_eval(MapConst mc, FrameCo
 // memory (double-buffered cp.async); thread z < np adds its column in list order: one fp32 chain per point.
 // Measured on B200 (cfg2): 256 threads with 2 x 32 KB tiles (3 CTAs / SM) 54 us, 128 threads with 2 x 16 KB tiles
 // (6 CTAs / SM, every pyramid resident at once) 64 us — the longer tiles amortise the per-tile barrier better.
-template <int CZ_THREADS, int CZ_TILE, int CZ_JT>
+// STG (experiment switch DSPMAP_CZ_STAGED=1): the pyramid's neighbour table (list lengths and offsets) is read into shared
+// memory once per pyramid.  In the default instantiation every tile re-walks nbr -> plen and nbr -> poff in global memory:
+// four dependent L2 round trips (~1 000 cycles) in front of a tile whose chain takes ~700 (profiles/r01_top_kernels.md).
+#define CZ_STG_MAXNB 128
+template <int CZ_THREADS, int CZ_TILE, int CZ_JT, bool STG = false>
 __global__ void __launch_bounds__(CZ_THREADS) k_cz_chain(MapConst mc, FrameConst fc, DevPtrs dp) {
     pdl_enter();
     extern __shared__ float czsm[];
     float *tile0 = czsm, *tile1 = czsm + CZ_TILE + 8;  // + room for the alignment phase
     float *pws0 = czsm + 2 * (CZ_TILE + 8), *pws1 = pws0 + CZ_JT;
     __shared__ int s_item;
+    __shared__ int s_len[STG ? CZ_STG_MAXNB : 1], s_off[STG ? CZ_STG_MAXNB : 1];
     if (!use_pair_buffer(mc, dp)) return;
     const float enb = fc.nb_weight * (float)dp.st->n_valid * (float)fc.nb_num;  // :292
     const float add_k = enb + fc.kappa;
@@ -873,15 +878,26 @@ __global__ void __launch_bounds__(CZ_THREADS) k_cz_chain(MapConst mc, FrameConst
         const int nn = dp.nbr[i * mc.NBW];
         const int JT = min(CZ_JT, CZ_TILE / np);
         const float *gsrc = dp.G + (size_t)dp.rowbase[i];
+        const bool staged = STG && nn <= CZ_STG_MAXNB;
+        if (STG) {  // (the barrier at the top of the loop keeps the previous pyramid's readers ahead of these writes)
+            if (staged && tid < nn) {
+                const int b = dp.nbr[i * mc.NBW + 1 + tid];
+                s_len[tid] = dp.plen[b];
+                s_off[tid] = dp.poff[b];
+            }
+            __syncthreads();
+        }
+        auto len_of = [&](int k) { return staged ? s_len[k] : dp.plen[dp.nbr[i * mc.NBW + 1 + k]]; };
+        auto off_of = [&](int k) { return staged ? s_off[k] : dp.poff[dp.nbr[i * mc.NBW + 1 + k]]; };
         // tile iterator over (neighbour ns, particle offset k0); the "issue" state runs one tile ahead of the consumer
-        int ins = 0, ik0 = 0, iln = nn > 0 ? dp.plen[dp.nbr[i * mc.NBW + 1]] : 0;
+        int ins = 0, ik0 = 0, iln = nn > 0 ? len_of(0) : 0;
         int ph0 = 0, ph1 = 0;
         const float *ig = gsrc;
         auto issue = [&](int buf) -> int {  // returns the number of particle rows of the issued tile, 0 when exhausted
             while (ins < nn && ik0 >= iln) {
                 ++ins;
                 ik0 = 0;
-                iln = ins < nn ? dp.plen[dp.nbr[i * mc.NBW + 1 + ins]] : 0;
+                iln = ins < nn ? len_of(ins) : 0;
             }
             if (ins >= nn) return 0;
             const int cur = min(JT, iln - ik0), nfl = cur * np;
@@ -892,7 +908,7 @@ __global__ void __launch_bounds__(CZ_THREADS) k_cz_chain(MapConst mc, FrameConst
             const int nq = (ph + nfl + 3) >> 2;
             for (int q = tid; q < nq; q += CZ_THREADS) __pipeline_memcpy_async(t + 4 * q, src + 4 * q, 16);
             if (buf) ph1 = ph; else ph0 = ph;
-            if (tid < cur) __pipeline_memcpy_async((buf ? pws1 : pws0) + tid, dp.PW + dp.poff[dp.nbr[i * mc.NBW + 1 + ins]] + ik0 + tid, 4);
+            if (tid < cur) __pipeline_memcpy_async((buf ? pws1 : pws0) + tid, dp.PW + off_of(ins) + ik0 + tid, 4);
             ig += nfl;
             ik0 += cur;
             return cur;
