@@ -83,6 +83,13 @@ struct dspmap {
     float *d_xyz = nullptr, *d_future = nullptr;
     int occ_blocks = 0;
     int occ_guess = 4096;  // occupied voxels copied along with the count (twice the last count): one round trip, not two
+    // sparse copy-out of the future grid into a registered (page-locked) caller buffer (DSPMAP_SPARSE_FUTURE=1)
+    bool sparse_future = false;
+    int *d_fcnt = nullptr, *d_foff = nullptr, *d_fidx = nullptr, *d_nf = nullptr, *h_fidx = nullptr, *h_nf = nullptr;
+    float *d_fval = nullptr, *h_fval = nullptr;
+    int fut_guess = 8192;                 // rows copied along with their count
+    float *sparse_ptr = nullptr;          // the caller buffer that holds exactly the previous call's result
+    std::vector<int> sparse_prev;         // its non-zero rows
     // pipelined reader (dspmap_get_occupancy_async): two result slots, copies on their own stream
     struct ReaderSlot {
         float *d_xyz = nullptr, *d_future = nullptr, *h_xyz = nullptr, *h_future = nullptr;
@@ -754,6 +761,8 @@ int dspmap_create(const dspmap_config *cfg, dspmap **out) {
         m->pdl = e && *e && strcmp(e, "0") != 0;
         e = getenv("DSPMAP_CZ_TMA");
         m->cz_tma = e && *e && strcmp(e, "0") != 0;
+        e = getenv("DSPMAP_SPARSE_FUTURE");
+        m->sparse_future = e && *e && strcmp(e, "0") != 0;
         e = getenv("DSPMAP_CZ_STAGED");
         m->cz_staged = e && *e && strcmp(e, "0") != 0;
         e = getenv("DSPMAP_G_COL");
@@ -804,6 +813,9 @@ void dspmap_destroy(dspmap *m) {
     if (m->h_xyz) cudaFreeHost(m->h_xyz);
     if (m->h_state) cudaFreeHost(m->h_state);
     if (m->h_count) cudaFreeHost(m->h_count);
+    if (m->h_fidx) cudaFreeHost(m->h_fidx);
+    if (m->h_fval) cudaFreeHost(m->h_fval);
+    if (m->h_nf) cudaFreeHost(m->h_nf);
     for (auto &s : m->prof_slots) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     if (m->ev_fork) cudaEventDestroy(m->ev_fork);
     if (m->ev_join) cudaEventDestroy(m->ev_join);
@@ -1107,8 +1119,53 @@ int dspmap_get_occupancy(dspmap *m, float thr, float *xyz_out, int cap, int *n_o
     const size_t fbytes = sizeof(float) * (size_t)mc.V * mc.T;
     const bool direct = future && m->pinned_user && (char *)future >= (char *)m->pinned_user &&
                         (char *)future + fbytes <= (char *)m->pinned_user + m->pinned_bytes;
-    if (future) CK(cudaMemcpyAsync(direct ? future : m->h_future, m->d_future, fbytes, cudaMemcpyDeviceToHost, m->stream));
+    // A registered buffer is only ever written by this function, so it still holds the previous call's result: instead of
+    // the dense grid, the non-zero voxel rows travel and the buffer is patched (rows that were non-zero last time are cleared
+    // first).  Contract (include/dspmap_b200.h): while registered, the application treats the buffer as read-only.
+    const bool sparse = direct && m->sparse_future && mc.T > 0;
+    int fguess = 0;
+    if (sparse) {
+        if (!m->d_fcnt) {
+            if (dalloc(m, &m->d_fcnt, m->occ_blocks + 1) != DSPMAP_OK || dalloc(m, &m->d_foff, m->occ_blocks + 1) != DSPMAP_OK ||
+                dalloc(m, &m->d_fidx, (size_t)mc.V, false) != DSPMAP_OK || dalloc(m, &m->d_fval, (size_t)mc.V * mc.T, false) != DSPMAP_OK ||
+                dalloc(m, &m->d_nf, 1) != DSPMAP_OK)
+                return DSPMAP_E_CUDA;
+            CK(cudaMallocHost(&m->h_fidx, sizeof(int) * (size_t)mc.V));
+            CK(cudaMallocHost(&m->h_fval, sizeof(float) * (size_t)mc.V * mc.T));
+            CK(cudaMallocHost(&m->h_nf, sizeof(int)));
+        }
+        LAUNCH(m, FAM_READER, k_fut_count, m->occ_blocks, 256, 0, mc, m->d_future, m->d_fcnt);
+        LAUNCH(m, FAM_READER, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{m->d_fcnt, m->d_foff, nullptr, 0, m->occ_blocks}, ScanJob{}, ScanJob{}}});
+        LAUNCH(m, FAM_READER, k_fut_compact, m->occ_blocks, 256, 0, mc, m->d_future, m->d_foff, m->d_fidx, m->d_fval, m->d_nf, m->occ_blocks);
+        CK(cudaGetLastError());
+        fguess = std::min(m->fut_guess, mc.V);
+        CK(cudaMemcpyAsync(m->h_nf, m->d_nf, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+        CK(cudaMemcpyAsync(m->h_fidx, m->d_fidx, sizeof(int) * (size_t)fguess, cudaMemcpyDeviceToHost, m->stream));
+        CK(cudaMemcpyAsync(m->h_fval, m->d_fval, sizeof(float) * (size_t)fguess * mc.T, cudaMemcpyDeviceToHost, m->stream));
+    } else if (future) {
+        CK(cudaMemcpyAsync(direct ? future : m->h_future, m->d_future, fbytes, cudaMemcpyDeviceToHost, m->stream));
+        if (direct) m->sparse_ptr = nullptr;  // a dense copy went into the buffer: the row list no longer describes it
+    }
     CK(cudaStreamSynchronize(m->stream));
+    if (sparse) {
+        const int nf = *m->h_nf;
+        if (nf > fguess) {  // more rows than the speculative copy carried
+            CK(cudaMemcpyAsync(m->h_fidx + fguess, m->d_fidx + fguess, sizeof(int) * (size_t)(nf - fguess), cudaMemcpyDeviceToHost, m->stream));
+            CK(cudaMemcpyAsync(m->h_fval + (size_t)fguess * mc.T, m->d_fval + (size_t)fguess * mc.T, sizeof(float) * (size_t)(nf - fguess) * mc.T,
+                               cudaMemcpyDeviceToHost, m->stream));
+            CK(cudaStreamSynchronize(m->stream));
+        }
+        m->fut_guess = std::max(8192, 2 * nf);
+        const size_t row = sizeof(float) * (size_t)mc.T;
+        if (m->sparse_ptr != future) {  // first use of this buffer (or a dense copy in between): its content is unknown
+            memset(future, 0, fbytes);
+            m->sparse_ptr = future;
+        } else {
+            for (int v : m->sparse_prev) memset(future + (size_t)v * mc.T, 0, row);
+        }
+        for (int k = 0; k < nf; ++k) memcpy(future + (size_t)m->h_fidx[k] * mc.T, m->h_fval + (size_t)k * mc.T, row);
+        m->sparse_prev.assign(m->h_fidx, m->h_fidx + nf);
+    }
     int n = *m->h_count;
     if (n_out) *n_out = n;
     int ncopy = std::min(n, cap);
@@ -1189,6 +1246,8 @@ int dspmap_pin_host_buffer(dspmap *m, void *ptr, size_t bytes) {
         m->pinned_user = nullptr;
         m->pinned_bytes = 0;
     }
+    m->sparse_ptr = nullptr;
+    m->sparse_prev.clear();
     if (ptr && bytes) {
         if (cudaHostRegister(ptr, bytes, cudaHostRegisterPortable) != cudaSuccess) {
             cudaGetLastError();  // not fatal: the staged path stays in use

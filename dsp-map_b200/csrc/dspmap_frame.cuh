@@ -2047,6 +2047,56 @@ __global__ void __launch_bounds__(256) k_occ_write(MapConst mc, DevPtrs dp, floa
         __syncthreads();
     }
 }
+// Sparse copy-out of the future-status grid (experiment switch DSPMAP_SPARSE_FUTURE=1).  The reference hands the application
+// V x T floats per call (dsp_dynamic.h:416-418), 4.2 MB at cfg2, of which 2.4 % of the voxel rows are non-zero (measured on
+// the reference's state): over PCIe only those rows travel, as (voxel id, T values) records in ascending voxel order, and the
+// host patches the application's array (dspmap_get_occupancy).  Both kernels read the dense device copy k_occ_count made.
+__global__ void __launch_bounds__(256) k_fut_count(MapConst mc, const float *d_future, int *blockcnt) {
+    pdl_enter();
+    __shared__ int s;
+    if (threadIdx.x == 0) s = 0;
+    __syncthreads();
+    const int b = blockIdx.x * OCC_BLOCK;
+    int c = 0;
+    for (int i = threadIdx.x; i < OCC_BLOCK; i += blockDim.x) {
+        const int v = b + i;
+        if (v < mc.V) {
+            bool nz = false;
+            for (int t = 0; t < mc.T; ++t) nz |= d_future[(size_t)v * mc.T + t] != 0.f;
+            c += nz ? 1 : 0;
+        }
+    }
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_down_sync(FULLMASK, c, d);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s, c);
+    __syncthreads();
+    if (threadIdx.x == 0) blockcnt[blockIdx.x] = s;
+}
+__global__ void __launch_bounds__(256) k_fut_compact(MapConst mc, const float *d_future, const int *blockoff, int *fidx, float *fval, int *d_nf, int nblocks) {
+    pdl_enter();
+    __shared__ int wsum[8];
+    const int b = blockIdx.x * OCC_BLOCK;
+    int run = blockoff[blockIdx.x];
+    if (blockIdx.x == 0 && threadIdx.x == 0) *d_nf = blockoff[nblocks];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int i0 = 0; i0 < OCC_BLOCK; i0 += 256) {
+        const int v = b + i0 + threadIdx.x;
+        bool nz = false;
+        if (v < mc.V)
+            for (int t = 0; t < mc.T; ++t) nz |= d_future[(size_t)v * mc.T + t] != 0.f;
+        const unsigned bal = __ballot_sync(FULLMASK, nz);
+        if (lane == 0) wsum[w] = __popc(bal);
+        __syncthreads();
+        int before = 0, tot = 0;
+        for (int k = 0; k < 8; ++k) { const int x = wsum[k]; if (k < w) before += x; tot += x; }
+        if (nz) {
+            const int pos = run + before + __popc(bal & ((1u << lane) - 1u));
+            fidx[pos] = v;
+            for (int t = 0; t < mc.T; ++t) fval[(size_t)pos * mc.T + t] = d_future[(size_t)v * mc.T + t];
+        }
+        run += tot;
+        __syncthreads();
+    }
+}
 __global__ void k_future_clear(MapConst mc, DevPtrs dp) {
     pdl_enter();
     size_t n = (size_t)mc.V * mc.T;

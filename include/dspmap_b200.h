@@ -116,7 +116,11 @@ int dspmap_get_occupancy_async(dspmap *m, float threshold, int with_future, int 
 int dspmap_wait_occupancy(dspmap *m, int ticket, const float **xyz, int *n, const float **future);
 /* Optional: page-locks a caller-owned output buffer (e.g. the application's static future_status array) so that
  * dspmap_get_occupancy can DMA straight into it instead of staging + memcpy. The buffer must outlive the handle or be
- * released with bytes == 0. */
+ * released with bytes == 0.
+ * With DSPMAP_SPARSE_FUTURE=1 in the environment a registered future_status buffer is updated incrementally: only the
+ * voxel rows with a non-zero future value cross PCIe (2-3 % of the grid) and the rows of the previous call are cleared on
+ * the host, which yields the same V x T array as the dense copy.  While registered, the application must then treat the
+ * buffer as read-only between calls (the reference application only reads it, map_sim_example.cpp:371-437). */
 int dspmap_pin_host_buffer(dspmap *m, void *ptr, size_t bytes);
 /* clearOccupancyMapPrediction (:431-438). */
 int dspmap_clear_prediction(dspmap *m);
