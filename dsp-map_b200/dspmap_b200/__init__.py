@@ -240,14 +240,18 @@ class DSPMap:
 
     def getOccupancyMap(self, threshold=0.7):
         """Returns (obstacles_num, cloud[n,3]); zeroes the future columns like the reference (dsp_dynamic.h:385-402)."""
-        xyz = np.zeros((self.V, 3), np.float32)
+        xyz = getattr(self, "_xyz_buf", None)
+        if xyz is None:
+            xyz = self._xyz_buf = np.zeros((self.V, 3), np.float32)
         n = C.c_int32(0)
         self._check(self.lib.dspmap_get_occupancy(self.h, threshold, _fp(xyz), self.V, C.byref(n), None))
         return n.value, xyz[:n.value].copy()
 
     def getOccupancyMapWithFutureStatus(self, threshold=0.7, future_status=None):
         """Returns (obstacles_num, cloud[n,3], future_status[V,T]) (dsp_dynamic.h:405-426)."""
-        xyz = np.zeros((self.V, 3), np.float32)
+        xyz = getattr(self, "_xyz_buf", None)   # reused: the library fills the first n rows, which are copied out below
+        if xyz is None:
+            xyz = self._xyz_buf = np.zeros((self.V, 3), np.float32)
         if future_status is None:
             future_status = np.zeros((self.V, self.T), np.float32)
         n = C.c_int32(0)
