@@ -112,6 +112,9 @@ struct dspmap {
     bool nb_prefix_done = false;  // this frame's first newborn kernels already ran on the side branch
     bool pdl = false;             // programmatic dependent launch of the frame's kernels (DSPMAP_PDL=1)
     bool cz_tma = false;          // C_z chains fed by a cp.async.bulk / mbarrier ring, heaviest pyramid first (DSPMAP_CZ_TMA=1)
+    bool async_update = false;    // dspmap_update returns once the frame is enqueued; the next call that needs results waits (DSPMAP_ASYNC_UPDATE=1)
+    bool staged_pending = false;  // the page-locked staging buffers are still being read by the previous frame's copies
+    cudaEvent_t ev_staged = nullptr;
     bool cz_staged = false;       // k_cz_chain with the neighbour table staged per pyramid (DSPMAP_CZ_STAGED=1)
     bool g_col = false;           // column-major pair buffer: k_pair_eval_col / k_cz_chain_col / k_weight2<.., COL> (DSPMAP_G_COL=1)
     bool nb_redux = false;        // newborn placement with REDUX minima (DSPMAP_NB_REDUX=1)
@@ -667,6 +670,7 @@ int dspmap_create(const dspmap_config *cfg, dspmap **out) {
     CK(cudaEventCreateWithFlags(&m->ev_fork_obs, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&m->ev_join_obs, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&m->ev_state, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&m->ev_staged, cudaEventDisableTiming));
     m->stream = m->own_stream;
 
     DevPtrs &dp = m->dp;
@@ -761,6 +765,8 @@ int dspmap_create(const dspmap_config *cfg, dspmap **out) {
         m->pdl = e && *e && strcmp(e, "0") != 0;
         e = getenv("DSPMAP_CZ_TMA");
         m->cz_tma = e && *e && strcmp(e, "0") != 0;
+        e = getenv("DSPMAP_ASYNC_UPDATE");
+        m->async_update = e && *e && strcmp(e, "0") != 0;
         e = getenv("DSPMAP_SPARSE_FUTURE");
         m->sparse_future = e && *e && strcmp(e, "0") != 0;
         e = getenv("DSPMAP_CZ_STAGED");
@@ -822,6 +828,7 @@ void dspmap_destroy(dspmap *m) {
     if (m->ev_fork_obs) cudaEventDestroy(m->ev_fork_obs);
     if (m->ev_join_obs) cudaEventDestroy(m->ev_join_obs);
     if (m->ev_state) cudaEventDestroy(m->ev_state);
+    if (m->ev_staged) cudaEventDestroy(m->ev_staged);
     for (auto &s : m->rslot) {
         if (s.done) cudaEventDestroy(s.done);
         if (s.h_xyz) cudaFreeHost(s.h_xyz);
@@ -850,6 +857,10 @@ static int update_common(dspmap *m, int n, int stride, const float *pts, float p
         fc.fast_sigma = m->fast_sigma;
     }
     if ((rc = ensure_cand_capacity(m)) != DSPMAP_OK) return rc;
+    if (m->staged_pending) {  // asynchronous updates: the previous frame's host-to-device copies must have left the staging buffers
+        CK(cudaEventSynchronize(m->ev_staged));
+        m->staged_pending = false;
+    }
     for (int i = 0; i < n; ++i) {
         m->h_pts[3 * i] = pts[(size_t)i * stride];
         m->h_pts[3 * i + 1] = pts[(size_t)i * stride + 1];
@@ -879,7 +890,15 @@ static int update_common(dspmap *m, int n, int stride, const float *pts, float p
         CK(cudaMemcpyAsync((void *)m->dp.tagged, m->h_tagged, sizeof(float) * 7 * (size_t)nt, cudaMemcpyHostToDevice, m->stream));
     }
     fc.n_tagged = nt;
+    if (m->async_update) {
+        CK(cudaEventRecord(m->ev_staged, m->stream));  // behind both staging copies
+        m->staged_pending = true;
+    }
     if ((rc = enqueue_frame_b(m, fc, m->dp.tagged)) != DSPMAP_OK) return rc;
+    // Asynchronous update: like dspmap_update_device, return with the frame enqueued; readers and dumps are stream-ordered or
+    // synchronise themselves, dspmap_counters / dspmap_synchronize pick up the frame's state copy.  (Capacity overruns are
+    // then reported by dspmap_synchronize instead of by this call.)
+    if (m->async_update && !m->vz_mode && !m->record_flag && !m->profile) return DSPMAP_OK;
     if ((rc = frame_epilogue(m)) != DSPMAP_OK) return rc;
     // particle CSV (:325-350)
     if (m->record_flag) {
@@ -1166,6 +1185,7 @@ int dspmap_get_occupancy(dspmap *m, float thr, float *xyz_out, int cap, int *n_o
         for (int k = 0; k < nf; ++k) memcpy(future + (size_t)m->h_fidx[k] * mc.T, m->h_fval + (size_t)k * mc.T, row);
         m->sparse_prev.assign(m->h_fidx, m->h_fidx + nf);
     }
+    if (m->async_update && m->update_counter > 0) m->last_state = *m->h_state;  // the frame's state copy has landed by now
     int n = *m->h_count;
     if (n_out) *n_out = n;
     int ncopy = std::min(n, cap);
@@ -1333,6 +1353,7 @@ int dspmap_dump_voxel_objects(dspmap *m, float *out) {
     if (!m) return DSPMAP_E_BAD_ARG;
     const MapConst &mc = m->mc;
     std::vector<float> occ(4 * (size_t)mc.V), fut((size_t)mc.V * std::max(mc.T, 1));
+    CK(cudaStreamSynchronize(m->stream));  // the map's stream does not synchronise with the default stream
     CK(cudaMemcpy(occ.data(), m->dp.OCCV, sizeof(float) * occ.size(), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(fut.data(), m->dp.FUT, sizeof(float) * fut.size(), cudaMemcpyDeviceToHost));
     for (int v = 0; v < mc.V; ++v) {
@@ -1404,6 +1425,10 @@ int dspmap_set_cursors(dspmap *m, int64_t p, int64_t v, int64_t u) {
 }
 int dspmap_counters(dspmap *m, int64_t *out) {
     if (!m) return DSPMAP_E_BAD_ARG;
+    if (m->async_update && m->update_counter > 0) {  // the last frame may still be running: wait for its state copy
+        CK(cudaStreamSynchronize(m->stream));
+        m->last_state = *m->h_state;
+    }
     const DevState &s = m->last_state;
     int64_t v[16] = {s.n_live, s.n_left_map, s.n_voxel_full, s.n_pyramid_full, s.n_moved, s.n_fov, s.n_cand, s.n_born,
                      s.n_low_weight, s.n_pre, s.n_old, s.n_out, s.n_valid, s.n_inexact, m->launches_frame, m->launches_total};
