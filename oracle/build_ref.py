@@ -50,7 +50,15 @@ def patch_header(src, cfg):
     return src
 
 
-def build(name):
+# The reference's own CMakeLists.txt:4 compiles with -O3 -ftree-vectorize -ffast-math -march=native.  The parity libraries
+# cannot use those flags (-ffast-math changes results, -march=native does not travel to another box); for TIMING the
+# reference arm of bench.py also gets a "<cfg>_fast" library with the reference's flags, -march=native replaced by the
+# portable -mavx2 -mfma (bench.py checks /proc/cpuinfo before loading it).
+FAST_FLAGS = ["-O3", "-ftree-vectorize", "-ffast-math", "-mavx2", "-mfma"]
+FAST_CONFIGS = ("cfg2",)
+
+
+def build(name, fast=False):
     cfg = CONFIGS[name]
     os.makedirs(os.path.join(OUT, "gen", name), exist_ok=True)
     with open(os.path.join(REF_INCLUDE, cfg["header"])) as f:
@@ -58,9 +66,9 @@ def build(name):
     gen = os.path.join(OUT, "gen", name, "dsp_ref.h")
     with open(gen, "w") as f:
         f.write(patch_header(src, cfg))
-    so = os.path.join(OUT, "libdspref_%s.so" % name)
+    so = os.path.join(OUT, "libdspref_%s%s.so" % (name, "_fast" if fast else ""))
     V = cfg["nx"] * cfg["ny"] * cfg["nz"]
-    cmd = ["g++", "-std=c++14", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-Wl,-Bsymbolic", "-w",
+    cmd = ["g++", "-std=c++14"] + (FAST_FLAGS if fast else ["-O2", "-ffp-contract=off"]) + ["-fPIC", "-shared", "-Wl,-Bsymbolic", "-w",
            # function-local statics of the reference's inline methods must stay private to each loaded copy
            "-fno-gnu-unique",
            "-I", os.path.join(ROOT, "oracle", "shim"), '-DREF_HEADER="%s"' % gen]
@@ -83,3 +91,5 @@ if __name__ == "__main__":
     names = sys.argv[1:] or list(CONFIGS)
     for n in names:
         print("built", build(n))
+        if n in FAST_CONFIGS:
+            print("built", build(n, fast=True))

@@ -20,6 +20,18 @@ def available(cfg_name):
     return os.path.exists(os.path.join(REF_DIR, "libdspref_%s.so" % cfg_name))
 
 
+def fast_variant(cfg_name):
+    """Name of the timing-only build with the reference's own compiler flags (oracle/build_ref.py: FAST_FLAGS), or None
+    when it has not been built or this host lacks AVX2 / FMA."""
+    if not available(cfg_name + "_fast"):
+        return None
+    try:
+        flags = next(line for line in open("/proc/cpuinfo") if line.startswith("flags")).split()
+    except (OSError, StopIteration):
+        return None
+    return cfg_name + "_fast" if "avx2" in flags and "fma" in flags else None
+
+
 def _fp(a):
     return a.ctypes.data_as(C.POINTER(C.c_float))
 
