@@ -236,8 +236,8 @@ inline void launch_kernel(bool pdl, cudaStream_t st, void (*kernel)(KArgs...), i
 
 const int kSMs = 148;
 // the two configurations of the C_z chain kernel (threads, floats per tile, rows per tile)
-const auto k_weight2 = &k_weight2_t<false, false>, k_weight2q = &k_weight2_t<true, false>;
-const auto k_weight2c = &k_weight2_t<false, true>, k_weight2qc = &k_weight2_t<true, true>;  // column-major pair buffer
+const auto k_weight2 = &k_weight2_t<false>, k_weight2q = &k_weight2_t<true>;
+const auto k_weight_c = &k_weight_col<false>, k_weight_cq = &k_weight_col<true>;  // column-major pair buffer
 const auto k_weight2w = &k_weight2w_t<false>, k_weight2wq = &k_weight2w_t<true>;
 const auto k_cz_narrow = &k_cz_chain<128, 4096, 128>;
 const auto k_cz_wide = &k_cz_chain<256, 8192, 128>;
@@ -416,9 +416,9 @@ int enqueue_frame_a(dspmap *m, const FrameConst &fc, const float *d_pts, const f
             ++m->launches_frame;
             CK(cudaEventRecord(m->ev_join, m->side));
         }
-        if (m->g_col) {  // the CTA-per-chunk kernel takes every frame (the warp-per-chunk variant reads the row-major buffer)
-            if (m->quot_fast) LAUNCH(m, FAM_WEIGHT, k_weight2qc, kSMs * 8, W2_THREADS, 0, mc, fc, dp);
-            else LAUNCH(m, FAM_WEIGHT, k_weight2c, kSMs * 8, W2_THREADS, 0, mc, fc, dp);
+        if (m->g_col) {
+            if (m->quot_fast) LAUNCH(m, FAM_WEIGHT, k_weight_cq, kSMs * 8, 256, 0, mc, fc, dp);
+            else LAUNCH(m, FAM_WEIGHT, k_weight_c, kSMs * 8, 256, 0, mc, fc, dp);
         } else if (m->quot_fast) {
             LAUNCH(m, FAM_WEIGHT, k_weight2q, kSMs * 8, W2_THREADS, 0, mc, fc, dp);
             LAUNCH(m, FAM_WEIGHT, k_weight2wq, kSMs * 6, W2W_THREADS, 0, mc, fc, dp);

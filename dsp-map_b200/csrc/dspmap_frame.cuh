@@ -956,7 +956,8 @@ __global__ void __launch_bounds__(CZ_THREADS) k_cz_chain(MapConst mc, FrameConst
 //   * k_cz_chain_col: every column is contiguous and 16-byte aligned, so the chain thread of point z streams ITS column
 //     through shared memory with cp.async.bulk and reads it four rows per LDS.128 — 10 instructions per 4 rows instead of
 //     ~22, which leaves the 4-cycle dependent FADD as the only limit of the longest chain (4 559 rows at cfg2);
-//   * k_weight2 (COL): a flat index is (point f / 32, particle f % 32): no division by np per element.
+//   * k_weight_col: lane = particle reads its value for point z as part of one coalesced 128-byte load, divides and adds:
+//     the weight pass needs no shared memory, no barrier and no per-element index arithmetic any more.
 // Sums are formed from the same terms in the same order: results are bit-identical.
 // ------------------------------------------------------------------------------------------------------------
 #define EVALC_KEYS 2048  // shared-memory room for cz_build_order (== CZ_ORDER_MAX)
@@ -1089,6 +1090,72 @@ __global__ void __launch_bounds__(CZC_THREADS) k_cz_chain_col(MapConst mc, Frame
         }
     }
 }
+// weights (dsp_dynamic.h:743-790) on the column-major buffer: one WARP per 32 particles of a pyramid, lane = particle.  For
+// every point z of every neighbour pyramid (table order, bin order — the reference's chain order) the chunk's 32 values are
+// 32 consecutive floats, i.e. one coalesced load; the lane divides its own value and adds it.  No shared memory, no barrier,
+// no transposition: the loads do not depend on the running sum, so sixteen of them are in flight per warp.
+template <bool QF>
+__global__ void __launch_bounds__(256) k_weight_col(MapConst mc, FrameConst fc, DevPtrs dp) {
+    pdl_enter();
+    if (!use_pair_buffer(mc, dp)) return;
+    const int lane = threadIdx.x & 31;
+    const int nchunks = dp.chunk_off[mc.P];
+    for (;;) {
+        int c = 0;
+        if (lane == 0) c = atomicAdd(&dp.st->work_w2, 1);
+        c = __shfl_sync(FULLMASK, c, 0);
+        if (c >= nchunks) break;
+        if (mc.sharded && c % mc.nranks != mc.rank) continue;  // chunks are dealt round-robin over the ranks
+        const int a = chunk_to_pyramid(dp.chunk_off, mc.P, c);
+        const int k0 = (c - dp.chunk_off[a]) << 5;
+        const int lb = dp.poff[a];
+        const int nrows = min(32, dp.plen[a] - k0);
+        const bool mine = lane < nrows;
+        bool act = false;
+        float pw = 0.f;
+        if (mine) {
+            const float4 p = dp.LP[lb + k0 + lane];
+            pw = p.w;
+            const float dist = sqrtf(p.x * p.x + p.y * p.y + p.z * p.z);
+            const float maxlen = __int_as_float(dp.obs_maxbits[a]);
+            act = !(maxlen > 0.f && dist > maxlen + mc.occl);  // occluded particles keep their weight (:761)
+        }
+        float sum = 0.f;
+        const int nn = dp.nbr[a * mc.NBW];
+        for (int ns = 0; ns < nn; ++ns) {
+            const int b = dp.nbr[a * mc.NBW + 1 + ns];
+            const int np = min(dp.obs_cnt[b], mc.OBS - 1);
+            if (np == 0) continue;
+            const size_t tl = (size_t)((dp.totlen[b] + 3) & ~3);
+            const float *g = dp.G + (size_t)dp.rowbase[b] + (size_t)(dp.cum[b * mc.NBW + nb_index_of(mc, dp, b, a)] + k0) + lane;
+            const float *cz = dp.CZ + (size_t)b * mc.OBS;
+            // C_z of the pyramid's points: lane l keeps points l, l + 32, l + 64, l + 96; broadcast by shuffle when needed
+            float czr[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) czr[q] = q * 32 + lane < np ? cz[q * 32 + lane] : 1.f;
+            // sixteen loads are issued before the first of them is used (the division's slow-path branch keeps the compiler
+            // from hoisting loads across iterations on its own); every lane runs the loop, so the shuffles stay convergent
+            for (int z0 = 0; z0 < np; z0 += 16) {
+                float gv[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) gv[u] = (mine && z0 + u < np) ? __ldg(g + (size_t)(z0 + u) * tl) : 0.f;
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    const int z = z0 + u;
+                    if (z < np) {  // uniform
+                        const float src = z < 32 ? czr[0] : (z < 64 ? czr[1] : (z < 96 ? czr[2] : czr[3]));
+                        sum += dsp_quot<QF>(fc.Pd * gv[u], __shfl_sync(FULLMASK, src, z & 31));
+                    }
+                }
+            }
+        }
+        if (mine) {
+            const float w_new = act ? pw * (fc.one_minus_Pd + sum) : pw;
+            if (mc.sharded) dp.NW[lb + k0 + lane] = w_new;  // merged over ranks, applied by the particle's owner
+            else if (act) dp.PA[dp.LA[lb + k0 + lane]].w = w_new;
+        }
+    }
+}
 // C_z with a bulk-copy ring (experiment switch DSPMAP_CZ_TMA=1).  The chain of one observation point is serial — rows x 4
 // cycles at best — so the kernel lasts as long as its heaviest pyramid, and the double-buffered version above spends half
 // of that waiting: one tile of lead (<= 128 rows, ~500 cycles of chain) is less than the L2 round trip of the next tile.
@@ -1210,9 +1277,7 @@ __global__ void __launch_bounds__(CZT_THREADS) k_cz_chain_tma(MapConst mc, Frame
 #define W2_SWITCH 4096  // chunks of 32 particles: below, CTA-per-chunk (k_weight2); from here on, warp-per-chunk (k_weight2w)
 #define W2_THREADS 128
 #define W2_NP 100  // padded row length (np <= 99; odd stride: no bank conflicts in the chain)
-// QF: quotients through dsp_quot's fast path (DSPMAP_QUOT_FAST=1); COL: column-major pair buffer (DSPMAP_G_COL=1) — the
-// chunk's values for one point are 32 consecutive floats, a flat index f means (point f / 32, particle f % 32)
-template <bool QF, bool COL>
+template <bool QF>  // QF: quotients through dsp_quot's fast path (DSPMAP_QUOT_FAST=1)
 __global__ void __launch_bounds__(W2_THREADS) k_weight2_t(MapConst mc, FrameConst fc, DevPtrs dp) {
     pdl_enter();
     __shared__ float terms[2][32 * (W2_NP + 1)];
@@ -1221,7 +1286,7 @@ __global__ void __launch_bounds__(W2_THREADS) k_weight2_t(MapConst mc, FrameCons
     if (!use_pair_buffer(mc, dp)) return;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int nchunks = dp.chunk_off[mc.P];
-    if (!COL && nchunks >= W2_SWITCH) return;  // many chunks: k_weight2w takes the frame (row-major buffer only)
+    if (nchunks >= W2_SWITCH) return;  // many chunks: k_weight2w takes the frame
     for (;;) {
         __syncthreads();
         if (tid == 0) s_item = atomicAdd(&dp.st->work_w2, 1);
@@ -1253,30 +1318,19 @@ __global__ void __launch_bounds__(W2_THREADS) k_weight2_t(MapConst mc, FrameCons
         const int PSTR = W2_THREADS - 32;
         float gpre[8], czpre0 = 1.f, czpre1 = 1.f;
         const float *gb_n = nullptr;
-        int nfl_n = 0, tl_n = 0;
-        // address of flat element f of the tile at g (stride tl between the points' columns when COL); false: no such element
-        auto elem = [&](const float *g, int tl, int nfl, int f, const float *&addr) -> bool {
-            if (COL) {
-                addr = g + (size_t)(f >> 5) * tl + (f & 31);
-                return f < nfl && (f & 31) < nrows;
-            }
-            addr = g + f;
-            return f < nfl;
-        };
+        int nfl_n = 0;
         auto prefetch = [&](int ns) {
             nfl_n = 0;
             if (ns >= nn) return;
             const int b = dp.nbr[a * mc.NBW + 1 + ns];
             const int np = min(dp.obs_cnt[b], mc.OBS - 1);
             if (np == 0) return;
-            const int jb = dp.cum[b * mc.NBW + nb_index_of(mc, dp, b, a)] + k0;
-            gb_n = dp.G + (size_t)dp.rowbase[b] + (COL ? (size_t)jb : (size_t)jb * np);
-            tl_n = COL ? ((dp.totlen[b] + 3) & ~3) : 0;
-            nfl_n = COL ? 32 * np : nrows * np;
+            gb_n = dp.G + (size_t)dp.rowbase[b] + (size_t)(dp.cum[b * mc.NBW + nb_index_of(mc, dp, b, a)] + k0) * np;
+            nfl_n = nrows * np;
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                const float *ad;
-                gpre[u] = elem(gb_n, tl_n, nfl_n, t96 + u * PSTR, ad) ? __ldg(ad) : 0.f;
+                const int f = t96 + u * PSTR;
+                gpre[u] = f < nfl_n ? __ldg(gb_n + f) : 0.f;
             }
             const float *cz = dp.CZ + (size_t)b * mc.OBS;
             czpre0 = t96 < np ? cz[t96] : 1.f;
@@ -1296,21 +1350,15 @@ __global__ void __launch_bounds__(W2_THREADS) k_weight2_t(MapConst mc, FrameCons
                     if (t96 < np) czs[buf][t96] = czpre0;
                     if (t96 + PSTR < np) czs[buf][t96 + PSTR] = czpre1;
                     const float *gb = gb_n;
-                    const int nfl = nfl_n, tl = tl_n;
+                    const int nfl = nfl_n;
                     asm volatile("bar.sync 1, 96;" ::: "memory");  // only the three producer warps
                     const unsigned magic = np > 1 ? 0xffffffffu / (unsigned)np + 1u : 0u;  // exact f / np for f < 65536
-                    // (particle row r, point z) of flat element f
-                    auto row_col = [&](int f, int &r, int &z) {
-                        if (COL) { r = f & 31; z = f >> 5; }
-                        else { r = np > 1 ? (int)__umulhi((unsigned)f, magic) : f; z = f - r * np; }
-                    };
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
                         const int f = t96 + u * PSTR;
-                        const float *ad;
-                        if (elem(gb, tl, nfl, f, ad)) {
-                            int r, z;
-                            row_col(f, r, z);
+                        if (f < nfl) {
+                            const int r = np > 1 ? (int)__umulhi((unsigned)f, magic) : f;
+                            const int z = f - r * np;
                             terms[buf][r * ld + z] = dsp_quot<QF>(fc.Pd * gpre[u], czs[buf][z]);
                         }
                     }
@@ -1319,16 +1367,15 @@ __global__ void __launch_bounds__(W2_THREADS) k_weight2_t(MapConst mc, FrameCons
                         float g[8];
 #pragma unroll
                         for (int u = 0; u < 8; ++u) {
-                            const float *ad;
-                            g[u] = elem(gb, tl, nfl, f0 + u * PSTR, ad) ? __ldg(ad) : 0.f;
+                            const int f = f0 + u * PSTR;
+                            g[u] = f < nfl ? __ldg(gb + f) : 0.f;
                         }
 #pragma unroll
                         for (int u = 0; u < 8; ++u) {
                             const int f = f0 + u * PSTR;
-                            const float *ad;
-                            if (elem(gb, tl, nfl, f, ad)) {
-                                int r, z;
-                                row_col(f, r, z);
+                            if (f < nfl) {
+                                const int r = np > 1 ? (int)__umulhi((unsigned)f, magic) : f;
+                                const int z = f - r * np;
                                 terms[buf][r * ld + z] = dsp_quot<QF>(fc.Pd * g[u], czs[buf][z]);
                             }
                         }

@@ -1,5 +1,5 @@
 """CPU model of the column-major pair-buffer layout (DSPMAP_G_COL): the addresses k_pair_eval_col
-writes are exactly the addresses k_cz_chain_col and k_weight2<.., COL> read, every bulk copy is 16-byte aligned, and a
+writes are exactly the addresses k_cz_chain_col and k_weight_col read, every bulk copy is 16-byte aligned, and a
 pyramid's block is filled without gaps or overlaps.  It restates the kernels' index arithmetic (dspmap_frame.cuh); the
 kernels themselves are checked on the GPU by tests/ab_toggles.py."""
 import numpy as np
@@ -65,7 +65,7 @@ def test_column_major_pair_buffer_addressing_is_consistent():
                 for jj in range(cur):
                     assert G[src + jj] == (i, j0 + jj, c)
         assert rowbase[i] + ncol * tl == rowbase[i + 1]
-    # k_weight2<.., COL>: flat element f of a chunk's tile = (point f >> 5, particle f & 31)
+    # k_weight_col: lane r of the chunk's warp reads point z of neighbour b at column z, row jb + r
     for a in range(P):
         for ch in range(chunks[a]):
             k0 = ch << 5
