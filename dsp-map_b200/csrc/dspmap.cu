@@ -115,6 +115,7 @@ struct dspmap {
     bool async_update = false;    // dspmap_update returns once the frame is enqueued; the next call that needs results waits (DSPMAP_ASYNC_UPDATE=1)
     bool staged_pending = false;  // the page-locked staging buffers are still being read by the previous frame's copies
     cudaEvent_t ev_staged = nullptr;
+    bool norm_fast = false;       // k_norm_fast (DSPMAP_NORM_FAST=1)
     bool cz_staged = false;       // k_cz_chain with the neighbour table staged per pyramid (DSPMAP_CZ_STAGED=1)
     bool g_col = false;           // column-major pair buffer: k_pair_eval_col / k_cz_chain_col / k_weight2<.., COL> (DSPMAP_G_COL=1)
     bool nb_redux = false;        // newborn placement with REDUX minima (DSPMAP_NB_REDUX=1)
@@ -411,7 +412,8 @@ int enqueue_frame_a(dspmap *m, const FrameConst &fc, const float *d_pts, const f
         if (fc.stage_limit >= 3) {  // the newborn normaliser is one long serial chain: run it beside the weight pass
             CK(cudaEventRecord(m->ev_fork, m->stream));
             CK(cudaStreamWaitEvent(m->side, m->ev_fork, 0));
-            launch_kernel(m->pdl, m->side, k_norm, 1, 128, 0, mc, fc, dp);
+            if (m->norm_fast) launch_kernel(m->pdl, m->side, k_norm_fast, 1, 256, 0, mc, fc, dp);
+            else launch_kernel(m->pdl, m->side, k_norm, 1, 128, 0, mc, fc, dp);
             ++m->launches_total;
             ++m->launches_frame;
             CK(cudaEventRecord(m->ev_join, m->side));
@@ -432,7 +434,7 @@ int enqueue_frame_a(dspmap *m, const FrameConst &fc, const float *d_pts, const f
         // the normaliser is first read by k_nb_cand (w_new).  With the fast weight pass it is the longer branch, so its join
         // moves behind the newborn kernels that do not need it (enqueue_frame_b); otherwise it is joined here
         m->norm_join_pending = fc.stage_limit >= 3;
-        if (m->norm_join_pending && !m->quot_fast) {
+        if (m->norm_join_pending && !(m->quot_fast || m->g_col || m->norm_fast)) {
             CK(cudaStreamWaitEvent(m->stream, m->ev_join, 0));
             m->norm_join_pending = false;
         }
@@ -769,6 +771,8 @@ int dspmap_create(const dspmap_config *cfg, dspmap **out) {
         m->async_update = e && *e && strcmp(e, "0") != 0;
         e = getenv("DSPMAP_SPARSE_FUTURE");
         m->sparse_future = e && *e && strcmp(e, "0") != 0;
+        e = getenv("DSPMAP_NORM_FAST");
+        m->norm_fast = e && *e && strcmp(e, "0") != 0;
         e = getenv("DSPMAP_CZ_STAGED");
         m->cz_staged = e && *e && strcmp(e, "0") != 0;
         e = getenv("DSPMAP_G_COL");

@@ -1541,6 +1541,50 @@ __global__ void k_norm(MapConst mc, FrameConst fc, DevPtrs dp) {
     }
 }
 
+// The same chain with the shared-memory loads taken out of the FADD chain's way (experiment switch DSPMAP_NORM_FAST=1): the
+// adding thread keeps the NEXT sixteen values in registers while it adds the current sixteen (4 cycles each), so the 29-cycle
+// LDS latency is never exposed; 4096-value chunks quarter the number of block barriers.  One fp32 chain in (pyramid, bin)
+// order, as before: bit-identical.  Matters once the weight pass is shorter than this kernel.
+#define NORMF_CHUNK 4096
+__global__ void __launch_bounds__(256) k_norm_fast(MapConst mc, FrameConst fc, DevPtrs dp) {
+    pdl_enter();
+    __shared__ __align__(16) float buf[2][NORMF_CHUNK];
+    const int n = dp.obs_capoff[mc.P];
+    const int nchunk = (n + NORMF_CHUNK - 1) / NORMF_CHUNK;
+    float acc = 0.f;
+    if (nchunk > 0)
+        for (int t = threadIdx.x; t < NORMF_CHUNK; t += blockDim.x) buf[0][t] = t < n ? dp.INV[t] : 0.f;
+    __syncthreads();
+    for (int c = 0; c < nchunk; ++c) {
+        const int b0 = (c + 1) * NORMF_CHUNK;
+        if (threadIdx.x >= 32) {  // warps 1.. fetch the next chunk while thread 0 adds the current one
+            if (c + 1 < nchunk)
+                for (int t = threadIdx.x - 32; t < NORMF_CHUNK; t += blockDim.x - 32) buf[(c + 1) & 1][t] = b0 + t < n ? dp.INV[b0 + t] : 0.f;
+        } else if (threadIdx.x == 0) {
+            const int cnt = min(NORMF_CHUNK, n - c * NORMF_CHUNK);
+            const float4 *s4 = reinterpret_cast<const float4 *>(buf[c & 1]);
+            const int nb = cnt >> 4;  // batches of sixteen
+            float4 a0, a1, a2, a3;
+            if (nb > 0) { a0 = s4[0]; a1 = s4[1]; a2 = s4[2]; a3 = s4[3]; }
+            for (int k = 0; k < nb; ++k) {
+                float4 n0 = a0, n1 = a1, n2 = a2, n3 = a3;
+                if (k + 1 < nb) { n0 = s4[4 * k + 4]; n1 = s4[4 * k + 5]; n2 = s4[4 * k + 6]; n3 = s4[4 * k + 7]; }
+                acc += a0.x; acc += a0.y; acc += a0.z; acc += a0.w;
+                acc += a1.x; acc += a1.y; acc += a1.z; acc += a1.w;
+                acc += a2.x; acc += a2.y; acc += a2.z; acc += a2.w;
+                acc += a3.x; acc += a3.y; acc += a3.z; acc += a3.w;
+                a0 = n0; a1 = n1; a2 = n2; a3 = n3;
+            }
+            for (int k = nb << 4; k < cnt; ++k) acc += buf[c & 1][k];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        dp.st->norm = acc;
+        dp.st->w_new = fc.nb_weight * acc;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // K6  newborn particles (dsp_dynamic.h:796-921; dsp_static.h:779-829)
 // ------------------------------------------------------------------------------------------------------------
