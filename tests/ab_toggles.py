@@ -9,6 +9,9 @@ between steps) and the host-pointer frame (update + getOccupancyMapWithFutureSta
 
     python tests/ab_toggles.py [--cfg cfg2] [--frames 10] [--steps 40] [--also cfg3:2] DSPMAP_PDL=1 ...
 
+Every switch set runs in its own process with a timeout (--timeout), so a kernel that hangs or faults under one switch
+costs that set only; the default path is timed once, by the first child.
+
 Results are appended line by line to gpurun_out/ab_toggles.jsonl (flushed as it goes, so a run cut short keeps what it had).
 This is a measurement tool, not part of the test-suite (pytest does not collect it)."""
 import argparse
@@ -45,8 +48,42 @@ def main():
     ap.add_argument("--preroll", type=int, default=25, help="untimed frames before the timed ones")
     ap.add_argument("--also", default="", help="extra parity-only configs, name:frames[,name:frames]")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "ab_toggles.jsonl"))
+    ap.add_argument("--timeout", type=float, default=90.0, help="seconds per switch set (each set runs in its own process)")
+    ap.add_argument("--inproc", action="store_true", help="run all sets in this process (no protection against a hung kernel)")
+    ap.add_argument("--baseline", default="", help="(internal) baseline device_ms,host_ms measured by the driver process")
     ap.add_argument("sets", nargs="+")
     args = ap.parse_args()
+
+    if not args.inproc:
+        # one process per switch set, so that a kernel that hangs or faults under one switch costs that set only
+        import subprocess
+        common = [sys.executable, os.path.abspath(__file__), "--inproc", "--cfg", args.cfg, "--frames", str(args.frames), "--steps", str(args.steps),
+                  "--preroll", str(args.preroll), "--out", args.out]
+        if args.also:
+            common += ["--also", args.also]
+        base = ""
+        if args.steps > 0:
+            r = subprocess.run(common + ["--baseline", "measure", "BASELINE"], capture_output=True, text=True, timeout=args.timeout)
+            for line in r.stdout.splitlines():
+                if line.startswith("BASELINE "):
+                    base = line.split()[1]
+            print("baseline (device ms, host-api ms):", base or "failed: " + r.stderr[-300:], flush=True)
+        rc = 0
+        for spec in args.sets:
+            try:
+                r = subprocess.run(common + (["--baseline", base] if base else []) + [spec], capture_output=True, text=True, timeout=args.timeout)
+                sys.stdout.write(r.stdout)
+                if r.returncode != 0:
+                    rc = 1
+                    rec = {"switches": spec, "cfg": args.cfg, "stage": "error", "returncode": r.returncode, "stderr": r.stderr[-600:]}
+                    open(args.out, "a").write(json.dumps(rec) + "\n")
+                    print(json.dumps(rec), flush=True)
+            except subprocess.TimeoutExpired:
+                rc = 1
+                rec = {"switches": spec, "cfg": args.cfg, "stage": "timeout", "seconds": args.timeout}
+                open(args.out, "a").write(json.dumps(rec) + "\n")
+                print(json.dumps(rec), flush=True)
+        return rc
 
     import torch
     import dspmap_b200 as dm
@@ -168,6 +205,12 @@ def main():
         return dev_ms, 1e3 * float(np.mean(ts))
 
     base = None
+    if args.baseline == "measure":  # driver's first child: time the default path once for all sets
+        b_dev, b_host = timing(args.cfg, {}, args.steps)
+        print("BASELINE %r,%r" % (b_dev, b_host), flush=True)
+        return 0
+    if args.baseline:
+        base = tuple(float(x) for x in args.baseline.split(","))
     for spec in args.sets:
         env = dict(kv.split("=", 1) for kv in spec.split(",") if kv)
         rec = {"switches": env, "cfg": args.cfg}
