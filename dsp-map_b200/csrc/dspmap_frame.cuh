@@ -994,11 +994,15 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_pair_eval_col(MapConst mc, Fra
         float *gb = dp.G + (size_t)dp.rowbase[i] + (size_t)(dp.cum[i * mc.NBW + nb_index_of(mc, dp, i, a)] + k0) + lane;
         if (mine) gb[(size_t)np * tl] = dp.PW[dp.poff[a] + k0 + lane];  // the weight column (P_d * w, as k_pyr_sort rounded it)
         const float4 *zs = dp.OBSP + (size_t)i * mc.OBS;
+        // the next point is requested before the current one is evaluated (in the row-major kernel 14 % of the samples wait
+        // for this load: profiles/r01_top_kernels.md)
+        float4 o = zs[0];
 #pragma unroll 2
         for (int z = 0; z < np; ++z) {
-            const float4 o = zs[z];
+            const float4 on = zs[min(z + 1, np - 1)];
             const float g = dsp_pdf_f(lut, p.x, o.x, fc) * dsp_pdf_f(lut, p.y, o.y, fc) * dsp_pdf_f(lut, p.z, o.z, fc);
             if (mine) gb[(size_t)z * tl] = g;
+            o = on;
         }
     }
 }
