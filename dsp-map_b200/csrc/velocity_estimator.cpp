@@ -125,13 +125,14 @@ namespace {
 struct ClusterScratch {
     std::vector<int> grid;  // padded dense cell grid -> compact cell number; all -1 between calls
     std::vector<float> box;
-    std::vector<unsigned char> bits;
+    std::vector<unsigned char> bits, rowocc;
     std::vector<int> cell_of, next, rep, tail, cell_lin, parent, croot, comp_of_root, comp_size;
 };
 const long long kDenseCells = 1ll << 23;  // 32 MB of int; larger bounding boxes take the hash-grid path
 
 // Connected components on a dense cell grid over the cloud's bounding box.  Returns false when the box is too large.
-bool dense_clusters(const float *xyz, int n, float tol, int min_size, int max_size, std::vector<std::vector<int>> &out) {
+bool dense_clusters(const float *xyz, int n, float tol, int min_size, int max_size, std::vector<std::vector<int>> &out,
+                    const float *bbox = nullptr) {
     static thread_local ClusterScratch S;
     const float tol2 = tol * tol;
     const float inv_edge = 1.f / (tol * 0.57f);  // cells only need edge < tol / sqrt(3) up to rounding (1.3 % slack)
@@ -142,12 +143,16 @@ bool dense_clusters(const float *xyz, int n, float tol, int min_size, int max_si
     };
     // bounding box first (floor is monotone, so the extreme cells are the cells of the extreme coordinates)
     float fl[3] = {xyz[0], xyz[1], xyz[2]}, fh[3] = {xyz[0], xyz[1], xyz[2]};
-    for (int i = 1; i < n; ++i)
-        for (int k = 0; k < 3; ++k) {
-            const float v = xyz[3 * i + k];
-            fl[k] = v < fl[k] ? v : fl[k];
-            fh[k] = v > fh[k] ? v : fh[k];
-        }
+    if (bbox) {  // the caller already swept the points (VelocityEstimator::estimate)
+        for (int k = 0; k < 3; ++k) { fl[k] = bbox[k]; fh[k] = bbox[3 + k]; }
+    } else {
+        for (int i = 1; i < n; ++i)
+            for (int k = 0; k < 3; ++k) {
+                const float v = xyz[3 * i + k];
+                fl[k] = v < fl[k] ? v : fl[k];
+                fh[k] = v > fh[k] ? v : fh[k];
+            }
+    }
     int lo[3];
     long long dim[3];
     for (int k = 0; k < 3; ++k) {
@@ -224,9 +229,9 @@ bool dense_clusters(const float *xyz, int n, float tol, int min_size, int max_si
     // Each unordered pair of cells once: the lexicographically positive half of the 5 x 5 x 5 neighbourhood, scanned as
     // rows of five x-adjacent cells (one cache line; an all-empty row is skipped with one test).  Adjacent cells (pass 0)
     // before cells two apart (pass 1): most of the far links are then already implied.
-    struct Row { int off; int amask; };  // bit (a + 2) set: offset a of this row belongs to the pass
-    Row rows[2][13];
-    int nrows[2] = {0, 0};
+    struct Row { int off; int amask[2]; };  // bit (a + 2) of amask[pass] set: offset a of this row belongs to the pass
+    Row rows[13];
+    int nrows = 0;
     for (int d = 0; d <= 2; ++d)
         for (int b = -2; b <= 2; ++b) {
             if (d == 0 && b < 0) continue;
@@ -236,18 +241,27 @@ bool dense_clusters(const float *xyz, int n, float tol, int min_size, int max_si
                 const int ch = std::max(std::max(a < 0 ? -a : a, b < 0 ? -b : b), d);
                 m[ch - 1] |= 1 << (a + 2);
             }
-            for (int ps = 0; ps < 2; ++ps)
-                if (m[ps]) rows[ps][nrows[ps]++] = Row{(int)((d * dy + b) * dx), m[ps]};
+            if (m[0] | m[1]) rows[nrows++] = Row{(int)((d * dy + b) * dx), {m[0], m[1]}};
         }
+    // the occupancy of every row is read from the bitmap once (pass 0) and kept for pass 1: 13 bytes per cell
+    S.rowocc.resize((size_t)nc * 13);
+    unsigned char *rowocc = S.rowocc.data();
     for (int pass = 0; pass < 2; ++pass)
         for (int c = 0; c < nc; ++c) {
             const int base = S.cell_lin[c];
             const int hc = S.rep[c];
-            for (int k = 0; k < nrows[pass]; ++k) {
-                const int pos = base + rows[pass][k].off - 2;  // >= 0: the grid is padded by two cells
-                uint64_t w;
-                memcpy(&w, bits + (pos >> 3), 8);
-                unsigned occ = (unsigned)(w >> (pos & 7)) & (unsigned)rows[pass][k].amask;
+            for (int k = 0; k < nrows; ++k) {
+                const int pos = base + rows[k].off - 2;  // >= 0: the grid is padded by two cells
+                unsigned row5;
+                if (pass == 0) {
+                    uint64_t w;
+                    memcpy(&w, bits + (pos >> 3), 8);
+                    row5 = (unsigned)(w >> (pos & 7)) & 31u;
+                    rowocc[(size_t)c * 13 + k] = (unsigned char)row5;
+                } else {
+                    row5 = rowocc[(size_t)c * 13 + k];
+                }
+                unsigned occ = row5 & (unsigned)rows[k].amask[pass];
                 while (occ) {
                     const int a = __builtin_ctz(occ);
                     occ &= occ - 1;
@@ -293,12 +307,19 @@ void euclidean_clusters(const float *xyz, int n, float tol, int min_size, int ma
     euclidean_clusters_path(xyz, n, tol, min_size, max_size, 0, out);
 }
 
+namespace {
+bool clusters_impl(const float *xyz, int n, float tol, int min_size, int max_size, int path, std::vector<std::vector<int>> &out, const float *bbox);
+}
 bool euclidean_clusters_path(const float *xyz, int n, float tol, int min_size, int max_size, int path, std::vector<std::vector<int>> &out) {
+    return clusters_impl(xyz, n, tol, min_size, max_size, path, out, nullptr);
+}
+namespace {
+bool clusters_impl(const float *xyz, int n, float tol, int min_size, int max_size, int path, std::vector<std::vector<int>> &out, const float *bbox) {
     out.clear();
     if (n == 0 || !(tol > 0.f)) return true;
     bool done = false;
     if (path != 1) {
-        done = dense_clusters(xyz, n, tol, min_size, max_size, out);
+        done = dense_clusters(xyz, n, tol, min_size, max_size, out, bbox);
         if (!done) out.clear();
         if (!done && path == 2) return false;
     }
@@ -306,6 +327,7 @@ bool euclidean_clusters_path(const float *xyz, int n, float tol, int min_size, i
     std::stable_sort(out.begin(), out.end(), [](const std::vector<int> &a, const std::vector<int> &b) { return a.size() > b.size(); });
     return true;
 }
+}  // namespace
 
 void hungarian(const std::vector<float> &cost, int R, int C, std::vector<int> &assign) {
     assign.assign(R, -1);
@@ -395,6 +417,75 @@ int rotate_in_view(const float *pts, int n, const float *q, const float *qi, con
 }
 }  // namespace
 
+namespace {
+// The dynamic model's front end in ONE sweep over the cloud: rotation + FOV test as in rotate_in_view, the shift into the
+// world frame, the ground / non-ground split (dsp_dynamic.h:1387-1398) and the non-ground bounding box the clustering grid
+// needs.  Both destinations are written and only one cursor advances (the side a point falls on is data-dependent).  Every
+// lane evaluates the scalar expressions in the scalar order, so the outputs are bit-identical to the three separate passes.
+// Returns the number of points in view; counts[0] = floats written to sp, counts[1] = floats written to gp.
+__attribute__((target_clones("avx2", "default")))
+int rotate_split(const float *pts, int n, const float *q, const float *qi, const float *nrm, const float *cur, float filter_res,
+                 float *sp, float *gp, size_t *counts, float *bbox) {
+    const float aw = q[0], ax = q[1], ay = q[2], az = q[3];
+    const float iw = qi[0], ix = qi[1], iy = qi[2], iz = qi[3];
+    const float cx = cur[0], cy = cur[1], cz = cur[2];
+    float *sp0 = sp, *gp0 = gp;
+    const vf8 big = {3.4e38f, 3.4e38f, 3.4e38f, 3.4e38f, 3.4e38f, 3.4e38f, 3.4e38f, 3.4e38f};
+    vf8 lo0 = big, lo1 = big, lo2 = big, hi0 = -big, hi1 = -big, hi2 = -big;  // per-lane running box of the non-ground points
+    int nk = 0;
+    for (int i0 = 0; i0 < n; i0 += 8) {
+        alignas(32) float sx[8], sy[8], sz[8];
+        const int m = std::min(8, n - i0);
+        for (int l = 0; l < m; ++l) {
+            sx[l] = pts[3 * (size_t)(i0 + l)];
+            sy[l] = pts[3 * (size_t)(i0 + l) + 1];
+            sz[l] = pts[3 * (size_t)(i0 + l) + 2];
+        }
+        for (int l = m; l < 8; ++l) sx[l] = sy[l] = sz[l] = 0.f;
+        const vf8 bx = *(const vf8 *)sx, by = *(const vf8 *)sy, bz = *(const vf8 *)sz;
+        const vf8 bw = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const vf8 tw = aw * bw - ax * bx - ay * by - az * bz;
+        const vf8 tx = aw * bx + ax * bw + ay * bz - az * by;
+        const vf8 ty = aw * by + ay * bw + az * bx - ax * bz;
+        const vf8 tz = aw * bz + az * bw + ax * by - ay * bx;
+        const vf8 rx = tw * ix + tx * iw + ty * iz - tz * iy;
+        const vf8 ry = tw * iy + ty * iw + tz * ix - tx * iz;
+        const vf8 rz = tw * iz + tz * iw + tx * iy - ty * ix;
+        const vf8 d0 = rx * nrm[0] + ry * nrm[1] + rz * nrm[2];
+        const vf8 d1 = rx * nrm[3] + ry * nrm[4] + rz * nrm[5];
+        const vf8 d2 = rx * nrm[6] + ry * nrm[7] + rz * nrm[8];
+        const vf8 d3 = rx * nrm[9] + ry * nrm[10] + rz * nrm[11];
+        const vi8 in = (d0 >= 0.f) & (d1 <= 0.f) & (d2 <= 0.f) & (d3 >= 0.f);
+        const vf8 wx = rx + cx, wy = ry + cy, wz = rz + cz;
+        const vi8 ngm = in & (wz > filter_res);  // in view and above the ground threshold (padding lanes are never in view)
+        const vf8 lx = ngm ? wx : big, ly = ngm ? wy : big, lz = ngm ? wz : big;
+        const vf8 hx = ngm ? wx : -big, hy = ngm ? wy : -big, hz = ngm ? wz : -big;
+        lo0 = lx < lo0 ? lx : lo0; lo1 = ly < lo1 ? ly : lo1; lo2 = lz < lo2 ? lz : lo2;
+        hi0 = hx > hi0 ? hx : hi0; hi1 = hy > hi1 ? hy : hi1; hi2 = hz > hi2 ? hz : hi2;
+        for (int l = 0; l < m; ++l)
+            if (in[l]) {
+                const float x = wx[l], y = wy[l], z = wz[l];
+                sp[0] = x; sp[1] = y; sp[2] = z;
+                gp[0] = x; gp[1] = y; gp[2] = z;
+                const int ng = z > filter_res;
+                gp += 3 * ng;
+                sp += 3 * (1 - ng);
+                ++nk;
+            }
+    }
+    counts[0] = (size_t)(sp - sp0);
+    counts[1] = (size_t)(gp - gp0);
+    const vf8 *lo[3] = {&lo0, &lo1, &lo2}, *hi[3] = {&hi0, &hi1, &hi2};
+    for (int k = 0; k < 3; ++k) {
+        float a = (*lo[k])[0], b = (*hi[k])[0];
+        for (int l = 1; l < 8; ++l) { a = (*lo[k])[l] < a ? (*lo[k])[l] : a; b = (*hi[k])[l] > b ? (*hi[k])[l] : b; }
+        bbox[k] = a;
+        bbox[3 + k] = b;
+    }
+    return nk;
+}
+}  // namespace
+
 void VelocityEstimator::estimate(const MapConst &mc, const FrameConst &fc, const float *planes0, const float *pts, int n,
                                  int model, std::vector<float> &out) {
     // rotated outer boundary planes and the in-view rotated cloud, same arithmetic as the device (dsp_dynamic.h:226-257)
@@ -403,8 +494,17 @@ void VelocityEstimator::estimate(const MapConst &mc, const FrameConst &fc, const
     dsp_rotate(planes0 + 3 * mc.Nh, fc.q, fc.qi, nrm + 3);
     dsp_rotate(planes0 + 3 * (mc.Nh + 1), fc.q, fc.qi, nrm + 6);
     dsp_rotate(planes0 + 3 * (mc.Nh + 1 + mc.Nv), fc.q, fc.qi, nrm + 9);
-    rotated.resize(3 * (size_t)n);
-    const int nv = rotate_in_view(pts, n, fc.q, fc.qi, nrm, rotated.data());
+    int nv;
+    size_t split_counts[2] = {0, 0};
+    float ng_box[6];
+    if (model == 1) {
+        rotated.resize(3 * (size_t)n);
+        nv = rotate_in_view(pts, n, fc.q, fc.qi, nrm, rotated.data());
+    } else {  // rotation, FOV test, world shift, ground split and the clustering grid's bounding box in one sweep
+        statics.resize(3 * (size_t)n + 3);
+        nonground.resize(3 * (size_t)n + 3);
+        nv = rotate_split(pts, n, fc.q, fc.qi, nrm, fc.cur, filter_res, statics.data(), nonground.data(), split_counts, ng_box);
+    }
     if (nv == 0) return;  // :1379 — the previous cloud is kept
     out.resize(7 * (size_t)nv);  // every in-view point is written at most once
     size_t no = 0;
@@ -419,28 +519,13 @@ void VelocityEstimator::estimate(const MapConst &mc, const FrameConst &fc, const
     }
     // ground / non-ground split, xyz triples in the world frame (:1387-1398).  Both destinations are written and only
     // one cursor advances: the side a point falls on is data-dependent, a branch here mispredicts
-    statics.resize(3 * (size_t)nv + 3);
-    nonground.resize(3 * (size_t)nv + 3);
-    {
-        float *sp = statics.data(), *gp = nonground.data();
-        const float cx = fc.cur[0], cy = fc.cur[1], cz = fc.cur[2];
-        for (int i = 0; i < nv; ++i) {
-            const float x = rotated[3 * i] + cx, y = rotated[3 * i + 1] + cy, z = rotated[3 * i + 2] + cz;
-            sp[0] = x; sp[1] = y; sp[2] = z;
-            gp[0] = x; gp[1] = y; gp[2] = z;
-            const int ng = z > filter_res;
-            gp += 3 * ng;
-            sp += 3 * (1 - ng);
-        }
-        const size_t ns = sp - statics.data(), ngr = gp - nonground.data();
-        statics.resize(ns);
-        nonground.resize(ngr);
-        statics.reserve(3 * (size_t)nv);  // clusters reclassified as static are appended below
-    }
+    statics.resize(split_counts[0]);
+    nonground.resize(split_counts[1]);
+    statics.reserve(3 * (size_t)nv);  // clusters reclassified as static are appended below
     std::vector<ClusterFeature> cur;
     if (!nonground.empty()) {
         std::vector<std::vector<int>> clusters;
-        euclidean_clusters(nonground.data(), (int)nonground.size() / 3, 2 * filter_res, 5, 10000, clusters);  // :1410-1417
+        clusters_impl(nonground.data(), (int)nonground.size() / 3, 2 * filter_res, 5, 10000, 0, clusters, ng_box);  // :1410-1417
         std::vector<char> dynamic_flag;
         for (const auto &cl : clusters) {  // :1419-1447
             ClusterFeature f;
