@@ -235,6 +235,12 @@ inline void launch_kernel(bool pdl, cudaStream_t st, void (*kernel)(KArgs...), i
         ++(m)->launches_frame;                                                      \
     } while (0)
 
+// experiment switches are environment variables read once, by dspmap_create: set to anything but "" or "0"
+bool env_on(const char *name) {
+    const char *e = getenv(name);
+    return e && *e && strcmp(e, "0") != 0;
+}
+
 const int kSMs = 148;
 // the two configurations of the C_z chain kernel (threads, floats per tile, rows per tile)
 const auto k_weight2 = &k_weight2_t<false>, k_weight2q = &k_weight2_t<true>;
@@ -762,29 +768,18 @@ int dspmap_create(const dspmap_config *cfg, dspmap **out) {
     CK(cudaFuncSetAttribute(k_cz_chain_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, CZT_SMEM_BYTES));
     CK(cudaFuncSetAttribute(k_cz_chain_col, cudaFuncAttributeMaxDynamicSharedMemorySize, CZC_SMEM_BYTES));
     CK(cudaFuncSetAttribute(k_pair_eval_col, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * (DSP_LUT_HALF + 3 + EVALC_KEYS))));
-    {   // experiment switch, off unless DSPMAP_PDL is set to something other than 0
-        const char *e = getenv("DSPMAP_PDL");
-        m->pdl = e && *e && strcmp(e, "0") != 0;
-        e = getenv("DSPMAP_CZ_TMA");
-        m->cz_tma = e && *e && strcmp(e, "0") != 0;
-        e = getenv("DSPMAP_ASYNC_UPDATE");
-        m->async_update = e && *e && strcmp(e, "0") != 0;
-        e = getenv("DSPMAP_SPARSE_FUTURE");
-        m->sparse_future = e && *e && strcmp(e, "0") != 0;
-        e = getenv("DSPMAP_NORM_FAST");
-        m->norm_fast = e && *e && strcmp(e, "0") != 0;
-        e = getenv("DSPMAP_CZ_STAGED");
-        m->cz_staged = e && *e && strcmp(e, "0") != 0;
-        e = getenv("DSPMAP_G_COL");
-        m->g_col = e && *e && strcmp(e, "0") != 0;
-        dp.cz_order = (m->cz_tma || m->g_col) ? cz_order_buf : nullptr;
-        e = getenv("DSPMAP_NB_REDUX");
-        m->nb_redux = e && *e && strcmp(e, "0") != 0;
-        e = getenv("DSPMAP_QUOT_FAST");
-        m->quot_fast = e && *e && strcmp(e, "0") != 0;
-        e = getenv("DSPMAP_EST_THREAD");
-        m->est_thread = e && *e && strcmp(e, "0") != 0;
-    }
+    // experiment switches; all off by default
+    m->pdl = env_on("DSPMAP_PDL");
+    m->cz_tma = env_on("DSPMAP_CZ_TMA");
+    m->cz_staged = env_on("DSPMAP_CZ_STAGED");
+    m->g_col = env_on("DSPMAP_G_COL");
+    dp.cz_order = (m->cz_tma || m->g_col) ? cz_order_buf : nullptr;
+    m->nb_redux = env_on("DSPMAP_NB_REDUX");
+    m->quot_fast = env_on("DSPMAP_QUOT_FAST");
+    m->norm_fast = env_on("DSPMAP_NORM_FAST");
+    m->est_thread = env_on("DSPMAP_EST_THREAD");
+    m->sparse_future = env_on("DSPMAP_SPARSE_FUTURE");
+    m->async_update = env_on("DSPMAP_ASYNC_UPDATE");
     m->cz_wide = getenv("DSPMAP_CZ_NARROW") == nullptr;  // experiment switch: DSPMAP_CZ_NARROW selects the 128-thread / 32 KB configuration
     CK(cudaFuncSetAttribute(k_weight, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaStreamSynchronize(m->stream));
@@ -1122,6 +1117,7 @@ int dspmap_set_voxel_filter_resolution(dspmap *m, float r) { if (!m) return DSPM
 
 int dspmap_get_occupancy_device(dspmap *m, float thr, float *d_xyz, int cap, int *d_count, float *d_future) {
     if (!m) return DSPMAP_E_BAD_ARG;
+    CK(cudaSetDevice(m->cfg.device));
     const MapConst &mc = m->mc;
     LAUNCH(m, FAM_READER, k_occ_count, m->occ_blocks, 256, 0, mc, m->dp, thr, m->d_blockcnt, d_future);
     LAUNCH(m, FAM_READER, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{m->d_blockcnt, m->d_blockoff, nullptr, 0, m->occ_blocks}, ScanJob{}, ScanJob{}}});
