@@ -115,6 +115,7 @@ struct dspmap {
     bool async_update = false;    // dspmap_update returns once the frame is enqueued; the next call that needs results waits (DSPMAP_ASYNC_UPDATE=1)
     bool staged_pending = false;  // the page-locked staging buffers are still being read by the previous frame's copies
     cudaEvent_t ev_staged = nullptr;
+    bool resample_sm = false;     // k_resample_sm (DSPMAP_RESAMPLE_SM=1)
     bool norm_fast = false;       // k_norm_fast (DSPMAP_NORM_FAST=1)
     bool cz_staged = false;       // k_cz_chain with the neighbour table staged per pyramid (DSPMAP_CZ_STAGED=1)
     bool g_col = false;           // column-major pair buffer: k_pair_eval_col / k_cz_chain_col / k_weight2<.., COL> (DSPMAP_G_COL=1)
@@ -478,7 +479,8 @@ int enqueue_frame_b(dspmap *m, const FrameConst &fc, const float *d_tagged) {
     }
     if (fc.stage_limit >= 4) {
         LAUNCH(m, FAM_RESAMPLE, k_voxel_list, grid_for(mc.V, B), B, 0, mc, dp);
-        LAUNCH(m, FAM_RESAMPLE, k_resample, kSMs * 8, 256, 0, mc, fc, dp);
+        if (m->resample_sm) LAUNCH(m, FAM_RESAMPLE, k_resample_sm, kSMs * 8, 32 * RS_WARPS, 0, mc, fc, dp);
+        else LAUNCH(m, FAM_RESAMPLE, k_resample, kSMs * 8, 256, 0, mc, fc, dp);
     }
     if (m->norm_join_pending) {  // no newborn kernels this frame: k_norm must still be over before the next frame resets its outputs
         CK(cudaStreamWaitEvent(m->stream, m->ev_join, 0));
@@ -777,6 +779,7 @@ int dspmap_create(const dspmap_config *cfg, dspmap **out) {
     m->nb_redux = env_on("DSPMAP_NB_REDUX");
     m->quot_fast = env_on("DSPMAP_QUOT_FAST");
     m->norm_fast = env_on("DSPMAP_NORM_FAST");
+    m->resample_sm = env_on("DSPMAP_RESAMPLE_SM");
     m->est_thread = env_on("DSPMAP_EST_THREAD");
     m->sparse_future = env_on("DSPMAP_SPARSE_FUTURE");
     m->async_update = env_on("DSPMAP_ASYNC_UPDATE");
@@ -1074,7 +1077,8 @@ int dspmap_shard_phase(dspmap *m, int phase, int n, const float *d_pts, float px
             newborn_ran = 1;
         }
         LAUNCH(m, FAM_RESAMPLE, k_voxel_list, grid_for(mc.V, B), B, 0, mc, dp);
-        LAUNCH(m, FAM_RESAMPLE, k_resample, kSMs * 8, 256, 0, mc, fc, dp);
+        if (m->resample_sm) LAUNCH(m, FAM_RESAMPLE, k_resample_sm, kSMs * 8, 32 * RS_WARPS, 0, mc, fc, dp);
+        else LAUNCH(m, FAM_RESAMPLE, k_resample, kSMs * 8, 256, 0, mc, fc, dp);
         LAUNCH(m, FAM_CLEANUP, k_cleanup, kSMs * 2, B, 0, mc, fc, dp, newborn_ran, 0);
         CK(cudaMemcpyAsync(m->h_state, m->dp.st, sizeof(DevState), cudaMemcpyDeviceToHost, m->stream));
         CK(cudaEventRecord(m->ev_state, m->stream));

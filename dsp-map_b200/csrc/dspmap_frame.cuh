@@ -2065,6 +2065,150 @@ __global__ void __launch_bounds__(256) k_resample(MapConst mc, FrameConst fc, De
     }
 }
 
+// K7 with the order-dependent loops fed from shared memory (experiment switch DSPMAP_RESAMPLE_SM=1).  k_resample walks the
+// kept particles of a voxel in slot order twice (sums, then the systematic-resampling state machine) and fetches every
+// operand with a find-first-set + shuffle (2 450 instructions per voxel, 19.7 kept particles on average; wait / scoreboard
+// stalls dominate).  Here each lane first writes its kept particles to the warp's shared-memory tile at their rank in slot
+// order; both loops then run over that compact array with broadcast loads whose addresses do not depend on the running
+// sums, and their verdicts (new weight, or removed) go back through the tile.  Same operations in the same order.
+#define RS_WARPS 8
+__global__ void __launch_bounds__(32 * RS_WARPS, 3) k_resample_sm(MapConst mc, FrameConst fc, DevPtrs dp) {
+    pdl_enter();
+    __shared__ float4 sA[RS_WARPS][DSP_MAX_SLOTS], sB[RS_WARPS][DSP_MAX_SLOTS];  // position + weight; velocity + "old" flag
+    __shared__ float sNW[RS_WARPS][DSP_MAX_SLOTS];                               // verdict: new weight, < 0 = removed
+    __shared__ unsigned char sSlot[RS_WARPS][DSP_MAX_SLOTS];
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int R = (mc.S + 31) >> 5;
+    const unsigned below = (1u << lane) - 1u;
+    int c_pre = 0, c_old = 0, c_out = 0, c_low = 0;
+    const int nocc = dp.st->n_occ_voxels;
+    for (int item = warp; item < nocc; item += nwarps) {
+        const int v = dp.E[item];  // E carries the occupied-voxel list (k_voxel_list)
+        const ulonglong2 mv = dp.M[v];
+        const u64 mx = mv.x, my = mv.y;
+        float4 A[4], B[4];
+        unsigned keep[4], old[4];
+        int n_low = 0;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const unsigned live = r < 2 ? (unsigned)(mx >> (32 * r)) : (unsigned)(my >> (32 * (r - 2)));
+            A[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+            B[r] = A[r];
+            const bool mine = r < R && ((live >> lane) & 1u);
+            if (mine) {
+                const int a = v * mc.S + 32 * r + lane;
+                A[r] = dp.PA[a];
+                B[r] = dp.PB[a];
+            }
+            const bool kp = mine && !((double)A[r].w < 1e-3);  // (:941) particles below 1e-3 are dropped
+            keep[r] = __ballot_sync(FULLMASK, kp);
+            old[r] = __ballot_sync(FULLMASK, kp && B[r].w < 10.f);  // not newborn (:944)
+            n_low += __popc(live) - __popc(keep[r]);
+        }
+        // kept particles to the tile, at their rank in slot order
+        int n = 0, n_old = 0;
+        __syncwarp();  // the previous voxel's readers are done with the tile
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            if ((keep[r] >> lane) & 1u) {
+                const int j = n + __popc(keep[r] & below);
+                sA[wl][j] = A[r];
+                sB[wl][j] = make_float4(B[r].x, B[r].y, B[r].z, ((old[r] >> lane) & 1u) ? 1.f : 0.f);
+                sSlot[wl][j] = (unsigned char)(32 * r + lane);
+            }
+            n += __popc(keep[r]);
+            n_old += __popc(old[r]);
+        }
+        __syncwarp();
+        // sums in slot order (:938-973), every lane the same chain
+        float wsum = 0.f, sx = 0.f, sy = 0.f, sz = 0.f;
+        for (int j = 0; j < n; ++j) {
+            const float4 a = sA[wl][j], b = sB[wl][j];
+            if (b.w != 0.f) { sx += b.x; sy += b.y; sz += b.z; }
+            wsum += a.w;
+        }
+        // future status of the old particles (:950-964): each lane scatters its own
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            if ((old[r] >> lane) & 1u)
+                for (int t = 0; t < mc.T; ++t) {
+                    const float ft = mc.ft[t];
+                    const float fx = A[r].x + B[r].x * ft, fy = A[r].y + B[r].y * ft, fz = A[r].z + B[r].z * ft;
+                    const int fi = dsp_voxel_index(mc, fx, fy, fz);
+                    if (fi >= 0) atomicAdd(&dp.FUT[(size_t)fi * mc.T + t], A[r].w);
+                }
+        if (lane == 0) {
+            float4 o = make_float4(wsum, 0.f, 0.f, 0.f);
+            if (n_old > 0) { o.y = sx / (float)n_old; o.z = sy / (float)n_old; o.w = sz / (float)n_old; }
+            dp.OCCV[v] = o;
+        }
+        ulonglong2 occ = make_ulonglong2((u64)keep[0] | ((u64)keep[1] << 32), (u64)keep[2] | ((u64)keep[3] << 32));
+        const bool resample = n >= 5;  // (:986)
+        if (resample) {  // systematic resampling to at most MAX particles, offset 0.5 * w_after, slot order
+            const int n_after = n > mc.max_ppv ? mc.max_ppv : n;
+            const float w_after = wsum / (float)n_after;
+            float acc_ori = 0.f, acc_new = w_after * 0.5f;
+            for (int j = 0; j < n; ++j) {
+                acc_ori += sA[wl][j].w;
+                float verdict;
+                if (acc_ori > acc_new) {
+                    float wk = w_after;
+                    acc_new += w_after;
+                    bool full = false;
+                    while (acc_ori > acc_new) {  // duplicate heavy particles into the first free slot (:1021-1044)
+                        const int fs = full ? -1 : mask_nth_free(mc, occ, 0);
+                        if (fs >= 0) {
+                            if (lane == 0) {
+                                const float4 a = sA[wl][j], b = sB[wl][j];
+                                dp.PA[v * mc.S + fs] = make_float4(a.x, a.y, a.z, wk);
+                                dp.PB[v * mc.S + fs] = make_float4(b.x, b.y, b.z, 0.6f);
+                            }
+                            if (fs < 64) occ.x |= 1ull << fs; else occ.y |= 1ull << (fs - 64);
+                        } else {
+                            wk += w_after;
+                            full = true;
+                        }
+                        acc_new += w_after;
+                    }
+                    verdict = wk;
+                } else {  // removed (:1046-1050)
+                    const int sl = sSlot[wl][j];
+                    if (sl < 64) occ.x &= ~(1ull << sl); else occ.y &= ~(1ull << (sl - 64));
+                    verdict = -1.f;
+                }
+                if (lane == 0) sNW[wl][j] = verdict;
+            }
+        }
+        __syncwarp();
+        // every lane applies the verdicts of its own particles
+        int base = 0;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            if ((keep[r] >> lane) & 1u) {
+                const int a = v * mc.S + 32 * r + lane;
+                const float nw = resample ? sNW[wl][base + __popc(keep[r] & below)] : A[r].w;
+                if (!(nw < 0.f)) {
+                    if (nw != A[r].w) dp.PA[a].w = nw;
+                    if (B[r].w != 1.f) dp.PB[a].w = 1.f;  // newborn / moved flags become "valid" (:968)
+                }
+            }
+            base += __popc(keep[r]);
+        }
+        if (lane == 0) dp.M[v] = occ;
+        c_pre += n;
+        c_old += n_old;
+        c_out += mask_popc(occ);
+        c_low += n_low;
+    }
+    if (lane == 0 && (c_pre | c_low)) {
+        atomicAdd(&dp.st->n_pre, c_pre);
+        atomicAdd(&dp.st->n_old, c_old);
+        atomicAdd(&dp.st->n_out, c_out);
+        if (c_low) atomicAdd(&dp.st->n_low_weight, c_low);
+    }
+}
+
 // end of frame: reset the arrival-grouping tables touched this frame; advance the noise cursors by what the reference's
 // serial newborn loop would have drawn (dsp_dynamic.h:1162-1178); flag a frame no observation kernel handled
 __global__ void k_cleanup(MapConst mc, FrameConst fc, DevPtrs dp, int newborn_ran, int fallback_launched) {
