@@ -17,8 +17,16 @@
 // prerequisite grid has completed and its memory is visible.  EVERY kernel executes the wait before it exits (also on its
 // early-return paths): the guarantee is transitive only through kernels that waited.  Launched without the attribute both
 // instructions are no-ops.
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() {
+#ifdef __CUDA_ARCH__  // (the warp-level kernels are also compiled for the host by tests/simt: no PTX there)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_wait() {
+#ifdef __CUDA_ARCH__
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
 __device__ __forceinline__ void pdl_enter() {
     pdl_trigger();
     pdl_wait();

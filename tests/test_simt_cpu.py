@@ -1,0 +1,28 @@
+"""CPU check of kernel variants by running the kernels' OWN source on the host: tests/simt/extract.py slices the kernels out of
+dsp-map_b200/csrc/dspmap_frame.cuh, tests/simt/simt_host.h supplies threadIdx, __shared__, warp collectives and atomics (one
+OS thread per CUDA thread), and tests/simt/check_*.cpp feeds a variant and the kernel it replaces the same random inputs
+and requires bit-identical outputs.  No GPU involved; the GPU-side A/B of the same variants is tests/ab_toggles.py."""
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SIMT = os.path.join(ROOT, "tests", "simt")
+BUILD = os.path.join(ROOT, "tests", "_build", "simt")
+CUH = os.path.join(ROOT, "dsp-map_b200", "csrc", "dspmap_frame.cuh")
+
+
+def build_and_run(check, inc, kernels, timeout=600):
+    os.makedirs(BUILD, exist_ok=True)
+    subprocess.check_call([sys.executable, os.path.join(SIMT, "extract.py"), CUH, os.path.join(BUILD, inc)] + kernels)
+    exe = os.path.join(BUILD, check)
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-I/usr/local/cuda/include", "-I" + SIMT, "-I" + BUILD,
+                           "-I" + os.path.join(ROOT, "dsp-map_b200", "csrc"), os.path.join(SIMT, check + ".cpp"), "-o", exe, "-lpthread"])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=timeout)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return r.stdout
+
+
+def test_warp_level_variants_equal_the_kernels_they_replace():
+    out = build_and_run("check_warp_kernels", "warp_kernels.inc", ["k_resample", "k_resample_sm", "k_nb_place", "k_nb_place_redux"])
+    assert out.count("identical") == 6 and "DIFFERENT" not in out
