@@ -4,9 +4,9 @@
 // one warp, one OS thread per lane.  Same random inputs to both kernels of a pair; outputs must be bit-identical.
 #include "simt_host.h"
 
-inline void __syncthreads() { abort(); }  // referenced by a header helper that these kernels do not call
+
 #include "dspmap_kernels.cuh"
-#define RS_WARPS 8  // as in dspmap_frame.cuh (the extractor takes the kernels only)
+
 #include "warp_kernels.inc"
 
 #include <cstdio>

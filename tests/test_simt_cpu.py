@@ -26,3 +26,18 @@ def build_and_run(check, inc, kernels, timeout=600):
 def test_warp_level_variants_equal_the_kernels_they_replace():
     out = build_and_run("check_warp_kernels", "warp_kernels.inc", ["k_resample", "k_resample_sm", "k_nb_place", "k_nb_place_redux"])
     assert out.count("identical") == 6 and "DIFFERENT" not in out
+
+
+def test_observation_pass_variants_equal_the_row_major_kernels():
+    """k_cz_chain<STG>, k_cz_chain_tma, k_weight2<QF> and the whole column-major family (k_pair_eval_col -> k_cz_chain_col ->
+    k_weight_col, with and without the dsp_quot fast path) reproduce C_z, 1/C_z and the particle weights of k_pair_eval ->
+    k_cz_chain -> k_weight2 bit for bit; the emulated cp.async.bulk aborts on a copy that breaks the 16-byte rules."""
+    out = build_and_run("check_obs_kernels", "obs_kernels.inc",
+                        ["use_pair_buffer", "chunk_to_pyramid", "nb_index_of", "cz_build_order", "k_pair_prep", "k_pair_eval", "k_cz_chain",
+                         "k_cz_chain_tma", "k_weight2_t", "k_pair_eval_col", "k_cz_chain_col", "k_weight_col"])
+    assert out.count("identical") == 10 and "DIFFERENT" not in out and "does not exercise" not in out
+
+
+def test_normaliser_and_sparse_future_kernels():
+    out = build_and_run("check_misc_kernels", "misc_kernels.inc", ["k_norm", "k_norm_fast", "k_fut_count", "k_fut_compact"])
+    assert out.count("identical") == 16 and "DIFFERENT" not in out
