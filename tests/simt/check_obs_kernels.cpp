@@ -14,7 +14,8 @@
 #include <random>
 
 namespace {
-const int Nh = 4, Nv = 3, P = Nh * Nv, NBW = 10, OBS = 100;
+int Nh = 4, Nv = 3, P = Nh * Nv, NBN = 1, NBW = 10;  // geometry of the current scene (3 x 3 or 5 x 5 neighbourhoods)
+const int OBS = 100;
 
 struct Scene {
     MapConst mc;
@@ -25,13 +26,14 @@ struct Scene {
     int n_fov = 0, n_pts = 0;
 };
 
-Scene make_scene(unsigned seed) {
+Scene make_scene(unsigned seed, int nh, int nv, int nbn) {
+    Nh = nh; Nv = nv; P = nh * nv; NBN = nbn; NBW = (2 * nbn + 1) * (2 * nbn + 1) + 1;
     Scene s;
     std::mt19937 rng(seed);
     auto uni = [&](float lo, float hi) { return lo + (hi - lo) * (float)(rng() >> 8) / 16777216.f; };
     memset(&s.mc, 0, sizeof(s.mc));
     memset(&s.fc, 0, sizeof(s.fc));
-    s.mc.P = P; s.mc.NB = 9; s.mc.NBW = NBW; s.mc.OBS = OBS; s.mc.Nh = Nh; s.mc.Nv = Nv; s.mc.occl = 0.3f;
+    s.mc.P = P; s.mc.NB = NBW - 1; s.mc.NBW = NBW; s.mc.OBS = OBS; s.mc.Nh = Nh; s.mc.Nv = Nv; s.mc.occl = 0.3f;
     s.mc.cap_pairs = 1ll << 40;
     s.fc.sigma = 0.1f; s.fc.sigma_r = 1.f / 0.1f; s.fc.fast_sigma = 0; s.fc.Pd = 0.95f; s.fc.one_minus_Pd = 1 - 0.95f;
     s.fc.kappa = 0.01f; s.fc.nb_weight = 1e-4f; s.fc.nb_num = 20;
@@ -46,8 +48,8 @@ Scene make_scene(unsigned seed) {
     for (int p = 0; p < P; ++p) {
         const int h = p / Nv, v = p % Nv;
         int n = 0;
-        for (int i = -1; i <= 1; ++i)
-            for (int j = -1; j <= 1; ++j)
+        for (int i = -NBN; i <= NBN; ++i)
+            for (int j = -NBN; j <= NBN; ++j)
                 if (h + i >= 0 && h + i < Nh && v + j >= 0 && v + j < Nv) s.nbr[p * NBW + 1 + n++] = (h + i) * Nv + v + j;
         s.nbr[p * NBW] = n;
     }
@@ -159,8 +161,8 @@ Result run(const Scene &s, bool col, CzKernel czk, bool quot_fast) {
 
 int main() {
     int bad = 0;
-    for (unsigned seed = 1; seed <= 2; ++seed) {
-        const Scene s = make_scene(seed);
+    for (unsigned seed = 1; seed <= 3; ++seed) {
+        const Scene s = seed < 3 ? make_scene(seed, 4, 3, 1) : make_scene(seed, 5, 5, 2);  // the last one: multiple-neighbours variant
         const Result ref = run(s, false, CZ_DEFAULT, false);
         int changed = 0, tiny = 0;
         for (int i = 0; i < s.n_fov; ++i) changed += ref.W[i] != s.w0[i];
