@@ -968,7 +968,6 @@ int dspmap_shard_config(dspmap *m, int rank, int nranks, float *xsend, float *xr
     dp.nst_shared = shared;                          // newborn split first, then the new weights by global list index
     dp.NW = shared + m->max_points;
     m->fallback_armed = false;  // sharded frames always use the pair buffer (checked: overflow flag otherwise)
-    m->g_col = false;           // the sharded phases launch the row-major observation kernels
     return DSPMAP_OK;
 }
 int dspmap_shard_gather_records(dspmap *m, int records) {
@@ -1036,14 +1035,24 @@ int dspmap_shard_phase(dspmap *m, int phase, int n, const float *d_pts, float px
         LAUNCH(m, FAM_CK, k_pair_prep, grid_for(mc.P, B), B, 0, mc, dp, m->g_col ? 1 : 0);
         LAUNCH(m, FAM_CK, k_scan_small, 2, 1024, 0, ScanJobs{{ScanJob{dp.pairs, dp.rowbase, nullptr, 0, mc.P}, ScanJob{dp.chunks, dp.chunk_off, nullptr, 0, mc.P}, ScanJob{}}});
         LAUNCH(m, FAM_CK, k_shard_zero, kSMs * 2, B, 0, mc, fc, dp, 0);
+        if (m->g_col) {
+            LAUNCH(m, FAM_CK, k_pair_eval_col, kSMs * 4, EVAL_THREADS, sizeof(float) * (DSP_LUT_HALF + 3 + EVALC_KEYS), mc, fc, dp, 1);
+            LAUNCH(m, FAM_CK, k_cz_chain_col, std::min(mc.P, kSMs * 2), CZC_THREADS, CZC_SMEM_BYTES, mc, fc, dp);
+        } else {
         LAUNCH(m, FAM_CK, k_pair_eval, kSMs * 2, EVAL_THREADS, sizeof(float) * (DSP_LUT_HALF + 3 + (EVAL_THREADS / 32) * 32 * TILE_LD), mc, fc, dp, 1);
         if (m->cz_tma) LAUNCH(m, FAM_CK, k_cz_chain_tma, std::min(mc.P, kSMs * 2), CZT_THREADS, CZT_SMEM_BYTES, mc, fc, dp);
         else if (m->cz_staged) LAUNCH(m, FAM_CK, k_cz_wide_staged, std::min(mc.P, kSMs * 3), 256, sizeof(float) * (2 * (8192 + 8) + 2 * 128), mc, fc, dp);
         else if (m->cz_wide) LAUNCH(m, FAM_CK, k_cz_wide, std::min(mc.P, kSMs * 3), 256, sizeof(float) * (2 * (8192 + 8) + 2 * 128), mc, fc, dp);
         else LAUNCH(m, FAM_CK, k_cz_narrow, std::min(mc.P, kSMs * 6), 128, sizeof(float) * (2 * (4096 + 8) + 2 * 128), mc, fc, dp);
+        }
     } else if (phase == 3) {
         dp.tagged = d_tagged;
         LAUNCH(m, FAM_WEIGHT, k_shard_zero, kSMs * 2, B, 0, mc, fc, dp, 1);
+        if (m->g_col) {
+            LAUNCH(m, FAM_WEIGHT, k_pair_eval_col, kSMs * 4, EVAL_THREADS, sizeof(float) * (DSP_LUT_HALF + 3 + EVALC_KEYS), mc, fc, dp, 2);
+            if (m->quot_fast) LAUNCH(m, FAM_WEIGHT, k_weight_cq, kSMs * 8, 256, 0, mc, fc, dp);
+            else LAUNCH(m, FAM_WEIGHT, k_weight_c, kSMs * 8, 256, 0, mc, fc, dp);
+        } else {
         LAUNCH(m, FAM_WEIGHT, k_pair_eval, kSMs * 2, EVAL_THREADS, sizeof(float) * (DSP_LUT_HALF + 3 + (EVAL_THREADS / 32) * 32 * TILE_LD), mc, fc, dp, 2);
         if (m->quot_fast) {
             LAUNCH(m, FAM_WEIGHT, k_weight2q, kSMs * 8, W2_THREADS, 0, mc, fc, dp);
@@ -1051,6 +1060,7 @@ int dspmap_shard_phase(dspmap *m, int phase, int n, const float *d_pts, float px
         } else {
             LAUNCH(m, FAM_WEIGHT, k_weight2, kSMs * 8, W2_THREADS, 0, mc, fc, dp);
             LAUNCH(m, FAM_WEIGHT, k_weight2w, kSMs * 6, W2W_THREADS, 0, mc, fc, dp);
+        }
         }
     } else if (phase == 4) {  // owners take their new weights; the newborn split reads them (dsp_dynamic.h:829-866)
         dp.tagged = d_tagged;
