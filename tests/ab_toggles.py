@@ -201,16 +201,29 @@ def main():
             m.getOccupancyMapWithFutureStatus(0.2, fut_host)
             if k >= W:
                 ts.append(time.perf_counter() - t0)
+        # per-kernel device time (CUDA events around every launch site) on the frames of the stream that are left
+        m.profile_enable(True)
+        NP = min(10, pre)
+        for k in range(NP):
+            f = 2 * F - pre + k
+            flush.zero_()
+            gpu_update(m, st["points"][f], st["pos"][f], st["t"][f], st["quat"][f])
+            m.get_occupancy_device(0.2, d_xyz.data_ptr(), m.V, d_cnt.data_ptr(), d_fut.data_ptr())
+        m.synchronize()
+        kern = {n: round(1e3 * ms / NP, 2) for n, (ms, ln) in m.profile_read_kernels().items() if ln}
+        m.profile_enable(False)
         m.close()
-        return dev_ms, 1e3 * float(np.mean(ts))
+        return dev_ms, 1e3 * float(np.mean(ts)), kern
 
     base = None
     if args.baseline == "measure":  # driver's first child: time the default path once for all sets
-        b_dev, b_host = timing(args.cfg, {}, args.steps)
+        b_dev, b_host, b_kern = timing(args.cfg, {}, args.steps)
+        json.dump({"dev": b_dev, "host": b_host, "kernels": b_kern}, open(args.out + ".baseline", "w"))
         print("BASELINE %r,%r" % (b_dev, b_host), flush=True)
         return 0
     if args.baseline:
-        base = tuple(float(x) for x in args.baseline.split(","))
+        bj = json.load(open(args.out + ".baseline"))
+        base = (bj["dev"], bj["host"], bj["kernels"])
     for spec in args.sets:
         env = dict(kv.split("=", 1) for kv in spec.split(",") if kv)
         rec = {"switches": env, "cfg": args.cfg}
@@ -228,9 +241,12 @@ def main():
         if args.steps > 0:
             if base is None:
                 base = timing(args.cfg, {}, args.steps)
-            base_dev, base_host = base
-            sw_dev, sw_host = timing(args.cfg, env, args.steps)
-            emit({"switches": env, "cfg": args.cfg, "stage": "timing", "steps": args.steps,
+            base_dev, base_host, base_kern = base
+            sw_dev, sw_host, sw_kern = timing(args.cfg, env, args.steps)
+            # kernels whose device time per frame moved by more than 1 us (replaying already-seen frames: comparable state)
+            moved = {n: [base_kern.get(n), sw_kern.get(n)] for n in sorted(set(base_kern) | set(sw_kern))
+                     if abs((base_kern.get(n) or 0.0) - (sw_kern.get(n) or 0.0)) > 1.0}
+            emit({"switches": env, "cfg": args.cfg, "stage": "timing", "steps": args.steps, "kernel_us_per_frame_baseline_vs_switched": moved,
                   "device_ms_per_frame": {"baseline": base_dev, "switched": sw_dev},
                   "host_api_ms_per_frame": {"baseline": base_host, "switched": sw_host},
                   "updates_per_s_device": {"baseline": 1e3 / base_dev, "switched": 1e3 / sw_dev},
