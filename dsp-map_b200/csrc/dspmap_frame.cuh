@@ -602,6 +602,76 @@ __global__ void __launch_bounds__(512) k_pyr_sort(MapConst mc, DevPtrs dp, float
         }
     }
 }
+// k_pyr_sort with warp-local sorting stages (experiment switch DSPMAP_SORT_WARP=1): of the 55 stages of a 1024-key bitonic
+// network 40 exchange keys less than 32 apart; with one thread per pair those stay inside one warp's 64-element block and
+// are separated by __syncwarp instead of the block-wide barrier the profile shows as the kernel's first stall (27 %).
+// Same keys, unique, fully sorted: the outputs are those of k_pyr_sort.
+__global__ void __launch_bounds__(512) k_pyr_sort_w(MapConst mc, DevPtrs dp, float Pd) {
+    pdl_enter();
+    extern __shared__ u64 skey[];  // PYR_SORT_CAP entries: (sweep key << 32) | slot address
+    for (int q = blockIdx.x; q < mc.P; q += gridDim.x) {
+        const int n = dp.pcount[q], b = dp.poff[q];
+        const int keep = min(n, mc.L);
+        if (threadIdx.x == 0) dp.plen[q] = keep;
+        if (n == 0) continue;
+        if (n <= PYR_SORT_CAP) {
+            int m = 1;
+            while (m < n) m <<= 1;
+            for (int i = threadIdx.x; i < m; i += blockDim.x)
+                skey[i] = i < n ? ((u64)(unsigned)dp.PSkey[b + i] << 32) | (unsigned)(mc.sharded ? i : dp.PSaddr[b + i]) : ~0ull;
+            __syncthreads();
+            // one thread per compare-exchange PAIR; a warp's 32 consecutive pairs of a stage with j <= 16 lie inside one
+            // 64-element block that no other warp touches in that stage, so those stages need a warp barrier only
+            for (int k = 2; k <= m; k <<= 1) {
+                if (k >= 64) __syncthreads();  // the previous round ended in warp-local stages: publish them block-wide
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    for (int t = threadIdx.x; t < (m >> 1); t += blockDim.x) {
+                        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), p = i | j;
+                        const u64 x = skey[i], y = skey[p];
+                        const bool up = (i & k) == 0;
+                        if ((x > y) == up) { skey[i] = y; skey[p] = x; }
+                    }
+                    if (j >= 32) __syncthreads(); else __syncwarp();
+                }
+            }
+            __syncthreads();
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                int a = (int)(unsigned)(skey[i] & 0xffffffffull);
+                float4 pa;
+                if (mc.sharded) {  // the low word is the position inside the segment: address and payload come from there
+                    pa = dp.PSpay[b + a];
+                    a = dp.PSaddr[b + a];
+                } else {
+                    pa = dp.PA[a];
+                }
+                if (i < keep) {
+                    dp.LA[b + i] = a;
+                    dp.LP[b + i] = pa;
+                    dp.PW[b + i] = Pd * pa.w;
+                } else if (a >= 0) {  // pyramid full: the particle vanishes and frees its voxel slot (:1256-1259)
+                    mask_atomic_clear(dp.M, a / mc.S, a % mc.S);
+                    atomicAdd(&dp.st->n_pyramid_full, 1);
+                }
+            }
+            __syncthreads();
+        } else {  // oversized segment: rank by counting straight from global memory (slow, rare)
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                int ki = dp.PSkey[b + i], r = 0;
+                for (int j = 0; j < n; ++j) r += dp.PSkey[b + j] < ki;
+                int a = dp.PSaddr[b + i];
+                if (r < keep) {
+                    const float4 pa = mc.sharded ? dp.PSpay[b + i] : dp.PA[a];
+                    dp.LA[b + r] = a;
+                    dp.LP[b + r] = pa;
+                    dp.PW[b + r] = Pd * pa.w;
+                } else if (a >= 0) {
+                    mask_atomic_clear(dp.M, a / mc.S, a % mc.S);
+                    atomicAdd(&dp.st->n_pyramid_full, 1);
+                }
+            }
+        }
+    }
+}
 
 // ------------------------------------------------------------------------------------------------------------
 // K4  C_z pass (dsp_dynamic.h:709-739).  For every observation point z of pyramid i:

@@ -1,11 +1,13 @@
 // check_misc_kernels.cpp — CPU check of two more kernel variants under simt_host.h (TEST INFRASTRUCTURE):
 //   k_norm_fast against k_norm (one fp32 chain over all 1/C_z: same bits), and
-//   k_fut_count / k_fut_compact (the sparse copy-out of the future grid) against the rows a host loop finds.
+//   k_fut_count / k_fut_compact (the sparse copy-out of the future grid) against the rows a host loop finds,
+//   k_pyr_sort_w (warp-local sorting stages) against k_pyr_sort and against std::sort.
 #include "simt_host.h"
 
 #include "dspmap_kernels.cuh"
 #include "misc_kernels.inc"
 
+#include <algorithm>
 #include <random>
 
 int main() {
@@ -61,6 +63,52 @@ int main() {
         for (int k = 0; ok && k < nf; ++k)
             ok = fidx[k] == want[k] && memcmp(&fval[(size_t)k * mc.T], &fut[(size_t)want[k] * mc.T], 4 * mc.T) == 0;
         printf("sparse future rows, %4d voxels: %d rows %s\n", V, nf, ok ? "identical" : "DIFFERENT");
+        bad += ok ? 0 : 1;
+    }
+    // ---- pyramid-list sort: warp-local stages against the block-barrier network
+    for (unsigned seed = 1; seed <= 2; ++seed) {
+        std::mt19937 r2(seed);
+        MapConst mc;
+        memset(&mc, 0, sizeof(mc));
+        mc.P = 14; mc.S = 48; mc.L = 700;
+        const int sizes[14] = {0, 1, 2, 3, 31, 32, 33, 64, 100, 513, 700, 1024, 1500, 2049};
+        std::vector<int> pcount(sizes, sizes + 14), poff(15, 0);
+        for (int q = 0; q < 14; ++q) poff[q + 1] = poff[q] + pcount[q];
+        const int n = poff[14];
+        std::vector<int> key(n), addr(n);
+        std::vector<int> perm(n);
+        for (int i = 0; i < n; ++i) perm[i] = i;
+        std::shuffle(perm.begin(), perm.end(), r2);
+        for (int i = 0; i < n; ++i) { key[i] = perm[i] * 3 + 1; addr[i] = (int)(r2() % 4000) * 1 + 0; }
+        std::sort(addr.begin(), addr.end());
+        addr.erase(std::unique(addr.begin(), addr.end()), addr.end());
+        while ((int)addr.size() < n) addr.push_back((int)addr.size() + 5000);  // distinct slot addresses
+        std::shuffle(addr.begin(), addr.end(), r2);
+        std::vector<float4> PA(20000);
+        for (auto &x : PA) x = make_float4((float)(r2() % 1000), 1.f, 2.f, (float)(1 + r2() % 200) / 4096.f);
+        struct Out { std::vector<int> LA, plen; std::vector<float4> LP; std::vector<float> PW; std::vector<ulonglong2> M; DevState st; } o[2];
+        for (int k = 0; k < 2; ++k) {
+            o[k].LA.assign(n, -1); o[k].plen.assign(14, -1); o[k].LP.assign(n, make_float4(-1, -1, -1, -1)); o[k].PW.assign(n, -1.f);
+            o[k].M.assign(500, make_ulonglong2(~0ull, ~0ull));
+            memset(&o[k].st, 0, sizeof(DevState));
+            DevPtrs dp;
+            memset(&dp, 0, sizeof(dp));
+            dp.pcount = pcount.data(); dp.poff = poff.data(); dp.plen = o[k].plen.data(); dp.PSkey = key.data(); dp.PSaddr = addr.data();
+            dp.PA = PA.data(); dp.LA = o[k].LA.data(); dp.LP = o[k].LP.data(); dp.PW = o[k].PW.data(); dp.M = o[k].M.data(); dp.st = &o[k].st;
+            if (k == 0) simt::launch_block(512, [&] { k_pyr_sort(mc, dp, 0.95f); });
+            else simt::launch_block(512, [&] { k_pyr_sort_w(mc, dp, 0.95f); });
+        }
+        bool ok = o[0].LA == o[1].LA && o[0].plen == o[1].plen && memcmp(o[0].LP.data(), o[1].LP.data(), 16 * (size_t)n) == 0 &&
+                  memcmp(o[0].PW.data(), o[1].PW.data(), 4 * (size_t)n) == 0 && memcmp(o[0].M.data(), o[1].M.data(), 16 * 500) == 0 &&
+                  o[0].st.n_pyramid_full == o[1].st.n_pyramid_full && o[0].st.n_pyramid_full > 0;
+        // and the reference result is really sorted by key
+        for (int q = 0; ok && q < 14; ++q) {
+            std::vector<std::pair<int, int>> kv;
+            for (int i = poff[q]; i < poff[q + 1]; ++i) kv.push_back({key[i], addr[i]});
+            std::sort(kv.begin(), kv.end());
+            for (int i = 0; ok && i < std::min((int)kv.size(), mc.L); ++i) ok = o[1].LA[poff[q] + i] == kv[i].second;
+        }
+        printf("pyramid-list sort seed %u: %d keys in 14 lists, %d dropped beyond L: %s\n", seed, n, o[0].st.n_pyramid_full, ok ? "identical" : "DIFFERENT");
         bad += ok ? 0 : 1;
     }
     return bad ? 1 : 0;
