@@ -19,6 +19,7 @@
 #include "dspmap_frame.cuh"
 #include "velocity_estimator.h"
 #include "host_worker.h"
+#include "sparse_rows.h"
 
 namespace {
 
@@ -88,8 +89,7 @@ struct dspmap {
     int *d_fcnt = nullptr, *d_foff = nullptr, *d_fidx = nullptr, *d_nf = nullptr, *h_fidx = nullptr, *h_nf = nullptr;
     float *d_fval = nullptr, *h_fval = nullptr;
     int fut_guess = 8192;                 // rows copied along with their count
-    float *sparse_ptr = nullptr;          // the caller buffer that holds exactly the previous call's result
-    std::vector<int> sparse_prev;         // its non-zero rows
+    SparseRows sparse_rows;               // which caller buffer holds the previous call's result, and its non-zero rows
     // pipelined reader (dspmap_get_occupancy_async): two result slots, copies on their own stream
     struct ReaderSlot {
         float *d_xyz = nullptr, *d_future = nullptr, *h_xyz = nullptr, *h_future = nullptr;
@@ -1182,7 +1182,7 @@ int dspmap_get_occupancy(dspmap *m, float thr, float *xyz_out, int cap, int *n_o
         CK(cudaMemcpyAsync(m->h_fval, m->d_fval, sizeof(float) * (size_t)fguess * mc.T, cudaMemcpyDeviceToHost, m->stream));
     } else if (future) {
         CK(cudaMemcpyAsync(direct ? future : m->h_future, m->d_future, fbytes, cudaMemcpyDeviceToHost, m->stream));
-        if (direct) m->sparse_ptr = nullptr;  // a dense copy went into the buffer: the row list no longer describes it
+        if (direct) m->sparse_rows.invalidate();  // a dense copy went into the buffer: the row list no longer describes it
     }
     CK(cudaStreamSynchronize(m->stream));
     if (sparse) {
@@ -1194,15 +1194,7 @@ int dspmap_get_occupancy(dspmap *m, float thr, float *xyz_out, int cap, int *n_o
             CK(cudaStreamSynchronize(m->stream));
         }
         m->fut_guess = std::max(8192, 2 * nf);
-        const size_t row = sizeof(float) * (size_t)mc.T;
-        if (m->sparse_ptr != future) {  // first use of this buffer (or a dense copy in between): its content is unknown
-            memset(future, 0, fbytes);
-            m->sparse_ptr = future;
-        } else {
-            for (int v : m->sparse_prev) memset(future + (size_t)v * mc.T, 0, row);
-        }
-        for (int k = 0; k < nf; ++k) memcpy(future + (size_t)m->h_fidx[k] * mc.T, m->h_fval + (size_t)k * mc.T, row);
-        m->sparse_prev.assign(m->h_fidx, m->h_fidx + nf);
+        m->sparse_rows.apply(future, mc.V, mc.T, m->h_fidx, m->h_fval, nf);
     }
     if (m->async_update && m->update_counter > 0) m->last_state = *m->h_state;  // the frame's state copy has landed by now
     int n = *m->h_count;
@@ -1285,8 +1277,7 @@ int dspmap_pin_host_buffer(dspmap *m, void *ptr, size_t bytes) {
         m->pinned_user = nullptr;
         m->pinned_bytes = 0;
     }
-    m->sparse_ptr = nullptr;
-    m->sparse_prev.clear();
+    m->sparse_rows.invalidate();
     if (ptr && bytes) {
         if (cudaHostRegister(ptr, bytes, cudaHostRegisterPortable) != cudaSuccess) {
             cudaGetLastError();  // not fatal: the staged path stays in use

@@ -6,6 +6,7 @@
 
 #include "dspmap_kernels.cuh"
 #include "misc_kernels.inc"
+#include "sparse_rows.h"
 
 #include <algorithm>
 #include <random>
@@ -63,6 +64,31 @@ int main() {
         for (int k = 0; ok && k < nf; ++k)
             ok = fidx[k] == want[k] && memcmp(&fval[(size_t)k * mc.T], &fut[(size_t)want[k] * mc.T], 4 * mc.T) == 0;
         printf("sparse future rows, %4d voxels: %d rows %s\n", V, nf, ok ? "identical" : "DIFFERENT");
+        bad += ok ? 0 : 1;
+    }
+    // ---- host side of the sparse copy-out: a sequence of grids through SparseRows::apply equals the dense grids
+    {
+        const int V = 3000, T = 6;
+        std::vector<float> bufA((size_t)V * T, 9.f), bufB((size_t)V * T, -3.f), dense((size_t)V * T);
+        SparseRows sr;
+        bool ok = true;
+        for (int frame = 0; frame < 12 && ok; ++frame) {
+            std::fill(dense.begin(), dense.end(), 0.f);
+            std::vector<int> idx;
+            std::vector<float> val;
+            for (int v = 0; v < V; ++v)
+                if (rng() % (frame % 3 == 0 ? 5 : 40) == 0) {
+                    for (int t = 0; t < T; ++t) dense[(size_t)v * T + t] = rng() % 2 ? uni(0.01f, 1.f) : 0.f;
+                    dense[(size_t)v * T + rng() % T] = uni(0.01f, 1.f);
+                    idx.push_back(v);
+                    val.insert(val.end(), dense.begin() + (size_t)v * T, dense.begin() + (size_t)(v + 1) * T);
+                }
+            float *target = frame == 6 ? bufB.data() : bufA.data();  // the application switches arrays once, and back
+            if (frame == 9) { std::fill(bufA.begin(), bufA.end(), 5.f); sr.invalidate(); }  // a dense copy overwrote it
+            sr.apply(target, V, T, idx.data(), val.data(), (int)idx.size());
+            ok = memcmp(target, dense.data(), sizeof(float) * dense.size()) == 0;
+        }
+        printf("sparse rows applied on the host over 12 frames: %s\n", ok ? "identical" : "DIFFERENT");
         bad += ok ? 0 : 1;
     }
     // ---- pyramid-list sort: warp-local stages against the block-barrier network

@@ -40,4 +40,4 @@ def test_observation_pass_variants_equal_the_row_major_kernels():
 
 def test_normaliser_sparse_future_and_sort_kernels():
     out = build_and_run("check_misc_kernels", "misc_kernels.inc", ["k_norm", "k_norm_fast", "k_fut_count", "k_fut_compact", "k_pyr_sort", "k_pyr_sort_w"])
-    assert out.count("identical") == 18 and "DIFFERENT" not in out
+    assert out.count("identical") == 19 and "DIFFERENT" not in out
