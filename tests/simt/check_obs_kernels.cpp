@@ -157,6 +157,71 @@ Result run(const Scene &s, bool col, CzKernel czk, bool quot_fast) {
     for (int i = 0; i < s.n_fov; ++i) r.W[i] = PA[i].w;
     return r;
 }
+// The same pass sharded over `nranks` ranks the way dspmap_shard_phase runs it: rank r evaluates and chains the point
+// pyramids i % nranks == r (mode 1) into a zero-initialised C_z buffer, the buffers are summed (all-reduce: one writer per
+// element); then rank r evaluates and weighs the particle chunks c % nranks == r (mode 2) into a zero-initialised weight
+// buffer, which is summed and applied through the list's slot addresses.
+Result run_sharded(const Scene &s, bool col, int nranks) {
+    const FrameConst fc = s.fc;
+    std::vector<float> CZ((size_t)P * OBS, 0.f), INV(s.n_pts + 8, 0.f), NW(s.n_fov + 8, 0.f);
+    std::vector<float4> PA(s.n_fov);
+    for (int i = 0; i < s.n_fov; ++i) PA[i] = make_float4(0, 0, 0, s.w0[i]);
+    for (int phase = 0; phase < 2; ++phase)
+        for (int rank = 0; rank < nranks; ++rank) {
+            MapConst mc = s.mc;
+            mc.sharded = 1; mc.nranks = nranks; mc.rank = rank;
+            DevState st;
+            memset(&st, 0, sizeof(st));
+            st.n_valid = s.n_pts;
+            std::vector<int> cum(P * NBW), totlen(P), pairs(P + 1), rowbase(P + 1), chunks(P + 1), chunk_off(P + 1), cz_order(P);
+            std::vector<float> cz_r((size_t)P * OBS, 0.f), inv_r(s.n_pts + 8, 0.f), nw_r(s.n_fov + 8, 0.f);
+            DevPtrs dp;
+            memset(&dp, 0, sizeof(dp));
+            dp.st = &st; dp.nbr = s.nbr.data(); dp.obs_cnt = const_cast<int *>(s.obs_cnt.data()); dp.obs_maxbits = const_cast<int *>(s.obs_maxbits.data());
+            dp.obs_capoff = const_cast<int *>(s.obs_capoff.data()); dp.plen = const_cast<int *>(s.plen.data()); dp.poff = const_cast<int *>(s.poff.data());
+            dp.OBSP = const_cast<float4 *>(s.OBSP.data()); dp.LP = const_cast<float4 *>(s.LP.data()); dp.PW = const_cast<float *>(s.PW.data());
+            dp.LA = const_cast<int *>(s.LA.data()); dp.lut = s.lut.data(); dp.PA = PA.data();
+            dp.CZ = phase == 0 ? cz_r.data() : CZ.data();    // phase 1 reads the merged C_z
+            dp.INV = phase == 0 ? inv_r.data() : INV.data();
+            dp.NW = nw_r.data();
+            dp.cum = cum.data(); dp.totlen = totlen.data(); dp.pairs = pairs.data(); dp.rowbase = rowbase.data(); dp.chunks = chunks.data();
+            dp.chunk_off = chunk_off.data();
+            dp.cz_order = col ? cz_order.data() : nullptr;
+            simt::launch_block(32, [&] { k_pair_prep(mc, dp, col ? 1 : 0); });
+            rowbase[0] = chunk_off[0] = 0;
+            for (int p = 0; p < P; ++p) { rowbase[p + 1] = rowbase[p] + pairs[p]; chunk_off[p + 1] = chunk_off[p] + chunks[p]; }
+            float *G = static_cast<float *>(aligned_alloc(256, sizeof(float) * ((size_t)rowbase[P] + 128)));
+            for (size_t i = 0; i < (size_t)rowbase[P] + 128; ++i) G[i] = NAN;
+            dp.G = G;
+            const int mode = phase + 1;
+            if (col) simt::launch_block(EVAL_THREADS, [&] { k_pair_eval_col(mc, fc, dp, mode); });
+            else simt::launch_block(EVAL_THREADS, [&] { k_pair_eval(mc, fc, dp, mode); });
+            if (phase == 0) {
+                if (col) simt::launch_block(CZC_THREADS, [&] { k_cz_chain_col(mc, fc, dp); });
+                else simt::launch_block(256, [&] { k_cz_chain<256, 8192, 128>(mc, fc, dp); });
+                for (size_t i = 0; i < CZ.size(); ++i) CZ[i] += cz_r[i];
+                for (int i = 0; i < s.n_pts; ++i) INV[i] += inv_r[i];
+            } else {
+                if (col) simt::launch_block(32, [&] { k_weight_col<false>(mc, fc, dp); });
+                else simt::launch_block(W2_THREADS, [&] { k_weight2_t<false>(mc, fc, dp); }, 96);
+                for (int i = 0; i < s.n_fov; ++i) NW[i] += nw_r[i];
+            }
+            free(G);
+        }
+    Result r;
+    r.CZ = CZ;
+    r.INV.assign(INV.begin(), INV.begin() + s.n_pts);
+    r.W.resize(s.n_fov);
+    for (int i = 0; i < s.n_fov; ++i) r.W[i] = NW[s.LA[i]];  // k_shard_apply_weights: PA[LA[i]].w = NW[i], LA is the identity here
+    return r;
+}
+// C_z entries that exist (pyramids with points): the sharded buffers are zero where the single-rank pass leaves them untouched
+std::vector<float> valid_cz(const Scene &s, const std::vector<float> &cz) {
+    std::vector<float> out;
+    for (int p = 0; p < P; ++p)
+        for (int z = 0; z < std::min(s.obs_cnt[p], OBS - 1); ++z) out.push_back(cz[(size_t)p * OBS + z]);
+    return out;
+}
 }  // namespace
 
 int main() {
@@ -182,6 +247,14 @@ int main() {
             ok &= same(ref.INV, r.INV, "1 / C_z");
             ok &= same(ref.W, r.W, "particle weights");
             printf("  %-42s %s\n", c.name, ok ? "identical" : "DIFFERENT");
+            bad += ok ? 0 : 1;
+        }
+        for (int col = 0; col < 2; ++col) {
+            const Result r = run_sharded(s, col != 0, seed == 2 ? 3 : 2);
+            bool ok = same(valid_cz(s, ref.CZ), valid_cz(s, r.CZ), "C_z");
+            ok &= same(ref.INV, r.INV, "1 / C_z");
+            ok &= same(ref.W, r.W, "particle weights");
+            printf("  %-42s %s\n", col ? "column-major family, sharded" : "row-major family, sharded", ok ? "identical" : "DIFFERENT");
             bad += ok ? 0 : 1;
         }
     }
