@@ -115,6 +115,7 @@ struct dspmap {
     bool async_update = false;    // dspmap_update returns once the frame is enqueued; the next call that needs results waits (DSPMAP_ASYNC_UPDATE=1)
     bool staged_pending = false;  // the page-locked staging buffers are still being read by the previous frame's copies
     cudaEvent_t ev_staged = nullptr;
+    bool eval_packed = false;     // k_pair_eval_col<true>: packed fp32 arithmetic, two points per step (DSPMAP_EVAL_PACKED=1, with G_COL)
     bool sort_warp = false;       // k_pyr_sort_w (DSPMAP_SORT_WARP=1)
     bool resample_sm = false;     // k_resample_sm (DSPMAP_RESAMPLE_SM=1)
     bool norm_fast = false;       // k_norm_fast (DSPMAP_NORM_FAST=1)
@@ -246,6 +247,7 @@ bool env_on(const char *name) {
 const int kSMs = 148;
 // the two configurations of the C_z chain kernel (threads, floats per tile, rows per tile)
 const auto k_weight2 = &k_weight2_t<false>, k_weight2q = &k_weight2_t<true>;
+const auto k_pair_eval_c = &k_pair_eval_col<false>, k_pair_eval_cp = &k_pair_eval_col<true>;  // scalar / packed fp32 arithmetic
 const auto k_weight_c = &k_weight_col<false>, k_weight_cq = &k_weight_col<true>;  // column-major pair buffer
 const auto k_weight2w = &k_weight2w_t<false>, k_weight2wq = &k_weight2w_t<true>;
 const auto k_cz_narrow = &k_cz_chain<128, 4096, 128>;
@@ -407,7 +409,8 @@ int enqueue_frame_a(dspmap *m, const FrameConst &fc, const float *d_pts, const f
         LAUNCH(m, FAM_CK, k_pair_prep, grid_for(mc.P, B), B, 0, mc, dp, m->g_col ? 1 : 0);
         LAUNCH(m, FAM_CK, k_scan_small, 2, 1024, 0, ScanJobs{{ScanJob{dp.pairs, dp.rowbase, nullptr, 0, mc.P}, ScanJob{dp.chunks, dp.chunk_off, nullptr, 0, mc.P}, ScanJob{}}});
         if (m->g_col) {
-            LAUNCH(m, FAM_CK, k_pair_eval_col, kSMs * 4, EVAL_THREADS, sizeof(float) * (DSP_LUT_HALF + 3 + EVALC_KEYS), mc, fc, dp, 0);
+            if (m->eval_packed) LAUNCH(m, FAM_CK, k_pair_eval_cp, kSMs * 4, EVAL_THREADS, sizeof(float) * (DSP_LUT_HALF + 3 + EVALC_KEYS), mc, fc, dp, 0);
+            else LAUNCH(m, FAM_CK, k_pair_eval_c, kSMs * 4, EVAL_THREADS, sizeof(float) * (DSP_LUT_HALF + 3 + EVALC_KEYS), mc, fc, dp, 0);
             LAUNCH(m, FAM_CK, k_cz_chain_col, std::min(mc.P, kSMs * 2), CZC_THREADS, CZC_SMEM_BYTES, mc, fc, dp);
         } else {
         LAUNCH(m, FAM_CK, k_pair_eval, kSMs * 2, EVAL_THREADS, sizeof(float) * (DSP_LUT_HALF + 3 + (EVAL_THREADS / 32) * 32 * TILE_LD), mc, fc, dp, 0);
@@ -772,7 +775,8 @@ int dspmap_create(const dspmap_config *cfg, dspmap **out) {
     CK(cudaFuncSetAttribute(k_cz_wide_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
     CK(cudaFuncSetAttribute(k_cz_chain_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, CZT_SMEM_BYTES));
     CK(cudaFuncSetAttribute(k_cz_chain_col, cudaFuncAttributeMaxDynamicSharedMemorySize, CZC_SMEM_BYTES));
-    CK(cudaFuncSetAttribute(k_pair_eval_col, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * (DSP_LUT_HALF + 3 + EVALC_KEYS))));
+    CK(cudaFuncSetAttribute(k_pair_eval_c, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * (DSP_LUT_HALF + 3 + EVALC_KEYS))));
+    CK(cudaFuncSetAttribute(k_pair_eval_cp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * (DSP_LUT_HALF + 3 + EVALC_KEYS))));
     // experiment switches; all off by default
     m->pdl = env_on("DSPMAP_PDL");
     m->cz_tma = env_on("DSPMAP_CZ_TMA");
@@ -784,6 +788,7 @@ int dspmap_create(const dspmap_config *cfg, dspmap **out) {
     m->norm_fast = env_on("DSPMAP_NORM_FAST");
     m->resample_sm = env_on("DSPMAP_RESAMPLE_SM");
     m->sort_warp = env_on("DSPMAP_SORT_WARP");
+    m->eval_packed = env_on("DSPMAP_EVAL_PACKED");
     m->est_thread = env_on("DSPMAP_EST_THREAD");
     m->sparse_future = env_on("DSPMAP_SPARSE_FUTURE");
     m->async_update = env_on("DSPMAP_ASYNC_UPDATE");
@@ -1041,7 +1046,8 @@ int dspmap_shard_phase(dspmap *m, int phase, int n, const float *d_pts, float px
         LAUNCH(m, FAM_CK, k_scan_small, 2, 1024, 0, ScanJobs{{ScanJob{dp.pairs, dp.rowbase, nullptr, 0, mc.P}, ScanJob{dp.chunks, dp.chunk_off, nullptr, 0, mc.P}, ScanJob{}}});
         LAUNCH(m, FAM_CK, k_shard_zero, kSMs * 2, B, 0, mc, fc, dp, 0);
         if (m->g_col) {
-            LAUNCH(m, FAM_CK, k_pair_eval_col, kSMs * 4, EVAL_THREADS, sizeof(float) * (DSP_LUT_HALF + 3 + EVALC_KEYS), mc, fc, dp, 1);
+            if (m->eval_packed) LAUNCH(m, FAM_CK, k_pair_eval_cp, kSMs * 4, EVAL_THREADS, sizeof(float) * (DSP_LUT_HALF + 3 + EVALC_KEYS), mc, fc, dp, 1);
+            else LAUNCH(m, FAM_CK, k_pair_eval_c, kSMs * 4, EVAL_THREADS, sizeof(float) * (DSP_LUT_HALF + 3 + EVALC_KEYS), mc, fc, dp, 1);
             LAUNCH(m, FAM_CK, k_cz_chain_col, std::min(mc.P, kSMs * 2), CZC_THREADS, CZC_SMEM_BYTES, mc, fc, dp);
         } else {
         LAUNCH(m, FAM_CK, k_pair_eval, kSMs * 2, EVAL_THREADS, sizeof(float) * (DSP_LUT_HALF + 3 + (EVAL_THREADS / 32) * 32 * TILE_LD), mc, fc, dp, 1);
@@ -1054,7 +1060,8 @@ int dspmap_shard_phase(dspmap *m, int phase, int n, const float *d_pts, float px
         dp.tagged = d_tagged;
         LAUNCH(m, FAM_WEIGHT, k_shard_zero, kSMs * 2, B, 0, mc, fc, dp, 1);
         if (m->g_col) {
-            LAUNCH(m, FAM_WEIGHT, k_pair_eval_col, kSMs * 4, EVAL_THREADS, sizeof(float) * (DSP_LUT_HALF + 3 + EVALC_KEYS), mc, fc, dp, 2);
+            if (m->eval_packed) LAUNCH(m, FAM_WEIGHT, k_pair_eval_cp, kSMs * 4, EVAL_THREADS, sizeof(float) * (DSP_LUT_HALF + 3 + EVALC_KEYS), mc, fc, dp, 2);
+            else LAUNCH(m, FAM_WEIGHT, k_pair_eval_c, kSMs * 4, EVAL_THREADS, sizeof(float) * (DSP_LUT_HALF + 3 + EVALC_KEYS), mc, fc, dp, 2);
             if (m->quot_fast) LAUNCH(m, FAM_WEIGHT, k_weight_cq, kSMs * 8, 256, 0, mc, fc, dp);
             else LAUNCH(m, FAM_WEIGHT, k_weight_c, kSMs * 8, 256, 0, mc, fc, dp);
         } else {

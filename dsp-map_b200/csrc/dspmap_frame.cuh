@@ -1031,6 +1031,23 @@ __global__ void __launch_bounds__(CZ_THREADS) k_cz_chain(MapConst mc, FrameConst
 // Sums are formed from the same terms in the same order: results are bit-identical.
 // ------------------------------------------------------------------------------------------------------------
 #define EVALC_KEYS 2048  // shared-memory room for cz_build_order (== CZ_ORDER_MAX)
+// Two points per step with Blackwell's packed fp32 arithmetic (experiment switch DSPMAP_EVAL_PACKED=1 on top of G_COL):
+// the subtraction, the three operations of the verified fast division, the scaling to a table index and the products are
+// issued as FADD2 / FMUL2 / FFMA2 on (point z, point z + 1) pairs — each half is the scalar IEEE operation, so the values
+// are the scalar kernel's; clamps, conversions and look-ups stay scalar.  Only with the verified division (fc.fast_sigma).
+__device__ __forceinline__ float2 dsp_pdf2_f(const float *lut, float x, float mu0, float mu1, const FrameConst &fc) {
+    const float2 a = __fadd2_rn(make_float2(x, x), make_float2(-mu0, -mu1));                  // x - mu
+    const float2 r = make_float2(fc.sigma_r, fc.sigma_r), b = make_float2(fc.sigma, fc.sigma);
+    const float2 q0 = __fmul2_rn(a, r);                                                       // dsp_div_known
+    const float2 e = __ffma2_rn(make_float2(-q0.x, -q0.y), b, a);
+    float2 c = __ffma2_rn(e, r, q0);
+    c.x = c.x > 9.9f ? 9.9f : (c.x < -9.9f ? -9.9f : c.x);
+    c.y = c.y > 9.9f ? 9.9f : (c.y < -9.9f ? -9.9f : c.y);
+    const float2 t = __fadd2_rn(__fmul2_rn(c, make_float2(1000.f, 1000.f)), make_float2(10000.f, 10000.f));
+    const int i0 = (int)t.x - 10000, i1 = (int)t.y - 10000;
+    return make_float2(lut[i0 < 0 ? -i0 : i0], lut[i1 < 0 ? -i1 : i1]);
+}
+template <bool PK>
 __global__ void __launch_bounds__(EVAL_THREADS) k_pair_eval_col(MapConst mc, FrameConst fc, DevPtrs dp, int mode) {
     extern __shared__ float sm[];
     float *lut = sm;
@@ -1066,13 +1083,27 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_pair_eval_col(MapConst mc, Fra
         const float4 *zs = dp.OBSP + (size_t)i * mc.OBS;
         // the next point is requested before the current one is evaluated (in the row-major kernel 14 % of the samples wait
         // for this load: profiles/r01_top_kernels.md)
-        float4 o = zs[0];
+        int z = 0;
+        if (PK && fc.fast_sigma) {  // two points per step; an odd last point goes through the scalar loop below
+            for (; z + 2 <= np; z += 2) {
+                const float4 o0 = zs[z], o1 = zs[z + 1];
+                const float2 g = __fmul2_rn(__fmul2_rn(dsp_pdf2_f(lut, p.x, o0.x, o1.x, fc), dsp_pdf2_f(lut, p.y, o0.y, o1.y, fc)),
+                                            dsp_pdf2_f(lut, p.z, o0.z, o1.z, fc));
+                if (mine) {
+                    gb[(size_t)z * tl] = g.x;
+                    gb[(size_t)(z + 1) * tl] = g.y;
+                }
+            }
+        }
+        if (z < np) {
+            float4 o = zs[z];
 #pragma unroll 2
-        for (int z = 0; z < np; ++z) {
-            const float4 on = zs[min(z + 1, np - 1)];
-            const float g = dsp_pdf_f(lut, p.x, o.x, fc) * dsp_pdf_f(lut, p.y, o.y, fc) * dsp_pdf_f(lut, p.z, o.z, fc);
-            if (mine) gb[(size_t)z * tl] = g;
-            o = on;
+            for (; z < np; ++z) {
+                const float4 on = zs[min(z + 1, np - 1)];
+                const float g = dsp_pdf_f(lut, p.x, o.x, fc) * dsp_pdf_f(lut, p.y, o.y, fc) * dsp_pdf_f(lut, p.z, o.z, fc);
+                if (mine) gb[(size_t)z * tl] = g;
+                o = on;
+            }
         }
     }
 }

@@ -108,10 +108,14 @@ bool same(const std::vector<float> &a, const std::vector<float> &b, const char *
 }
 
 enum CzKernel { CZ_DEFAULT, CZ_STAGED, CZ_TMA, CZ_COL };
-// One pass of the three observation kernels over the scene; col selects the column-major family.
-Result run(const Scene &s, bool col, CzKernel czk, bool quot_fast) {
+// One pass of the three observation kernels over the scene; col selects the column-major family, packed its evaluation
+// kernel with packed fp32 arithmetic (taken only with the verified fast division, so fast_sigma is switched on for it: on
+// the host the scalar path divides and the packed path runs the multiply / fused-correction sequence — the table index
+// they produce is the same for every reachable argument, which is what k_verify_div establishes on the device).
+Result run(const Scene &s, bool col, CzKernel czk, bool quot_fast, bool packed = false) {
     MapConst mc = s.mc;
-    const FrameConst fc = s.fc;
+    FrameConst fc = s.fc;
+    if (packed) fc.fast_sigma = 1;
     DevState st;
     memset(&st, 0, sizeof(st));
     st.n_valid = s.n_pts;
@@ -134,7 +138,8 @@ Result run(const Scene &s, bool col, CzKernel czk, bool quot_fast) {
     float *G = static_cast<float *>(aligned_alloc(256, sizeof(float) * ((size_t)rowbase[P] + 64 + 64)));
     for (size_t i = 0; i < (size_t)rowbase[P] + 128; ++i) G[i] = NAN;  // every element a consumer reads must have been produced
     dp.G = G;
-    if (col) simt::launch_block(EVAL_THREADS, [&] { k_pair_eval_col(mc, fc, dp, 0); });
+    if (col && packed) simt::launch_block(EVAL_THREADS, [&] { k_pair_eval_col<true>(mc, fc, dp, 0); });
+    else if (col) simt::launch_block(EVAL_THREADS, [&] { k_pair_eval_col<false>(mc, fc, dp, 0); });
     else simt::launch_block(EVAL_THREADS, [&] { k_pair_eval(mc, fc, dp, 0); });
     switch (czk) {
     case CZ_DEFAULT: simt::launch_block(256, [&] { k_cz_chain<256, 8192, 128>(mc, fc, dp); }); break;
@@ -194,7 +199,7 @@ Result run_sharded(const Scene &s, bool col, int nranks) {
             for (size_t i = 0; i < (size_t)rowbase[P] + 128; ++i) G[i] = NAN;
             dp.G = G;
             const int mode = phase + 1;
-            if (col) simt::launch_block(EVAL_THREADS, [&] { k_pair_eval_col(mc, fc, dp, mode); });
+            if (col) simt::launch_block(EVAL_THREADS, [&] { k_pair_eval_col<false>(mc, fc, dp, mode); });
             else simt::launch_block(EVAL_THREADS, [&] { k_pair_eval(mc, fc, dp, mode); });
             if (phase == 0) {
                 if (col) simt::launch_block(CZC_THREADS, [&] { k_cz_chain_col(mc, fc, dp); });
@@ -234,15 +239,16 @@ int main() {
         printf("scene %u: %d pyramids, %d registered particles, %d binned points; reference pass changed %d weights\n", seed, P, s.n_fov, s.n_pts, changed);
         if (changed < s.n_fov / 2) { printf("the scene does not exercise the weight pass\n"); ++bad; }
         (void)tiny;
-        struct Case { const char *name; bool col; CzKernel cz; bool qf; } cases[] = {
+        struct Case { const char *name; bool col; CzKernel cz; bool qf; bool packed = false; } cases[] = {
             {"k_cz_chain<STG>", false, CZ_STAGED, false},
             {"k_cz_chain_tma", false, CZ_TMA, false},
             {"k_weight2<QF>", false, CZ_DEFAULT, true},
             {"column-major family", true, CZ_COL, false},
             {"column-major family + dsp_quot fast path", true, CZ_COL, true},
+            {"column-major family, packed evaluation", true, CZ_COL, false, true},
         };
         for (const Case &c : cases) {
-            const Result r = run(s, c.col, c.cz, c.qf);
+            const Result r = run(s, c.col, c.cz, c.qf, c.packed);
             bool ok = same(ref.CZ, r.CZ, "C_z");
             ok &= same(ref.INV, r.INV, "1 / C_z");
             ok &= same(ref.W, r.W, "particle weights");

@@ -146,6 +146,11 @@ inline int atomicOr(int *p, int v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ
 using std::max;
 using std::min;
 
+// packed fp32 arithmetic of sm_100 (crt/sm_100_rt.h): each half is the scalar IEEE operation
+inline float2 __fadd2_rn(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+inline float2 __fmul2_rn(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+
 // cp.async pipelines (<cuda_pipeline.h>): the copy lands at once
 inline void __pipeline_memcpy_async(void *dst, const void *src, size_t n) { memcpy(dst, src, n); }
 inline void __pipeline_commit() {}

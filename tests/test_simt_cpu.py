@@ -34,8 +34,8 @@ def test_observation_pass_variants_equal_the_row_major_kernels():
     k_cz_chain -> k_weight2 bit for bit; the emulated cp.async.bulk aborts on a copy that breaks the 16-byte rules."""
     out = build_and_run("check_obs_kernels", "obs_kernels.inc",
                         ["use_pair_buffer", "chunk_to_pyramid", "nb_index_of", "cz_build_order", "k_pair_prep", "k_pair_eval", "k_cz_chain",
-                         "k_cz_chain_tma", "k_weight2_t", "k_pair_eval_col", "k_cz_chain_col", "k_weight_col"])
-    assert out.count("identical") == 21 and "DIFFERENT" not in out and "does not exercise" not in out
+                         "k_cz_chain_tma", "k_weight2_t", "dsp_pdf2_f", "k_pair_eval_col", "k_cz_chain_col", "k_weight_col"])
+    assert out.count("identical") == 24 and "DIFFERENT" not in out and "does not exercise" not in out
 
 
 def test_normaliser_sparse_future_and_sort_kernels():
