@@ -151,8 +151,13 @@ Result run(const Scene &s, bool col, CzKernel czk, bool quot_fast, bool packed =
         if (quot_fast) simt::launch_block(32, [&] { k_weight_col<true>(mc, fc, dp); });
         else simt::launch_block(32, [&] { k_weight_col<false>(mc, fc, dp); });
     } else {
+#ifdef CHECK_W2W  // built with -DW2_SWITCH=0: the warp-per-chunk kernel takes every frame
+        if (quot_fast) simt::launch_block(W2W_THREADS, [&] { k_weight2w_t<true>(mc, fc, dp); });
+        else simt::launch_block(W2W_THREADS, [&] { k_weight2w_t<false>(mc, fc, dp); });
+#else
         if (quot_fast) simt::launch_block(W2_THREADS, [&] { k_weight2_t<true>(mc, fc, dp); }, 96);
         else simt::launch_block(W2_THREADS, [&] { k_weight2_t<false>(mc, fc, dp); }, 96);
+#endif
     }
     free(G);
     Result r;
@@ -233,19 +238,28 @@ int main() {
     int bad = 0;
     for (unsigned seed = 1; seed <= 3; ++seed) {
         const Scene s = seed < 3 ? make_scene(seed, 4, 3, 1) : make_scene(seed, 5, 5, 2);  // the last one: multiple-neighbours variant
+#ifdef CHECK_W2W
+        const Result ref = run(s, true, CZ_COL, false);  // the column-major family (equal to k_weight2 by the other build of this check)
+#else
         const Result ref = run(s, false, CZ_DEFAULT, false);
+#endif
         int changed = 0, tiny = 0;
         for (int i = 0; i < s.n_fov; ++i) changed += ref.W[i] != s.w0[i];
         printf("scene %u: %d pyramids, %d registered particles, %d binned points; reference pass changed %d weights\n", seed, P, s.n_fov, s.n_pts, changed);
         if (changed < s.n_fov / 2) { printf("the scene does not exercise the weight pass\n"); ++bad; }
         (void)tiny;
         struct Case { const char *name; bool col; CzKernel cz; bool qf; bool packed = false; } cases[] = {
+#ifdef CHECK_W2W
+            {"k_weight2w (warp per chunk)", false, CZ_DEFAULT, false},
+            {"k_weight2w<QF>", false, CZ_DEFAULT, true},
+#else
             {"k_cz_chain<STG>", false, CZ_STAGED, false},
             {"k_cz_chain_tma", false, CZ_TMA, false},
             {"k_weight2<QF>", false, CZ_DEFAULT, true},
             {"column-major family", true, CZ_COL, false},
             {"column-major family + dsp_quot fast path", true, CZ_COL, true},
             {"column-major family, packed evaluation", true, CZ_COL, false, true},
+#endif
         };
         for (const Case &c : cases) {
             const Result r = run(s, c.col, c.cz, c.qf, c.packed);
@@ -255,6 +269,7 @@ int main() {
             printf("  %-42s %s\n", c.name, ok ? "identical" : "DIFFERENT");
             bad += ok ? 0 : 1;
         }
+#ifndef CHECK_W2W
         for (int col = 0; col < 2; ++col) {
             const Result r = run_sharded(s, col != 0, seed == 2 ? 3 : 2);
             bool ok = same(valid_cz(s, ref.CZ), valid_cz(s, r.CZ), "C_z");
@@ -263,6 +278,7 @@ int main() {
             printf("  %-42s %s\n", col ? "column-major family, sharded" : "row-major family, sharded", ok ? "identical" : "DIFFERENT");
             bad += ok ? 0 : 1;
         }
+#endif
     }
     return bad ? 1 : 0;
 }

@@ -12,12 +12,13 @@ BUILD = os.path.join(ROOT, "tests", "_build", "simt")
 CUH = os.path.join(ROOT, "dsp-map_b200", "csrc", "dspmap_frame.cuh")
 
 
-def build_and_run(check, inc, kernels, timeout=600):
+def build_and_run(check, inc, kernels, timeout=600, defines=(), tag=""):
     os.makedirs(BUILD, exist_ok=True)
     subprocess.check_call([sys.executable, os.path.join(SIMT, "extract.py"), CUH, os.path.join(BUILD, inc)] + kernels)
-    exe = os.path.join(BUILD, check)
+    exe = os.path.join(BUILD, check + tag)
     subprocess.check_call(["g++", "-std=c++20", "-O1", "-I/usr/local/cuda/include", "-I" + SIMT, "-I" + BUILD,
-                           "-I" + os.path.join(ROOT, "dsp-map_b200", "csrc"), os.path.join(SIMT, check + ".cpp"), "-o", exe, "-lpthread"])
+                           "-I" + os.path.join(ROOT, "dsp-map_b200", "csrc")] + ["-D" + d for d in defines] +
+                          [os.path.join(SIMT, check + ".cpp"), "-o", exe, "-lpthread"])
     r = subprocess.run([exe], capture_output=True, text=True, timeout=timeout)
     assert r.returncode == 0, r.stdout + r.stderr
     return r.stdout
@@ -36,6 +37,16 @@ def test_observation_pass_variants_equal_the_row_major_kernels():
                         ["use_pair_buffer", "chunk_to_pyramid", "nb_index_of", "cz_build_order", "k_pair_prep", "k_pair_eval", "k_cz_chain",
                          "k_cz_chain_tma", "k_weight2_t", "dsp_pdf2_f", "k_pair_eval_col", "k_cz_chain_col", "k_weight_col"])
     assert out.count("identical") == 24 and "DIFFERENT" not in out and "does not exercise" not in out
+
+
+def test_warp_per_chunk_weight_kernel_equals_the_other_weight_kernels():
+    """k_weight2w takes the frames with many particle chunks (cfg3, cfg5).  Built with W2_SWITCH = 0 it takes the small test
+    scenes too and has to reproduce the weights of the column-major family (which the test above ties to k_weight2)."""
+    out = build_and_run("check_obs_kernels", "obs_kernels.inc",
+                        ["use_pair_buffer", "chunk_to_pyramid", "nb_index_of", "cz_build_order", "k_pair_prep", "k_pair_eval", "k_cz_chain",
+                         "k_cz_chain_tma", "k_weight2_t", "k_weight2w_t", "dsp_pdf2_f", "k_pair_eval_col", "k_cz_chain_col", "k_weight_col"],
+                        defines=("CHECK_W2W", "W2_SWITCH=0"), tag="_w2w")
+    assert out.count("identical") == 6 and "DIFFERENT" not in out and "does not exercise" not in out
 
 
 def test_normaliser_sparse_future_and_sort_kernels():
