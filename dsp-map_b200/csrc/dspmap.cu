@@ -115,6 +115,7 @@ struct dspmap {
     bool async_update = false;    // dspmap_update returns once the frame is enqueued; the next call that needs results waits (DSPMAP_ASYNC_UPDATE=1)
     bool staged_pending = false;  // the page-locked staging buffers are still being read by the previous frame's copies
     cudaEvent_t ev_staged = nullptr;
+    bool fuse_scan = false;       // small scans fused into their producers' last block (DSPMAP_FUSE_SCAN=1)
     bool eval_packed = false;     // k_pair_eval_col<true>: packed fp32 arithmetic, two points per step (DSPMAP_EVAL_PACKED=1, with G_COL)
     bool sort_warp = false;       // k_pyr_sort_w (DSPMAP_SORT_WARP=1)
     bool resample_sm = false;     // k_resample_sm (DSPMAP_RESAMPLE_SM=1)
@@ -399,15 +400,23 @@ int enqueue_frame_a(dspmap *m, const FrameConst &fc, const float *d_pts, const f
     if (fc.vz_mode) LAUNCH(m, FAM_PREDICT, k_vz_advance, 1, 32, 0, mc, dp);
     LAUNCH(m, FAM_ARRIVE, k_group_owner, kSMs * 2, B, 0, dp, &dp.st->n_mov_owner, dp.mowner, dp.mcnt, dp.mbase, &dp.st->mov_top);
     LAUNCH(m, FAM_ARRIVE, k_group_scatter, kSMs * 4, B, 0, &dp.st->n_mov, dp.MBdst, dp.MBkey, dp.mbase, dp.mfill, dp.mseg, (int *)nullptr);
-    LAUNCH(m, FAM_ARRIVE, k_arrive, kSMs * 4, B, 0, mc, fc, dp);
-    LAUNCH(m, FAM_PYRAMID, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{dp.pcount, dp.poff, nullptr, 0, mc.P}, ScanJob{}, ScanJob{}}});
+    if (m->fuse_scan) {  // the scan of the pyramid counts rides on the arrival kernel's last block
+        LAUNCH(m, FAM_ARRIVE, k_arrive_fs, kSMs * 4, B, 0, mc, fc, dp);
+    } else {
+        LAUNCH(m, FAM_ARRIVE, k_arrive, kSMs * 4, B, 0, mc, fc, dp);
+        LAUNCH(m, FAM_PYRAMID, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{dp.pcount, dp.poff, nullptr, 0, mc.P}, ScanJob{}, ScanJob{}}});
+    }
     LAUNCH(m, FAM_PYRAMID, k_pyr_scatter, kSMs * 8, B, 0, dp);
     if (m->sort_warp) LAUNCH(m, FAM_PYRAMID, k_pyr_sort_w, std::min(mc.P, kSMs * 3), 512, PYR_SORT_CAP * sizeof(u64), mc, dp, fc.Pd);
     else LAUNCH(m, FAM_PYRAMID, k_pyr_sort, std::min(mc.P, kSMs * 3), 512, PYR_SORT_CAP * sizeof(u64), mc, dp, fc.Pd);
     CK(cudaStreamWaitEvent(m->stream, m->ev_join_obs, 0));
     if (fc.stage_limit >= 2) {
-        LAUNCH(m, FAM_CK, k_pair_prep, grid_for(mc.P, B), B, 0, mc, dp, m->g_col ? 1 : 0);
-        LAUNCH(m, FAM_CK, k_scan_small, 2, 1024, 0, ScanJobs{{ScanJob{dp.pairs, dp.rowbase, nullptr, 0, mc.P}, ScanJob{dp.chunks, dp.chunk_off, nullptr, 0, mc.P}, ScanJob{}}});
+        if (m->fuse_scan) {
+            LAUNCH(m, FAM_CK, k_pair_prep_scan, 1, 1024, 0, mc, dp, m->g_col ? 1 : 0);
+        } else {
+            LAUNCH(m, FAM_CK, k_pair_prep, grid_for(mc.P, B), B, 0, mc, dp, m->g_col ? 1 : 0);
+            LAUNCH(m, FAM_CK, k_scan_small, 2, 1024, 0, ScanJobs{{ScanJob{dp.pairs, dp.rowbase, nullptr, 0, mc.P}, ScanJob{dp.chunks, dp.chunk_off, nullptr, 0, mc.P}, ScanJob{}}});
+        }
         if (m->g_col) {
             if (m->eval_packed) LAUNCH(m, FAM_CK, k_pair_eval_cp, kSMs * 4, EVAL_THREADS, sizeof(float) * (DSP_LUT_HALF + 3 + EVALC_KEYS), mc, fc, dp, 0);
             else LAUNCH(m, FAM_CK, k_pair_eval_c, kSMs * 4, EVAL_THREADS, sizeof(float) * (DSP_LUT_HALF + 3 + EVALC_KEYS), mc, fc, dp, 0);
@@ -468,8 +477,12 @@ int enqueue_frame_b(dspmap *m, const FrameConst &fc, const float *d_tagged) {
                 LAUNCH(m, FAM_NEWBORN, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{dp.ninmap, dp.nrank, nullptr, 0, fc.n_tagged}, ScanJob{}, ScanJob{}}});
                 LAUNCH(m, FAM_NEWBORN, k_nb_mask, grid_for((long long)fc.n_tagged * fc.nb_num, B), B, 0, mc, fc, dp);
             }
-            LAUNCH(m, FAM_NEWBORN, k_nb_point1, grid_for((long long)fc.n_tagged * 32, B), B, 0, mc, fc, dp, 0);
-            LAUNCH(m, FAM_NEWBORN, k_scan_small, 2, 1024, 0, ScanJobs{{ScanJob{dp.nvcnt, dp.nvoff, nullptr, 0, fc.n_tagged}, ScanJob{dp.nrcnt, dp.nroff, nullptr, 0, fc.n_tagged}, ScanJob{}}});
+            if (m->fuse_scan) {
+                LAUNCH(m, FAM_NEWBORN, k_nb_point1_fs, grid_for((long long)fc.n_tagged * 32, B), B, 0, mc, fc, dp, 0);
+            } else {
+                LAUNCH(m, FAM_NEWBORN, k_nb_point1, grid_for((long long)fc.n_tagged * 32, B), B, 0, mc, fc, dp, 0);
+                LAUNCH(m, FAM_NEWBORN, k_scan_small, 2, 1024, 0, ScanJobs{{ScanJob{dp.nvcnt, dp.nvoff, nullptr, 0, fc.n_tagged}, ScanJob{dp.nrcnt, dp.nroff, nullptr, 0, fc.n_tagged}, ScanJob{}}});
+            }
             if (m->norm_join_pending) {  // k_norm (side stream) wrote w_new, which k_nb_cand reads
                 CK(cudaStreamWaitEvent(m->stream, m->ev_join, 0));
                 m->norm_join_pending = false;
@@ -789,6 +802,7 @@ int dspmap_create(const dspmap_config *cfg, dspmap **out) {
     m->resample_sm = env_on("DSPMAP_RESAMPLE_SM");
     m->sort_warp = env_on("DSPMAP_SORT_WARP");
     m->eval_packed = env_on("DSPMAP_EVAL_PACKED");
+    m->fuse_scan = env_on("DSPMAP_FUSE_SCAN");
     m->est_thread = env_on("DSPMAP_EST_THREAD");
     m->sparse_future = env_on("DSPMAP_SPARSE_FUTURE");
     m->async_update = env_on("DSPMAP_ASYNC_UPDATE");
@@ -1145,8 +1159,12 @@ int dspmap_get_occupancy_device(dspmap *m, float thr, float *d_xyz, int cap, int
     if (!m) return DSPMAP_E_BAD_ARG;
     CK(cudaSetDevice(m->cfg.device));
     const MapConst &mc = m->mc;
-    LAUNCH(m, FAM_READER, k_occ_count, m->occ_blocks, 256, 0, mc, m->dp, thr, m->d_blockcnt, d_future);
-    LAUNCH(m, FAM_READER, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{m->d_blockcnt, m->d_blockoff, nullptr, 0, m->occ_blocks}, ScanJob{}, ScanJob{}}});
+    if (m->fuse_scan) {
+        LAUNCH(m, FAM_READER, k_occ_count_fs, m->occ_blocks, 256, 0, mc, m->dp, thr, m->d_blockcnt, m->d_blockoff, m->occ_blocks, d_future);
+    } else {
+        LAUNCH(m, FAM_READER, k_occ_count, m->occ_blocks, 256, 0, mc, m->dp, thr, m->d_blockcnt, d_future);
+        LAUNCH(m, FAM_READER, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{m->d_blockcnt, m->d_blockoff, nullptr, 0, m->occ_blocks}, ScanJob{}, ScanJob{}}});
+    }
     LAUNCH(m, FAM_READER, k_occ_write, m->occ_blocks, 256, 0, mc, m->dp, thr, m->d_blockoff, d_xyz, cap, d_count, m->occ_blocks);
     CK(cudaGetLastError());
     return DSPMAP_OK;

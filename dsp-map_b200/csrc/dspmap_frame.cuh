@@ -127,6 +127,59 @@ __global__ void __launch_bounds__(1024) k_scan_small(ScanJobs jobs) {
     if (threadIdx.x == 1023) { J.out[n] = run; if (J.out_capped) J.out_capped[n] = runc; }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Scans fused into the kernel that produces their input (experiment switch DSPMAP_FUSE_SCAN=1): the block that finishes
+// last (a ticket counter, the classic "last block done" pattern) performs the small exclusive scan that otherwise costs a
+// launch of its own on the frame's critical path.  scan_block works for any block size that is a multiple of 32.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool last_block_done(int *ticket) {
+    __shared__ bool s_last;
+    __threadfence();  // this block's results are visible device-wide before its ticket is
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s_last = atomicAdd(ticket, 1) == (int)gridDim.x - 1;
+        if (s_last) *ticket = 0;  // ready for the next launch
+    }
+    __syncthreads();
+    if (s_last) __threadfence();
+    return s_last;
+}
+__device__ __forceinline__ void scan_block(const int *in, int *out, int *out_capped, int cap, int n) {
+    __shared__ int wsum[32], wcap[32];
+    const int T = blockDim.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = T >> 5;
+    const int per = (n + T - 1) / T;
+    const int b0 = min(n, (int)threadIdx.x * per), b1 = min(n, b0 + per);
+    int s = 0, sc = 0;
+    for (int i = b0; i < b1; ++i) { const int x = __ldcg(in + i); s += x; sc += min(x, cap); }  // written by other blocks: read from L2
+    int incl = s, inclc = sc;
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(FULLMASK, incl, d), tc = __shfl_up_sync(FULLMASK, inclc, d);
+        if (lane >= d) { incl += t; inclc += tc; }
+    }
+    if (lane == 31) { wsum[wid] = incl; wcap[wid] = inclc; }
+    __syncthreads();
+    if (wid == 0) {
+        const int y0 = lane < nw ? wsum[lane] : 0, yc0 = lane < nw ? wcap[lane] : 0;
+        int y = y0, yc = yc0;
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(FULLMASK, y, d), tc = __shfl_up_sync(FULLMASK, yc, d);
+            if (lane >= d) { y += t; yc += tc; }
+        }
+        wsum[lane] = y - y0;  // exclusive prefix of the warp totals
+        wcap[lane] = yc - yc0;
+    }
+    __syncthreads();
+    int run = wsum[wid] + incl - s, runc = wcap[wid] + inclc - sc;
+    for (int i = b0; i < b1; ++i) {
+        const int x = __ldcg(in + i);
+        out[i] = run;
+        run += x;
+        if (out_capped) { out_capped[i] = runc; runc += min(x, cap); }
+    }
+    if ((int)threadIdx.x == T - 1) { out[n] = run; if (out_capped) out_capped[n] = runc; }
+    __syncthreads();  // the shared totals may be reused by a following scan
+}
+
 __global__ void k_obs_scatter(MapConst mc, FrameConst fc, DevPtrs dp) {
     pdl_enter();
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < fc.n_points; i += gridDim.x * blockDim.x) {
@@ -380,8 +433,7 @@ __global__ void k_group_scatter(const int *n_items, const int *dst, const int *k
 //     frame-start mask M0; the destination's own leavers then free their slots; arrivals from higher-index voxels
 //     come last.  The k-th arrival of a phase takes the k-th free slot; no free slot => the particle vanishes.
 // ------------------------------------------------------------------------------------------------------------
-__global__ void k_arrive(MapConst mc, FrameConst fc, DevPtrs dp) {
-    pdl_enter();
+__device__ __forceinline__ void arrive_body(const MapConst &mc, const FrameConst &fc, const DevPtrs &dp) {
     const int n = dp.st->n_mov;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         int d = dp.MBdst[i], key = dp.MBkey[i];
@@ -423,6 +475,16 @@ __global__ void k_arrive(MapConst mc, FrameConst fc, DevPtrs dp) {
             if (!mc.sharded) atomicAdd(&dp.pcount[q], 1);
         }
     }
+}
+__global__ void k_arrive(MapConst mc, FrameConst fc, DevPtrs dp) {
+    pdl_enter();
+    arrive_body(mc, fc, dp);
+}
+// + the scan of the pyramid counts (the input of k_pyr_scatter) by the block that finishes last
+__global__ void k_arrive_fs(MapConst mc, FrameConst fc, DevPtrs dp) {
+    pdl_enter();
+    arrive_body(mc, fc, dp);
+    if (last_block_done(&dp.st->tickets[0])) scan_block(dp.pcount, dp.poff, nullptr, 0, mc.P);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -825,6 +887,30 @@ __global__ void k_pair_prep(MapConst mc, DevPtrs dp, int col) {
         dp.chunks[i] = (dp.plen[i] + 31) >> 5;
     }
     if (local) atomicAdd(&dp.st->total_pairs, local);
+}
+// k_pair_prep and its two scans (pair counts -> row bases, chunk counts -> chunk offsets) as ONE block of 1024 threads
+__global__ void __launch_bounds__(1024) k_pair_prep_scan(MapConst mc, DevPtrs dp, int col) {
+    pdl_enter();
+    unsigned long long local = 0ull;
+    for (int i = threadIdx.x; i < mc.P; i += blockDim.x) {
+        const int np = min(dp.obs_cnt[i], mc.OBS - 1), nn = dp.nbr[i * mc.NBW];
+        int c = 0;
+        for (int ns = 0; ns < nn; ++ns) {
+            dp.cum[i * mc.NBW + ns] = c;
+            c += dp.plen[dp.nbr[i * mc.NBW + 1 + ns]];
+        }
+        dp.totlen[i] = c;
+        unsigned long long pr = (unsigned long long)np * (unsigned long long)c;
+        if (col) pr = np > 0 ? (unsigned long long)(np + 1) * (unsigned long long)((c + 3) & ~3) : 0ull;
+        dp.pairs[i] = pr > 0x3fffffffull ? 0x3fffffff : (int)pr;
+        local += pr;
+        dp.chunks[i] = (dp.plen[i] + 31) >> 5;
+    }
+    if (local) atomicAdd(&dp.st->total_pairs, local);
+    __threadfence();  // scan_block reads the counts through L2
+    __syncthreads();
+    scan_block(dp.pairs, dp.rowbase, nullptr, 0, mc.P);
+    scan_block(dp.chunks, dp.chunk_off, nullptr, 0, mc.P);
 }
 // position of pyramid a inside pyramid b's neighbour list (the relation is symmetric)
 __device__ __forceinline__ int nb_index_of(const MapConst &mc, const DevPtrs &dp, int b, int a) {
@@ -1724,8 +1810,7 @@ __global__ void k_nb_mask(MapConst mc, FrameConst fc, DevPtrs dp) {
 // point pass 1: Dempster-Shafer split from the resident particles of the point's voxel (:829-866) — one warp per point,
 // lanes = slots, the three weight sums added in slot order — and how many table / uniform draws the point consumes.
 // phase 0: single GPU (split + counts); phase 1: sharded, split by the owner of the point's voxel only; phase 2: sharded, counts
-__global__ void __launch_bounds__(256) k_nb_point1(MapConst mc, FrameConst fc, DevPtrs dp, int phase) {
-    pdl_enter();
+__device__ __forceinline__ void nb_point1_body(const MapConst &mc, const FrameConst &fc, const DevPtrs &dp, int phase) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     const int R = (mc.S + 31) >> 5;
@@ -1800,6 +1885,19 @@ __global__ void __launch_bounds__(256) k_nb_point1(MapConst mc, FrameConst fc, D
             dp.nvcnt[m] = __popcll(vm);
             dp.nrcnt[m] = __popcll(rm);
         }
+    }
+}
+__global__ void __launch_bounds__(256) k_nb_point1(MapConst mc, FrameConst fc, DevPtrs dp, int phase) {
+    pdl_enter();
+    nb_point1_body(mc, fc, dp, phase);
+}
+// + the scans of the points' velocity-table / uniform draws (the cursors of k_nb_cand) by the block that finishes last
+__global__ void __launch_bounds__(256) k_nb_point1_fs(MapConst mc, FrameConst fc, DevPtrs dp, int phase) {
+    pdl_enter();
+    nb_point1_body(mc, fc, dp, phase);
+    if (last_block_done(&dp.st->tickets[1])) {
+        scan_block(dp.nvcnt, dp.nvoff, nullptr, 0, fc.n_tagged);
+        scan_block(dp.nrcnt, dp.nroff, nullptr, 0, fc.n_tagged);
     }
 }
 // candidate pass: position (:871-873), velocity class (:877-907), weight (:909); candidates inside the map join
@@ -2359,6 +2457,29 @@ __global__ void __launch_bounds__(256) k_occ_count(MapConst mc, DevPtrs dp, floa
         if (d_future) d_future[i] = dp.FUT[i];
         dp.FUT[i] = 0.f;
     }
+}
+// the same with the scan of the per-block counts (the offsets of k_occ_write) by the block that finishes last (DSPMAP_FUSE_SCAN)
+__global__ void __launch_bounds__(256) k_occ_count_fs(MapConst mc, DevPtrs dp, float thr, int *blockcnt, int *blockoff, int nblocks, float *d_future) {
+    pdl_enter();
+    __shared__ int s;
+    if (threadIdx.x == 0) s = 0;
+    __syncthreads();
+    int b = blockIdx.x * OCC_BLOCK, c = 0;
+    for (int i = threadIdx.x; i < OCC_BLOCK; i += blockDim.x) {
+        int v = b + i;
+        if (v < mc.V && dp.OCCV[v].x > thr) ++c;
+    }
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_down_sync(FULLMASK, c, d);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s, c);
+    __syncthreads();
+    if (threadIdx.x == 0) blockcnt[blockIdx.x] = s;
+    // future status: copy out (if asked) and clear (:416-424)
+    size_t fb = (size_t)b * mc.T, fe = min((size_t)mc.V, (size_t)b + OCC_BLOCK) * mc.T;
+    for (size_t i = fb + threadIdx.x; i < fe; i += blockDim.x) {
+        if (d_future) d_future[i] = dp.FUT[i];
+        dp.FUT[i] = 0.f;
+    }
+    if (last_block_done(&dp.st->tickets[2])) scan_block(blockcnt, blockoff, nullptr, 0, nblocks);
 }
 __global__ void __launch_bounds__(256) k_occ_write(MapConst mc, DevPtrs dp, float thr, const int *blockoff, float *xyz, int cap, int *d_count, int nblocks) {
     pdl_enter();

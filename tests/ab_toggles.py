@@ -27,7 +27,7 @@ for p in (os.path.join(ROOT, "dsp-map_b200"), os.path.join(ROOT, "tests")):
 
 import numpy as np  # noqa: E402
 
-SWITCHES = ("DSPMAP_PDL", "DSPMAP_EST_THREAD", "DSPMAP_CZ_NARROW", "DSPMAP_CZ_TMA", "DSPMAP_CZ_STAGED", "DSPMAP_QUOT_FAST", "DSPMAP_NB_REDUX", "DSPMAP_G_COL", "DSPMAP_SPARSE_FUTURE", "DSPMAP_ASYNC_UPDATE", "DSPMAP_NORM_FAST", "DSPMAP_RESAMPLE_SM", "DSPMAP_SORT_WARP", "DSPMAP_EVAL_PACKED")
+SWITCHES = ("DSPMAP_PDL", "DSPMAP_EST_THREAD", "DSPMAP_CZ_NARROW", "DSPMAP_CZ_TMA", "DSPMAP_CZ_STAGED", "DSPMAP_QUOT_FAST", "DSPMAP_NB_REDUX", "DSPMAP_G_COL", "DSPMAP_SPARSE_FUTURE", "DSPMAP_ASYNC_UPDATE", "DSPMAP_NORM_FAST", "DSPMAP_RESAMPLE_SM", "DSPMAP_SORT_WARP", "DSPMAP_EVAL_PACKED", "DSPMAP_FUSE_SCAN")
 
 
 def make_map(dm, gpu_map, name, env, **kw):

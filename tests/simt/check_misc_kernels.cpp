@@ -66,6 +66,97 @@ int main() {
         printf("sparse future rows, %4d voxels: %d rows %s\n", V, nf, ok ? "identical" : "DIFFERENT");
         bad += ok ? 0 : 1;
     }
+    // ---- scans fused into their producers (last block done): reader counts, newborn draw counts
+    for (int V : {300, 512, 5000}) {
+        MapConst mc;
+        memset(&mc, 0, sizeof(mc));
+        mc.V = V;
+        mc.T = 2;
+        const int nblocks = (V + OCC_BLOCK - 1) / OCC_BLOCK;
+        std::vector<float4> occv(V);
+        for (auto &o : occv) o = make_float4(uni(0.f, 0.5f), 0, 0, 0);
+        std::vector<float> fut0((size_t)V * mc.T);
+        for (auto &f : fut0) f = rng() % 3 ? 0.f : uni(0.1f, 1.f);
+        std::vector<int> cnt[2], off[2];
+        std::vector<float> fut[2], dfut[2];
+        DevState st;
+        memset(&st, 0, sizeof(st));
+        for (int k = 0; k < 2; ++k) {
+            cnt[k].assign(nblocks + 1, -1); off[k].assign(nblocks + 1, -1); fut[k] = fut0; dfut[k].assign(fut0.size(), -1.f);
+            DevPtrs dp;
+            memset(&dp, 0, sizeof(dp));
+            dp.OCCV = occv.data(); dp.FUT = fut[k].data(); dp.st = &st;
+            if (k == 0) {
+                simt::launch_grid(nblocks, 256, [&] { k_occ_count(mc, dp, 0.2f, cnt[0].data(), dfut[0].data()); });
+                off[0][0] = 0;
+                for (int b = 0; b < nblocks; ++b) off[0][b + 1] = off[0][b] + cnt[0][b];
+            } else {
+                simt::launch_grid(nblocks, 256, [&] { k_occ_count_fs(mc, dp, 0.2f, cnt[1].data(), off[1].data(), nblocks, dfut[1].data()); });
+            }
+        }
+        cnt[0][nblocks] = cnt[1][nblocks] = 0;
+        const bool ok = cnt[0] == cnt[1] && off[0] == off[1] && fut[0] == fut[1] && dfut[0] == dfut[1] && st.tickets[2] == 0;
+        printf("reader count + fused scan, %4d voxels (%d blocks): %s\n", V, nblocks, ok ? "identical" : "DIFFERENT");
+        bad += ok ? 0 : 1;
+    }
+    {
+        MapConst mc;
+        FrameConst fc;
+        memset(&mc, 0, sizeof(mc));
+        memset(&fc, 0, sizeof(fc));
+        mc.V = 40; mc.S = 48; mc.model = 0; mc.v_hi = mc.V;
+        fc.n_tagged = 700; fc.nb_num = 20; fc.nb_model_gen = 16; fc.nb_min_static = 3;
+        const int n = fc.n_tagged;
+        std::vector<float4> PA((size_t)mc.V * mc.S), PB(PA.size()), NPC(n);
+        std::vector<ulonglong2> M(mc.V);
+        std::vector<int> ninmap(n + 1);
+        std::vector<u64> nimask(n);
+        std::vector<float> tagged((size_t)n * 7);
+        for (int v = 0; v < mc.V; ++v) {
+            M[v] = make_ulonglong2((((u64)rng() << 32) | rng()) & ((1ull << 48) - 1ull), 0ull);
+            if (rng() % 6 == 0) M[v].x = 0ull;
+            for (int sl = 0; sl < mc.S; ++sl) {
+                PA[(size_t)v * mc.S + sl] = make_float4(0, 0, 0, uni(0.001f, 0.05f));
+                const float fl[4] = {1.f, 7.f, 15.f, 0.6f};
+                const int kind = rng() % 3;
+                PB[(size_t)v * mc.S + sl] = make_float4(kind == 0 ? 0.f : uni(-0.6f, 0.6f), kind == 2 ? uni(-0.6f, 0.6f) : 0.f, 0.f, fl[rng() % 4]);
+            }
+        }
+        for (int m = 0; m < n; ++m) {
+            ninmap[m] = rng() % 8 != 0;
+            NPC[m] = make_float4(0, 0, 0, __int_as_float((int)(rng() % mc.V)));
+            nimask[m] = (u64)(rng() & 0xfffff);
+            float *pt = &tagged[(size_t)m * 7];
+            pt[3] = rng() % 3 ? uni(-1.f, 1.f) : -10000.f;
+            pt[6] = rng() % 2 ? 1.f : 0.f;
+        }
+        std::vector<int> nstatic[2], nvcnt[2], nrcnt[2], nvoff[2], nroff[2];
+        DevState st;
+        memset(&st, 0, sizeof(st));
+        const int nblocks = (n * 32 + 255) / 256;
+        for (int k = 0; k < 2; ++k) {
+            nstatic[k].assign(n, -9); nvcnt[k].assign(n + 1, -9); nrcnt[k].assign(n + 1, -9); nvoff[k].assign(n + 1, -9); nroff[k].assign(n + 1, -9);
+            DevPtrs dp;
+            memset(&dp, 0, sizeof(dp));
+            dp.PA = PA.data(); dp.PB = PB.data(); dp.M = M.data(); dp.NPC = NPC.data(); dp.ninmap = ninmap.data(); dp.nimask = nimask.data();
+            dp.tagged = tagged.data(); dp.nstatic = nstatic[k].data(); dp.nvcnt = nvcnt[k].data(); dp.nrcnt = nrcnt[k].data();
+            dp.nvoff = nvoff[k].data(); dp.nroff = nroff[k].data(); dp.st = &st;
+            if (k == 0) {
+                simt::launch_grid(nblocks, 256, [&] { k_nb_point1(mc, fc, dp, 0); });
+                nvoff[0][0] = nroff[0][0] = 0;
+                for (int m = 0; m < n; ++m) { nvoff[0][m + 1] = nvoff[0][m] + nvcnt[0][m]; nroff[0][m + 1] = nroff[0][m] + nrcnt[0][m]; }
+            } else {
+                simt::launch_grid(nblocks, 256, [&] { k_nb_point1_fs(mc, fc, dp, 0); });
+            }
+        }
+        nvcnt[0][n] = nvcnt[1][n] = nrcnt[0][n] = nrcnt[1][n] = 0;
+        // points outside the map leave nstatic untouched in both
+        const bool ok = nstatic[0] == nstatic[1] && nvcnt[0] == nvcnt[1] && nrcnt[0] == nrcnt[1] && nvoff[0] == nvoff[1] && nroff[0] == nroff[1] &&
+                        nvoff[0][n] > 0 && nroff[0][n] > 0 && st.tickets[1] == 0;
+        printf("newborn draw counts + fused scans, %d points (%d blocks): %d table draws, %d uniform draws: %s\n", n, nblocks, nvoff[0][n], nroff[0][n],
+               ok ? "identical" : "DIFFERENT");
+        bad += ok ? 0 : 1;
+    }
     // ---- host side of the sparse copy-out: a sequence of grids through SparseRows::apply equals the dense grids
     {
         const int V = 3000, T = 6;

@@ -112,7 +112,7 @@ enum CzKernel { CZ_DEFAULT, CZ_STAGED, CZ_TMA, CZ_COL };
 // kernel with packed fp32 arithmetic (taken only with the verified fast division, so fast_sigma is switched on for it: on
 // the host the scalar path divides and the packed path runs the multiply / fused-correction sequence — the table index
 // they produce is the same for every reachable argument, which is what k_verify_div establishes on the device).
-Result run(const Scene &s, bool col, CzKernel czk, bool quot_fast, bool packed = false) {
+Result run(const Scene &s, bool col, CzKernel czk, bool quot_fast, bool packed = false, bool fused_prep = false) {
     MapConst mc = s.mc;
     FrameConst fc = s.fc;
     if (packed) fc.fast_sigma = 1;
@@ -132,9 +132,13 @@ Result run(const Scene &s, bool col, CzKernel czk, bool quot_fast, bool packed =
     dp.cum = cum.data(); dp.totlen = totlen.data(); dp.pairs = pairs.data(); dp.rowbase = rowbase.data(); dp.chunks = chunks.data();
     dp.chunk_off = chunk_off.data();
     dp.cz_order = (col || czk == CZ_TMA) ? cz_order.data() : nullptr;
-    simt::launch_block(32, [&] { k_pair_prep(mc, dp, col ? 1 : 0); });
-    rowbase[0] = chunk_off[0] = 0;  // the two exclusive scans k_scan_small performs
-    for (int p = 0; p < P; ++p) { rowbase[p + 1] = rowbase[p] + pairs[p]; chunk_off[p + 1] = chunk_off[p] + chunks[p]; }
+    if (fused_prep) {  // DSPMAP_FUSE_SCAN: preparation and both scans in one block
+        simt::launch_block(1024, [&] { k_pair_prep_scan(mc, dp, col ? 1 : 0); });
+    } else {
+        simt::launch_block(32, [&] { k_pair_prep(mc, dp, col ? 1 : 0); });
+        rowbase[0] = chunk_off[0] = 0;  // the two exclusive scans k_scan_small performs
+        for (int p = 0; p < P; ++p) { rowbase[p + 1] = rowbase[p] + pairs[p]; chunk_off[p + 1] = chunk_off[p] + chunks[p]; }
+    }
     float *G = static_cast<float *>(aligned_alloc(256, sizeof(float) * ((size_t)rowbase[P] + 64 + 64)));
     for (size_t i = 0; i < (size_t)rowbase[P] + 128; ++i) G[i] = NAN;  // every element a consumer reads must have been produced
     dp.G = G;
@@ -248,7 +252,7 @@ int main() {
         printf("scene %u: %d pyramids, %d registered particles, %d binned points; reference pass changed %d weights\n", seed, P, s.n_fov, s.n_pts, changed);
         if (changed < s.n_fov / 2) { printf("the scene does not exercise the weight pass\n"); ++bad; }
         (void)tiny;
-        struct Case { const char *name; bool col; CzKernel cz; bool qf; bool packed = false; } cases[] = {
+        struct Case { const char *name; bool col; CzKernel cz; bool qf; bool packed = false; bool fused_prep = false; } cases[] = {
 #ifdef CHECK_W2W
             {"k_weight2w (warp per chunk)", false, CZ_DEFAULT, false},
             {"k_weight2w<QF>", false, CZ_DEFAULT, true},
@@ -259,10 +263,12 @@ int main() {
             {"column-major family", true, CZ_COL, false},
             {"column-major family + dsp_quot fast path", true, CZ_COL, true},
             {"column-major family, packed evaluation", true, CZ_COL, false, true},
+            {"k_pair_prep_scan (row-major)", false, CZ_DEFAULT, false, false, true},
+            {"k_pair_prep_scan (column-major)", true, CZ_COL, false, false, true},
 #endif
         };
         for (const Case &c : cases) {
-            const Result r = run(s, c.col, c.cz, c.qf, c.packed);
+            const Result r = run(s, c.col, c.cz, c.qf, c.packed, c.fused_prep);
             bool ok = same(ref.CZ, r.CZ, "C_z");
             ok &= same(ref.INV, r.INV, "1 / C_z");
             ok &= same(ref.W, r.W, "particle weights");

@@ -131,6 +131,9 @@ inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
 template <typename T>
 inline T __ldg(const T *p) { return *p; }
 template <typename T>
+inline T __ldcg(const T *p) { return *p; }
+inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+template <typename T>
 inline T atomicAdd(T *p, T v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline float atomicAdd(float *p, float v) {
     static std::atomic_flag lock = ATOMIC_FLAG_INIT;

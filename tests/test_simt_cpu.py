@@ -34,21 +34,22 @@ def test_observation_pass_variants_equal_the_row_major_kernels():
     k_weight_col, with and without the dsp_quot fast path) reproduce C_z, 1/C_z and the particle weights of k_pair_eval ->
     k_cz_chain -> k_weight2 bit for bit; the emulated cp.async.bulk aborts on a copy that breaks the 16-byte rules."""
     out = build_and_run("check_obs_kernels", "obs_kernels.inc",
-                        ["use_pair_buffer", "chunk_to_pyramid", "nb_index_of", "cz_build_order", "k_pair_prep", "k_pair_eval", "k_cz_chain",
+                        ["use_pair_buffer", "chunk_to_pyramid", "nb_index_of", "cz_build_order", "scan_block", "k_pair_prep", "k_pair_prep_scan", "k_pair_eval", "k_cz_chain",
                          "k_cz_chain_tma", "k_weight2_t", "dsp_pdf2_f", "k_pair_eval_col", "k_cz_chain_col", "k_weight_col"])
-    assert out.count("identical") == 24 and "DIFFERENT" not in out and "does not exercise" not in out
+    assert out.count("identical") == 30 and "DIFFERENT" not in out and "does not exercise" not in out
 
 
 def test_warp_per_chunk_weight_kernel_equals_the_other_weight_kernels():
     """k_weight2w takes the frames with many particle chunks (cfg3, cfg5).  Built with W2_SWITCH = 0 it takes the small test
     scenes too and has to reproduce the weights of the column-major family (which the test above ties to k_weight2)."""
     out = build_and_run("check_obs_kernels", "obs_kernels.inc",
-                        ["use_pair_buffer", "chunk_to_pyramid", "nb_index_of", "cz_build_order", "k_pair_prep", "k_pair_eval", "k_cz_chain",
+                        ["use_pair_buffer", "chunk_to_pyramid", "nb_index_of", "cz_build_order", "scan_block", "k_pair_prep", "k_pair_prep_scan", "k_pair_eval", "k_cz_chain",
                          "k_cz_chain_tma", "k_weight2_t", "k_weight2w_t", "dsp_pdf2_f", "k_pair_eval_col", "k_cz_chain_col", "k_weight_col"],
                         defines=("CHECK_W2W", "W2_SWITCH=0"), tag="_w2w")
     assert out.count("identical") == 6 and "DIFFERENT" not in out and "does not exercise" not in out
 
 
 def test_normaliser_sparse_future_and_sort_kernels():
-    out = build_and_run("check_misc_kernels", "misc_kernels.inc", ["k_norm", "k_norm_fast", "k_fut_count", "k_fut_compact", "k_pyr_sort", "k_pyr_sort_w"])
-    assert out.count("identical") == 19 and "DIFFERENT" not in out
+    out = build_and_run("check_misc_kernels", "misc_kernels.inc", ["last_block_done", "scan_block", "k_norm", "k_norm_fast", "k_fut_count", "k_fut_compact", "k_pyr_sort", "k_pyr_sort_w",
+                         "k_occ_count", "k_occ_count_fs", "bits_below", "nb_point1_body", "k_nb_point1", "k_nb_point1_fs"])
+    assert out.count("identical") == 23 and "DIFFERENT" not in out
