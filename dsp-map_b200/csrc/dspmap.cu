@@ -85,7 +85,6 @@ struct dspmap {
     int occ_blocks = 0;
     int occ_guess = 4096;  // occupied voxels copied along with the count (twice the last count): one round trip, not two
     // sparse copy-out of the future grid into a registered (page-locked) caller buffer (DSPMAP_SPARSE_FUTURE=1)
-    bool sparse_future = false;
     int *d_fcnt = nullptr, *d_foff = nullptr, *d_fidx = nullptr, *d_nf = nullptr, *h_fidx = nullptr, *h_nf = nullptr;
     float *d_fval = nullptr, *h_fval = nullptr;
     int fut_guess = 8192;                 // rows copied along with their count
@@ -107,24 +106,17 @@ struct dspmap {
     int vz_blocks = 0;
     // the recompute kernels (k_ck / k_weight) are launched only while the pair buffer may overflow
     bool fallback_armed = true;
-    bool cz_wide = true;
+    bool fallback_forced = false;  // a frame overran the pair buffer without the recompute kernels: keep them armed from now on
+    int overflow_latched = 0;      // capacity overruns seen on the device and not yet reported to the caller (codes OR-ed)
+    bool clear_overflow = false;   // the device-side flag has been absorbed: clear it in front of the next frame
+    long long state_copies = 0, state_absorbed = 0;  // frame-end state copies enqueued / taken over by the host
     bool norm_join_pending = false;  // k_norm runs on the side stream and has not been joined yet
     bool nb_prefix_done = false;  // this frame's first newborn kernels already ran on the side branch
-    bool pdl = false;             // programmatic dependent launch of the frame's kernels (DSPMAP_PDL=1)
-    bool cz_tma = false;          // C_z chains fed by a cp.async.bulk / mbarrier ring, heaviest pyramid first (DSPMAP_CZ_TMA=1)
-    bool async_update = false;    // dspmap_update returns once the frame is enqueued; the next call that needs results waits (DSPMAP_ASYNC_UPDATE=1)
+    bool pdl = true;              // programmatic dependent launch of the frame's kernels (DSPMAP_PDL=0 turns it off)
+    bool async_update = true;     // dspmap_update returns once the frame is enqueued; the next call that needs results waits (DSPMAP_ASYNC_UPDATE=0: wait in update)
     bool staged_pending = false;  // the page-locked staging buffers are still being read by the previous frame's copies
     cudaEvent_t ev_staged = nullptr;
-    bool fuse_scan = false;       // small scans fused into their producers' last block (DSPMAP_FUSE_SCAN=1)
-    bool eval_packed = false;     // k_pair_eval_col<true>: packed fp32 arithmetic, two points per step (DSPMAP_EVAL_PACKED=1, with G_COL)
-    bool sort_warp = false;       // k_pyr_sort_w (DSPMAP_SORT_WARP=1)
-    bool resample_sm = false;     // k_resample_sm (DSPMAP_RESAMPLE_SM=1)
-    bool norm_fast = false;       // k_norm_fast (DSPMAP_NORM_FAST=1)
-    bool cz_staged = false;       // k_cz_chain with the neighbour table staged per pyramid (DSPMAP_CZ_STAGED=1)
-    bool g_col = false;           // column-major pair buffer: k_pair_eval_col / k_cz_chain_col / k_weight2<.., COL> (DSPMAP_G_COL=1)
-    bool nb_redux = false;        // newborn placement with REDUX minima (DSPMAP_NB_REDUX=1)
-    bool quot_fast = false;       // weight pass: zero / tiny dividends bypass the IEEE division's slow path (DSPMAP_QUOT_FAST=1)
-    bool est_thread = false;      // velocity estimation on the helper thread, beside the enqueueing of the frame (DSPMAP_EST_THREAD=1)
+    bool est_thread = true;       // velocity estimation on the helper thread, beside the enqueueing of the frame (DSPMAP_EST_THREAD=0: calling thread)
     HostWorker worker;
     FrameConst shard_fc;  // frame scalars carried across the phases of a sharded frame
     int shard_cap_g = 0;
@@ -148,6 +140,17 @@ namespace {
         cudaError_t e_ = (x);                                                                   \
         if (e_ != cudaSuccess) {                                                                \
             g_err = std::string(#x) + ": " + cudaGetErrorString(e_);                            \
+            return DSPMAP_E_CUDA;                                                               \
+        }                                                                                       \
+    } while (0)
+
+// inside dspmap_create: a failure releases the half-built handle (device memory, streams, events) before returning
+#define CKM(x)                                                                                  \
+    do {                                                                                        \
+        cudaError_t e_ = (x);                                                                   \
+        if (e_ != cudaSuccess) {                                                                \
+            g_err = std::string(#x) + ": " + cudaGetErrorString(e_);                            \
+            dspmap_destroy(m);                                                                  \
             return DSPMAP_E_CUDA;                                                               \
         }                                                                                       \
     } while (0)
@@ -192,6 +195,29 @@ void prof_collect(dspmap *m) {
         }
     }
     m->prof_used = 0;
+}
+
+// The device state copy that ends every frame has landed in h_state: take it over, latch capacity overruns.
+void absorb_state(dspmap *m) {
+    m->last_state = *m->h_state;
+    if (m->state_absorbed == m->state_copies) return;  // this copy has been looked at already
+    m->state_absorbed = m->state_copies;
+    if (m->last_state.overflow && !m->clear_overflow) {
+        m->overflow_latched |= m->last_state.overflow;
+        if (m->last_state.overflow & 4) m->fallback_forced = true;
+        m->clear_overflow = true;  // the device flag is sticky until the host has seen it
+    }
+}
+// Reports (once) what absorb_state latched.
+int report_overflow(dspmap *m) {
+    if (!m->overflow_latched) return DSPMAP_OK;
+    char buf[256];
+    snprintf(buf, sizeof(buf), "device capacity exceeded: code %d (1 live list, 2 newborn candidates, 4 pair buffer without fallback, "
+             "8 shard crossers, 16 shard gather); pairs last frame %llu, capacity %lld", m->overflow_latched,
+             m->last_state.total_pairs, m->mc.cap_pairs);
+    g_err = buf;
+    m->overflow_latched = 0;
+    return DSPMAP_E_CAPACITY;
 }
 
 // One launch site for every kernel of a frame.  With dspmap::pdl the kernel is launched for programmatic dependent
@@ -239,21 +265,15 @@ inline void launch_kernel(bool pdl, cudaStream_t st, void (*kernel)(KArgs...), i
         ++(m)->launches_frame;                                                      \
     } while (0)
 
-// experiment switches are environment variables read once, by dspmap_create: set to anything but "" or "0"
-bool env_on(const char *name) {
+// the library's A/B switches are environment variables read once, by dspmap_create
+bool env_off(const char *name) {  // defaults are on; NAME=0 turns one off
     const char *e = getenv(name);
-    return e && *e && strcmp(e, "0") != 0;
+    return e && strcmp(e, "0") == 0;
 }
 
 const int kSMs = 148;
 // the two configurations of the C_z chain kernel (threads, floats per tile, rows per tile)
-const auto k_weight2 = &k_weight2_t<false>, k_weight2q = &k_weight2_t<true>;
-const auto k_pair_eval_c = &k_pair_eval_col<false>, k_pair_eval_cp = &k_pair_eval_col<true>;  // scalar / packed fp32 arithmetic
-const auto k_weight_c = &k_weight_col<false>, k_weight_cq = &k_weight_col<true>;  // column-major pair buffer
-const auto k_weight2w = &k_weight2w_t<false>, k_weight2wq = &k_weight2w_t<true>;
-const auto k_cz_narrow = &k_cz_chain<128, 4096, 128>;
 const auto k_cz_wide = &k_cz_chain<256, 8192, 128>;
-const auto k_cz_wide_staged = &k_cz_chain<256, 8192, 128, true>;
 inline int grid_for(long long n, int block, int max_blocks = kSMs * 8) {
     long long g = (n + block - 1) / block;
     if (g < 1) g = 1;
@@ -400,65 +420,33 @@ int enqueue_frame_a(dspmap *m, const FrameConst &fc, const float *d_pts, const f
     if (fc.vz_mode) LAUNCH(m, FAM_PREDICT, k_vz_advance, 1, 32, 0, mc, dp);
     LAUNCH(m, FAM_ARRIVE, k_group_owner, kSMs * 2, B, 0, dp, &dp.st->n_mov_owner, dp.mowner, dp.mcnt, dp.mbase, &dp.st->mov_top);
     LAUNCH(m, FAM_ARRIVE, k_group_scatter, kSMs * 4, B, 0, &dp.st->n_mov, dp.MBdst, dp.MBkey, dp.mbase, dp.mfill, dp.mseg, (int *)nullptr);
-    if (m->fuse_scan) {  // the scan of the pyramid counts rides on the arrival kernel's last block
-        LAUNCH(m, FAM_ARRIVE, k_arrive_fs, kSMs * 4, B, 0, mc, fc, dp);
-    } else {
-        LAUNCH(m, FAM_ARRIVE, k_arrive, kSMs * 4, B, 0, mc, fc, dp);
-        LAUNCH(m, FAM_PYRAMID, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{dp.pcount, dp.poff, nullptr, 0, mc.P}, ScanJob{}, ScanJob{}}});
-    }
+    LAUNCH(m, FAM_ARRIVE, k_arrive, kSMs * 4, B, 0, mc, fc, dp);
+    LAUNCH(m, FAM_PYRAMID, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{dp.pcount, dp.poff, nullptr, 0, mc.P}, ScanJob{}, ScanJob{}}});
     LAUNCH(m, FAM_PYRAMID, k_pyr_scatter, kSMs * 8, B, 0, dp);
-    if (m->sort_warp) LAUNCH(m, FAM_PYRAMID, k_pyr_sort_w, std::min(mc.P, kSMs * 3), 512, PYR_SORT_CAP * sizeof(u64), mc, dp, fc.Pd);
-    else LAUNCH(m, FAM_PYRAMID, k_pyr_sort, std::min(mc.P, kSMs * 3), 512, PYR_SORT_CAP * sizeof(u64), mc, dp, fc.Pd);
+    LAUNCH(m, FAM_PYRAMID, k_pyr_sort, std::min(mc.P, kSMs * 3), 512, PYR_SORT_CAP * sizeof(u64), mc, dp, fc.Pd);
     CK(cudaStreamWaitEvent(m->stream, m->ev_join_obs, 0));
     if (fc.stage_limit >= 2) {
-        if (m->fuse_scan) {
-            LAUNCH(m, FAM_CK, k_pair_prep_scan, 1, 1024, 0, mc, dp, m->g_col ? 1 : 0);
-        } else {
-            LAUNCH(m, FAM_CK, k_pair_prep, grid_for(mc.P, B), B, 0, mc, dp, m->g_col ? 1 : 0);
-            LAUNCH(m, FAM_CK, k_scan_small, 2, 1024, 0, ScanJobs{{ScanJob{dp.pairs, dp.rowbase, nullptr, 0, mc.P}, ScanJob{dp.chunks, dp.chunk_off, nullptr, 0, mc.P}, ScanJob{}}});
-        }
-        if (m->g_col) {
-            if (m->eval_packed) LAUNCH(m, FAM_CK, k_pair_eval_cp, kSMs * 4, EVAL_THREADS, sizeof(float) * (DSP_LUT_HALF + 3 + EVALC_KEYS), mc, fc, dp, 0);
-            else LAUNCH(m, FAM_CK, k_pair_eval_c, kSMs * 4, EVAL_THREADS, sizeof(float) * (DSP_LUT_HALF + 3 + EVALC_KEYS), mc, fc, dp, 0);
-            LAUNCH(m, FAM_CK, k_cz_chain_col, std::min(mc.P, kSMs * 2), CZC_THREADS, CZC_SMEM_BYTES, mc, fc, dp);
-        } else {
+        LAUNCH(m, FAM_CK, k_pair_prep, grid_for(mc.P, B), B, 0, mc, dp);
+        LAUNCH(m, FAM_CK, k_scan_small, 2, 1024, 0, ScanJobs{{ScanJob{dp.pairs, dp.rowbase, nullptr, 0, mc.P}, ScanJob{dp.chunks, dp.chunk_off, nullptr, 0, mc.P}, ScanJob{}}});
         LAUNCH(m, FAM_CK, k_pair_eval, kSMs * 2, EVAL_THREADS, sizeof(float) * (DSP_LUT_HALF + 3 + (EVAL_THREADS / 32) * 32 * TILE_LD), mc, fc, dp, 0);
-        if (m->cz_tma) LAUNCH(m, FAM_CK, k_cz_chain_tma, std::min(mc.P, kSMs * 2), CZT_THREADS, CZT_SMEM_BYTES, mc, fc, dp);
-        else if (m->cz_staged) LAUNCH(m, FAM_CK, k_cz_wide_staged, std::min(mc.P, kSMs * 3), 256, sizeof(float) * (2 * (8192 + 8) + 2 * 128), mc, fc, dp);
-        else if (m->cz_wide) LAUNCH(m, FAM_CK, k_cz_wide, std::min(mc.P, kSMs * 3), 256, sizeof(float) * (2 * (8192 + 8) + 2 * 128), mc, fc, dp);
-        else LAUNCH(m, FAM_CK, k_cz_narrow, std::min(mc.P, kSMs * 6), 128, sizeof(float) * (2 * (4096 + 8) + 2 * 128), mc, fc, dp);
-        }
+        LAUNCH(m, FAM_CK, k_cz_wide, std::min(mc.P, kSMs * 3), 256, sizeof(float) * (2 * (8192 + 8) + 2 * 128), mc, fc, dp);
         size_t smem4 = sizeof(float) * (DSP_LUT_HALF + 3 + K4_TERMS) + sizeof(float4) * (256 + mc.OBS);
         if (m->fallback_armed) LAUNCH(m, FAM_CK, k_ck, std::min(mc.P, kSMs * 2), K4_THREADS, smem4, mc, fc, dp);  // returns at once when the pair buffer is used
         if (fc.stage_limit >= 3) {  // the newborn normaliser is one long serial chain: run it beside the weight pass
             CK(cudaEventRecord(m->ev_fork, m->stream));
             CK(cudaStreamWaitEvent(m->side, m->ev_fork, 0));
-            if (m->norm_fast) launch_kernel(m->pdl, m->side, k_norm_fast, 1, 256, 0, mc, fc, dp);
-            else launch_kernel(m->pdl, m->side, k_norm, 1, 128, 0, mc, fc, dp);
+            launch_kernel(m->pdl, m->side, k_norm, 1, 256, 0, mc, fc, dp);
             ++m->launches_total;
             ++m->launches_frame;
             CK(cudaEventRecord(m->ev_join, m->side));
         }
-        if (m->g_col) {
-            if (m->quot_fast) LAUNCH(m, FAM_WEIGHT, k_weight_cq, kSMs * 8, 256, 0, mc, fc, dp);
-            else LAUNCH(m, FAM_WEIGHT, k_weight_c, kSMs * 8, 256, 0, mc, fc, dp);
-        } else if (m->quot_fast) {
-            LAUNCH(m, FAM_WEIGHT, k_weight2q, kSMs * 8, W2_THREADS, 0, mc, fc, dp);
-            LAUNCH(m, FAM_WEIGHT, k_weight2wq, kSMs * 6, W2W_THREADS, 0, mc, fc, dp);
-        } else {
-            LAUNCH(m, FAM_WEIGHT, k_weight2, kSMs * 8, W2_THREADS, 0, mc, fc, dp);
-            LAUNCH(m, FAM_WEIGHT, k_weight2w, kSMs * 6, W2W_THREADS, 0, mc, fc, dp);
-        }
+        LAUNCH(m, FAM_WEIGHT, k_weight2, kSMs * 8, W2_THREADS, 0, mc, fc, dp);
+        LAUNCH(m, FAM_WEIGHT, k_weight2w, kSMs * 6, W2W_THREADS, 0, mc, fc, dp);
         size_t smem5 = sizeof(float) * (DSP_LUT_HALF + 3) + sizeof(float4) * (size_t)mc.NB * (mc.OBS - 1);
         int chunks = (mc.L + K5_THREADS - 1) / K5_THREADS;
         if (m->fallback_armed) LAUNCH(m, FAM_WEIGHT, k_weight, kSMs * 2, K5_THREADS, smem5, mc, fc, dp, chunks);
-        // the normaliser is first read by k_nb_cand (w_new).  With the fast weight pass it is the longer branch, so its join
-        // moves behind the newborn kernels that do not need it (enqueue_frame_b); otherwise it is joined here
+        // the normaliser is first read by k_nb_cand (w_new): it is joined behind the newborn kernels that do not need it
         m->norm_join_pending = fc.stage_limit >= 3;
-        if (m->norm_join_pending && !(m->quot_fast || m->g_col || m->norm_fast)) {
-            CK(cudaStreamWaitEvent(m->stream, m->ev_join, 0));
-            m->norm_join_pending = false;
-        }
     }
     CK(cudaGetLastError());
     return DSPMAP_OK;
@@ -477,12 +465,8 @@ int enqueue_frame_b(dspmap *m, const FrameConst &fc, const float *d_tagged) {
                 LAUNCH(m, FAM_NEWBORN, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{dp.ninmap, dp.nrank, nullptr, 0, fc.n_tagged}, ScanJob{}, ScanJob{}}});
                 LAUNCH(m, FAM_NEWBORN, k_nb_mask, grid_for((long long)fc.n_tagged * fc.nb_num, B), B, 0, mc, fc, dp);
             }
-            if (m->fuse_scan) {
-                LAUNCH(m, FAM_NEWBORN, k_nb_point1_fs, grid_for((long long)fc.n_tagged * 32, B), B, 0, mc, fc, dp, 0);
-            } else {
-                LAUNCH(m, FAM_NEWBORN, k_nb_point1, grid_for((long long)fc.n_tagged * 32, B), B, 0, mc, fc, dp, 0);
-                LAUNCH(m, FAM_NEWBORN, k_scan_small, 2, 1024, 0, ScanJobs{{ScanJob{dp.nvcnt, dp.nvoff, nullptr, 0, fc.n_tagged}, ScanJob{dp.nrcnt, dp.nroff, nullptr, 0, fc.n_tagged}, ScanJob{}}});
-            }
+            LAUNCH(m, FAM_NEWBORN, k_nb_point1, grid_for((long long)fc.n_tagged * 32, B), B, 0, mc, fc, dp, 0);
+            LAUNCH(m, FAM_NEWBORN, k_scan_small, 2, 1024, 0, ScanJobs{{ScanJob{dp.nvcnt, dp.nvoff, nullptr, 0, fc.n_tagged}, ScanJob{dp.nrcnt, dp.nroff, nullptr, 0, fc.n_tagged}, ScanJob{}}});
             if (m->norm_join_pending) {  // k_norm (side stream) wrote w_new, which k_nb_cand reads
                 CK(cudaStreamWaitEvent(m->stream, m->ev_join, 0));
                 m->norm_join_pending = false;
@@ -490,15 +474,13 @@ int enqueue_frame_b(dspmap *m, const FrameConst &fc, const float *d_tagged) {
             LAUNCH(m, FAM_NEWBORN, k_nb_cand, grid_for((long long)fc.n_tagged * fc.nb_num, B), B, 0, mc, fc, dp, (u64)m->cfg.uniform_seed);
             LAUNCH(m, FAM_NEWBORN, k_group_owner, kSMs * 2, B, 0, dp, &dp.st->n_cand_owner, dp.cowner, dp.ccnt, dp.cbase, &dp.st->cand_top);
             LAUNCH(m, FAM_NEWBORN, k_group_scatter, kSMs * 4, B, 0, &dp.st->n_cand, dp.Cdst, dp.Ckey, dp.cbase, dp.cfill, dp.cseg, dp.csegi);
-            if (m->nb_redux) LAUNCH(m, FAM_NEWBORN, k_nb_place_redux, kSMs * 8, B, 0, mc, fc, dp);
-            else LAUNCH(m, FAM_NEWBORN, k_nb_place, kSMs * 8, B, 0, mc, fc, dp);
+            LAUNCH(m, FAM_NEWBORN, k_nb_place, kSMs * 8, B, 0, mc, fc, dp);
             newborn_ran = 1;
         }
     }
     if (fc.stage_limit >= 4) {
         LAUNCH(m, FAM_RESAMPLE, k_voxel_list, grid_for(mc.V, B), B, 0, mc, dp);
-        if (m->resample_sm) LAUNCH(m, FAM_RESAMPLE, k_resample_sm, kSMs * 8, 32 * RS_WARPS, 0, mc, fc, dp);
-        else LAUNCH(m, FAM_RESAMPLE, k_resample, kSMs * 8, 256, 0, mc, fc, dp);
+        LAUNCH(m, FAM_RESAMPLE, k_resample, kSMs * 8, 256, 0, mc, fc, dp);
     }
     if (m->norm_join_pending) {  // no newborn kernels this frame: k_norm must still be over before the next frame resets its outputs
         CK(cudaStreamWaitEvent(m->stream, m->ev_join, 0));
@@ -509,6 +491,7 @@ int enqueue_frame_b(dspmap *m, const FrameConst &fc, const float *d_tagged) {
     CK(cudaMemcpyAsync(m->h_state, m->dp.st, sizeof(DevState), cudaMemcpyDeviceToHost, m->stream));
     CK(cudaEventRecord(m->ev_state, m->stream));
     m->state_event_recorded = true;
+    ++m->state_copies;
     CK(cudaGetLastError());
     return DSPMAP_OK;
 }
@@ -561,29 +544,26 @@ int frame_prologue(dspmap *m, int n, float px, float py, float pz, double t, flo
     // The recompute kernels are left out only when the host KNOWS the previous frame's pair count (its state copy has
     // completed) and it is below half the buffer; growth from one frame to the next is gradual.
     m->fallback_armed = true;
-    if (m->update_counter > 2 && m->state_event_recorded && cudaEventQuery(m->ev_state) == cudaSuccess)
-        m->fallback_armed = m->h_state->total_pairs * 2ull > (unsigned long long)m->mc.cap_pairs;
-    else
+    if (m->state_event_recorded && cudaEventQuery(m->ev_state) == cudaSuccess) {
+        absorb_state(m);
+        if (m->update_counter > 2) m->fallback_armed = m->fallback_forced || m->h_state->total_pairs * 2ull > (unsigned long long)m->mc.cap_pairs;
+    } else {
         cudaGetLastError();  // cudaErrorNotReady is not an error here
+    }
+    if (m->clear_overflow) {  // stream-ordered in front of this frame's kernels
+        if (cudaMemsetAsync(&m->dp.st->overflow, 0, sizeof(int), m->stream) != cudaSuccess) { g_err = "cudaMemsetAsync(overflow)"; return DSPMAP_E_CUDA; }
+        m->clear_overflow = false;
+    }
     return DSPMAP_OK;
 }
 
 int frame_epilogue(dspmap *m) {
-    CK(cudaMemcpyAsync(m->h_state, m->dp.st, sizeof(DevState), cudaMemcpyDeviceToHost, m->stream));
-    CK(cudaStreamSynchronize(m->stream));
-    m->last_state = *m->h_state;
+    CK(cudaStreamSynchronize(m->stream));  // (every frame ends with an asynchronous copy of the device state)
+    absorb_state(m);
     if (m->profile) prof_collect(m);
     // once a frame has predicted every particle and drew no noise, all vz are 0 for good (LIMIT_MOVEMENT_IN_XY_PLANE)
     if (m->vz_mode && m->stage_limit >= 4 && m->last_state.n_vz == 0 && m->last_state.n_skipped == 0) m->vz_mode = false;
-    if (m->last_state.overflow) {
-        char buf[256];
-        snprintf(buf, sizeof(buf), "device capacity exceeded: code %d (1 live list, 2 newborn candidates, 4 pair buffer without fallback, "
-                 "8 shard crossers, 16 shard gather); pairs this frame %llu, capacity %lld", m->last_state.overflow,
-                 m->last_state.total_pairs, m->mc.cap_pairs);
-        g_err = buf;
-        return DSPMAP_E_CAPACITY;
-    }
-    return DSPMAP_OK;
+    return report_overflow(m);
 }
 
 int write_particle_csv(dspmap *m);
@@ -631,8 +611,12 @@ void dspmap_default_config(dspmap_config *c) {
     c->occlusion_margin = 0.3f;
     c->init_particle_num = 0;
     c->init_weight = 0.01f;
+    // the reference seeds both generators from the wall clock (dsp_dynamic.h:586, 1151); DSPMAP_TABLE_SEED / DSPMAP_UNIFORM_SEED
+    // pin them for reproducible runs of an unchanged application (tests/test_dropin.py compares such a run bit for bit)
     c->table_seed = (uint64_t)time(nullptr);
     c->uniform_seed = (uint64_t)time(nullptr);
+    if (const char *e = getenv("DSPMAP_TABLE_SEED")) if (*e) c->table_seed = strtoull(e, nullptr, 10);
+    if (const char *e = getenv("DSPMAP_UNIFORM_SEED")) if (*e) c->uniform_seed = strtoull(e, nullptr, 10);
     c->gaussian_table_size = 10000000;
     c->max_observations_per_pyramid = 100;
     c->device = 0;
@@ -650,6 +634,12 @@ int dspmap_create(const dspmap_config *cfg, dspmap **out) {
     if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess || prop.major < 10) {
         g_err = "device is not sm_100 class: the kernels are built for sm_100a only";
         return DSPMAP_E_NO_DEVICE;
+    }
+    if (cfg->nx <= 0 || cfg->ny <= 0 || cfg->nz <= 0 || !(cfg->resolution > 0.f) || cfg->angle_resolution <= 0 || cfg->half_fov_h <= 0 ||
+        cfg->half_fov_v <= 0 || cfg->max_particles_per_voxel <= 0 || cfg->pyramid_neighbor_n < 0 || cfg->prediction_times < 0 ||
+        (long long)cfg->nx * cfg->ny * cfg->nz * DSP_MAX_SLOTS > 2147483647ll) {
+        g_err = "bad configuration: sizes, resolutions and field-of-view angles must be positive and V * 128 < 2^31";
+        return DSPMAP_E_BAD_ARG;
     }
     CK(cudaSetDevice(cfg->device));
     dspmap *m = new dspmap();
@@ -691,14 +681,14 @@ int dspmap_create(const dspmap_config *cfg, dspmap **out) {
     mc.vlo = mc.S >= 64 ? ~0ull : ((1ull << mc.S) - 1ull);
     mc.vhi = mc.S <= 64 ? 0ull : (mc.S >= 128 ? ~0ull : ((1ull << (mc.S - 64)) - 1ull));
     m->max_points = cfg->max_points > 0 ? cfg->max_points : 65536;
-    CK(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking));
-    CK(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&m->ev_fork_obs, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&m->ev_join_obs, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&m->ev_state, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&m->ev_staged, cudaEventDisableTiming));
+    CKM(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
+    CKM(cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking));
+    CKM(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+    CKM(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
+    CKM(cudaEventCreateWithFlags(&m->ev_fork_obs, cudaEventDisableTiming));
+    CKM(cudaEventCreateWithFlags(&m->ev_join_obs, cudaEventDisableTiming));
+    CKM(cudaEventCreateWithFlags(&m->ev_state, cudaEventDisableTiming));
+    CKM(cudaEventCreateWithFlags(&m->ev_staged, cudaEventDisableTiming));
     m->stream = m->own_stream;
 
     DevPtrs &dp = m->dp;
@@ -722,8 +712,6 @@ int dspmap_create(const dspmap_config *cfg, dspmap **out) {
     mc.cap_pairs = 512ll << 20;  // 2 GB of fp32 pair terms (of 180 GB); larger frames fall back to the recompute kernels
     A(dp.G, (size_t)mc.cap_pairs + 64); A(dp.cum, P * mc.NBW); A(dp.totlen, P); A(dp.pairs, P + 1); A(dp.rowbase, P + 1);
     A(dp.chunks, P + 1); A(dp.chunk_off, P + 1);
-    int *cz_order_buf = nullptr;
-    A(cz_order_buf, P);
     A(dp.NPC, MP); A(dp.ninmap, MP + 1); A(dp.nrank, MP + 1); A(dp.nstatic, MP); A(dp.nvcnt, MP + 1); A(dp.nrcnt, MP + 1);
     A(dp.nvoff, MP + 1); A(dp.nroff, MP + 1); A(dp.nimask, MP);
     A(dp.ccnt, V); A(dp.cfill, V); A(dp.cbase, V); A(dp.cowner, V);
@@ -740,12 +728,12 @@ int dspmap_create(const dspmap_config *cfg, dspmap **out) {
     dp.ptab = d_ptab; dp.vtab = d_vtab; dp.lut = d_lut; dp.planes0 = d_planes0; dp.nbr = d_nbr;
     dp.pts = d_pts; dp.tagged = d_tagged;
     if (ensure_cand_capacity(m) != DSPMAP_OK) { dspmap_destroy(m); return DSPMAP_E_CUDA; }
-    CK(cudaMallocHost(&m->h_pts, sizeof(float) * MP * 3));
-    CK(cudaMallocHost(&m->h_tagged, sizeof(float) * MP * 7));
-    CK(cudaMallocHost(&m->h_future, sizeof(float) * V * std::max(mc.T, 1)));
-    CK(cudaMallocHost(&m->h_xyz, sizeof(float) * V * 3));
-    CK(cudaMallocHost(&m->h_state, sizeof(DevState)));
-    CK(cudaMallocHost(&m->h_count, sizeof(int)));
+    CKM(cudaMallocHost(&m->h_pts, sizeof(float) * MP * 3));
+    CKM(cudaMallocHost(&m->h_tagged, sizeof(float) * MP * 7));
+    CKM(cudaMallocHost(&m->h_future, sizeof(float) * V * std::max(mc.T, 1)));
+    CKM(cudaMallocHost(&m->h_xyz, sizeof(float) * V * 3));
+    CKM(cudaMallocHost(&m->h_state, sizeof(DevState)));
+    CKM(cudaMallocHost(&m->h_count, sizeof(int)));
 
     make_planes0(cfg, mc.Nh, mc.Nv, m->planes0);  // boundary-plane normals in the sensor frame (:563-578)
     // neighbour table (:1128-1147; mn:1135-1136)
@@ -777,38 +765,19 @@ int dspmap_create(const dspmap_config *cfg, dspmap **out) {
         for (int h = 0; h < 10000; ++h) m->lut[h] = full[10000 + h];
         m->lut[10000] = full[0];  // |i - 10000| = 10000 only for i = 0 (x = -10); unreachable, queries clamp to |x| <= 9.9
     }
-    CK(cudaMemcpyAsync(d_lut, m->lut.data(), sizeof(float) * DSP_LUT_HALF, cudaMemcpyHostToDevice, m->stream));
-    CK(cudaMemcpyAsync(d_planes0, m->planes0.data(), sizeof(float) * m->planes0.size(), cudaMemcpyHostToDevice, m->stream));
-    CK(cudaMemcpyAsync(d_nbr, m->nbr.data(), sizeof(int) * m->nbr.size(), cudaMemcpyHostToDevice, m->stream));
-    CK(cudaFuncSetAttribute(k_pyr_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PYR_SORT_CAP * sizeof(u64))));
-    CK(cudaFuncSetAttribute(k_pyr_sort_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PYR_SORT_CAP * sizeof(u64))));
-    CK(cudaFuncSetAttribute(k_ck, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    CK(cudaFuncSetAttribute(k_pair_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-    CK(cudaFuncSetAttribute(k_cz_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
-    CK(cudaFuncSetAttribute(k_cz_wide_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
-    CK(cudaFuncSetAttribute(k_cz_chain_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, CZT_SMEM_BYTES));
-    CK(cudaFuncSetAttribute(k_cz_chain_col, cudaFuncAttributeMaxDynamicSharedMemorySize, CZC_SMEM_BYTES));
-    CK(cudaFuncSetAttribute(k_pair_eval_c, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * (DSP_LUT_HALF + 3 + EVALC_KEYS))));
-    CK(cudaFuncSetAttribute(k_pair_eval_cp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * (DSP_LUT_HALF + 3 + EVALC_KEYS))));
-    // experiment switches; all off by default
-    m->pdl = env_on("DSPMAP_PDL");
-    m->cz_tma = env_on("DSPMAP_CZ_TMA");
-    m->cz_staged = env_on("DSPMAP_CZ_STAGED");
-    m->g_col = env_on("DSPMAP_G_COL");
-    dp.cz_order = (m->cz_tma || m->g_col) ? cz_order_buf : nullptr;
-    m->nb_redux = env_on("DSPMAP_NB_REDUX");
-    m->quot_fast = env_on("DSPMAP_QUOT_FAST");
-    m->norm_fast = env_on("DSPMAP_NORM_FAST");
-    m->resample_sm = env_on("DSPMAP_RESAMPLE_SM");
-    m->sort_warp = env_on("DSPMAP_SORT_WARP");
-    m->eval_packed = env_on("DSPMAP_EVAL_PACKED");
-    m->fuse_scan = env_on("DSPMAP_FUSE_SCAN");
-    m->est_thread = env_on("DSPMAP_EST_THREAD");
-    m->sparse_future = env_on("DSPMAP_SPARSE_FUTURE");
-    m->async_update = env_on("DSPMAP_ASYNC_UPDATE");
-    m->cz_wide = getenv("DSPMAP_CZ_NARROW") == nullptr;  // experiment switch: DSPMAP_CZ_NARROW selects the 128-thread / 32 KB configuration
-    CK(cudaFuncSetAttribute(k_weight, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CK(cudaStreamSynchronize(m->stream));
+    CKM(cudaMemcpyAsync(d_lut, m->lut.data(), sizeof(float) * DSP_LUT_HALF, cudaMemcpyHostToDevice, m->stream));
+    CKM(cudaMemcpyAsync(d_planes0, m->planes0.data(), sizeof(float) * m->planes0.size(), cudaMemcpyHostToDevice, m->stream));
+    CKM(cudaMemcpyAsync(d_nbr, m->nbr.data(), sizeof(int) * m->nbr.size(), cudaMemcpyHostToDevice, m->stream));
+    CKM(cudaFuncSetAttribute(k_pyr_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PYR_SORT_CAP * sizeof(u64))));
+    CKM(cudaFuncSetAttribute(k_ck, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CKM(cudaFuncSetAttribute(k_pair_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    CKM(cudaFuncSetAttribute(k_cz_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    // the three defaults that can be turned off for A/B measurements (profiles/r02_ab_switches.jsonl)
+    m->pdl = !env_off("DSPMAP_PDL");
+    m->est_thread = !env_off("DSPMAP_EST_THREAD");
+    m->async_update = !env_off("DSPMAP_ASYNC_UPDATE");
+    CKM(cudaFuncSetAttribute(k_weight, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CKM(cudaStreamSynchronize(m->stream));
     if (gen_tables(m) != DSPMAP_OK) { dspmap_destroy(m); return DSPMAP_E_CUDA; }
     {   // (p + half) / res with p inside the map: dividends lie in (0, 2*half)
         mc.res_r = 1.f / mc.res;
@@ -823,7 +792,7 @@ int dspmap_create(const dspmap_config *cfg, dspmap **out) {
         DevState st;
         memset(&st, 0, sizeof(st));
         st.u_cur = m->host_u_cur;
-        CK(cudaMemcpy(dp.st, &st, sizeof(st), cudaMemcpyHostToDevice));
+        CKM(cudaMemcpy(dp.st, &st, sizeof(st), cudaMemcpyHostToDevice));
     }
     memset(&m->last_state, 0, sizeof(m->last_state));
     printf("Map is ready to update!\n");  // :174
@@ -869,7 +838,7 @@ void dspmap_destroy(dspmap *m) {
 
 static int update_common(dspmap *m, int n, int stride, const float *pts, float px, float py, float pz, double t, float qw,
                          float qx, float qy, float qz, const float *tagged, int n_tagged, bool use_estimator) {
-    if (!m || n < 0 || stride < 3 || (n > 0 && !pts)) { g_err = "bad argument"; return DSPMAP_E_BAD_ARG; }
+    if (!m || n < 0 || stride < 3 || (n > 0 && !pts) || n_tagged < 0 || (n_tagged > 0 && !tagged)) { g_err = "bad argument"; return DSPMAP_E_BAD_ARG; }
     if (n > m->max_points || n_tagged > m->max_points) { g_err = "more points than dspmap_config.max_points"; return DSPMAP_E_CAPACITY; }
     CK(cudaSetDevice(m->cfg.device));
     FrameConst fc;
@@ -905,8 +874,9 @@ static int update_common(dspmap *m, int n, int stride, const float *pts, float p
         // the reference's side thread (dsp_dynamic.h:297, 1377-1544), overlapped with the kernels enqueued above exactly
         // as the reference overlaps it with prediction + update (:297-311)
         m->estimator.estimate(m->mc, fc, m->planes0.data(), m->h_pts, n, m->cfg.model, m->tagged_host);
-    } else if (tagged) {
-        m->tagged_host.assign(tagged, tagged + (size_t)7 * n_tagged);
+    } else if (!use_estimator) {  // explicit newborn input: exactly what the caller passed, possibly nothing
+        if (n_tagged > 0) m->tagged_host.assign(tagged, tagged + (size_t)7 * n_tagged);
+        else m->tagged_host.clear();
     }
     int nt = (int)(m->tagged_host.size() / 7);
     if (nt > m->max_points) { g_err = "newborn input larger than max_points"; return DSPMAP_E_CAPACITY; }
@@ -921,9 +891,10 @@ static int update_common(dspmap *m, int n, int stride, const float *pts, float p
     }
     if ((rc = enqueue_frame_b(m, fc, m->dp.tagged)) != DSPMAP_OK) return rc;
     // Asynchronous update: like dspmap_update_device, return with the frame enqueued; readers and dumps are stream-ordered or
-    // synchronise themselves, dspmap_counters / dspmap_synchronize pick up the frame's state copy.  (Capacity overruns are
-    // then reported by dspmap_synchronize instead of by this call.)
-    if (m->async_update && !m->vz_mode && !m->record_flag && !m->profile) return DSPMAP_OK;
+    // synchronise themselves, dspmap_counters / dspmap_synchronize pick up the frame's state copy.  A capacity overrun of an
+    // earlier frame (latched by frame_prologue from that frame's state copy) is reported here; this frame's own by the next
+    // call that synchronises.
+    if (m->async_update && !m->vz_mode && !m->record_flag && !m->profile) return report_overflow(m);
     if ((rc = frame_epilogue(m)) != DSPMAP_OK) return rc;
     // particle CSV (:325-350)
     if (m->record_flag) {
@@ -945,7 +916,10 @@ int dspmap_update_tagged(dspmap *m, int n, int stride, const float *pts, float p
 }
 int dspmap_update_device(dspmap *m, int n, const float *d_pts, float px, float py, float pz, double t, float qw,
                          float qx, float qy, float qz, const float *d_tagged, int n_tagged) {
-    if (!m || n < 0 || n > m->max_points || n_tagged > m->max_points) { g_err = "bad argument"; return DSPMAP_E_BAD_ARG; }
+    if (!m || n < 0 || n > m->max_points || n_tagged < 0 || n_tagged > m->max_points || (n > 0 && !d_pts) || (n_tagged > 0 && !d_tagged)) {
+        g_err = "bad argument";
+        return DSPMAP_E_BAD_ARG;
+    }
     CK(cudaSetDevice(m->cfg.device));
     FrameConst fc;
     int rc = frame_prologue(m, n, px, py, pz, t, qw, qx, qy, qz, &fc);
@@ -961,7 +935,7 @@ int dspmap_update_device(dspmap *m, int n, const float *d_pts, float px, float p
     if ((rc = enqueue_frame_a(m, fc, d_pts, d_tagged)) != DSPMAP_OK) return rc;
     if ((rc = enqueue_frame_b(m, fc, d_tagged)) != DSPMAP_OK) return rc;
     if (m->vz_mode) return frame_epilogue(m);  // keep the ordered-noise path armed only as long as it is needed
-    return DSPMAP_OK;
+    return report_overflow(m);  // an earlier frame's overrun, latched by frame_prologue; this frame's own shows up at the next synchronising call
 }
 
 int dspmap_shard_config(dspmap *m, int rank, int nranks, float *xsend, float *xrecv, int cap_x, float *gsend, float *grecv,
@@ -1054,44 +1028,22 @@ int dspmap_shard_phase(dspmap *m, int phase, int n, const float *d_pts, float px
         LAUNCH(m, FAM_PYRAMID, k_shard_fov_gathered, kSMs * 8, B, 0, mc, dp, 0);
         LAUNCH(m, FAM_PYRAMID, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{dp.pcount, dp.poff, nullptr, 0, mc.P}, ScanJob{}, ScanJob{}}});
         LAUNCH(m, FAM_PYRAMID, k_shard_fov_gathered, kSMs * 8, B, 0, mc, dp, 1);
-        if (m->sort_warp) LAUNCH(m, FAM_PYRAMID, k_pyr_sort_w, std::min(mc.P, kSMs * 3), 512, PYR_SORT_CAP * sizeof(u64), mc, dp, fc.Pd);
-        else LAUNCH(m, FAM_PYRAMID, k_pyr_sort, std::min(mc.P, kSMs * 3), 512, PYR_SORT_CAP * sizeof(u64), mc, dp, fc.Pd);
-        LAUNCH(m, FAM_CK, k_pair_prep, grid_for(mc.P, B), B, 0, mc, dp, m->g_col ? 1 : 0);
+        LAUNCH(m, FAM_PYRAMID, k_pyr_sort, std::min(mc.P, kSMs * 3), 512, PYR_SORT_CAP * sizeof(u64), mc, dp, fc.Pd);
+        LAUNCH(m, FAM_CK, k_pair_prep, grid_for(mc.P, B), B, 0, mc, dp);
         LAUNCH(m, FAM_CK, k_scan_small, 2, 1024, 0, ScanJobs{{ScanJob{dp.pairs, dp.rowbase, nullptr, 0, mc.P}, ScanJob{dp.chunks, dp.chunk_off, nullptr, 0, mc.P}, ScanJob{}}});
         LAUNCH(m, FAM_CK, k_shard_zero, kSMs * 2, B, 0, mc, fc, dp, 0);
-        if (m->g_col) {
-            if (m->eval_packed) LAUNCH(m, FAM_CK, k_pair_eval_cp, kSMs * 4, EVAL_THREADS, sizeof(float) * (DSP_LUT_HALF + 3 + EVALC_KEYS), mc, fc, dp, 1);
-            else LAUNCH(m, FAM_CK, k_pair_eval_c, kSMs * 4, EVAL_THREADS, sizeof(float) * (DSP_LUT_HALF + 3 + EVALC_KEYS), mc, fc, dp, 1);
-            LAUNCH(m, FAM_CK, k_cz_chain_col, std::min(mc.P, kSMs * 2), CZC_THREADS, CZC_SMEM_BYTES, mc, fc, dp);
-        } else {
         LAUNCH(m, FAM_CK, k_pair_eval, kSMs * 2, EVAL_THREADS, sizeof(float) * (DSP_LUT_HALF + 3 + (EVAL_THREADS / 32) * 32 * TILE_LD), mc, fc, dp, 1);
-        if (m->cz_tma) LAUNCH(m, FAM_CK, k_cz_chain_tma, std::min(mc.P, kSMs * 2), CZT_THREADS, CZT_SMEM_BYTES, mc, fc, dp);
-        else if (m->cz_staged) LAUNCH(m, FAM_CK, k_cz_wide_staged, std::min(mc.P, kSMs * 3), 256, sizeof(float) * (2 * (8192 + 8) + 2 * 128), mc, fc, dp);
-        else if (m->cz_wide) LAUNCH(m, FAM_CK, k_cz_wide, std::min(mc.P, kSMs * 3), 256, sizeof(float) * (2 * (8192 + 8) + 2 * 128), mc, fc, dp);
-        else LAUNCH(m, FAM_CK, k_cz_narrow, std::min(mc.P, kSMs * 6), 128, sizeof(float) * (2 * (4096 + 8) + 2 * 128), mc, fc, dp);
-        }
+        LAUNCH(m, FAM_CK, k_cz_wide, std::min(mc.P, kSMs * 3), 256, sizeof(float) * (2 * (8192 + 8) + 2 * 128), mc, fc, dp);
     } else if (phase == 3) {
         dp.tagged = d_tagged;
         LAUNCH(m, FAM_WEIGHT, k_shard_zero, kSMs * 2, B, 0, mc, fc, dp, 1);
-        if (m->g_col) {
-            if (m->eval_packed) LAUNCH(m, FAM_WEIGHT, k_pair_eval_cp, kSMs * 4, EVAL_THREADS, sizeof(float) * (DSP_LUT_HALF + 3 + EVALC_KEYS), mc, fc, dp, 2);
-            else LAUNCH(m, FAM_WEIGHT, k_pair_eval_c, kSMs * 4, EVAL_THREADS, sizeof(float) * (DSP_LUT_HALF + 3 + EVALC_KEYS), mc, fc, dp, 2);
-            if (m->quot_fast) LAUNCH(m, FAM_WEIGHT, k_weight_cq, kSMs * 8, 256, 0, mc, fc, dp);
-            else LAUNCH(m, FAM_WEIGHT, k_weight_c, kSMs * 8, 256, 0, mc, fc, dp);
-        } else {
         LAUNCH(m, FAM_WEIGHT, k_pair_eval, kSMs * 2, EVAL_THREADS, sizeof(float) * (DSP_LUT_HALF + 3 + (EVAL_THREADS / 32) * 32 * TILE_LD), mc, fc, dp, 2);
-        if (m->quot_fast) {
-            LAUNCH(m, FAM_WEIGHT, k_weight2q, kSMs * 8, W2_THREADS, 0, mc, fc, dp);
-            LAUNCH(m, FAM_WEIGHT, k_weight2wq, kSMs * 6, W2W_THREADS, 0, mc, fc, dp);
-        } else {
-            LAUNCH(m, FAM_WEIGHT, k_weight2, kSMs * 8, W2_THREADS, 0, mc, fc, dp);
-            LAUNCH(m, FAM_WEIGHT, k_weight2w, kSMs * 6, W2W_THREADS, 0, mc, fc, dp);
-        }
-        }
+        LAUNCH(m, FAM_WEIGHT, k_weight2, kSMs * 8, W2_THREADS, 0, mc, fc, dp);
+        LAUNCH(m, FAM_WEIGHT, k_weight2w, kSMs * 6, W2W_THREADS, 0, mc, fc, dp);
     } else if (phase == 4) {  // owners take their new weights; the newborn split reads them (dsp_dynamic.h:829-866)
         dp.tagged = d_tagged;
         LAUNCH(m, FAM_WEIGHT, k_shard_apply_weights, kSMs * 4, B, 0, mc, dp);
-        LAUNCH(m, FAM_NORM, k_norm, 1, 128, 0, mc, fc, dp);
+        LAUNCH(m, FAM_NORM, k_norm, 1, 256, 0, mc, fc, dp);
         if (fc.n_tagged > 0 && fc.nb_num > 0) {
             LAUNCH(m, FAM_NEWBORN, k_shard_zero, kSMs, B, 0, mc, fc, dp, 2);
             LAUNCH(m, FAM_NEWBORN, k_nb_point0, grid_for(fc.n_tagged, B), B, 0, mc, fc, dp);
@@ -1108,17 +1060,16 @@ int dspmap_shard_phase(dspmap *m, int phase, int n, const float *d_pts, float px
             LAUNCH(m, FAM_NEWBORN, k_nb_cand, grid_for((long long)fc.n_tagged * fc.nb_num, B), B, 0, mc, fc, dp, (u64)m->cfg.uniform_seed);
             LAUNCH(m, FAM_NEWBORN, k_group_owner, kSMs * 2, B, 0, dp, &dp.st->n_cand_owner, dp.cowner, dp.ccnt, dp.cbase, &dp.st->cand_top);
             LAUNCH(m, FAM_NEWBORN, k_group_scatter, kSMs * 4, B, 0, &dp.st->n_cand, dp.Cdst, dp.Ckey, dp.cbase, dp.cfill, dp.cseg, dp.csegi);
-            if (m->nb_redux) LAUNCH(m, FAM_NEWBORN, k_nb_place_redux, kSMs * 8, B, 0, mc, fc, dp);
-            else LAUNCH(m, FAM_NEWBORN, k_nb_place, kSMs * 8, B, 0, mc, fc, dp);
+            LAUNCH(m, FAM_NEWBORN, k_nb_place, kSMs * 8, B, 0, mc, fc, dp);
             newborn_ran = 1;
         }
         LAUNCH(m, FAM_RESAMPLE, k_voxel_list, grid_for(mc.V, B), B, 0, mc, dp);
-        if (m->resample_sm) LAUNCH(m, FAM_RESAMPLE, k_resample_sm, kSMs * 8, 32 * RS_WARPS, 0, mc, fc, dp);
-        else LAUNCH(m, FAM_RESAMPLE, k_resample, kSMs * 8, 256, 0, mc, fc, dp);
+        LAUNCH(m, FAM_RESAMPLE, k_resample, kSMs * 8, 256, 0, mc, fc, dp);
         LAUNCH(m, FAM_CLEANUP, k_cleanup, kSMs * 2, B, 0, mc, fc, dp, newborn_ran, 0);
         CK(cudaMemcpyAsync(m->h_state, m->dp.st, sizeof(DevState), cudaMemcpyDeviceToHost, m->stream));
         CK(cudaEventRecord(m->ev_state, m->stream));
         m->state_event_recorded = true;
+        ++m->state_copies;
     } else {
         g_err = "phase must be 0..5";
         return DSPMAP_E_BAD_ARG;
@@ -1159,12 +1110,8 @@ int dspmap_get_occupancy_device(dspmap *m, float thr, float *d_xyz, int cap, int
     if (!m) return DSPMAP_E_BAD_ARG;
     CK(cudaSetDevice(m->cfg.device));
     const MapConst &mc = m->mc;
-    if (m->fuse_scan) {
-        LAUNCH(m, FAM_READER, k_occ_count_fs, m->occ_blocks, 256, 0, mc, m->dp, thr, m->d_blockcnt, m->d_blockoff, m->occ_blocks, d_future);
-    } else {
-        LAUNCH(m, FAM_READER, k_occ_count, m->occ_blocks, 256, 0, mc, m->dp, thr, m->d_blockcnt, d_future);
-        LAUNCH(m, FAM_READER, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{m->d_blockcnt, m->d_blockoff, nullptr, 0, m->occ_blocks}, ScanJob{}, ScanJob{}}});
-    }
+    LAUNCH(m, FAM_READER, k_occ_count, m->occ_blocks, 256, 0, mc, m->dp, thr, m->d_blockcnt, d_future);
+    LAUNCH(m, FAM_READER, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{m->d_blockcnt, m->d_blockoff, nullptr, 0, m->occ_blocks}, ScanJob{}, ScanJob{}}});
     LAUNCH(m, FAM_READER, k_occ_write, m->occ_blocks, 256, 0, mc, m->dp, thr, m->d_blockoff, d_xyz, cap, d_count, m->occ_blocks);
     CK(cudaGetLastError());
     return DSPMAP_OK;
@@ -1185,7 +1132,7 @@ int dspmap_get_occupancy(dspmap *m, float thr, float *xyz_out, int cap, int *n_o
     // A registered buffer is only ever written by this function, so it still holds the previous call's result: instead of
     // the dense grid, the non-zero voxel rows travel and the buffer is patched (rows that were non-zero last time are cleared
     // first).  Contract (include/dspmap_b200.h): while registered, the application treats the buffer as read-only.
-    const bool sparse = direct && m->sparse_future && mc.T > 0;
+    const bool sparse = direct && mc.T > 0;
     int fguess = 0;
     if (sparse) {
         if (!m->d_fcnt) {
@@ -1221,7 +1168,7 @@ int dspmap_get_occupancy(dspmap *m, float thr, float *xyz_out, int cap, int *n_o
         m->fut_guess = std::max(8192, 2 * nf);
         m->sparse_rows.apply(future, mc.V, mc.T, m->h_fidx, m->h_fval, nf);
     }
-    if (m->async_update && m->update_counter > 0) m->last_state = *m->h_state;  // the frame's state copy has landed by now
+    if (m->update_counter > 0 && m->state_event_recorded) absorb_state(m);  // the frame's state copy has landed by now
     int n = *m->h_count;
     if (n_out) *n_out = n;
     int ncopy = std::min(n, cap);
@@ -1460,13 +1407,13 @@ int dspmap_set_cursors(dspmap *m, int64_t p, int64_t v, int64_t u) {
 }
 int dspmap_counters(dspmap *m, int64_t *out) {
     if (!m) return DSPMAP_E_BAD_ARG;
-    if (m->async_update && m->update_counter > 0) {  // the last frame may still be running: wait for its state copy
+    if (m->update_counter > 0 && m->state_event_recorded) {  // the last frame may still be running: wait for its state copy
         CK(cudaStreamSynchronize(m->stream));
-        m->last_state = *m->h_state;
+        absorb_state(m);
     }
     const DevState &s = m->last_state;
     int64_t v[16] = {s.n_live, s.n_left_map, s.n_voxel_full, s.n_pyramid_full, s.n_moved, s.n_fov, s.n_cand, s.n_born,
-                     s.n_low_weight, s.n_pre, s.n_old, s.n_out, s.n_valid, s.n_inexact, m->launches_frame, m->launches_total};
+                     s.n_low_weight, s.n_pre, s.n_old, s.n_out, s.n_valid, (int64_t)(s.overflow | m->overflow_latched), m->launches_frame, m->launches_total};
     memcpy(out, v, sizeof(v));
     return DSPMAP_OK;
 }
@@ -1488,8 +1435,8 @@ int dspmap_synchronize(dspmap *m) {
     if (!m) return DSPMAP_E_BAD_ARG;
     CK(cudaStreamSynchronize(m->stream));
     if (m->profile) prof_collect(m);
-    if (m->update_counter > 0) m->last_state = *m->h_state;  // every frame ends with an async copy of the device state
-    return DSPMAP_OK;
+    if (m->update_counter > 0 && m->state_event_recorded) absorb_state(m);  // every frame ends with an async copy of the device state
+    return report_overflow(m);
 }
 int dspmap_profile_enable(dspmap *m, int on) {
     if (!m) return DSPMAP_E_BAD_ARG;

@@ -72,7 +72,6 @@ struct DevPtrs {
     // pair buffer: G[rowbase[i] + z * totlen[i] + j] = g(particle j of pyramid i's concatenated neighbour lists; point z of i)
     float *G;
     int *cum, *totlen, *pairs, *rowbase, *chunks, *chunk_off;
-    int *cz_order;      // work order of k_cz_chain_tma (heaviest pyramid first); null unless DSPMAP_CZ_TMA
     // newborn
     const float *tagged;  // n_tagged x 7, world frame
     float4 *NPC;          // corrected point + voxel id
@@ -188,29 +187,6 @@ __device__ __forceinline__ float dsp_pdf_f(const float *lut, float x, float mu, 
     else if (cx < -9.9f) cx = -9.9f;
     int i = (int)(cx * 1000 + 10000) - 10000;
     return lut[i < 0 ? -i : i];
-}
-// (P_d * g) / C_z, rounded exactly as the IEEE division the reference performs (dsp_dynamic.h:776), without the division's
-// slow path.  nvcc's a / b is 7 instructions plus FCHK; FCHK sends zero and subnormal dividends (and quotients that may be
-// subnormal) to a ~30-80 instruction subroutine, and the warp pays for it as soon as ONE lane needs it.  g is a product of
-// three table values down to 3e-22 each: for a particle a metre or more from the point in two axes it is subnormal, in three
-// axes zero.  Measured on the reference's state at cfg2 (18 M pairs): 0.3 % zero, 3.2 % subnormal, 3.9 % below 2^-100 — rare
-// per pair, but two warps in three hold at least one such lane.  With FAST:
-//   a == 0           ->  +0 (b is a positive finite C_z), no division at all;
-//   a < 2^-96        ->  (the fast path's residual a - q*b would lose bits below ~2^-102, which is what FCHK guards)
-//                        the division is done in double and rounded to float once more.  For the quotient of two floats
-//                        this double rounding is innocuous (53 >= 2 * 24 + 2 bits: a quotient that is not itself a
-//                        midpoint of the float grid — normal or subnormal — lies further than 2^-49 relative from one),
-//                        and float subnormals are normal doubles, so the double division stays on its own fast path;
-//   otherwise        ->  a / b, whose FCHK now never fires (C_z is within 2^+-20 of 1).
-// Experiment switch DSPMAP_QUOT_FAST=1 selects the kernel instantiations with FAST = true; results are bit-identical by
-// construction.
-template <bool FAST>
-__device__ __forceinline__ float dsp_quot(float a, float b) {
-    if (FAST) {
-        if (a == 0.f) return 0.f;
-        if (a < 1.262177448e-29f) return (float)((double)a / (double)b);  // 2^-96
-    }
-    return a / b;
 }
 // the counter-based uniform stream standing where rand() is (dsp_dynamic.h:1552)
 __host__ __device__ __forceinline__ uint32_t dsp_u31(u64 seed, u64 k) {

@@ -60,5 +60,4 @@ struct DevState {
     float norm;      // sum of 1/C_z               (dsp_dynamic.h:799-805)
     float w_new;     // newborn particle weight    (dsp_dynamic.h:805)
     long long p_cur, v_cur, u_cur;  // noise-table cursors and uniform-stream counter (dsp_dynamic.h:483-484)
-    int tickets[4];  // "last block done" counters of the fused scans (DSPMAP_FUSE_SCAN); each user leaves its counter at 0
 };

@@ -20,7 +20,7 @@ OK, REJECTED = 1, 0
 MAX_T = 8
 
 COUNTER_NAMES = ["n_in", "n_left_map", "n_voxel_full", "n_pyramid_full", "n_moved", "n_fov", "n_candidates", "n_born",
-                 "n_low_weight", "n_pre", "n_old", "n_out", "n_valid_points", "n_inexact", "launches_frame",
+                 "n_low_weight", "n_pre", "n_old", "n_out", "n_valid_points", "overflow", "launches_frame",
                  "launches_total"]
 
 

@@ -7,6 +7,7 @@
 // application relies on them (map_sim_example.cpp:39-57, 342, 443).
 #pragma once
 #include <cmath>
+#include <cstdlib>
 #include <ctime>
 #include <fstream>
 #include <iostream>
@@ -52,12 +53,12 @@ public:
         c.init_particle_num = init_particle_num;
         c.init_weight = init_weight;
         if (dspmap_create(&c, &map_) != DSPMAP_OK) {
-            cout << "DSPMap: " << dspmap_last_error() << endl;
-            map_ = nullptr;
-        } else {
-            instances().push_back(map_);
-            dspmap_set_voxel_filter_resolution(map_, filter_resolution());
+            // the reference's constructor cannot fail; there is no CPU path to fall back to, so say why and stop
+            cerr << "DSPMap: " << dspmap_last_error() << endl;
+            std::abort();
         }
+        instances().push_back(map_);
+        dspmap_set_voxel_filter_resolution(map_, filter_resolution());
     }
     ~DSPMap() {  // :177
         for (size_t i = 0; i < instances().size(); ++i)

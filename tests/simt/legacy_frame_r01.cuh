@@ -1,8 +1,11 @@
+// TEST INFRASTRUCTURE: the round-1 kernels exactly as they were verified on a B200 against the reference (GPUTEST_r01).
+// tests/simt compiles kernels out of this frozen copy for the host and requires the current kernels to reproduce their
+// outputs bit for bit.  Not part of the product; nothing in dsp-map_b200/ includes it.
 // dspmap_frame.cuh — the kernels of one map update, in pipeline order (product code, sm_100a).
 #pragma once
 #include <cuda_pipeline.h>
 #include <cuda/ptx>
-#include "dspmap_kernels.cuh"
+#include "legacy_kernels_r01.cuh"
 
 // ------------------------------------------------------------------------------------------------------------
 // (helper) the pair buffer is used when the frame's pairs fit it; otherwise the recompute kernels (k_ck / k_weight) take the frame
@@ -127,6 +130,58 @@ __global__ void __launch_bounds__(1024) k_scan_small(ScanJobs jobs) {
     if (threadIdx.x == 1023) { J.out[n] = run; if (J.out_capped) J.out_capped[n] = runc; }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Scans fused into the kernel that produces their input (experiment switch DSPMAP_FUSE_SCAN=1): the block that finishes
+// last (a ticket counter, the classic "last block done" pattern) performs the small exclusive scan that otherwise costs a
+// launch of its own on the frame's critical path.  scan_block works for any block size that is a multiple of 32.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool last_block_done(int *ticket) {
+    __shared__ bool s_last;
+    __threadfence();  // this block's results are visible device-wide before its ticket is
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s_last = atomicAdd(ticket, 1) == (int)gridDim.x - 1;
+        if (s_last) *ticket = 0;  // ready for the next launch
+    }
+    __syncthreads();
+    if (s_last) __threadfence();
+    return s_last;
+}
+__device__ __forceinline__ void scan_block(const int *in, int *out, int *out_capped, int cap, int n) {
+    __shared__ int wsum[32], wcap[32];
+    const int T = blockDim.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = T >> 5;
+    const int per = (n + T - 1) / T;
+    const int b0 = min(n, (int)threadIdx.x * per), b1 = min(n, b0 + per);
+    int s = 0, sc = 0;
+    for (int i = b0; i < b1; ++i) { const int x = __ldcg(in + i); s += x; sc += min(x, cap); }  // written by other blocks: read from L2
+    int incl = s, inclc = sc;
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(FULLMASK, incl, d), tc = __shfl_up_sync(FULLMASK, inclc, d);
+        if (lane >= d) { incl += t; inclc += tc; }
+    }
+    if (lane == 31) { wsum[wid] = incl; wcap[wid] = inclc; }
+    __syncthreads();
+    if (wid == 0) {
+        const int y0 = lane < nw ? wsum[lane] : 0, yc0 = lane < nw ? wcap[lane] : 0;
+        int y = y0, yc = yc0;
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(FULLMASK, y, d), tc = __shfl_up_sync(FULLMASK, yc, d);
+            if (lane >= d) { y += t; yc += tc; }
+        }
+        wsum[lane] = y - y0;  // exclusive prefix of the warp totals
+        wcap[lane] = yc - yc0;
+    }
+    __syncthreads();
+    int run = wsum[wid] + incl - s, runc = wcap[wid] + inclc - sc;
+    for (int i = b0; i < b1; ++i) {
+        const int x = __ldcg(in + i);
+        out[i] = run;
+        run += x;
+        if (out_capped) { out_capped[i] = runc; runc += min(x, cap); }
+    }
+    if ((int)threadIdx.x == T - 1) { out[n] = run; if (out_capped) out_capped[n] = runc; }
+    __syncthreads();  // the shared totals may be reused by a following scan
+}
 
 __global__ void k_obs_scatter(MapConst mc, FrameConst fc, DevPtrs dp) {
     pdl_enter();
@@ -174,12 +229,11 @@ __global__ void k_enumerate(MapConst mc, DevPtrs dp, int snapshot) {
         if (lane == 0) wbase = atomicAdd(&dp.st->n_live, total);
         wbase = __shfl_sync(FULLMASK, wbase, 0);
         int off = wbase + incl - c;
-        // past the capacity the particles are not enumerated (flagged); what fits is written, so E has no unwritten gaps
-        if (c && off + c > dp.cap_live) atomicOr(&dp.st->overflow, 1);
+        if (off + c > dp.cap_live) { if (c) atomicOr(&dp.st->overflow, 1); continue; }
         u64 z = m.x;
-        while (z) { int s = __ffsll((long long)z) - 1; z &= z - 1; if (off < dp.cap_live) dp.E[off] = (v << DSP_KEY_SHIFT) | s; ++off; }
+        while (z) { int s = __ffsll((long long)z) - 1; z &= z - 1; dp.E[off++] = (v << DSP_KEY_SHIFT) | s; }
         z = m.y;
-        while (z) { int s = __ffsll((long long)z) - 1; z &= z - 1; if (off < dp.cap_live) dp.E[off] = (v << DSP_KEY_SHIFT) | (64 + s); ++off; }
+        while (z) { int s = __ffsll((long long)z) - 1; z &= z - 1; dp.E[off++] = (v << DSP_KEY_SHIFT) | (64 + s); }
     }
 }
 
@@ -251,8 +305,8 @@ __global__ void k_vz_advance(MapConst mc, DevPtrs dp) {
 //      buffer, to be placed by k_arrive in the reference's sweep order.
 //      Velocity process noise (:653-659, :1262-1269) cannot fire here: with LIMIT_MOVEMENT_IN_XY_PLANE = 1 every
 //      particle has vz == 0 after its first prediction or at birth, so |vx*vy*vz| < 1e-6 always holds; the one
-//      reachable case (constructor-seeded particles in their first prediction) takes the ordered path below
-//      (fc.vz_mode: ranks from k_vz_count + scan).
+//      reachable case (constructor-seeded particles in their first frame) is applied by the host before the
+//      first update (see dspmap.cu: apply_seed_noise).
 // ------------------------------------------------------------------------------------------------------------
 __global__ void k_predict(MapConst mc, FrameConst fc, DevPtrs dp) {
     pdl_enter();
@@ -429,6 +483,12 @@ __global__ void k_arrive(MapConst mc, FrameConst fc, DevPtrs dp) {
     pdl_enter();
     arrive_body(mc, fc, dp);
 }
+// + the scan of the pyramid counts (the input of k_pyr_scatter) by the block that finishes last
+__global__ void k_arrive_fs(MapConst mc, FrameConst fc, DevPtrs dp) {
+    pdl_enter();
+    arrive_body(mc, fc, dp);
+    if (last_block_done(&dp.st->tickets[0])) scan_block(dp.pcount, dp.poff, nullptr, 0, mc.P);
+}
 
 // ------------------------------------------------------------------------------------------------------------
 // Sharded mode (multi-GPU, voxel subspaces = z slabs).  After the all-to-all, movers that crossed into this rank's slab
@@ -544,10 +604,74 @@ __global__ void k_pyr_scatter(DevPtrs dp) {
 }
 
 #define PYR_SORT_CAP 8192
-// Bitonic sort in shared memory, one thread per compare-exchange pair: the stages that exchange keys less than 32 apart (40 of
-// the 55 stages of a 1024-key network) stay inside one warp's 64-element block and need a warp barrier only.
-// (Measured on B200, cfg2: 27.3 -> 20.2 us against one thread per key with block-wide barriers; profiles/r02_ab_switches.jsonl.)
 __global__ void __launch_bounds__(512) k_pyr_sort(MapConst mc, DevPtrs dp, float Pd) {
+    pdl_enter();
+    extern __shared__ u64 skey[];  // PYR_SORT_CAP entries: (sweep key << 32) | slot address
+    for (int q = blockIdx.x; q < mc.P; q += gridDim.x) {
+        const int n = dp.pcount[q], b = dp.poff[q];
+        const int keep = min(n, mc.L);
+        if (threadIdx.x == 0) dp.plen[q] = keep;
+        if (n == 0) continue;
+        if (n <= PYR_SORT_CAP) {
+            int m = 1;
+            while (m < n) m <<= 1;
+            for (int i = threadIdx.x; i < m; i += blockDim.x)
+                skey[i] = i < n ? ((u64)(unsigned)dp.PSkey[b + i] << 32) | (unsigned)(mc.sharded ? i : dp.PSaddr[b + i]) : ~0ull;
+            __syncthreads();
+            for (int k = 2; k <= m; k <<= 1)
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+                        int p = i ^ j;
+                        if (p > i) {
+                            u64 x = skey[i], y = skey[p];
+                            bool up = (i & k) == 0;
+                            if ((x > y) == up) { skey[i] = y; skey[p] = x; }
+                        }
+                    }
+                    __syncthreads();
+                }
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                int a = (int)(unsigned)(skey[i] & 0xffffffffull);
+                float4 pa;
+                if (mc.sharded) {  // the low word is the position inside the segment: address and payload come from there
+                    pa = dp.PSpay[b + a];
+                    a = dp.PSaddr[b + a];
+                } else {
+                    pa = dp.PA[a];
+                }
+                if (i < keep) {
+                    dp.LA[b + i] = a;
+                    dp.LP[b + i] = pa;
+                    dp.PW[b + i] = Pd * pa.w;
+                } else if (a >= 0) {  // pyramid full: the particle vanishes and frees its voxel slot (:1256-1259)
+                    mask_atomic_clear(dp.M, a / mc.S, a % mc.S);
+                    atomicAdd(&dp.st->n_pyramid_full, 1);
+                }
+            }
+            __syncthreads();
+        } else {  // oversized segment: rank by counting straight from global memory (slow, rare)
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                int ki = dp.PSkey[b + i], r = 0;
+                for (int j = 0; j < n; ++j) r += dp.PSkey[b + j] < ki;
+                int a = dp.PSaddr[b + i];
+                if (r < keep) {
+                    const float4 pa = mc.sharded ? dp.PSpay[b + i] : dp.PA[a];
+                    dp.LA[b + r] = a;
+                    dp.LP[b + r] = pa;
+                    dp.PW[b + r] = Pd * pa.w;
+                } else if (a >= 0) {
+                    mask_atomic_clear(dp.M, a / mc.S, a % mc.S);
+                    atomicAdd(&dp.st->n_pyramid_full, 1);
+                }
+            }
+        }
+    }
+}
+// k_pyr_sort with warp-local sorting stages (experiment switch DSPMAP_SORT_WARP=1): of the 55 stages of a 1024-key bitonic
+// network 40 exchange keys less than 32 apart; with one thread per pair those stay inside one warp's 64-element block and
+// are separated by __syncwarp instead of the block-wide barrier the profile shows as the kernel's first stall (27 %).
+// Same keys, unique, fully sorted: the outputs are those of k_pyr_sort.
+__global__ void __launch_bounds__(512) k_pyr_sort_w(MapConst mc, DevPtrs dp, float Pd) {
     pdl_enter();
     extern __shared__ u64 skey[];  // PYR_SORT_CAP entries: (sweep key << 32) | slot address
     for (int q = blockIdx.x; q < mc.P; q += gridDim.x) {
@@ -746,7 +870,9 @@ __global__ void __launch_bounds__(K5_THREADS) k_weight(MapConst mc, FrameConst f
 //           particle in the concatenation of i's neighbour lists (neighbour-table order, list order)
 //   k_cz_chain reads a row sequentially (j); k_weight2 reads it with consecutive lanes = consecutive particles.
 // ------------------------------------------------------------------------------------------------------------
-__global__ void k_pair_prep(MapConst mc, DevPtrs dp) {
+// col != 0 (DSPMAP_G_COL): pyramid i's block of G is column-major — np + 1 columns (its points, then P_d * w) of
+// tl = round-up-to-4(rows) floats each, so every column and every 8-row tile of it starts on a 16-byte boundary.
+__global__ void k_pair_prep(MapConst mc, DevPtrs dp, int col) {
     pdl_enter();
     unsigned long long local = 0ull;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < mc.P; i += gridDim.x * blockDim.x) {
@@ -758,11 +884,36 @@ __global__ void k_pair_prep(MapConst mc, DevPtrs dp) {
         }
         dp.totlen[i] = c;
         unsigned long long pr = (unsigned long long)np * (unsigned long long)c;
+        if (col) pr = np > 0 ? (unsigned long long)(np + 1) * (unsigned long long)((c + 3) & ~3) : 0ull;
         dp.pairs[i] = pr > 0x3fffffffull ? 0x3fffffff : (int)pr;
         local += pr;
         dp.chunks[i] = (dp.plen[i] + 31) >> 5;
     }
     if (local) atomicAdd(&dp.st->total_pairs, local);
+}
+// k_pair_prep and its two scans (pair counts -> row bases, chunk counts -> chunk offsets) as ONE block of 1024 threads
+__global__ void __launch_bounds__(1024) k_pair_prep_scan(MapConst mc, DevPtrs dp, int col) {
+    pdl_enter();
+    unsigned long long local = 0ull;
+    for (int i = threadIdx.x; i < mc.P; i += blockDim.x) {
+        const int np = min(dp.obs_cnt[i], mc.OBS - 1), nn = dp.nbr[i * mc.NBW];
+        int c = 0;
+        for (int ns = 0; ns < nn; ++ns) {
+            dp.cum[i * mc.NBW + ns] = c;
+            c += dp.plen[dp.nbr[i * mc.NBW + 1 + ns]];
+        }
+        dp.totlen[i] = c;
+        unsigned long long pr = (unsigned long long)np * (unsigned long long)c;
+        if (col) pr = np > 0 ? (unsigned long long)(np + 1) * (unsigned long long)((c + 3) & ~3) : 0ull;
+        dp.pairs[i] = pr > 0x3fffffffull ? 0x3fffffff : (int)pr;
+        local += pr;
+        dp.chunks[i] = (dp.plen[i] + 31) >> 5;
+    }
+    if (local) atomicAdd(&dp.st->total_pairs, local);
+    __threadfence();  // scan_block reads the counts through L2
+    __syncthreads();
+    scan_block(dp.pairs, dp.rowbase, nullptr, 0, mc.P);
+    scan_block(dp.chunks, dp.chunk_off, nullptr, 0, mc.P);
 }
 // position of pyramid a inside pyramid b's neighbour list (the relation is symmetric)
 __device__ __forceinline__ int nb_index_of(const MapConst &mc, const DevPtrs &dp, int b, int a) {
@@ -779,6 +930,29 @@ __device__ __forceinline__ int chunk_to_pyramid(const int *chunk_off, int P, int
     }
     return lo;
 }
+// Work order of the C_z pass for k_cz_chain_tma: pyramids by descending pair count (ties by index).  The C_z kernel's run
+// time is the longest serial chain it contains, so the heaviest pyramids have to start first.  Built by ONE CTA of
+// k_pair_eval (rank by counting over keys staged in shared memory); beyond CZ_ORDER_MAX pyramids the lists are short and
+// the identity order is kept.
+#define CZ_ORDER_MAX 2048
+__device__ __forceinline__ void cz_build_order(const MapConst &mc, const DevPtrs &dp, int *keys) {
+    if (mc.P > CZ_ORDER_MAX) {
+        for (int i = threadIdx.x; i < mc.P; i += blockDim.x) dp.cz_order[i] = i;
+        return;
+    }
+    for (int i = threadIdx.x; i < mc.P; i += blockDim.x) keys[i] = dp.pairs[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < mc.P; i += blockDim.x) {
+        const int ki = keys[i];
+        int r = 0;
+        for (int j = 0; j < mc.P; ++j) {
+            const int kj = keys[j];
+            r += (kj > ki) || (kj == ki && j < i);
+        }
+        dp.cz_order[r] = i;
+    }
+    __syncthreads();  // the staging area is the evaluation tiles' from here on
+}
 #define EVAL_THREADS 512
 #define TILE_LD 33  // per-warp 32 x 32 staging tile, padded
 // mode 0: all items; sharded: mode 1 = rows of the point pyramids this rank computes C_z for (i % nranks == rank),
@@ -791,6 +965,7 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_pair_eval(MapConst mc, FrameCo
     for (int i = threadIdx.x; i < DSP_LUT_HALF; i += blockDim.x) lut[i] = dp.lut[i];  // constant after create: staged before the wait
     pdl_wait();
     if (!use_pair_buffer(mc, dp)) return;
+    if (dp.cz_order && blockIdx.x == 0) cz_build_order(mc, dp, reinterpret_cast<int *>(sm + (DSP_LUT_HALF + 3)));  // before this CTA joins the queue
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int nchunks = dp.chunk_off[mc.P];
@@ -834,13 +1009,18 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_pair_eval(MapConst mc, FrameCo
 // memory (double-buffered cp.async); thread z < np adds its column in list order: one fp32 chain per point.
 // Measured on B200 (cfg2): 256 threads with 2 x 32 KB tiles (3 CTAs / SM) 54 us, 128 threads with 2 x 16 KB tiles
 // (6 CTAs / SM, every pyramid resident at once) 64 us — the longer tiles amortise the per-tile barrier better.
-template <int CZ_THREADS, int CZ_TILE, int CZ_JT>
+// STG (experiment switch DSPMAP_CZ_STAGED=1): the pyramid's neighbour table (list lengths and offsets) is read into shared
+// memory once per pyramid.  In the default instantiation every tile re-walks nbr -> plen and nbr -> poff in global memory:
+// four dependent L2 round trips (~1 000 cycles) in front of a tile whose chain takes ~700 (profiles/r01_top_kernels.md).
+#define CZ_STG_MAXNB 128
+template <int CZ_THREADS, int CZ_TILE, int CZ_JT, bool STG = false>
 __global__ void __launch_bounds__(CZ_THREADS) k_cz_chain(MapConst mc, FrameConst fc, DevPtrs dp) {
     pdl_enter();
     extern __shared__ float czsm[];
     float *tile0 = czsm, *tile1 = czsm + CZ_TILE + 8;  // + room for the alignment phase
     float *pws0 = czsm + 2 * (CZ_TILE + 8), *pws1 = pws0 + CZ_JT;
     __shared__ int s_item;
+    __shared__ int s_len[STG ? CZ_STG_MAXNB : 1], s_off[STG ? CZ_STG_MAXNB : 1];
     if (!use_pair_buffer(mc, dp)) return;
     const float enb = fc.nb_weight * (float)dp.st->n_valid * (float)fc.nb_num;  // :292
     const float add_k = enb + fc.kappa;
@@ -857,8 +1037,17 @@ __global__ void __launch_bounds__(CZ_THREADS) k_cz_chain(MapConst mc, FrameConst
         const int nn = dp.nbr[i * mc.NBW];
         const int JT = min(CZ_JT, CZ_TILE / np);
         const float *gsrc = dp.G + (size_t)dp.rowbase[i];
-        auto len_of = [&](int k) { return dp.plen[dp.nbr[i * mc.NBW + 1 + k]]; };
-        auto off_of = [&](int k) { return dp.poff[dp.nbr[i * mc.NBW + 1 + k]]; };
+        const bool staged = STG && nn <= CZ_STG_MAXNB;
+        if (STG) {  // (the barrier at the top of the loop keeps the previous pyramid's readers ahead of these writes)
+            if (staged && tid < nn) {
+                const int b = dp.nbr[i * mc.NBW + 1 + tid];
+                s_len[tid] = dp.plen[b];
+                s_off[tid] = dp.poff[b];
+            }
+            __syncthreads();
+        }
+        auto len_of = [&](int k) { return staged ? s_len[k] : dp.plen[dp.nbr[i * mc.NBW + 1 + k]]; };
+        auto off_of = [&](int k) { return staged ? s_off[k] : dp.poff[dp.nbr[i * mc.NBW + 1 + k]]; };
         // tile iterator over (neighbour ns, particle offset k0); the "issue" state runs one tile ahead of the consumer
         int ins = 0, ik0 = 0, iln = nn > 0 ? len_of(0) : 0;
         int ph0 = 0, ph1 = 0;
@@ -917,6 +1106,364 @@ __global__ void __launch_bounds__(CZ_THREADS) k_cz_chain(MapConst mc, FrameConst
         }
     }
 }
+// ------------------------------------------------------------------------------------------------------------
+// Column-major pair buffer (experiment switch DSPMAP_G_COL=1).  Pyramid i's block of G holds np + 1 columns of
+// tl = round-up-to-4(rows) floats: column z < np = g(particle j; point z) down the concatenation j of i's neighbour
+// lists, column np = P_d * w_j.  What it buys:
+//   * k_pair_eval_col: lanes are particles, so the 32 values of one point are one coalesced store — no transposing
+//     tile in shared memory (the row-major kernel spends a third of its shared-memory traffic on it);
+//   * k_cz_chain_col: every column is contiguous and 16-byte aligned, so the chain thread of point z streams ITS column
+//     through shared memory with cp.async.bulk and reads it four rows per LDS.128 — 10 instructions per 4 rows instead of
+//     ~22, which leaves the 4-cycle dependent FADD as the only limit of the longest chain (4 559 rows at cfg2);
+//   * k_weight_col: lane = particle reads its value for point z as part of one coalesced 128-byte load, divides and adds:
+//     the weight pass needs no shared memory, no barrier and no per-element index arithmetic any more.
+// Sums are formed from the same terms in the same order: results are bit-identical.
+// ------------------------------------------------------------------------------------------------------------
+#define EVALC_KEYS 2048  // shared-memory room for cz_build_order (== CZ_ORDER_MAX)
+// Two points per step with Blackwell's packed fp32 arithmetic (experiment switch DSPMAP_EVAL_PACKED=1 on top of G_COL):
+// the subtraction, the three operations of the verified fast division, the scaling to a table index and the products are
+// issued as FADD2 / FMUL2 / FFMA2 on (point z, point z + 1) pairs — each half is the scalar IEEE operation, so the values
+// are the scalar kernel's; clamps, conversions and look-ups stay scalar.  Only with the verified division (fc.fast_sigma).
+__device__ __forceinline__ float2 dsp_pdf2_f(const float *lut, float x, float mu0, float mu1, const FrameConst &fc) {
+    const float2 a = __fadd2_rn(make_float2(x, x), make_float2(-mu0, -mu1));                  // x - mu
+    const float2 r = make_float2(fc.sigma_r, fc.sigma_r), b = make_float2(fc.sigma, fc.sigma);
+    const float2 q0 = __fmul2_rn(a, r);                                                       // dsp_div_known
+    const float2 e = __ffma2_rn(make_float2(-q0.x, -q0.y), b, a);
+    float2 c = __ffma2_rn(e, r, q0);
+    c.x = c.x > 9.9f ? 9.9f : (c.x < -9.9f ? -9.9f : c.x);
+    c.y = c.y > 9.9f ? 9.9f : (c.y < -9.9f ? -9.9f : c.y);
+    const float2 t = __fadd2_rn(__fmul2_rn(c, make_float2(1000.f, 1000.f)), make_float2(10000.f, 10000.f));
+    const int i0 = (int)t.x - 10000, i1 = (int)t.y - 10000;
+    return make_float2(lut[i0 < 0 ? -i0 : i0], lut[i1 < 0 ? -i1 : i1]);
+}
+template <bool PK>
+__global__ void __launch_bounds__(EVAL_THREADS) k_pair_eval_col(MapConst mc, FrameConst fc, DevPtrs dp, int mode) {
+    extern __shared__ float sm[];
+    float *lut = sm;
+    pdl_trigger();
+    for (int i = threadIdx.x; i < DSP_LUT_HALF; i += blockDim.x) lut[i] = dp.lut[i];  // constant after create: staged before the wait
+    pdl_wait();
+    if (!use_pair_buffer(mc, dp)) return;
+    if (dp.cz_order && blockIdx.x == 0) cz_build_order(mc, dp, reinterpret_cast<int *>(sm + (DSP_LUT_HALF + 3)));
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int nchunks = dp.chunk_off[mc.P];
+    const int items = nchunks * mc.NB;
+    for (;;) {
+        int it = 0;
+        if (lane == 0) it = atomicAdd(mode == 2 ? &dp.st->work_eval2 : &dp.st->work_eval, 1);
+        it = __shfl_sync(FULLMASK, it, 0);
+        if (it >= items) break;
+        const int c = it / mc.NB, ns = it - c * mc.NB;
+        if (mode == 2 && c % mc.nranks != mc.rank) continue;
+        const int a = chunk_to_pyramid(dp.chunk_off, mc.P, c);
+        if (ns >= dp.nbr[a * mc.NBW]) continue;
+        const int i = dp.nbr[a * mc.NBW + 1 + ns];  // a point pyramid that sees pyramid a
+        if (mode == 1 && i % mc.nranks != mc.rank) continue;
+        const int np = min(dp.obs_cnt[i], mc.OBS - 1);
+        if (np == 0) continue;
+        const int k0 = (c - dp.chunk_off[a]) << 5;
+        const int nrows = min(32, dp.plen[a] - k0);
+        const bool mine = lane < nrows;
+        const float4 p = mine ? dp.LP[dp.poff[a] + k0 + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const size_t tl = (size_t)((dp.totlen[i] + 3) & ~3);
+        float *gb = dp.G + (size_t)dp.rowbase[i] + (size_t)(dp.cum[i * mc.NBW + nb_index_of(mc, dp, i, a)] + k0) + lane;
+        if (mine) gb[(size_t)np * tl] = dp.PW[dp.poff[a] + k0 + lane];  // the weight column (P_d * w, as k_pyr_sort rounded it)
+        const float4 *zs = dp.OBSP + (size_t)i * mc.OBS;
+        // the next point is requested before the current one is evaluated (in the row-major kernel 14 % of the samples wait
+        // for this load: profiles/r01_top_kernels.md)
+        int z = 0;
+        if (PK && fc.fast_sigma) {  // two points per step; an odd last point goes through the scalar loop below
+            for (; z + 2 <= np; z += 2) {
+                const float4 o0 = zs[z], o1 = zs[z + 1];
+                const float2 g = __fmul2_rn(__fmul2_rn(dsp_pdf2_f(lut, p.x, o0.x, o1.x, fc), dsp_pdf2_f(lut, p.y, o0.y, o1.y, fc)),
+                                            dsp_pdf2_f(lut, p.z, o0.z, o1.z, fc));
+                if (mine) {
+                    gb[(size_t)z * tl] = g.x;
+                    gb[(size_t)(z + 1) * tl] = g.y;
+                }
+            }
+        }
+        if (z < np) {
+            float4 o = zs[z];
+#pragma unroll 2
+            for (; z < np; ++z) {
+                const float4 on = zs[min(z + 1, np - 1)];
+                const float g = dsp_pdf_f(lut, p.x, o.x, fc) * dsp_pdf_f(lut, p.y, o.y, fc) * dsp_pdf_f(lut, p.z, o.z, fc);
+                if (mine) gb[(size_t)z * tl] = g;
+                o = on;
+            }
+        }
+    }
+}
+#define CZC_STAGES 6
+#define CZC_TILE 4096   // floats per stage: (np + 1) columns of RT + 4
+#define CZC_RT_MAX 512
+#define CZC_CHAIN_WARPS 4
+#define CZC_THREADS (32 * (CZC_CHAIN_WARPS + 1))
+#define CZC_SMEM_BYTES (CZC_STAGES * CZC_TILE * 4 + 2 * CZC_STAGES * 8)
+__global__ void __launch_bounds__(CZC_THREADS) k_cz_chain_col(MapConst mc, FrameConst fc, DevPtrs dp) {
+    pdl_enter();
+    extern __shared__ __align__(128) float czcsm[];
+    float *stages = czcsm;
+    uint64_t *full = reinterpret_cast<uint64_t *>(stages + CZC_STAGES * CZC_TILE);
+    uint64_t *empty = full + CZC_STAGES;
+    __shared__ int s_item;
+    if (!use_pair_buffer(mc, dp)) return;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) {
+        for (int s = 0; s < CZC_STAGES; ++s) {
+            cuda::ptx::mbarrier_init(&full[s], 1);                  // the producer's arrive.expect_tx; completes with the bytes
+            cuda::ptx::mbarrier_init(&empty[s], CZC_CHAIN_WARPS);   // one arrival per chain warp
+        }
+        cuda::ptx::fence_mbarrier_init(cuda::ptx::sem_release, cuda::ptx::scope_cluster);
+        cuda::ptx::fence_proxy_async(cuda::ptx::space_shared);
+    }
+    __syncthreads();
+    const float enb = fc.nb_weight * (float)dp.st->n_valid * (float)fc.nb_num;  // :292
+    const float add_k = enb + fc.kappa;
+    unsigned it = 0;  // stages this CTA has been through: the producer warp and the chain warps walk the same sequence
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_item = atomicAdd(&dp.st->work_k4, 1);
+        __syncthreads();
+        const int wi = s_item;
+        if (wi >= mc.P) break;
+        const int i = dp.cz_order ? dp.cz_order[wi] : wi;
+        const int np = min(dp.obs_cnt[i], mc.OBS - 1);
+        if (np == 0) continue;
+        if (mc.sharded && i % mc.nranks != mc.rank) continue;  // another rank computes this pyramid's C_z
+        const int rows = dp.totlen[i];
+        const size_t tl = (size_t)((rows + 3) & ~3);
+        const int ncol = np + 1;
+        // rows per stage: a multiple of 8 with (RT + 4) / 4 odd, so that the LDS.128 of eight neighbouring columns fall into
+        // eight different 16-byte bank groups
+        const int RT = min(CZC_RT_MAX, (CZC_TILE / ncol - 4) & ~7);
+        const int stride = RT + 4;
+        const float *gsrc = dp.G + (size_t)dp.rowbase[i];
+        float acc = 0.f;
+        for (int j0 = 0; j0 < rows; j0 += RT, ++it) {
+            const int cur = min(RT, rows - j0), cur4 = (cur + 3) & ~3;
+            const int s = (int)(it % CZC_STAGES);
+            const unsigned par = (it / CZC_STAGES) & 1u;
+            float *st = stages + s * CZC_TILE;
+            if (wid == CZC_CHAIN_WARPS) {  // producer warp: lane c feeds columns c, c + 32, ...
+                if (lane == 0) {
+                    while (!cuda::ptx::mbarrier_try_wait_parity(&empty[s], par ^ 1u)) {}  // a fresh barrier passes at once
+                    cuda::ptx::mbarrier_arrive_expect_tx(cuda::ptx::sem_release, cuda::ptx::scope_cta, cuda::ptx::space_shared, &full[s],
+                                                         (unsigned)(ncol * cur4 * 4));
+                }
+                __syncwarp();
+                for (int c = lane; c < ncol; c += 32)
+                    cuda::ptx::cp_async_bulk(cuda::ptx::space_cluster, cuda::ptx::space_global, st + c * stride, gsrc + (size_t)c * tl + j0,
+                                             (unsigned)(cur4 * 4), &full[s]);
+                __syncwarp();
+            } else {
+                while (!cuda::ptx::mbarrier_try_wait_parity(&full[s], par)) {}
+                if (tid < np) {  // the chain: (P_d * w) * g added in list order, one fp32 add per term
+                    const float4 *g4 = reinterpret_cast<const float4 *>(st + tid * stride);
+                    const float4 *w4 = reinterpret_cast<const float4 *>(st + np * stride);
+                    const int nq = cur >> 2;
+#pragma unroll 4
+                    for (int q = 0; q < nq; ++q) {
+                        float4 g = g4[q];
+                        const float4 w = w4[q];
+                        g.x *= w.x; g.y *= w.y; g.z *= w.z; g.w *= w.w;
+                        acc += g.x; acc += g.y; acc += g.z; acc += g.w;
+                    }
+                    for (int jj = nq << 2; jj < cur; ++jj) acc += st[np * stride + jj] * st[tid * stride + jj];
+                }
+                __syncwarp();
+                if (lane == 0) cuda::ptx::mbarrier_arrive(&empty[s]);
+            }
+        }
+        if (tid < np) {
+            acc += add_k;
+            dp.CZ[i * mc.OBS + tid] = acc;
+            dp.INV[dp.obs_capoff[i] + tid] = 1.f / acc;  // for the newborn normaliser (:802)
+        }
+    }
+}
+// weights (dsp_dynamic.h:743-790) on the column-major buffer: one WARP per 32 particles of a pyramid, lane = particle.  For
+// every point z of every neighbour pyramid (table order, bin order — the reference's chain order) the chunk's 32 values are
+// 32 consecutive floats, i.e. one coalesced load; the lane divides its own value and adds it.  No shared memory, no barrier,
+// no transposition: the loads do not depend on the running sum, so sixteen of them are in flight per warp.
+template <bool QF>
+__global__ void __launch_bounds__(256) k_weight_col(MapConst mc, FrameConst fc, DevPtrs dp) {
+    pdl_enter();
+    if (!use_pair_buffer(mc, dp)) return;
+    const int lane = threadIdx.x & 31;
+    const int nchunks = dp.chunk_off[mc.P];
+    for (;;) {
+        int c = 0;
+        if (lane == 0) c = atomicAdd(&dp.st->work_w2, 1);
+        c = __shfl_sync(FULLMASK, c, 0);
+        if (c >= nchunks) break;
+        if (mc.sharded && c % mc.nranks != mc.rank) continue;  // chunks are dealt round-robin over the ranks
+        const int a = chunk_to_pyramid(dp.chunk_off, mc.P, c);
+        const int k0 = (c - dp.chunk_off[a]) << 5;
+        const int lb = dp.poff[a];
+        const int nrows = min(32, dp.plen[a] - k0);
+        const bool mine = lane < nrows;
+        bool act = false;
+        float pw = 0.f;
+        if (mine) {
+            const float4 p = dp.LP[lb + k0 + lane];
+            pw = p.w;
+            const float dist = sqrtf(p.x * p.x + p.y * p.y + p.z * p.z);
+            const float maxlen = __int_as_float(dp.obs_maxbits[a]);
+            act = !(maxlen > 0.f && dist > maxlen + mc.occl);  // occluded particles keep their weight (:761)
+        }
+        float sum = 0.f;
+        const int nn = dp.nbr[a * mc.NBW];
+        for (int ns = 0; ns < nn; ++ns) {
+            const int b = dp.nbr[a * mc.NBW + 1 + ns];
+            const int np = min(dp.obs_cnt[b], mc.OBS - 1);
+            if (np == 0) continue;
+            const size_t tl = (size_t)((dp.totlen[b] + 3) & ~3);
+            const float *g = dp.G + (size_t)dp.rowbase[b] + (size_t)(dp.cum[b * mc.NBW + nb_index_of(mc, dp, b, a)] + k0) + lane;
+            const float *cz = dp.CZ + (size_t)b * mc.OBS;
+            // C_z of the pyramid's points: lane l keeps points l, l + 32, l + 64, l + 96; broadcast by shuffle when needed
+            float czr[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) czr[q] = q * 32 + lane < np ? cz[q * 32 + lane] : 1.f;
+            // sixteen loads are issued before the first of them is used (the division's slow-path branch keeps the compiler
+            // from hoisting loads across iterations on its own); every lane runs the loop, so the shuffles stay convergent
+            for (int z0 = 0; z0 < np; z0 += 16) {
+                float gv[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) gv[u] = (mine && z0 + u < np) ? __ldg(g + (size_t)(z0 + u) * tl) : 0.f;
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    const int z = z0 + u;
+                    if (z < np) {  // uniform
+                        const float src = z < 32 ? czr[0] : (z < 64 ? czr[1] : (z < 96 ? czr[2] : czr[3]));
+                        sum += dsp_quot<QF>(fc.Pd * gv[u], __shfl_sync(FULLMASK, src, z & 31));
+                    }
+                }
+            }
+        }
+        if (mine) {
+            const float w_new = act ? pw * (fc.one_minus_Pd + sum) : pw;
+            if (mc.sharded) dp.NW[lb + k0 + lane] = w_new;  // merged over ranks, applied by the particle's owner
+            else if (act) dp.PA[dp.LA[lb + k0 + lane]].w = w_new;
+        }
+    }
+}
+// C_z with a bulk-copy ring (experiment switch DSPMAP_CZ_TMA=1).  The chain of one observation point is serial — rows x 4
+// cycles at best — so the kernel lasts as long as its heaviest pyramid, and the double-buffered version above spends half
+// of that waiting: one tile of lead (<= 128 rows, ~500 cycles of chain) is less than the L2 round trip of the next tile.
+// Here a producer thread streams the pyramid's contiguous block of G (and the matching P_d * w values) through a ring of
+// CZT_STAGES shared-memory stages with cp.async.bulk (TMA, 1-D) completing on per-stage mbarriers; the chain warps wait on
+// "full", add their column in list order, and release the stage on "empty".  ~96 KB in flight per CTA covers
+// np x 4 B per 4 cycles x the L2 latency for np = 99; no block-wide barrier inside a pyramid.
+// Work items come from dp.cz_order (heaviest first).  Results are bit-identical to k_cz_chain: same terms, same order.
+#define CZT_STAGES 6
+#define CZT_TILE 4096   // floats per stage
+#define CZT_JT 128      // particle rows per stage at most
+#define CZT_CHAIN_WARPS 4
+#define CZT_MAXNB 128    // neighbour tables staged in shared memory up to this many neighbours (== chain threads)
+#define CZT_THREADS (32 * (CZT_CHAIN_WARPS + 1))
+#define CZT_SMEM_BYTES (CZT_STAGES * (CZT_TILE + 4 + CZT_JT + 4) * 4 + 2 * CZT_STAGES * 8)
+__global__ void __launch_bounds__(CZT_THREADS) k_cz_chain_tma(MapConst mc, FrameConst fc, DevPtrs dp) {
+    pdl_enter();
+    extern __shared__ __align__(128) float cztsm[];
+    float *tiles = cztsm;                                       // CZT_STAGES x (CZT_TILE + 4): + room for the alignment phase
+    float *pws = tiles + CZT_STAGES * (CZT_TILE + 4);           // CZT_STAGES x (CZT_JT + 4)
+    uint64_t *full = reinterpret_cast<uint64_t *>(pws + CZT_STAGES * (CZT_JT + 4));
+    uint64_t *empty = full + CZT_STAGES;
+    __shared__ int s_item;
+    __shared__ int s_len[CZT_MAXNB], s_off[CZT_MAXNB];  // this pyramid's neighbour lists (length, offset into PW): read once, walked per tile
+    if (!use_pair_buffer(mc, dp)) return;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) {
+        for (int s = 0; s < CZT_STAGES; ++s) {
+            cuda::ptx::mbarrier_init(&full[s], 1);                  // the producer's arrive.expect_tx; completes with the bytes
+            cuda::ptx::mbarrier_init(&empty[s], CZT_CHAIN_WARPS);   // one arrival per chain warp
+        }
+        cuda::ptx::fence_mbarrier_init(cuda::ptx::sem_release, cuda::ptx::scope_cluster);
+        cuda::ptx::fence_proxy_async(cuda::ptx::space_shared);
+    }
+    __syncthreads();
+    const float enb = fc.nb_weight * (float)dp.st->n_valid * (float)fc.nb_num;  // :292
+    const float add_k = enb + fc.kappa;
+    unsigned it = 0;  // tiles this CTA has been through: the producer and the chain warps walk the same sequence
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_item = atomicAdd(&dp.st->work_k4, 1);
+        __syncthreads();
+        const int wi = s_item;
+        if (wi >= mc.P) break;
+        const int i = dp.cz_order ? dp.cz_order[wi] : wi;
+        const int np = min(dp.obs_cnt[i], mc.OBS - 1);
+        if (np == 0) continue;
+        if (mc.sharded && i % mc.nranks != mc.rank) continue;  // another rank computes this pyramid's C_z
+        const int nn = dp.nbr[i * mc.NBW];
+        const bool staged = nn <= CZT_MAXNB;  // larger neighbourhoods (PYRAMID_NEIGHBOR_N >= 6) read the tables per tile
+        if (staged && tid < nn) {
+            const int b = dp.nbr[i * mc.NBW + 1 + tid];
+            s_len[tid] = dp.plen[b];
+            s_off[tid] = dp.poff[b];
+        }
+        __syncthreads();  // (the barrier at the top of the loop keeps the previous pyramid's readers ahead of these writes)
+        auto len_of = [&](int k) { return staged ? s_len[k] : dp.plen[dp.nbr[i * mc.NBW + 1 + k]]; };
+        auto off_of = [&](int k) { return staged ? s_off[k] : dp.poff[dp.nbr[i * mc.NBW + 1 + k]]; };
+        const int JT = min(CZT_JT, CZT_TILE / np);
+        const float *g = dp.G + (size_t)dp.rowbase[i];
+        int ns = 0, k0 = 0, ln = nn > 0 ? len_of(0) : 0;
+        float acc = 0.f;
+        for (;;) {
+            while (ns < nn && k0 >= ln) {
+                ++ns;
+                k0 = 0;
+                ln = ns < nn ? len_of(ns) : 0;
+            }
+            if (ns >= nn) break;
+            const int cur = min(JT, ln - k0), nfl = cur * np;
+            const float *wsrc = dp.PW + off_of(ns) + k0;
+            // bulk copies move 16-byte units between 16-byte aligned addresses: start at the boundary below and keep the phase
+            const int phg = (int)((reinterpret_cast<size_t>(g) >> 2) & 3), phw = (int)((reinterpret_cast<size_t>(wsrc) >> 2) & 3);
+            const int s = (int)(it % CZT_STAGES);
+            const unsigned par = (it / CZT_STAGES) & 1u;
+            float *ts = tiles + s * (CZT_TILE + 4), *ws = pws + s * (CZT_JT + 4);
+            if (wid == CZT_CHAIN_WARPS) {  // producer warp: one thread feeds the ring
+                if (lane == 0) {
+                    while (!cuda::ptx::mbarrier_try_wait_parity(&empty[s], par ^ 1u)) {}  // a fresh barrier passes at once
+                    const unsigned bg = (unsigned)((phg + nfl + 3) >> 2) * 16u, bw = (unsigned)((phw + cur + 3) >> 2) * 16u;
+                    cuda::ptx::mbarrier_arrive_expect_tx(cuda::ptx::sem_release, cuda::ptx::scope_cta, cuda::ptx::space_shared, &full[s], bg + bw);
+                    cuda::ptx::cp_async_bulk(cuda::ptx::space_cluster, cuda::ptx::space_global, ts, g - phg, bg, &full[s]);
+                    cuda::ptx::cp_async_bulk(cuda::ptx::space_cluster, cuda::ptx::space_global, ws, wsrc - phw, bw, &full[s]);
+                }
+                __syncwarp();
+            } else {
+                while (!cuda::ptx::mbarrier_try_wait_parity(&full[s], par)) {}
+                if (tid < np) {  // the chain: (P_d * w) * g added in list order, one fp32 add per term
+                    const float *t = ts + phg + tid;
+                    const float *w = ws + phw;
+                    int jj = 0;
+                    for (; jj + 8 <= cur; jj += 8) {
+                        float g0 = t[jj * np], g1 = t[(jj + 1) * np], g2 = t[(jj + 2) * np], g3 = t[(jj + 3) * np];
+                        float g4 = t[(jj + 4) * np], g5 = t[(jj + 5) * np], g6 = t[(jj + 6) * np], g7 = t[(jj + 7) * np];
+                        g0 *= w[jj]; g1 *= w[jj + 1]; g2 *= w[jj + 2]; g3 *= w[jj + 3];
+                        g4 *= w[jj + 4]; g5 *= w[jj + 5]; g6 *= w[jj + 6]; g7 *= w[jj + 7];
+                        acc += g0; acc += g1; acc += g2; acc += g3; acc += g4; acc += g5; acc += g6; acc += g7;
+                    }
+                    for (; jj < cur; ++jj) acc += w[jj] * t[jj * np];
+                }
+                __syncwarp();
+                if (lane == 0) cuda::ptx::mbarrier_arrive(&empty[s]);
+            }
+            g += nfl;
+            k0 += cur;
+            ++it;
+        }
+        if (tid < np) {
+            acc += add_k;
+            dp.CZ[i * mc.OBS + tid] = acc;
+            dp.INV[dp.obs_capoff[i] + tid] = 1.f / acc;  // for the newborn normaliser (:802)
+        }
+    }
+}
 // weights (dsp_dynamic.h:743-790): a CTA per 32 particles of a pyramid.  For one neighbour pyramid at a time, ALL threads
 // turn the chunk's contiguous 32 x np tile of G into quotient terms (P_d * g) / C_z (flat, coalesced loads); then warp 0,
 // lane = particle, adds its row in bin order.  Neighbours are visited in table order, so each particle's sum is one fp32
@@ -924,7 +1471,8 @@ __global__ void __launch_bounds__(CZ_THREADS) k_cz_chain(MapConst mc, FrameConst
 #define W2_SWITCH 4096  // chunks of 32 particles: below, CTA-per-chunk (k_weight2); from here on, warp-per-chunk (k_weight2w)
 #define W2_THREADS 128
 #define W2_NP 100  // padded row length (np <= 99; odd stride: no bank conflicts in the chain)
-__global__ void __launch_bounds__(W2_THREADS) k_weight2(MapConst mc, FrameConst fc, DevPtrs dp) {
+template <bool QF>  // QF: quotients through dsp_quot's fast path (DSPMAP_QUOT_FAST=1)
+__global__ void __launch_bounds__(W2_THREADS) k_weight2_t(MapConst mc, FrameConst fc, DevPtrs dp) {
     pdl_enter();
     __shared__ float terms[2][32 * (W2_NP + 1)];
     __shared__ float czs[2][W2_NP];
@@ -1005,7 +1553,7 @@ __global__ void __launch_bounds__(W2_THREADS) k_weight2(MapConst mc, FrameConst 
                         if (f < nfl) {
                             const int r = np > 1 ? (int)__umulhi((unsigned)f, magic) : f;
                             const int z = f - r * np;
-                            terms[buf][r * ld + z] = (fc.Pd * gpre[u]) / czs[buf][z];
+                            terms[buf][r * ld + z] = dsp_quot<QF>(fc.Pd * gpre[u], czs[buf][z]);
                         }
                     }
                     // tiles of more than 768 terms (np > 24): further batches of eight loads in flight per thread
@@ -1022,7 +1570,7 @@ __global__ void __launch_bounds__(W2_THREADS) k_weight2(MapConst mc, FrameConst 
                             if (f < nfl) {
                                 const int r = np > 1 ? (int)__umulhi((unsigned)f, magic) : f;
                                 const int z = f - r * np;
-                                terms[buf][r * ld + z] = (fc.Pd * g[u]) / czs[buf][z];
+                                terms[buf][r * ld + z] = dsp_quot<QF>(fc.Pd * g[u], czs[buf][z]);
                             }
                         }
                     }
@@ -1051,7 +1599,8 @@ __global__ void __launch_bounds__(W2_THREADS) k_weight2(MapConst mc, FrameConst 
 // are read as coalesced rows (lane = point) into registers one sub-tile AHEAD of the one being consumed, staged through a
 // per-warp shared tile, and each lane adds its particle's row in (neighbour-table, bin) order.
 #define W2W_THREADS 256
-__global__ void __launch_bounds__(W2W_THREADS, 3) k_weight2w(MapConst mc, FrameConst fc, DevPtrs dp) {
+template <bool QF>
+__global__ void __launch_bounds__(W2W_THREADS, 3) k_weight2w_t(MapConst mc, FrameConst fc, DevPtrs dp) {
     pdl_enter();
     __shared__ float tiles[(W2W_THREADS / 32) * 32 * TILE_LD];
     __shared__ float czall[(W2W_THREADS / 32) * 32];
@@ -1119,7 +1668,7 @@ __global__ void __launch_bounds__(W2W_THREADS, 3) k_weight2w(MapConst mc, FrameC
             if (nsub) prefetch(nsub);  // in flight while the current sub-tile is consumed
             if (act) {
 #pragma unroll 4
-                for (int zl = 0; zl < cur; ++zl) sum += (fc.Pd * tile[lane * TILE_LD + zl]) / czs[zl];
+                for (int zl = 0; zl < cur; ++zl) sum += dsp_quot<QF>(fc.Pd * tile[lane * TILE_LD + zl], czs[zl]);
             }
             __syncwarp();
         }
@@ -1152,9 +1701,46 @@ __global__ void k_verify_div(float b, float r, unsigned max_bits, int mode, int 
     if (local) atomicAdd(bad, local);
 }
 
+// K6a  newborn normaliser (dsp_dynamic.h:799-805): sum of 1/C_z over (pyramid, bin) order, one fp32 chain.
+__global__ void k_norm(MapConst mc, FrameConst fc, DevPtrs dp) {
+    pdl_enter();
+    __shared__ __align__(16) float buf[2][1024];
+    const int n = dp.obs_capoff[mc.P];
+    float acc = 0.f;
+    int nchunk = (n + 1023) / 1024;
+    if (nchunk > 0)
+        for (int t = threadIdx.x; t < 1024; t += blockDim.x) buf[0][t] = t < n ? dp.INV[t] : 0.f;
+    __syncthreads();
+    for (int c = 0; c < nchunk; ++c) {
+        int nb = (c + 1) & 1, b0 = (c + 1) * 1024;
+        if (threadIdx.x >= 32) {  // warps 1.. prefetch the next chunk while warp 0 adds the current one
+            if (c + 1 < nchunk)
+                for (int t = threadIdx.x - 32; t < 1024; t += blockDim.x - 32) buf[nb][t] = b0 + t < n ? dp.INV[b0 + t] : 0.f;
+        } else if (threadIdx.x == 0) {
+            int cnt = min(1024, n - c * 1024);
+            const float4 *s4 = reinterpret_cast<const float4 *>(buf[c & 1]);
+            const int c4 = cnt >> 2;
+#pragma unroll 4
+            for (int k = 0; k < c4; ++k) {
+                float4 x = s4[k];
+                acc += x.x; acc += x.y; acc += x.z; acc += x.w;
+            }
+            for (int k = c4 << 2; k < cnt; ++k) acc += buf[c & 1][k];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        dp.st->norm = acc;
+        dp.st->w_new = fc.nb_weight * acc;
+    }
+}
 
+// The same chain with the shared-memory loads taken out of the FADD chain's way (experiment switch DSPMAP_NORM_FAST=1): the
+// adding thread keeps the NEXT sixteen values in registers while it adds the current sixteen (4 cycles each), so the 29-cycle
+// LDS latency is never exposed; 4096-value chunks quarter the number of block barriers.  One fp32 chain in (pyramid, bin)
+// order, as before: bit-identical.  Matters once the weight pass is shorter than this kernel.
 #define NORMF_CHUNK 4096
-__global__ void __launch_bounds__(256) k_norm(MapConst mc, FrameConst fc, DevPtrs dp) {
+__global__ void __launch_bounds__(256) k_norm_fast(MapConst mc, FrameConst fc, DevPtrs dp) {
     pdl_enter();
     __shared__ __align__(16) float buf[2][NORMF_CHUNK];
     const int n = dp.obs_capoff[mc.P];
@@ -1308,6 +1894,15 @@ __global__ void __launch_bounds__(256) k_nb_point1(MapConst mc, FrameConst fc, D
     pdl_enter();
     nb_point1_body(mc, fc, dp, phase);
 }
+// + the scans of the points' velocity-table / uniform draws (the cursors of k_nb_cand) by the block that finishes last
+__global__ void __launch_bounds__(256) k_nb_point1_fs(MapConst mc, FrameConst fc, DevPtrs dp, int phase) {
+    pdl_enter();
+    nb_point1_body(mc, fc, dp, phase);
+    if (last_block_done(&dp.st->tickets[1])) {
+        scan_block(dp.nvcnt, dp.nvoff, nullptr, 0, fc.n_tagged);
+        scan_block(dp.nrcnt, dp.nroff, nullptr, 0, fc.n_tagged);
+    }
+}
 // candidate pass: position (:871-873), velocity class (:877-907), weight (:909); candidates inside the map join
 // the arrival grouping of their voxel, ordered by (point, candidate) = the reference's serial order.
 __global__ void k_nb_cand(MapConst mc, FrameConst fc, DevPtrs dp, u64 useed) {
@@ -1357,13 +1952,82 @@ __global__ void k_nb_cand(MapConst mc, FrameConst fc, DevPtrs dp, u64 useed) {
         if (atomicAdd(&dp.ccnt[d], 1) == 0) dp.cowner[agg_inc(&dp.st->n_cand_owner)] = d;
     }
 }
+// addAParticle (:1183-1201) in serial order: the k-th candidate of a voxel (in (point, candidate) order) takes its k-th
+// free slot.  One warp per destination voxel: it extracts the next-smallest key as many times as the voxel has free
+// slots (lanes scan the voxel's segment, a shuffle reduction picks the minimum), then the winners are copied in parallel.
+// (Measured alternative on B200, cfg2: ranking all candidates of a voxel against each other through shuffles and placing
+// every winner in parallel is bit-identical but 2.8 % slower per frame — a voxel has ~3 free slots to fill, fewer rounds than
+// the all-pairs ranking has steps.)
+__global__ void __launch_bounds__(256) k_nb_place(MapConst mc, FrameConst fc, DevPtrs dp) {
+    pdl_enter();
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int nown = dp.st->n_cand_owner;
+    int born = 0;
+    for (int o = warp; o < nown; o += nwarps) {
+        const int d = dp.cowner[o];
+        const int b = dp.cbase[d], c = dp.ccnt[d];
+        ulonglong2 msk = dp.M[d];
+        const int nfree = min(mask_free(mc, msk), c);
+        long long last = -1;
+        int my_slot[4] = {-1, -1, -1, -1}, my_cand[4] = {0, 0, 0, 0};
+        const bool in_regs = c <= 256;  // the usual case: the segment's keys live in registers for all rounds
+        u64 K[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int j = q * 32 + lane;
+            K[q] = (in_regs && j < c) ? (((u64)(unsigned)dp.cseg[b + j] << 32) | (unsigned)j) : ~0ull;
+        }
+        for (int r = 0; r < nfree; ++r) {
+            u64 best = ~0ull;  // (key << 32) | position
+            if (in_regs) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) best = min(best, K[q]);
+            } else {
+                for (int j = lane; j < c; j += 32) {
+                    const long long kj = dp.cseg[b + j];
+                    if (kj > last) best = min(best, ((u64)kj << 32) | (unsigned)j);
+                }
+            }
+            for (int sft = 16; sft > 0; sft >>= 1) best = min(best, __shfl_xor_sync(FULLMASK, best, sft));
+            if (in_regs) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (K[q] == best) K[q] = ~0ull;
+            }
+            last = (long long)(best >> 32);
+            const int slot = mask_nth_free(mc, msk, 0);
+            if (slot < 64) msk.x |= 1ull << slot; else msk.y |= 1ull << (slot - 64);
+            if (lane == (r & 31)) {
+                const int q = r >> 5;
+                const int cand = dp.csegi[b + (int)(best & 0xffffffffull)];
+                if (q == 0) { my_slot[0] = slot; my_cand[0] = cand; }
+                else if (q == 1) { my_slot[1] = slot; my_cand[1] = cand; }
+                else if (q == 2) { my_slot[2] = slot; my_cand[2] = cand; }
+                else { my_slot[3] = slot; my_cand[3] = cand; }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (my_slot[q] >= 0) {
+                const int a = d * mc.S + my_slot[q];
+                dp.PA[a] = dp.CA[my_cand[q]];
+                dp.PB[a] = dp.CB[my_cand[q]];
+            }
+        if (lane == 0) {
+            dp.M[d] = msk;
+            born += nfree;
+        }
+    }
+    if (lane == 0 && born) atomicAdd(&dp.st->n_born, born);
+}
 // The same placement with the warp-wide minimum taken by one REDUX instruction (experiment switch DSPMAP_NB_REDUX=1).  At
 // cfg2 a destination voxel has ~100 candidates and ~20 free slots: k_nb_place spends each of its ~20 rounds in a five-step
 // 64-bit shuffle reduction (ten dependent SHFLs, ~250 cycles of latency) on (key, position) pairs.  Keys are unique 32-bit
 // integers, so the minimum key alone identifies the winner: __reduce_min_sync gives it to every lane at once, and the lane
 // that holds it keeps the slot for its own candidate (no position has to travel).  Voxels without a free slot are left
 // before their keys are loaded.  Same selection, same slots: bit-identical.
-__global__ void __launch_bounds__(256) k_nb_place(MapConst mc, FrameConst fc, DevPtrs dp) {
+__global__ void __launch_bounds__(256) k_nb_place_redux(MapConst mc, FrameConst fc, DevPtrs dp) {
     pdl_enter();
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -1609,6 +2273,143 @@ __global__ void __launch_bounds__(256) k_resample(MapConst mc, FrameConst fc, De
 // stalls dominate).  Here each lane first writes its kept particles to the warp's shared-memory tile at their rank in slot
 // order; both loops then run over that compact array with broadcast loads whose addresses do not depend on the running
 // sums, and their verdicts (new weight, or removed) go back through the tile.  Same operations in the same order.
+#define RS_WARPS 8
+__global__ void __launch_bounds__(32 * RS_WARPS, 3) k_resample_sm(MapConst mc, FrameConst fc, DevPtrs dp) {
+    pdl_enter();
+    __shared__ float4 sA[RS_WARPS][DSP_MAX_SLOTS], sB[RS_WARPS][DSP_MAX_SLOTS];  // position + weight; velocity + "old" flag
+    __shared__ float sNW[RS_WARPS][DSP_MAX_SLOTS];                               // verdict: new weight, < 0 = removed
+    __shared__ unsigned char sSlot[RS_WARPS][DSP_MAX_SLOTS];
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int R = (mc.S + 31) >> 5;
+    const unsigned below = (1u << lane) - 1u;
+    int c_pre = 0, c_old = 0, c_out = 0, c_low = 0;
+    const int nocc = dp.st->n_occ_voxels;
+    for (int item = warp; item < nocc; item += nwarps) {
+        const int v = dp.E[item];  // E carries the occupied-voxel list (k_voxel_list)
+        const ulonglong2 mv = dp.M[v];
+        const u64 mx = mv.x, my = mv.y;
+        float4 A[4], B[4];
+        unsigned keep[4], old[4];
+        int n_low = 0;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const unsigned live = r < 2 ? (unsigned)(mx >> (32 * r)) : (unsigned)(my >> (32 * (r - 2)));
+            A[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+            B[r] = A[r];
+            const bool mine = r < R && ((live >> lane) & 1u);
+            if (mine) {
+                const int a = v * mc.S + 32 * r + lane;
+                A[r] = dp.PA[a];
+                B[r] = dp.PB[a];
+            }
+            const bool kp = mine && !((double)A[r].w < 1e-3);  // (:941) particles below 1e-3 are dropped
+            keep[r] = __ballot_sync(FULLMASK, kp);
+            old[r] = __ballot_sync(FULLMASK, kp && B[r].w < 10.f);  // not newborn (:944)
+            n_low += __popc(live) - __popc(keep[r]);
+        }
+        // kept particles to the tile, at their rank in slot order
+        int n = 0, n_old = 0;
+        __syncwarp();  // the previous voxel's readers are done with the tile
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            if ((keep[r] >> lane) & 1u) {
+                const int j = n + __popc(keep[r] & below);
+                sA[wl][j] = A[r];
+                sB[wl][j] = make_float4(B[r].x, B[r].y, B[r].z, ((old[r] >> lane) & 1u) ? 1.f : 0.f);
+                sSlot[wl][j] = (unsigned char)(32 * r + lane);
+            }
+            n += __popc(keep[r]);
+            n_old += __popc(old[r]);
+        }
+        __syncwarp();
+        // sums in slot order (:938-973), every lane the same chain
+        float wsum = 0.f, sx = 0.f, sy = 0.f, sz = 0.f;
+        for (int j = 0; j < n; ++j) {
+            const float4 a = sA[wl][j], b = sB[wl][j];
+            if (b.w != 0.f) { sx += b.x; sy += b.y; sz += b.z; }
+            wsum += a.w;
+        }
+        // future status of the old particles (:950-964): each lane scatters its own
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            if ((old[r] >> lane) & 1u)
+                for (int t = 0; t < mc.T; ++t) {
+                    const float ft = mc.ft[t];
+                    const float fx = A[r].x + B[r].x * ft, fy = A[r].y + B[r].y * ft, fz = A[r].z + B[r].z * ft;
+                    const int fi = dsp_voxel_index(mc, fx, fy, fz);
+                    if (fi >= 0) atomicAdd(&dp.FUT[(size_t)fi * mc.T + t], A[r].w);
+                }
+        if (lane == 0) {
+            float4 o = make_float4(wsum, 0.f, 0.f, 0.f);
+            if (n_old > 0) { o.y = sx / (float)n_old; o.z = sy / (float)n_old; o.w = sz / (float)n_old; }
+            dp.OCCV[v] = o;
+        }
+        ulonglong2 occ = make_ulonglong2((u64)keep[0] | ((u64)keep[1] << 32), (u64)keep[2] | ((u64)keep[3] << 32));
+        const bool resample = n >= 5;  // (:986)
+        if (resample) {  // systematic resampling to at most MAX particles, offset 0.5 * w_after, slot order
+            const int n_after = n > mc.max_ppv ? mc.max_ppv : n;
+            const float w_after = wsum / (float)n_after;
+            float acc_ori = 0.f, acc_new = w_after * 0.5f;
+            for (int j = 0; j < n; ++j) {
+                acc_ori += sA[wl][j].w;
+                float verdict;
+                if (acc_ori > acc_new) {
+                    float wk = w_after;
+                    acc_new += w_after;
+                    bool full = false;
+                    while (acc_ori > acc_new) {  // duplicate heavy particles into the first free slot (:1021-1044)
+                        const int fs = full ? -1 : mask_nth_free(mc, occ, 0);
+                        if (fs >= 0) {
+                            if (lane == 0) {
+                                const float4 a = sA[wl][j], b = sB[wl][j];
+                                dp.PA[v * mc.S + fs] = make_float4(a.x, a.y, a.z, wk);
+                                dp.PB[v * mc.S + fs] = make_float4(b.x, b.y, b.z, 0.6f);
+                            }
+                            if (fs < 64) occ.x |= 1ull << fs; else occ.y |= 1ull << (fs - 64);
+                        } else {
+                            wk += w_after;
+                            full = true;
+                        }
+                        acc_new += w_after;
+                    }
+                    verdict = wk;
+                } else {  // removed (:1046-1050)
+                    const int sl = sSlot[wl][j];
+                    if (sl < 64) occ.x &= ~(1ull << sl); else occ.y &= ~(1ull << (sl - 64));
+                    verdict = -1.f;
+                }
+                if (lane == 0) sNW[wl][j] = verdict;
+            }
+        }
+        __syncwarp();
+        // every lane applies the verdicts of its own particles
+        int base = 0;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            if ((keep[r] >> lane) & 1u) {
+                const int a = v * mc.S + 32 * r + lane;
+                const float nw = resample ? sNW[wl][base + __popc(keep[r] & below)] : A[r].w;
+                if (!(nw < 0.f)) {
+                    if (nw != A[r].w) dp.PA[a].w = nw;
+                    if (B[r].w != 1.f) dp.PB[a].w = 1.f;  // newborn / moved flags become "valid" (:968)
+                }
+            }
+            base += __popc(keep[r]);
+        }
+        if (lane == 0) dp.M[v] = occ;
+        c_pre += n;
+        c_old += n_old;
+        c_out += mask_popc(occ);
+        c_low += n_low;
+    }
+    if (lane == 0 && (c_pre | c_low)) {
+        atomicAdd(&dp.st->n_pre, c_pre);
+        atomicAdd(&dp.st->n_old, c_old);
+        atomicAdd(&dp.st->n_out, c_out);
+        if (c_low) atomicAdd(&dp.st->n_low_weight, c_low);
+    }
+}
 
 // end of frame: reset the arrival-grouping tables touched this frame; advance the noise cursors by what the reference's
 // serial newborn loop would have drawn (dsp_dynamic.h:1162-1178); flag a frame no observation kernel handled
@@ -1659,6 +2460,29 @@ __global__ void __launch_bounds__(256) k_occ_count(MapConst mc, DevPtrs dp, floa
         if (d_future) d_future[i] = dp.FUT[i];
         dp.FUT[i] = 0.f;
     }
+}
+// the same with the scan of the per-block counts (the offsets of k_occ_write) by the block that finishes last (DSPMAP_FUSE_SCAN)
+__global__ void __launch_bounds__(256) k_occ_count_fs(MapConst mc, DevPtrs dp, float thr, int *blockcnt, int *blockoff, int nblocks, float *d_future) {
+    pdl_enter();
+    __shared__ int s;
+    if (threadIdx.x == 0) s = 0;
+    __syncthreads();
+    int b = blockIdx.x * OCC_BLOCK, c = 0;
+    for (int i = threadIdx.x; i < OCC_BLOCK; i += blockDim.x) {
+        int v = b + i;
+        if (v < mc.V && dp.OCCV[v].x > thr) ++c;
+    }
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_down_sync(FULLMASK, c, d);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s, c);
+    __syncthreads();
+    if (threadIdx.x == 0) blockcnt[blockIdx.x] = s;
+    // future status: copy out (if asked) and clear (:416-424)
+    size_t fb = (size_t)b * mc.T, fe = min((size_t)mc.V, (size_t)b + OCC_BLOCK) * mc.T;
+    for (size_t i = fb + threadIdx.x; i < fe; i += blockDim.x) {
+        if (d_future) d_future[i] = dp.FUT[i];
+        dp.FUT[i] = 0.f;
+    }
+    if (last_block_done(&dp.st->tickets[2])) scan_block(blockcnt, blockoff, nullptr, 0, nblocks);
 }
 __global__ void __launch_bounds__(256) k_occ_write(MapConst mc, DevPtrs dp, float thr, const int *blockoff, float *xyz, int cap, int *d_count, int nblocks) {
     pdl_enter();

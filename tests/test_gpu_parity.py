@@ -241,7 +241,7 @@ def test_full_size_properties(name, frames):
         if f in (frames // 2, frames - 1):
             c = g.counters()
             ids, vals = g.particles()
-            assert len(ids) == c["n_out"] and c["n_inexact"] == 0
+            assert len(ids) == c["n_out"] and c["overflow"] == 0
             key = ids[:, 0].astype(np.int64) * 128 + ids[:, 1]
             assert np.all(np.diff(key) > 0) and ids[:, 1].max() < d["S"]            # unique (voxel, slot), sweep order
             half = 0.5 * cfg["res"] * np.array([cfg["nx"], cfg["ny"], cfg["nz"]], np.float32)
@@ -265,18 +265,19 @@ def test_full_size_properties(name, frames):
     g.close()
 
 
-@pytest.mark.parametrize("switch", ["DSPMAP_PDL", "DSPMAP_EST_THREAD"])
-def test_library_switches_used_by_the_bench_do_not_change_a_bit(switch, monkeypatch):
-    """bench.py opts into programmatic dependent launch and the helper-thread velocity estimation (environment switches
-    read by dspmap_create).  A map created with the switch must stay bit-identical to a default map on the bench workload,
-    through the explicit-newborn-input path and through the library's own estimator."""
+@pytest.mark.parametrize("switch", ["DSPMAP_PDL", "DSPMAP_EST_THREAD", "DSPMAP_ASYNC_UPDATE"])
+def test_library_defaults_that_can_be_switched_off_do_not_change_a_bit(switch, monkeypatch):
+    """Programmatic dependent launch, the helper-thread velocity estimation and the asynchronous update are library defaults
+    (adopted from the A/B of profiles/r02_ab_switches.jsonl); NAME=0, read by dspmap_create, turns one off.  A map created
+    without one must stay bit-identical to a default map on the bench workload, through the explicit-newborn-input path and
+    through the library's own estimator."""
     name, frames = "cfg2", 3
     cfg = dm.CONFIGS[name]
     st = make_stream(cfg, seed=3, frames=frames + 2)
     est = dm.VelocityEstimator(cfg, seed=7, filter_res=0.1)
     monkeypatch.delenv(switch, raising=False)
     a = gpu_map(name, seed=7, max_points=cfg["points"])
-    monkeypatch.setenv(switch, "1")
+    monkeypatch.setenv(switch, "0")
     b = gpu_map(name, seed=7, max_points=cfg["points"])
     monkeypatch.delenv(switch, raising=False)
     bad = []

@@ -42,7 +42,7 @@ def test_sharded_equals_single_gpu(name, nranks, frames):
         for c in cl.cursors():
             assert np.array_equal(c[:3], c1[:3]), "frame %d: cursors" % f
         cs = cl.counters()
-        assert sum(c["n_out"] for c in cs) == one.counters()["n_out"] and all(c["n_inexact"] == 0 for c in cs)
+        assert sum(c["n_out"] for c in cs) == one.counters()["n_out"] and all(c["overflow"] == 0 for c in cs)
         # every shard only holds particles of its own voxel subspace
         for s in cl.shards:
             pid, _ = s.map.particles()
