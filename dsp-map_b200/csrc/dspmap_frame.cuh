@@ -33,6 +33,7 @@ __global__ void k_frame_setup(MapConst mc, FrameConst fc, DevPtrs dp) {
         s->n_inexact = 0;
         s->n_vz = s->n_skipped = 0;
         s->n_occ_voxels = 0;
+        s->ticket = 0;
         s->work_eval = s->work_eval2 = s->work_w2 = 0;
         s->total_pairs = 0ull;
         s->use_store = 0;
@@ -50,6 +51,7 @@ __global__ void k_frame_setup(MapConst mc, FrameConst fc, DevPtrs dp) {
         dp.obs_maxbits[i] = __float_as_int(-1.f);
         dp.pcount[i] = 0;
         dp.pfill[i] = 0;
+        dp.pub[i] = 0;
     }
 }
 
@@ -328,6 +330,7 @@ __global__ void k_predict(MapConst mc, FrameConst fc, DevPtrs dp) {
                 reinterpret_cast<int *>(rec)[10] = q;
                 continue;
             }
+            if (q >= 0 && !mc.sharded) atomicAdd(&dp.pub[q], 1);  // upper bound of the pyramid's list length (arrive_needs_replay)
             int k = agg_inc(&dp.st->n_mov);
             dp.MBA[k] = A;
             dp.MBB[k] = B;
@@ -425,9 +428,120 @@ __device__ __forceinline__ void arrive_body(const MapConst &mc, const FrameConst
         }
     }
 }
+// ------------------------------------------------------------------------------------------------------------
+// Pyramid-list overflow (dsp_dynamic.h:1243-1259).  When a pyramid's list is full the particle being processed vanishes and
+// frees its voxel slot AT THAT MOMENT of the sweep, so a later arrival of the same frame may take the slot: slot assignment
+// and list membership then depend on each other along the whole sweep, and the parallel ranking above no longer applies.
+// Lists overflow only when the reference's size formula yields a tiny L (a handful of entries for small maps at 1 degree);
+// no BASELINE configuration comes near.  k_arrive therefore first bounds every list from above — particles that stayed in
+// their voxel inside the field of view (counted by k_predict) plus ALL movers heading for the pyramid — and only if some
+// bound exceeds L it replays moveParticle serially, in sweep order, exactly as the reference executes it:
+//   phase A (whole grid): rank the frame's events (registered stayers and movers; keys are unique) by sweep key;
+//   phase B (the block that finishes last, one thread): walk them in order with working masks W (= MS, seeded from M0):
+//     arrivals from lower-index voxels see the destination before its own sweep, later ones after its own leavers
+//     (M0 & ~M, removed lazily when the sweep passes the voxel) and its own vanished stayers freed their slots.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool arrive_needs_replay(const MapConst &mc, const DevPtrs &dp) {
+    int over = 0;
+    if (!mc.sharded)
+        for (int q = threadIdx.x; q < mc.P; q += blockDim.x) over |= dp.pcount[q] + dp.pub[q] > mc.L;
+    return __syncthreads_or(over) != 0;
+}
+__device__ __forceinline__ void replay_apply_leavers(const DevPtrs &dp, int v) {  // the sweep has passed voxel v
+    if (dp.vzcnt[v]) return;
+    dp.vzcnt[v] = 1;
+    const ulonglong2 m0 = dp.M0[v], m = dp.M[v];  // M = M0 minus everything that left v (k_predict)
+    ulonglong2 w = dp.MS[v];
+    w.x &= ~(m0.x & ~m.x);
+    w.y &= ~(m0.y & ~m.y);
+    dp.MS[v] = w;
+}
+__device__ __forceinline__ void replay_clear(const DevPtrs &dp, int v, int s) {
+    ulonglong2 w = dp.MS[v];
+    if (s < 64) w.x &= ~(1ull << s); else w.y &= ~(1ull << (s - 64));
+    dp.MS[v] = w;
+}
+__device__ void arrive_replay(const MapConst &mc, const DevPtrs &dp) {
+    __shared__ bool s_last;
+    DevState *st = dp.st;
+    const int n_stay = st->n_fov, n_mov = st->n_mov, n_ev = n_stay + n_mov;  // (nobody changes them before phase B)
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    int *ev = dp.PSkey;  // free until k_pyr_scatter
+    // phase A
+    for (int v = tid; v < mc.V; v += nth) { dp.MS[v] = dp.M0[v]; dp.vzcnt[v] = 0; }
+    for (int e = tid; e < n_ev; e += nth) {
+        const int key = e < n_stay ? dp.Fkey[e] : dp.MBkey[e - n_stay];
+        int r = 0;
+        for (int j = 0; j < n_stay; ++j) r += dp.Fkey[j] < key;
+        for (int j = 0; j < n_mov; ++j) r += dp.MBkey[j] < key;
+        ev[r] = e;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&st->ticket, 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // phase B
+    for (int q = threadIdx.x; q < mc.P; q += blockDim.x) dp.pcount[q] = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int n_fov = n_stay, n_moved = 0, n_vfull = 0, n_pfull = 0;
+        for (int r = 0; r < n_ev; ++r) {
+            const int e = __ldcg(ev + r);
+            if (e < n_stay) {  // stayed in its voxel, inside the field of view: joins its pyramid's list unless that is full
+                const int key = dp.Fkey[e], q = dp.Fq[e];
+                if (dp.pcount[q] < mc.L) {
+                    ++dp.pcount[q];
+                } else {  // vanishes (:1256-1259)
+                    const int v = key >> DSP_KEY_SHIFT;
+                    replay_apply_leavers(dp, v);
+                    replay_clear(dp, v, key & (DSP_MAX_SLOTS - 1));
+                    dp.Fq[e] = -1;
+                    ++n_pfull;
+                }
+                continue;
+            }
+            const int i = e - n_stay;
+            const int key = dp.MBkey[i], d = dp.MBdst[i], q = dp.MBq[i];
+            if ((key >> DSP_KEY_SHIFT) > d) replay_apply_leavers(dp, d);
+            ulonglong2 w = dp.MS[d];
+            const int slot = mask_nth_free(mc, w, 0);
+            if (slot < 0) { ++n_vfull; continue; }  // voxel full: the particle vanishes (:1227-1229)
+            const int a = d * mc.S + slot;
+            dp.PA[a] = dp.MBA[i];
+            dp.PB[a] = dp.MBB[i];
+            ++n_moved;
+            if (q >= 0 && dp.pcount[q] >= mc.L) { ++n_pfull; continue; }  // pyramid full: the slot is free again at once
+            if (slot < 64) w.x |= 1ull << slot; else w.y |= 1ull << (slot - 64);
+            dp.MS[d] = w;
+            if (q >= 0) {
+                ++dp.pcount[q];
+                dp.Fkey[n_fov] = key;
+                dp.Faddr[n_fov] = a;
+                dp.Fq[n_fov] = q;
+                dp.FP[n_fov] = dp.MBA[i];
+                ++n_fov;
+            }
+        }
+        st->n_fov = n_fov;
+        st->n_moved = n_moved;
+        st->n_voxel_full = n_vfull;
+        st->n_pyramid_full = n_pfull;
+    }
+    __syncthreads();
+    // final masks: the working masks, with the leavers of the voxels the walk never passed removed as well
+    for (int v = threadIdx.x; v < mc.V; v += blockDim.x) {
+        const ulonglong2 m0 = dp.M0[v], m = dp.M[v];
+        ulonglong2 w = dp.MS[v];
+        if (!dp.vzcnt[v]) { w.x &= ~(m0.x & ~m.x); w.y &= ~(m0.y & ~m.y); }
+        dp.M[v] = w;
+    }
+}
 __global__ void k_arrive(MapConst mc, FrameConst fc, DevPtrs dp) {
     pdl_enter();
-    arrive_body(mc, fc, dp);
+    if (arrive_needs_replay(mc, dp)) arrive_replay(mc, dp);
+    else arrive_body(mc, fc, dp);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -590,8 +704,11 @@ __global__ void __launch_bounds__(512) k_pyr_sort(MapConst mc, DevPtrs dp, float
                     dp.LP[b + i] = pa;
                     dp.PW[b + i] = Pd * pa.w;
                 } else if (a >= 0) {  // pyramid full: the particle vanishes and frees its voxel slot (:1256-1259)
+                    // single GPU: unreachable, k_arrive replays such frames serially.  Sharded maps build their lists after the
+                    // gather, so the slot is freed after all arrivals were placed: flagged (code 32), see DESIGN.md
                     mask_atomic_clear(dp.M, a / mc.S, a % mc.S);
                     atomicAdd(&dp.st->n_pyramid_full, 1);
+                    atomicOr(&dp.st->overflow, 32);
                 }
             }
             __syncthreads();
@@ -608,6 +725,7 @@ __global__ void __launch_bounds__(512) k_pyr_sort(MapConst mc, DevPtrs dp, float
                 } else if (a >= 0) {
                     mask_atomic_clear(dp.M, a / mc.S, a % mc.S);
                     atomicAdd(&dp.st->n_pyramid_full, 1);
+                    atomicOr(&dp.st->overflow, 32);
                 }
             }
         }

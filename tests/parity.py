@@ -70,7 +70,7 @@ def compare_state(ref, gpu, check_future_exact=False, future_rtol=2e-6, label=""
     return bad
 
 
-def run_stream(ref, gpu, stream, frames, tagged_from_ref=True, reader_every=2, threshold=0.2, stop_on_first=True):
+def run_stream(ref, gpu, stream, frames, tagged_from_ref=True, reader_every=2, threshold=0.2, stop_on_first=True, seen=None):
     """Feeds the same frames to both; the newborn input of the GPU map is the reference's own tagged cloud, so the
     comparison isolates the hot path. Returns list of (frame, mismatches)."""
     out = []
@@ -83,6 +83,9 @@ def run_stream(ref, gpu, stream, frames, tagged_from_ref=True, reader_every=2, t
         b = gpu.update(len(pts), 3, pts, float(pos[0]), float(pos[1]), float(pos[2]), float(t), float(q[0]), float(q[1]),
                        float(q[2]), float(q[3]), tagged=tc if tagged_from_ref else None)
         bad = []
+        if seen is not None:  # which regimes the stream went through (per-frame counters of the CUDA path, summed)
+            for k, v in gpu.counters().items():
+                seen[k] = seen.get(k, 0) + v if k.startswith("n_") else max(seen.get(k, 0), v)
         if a != b:
             bad.append("return codes differ: ref %d gpu %d" % (a, b))
         bad += compare_state(ref, gpu, label="frame %d:" % f)

@@ -35,8 +35,8 @@ def test_gpu_reproduces_reference_golden(name, frames, initp):
     g.close()
 
 
-STREAMS = [("tiny_dyn", 14, 0), ("tiny_static", 8, 0), ("tiny_dyn", 6, 3000), ("cfg1", 6, 0), ("cfg2", 3, 0), ("cfg3", 2, 0),
-           ("cfg4", 2, 0), ("ref_default", 3, 0)]
+STREAMS = [("tiny_dyn", 14, 0), ("tiny_static", 8, 0), ("tiny_dyn", 6, 3000), ("cfg1", 6, 0), ("cfg2", 36, 0), ("cfg3", 8, 0),
+           ("cfg4", 8, 0), ("cfg5", 2, 0), ("ref_default", 3, 0)]
 
 
 @pytest.mark.parametrize("name,frames,initp", STREAMS)
@@ -44,12 +44,17 @@ def test_gpu_equals_reference_on_stream(name, frames, initp):
     if not refmap.available(name):
         pytest.skip("oracle/_ref/libdspref_%s.so not present" % name)
     cfg = dm.CONFIGS[name]
-    st = make_stream(cfg, seed=3, frames=frames)
+    # cfg2: bench.py's own stream (seed 1), through frame 35: voxels fill up in frames 4-13 and 33, as in the timed frames
+    st = make_stream(cfg, seed=1 if name == "cfg2" else 3, frames=frames)
     r = refmap.RefMap(name, seed=7, init_particles=initp)
-    g = gpu_map(name, seed=7, init_particles=initp)
-    bad = run_stream(r, g, st, frames)
+    g = gpu_map(name, seed=7, init_particles=initp, max_points=max(cfg["points"], 1024))
+    seen = {}
+    bad = run_stream(r, g, st, frames, seen=seen)
     g.close()
     assert not bad, "\n".join(str(b) for b in bad)
+    assert seen["overflow"] == 0
+    if name == "cfg2":  # the stream reaches the saturated population bench.py times: full voxels and dropped light particles
+        assert seen["n_voxel_full"] > 0 and seen["n_low_weight"] > 0 and seen["n_born"] > 0, seen
 
 
 def test_gpu_builtin_velocity_estimation_path():
@@ -66,18 +71,34 @@ def test_gpu_builtin_velocity_estimation_path():
     assert not bad, "\n".join(str(b) for b in bad)
 
 
-def test_pyramid_overflow_config_is_exact_until_a_slot_is_reused():
-    """tiny_mn: the reference's own size formula gives 2 list slots per pyramid, so lists overflow every frame. The
-    overflow itself (who is dropped) is reproduced exactly; a dropped particle's voxel slot being re-used by a later
-    arrival of the SAME frame is first-order only (DESIGN.md 'Known deviations')."""
+def test_pyramid_overflow_is_exact_including_slot_reuse():
+    """tiny_mn: the reference's own size formula gives 2 list slots per pyramid, so lists overflow every frame and the
+    dropped particles free their voxel slots in the middle of the sweep (dsp_dynamic.h:1256-1259), where later arrivals of
+    the same frame take them.  k_arrive replays such frames in sweep order: everything stays bit-identical."""
     name = "tiny_mn"
     if not refmap.available(name):
         pytest.skip("reference library not present")
-    st = make_stream(dm.CONFIGS[name], seed=3, frames=4)
+    frames = 12
+    st = make_stream(dm.CONFIGS[name], seed=3, frames=frames)
     r = refmap.RefMap(name, seed=7)
     g = gpu_map(name, seed=7)
-    bad = run_stream(r, g, st, 4)
+    bad = run_stream(r, g, st, frames)
     assert g.counters()["n_pyramid_full"] > 0
+    g.close()
+    assert not bad, "\n".join(str(b) for b in bad)
+
+
+@pytest.mark.parametrize("initp", [0, 4000])
+def test_pyramid_and_voxel_overflow_together_are_exact(initp):
+    """The same map seeded with constructor particles (voxels fill up as well): voxel-full and pyramid-full drops interleave."""
+    name = "tiny_mn"
+    if not refmap.available(name):
+        pytest.skip("reference library not present")
+    frames = 6
+    st = make_stream(dm.CONFIGS[name], seed=5, frames=frames)
+    r = refmap.RefMap(name, seed=11, init_particles=initp)
+    g = gpu_map(name, seed=11, init_particles=initp)
+    bad = run_stream(r, g, st, frames)
     g.close()
     assert not bad, "\n".join(str(b) for b in bad)
 
