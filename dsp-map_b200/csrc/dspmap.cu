@@ -68,7 +68,7 @@ struct dspmap {
     int record_flag = 0;
     float record_time = 1.f;
     bool recorded_once = false;
-    std::string record_folder = ".";
+    std::string record_prefix = "./";  // the CSV's path up to "particles_update_t_..." (the headers differ: dyn:333 adds "/", mn:335 and st:330 do not)
     int stage_limit = 4;
     int max_points = 0, cap_cand = 0;
     // pinned staging
@@ -1097,11 +1097,11 @@ int dspmap_set_newborn_number(dspmap *m, int n) {
     m->nb_num = n;
     return DSPMAP_OK;
 }
-int dspmap_set_particle_record_flag(dspmap *m, int flag, float record_time, const char *folder) {
+int dspmap_set_particle_record_flag(dspmap *m, int flag, float record_time, const char *prefix) {
     if (!m) return DSPMAP_E_BAD_ARG;
     m->record_flag = flag;
     m->record_time = record_time;
-    if (folder) m->record_folder = folder;
+    if (prefix) m->record_prefix = prefix;
     return DSPMAP_OK;
 }
 int dspmap_set_voxel_filter_resolution(dspmap *m, float r) { if (!m) return DSPMAP_E_BAD_ARG; m->estimator.filter_res = r; return DSPMAP_OK; }
@@ -1550,7 +1550,7 @@ int write_particle_csv(dspmap *m) {
     std::vector<int32_t> ids(2 * (size_t)std::max(n, 1));
     std::vector<float> vals(8 * (size_t)std::max(n, 1));
     n = dspmap_dump_particles(m, ids.data(), vals.data(), n);
-    std::string name = m->record_folder + "/particles_update_t_" + std::to_string(m->update_counter) + "_" +
+    std::string name = m->record_prefix + "particles_update_t_" + std::to_string(m->update_counter) + "_" +
                        std::to_string((int)(m->update_time * 1000)) + ".csv";
     std::ofstream f(name, std::ios::out | std::ios::trunc);
     for (int i = 0; i < n; ++i) {

@@ -233,7 +233,8 @@ class DSPMap:
         self._check(self.lib.dspmap_set_newborn_number(self.h, num))
 
     def setParticleRecordFlag(self, record_particle_flag, record_csv_time=1.0, folder="."):
-        self._check(self.lib.dspmap_set_particle_record_flag(self.h, record_particle_flag, record_csv_time, folder.encode()))
+        sep = "/" if self.cfg_dict.get("header", "dsp_dynamic.h") == "dsp_dynamic.h" else ""   # dyn:333 vs mn:335 / st:330
+        self._check(self.lib.dspmap_set_particle_record_flag(self.h, record_particle_flag, record_csv_time, (folder + sep).encode()))
 
     def setOriginalVoxelFilterResolution(self, res):
         self._check(self.lib.dspmap_set_voxel_filter_resolution(self.h, res))

@@ -94,7 +94,10 @@ int dspmap_set_prediction_variance(dspmap *m, float p_stddev, float v_stddev);
 int dspmap_set_observation_stddev(dspmap *m, float ob_stddev);
 int dspmap_set_newborn_weight(dspmap *m, float weight);
 int dspmap_set_newborn_number(dspmap *m, int num);
-int dspmap_set_particle_record_flag(dspmap *m, int flag, float record_time, const char *folder);
+/* The particle CSV (:325-350: one line flag,vx,vy,vz,px,py,pz,weight,voxel per live particle, sweep order) is written to
+ * <prefix>particles_update_t_<update counter>_<ms>.csv; the reference's headers differ in the prefix (dsp_dynamic.h:333
+ * particle_save_folder + "/", the other two without the separator), so the drop-in headers pass it complete. */
+int dspmap_set_particle_record_flag(dspmap *m, int flag, float record_time, const char *prefix);
 int dspmap_set_voxel_filter_resolution(dspmap *m, float res);
 
 /* getOccupancyMap (:385-402) when future == NULL, getOccupancyMapWithFutureStatus (:405-426) otherwise.
@@ -152,7 +155,7 @@ int dspmap_cursors(dspmap *m, int64_t *c);
 int dspmap_set_cursors(dspmap *m, int64_t p, int64_t v, int64_t u);
 
 /* Per-frame counters of the last update: n_in, n_left_map, n_voxel_full, n_pyramid_full, n_moved,
- * n_fov, n_candidates, n_born, n_low_weight, n_pre, n_old, n_out, n_valid_points, n_inexact, kernel launches of
+ * n_fov, n_candidates, n_born, n_low_weight, n_pre, n_old, n_out, n_valid_points, capacity-overrun code (0 = none; dspmap.cu: report_overflow), kernel launches of
  * the last frame, kernel launches since create (16 int64). */
 int dspmap_counters(dspmap *m, int64_t *out);
 

@@ -72,6 +72,8 @@ public:
     int update(int point_cloud_num, int size_of_one_point, float *point_cloud_ptr, float sensor_px, float sensor_py,
                float sensor_pz, double time_stamp_second, float sensor_quaternion_w, float sensor_quaternion_x,
                float sensor_quaternion_y, float sensor_quaternion_z) {  // :181-184
+        // the reference reads the global particle_save_folder when it writes the CSV (:333), not when the flag is set
+        if (record_flag_) dspmap_set_particle_record_flag(map_, record_flag_, record_time_, (particle_save_folder + DSPMAP_CSV_SEPARATOR).c_str());
         int rc = dspmap_update(map_, point_cloud_num, size_of_one_point, point_cloud_ptr, sensor_px, sensor_py, sensor_pz,
                                time_stamp_second, sensor_quaternion_w, sensor_quaternion_x, sensor_quaternion_y,
                                sensor_quaternion_z);
@@ -83,7 +85,9 @@ public:
     void setNewBornParticleWeight(float weight) { dspmap_set_newborn_weight(map_, weight); }                                 // :366
     void setNewBornParticleNumberofEachPoint(int num) { dspmap_set_newborn_number(map_, num); }                              // :370
     void setParticleRecordFlag(int record_particle_flag, float record_csv_time = 1.f) {                                      // :375
-        dspmap_set_particle_record_flag(map_, record_particle_flag, record_csv_time, particle_save_folder.c_str());
+        record_flag_ = record_particle_flag;
+        record_time_ = record_csv_time;
+        dspmap_set_particle_record_flag(map_, record_particle_flag, record_csv_time, (particle_save_folder + DSPMAP_CSV_SEPARATOR).c_str());
     }
     static void setOriginalVoxelFilterResolution(float res) {  // :380 (static in the reference: applies to the process)
         filter_resolution() = res;
@@ -144,6 +148,8 @@ private:
         }
     }
     dspmap *map_ = nullptr;
+    int record_flag_ = 0;
+    float record_time_ = 1.f;
     std::vector<float> xyz_;
     float *pinned_ = nullptr;
 };

@@ -116,6 +116,11 @@ void ref_set_observation_stddev(float s) { g_map->setObservationStdDev(s); }
 void ref_set_newborn_weight(float w) { g_map->setNewBornParticleWeight(w); }
 void ref_set_newborn_number(int n) { g_map->setNewBornParticleNumberofEachPoint(n); }
 void ref_set_voxel_filter_resolution(float r) { DSPMap::setOriginalVoxelFilterResolution(r); }
+// the particle CSV of update() (dsp_dynamic.h:325-350): the header's own writer, into `folder` (the header's global string)
+void ref_set_particle_record_flag(int flag, float record_time, const char *folder) {
+    particle_save_folder = folder;
+    g_map->setParticleRecordFlag(flag, record_time);
+}
 
 int ref_update(int n, int stride, float *pts, float px, float py, float pz, double t, float qw, float qx,
                float qy, float qz) {

@@ -63,7 +63,8 @@ class RefMap:
         L.ref_voxel_index.argtypes = [C.c_float] * 3
         for f, t in (("ref_set_prediction_variance", [C.c_float, C.c_float]), ("ref_set_observation_stddev", [C.c_float]),
                      ("ref_set_newborn_weight", [C.c_float]), ("ref_set_newborn_number", [C.c_int]),
-                     ("ref_set_voxel_filter_resolution", [C.c_float])):
+                     ("ref_set_voxel_filter_resolution", [C.c_float]),
+                     ("ref_set_particle_record_flag", [C.c_int, C.c_float, C.c_char_p])):
             getattr(L, f).argtypes = t
         d = np.zeros(16, np.int32)
         L.ref_dims(_ip(d))
@@ -100,6 +101,10 @@ class RefMap:
 
     def clear_prediction(self):
         self.lib.ref_clear_prediction()
+
+    def set_particle_record_flag(self, flag, record_time=1.0, folder="."):
+        """setParticleRecordFlag (dsp_dynamic.h:375) with the header's global particle_save_folder set to `folder`."""
+        self.lib.ref_set_particle_record_flag(int(flag), float(record_time), folder.encode())
 
     def tagged_cloud(self):
         n = self.lib.ref_tagged_cloud(None, 0)

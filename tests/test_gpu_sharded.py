@@ -18,7 +18,7 @@ def setters(g):
     g.setNewBornParticleWeight(SET["newborn_weight"])
 
 
-@pytest.mark.parametrize("name,nranks,frames", [("tiny_dyn", 2, 10), ("tiny_dyn", 3, 8), ("tiny_static", 2, 6), ("cfg1", 2, 5), ("cfg2", 4, 4)])
+@pytest.mark.parametrize("name,nranks,frames", [("tiny_dyn", 2, 10), ("tiny_dyn", 3, 8), ("tiny_static", 2, 6), ("cfg1", 2, 5), ("cfg2", 4, 4), ("cfg5", 8, 2)])
 def test_sharded_equals_single_gpu(name, nranks, frames):
     cfg = dm.CONFIGS[name]
     st = make_stream(cfg, seed=8, frames=frames)
