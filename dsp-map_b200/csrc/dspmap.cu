@@ -44,8 +44,9 @@ struct dspmap {
     dspmap_config cfg;
     MapConst mc;
     DevPtrs dp;
-    cudaStream_t stream = nullptr, own_stream = nullptr, side = nullptr;
+    cudaStream_t stream = nullptr, own_stream = nullptr, side = nullptr, nb = nullptr;  // frame; observation binning + normaliser; early newborn placement
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_state = nullptr, ev_fork_obs = nullptr, ev_join_obs = nullptr;
+    cudaEvent_t ev_arrived = nullptr, ev_nb_early = nullptr, ev_staged_t = nullptr;
     bool state_event_recorded = false;
     std::vector<void *> allocs;
     // host mirrors
@@ -111,7 +112,7 @@ struct dspmap {
     bool clear_overflow = false;   // the device-side flag has been absorbed: clear it in front of the next frame
     long long state_copies = 0, state_absorbed = 0;  // frame-end state copies enqueued / taken over by the host
     bool norm_join_pending = false;  // k_norm runs on the side stream and has not been joined yet
-    bool nb_prefix_done = false;  // this frame's first newborn kernels already ran on the side branch
+    bool nb_early_done = false;   // this frame's early newborn kernels (candidates, placement) are already enqueued on the newborn branch
     bool pdl = true;              // programmatic dependent launch of the frame's kernels (DSPMAP_PDL=0 turns it off)
     bool async_update = true;     // dspmap_update returns once the frame is enqueued; the next call that needs results waits (DSPMAP_ASYNC_UPDATE=0: wait in update)
     bool staged_pending = false;  // the page-locked staging buffers are still being read by the previous frame's copies
@@ -367,12 +368,34 @@ int ensure_cand_capacity(dspmap *m) {
     if (need <= m->cap_cand) return DSPMAP_OK;
     m->cap_cand = need;
     if (dalloc(m, &m->dp.CA, need, false) != DSPMAP_OK) return DSPMAP_E_CUDA;
-    if (dalloc(m, &m->dp.CB, need, false) != DSPMAP_OK) return DSPMAP_E_CUDA;
+    if (dalloc(m, &m->dp.Caddr, need, false) != DSPMAP_OK) return DSPMAP_E_CUDA;
     if (dalloc(m, &m->dp.Ckey, need, false) != DSPMAP_OK) return DSPMAP_E_CUDA;
     if (dalloc(m, &m->dp.Cdst, need, false) != DSPMAP_OK) return DSPMAP_E_CUDA;
     if (dalloc(m, &m->dp.cseg, need, false) != DSPMAP_OK) return DSPMAP_E_CUDA;
     if (dalloc(m, &m->dp.csegi, need, false) != DSPMAP_OK) return DSPMAP_E_CUDA;
     m->dp.cap_cand = need;
+    return DSPMAP_OK;
+}
+
+// The early half of the newborn step on its own branch (see k_nb_cand): in-map test and position-noise cursors of the points,
+// candidate positions, grouping by destination voxel, slot assignment.  Needs the masks after the arrival pass (ev_arrived).
+int enqueue_newborn_early(dspmap *m, const FrameConst &fc, const float *d_tagged) {
+    if (!(fc.stage_limit >= 3 && fc.n_tagged > 0 && fc.nb_num > 0)) return DSPMAP_OK;
+    const MapConst &mc = m->mc;
+    DevPtrs dp = m->dp;
+    dp.tagged = d_tagged;
+    const int B = 256;
+    cudaStream_t nb = m->nb;
+    LAUNCH_ON(m, FAM_NEWBORN, nb, k_nb_point0, grid_for(fc.n_tagged, B), B, 0, mc, fc, dp);
+    LAUNCH_ON(m, FAM_NEWBORN, nb, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{dp.ninmap, dp.nrank, nullptr, 0, fc.n_tagged}, ScanJob{}, ScanJob{}}});
+    LAUNCH_ON(m, FAM_NEWBORN, nb, k_nb_mask, grid_for((long long)fc.n_tagged * fc.nb_num, B), B, 0, mc, fc, dp);
+    CK(cudaStreamWaitEvent(nb, m->ev_arrived, 0));
+    LAUNCH_ON(m, FAM_NEWBORN, nb, k_nb_cand, grid_for((long long)fc.n_tagged * fc.nb_num, B), B, 0, mc, fc, dp);
+    LAUNCH_ON(m, FAM_NEWBORN, nb, k_group_owner, kSMs * 2, B, 0, dp, &dp.st->n_cand_owner, dp.cowner, dp.ccnt, dp.cbase, &dp.st->cand_top);
+    LAUNCH_ON(m, FAM_NEWBORN, nb, k_group_scatter, kSMs * 4, B, 0, &dp.st->n_cand, dp.Cdst, dp.Ckey, dp.cbase, dp.cfill, dp.cseg, dp.csegi);
+    LAUNCH_ON(m, FAM_NEWBORN, nb, k_nb_place, kSMs * 8, B, 0, mc, fc, dp);
+    CK(cudaEventRecord(m->ev_nb_early, nb));
+    m->nb_early_done = true;
     return DSPMAP_OK;
 }
 
@@ -383,6 +406,7 @@ int enqueue_frame_a(dspmap *m, const FrameConst &fc, const float *d_pts, const f
     dp.pts = d_pts;
     m->launches_frame = 0;
     const int B = 256;
+    int rc_nb = DSPMAP_OK;
     LAUNCH(m, FAM_SETUP, k_frame_setup, 1, 256, 0, mc, fc, dp);
     // observations: binning touches nothing the prediction / reassignment chain reads, and both are chains of small
     // latency-bound kernels, so they run side by side (joined before the pair preparation, the first consumer of the bins)
@@ -396,18 +420,10 @@ int enqueue_frame_a(dspmap *m, const FrameConst &fc, const float *d_pts, const f
         LAUNCH_ON(m, FAM_OBS, m->side, k_obs_scatter, grid_for(fc.n_points, B), B, 0, mc, fc, dp);
         LAUNCH_ON(m, FAM_OBS, m->side, k_obs_rank, grid_for(fc.n_points, B), B, 0, mc, fc, dp);
     }
-    // With a device-resident newborn input the first newborn kernels — they read only that cloud, the noise table and its
-    // cursor — follow on the same branch instead of waiting for the weight pass
-    m->nb_prefix_done = false;
-    if (d_tagged_early && fc.stage_limit >= 3 && fc.n_tagged > 0 && fc.nb_num > 0) {
-        DevPtrs dq = dp;
-        dq.tagged = d_tagged_early;
-        LAUNCH_ON(m, FAM_NEWBORN, m->side, k_nb_point0, grid_for(fc.n_tagged, B), B, 0, mc, fc, dq);
-        LAUNCH_ON(m, FAM_NEWBORN, m->side, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{dp.ninmap, dp.nrank, nullptr, 0, fc.n_tagged}, ScanJob{}, ScanJob{}}});
-        LAUNCH_ON(m, FAM_NEWBORN, m->side, k_nb_mask, grid_for((long long)fc.n_tagged * fc.nb_num, B), B, 0, mc, fc, dq);
-        m->nb_prefix_done = true;
-    }
     CK(cudaEventRecord(m->ev_join_obs, m->side));
+    // the newborn branch starts behind this frame's setup (i.e. behind everything of the previous frame)
+    CK(cudaStreamWaitEvent(m->nb, m->ev_fork_obs, 0));
+    m->nb_early_done = false;
     // prediction and reassignment
     if (fc.vz_mode) {
         LAUNCH(m, FAM_PREDICT, k_vz_count, grid_for(mc.V, B), B, 0, mc, dp);
@@ -421,6 +437,10 @@ int enqueue_frame_a(dspmap *m, const FrameConst &fc, const float *d_pts, const f
     LAUNCH(m, FAM_ARRIVE, k_group_owner, kSMs * 2, B, 0, dp, &dp.st->n_mov_owner, dp.mowner, dp.mcnt, dp.mbase, &dp.st->mov_top);
     LAUNCH(m, FAM_ARRIVE, k_group_scatter, kSMs * 4, B, 0, &dp.st->n_mov, dp.MBdst, dp.MBkey, dp.mbase, dp.mfill, dp.mseg, (int *)nullptr);
     LAUNCH(m, FAM_ARRIVE, k_arrive, kSMs * 4, B, 0, mc, fc, dp);
+    CK(cudaEventRecord(m->ev_arrived, m->stream));  // the occupancy masks are final until the newborn placement
+    // With a device-resident newborn input the early newborn kernels (they need the cloud, the noise table and these masks)
+    // run beside the observation passes; with a host cloud they are enqueued by enqueue_frame_b, once the cloud is there
+    if (d_tagged_early && (rc_nb = enqueue_newborn_early(m, fc, d_tagged_early)) != DSPMAP_OK) return rc_nb;
     LAUNCH(m, FAM_PYRAMID, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{dp.pcount, dp.poff, nullptr, 0, mc.P}, ScanJob{}, ScanJob{}}});
     LAUNCH(m, FAM_PYRAMID, k_pyr_scatter, kSMs * 8, B, 0, dp);
     LAUNCH(m, FAM_PYRAMID, k_pyr_sort, std::min(mc.P, kSMs * 3), 512, PYR_SORT_CAP * sizeof(u64), mc, dp, fc.Pd);
@@ -435,7 +455,7 @@ int enqueue_frame_a(dspmap *m, const FrameConst &fc, const float *d_pts, const f
         if (fc.stage_limit >= 3) {  // the newborn normaliser is one long serial chain: run it beside the weight pass
             CK(cudaEventRecord(m->ev_fork, m->stream));
             CK(cudaStreamWaitEvent(m->side, m->ev_fork, 0));
-            launch_kernel(m->pdl, m->side, k_norm, 1, 256, 0, mc, fc, dp);
+            launch_kernel(m->pdl, m->side, k_norm, 1, 128, 0, mc, fc, dp);
             ++m->launches_total;
             ++m->launches_frame;
             CK(cudaEventRecord(m->ev_join, m->side));
@@ -458,25 +478,18 @@ int enqueue_frame_b(dspmap *m, const FrameConst &fc, const float *d_tagged) {
     dp.tagged = d_tagged;
     const int B = 256;
     int newborn_ran = 0;
-    if (fc.stage_limit >= 3) {
-        if (fc.n_tagged > 0 && fc.nb_num > 0) {
-            if (!m->nb_prefix_done) {
-                LAUNCH(m, FAM_NEWBORN, k_nb_point0, grid_for(fc.n_tagged, B), B, 0, mc, fc, dp);
-                LAUNCH(m, FAM_NEWBORN, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{dp.ninmap, dp.nrank, nullptr, 0, fc.n_tagged}, ScanJob{}, ScanJob{}}});
-                LAUNCH(m, FAM_NEWBORN, k_nb_mask, grid_for((long long)fc.n_tagged * fc.nb_num, B), B, 0, mc, fc, dp);
-            }
-            LAUNCH(m, FAM_NEWBORN, k_nb_point1, grid_for((long long)fc.n_tagged * 32, B), B, 0, mc, fc, dp, 0);
-            LAUNCH(m, FAM_NEWBORN, k_scan_small, 2, 1024, 0, ScanJobs{{ScanJob{dp.nvcnt, dp.nvoff, nullptr, 0, fc.n_tagged}, ScanJob{dp.nrcnt, dp.nroff, nullptr, 0, fc.n_tagged}, ScanJob{}}});
-            if (m->norm_join_pending) {  // k_norm (side stream) wrote w_new, which k_nb_cand reads
-                CK(cudaStreamWaitEvent(m->stream, m->ev_join, 0));
-                m->norm_join_pending = false;
-            }
-            LAUNCH(m, FAM_NEWBORN, k_nb_cand, grid_for((long long)fc.n_tagged * fc.nb_num, B), B, 0, mc, fc, dp, (u64)m->cfg.uniform_seed);
-            LAUNCH(m, FAM_NEWBORN, k_group_owner, kSMs * 2, B, 0, dp, &dp.st->n_cand_owner, dp.cowner, dp.ccnt, dp.cbase, &dp.st->cand_top);
-            LAUNCH(m, FAM_NEWBORN, k_group_scatter, kSMs * 4, B, 0, &dp.st->n_cand, dp.Cdst, dp.Ckey, dp.cbase, dp.cfill, dp.cseg, dp.csegi);
-            LAUNCH(m, FAM_NEWBORN, k_nb_place, kSMs * 8, B, 0, mc, fc, dp);
-            newborn_ran = 1;
+    if (fc.stage_limit >= 3 && fc.n_tagged > 0 && fc.nb_num > 0) {
+        int rc;
+        if (!m->nb_early_done && (rc = enqueue_newborn_early(m, fc, d_tagged)) != DSPMAP_OK) return rc;
+        CK(cudaStreamWaitEvent(m->stream, m->ev_nb_early, 0));  // the newborn slots exist (flag 15): the split below skips them
+        LAUNCH(m, FAM_NEWBORN, k_nb_point1, grid_for((long long)fc.n_tagged * 32, B), B, 0, mc, fc, dp, 0);
+        LAUNCH(m, FAM_NEWBORN, k_scan_small, 2, 1024, 0, ScanJobs{{ScanJob{dp.nvcnt, dp.nvoff, nullptr, 0, fc.n_tagged}, ScanJob{dp.nrcnt, dp.nroff, nullptr, 0, fc.n_tagged}, ScanJob{}}});
+        if (m->norm_join_pending) {  // k_norm (side stream) wrote w_new, which k_nb_fill reads
+            CK(cudaStreamWaitEvent(m->stream, m->ev_join, 0));
+            m->norm_join_pending = false;
         }
+        LAUNCH(m, FAM_NEWBORN, k_nb_fill, kSMs * 8, B, 0, mc, fc, dp, (u64)m->cfg.uniform_seed);
+        newborn_ran = 1;
     }
     if (fc.stage_limit >= 4) {
         LAUNCH(m, FAM_RESAMPLE, k_voxel_list, grid_for(mc.V, B), B, 0, mc, dp);
@@ -683,6 +696,10 @@ int dspmap_create(const dspmap_config *cfg, dspmap **out) {
     m->max_points = cfg->max_points > 0 ? cfg->max_points : 65536;
     CKM(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
     CKM(cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking));
+    CKM(cudaStreamCreateWithFlags(&m->nb, cudaStreamNonBlocking));
+    CKM(cudaEventCreateWithFlags(&m->ev_arrived, cudaEventDisableTiming));
+    CKM(cudaEventCreateWithFlags(&m->ev_nb_early, cudaEventDisableTiming));
+    CKM(cudaEventCreateWithFlags(&m->ev_staged_t, cudaEventDisableTiming));
     CKM(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
     CKM(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
     CKM(cudaEventCreateWithFlags(&m->ev_fork_obs, cudaEventDisableTiming));
@@ -833,12 +850,16 @@ void dspmap_destroy(dspmap *m) {
     if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
     if (m->own_stream) cudaStreamDestroy(m->own_stream);
     if (m->side) cudaStreamDestroy(m->side);
+    if (m->nb) cudaStreamDestroy(m->nb);
+    if (m->ev_arrived) cudaEventDestroy(m->ev_arrived);
+    if (m->ev_nb_early) cudaEventDestroy(m->ev_nb_early);
+    if (m->ev_staged_t) cudaEventDestroy(m->ev_staged_t);
     delete m;
 }
 
 static int update_common(dspmap *m, int n, int stride, const float *pts, float px, float py, float pz, double t, float qw,
                          float qx, float qy, float qz, const float *tagged, int n_tagged, bool use_estimator) {
-    if (!m || n < 0 || stride < 3 || (n > 0 && !pts) || n_tagged < 0 || (n_tagged > 0 && !tagged)) { g_err = "bad argument"; return DSPMAP_E_BAD_ARG; }
+    if (!m || n < 0 || stride < 3 || (n > 0 && !pts) || n_tagged < 0) { g_err = "bad argument"; return DSPMAP_E_BAD_ARG; }
     if (n > m->max_points || n_tagged > m->max_points) { g_err = "more points than dspmap_config.max_points"; return DSPMAP_E_CAPACITY; }
     CK(cudaSetDevice(m->cfg.device));
     FrameConst fc;
@@ -853,6 +874,7 @@ static int update_common(dspmap *m, int n, int stride, const float *pts, float p
     if ((rc = ensure_cand_capacity(m)) != DSPMAP_OK) return rc;
     if (m->staged_pending) {  // asynchronous updates: the previous frame's host-to-device copies must have left the staging buffers
         CK(cudaEventSynchronize(m->ev_staged));
+        CK(cudaEventSynchronize(m->ev_staged_t));
         m->staged_pending = false;
     }
     for (int i = 0; i < n; ++i) {
@@ -861,6 +883,7 @@ static int update_common(dspmap *m, int n, int stride, const float *pts, float p
         m->h_pts[3 * i + 2] = pts[(size_t)i * stride + 2];
     }
     if (n > 0) CK(cudaMemcpyAsync((void *)m->dp.pts, m->h_pts, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, m->stream));
+    if (m->async_update) CK(cudaEventRecord(m->ev_staged, m->stream));  // behind the staging copy of the cloud
     const bool on_helper = use_estimator && m->est_thread;
     if (on_helper) {  // the estimation starts now, on the helper thread, while this thread enqueues the frame (host_worker.h)
         m->worker.start();
@@ -874,19 +897,23 @@ static int update_common(dspmap *m, int n, int stride, const float *pts, float p
         // the reference's side thread (dsp_dynamic.h:297, 1377-1544), overlapped with the kernels enqueued above exactly
         // as the reference overlaps it with prediction + update (:297-311)
         m->estimator.estimate(m->mc, fc, m->planes0.data(), m->h_pts, n, m->cfg.model, m->tagged_host);
-    } else if (!use_estimator) {  // explicit newborn input: exactly what the caller passed, possibly nothing
-        if (n_tagged > 0) m->tagged_host.assign(tagged, tagged + (size_t)7 * n_tagged);
-        else m->tagged_host.clear();
+    } else if (!use_estimator && tagged) {
+        // explicit newborn input.  A NULL pointer means "unchanged": the reference's input_cloud_with_velocity is a member that
+        // keeps its previous content when the side thread finds nothing in view (dsp_dynamic.h:1387-1391); a non-NULL pointer
+        // with n_tagged == 0 empties it
+        m->tagged_host.assign(tagged, tagged + (size_t)7 * n_tagged);
     }
     int nt = (int)(m->tagged_host.size() / 7);
     if (nt > m->max_points) { g_err = "newborn input larger than max_points"; return DSPMAP_E_CAPACITY; }
     if (nt > 0) {
+        // on the newborn branch (which is behind the previous frame by now): the copy and the early newborn kernels that
+        // follow it there do not queue up behind this frame's observation passes
         memcpy(m->h_tagged, m->tagged_host.data(), sizeof(float) * 7 * (size_t)nt);
-        CK(cudaMemcpyAsync((void *)m->dp.tagged, m->h_tagged, sizeof(float) * 7 * (size_t)nt, cudaMemcpyHostToDevice, m->stream));
+        CK(cudaMemcpyAsync((void *)m->dp.tagged, m->h_tagged, sizeof(float) * 7 * (size_t)nt, cudaMemcpyHostToDevice, m->nb));
     }
     fc.n_tagged = nt;
     if (m->async_update) {
-        CK(cudaEventRecord(m->ev_staged, m->stream));  // behind both staging copies
+        CK(cudaEventRecord(m->ev_staged_t, m->nb));  // behind the staging copy of the newborn input
         m->staged_pending = true;
     }
     if ((rc = enqueue_frame_b(m, fc, m->dp.tagged)) != DSPMAP_OK) return rc;
@@ -1043,7 +1070,7 @@ int dspmap_shard_phase(dspmap *m, int phase, int n, const float *d_pts, float px
     } else if (phase == 4) {  // owners take their new weights; the newborn split reads them (dsp_dynamic.h:829-866)
         dp.tagged = d_tagged;
         LAUNCH(m, FAM_WEIGHT, k_shard_apply_weights, kSMs * 4, B, 0, mc, dp);
-        LAUNCH(m, FAM_NORM, k_norm, 1, 256, 0, mc, fc, dp);
+        LAUNCH(m, FAM_NORM, k_norm, 1, 128, 0, mc, fc, dp);
         if (fc.n_tagged > 0 && fc.nb_num > 0) {
             LAUNCH(m, FAM_NEWBORN, k_shard_zero, kSMs, B, 0, mc, fc, dp, 2);
             LAUNCH(m, FAM_NEWBORN, k_nb_point0, grid_for(fc.n_tagged, B), B, 0, mc, fc, dp);
@@ -1057,10 +1084,11 @@ int dspmap_shard_phase(dspmap *m, int phase, int n, const float *d_pts, float px
         if (fc.n_tagged > 0 && fc.nb_num > 0) {
             LAUNCH(m, FAM_NEWBORN, k_nb_point1, grid_for((long long)fc.n_tagged * 32, B), B, 0, mc, fc, dp, 2);
             LAUNCH(m, FAM_NEWBORN, k_scan_small, 2, 1024, 0, ScanJobs{{ScanJob{dp.nvcnt, dp.nvoff, nullptr, 0, fc.n_tagged}, ScanJob{dp.nrcnt, dp.nroff, nullptr, 0, fc.n_tagged}, ScanJob{}}});
-            LAUNCH(m, FAM_NEWBORN, k_nb_cand, grid_for((long long)fc.n_tagged * fc.nb_num, B), B, 0, mc, fc, dp, (u64)m->cfg.uniform_seed);
+            LAUNCH(m, FAM_NEWBORN, k_nb_cand, grid_for((long long)fc.n_tagged * fc.nb_num, B), B, 0, mc, fc, dp);
             LAUNCH(m, FAM_NEWBORN, k_group_owner, kSMs * 2, B, 0, dp, &dp.st->n_cand_owner, dp.cowner, dp.ccnt, dp.cbase, &dp.st->cand_top);
             LAUNCH(m, FAM_NEWBORN, k_group_scatter, kSMs * 4, B, 0, &dp.st->n_cand, dp.Cdst, dp.Ckey, dp.cbase, dp.cfill, dp.cseg, dp.csegi);
             LAUNCH(m, FAM_NEWBORN, k_nb_place, kSMs * 8, B, 0, mc, fc, dp);
+            LAUNCH(m, FAM_NEWBORN, k_nb_fill, kSMs * 8, B, 0, mc, fc, dp, (u64)m->cfg.uniform_seed);
             newborn_ran = 1;
         }
         LAUNCH(m, FAM_RESAMPLE, k_voxel_list, grid_for(mc.V, B), B, 0, mc, dp);

@@ -1271,37 +1271,31 @@ __global__ void k_verify_div(float b, float r, unsigned max_bits, int mode, int 
 }
 
 
-#define NORMF_CHUNK 4096
-__global__ void __launch_bounds__(256) k_norm(MapConst mc, FrameConst fc, DevPtrs dp) {
+// K6a  newborn normaliser (dsp_dynamic.h:799-805): sum of 1/C_z over (pyramid, bin) order, one fp32 chain.
+__global__ void k_norm(MapConst mc, FrameConst fc, DevPtrs dp) {
     pdl_enter();
-    __shared__ __align__(16) float buf[2][NORMF_CHUNK];
+    __shared__ __align__(16) float buf[2][1024];
     const int n = dp.obs_capoff[mc.P];
-    const int nchunk = (n + NORMF_CHUNK - 1) / NORMF_CHUNK;
     float acc = 0.f;
+    int nchunk = (n + 1023) / 1024;
     if (nchunk > 0)
-        for (int t = threadIdx.x; t < NORMF_CHUNK; t += blockDim.x) buf[0][t] = t < n ? dp.INV[t] : 0.f;
+        for (int t = threadIdx.x; t < 1024; t += blockDim.x) buf[0][t] = t < n ? dp.INV[t] : 0.f;
     __syncthreads();
     for (int c = 0; c < nchunk; ++c) {
-        const int b0 = (c + 1) * NORMF_CHUNK;
-        if (threadIdx.x >= 32) {  // warps 1.. fetch the next chunk while thread 0 adds the current one
+        int nb = (c + 1) & 1, b0 = (c + 1) * 1024;
+        if (threadIdx.x >= 32) {  // warps 1.. prefetch the next chunk while warp 0 adds the current one
             if (c + 1 < nchunk)
-                for (int t = threadIdx.x - 32; t < NORMF_CHUNK; t += blockDim.x - 32) buf[(c + 1) & 1][t] = b0 + t < n ? dp.INV[b0 + t] : 0.f;
+                for (int t = threadIdx.x - 32; t < 1024; t += blockDim.x - 32) buf[nb][t] = b0 + t < n ? dp.INV[b0 + t] : 0.f;
         } else if (threadIdx.x == 0) {
-            const int cnt = min(NORMF_CHUNK, n - c * NORMF_CHUNK);
+            int cnt = min(1024, n - c * 1024);
             const float4 *s4 = reinterpret_cast<const float4 *>(buf[c & 1]);
-            const int nb = cnt >> 4;  // batches of sixteen
-            float4 a0, a1, a2, a3;
-            if (nb > 0) { a0 = s4[0]; a1 = s4[1]; a2 = s4[2]; a3 = s4[3]; }
-            for (int k = 0; k < nb; ++k) {
-                float4 n0 = a0, n1 = a1, n2 = a2, n3 = a3;
-                if (k + 1 < nb) { n0 = s4[4 * k + 4]; n1 = s4[4 * k + 5]; n2 = s4[4 * k + 6]; n3 = s4[4 * k + 7]; }
-                acc += a0.x; acc += a0.y; acc += a0.z; acc += a0.w;
-                acc += a1.x; acc += a1.y; acc += a1.z; acc += a1.w;
-                acc += a2.x; acc += a2.y; acc += a2.z; acc += a2.w;
-                acc += a3.x; acc += a3.y; acc += a3.z; acc += a3.w;
-                a0 = n0; a1 = n1; a2 = n2; a3 = n3;
+            const int c4 = cnt >> 2;
+#pragma unroll 4
+            for (int k = 0; k < c4; ++k) {
+                float4 x = s4[k];
+                acc += x.x; acc += x.y; acc += x.z; acc += x.w;
             }
-            for (int k = nb << 4; k < cnt; ++k) acc += buf[c & 1][k];
+            for (int k = c4 << 2; k < cnt; ++k) acc += buf[c & 1][k];
         }
         __syncthreads();
     }
@@ -1426,12 +1420,16 @@ __global__ void __launch_bounds__(256) k_nb_point1(MapConst mc, FrameConst fc, D
     pdl_enter();
     nb_point1_body(mc, fc, dp, phase);
 }
-// candidate pass: position (:871-873), velocity class (:877-907), weight (:909); candidates inside the map join
-// the arrival grouping of their voxel, ordered by (point, candidate) = the reference's serial order.
-__global__ void k_nb_cand(MapConst mc, FrameConst fc, DevPtrs dp, u64 useed) {
+// Newborn particles are born in two steps.  WHERE a candidate lands — its position (:871-873), its voxel, and which free slot
+// of that voxel it takes in the reference's serial (point, candidate) order (addAParticle, :1183-1201) — depends only on
+// the cloud, the position-noise table and the occupancy masks after the arrival pass, so k_nb_cand, the grouping kernels
+// and k_nb_place run EARLY, beside the observation passes.  WHAT it carries — the velocity class (:877-907: it needs the
+// Dempster-Shafer split, i.e. the weights the observation update has just produced) and the weight (:909: it needs
+// sum 1/C_z) — is filled in by k_nb_fill after the weight pass.  Slots born early carry the newborn flag 15 from the start,
+// so the split (which skips newborn particles, :830) and everything else that walks a voxel sees them as the reference does.
+__global__ void k_nb_cand(MapConst mc, FrameConst fc, DevPtrs dp) {
     pdl_enter();
     const int total = fc.n_tagged * fc.nb_num;
-    const float w_new = dp.st->w_new;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
         int m = t / fc.nb_num, p = t - m * fc.nb_num;
         u64 im = dp.nimask[m];
@@ -1443,22 +1441,41 @@ __global__ void k_nb_cand(MapConst mc, FrameConst fc, DevPtrs dp, u64 useed) {
         float pz = pc.z + dp.ptab[(c + 2) % mc.G];
         int d = dsp_voxel_index(mc, px, py, pz);
         if (mc.sharded && (d < mc.v_lo || d >= mc.v_hi)) continue;  // another rank places this candidate
+        int k = agg_inc(&dp.st->n_cand);
+        if (k >= dp.cap_cand) { atomicOr(&dp.st->overflow, 2); continue; }
+        dp.CA[k] = make_float4(px, py, pz, 0.f);
+        dp.Caddr[k] = -1;  // not born (yet)
+        dp.Ckey[k] = m * DSP_MAX_NB_NUM + p;
+        dp.Cdst[k] = d;
+        if (atomicAdd(&dp.ccnt[d], 1) == 0) dp.cowner[agg_inc(&dp.st->n_cand_owner)] = d;
+    }
+}
+// velocity (:877-907) and weight (:909) of the candidates that were born
+__global__ void k_nb_fill(MapConst mc, FrameConst fc, DevPtrs dp, u64 useed) {
+    pdl_enter();
+    const int n = min(dp.st->n_cand, dp.cap_cand);
+    const float w_new = dp.st->w_new;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const int a = dp.Caddr[k];
+        if (a < 0) continue;
+        const int key = dp.Ckey[k], m = key / DSP_MAX_NB_NUM, p = key - m * DSP_MAX_NB_NUM;
         float vx = 0.f, vy = 0.f, vz = 0.f;
         const float *pt = dp.tagged + 7 * m;
         if (mc.model == 0 && pt[6] > 0.01f) {
+            const u64 im = dp.nimask[m];
             int n_static = dp.nstatic[m];
             if (p >= n_static) {
                 u64 nonstatic = im & ~bits_below(max(n_static, 0));
                 u64 est = (pt[3] > -100.f) ? bits_below(fc.nb_model_gen) : 0ull;
                 if ((est >> p) & 1ull) {
-                    int k = __popcll(nonstatic & est & bits_below(p));
-                    long long vc = (dp.st->v_cur + 3ll * (dp.nvoff[m] + k)) % mc.G;
+                    int j = __popcll(nonstatic & est & bits_below(p));
+                    long long vc = (dp.st->v_cur + 3ll * (dp.nvoff[m] + j)) % mc.G;
                     vx = pt[3] + 4 * dp.vtab[vc];
                     vy = pt[4] + 4 * dp.vtab[(vc + 1) % mc.G];
                     vz = pt[5] + 4 * dp.vtab[(vc + 2) % mc.G];
                 } else {
-                    int k = __popcll(nonstatic & ~est & bits_below(p));
-                    u64 uc = (u64)dp.st->u_cur + 3ull * (u64)(dp.nroff[m] + k);
+                    int j = __popcll(nonstatic & ~est & bits_below(p));
+                    u64 uc = (u64)dp.st->u_cur + 3ull * (u64)(dp.nroff[m] + j);
                     vx = dsp_uniform(useed, uc, -1.5f, 1.5f);
                     vy = dsp_uniform(useed, uc + 1, -1.5f, 1.5f);
                     vz = dsp_uniform(useed, uc + 2, -0.5f, 0.5f);
@@ -1466,21 +1483,14 @@ __global__ void k_nb_cand(MapConst mc, FrameConst fc, DevPtrs dp, u64 useed) {
             }
             vz = 0.f;  // LIMIT_MOVEMENT_IN_XY_PLANE (:905-907)
         }
-        int k = agg_inc(&dp.st->n_cand);
-        if (k >= dp.cap_cand) { atomicOr(&dp.st->overflow, 2); continue; }
-        dp.CA[k] = make_float4(px, py, pz, w_new);
-        dp.CB[k] = make_float4(vx, vy, vz, 15.f);
-        dp.Ckey[k] = m * DSP_MAX_NB_NUM + p;
-        dp.Cdst[k] = d;
-        if (atomicAdd(&dp.ccnt[d], 1) == 0) dp.cowner[agg_inc(&dp.st->n_cand_owner)] = d;
+        dp.PB[a] = make_float4(vx, vy, vz, 15.f);
+        dp.PA[a].w = w_new;
     }
 }
-// The same placement with the warp-wide minimum taken by one REDUX instruction (experiment switch DSPMAP_NB_REDUX=1).  At
-// cfg2 a destination voxel has ~100 candidates and ~20 free slots: k_nb_place spends each of its ~20 rounds in a five-step
-// 64-bit shuffle reduction (ten dependent SHFLs, ~250 cycles of latency) on (key, position) pairs.  Keys are unique 32-bit
-// integers, so the minimum key alone identifies the winner: __reduce_min_sync gives it to every lane at once, and the lane
-// that holds it keeps the slot for its own candidate (no position has to travel).  Voxels without a free slot are left
-// before their keys are loaded.  Same selection, same slots: bit-identical.
+// addAParticle (:1183-1201) in serial order: the k-th candidate of a voxel (in (point, candidate) order) takes its k-th free
+// slot.  One warp per destination voxel; at cfg2 a voxel has ~100 candidates and ~20 free slots.  Keys are unique 32-bit
+// integers, so the minimum key alone identifies the next winner: __reduce_min_sync (REDUX) gives it to every lane at once and
+// the lane that holds it keeps the slot for its own candidate.  Voxels without a free slot are left before their keys are loaded.
 __global__ void __launch_bounds__(256) k_nb_place(MapConst mc, FrameConst fc, DevPtrs dp) {
     pdl_enter();
     const int lane = threadIdx.x & 31;
@@ -1518,8 +1528,9 @@ __global__ void __launch_bounds__(256) k_nb_place(MapConst mc, FrameConst fc, De
                 if (slot_q[q] >= 0) {
                     const int cand = dp.csegi[b + q * 32 + lane];
                     const int a = d * mc.S + slot_q[q];
-                    dp.PA[a] = dp.CA[cand];
-                    dp.PB[a] = dp.CB[cand];
+                    dp.PA[a] = dp.CA[cand];                        // position; the weight follows in k_nb_fill
+                    dp.PB[a] = make_float4(0.f, 0.f, 0.f, 15.f);   // newborn flag now, velocity in k_nb_fill
+                    dp.Caddr[cand] = a;
                 }
         } else {  // oversized segment: every round rescans it in global memory (rare)
             long long last = -1;
@@ -1548,7 +1559,8 @@ __global__ void __launch_bounds__(256) k_nb_place(MapConst mc, FrameConst fc, De
                 if (my_slot[q] >= 0) {
                     const int a = d * mc.S + my_slot[q];
                     dp.PA[a] = dp.CA[my_cand[q]];
-                    dp.PB[a] = dp.CB[my_cand[q]];
+                    dp.PB[a] = make_float4(0.f, 0.f, 0.f, 15.f);
+                    dp.Caddr[my_cand[q]] = a;
                 }
         }
         if (lane == 0) {

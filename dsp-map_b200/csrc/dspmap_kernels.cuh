@@ -78,8 +78,8 @@ struct DevPtrs {
     float4 *NPC;          // corrected point + voxel id
     int *ninmap, *nrank, *nstatic, *nvcnt, *nrcnt, *nvoff, *nroff;
     u64 *nimask;
-    float4 *CA, *CB;
-    int *Ckey, *Cdst;
+    float4 *CA;           // candidate position (w unused)
+    int *Ckey, *Cdst, *Caddr;  // (point, candidate) key, destination voxel, slot address once born (-1 otherwise)
     int *ccnt, *cfill, *cbase, *cowner, *cseg, *csegi;
     // tables
     const float *ptab, *vtab, *lut;

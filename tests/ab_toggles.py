@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """A/B harness for the library's experiment switches (environment variables read by dspmap_create).
 
-For every switch set given on the command line (e.g. `DSPMAP_PDL=1` or `DSPMAP_PDL=1,DSPMAP_EST_THREAD=1`) it creates a
+For every switch set given on the command line (e.g. `DSPMAP_PDL=0` or `DSPMAP_PDL=0,DSPMAP_EST_THREAD=0`: the remaining switches are defaults that NAME=0 turns off) it creates a
 baseline map (no switches) and a switched map with the same seeds, feeds both the same stream and requires the complete
 map state to be bit-identical after every frame (tests/parity.py: compare_state; the atomically accumulated future grid
 within rtol 2e-6); then it times the device-resident frame (update_device + get_occupancy_device, CUDA events, L2 flushed
@@ -27,7 +27,7 @@ for p in (os.path.join(ROOT, "dsp-map_b200"), os.path.join(ROOT, "tests")):
 
 import numpy as np  # noqa: E402
 
-SWITCHES = ("DSPMAP_PDL", "DSPMAP_EST_THREAD", "DSPMAP_CZ_NARROW", "DSPMAP_CZ_TMA", "DSPMAP_CZ_STAGED", "DSPMAP_QUOT_FAST", "DSPMAP_NB_REDUX", "DSPMAP_G_COL", "DSPMAP_SPARSE_FUTURE", "DSPMAP_ASYNC_UPDATE", "DSPMAP_NORM_FAST", "DSPMAP_RESAMPLE_SM", "DSPMAP_SORT_WARP", "DSPMAP_EVAL_PACKED", "DSPMAP_FUSE_SCAN")
+SWITCHES = ("DSPMAP_PDL", "DSPMAP_EST_THREAD", "DSPMAP_ASYNC_UPDATE")  # defaults that NAME=0 turns off
 
 
 def make_map(dm, gpu_map, name, env, **kw):
