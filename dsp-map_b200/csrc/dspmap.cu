@@ -493,7 +493,7 @@ int enqueue_frame_b(dspmap *m, const FrameConst &fc, const float *d_tagged) {
     }
     if (fc.stage_limit >= 4) {
         LAUNCH(m, FAM_RESAMPLE, k_voxel_list, grid_for(mc.V, B), B, 0, mc, dp);
-        LAUNCH(m, FAM_RESAMPLE, k_resample, kSMs * 8, 256, 0, mc, fc, dp);
+        LAUNCH(m, FAM_RESAMPLE, k_resample, kSMs * 4, 32 * RS_WARPS, RS_WARPS * rs_warp_bytes(mc.S), mc, fc, dp);
     }
     if (m->norm_join_pending) {  // no newborn kernels this frame: k_norm must still be over before the next frame resets its outputs
         CK(cudaStreamWaitEvent(m->stream, m->ev_join, 0));
@@ -583,7 +583,10 @@ int write_particle_csv(dspmap *m);
 
 // pyramid boundary-plane normals when the sensor has no rotation (dsp_dynamic.h:563-578)
 void make_planes0(const dspmap_config *cfg, int Nh, int Nv, std::vector<float> &planes0) {
-    const float ang = (float)cfg->angle_resolution / 180.f * 3.14159265358979323846;  // :543
+    // :543 `(float)angle_resolution / 180.f * M_PIf32`: glibc's <cmath> defines M_PIf32 as a FLOAT literal under _GNU_SOURCE
+    // (g++'s default), so the header's own double fallback (:77-79) is not used and the product is rounded in fp32
+    const float ang = cfg->pi_is_double ? (float)((float)cfg->angle_resolution / 180.f * 3.14159265358979323846)
+                                        : (float)cfg->angle_resolution / 180.f * 3.14159265358979323846f;
     planes0.assign(3 * (Nh + Nv + 2), 0.f);
     int h0 = -cfg->half_fov_h / cfg->angle_resolution, h1 = -h0;
     for (int i = h0; i <= h1; i++) {
@@ -794,6 +797,7 @@ int dspmap_create(const dspmap_config *cfg, dspmap **out) {
     m->est_thread = !env_off("DSPMAP_EST_THREAD");
     m->async_update = !env_off("DSPMAP_ASYNC_UPDATE");
     CKM(cudaFuncSetAttribute(k_weight, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CKM(cudaFuncSetAttribute(k_resample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RS_WARPS * rs_warp_bytes(DSP_MAX_SLOTS))));
     CKM(cudaStreamSynchronize(m->stream));
     if (gen_tables(m) != DSPMAP_OK) { dspmap_destroy(m); return DSPMAP_E_CUDA; }
     {   // (p + half) / res with p inside the map: dividends lie in (0, 2*half)
@@ -1092,7 +1096,7 @@ int dspmap_shard_phase(dspmap *m, int phase, int n, const float *d_pts, float px
             newborn_ran = 1;
         }
         LAUNCH(m, FAM_RESAMPLE, k_voxel_list, grid_for(mc.V, B), B, 0, mc, dp);
-        LAUNCH(m, FAM_RESAMPLE, k_resample, kSMs * 8, 256, 0, mc, fc, dp);
+        LAUNCH(m, FAM_RESAMPLE, k_resample, kSMs * 4, 32 * RS_WARPS, RS_WARPS * rs_warp_bytes(mc.S), mc, fc, dp);
         LAUNCH(m, FAM_CLEANUP, k_cleanup, kSMs * 2, B, 0, mc, fc, dp, newborn_ran, 0);
         CK(cudaMemcpyAsync(m->h_state, m->dp.st, sizeof(DevState), cudaMemcpyDeviceToHost, m->stream));
         CK(cudaEventRecord(m->ev_state, m->stream));
@@ -1415,6 +1419,14 @@ int dspmap_dump_pyramid_lists(dspmap *m, int32_t *offsets, int32_t *entries, int
     }
     offsets[mc.P] = n;
     return n;
+}
+int dspmap_dump_plane_normals(dspmap *m, float *h, float *v) {
+    if (!m || !h || !v) return DSPMAP_E_BAD_ARG;
+    const MapConst &mc = m->mc;
+    CK(cudaStreamSynchronize(m->stream));
+    CK(cudaMemcpy(h, m->dp.planes, sizeof(float) * 3 * (mc.Nh + 1), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(v, m->dp.planes + 3 * (mc.Nh + 1), sizeof(float) * 3 * (mc.Nv + 1), cudaMemcpyDeviceToHost));
+    return DSPMAP_OK;
 }
 int dspmap_cursors(dspmap *m, int64_t *c) {
     if (!m) return DSPMAP_E_BAD_ARG;

@@ -1596,149 +1596,205 @@ __global__ void k_voxel_list(MapConst mc, DevPtrs dp) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// K7  occupancy, future status and resampling (dsp_dynamic.h:924-1057).  One WARP per occupied voxel: lane l owns
-//     slots l, l+32, l+64, l+96 (coalesced row loads); the order-dependent parts — the fp32 sums in slot order and the
-//     systematic-resampling state machine — are executed warp-uniformly on values broadcast by shuffles.
+// K7  occupancy, future status and resampling (dsp_dynamic.h:924-1057).
+//     A voxel's sums (fp32, slot order) and its systematic-resampling state machine are serial over ~20 particles, and
+//     there are only a few thousand occupied voxels: the work is latency, not throughput.  A warp takes RS_VPW voxels:
+//       stage  (all lanes, one voxel after the other) lane l owns slots l, l+32, ...: coalesced loads, the low-weight test
+//              (:941), the future-status scatter of the old particles (:950-964); the kept particles go to the warp's
+//              shared tile at their rank in slot order: (vx, vy, vz, w), slot, "old" and "flag is not 1" bits;
+//       walk   (lane j = voxel j) both order-dependent loops run over the tile with plain shared-memory loads whose
+//              addresses do not depend on the running sums; the verdicts (new weight, or removed) and the duplicates to make
+//              (:1021-1044: the first free slot at that moment, else the weight piles up on the original) go back through
+//              shared memory;
+//       apply  (all lanes) survivors get their weight and flag 1, duplicates are copied from their source slot.
+//     (Round 1's kernel gave a whole warp to one voxel and fetched every operand of the walk with find-first-set +
+//     shuffle: 2 450 warp instructions per voxel, 35 us at cfg2.)
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_resample(MapConst mc, FrameConst fc, DevPtrs dp) {
+#define RS_VPW 8     // voxels per warp
+#define RS_WARPS 4   // warps per block
+// shared memory of one warp: tile[RS_VPW][S + 1] float4 | verd[RS_VPW][S] float | tagb, dsrc, ddst [RS_VPW][S] u8 | wafter[RS_VPW] float
+__host__ __device__ __forceinline__ size_t rs_warp_bytes(int S) {
+    return ((size_t)RS_VPW * (S + 1) * 16 + (size_t)RS_VPW * S * 4 + (size_t)RS_VPW * S * 3 + (size_t)RS_VPW * 4 + 15) & ~(size_t)15;
+}
+__global__ void __launch_bounds__(32 * RS_WARPS) k_resample(MapConst mc, FrameConst fc, DevPtrs dp) {
     pdl_enter();
-    const int lane = threadIdx.x & 31;
+    extern __shared__ __align__(16) float4 rs_smem4[];
+    unsigned char *rs_smem = reinterpret_cast<unsigned char *>(rs_smem4);
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-    const int R = (mc.S + 31) >> 5;
+    const int S = mc.S, R = (S + 31) >> 5, ROW = S + 1;  // (+1: the rows of the walking lanes start in different banks)
+    unsigned char *base = rs_smem + (size_t)wl * rs_warp_bytes(S);
+    float4 *tile = reinterpret_cast<float4 *>(base);
+    float *verd = reinterpret_cast<float *>(base + (size_t)RS_VPW * ROW * 16);
+    unsigned char *tagb = reinterpret_cast<unsigned char *>(verd + RS_VPW * S);  // slot | 0x80 if the flag is not 1 yet
+    unsigned char *dsrc = tagb + RS_VPW * S, *ddst = dsrc + RS_VPW * S;
+    float *wafter = reinterpret_cast<float *>(ddst + RS_VPW * S);
+    const unsigned below = (1u << lane) - 1u;
     int c_pre = 0, c_old = 0, c_out = 0, c_low = 0;
     const int nocc = dp.st->n_occ_voxels;
-    for (int item = warp; item < nocc; item += nwarps) {
-        {
-            const int v = dp.E[item];  // E is free after prediction: it carries the occupied-voxel list (k_voxel_list)
-            const ulonglong2 mv = dp.M[v];
-            const u64 mx = mv.x, my = mv.y;
-            float4 A[4], B[4];
-            unsigned keep[4], old[4], surv[4];
-            int n_low = 0;
+    for (int item0 = warp * RS_VPW; item0 < nocc; item0 += nwarps * RS_VPW) {
+        const int nv = min(RS_VPW, nocc - item0);
+        // lane j < nv fetches voxel j's id and mask; the staging loop reads them by shuffle
+        int my_v = 0;
+        ulonglong2 my_m = make_ulonglong2(0ull, 0ull);
+        if (lane < nv) {
+            my_v = dp.E[item0 + lane];  // E carries the occupied-voxel list (k_voxel_list)
+            my_m = dp.M[my_v];
+        }
+        int my_n = 0, my_ndup = 0;
+        bool my_res = false;
+        ulonglong2 my_occ = make_ulonglong2(0ull, 0ull), my_old = my_occ;  // kept slots; "old" bits by RANK
+        __syncwarp();  // the previous group's readers are done with the tile
+        // ---- stage
+#pragma unroll 2
+        for (int j = 0; j < nv; ++j) {
+            const int v = __shfl_sync(FULLMASK, my_v, j);
+            const u64 mx = __shfl_sync(FULLMASK, my_m.x, j), my = __shfl_sync(FULLMASK, my_m.y, j);
+            int n = 0, n_low = 0;
+            u64 kx = 0ull, ky = 0ull, ox = 0ull, oy = 0ull;
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
+                if (r >= R) break;
                 const unsigned live = r < 2 ? (unsigned)(mx >> (32 * r)) : (unsigned)(my >> (32 * (r - 2)));
-                A[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-                B[r] = A[r];
-                const bool mine = r < R && ((live >> lane) & 1u);
+                if (live == 0u) continue;
+                float4 A = make_float4(0.f, 0.f, 0.f, 0.f), B = A;
+                const bool mine = (live >> lane) & 1u;
                 if (mine) {
-                    const int a = v * mc.S + 32 * r + lane;
-                    A[r] = dp.PA[a];
-                    B[r] = dp.PB[a];
+                    const int a = v * S + 32 * r + lane;
+                    A = dp.PA[a];
+                    B = dp.PB[a];
                 }
-                const bool kp = mine && !((double)A[r].w < 1e-3);  // (:941) particles below 1e-3 are dropped
-                keep[r] = __ballot_sync(FULLMASK, kp);
-                old[r] = __ballot_sync(FULLMASK, kp && B[r].w < 10.f);  // not newborn (:944)
-                surv[r] = keep[r];
-                n_low += __popc(live) - __popc(keep[r]);
+                const bool kp = mine && !((double)A.w < 1e-3);  // (:941) particles below 1e-3 are dropped
+                const bool od = kp && B.w < 10.f;               // not newborn (:944)
+                const unsigned keep = __ballot_sync(FULLMASK, kp), old = __ballot_sync(FULLMASK, od);
+                if (kp) {
+                    const int i = n + __popc(keep & below);
+                    tile[j * ROW + i] = make_float4(B.x, B.y, B.z, A.w);
+                    tagb[j * S + i] = (unsigned char)((32 * r + lane) | (B.w != 1.f ? 0x80 : 0));
+                    if (od) {  // future status of the old particles (:950-964): each lane scatters its own
+                        for (int t = 0; t < mc.T; ++t) {
+                            const float ft = mc.ft[t];
+                            const float fx = A.x + B.x * ft, fy = A.y + B.y * ft, fz = A.z + B.z * ft;
+                            const int fi = dsp_voxel_index(mc, fx, fy, fz);
+                            if (fi >= 0) atomicAdd(&dp.FUT[(size_t)fi * mc.T + t], A.w);
+                        }
+                        // this particle's "old" bit at its rank, collected by a second ballot below
+                    }
+                }
+                // "old" bits in RANK order: lane i of the row's kept particles -> bit n + rank.  Every lane computes its own
+                // bit position; an OR-reduction over the warp assembles the 128-bit mask.
+                u64 bx = 0ull, by = 0ull;
+                if (od) {
+                    const int i = n + __popc(keep & below);
+                    if (i < 64) bx = 1ull << i; else by = 1ull << (i - 64);
+                }
+                if (old) {  // (uniform)
+                    bx |= __shfl_xor_sync(FULLMASK, bx, 16); by |= __shfl_xor_sync(FULLMASK, by, 16);
+                    bx |= __shfl_xor_sync(FULLMASK, bx, 8);  by |= __shfl_xor_sync(FULLMASK, by, 8);
+                    bx |= __shfl_xor_sync(FULLMASK, bx, 4);  by |= __shfl_xor_sync(FULLMASK, by, 4);
+                    bx |= __shfl_xor_sync(FULLMASK, bx, 2);  by |= __shfl_xor_sync(FULLMASK, by, 2);
+                    bx |= __shfl_xor_sync(FULLMASK, bx, 1);  by |= __shfl_xor_sync(FULLMASK, by, 1);
+                    ox |= bx;
+                    oy |= by;
+                }
+                if (r < 2) kx |= (u64)keep << (32 * r); else ky |= (u64)keep << (32 * (r - 2));
+                n += __popc(keep);
+                n_low += __popc(live) - __popc(keep);
             }
+            if (lane == j) {
+                my_n = n;
+                my_occ = make_ulonglong2(kx, ky);
+                my_old = make_ulonglong2(ox, oy);
+                c_low += n_low;
+            }
+        }
+        __syncwarp();
+        // ---- walk: lane j < nv owns voxel j
+        if (lane < nv) {
+            const int n = my_n;
+            const float4 *row = tile + lane * ROW;
             // sums in slot order (:938-973)
             float wsum = 0.f, sx = 0.f, sy = 0.f, sz = 0.f;
-            int n = 0, n_old = 0;
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                unsigned k = keep[r];
-                n += __popc(k);
-                n_old += __popc(old[r]);
-                while (k) {
-                    const int l = __ffs(k) - 1;
-                    k &= k - 1;
-                    const float w = __shfl_sync(FULLMASK, A[r].w, l);
-                    if ((old[r] >> l) & 1u) {
-                        sx += __shfl_sync(FULLMASK, B[r].x, l);
-                        sy += __shfl_sync(FULLMASK, B[r].y, l);
-                        sz += __shfl_sync(FULLMASK, B[r].z, l);
-                    }
-                    wsum += w;
-                }
+            for (int i = 0; i < n; ++i) {
+                const float4 p = row[i];
+                const bool od = i < 64 ? (my_old.x >> i) & 1ull : (my_old.y >> (i - 64)) & 1ull;
+                if (od) { sx += p.x; sy += p.y; sz += p.z; }
+                wsum += p.w;
             }
-            // future status of the old particles (:950-964): each lane scatters its own
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-                if ((old[r] >> lane) & 1u)
-                    for (int t = 0; t < mc.T; ++t) {
-                        const float ft = mc.ft[t];
-                        const float fx = A[r].x + B[r].x * ft, fy = A[r].y + B[r].y * ft, fz = A[r].z + B[r].z * ft;
-                        const int fi = dsp_voxel_index(mc, fx, fy, fz);
-                        if (fi >= 0) atomicAdd(&dp.FUT[(size_t)fi * mc.T + t], A[r].w);
-                    }
-            if (lane == 0) {
-                float4 o = make_float4(wsum, 0.f, 0.f, 0.f);
-                if (n_old > 0) { o.y = sx / (float)n_old; o.z = sy / (float)n_old; o.w = sz / (float)n_old; }
-                dp.OCCV[v] = o;
-            }
-            ulonglong2 occ = make_ulonglong2((u64)keep[0] | ((u64)keep[1] << 32), (u64)keep[2] | ((u64)keep[3] << 32));
-            float nw[4] = {A[0].w, A[1].w, A[2].w, A[3].w};
+            const int n_old = __popcll(my_old.x) + __popcll(my_old.y);
+            float4 o = make_float4(wsum, 0.f, 0.f, 0.f);
+            if (n_old > 0) { o.y = sx / (float)n_old; o.z = sy / (float)n_old; o.w = sz / (float)n_old; }
+            dp.OCCV[my_v] = o;
+            ulonglong2 occ = my_occ;
             if (n >= 5) {  // (:986) systematic resampling to at most MAX particles, offset 0.5 * w_after, slot order
+                my_res = true;
                 const int n_after = n > mc.max_ppv ? mc.max_ppv : n;
                 const float w_after = wsum / (float)n_after;
+                wafter[lane] = w_after;
                 float acc_ori = 0.f, acc_new = w_after * 0.5f;
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    unsigned k = keep[r];
-                    while (k) {
-                        const int l = __ffs(k) - 1;
-                        k &= k - 1;
-                        acc_ori += __shfl_sync(FULLMASK, A[r].w, l);
-                        if (acc_ori > acc_new) {
-                            float wk = w_after;
-                            acc_new += w_after;
-                            bool full = false;
-                            while (acc_ori > acc_new) {  // duplicate heavy particles into the first free slot (:1021-1044)
-                                const int fs = full ? -1 : mask_nth_free(mc, occ, 0);
-                                if (fs >= 0) {
-                                    const float x = __shfl_sync(FULLMASK, A[r].x, l), y = __shfl_sync(FULLMASK, A[r].y, l),
-                                                z = __shfl_sync(FULLMASK, A[r].z, l);
-                                    const float vx = __shfl_sync(FULLMASK, B[r].x, l), vy = __shfl_sync(FULLMASK, B[r].y, l),
-                                                vz = __shfl_sync(FULLMASK, B[r].z, l);
-                                    if (lane == 0) {
-                                        dp.PA[v * mc.S + fs] = make_float4(x, y, z, wk);
-                                        dp.PB[v * mc.S + fs] = make_float4(vx, vy, vz, 0.6f);
-                                    }
-                                    if (fs < 64) occ.x |= 1ull << fs; else occ.y |= 1ull << (fs - 64);
-                                } else {
-                                    wk += w_after;
-                                    full = true;
-                                }
-                                acc_new += w_after;
+                for (int i = 0; i < n; ++i) {
+                    acc_ori += row[i].w;
+                    if (acc_ori > acc_new) {
+                        float wk = w_after;
+                        acc_new += w_after;
+                        bool full = false;
+                        while (acc_ori > acc_new) {  // duplicate heavy particles into the first free slot (:1021-1044)
+                            const int fs = full ? -1 : mask_nth_free(mc, occ, 0);
+                            if (fs >= 0) {
+                                dsrc[lane * S + my_ndup] = (unsigned char)i;
+                                ddst[lane * S + my_ndup] = (unsigned char)fs;
+                                ++my_ndup;
+                                if (fs < 64) occ.x |= 1ull << fs; else occ.y |= 1ull << (fs - 64);
+                            } else {
+                                wk += w_after;
+                                full = true;
                             }
-                            if (lane == l) nw[r] = wk;
-                        } else {  // removed (:1046-1050)
-                            const int sl = 32 * r + l;
-                            if (sl < 64) occ.x &= ~(1ull << sl); else occ.y &= ~(1ull << (sl - 64));
-                            surv[r] &= ~(1u << l);
+                            acc_new += w_after;
                         }
+                        verd[lane * S + i] = wk;
+                    } else {  // removed (:1046-1050)
+                        const int sl = tagb[lane * S + i] & 0x7f;
+                        if (sl < 64) occ.x &= ~(1ull << sl); else occ.y &= ~(1ull << (sl - 64));
+                        verd[lane * S + i] = -1.f;
                     }
                 }
             }
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-                if ((surv[r] >> lane) & 1u) {
-                    const int a = v * mc.S + 32 * r + lane;
-                    if (nw[r] != A[r].w) dp.PA[a].w = nw[r];
-                    if (B[r].w != 1.f) dp.PB[a].w = 1.f;  // newborn / moved flags become "valid" (:968)
-                }
-            if (lane == 0) dp.M[v] = occ;
+            dp.M[my_v] = occ;
             c_pre += n;
             c_old += n_old;
             c_out += mask_popc(occ);
-            c_low += n_low;
+        }
+        __syncwarp();
+        // ---- apply
+        for (int j = 0; j < nv; ++j) {
+            const int v = __shfl_sync(FULLMASK, my_v, j), n = __shfl_sync(FULLMASK, my_n, j), nd = __shfl_sync(FULLMASK, my_ndup, j);
+            const bool res = __shfl_sync(FULLMASK, (int)my_res, j) != 0;
+            for (int i = lane; i < n; i += 32) {
+                const float4 p = tile[j * ROW + i];
+                const unsigned char tb = tagb[j * S + i];
+                const float nw = res ? verd[j * S + i] : p.w;
+                if (!(nw < 0.f)) {
+                    const int a = v * S + (tb & 0x7f);
+                    if (nw != p.w) dp.PA[a].w = nw;
+                    if (tb & 0x80) dp.PB[a].w = 1.f;  // newborn / moved flags become "valid" (:968)
+                }
+            }
+            for (int d = lane; d < nd; d += 32) {
+                const int i = dsrc[j * S + d], fs = ddst[j * S + d];
+                const float4 p = tile[j * ROW + i];
+                const float4 A = dp.PA[v * S + (tagb[j * S + i] & 0x7f)];  // position of the original (its weight is being rewritten: not used)
+                dp.PA[v * S + fs] = make_float4(A.x, A.y, A.z, wafter[j]);
+                dp.PB[v * S + fs] = make_float4(p.x, p.y, p.z, 0.6f);
+            }
         }
     }
-    if (lane == 0 && (c_pre | c_low)) {
+    if (c_pre | c_low) {  // (lanes that walked voxels hold the counts)
         atomicAdd(&dp.st->n_pre, c_pre);
         atomicAdd(&dp.st->n_old, c_old);
         atomicAdd(&dp.st->n_out, c_out);
         if (c_low) atomicAdd(&dp.st->n_low_weight, c_low);
     }
 }
-
-// K7 with the order-dependent loops fed from shared memory (experiment switch DSPMAP_RESAMPLE_SM=1).  k_resample walks the
-// kept particles of a voxel in slot order twice (sums, then the systematic-resampling state machine) and fetches every
-// operand with a find-first-set + shuffle (2 450 instructions per voxel, 19.7 kept particles on average; wait / scoreboard
-// stalls dominate).  Here each lane first writes its kept particles to the warp's shared-memory tile at their rank in slot
-// order; both loops then run over that compact array with broadcast loads whose addresses do not depend on the running
-// sums, and their verdicts (new weight, or removed) go back through the tile.  Same operations in the same order.
 
 // end of frame: reset the arrival-grouping tables touched this frame; advance the noise cursors by what the reference's
 // serial newborn loop would have drawn (dsp_dynamic.h:1162-1178); flag a frame no observation kernel handled

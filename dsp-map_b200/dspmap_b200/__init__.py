@@ -33,7 +33,7 @@ class Config(C.Structure):
                 ("occlusion_margin", C.c_float), ("init_particle_num", C.c_int32), ("init_weight", C.c_float),
                 ("table_seed", C.c_uint64), ("uniform_seed", C.c_uint64), ("gaussian_table_size", C.c_int32),
                 ("max_observations_per_pyramid", C.c_int32), ("device", C.c_int32), ("max_points", C.c_int32),
-                ("shard_z_begin", C.c_int32), ("shard_z_end", C.c_int32)]
+                ("shard_z_begin", C.c_int32), ("shard_z_end", C.c_int32), ("pi_is_double", C.c_int32)]
 
 
 class DSPMapError(RuntimeError):
@@ -82,6 +82,7 @@ def load_library():
         "dspmap_dump_voxel_objects": (i, [vp, fp]),
         "dspmap_dump_observations": (i, [vp, ip, fp, fp]),
         "dspmap_dump_pyramid_lists": (i, [vp, ip, ip, i]),
+        "dspmap_dump_plane_normals": (i, [vp, fp, fp]),
         "dspmap_cursors": (i, [vp, C.POINTER(C.c_int64)]),
         "dspmap_set_cursors": (i, [vp, C.c_int64, C.c_int64, C.c_int64]),
         "dspmap_counters": (i, [vp, C.POINTER(C.c_int64)]),
@@ -125,7 +126,7 @@ EXPORTED_SYMBOLS = [
     "dspmap_get_occupancy_async", "dspmap_wait_occupancy",
     "dspmap_clear_prediction", "dspmap_pin_host_buffer", "dspmap_get_tagged_cloud", "dspmap_voxel_center", "dspmap_voxel_index", "dspmap_uniform",
     "dspmap_dims", "dspmap_dump_particles", "dspmap_load_particles", "dspmap_dump_voxel_objects",
-    "dspmap_dump_observations", "dspmap_dump_pyramid_lists", "dspmap_cursors", "dspmap_set_cursors", "dspmap_counters",
+    "dspmap_dump_observations", "dspmap_dump_pyramid_lists", "dspmap_dump_plane_normals", "dspmap_cursors", "dspmap_set_cursors", "dspmap_counters",
     "dspmap_set_stage_limit", "dspmap_set_last_pose", "dspmap_set_stream", "dspmap_synchronize", "dspmap_profile_enable", "dspmap_profile_read", "dspmap_profile_read_kernels",
     "dspmap_estimator_create", "dspmap_estimator_destroy", "dspmap_estimator_estimate", "dspmap_estimator_set_threaded",
     "dspmap_euclidean_clusters",
@@ -159,6 +160,7 @@ def make_config(cfg, seed=1, init_particles=0, init_weight=0.01, device=0, max_p
     c.max_observations_per_pyramid = 100
     c.device = device
     c.max_points = max_points
+    c.pi_is_double = 0 if cfg["header"] == "dsp_dynamic.h" else 1   # dyn:543 with glibc's float M_PIf32; mn:78 / st:74 double
     return c
 
 
@@ -317,6 +319,12 @@ class DSPMap:
         if n:
             self._check(self.lib.dspmap_dump_pyramid_lists(self.h, _ip(off), _ip(ent), n))
         return off, ent
+
+    def plane_normals(self):
+        h = np.zeros((self.Nh + 1, 3), np.float32)
+        v = np.zeros((self.Nv + 1, 3), np.float32)
+        self._check(self.lib.dspmap_dump_plane_normals(self.h, _fp(h), _fp(v)))
+        return h, v
 
     def cursors(self):
         c = np.zeros(4, np.int64)

@@ -42,5 +42,6 @@ static std::string particle_save_folder = ".";
 #define DSPMAP_PYRAMID_NEIGHBOR_N 1
 #define DSPMAP_MODEL 0
 #define DSPMAP_OCCLUSION_MARGIN 0.3f
+#define DSPMAP_PI_IS_DOUBLE 0  // see dspmap_config.pi_is_double
 #define DSPMAP_CSV_SEPARATOR "/"  // particle CSV path = particle_save_folder + this + "particles_update_t_..." (dsp_dynamic.h:333)
 #include "dspmap_dropin.hpp"

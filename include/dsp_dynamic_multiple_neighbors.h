@@ -45,5 +45,6 @@ static std::string particle_save_folder = ".";
 #define DSPMAP_PYRAMID_NEIGHBOR_N PYRAMID_NEIGHBOR_N
 #define DSPMAP_MODEL 0
 #define DSPMAP_OCCLUSION_MARGIN ((float)VOXEL_RESOLUTION)
+#define DSPMAP_PI_IS_DOUBLE 1  // see dspmap_config.pi_is_double
 #define DSPMAP_CSV_SEPARATOR ""  // particle CSV path = particle_save_folder + this + "particles_update_t_..." (mn:335: no separator)
 #include "dspmap_dropin.hpp"

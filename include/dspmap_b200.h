@@ -57,6 +57,11 @@ typedef struct dspmap_config {
     int32_t max_points;                 /* capacity for points per update() (0 = 65536) */
     /* voxel-subspace shard owned by this handle (multi-GPU): z-layers [z_begin, z_end); 0,0 = whole map */
     int32_t shard_z_begin, shard_z_end;
+    /* How `(float)ANGLE_RESOLUTION / 180.f * M_PIf32` (:543) rounds.  dsp_dynamic.h keeps glibc's M_PIf32, a FLOAT literal
+     * (its own double fallback at :77-79 is skipped because <cmath> defines the macro under _GNU_SOURCE): fp32 product, 0.
+     * dsp_dynamic_multiple_neighbors.h:78 and dsp_static.h:74 redefine M_PIf32 as a DOUBLE literal: fp64 product rounded to
+     * fp32 once, 1.  The boundary-plane normals, hence pyramid ids of particles within an ulp of a plane, depend on it. */
+    int32_t pi_is_double;
 } dspmap_config;
 
 /* Fills `c` with the values of the reference tree as shipped (dsp_dynamic.h:38-50,145-168). */
@@ -150,6 +155,8 @@ int dspmap_dump_voxel_objects(dspmap *m, float *out);
 int dspmap_dump_observations(dspmap *m, int32_t *counts, float *maxlen, float *pts);
 /* Last frame's pyramid lists (:124): offsets[P+1], entries[n][2] = {voxel, slot} in list order. */
 int dspmap_dump_pyramid_lists(dspmap *m, int32_t *offsets, int32_t *entries, int cap);
+/* The boundary-plane normals of the last frame, rotated to the sensor attitude (:226-232): h[(Nh+1)*3], v[(Nv+1)*3]. */
+int dspmap_dump_plane_normals(dspmap *m, float *h, float *v);
 /* c[0] position-noise cursor, c[1] velocity-noise cursor, c[2] uniform-stream counter (:483-484). */
 int dspmap_cursors(dspmap *m, int64_t *c);
 int dspmap_set_cursors(dspmap *m, int64_t p, int64_t v, int64_t u);

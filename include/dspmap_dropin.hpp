@@ -50,6 +50,7 @@ public:
         c.prediction_times = PREDICTION_TIMES;
         for (int i = 0; i < PREDICTION_TIMES; ++i) c.prediction_future_time[i] = prediction_future_time[i];
         c.occlusion_margin = DSPMAP_OCCLUSION_MARGIN;
+        c.pi_is_double = DSPMAP_PI_IS_DOUBLE;
         c.init_particle_num = init_particle_num;
         c.init_weight = init_weight;
         if (dspmap_create(&c, &map_) != DSPMAP_OK) {

@@ -47,6 +47,7 @@ struct Config {
     uint64_t uniform_seed;
     int32_t gaussian_table_size;
     int32_t obs_max_per_pyramid;  // 100
+    int32_t pi_is_double;         // mn:78 / st:74 redefine M_PIf32 as a double literal; dsp_dynamic.h keeps glibc's float one
 };
 
 enum { F_FLAG = 0, F_VX, F_VY, F_VZ, F_PX, F_PY, F_PZ, F_W, F_N };
@@ -220,7 +221,8 @@ struct Map {
         obs.assign((size_t)P * OBS * 5, 0.f);
         obs_n.assign(P, 0);
         obs_maxlen.assign(P, 0.f);
-        float ang = (float)c.angle_resolution / 180.f * 3.14159265358979323846;  // :543 (double pi, float store)
+        // :543 (dsp_dynamic.h: M_PIf32 is glibc's float literal, fp32 product; mn / static: their own double literal)
+        float ang = c.pi_is_double ? (float)((float)c.angle_resolution / 180.f * 3.14159265358979323846) : (float)c.angle_resolution / 180.f * 3.14159265358979323846f;
         plane_h0.resize(3 * (Nh + 1));
         plane_v0.resize(3 * (Nv + 1));
         plane_h = plane_h0;

@@ -24,7 +24,7 @@ class Config(C.Structure):
                 ("neighbor_n", C.c_int32), ("model", C.c_int32), ("prediction_times", C.c_int32),
                 ("future_time", C.c_float * 8), ("occlusion_margin", C.c_float), ("init_particle_num", C.c_int32),
                 ("init_weight", C.c_float), ("table_seed", C.c_uint64), ("uniform_seed", C.c_uint64),
-                ("gaussian_table_size", C.c_int32), ("obs_max_per_pyramid", C.c_int32)]
+                ("gaussian_table_size", C.c_int32), ("obs_max_per_pyramid", C.c_int32), ("pi_is_double", C.c_int32)]
 
 
 def make_config(cfg, seed=1, init_particles=0, init_weight=0.01, safe_ppv=0, safe_pyramid=0, table_size=10000000):
@@ -46,6 +46,7 @@ def make_config(cfg, seed=1, init_particles=0, init_weight=0.01, safe_ppv=0, saf
     c.uniform_seed = seed
     c.gaussian_table_size = table_size
     c.obs_max_per_pyramid = 100
+    c.pi_is_double = 0 if cfg["header"] == "dsp_dynamic.h" else 1
     return c
 
 

@@ -187,6 +187,8 @@ int ref_dump_particles(int *ids, float *vals, int cap) {
             }
     return n;
 }
+// the raw 9 floats of one slot, live or not (a vanished particle keeps its data, only the flag is cleared): for debugging
+void ref_raw_slot(int v, int s, float *out9) { std::memcpy(out9, &voxels_with_particle[v][s][0], 9 * sizeof(float)); }
 void ref_dump_voxel_objects(float *out) {
     std::memcpy(out, &voxels_objects_number[0][0], sizeof(float) * (size_t)VOXEL_NUM * voxels_objects_number_dimension);
 }

@@ -15,6 +15,12 @@ def same(a, b):
 def compare_state(ref, gpu, check_future_exact=False, future_rtol=2e-6, label=""):
     """ref: RefMap or OracleMap; gpu: dspmap_b200.DSPMap. Returns a list of human-readable mismatch descriptions."""
     bad = []
+    if hasattr(ref, "plane_normals") and hasattr(gpu, "plane_normals"):
+        # the rotated boundary-plane normals decide the pyramid of every particle and point; a 1-ulp difference flips one particle
+        # in a few hundred thousand (that is how a fp32 / fp64 pi mix-up showed, 36 frames into the cfg2 stream)
+        (rh, rv), (gh, gv) = ref.plane_normals(), gpu.plane_normals()
+        if not (same(rh, gh) and same(rv, gv)):
+            bad.append("%s boundary-plane normals differ in %d words" % (label, int((bits(rh) != bits(gh)).sum() + (bits(rv) != bits(gv)).sum())))
     rc, rm, rp = ref.observations()
     gc, gm, gp = gpu.observations()
     if not same(rc, gc):

@@ -31,6 +31,27 @@ def test_restatement_reproduces_reference_golden(name, frames, initp):
 LIVE = [("tiny_dyn", 8, 0), ("tiny_mn", 6, 0), ("tiny_static", 6, 0), ("tiny_mn", 4, 2000), ("cfg1", 4, 0)]
 
 
+def test_restatement_equals_reference_on_the_bench_stream_including_the_plane_normals():
+    """cfg2 on bench.py's stream (seed 1), 8 frames.  Frame 6 holds a particle within 1e-7 of a pyramid boundary plane: it
+    lands in the reference's pyramid only if the plane normals are the reference's to the last bit, i.e. if the angular
+    resolution in radians is the fp32 product dsp_dynamic.h:543 forms with glibc's float M_PIf32 (dspmap_config.pi_is_double)."""
+    name = "cfg2"
+    if not refmap.available(name):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    cfg = CONFIGS[name]
+    st = make_stream(cfg, seed=1, frames=8)
+    r, o = refmap.RefMap(name, seed=7), OracleMap(cfg, seed=7)
+    for f in range(8):
+        r.update(st["points"][f], st["pos"][f], st["t"][f], st["quat"][f])
+        o.update(st["points"][f], st["pos"][f], st["t"][f], st["quat"][f], tagged=r.tagged_cloud())
+        for x, y in zip(r.plane_normals(), o.plane_normals()):
+            assert same(x, y), "frame %d boundary-plane normals" % f
+        for x, y in zip(r.pyramid_lists(), o.pyramid_lists()):
+            assert same(x, y), "frame %d pyramid lists" % f
+        for x, y in zip(r.particles(), o.particles()):
+            assert same(x, y), "frame %d particles" % f
+
+
 @pytest.mark.parametrize("name,frames,initp", LIVE)
 def test_restatement_equals_reference_live(name, frames, initp):
     if not refmap.available(name):
@@ -53,6 +74,8 @@ def test_restatement_equals_reference_live(name, frames, initp):
             assert same(x, y), "frame %d pyramid lists" % f
         assert same(r.voxel_objects(), o.voxel_objects()), "frame %d voxel objects" % f
         assert np.array_equal(r.cursors()[:3], o.cursors()[:3])
+        for x, y in zip(r.plane_normals(), o.plane_normals()):
+            assert same(x, y), "frame %d boundary-plane normals" % f
         if f % 2 == 0:
             (rx, rf), (ox, of) = r.occupancy(0.2), o.occupancy(0.2)
             assert same(rx, ox) and same(rf, of)

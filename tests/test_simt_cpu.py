@@ -27,3 +27,11 @@ def build_and_run(check, inc, kernels, legacy=(), timeout=600, defines=(), tag="
     r = subprocess.run([exe], capture_output=True, text=True, timeout=timeout)
     assert r.returncode == 0, r.stdout + r.stderr
     return r.stdout
+
+
+def test_resampling_kernel_equals_the_round1_kernel():
+    """k_resample (a warp walks RS_VPW voxels, one lane per voxel, over a shared-memory tile) against the warp-per-voxel kernel
+    of round 1: particles, masks, occupancy / mean velocity, future grid and counters, bit for bit, on random voxels (empty,
+    sparse, above MAX, full, heavy-tailed weights, weights below 1e-3, all four flag values)."""
+    out = build_and_run("check_resample", "resample.inc", ["rs_warp_bytes", "k_resample"], legacy=["k_resample"], defines=("GRID=3",))
+    assert out.count("identical") == 6 and "DIFFERENT" not in out
