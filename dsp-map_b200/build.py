@@ -31,14 +31,19 @@ def stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not stale():
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines / out: a compile-time variant (-DNAME=value ...) written to another path, for A/B runs on the GPU box."""
+    if out is None and not force and not stale():
         return SO
     os.makedirs(OUT, exist_ok=True)
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + sources() + ["-o", SO]
+    target = out or SO
+    cmd = [NVCC] + FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + sources() + ["-o", target]
     subprocess.check_call(cmd)
-    return SO
+    return target
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    # build.py [--force] [-v] [--out PATH -DNAME=value ...]
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    out = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else None
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, out=out))

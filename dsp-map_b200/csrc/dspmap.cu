@@ -446,9 +446,8 @@ int enqueue_frame_a(dspmap *m, const FrameConst &fc, const float *d_pts, const f
     LAUNCH(m, FAM_PYRAMID, k_pyr_sort, std::min(mc.P, kSMs * 3), 512, PYR_SORT_CAP * sizeof(u64), mc, dp, fc.Pd);
     CK(cudaStreamWaitEvent(m->stream, m->ev_join_obs, 0));
     if (fc.stage_limit >= 2) {
-        LAUNCH(m, FAM_CK, k_pair_prep, grid_for(mc.P, B), B, 0, mc, dp);
-        LAUNCH(m, FAM_CK, k_scan_small, 2, 1024, 0, ScanJobs{{ScanJob{dp.pairs, dp.rowbase, nullptr, 0, mc.P}, ScanJob{dp.chunks, dp.chunk_off, nullptr, 0, mc.P}, ScanJob{}}});
-        LAUNCH(m, FAM_CK, k_pair_eval, kSMs * 2, EVAL_THREADS, sizeof(float) * (DSP_LUT_HALF + 3 + (EVAL_THREADS / 32) * 32 * TILE_LD), mc, fc, dp, 0);
+        LAUNCH(m, FAM_CK, k_pair_prep, 1, 1024, 0, mc, dp);
+        LAUNCH(m, FAM_CK, k_pair_eval, kSMs * 2, EVAL_THREADS, EVAL_SMEM_BYTES, mc, fc, dp, 0);
         LAUNCH(m, FAM_CK, k_cz_wide, std::min(mc.P, kSMs * 3), 256, sizeof(float) * (2 * (8192 + 8) + 2 * 128), mc, fc, dp);
         size_t smem4 = sizeof(float) * (DSP_LUT_HALF + 3 + K4_TERMS) + sizeof(float4) * (256 + mc.OBS);
         if (m->fallback_armed) LAUNCH(m, FAM_CK, k_ck, std::min(mc.P, kSMs * 2), K4_THREADS, smem4, mc, fc, dp);  // returns at once when the pair buffer is used
@@ -493,7 +492,7 @@ int enqueue_frame_b(dspmap *m, const FrameConst &fc, const float *d_tagged) {
     }
     if (fc.stage_limit >= 4) {
         LAUNCH(m, FAM_RESAMPLE, k_voxel_list, grid_for(mc.V, B), B, 0, mc, dp);
-        LAUNCH(m, FAM_RESAMPLE, k_resample, kSMs * 4, 32 * RS_WARPS, RS_WARPS * rs_warp_bytes(mc.S), mc, fc, dp);
+        LAUNCH(m, FAM_RESAMPLE, k_resample, kSMs * (RS_VPW >= 4 ? 4 : 16), 32 * RS_WARPS, RS_WARPS * rs_warp_bytes(mc.S), mc, fc, dp);
     }
     if (m->norm_join_pending) {  // no newborn kernels this frame: k_norm must still be over before the next frame resets its outputs
         CK(cudaStreamWaitEvent(m->stream, m->ev_join, 0));
@@ -731,7 +730,7 @@ int dspmap_create(const dspmap_config *cfg, dspmap **out) {
     A(dp.PSkey, CL); A(dp.PSaddr, CL); A(dp.LA, CL); A(dp.LP, CL); A(dp.PW, CL);
     mc.cap_pairs = 512ll << 20;  // 2 GB of fp32 pair terms (of 180 GB); larger frames fall back to the recompute kernels
     A(dp.G, (size_t)mc.cap_pairs + 64); A(dp.cum, P * mc.NBW); A(dp.totlen, P); A(dp.pairs, P + 1); A(dp.rowbase, P + 1);
-    A(dp.chunks, P + 1); A(dp.chunk_off, P + 1);
+    A(dp.chunks, P + 1); A(dp.chunk_off, P + 1); A(dp.chunk_pyr, CL / 32 + P + 1);
     A(dp.NPC, MP); A(dp.ninmap, MP + 1); A(dp.nrank, MP + 1); A(dp.nstatic, MP); A(dp.nvcnt, MP + 1); A(dp.nrcnt, MP + 1);
     A(dp.nvoff, MP + 1); A(dp.nroff, MP + 1); A(dp.nimask, MP);
     A(dp.ccnt, V); A(dp.cfill, V); A(dp.cbase, V); A(dp.cowner, V);
@@ -739,13 +738,14 @@ int dspmap_create(const dspmap_config *cfg, dspmap **out) {
     float *d_ptab, *d_vtab, *d_lut, *d_planes0, *d_pts, *d_tagged;
     int *d_nbr;
     A(d_ptab, mc.G); A(d_vtab, mc.G); A(d_lut, DSP_LUT_HALF); A(d_planes0, 3 * (mc.Nh + mc.Nv + 2)); A(dp.planes, 3 * (mc.Nh + mc.Nv + 2));
-    A(d_nbr, P * mc.NBW); A(d_pts, MP * 3); A(d_tagged, MP * 7);
+    int *d_nbrev;
+    A(d_nbr, P * mc.NBW); A(d_nbrev, P * mc.NBW); A(d_pts, MP * 3); A(d_tagged, MP * 7);
     m->occ_blocks = (int)((V + OCC_BLOCK - 1) / OCC_BLOCK);
     A(m->d_blockcnt, m->occ_blocks + 1); A(m->d_blockoff, m->occ_blocks + 1); A(m->d_count, 1); A(m->d_xyz, V * 3);
     A(m->d_future, V * std::max(mc.T, 1));
 #undef A
     if (rc != DSPMAP_OK) { dspmap_destroy(m); return rc; }
-    dp.ptab = d_ptab; dp.vtab = d_vtab; dp.lut = d_lut; dp.planes0 = d_planes0; dp.nbr = d_nbr;
+    dp.ptab = d_ptab; dp.vtab = d_vtab; dp.lut = d_lut; dp.planes0 = d_planes0; dp.nbr = d_nbr; dp.nbrev = d_nbrev;
     dp.pts = d_pts; dp.tagged = d_tagged;
     if (ensure_cand_capacity(m) != DSPMAP_OK) { dspmap_destroy(m); return DSPMAP_E_CUDA; }
     CKM(cudaMallocHost(&m->h_pts, sizeof(float) * MP * 3));
@@ -767,6 +767,14 @@ int dspmap_create(const dspmap_config *cfg, dspmap **out) {
             }
         m->nbr[(size_t)p * mc.NBW] = n;
     }
+    // where each pyramid sits in its neighbours' lists (the relation is symmetric)
+    std::vector<int> nbrev(P * mc.NBW, 0);
+    for (int a = 0; a < mc.P; a++)
+        for (int ns = 0; ns < m->nbr[(size_t)a * mc.NBW]; ++ns) {
+            const int i = m->nbr[(size_t)a * mc.NBW + 1 + ns];
+            for (int k = 0; k < m->nbr[(size_t)i * mc.NBW]; ++k)
+                if (m->nbr[(size_t)i * mc.NBW + 1 + k] == a) nbrev[(size_t)a * mc.NBW + 1 + ns] = k;
+        }
     // PDF table (:1282-1292), host libm exactly as the reference evaluates it; only indices 10000..20000 are kept:
     // the table is symmetric (x = (i-10000)*0.001f negates exactly and powf(x,2) is even), checked here.
     m->lut.resize(DSP_LUT_HALF);
@@ -788,6 +796,8 @@ int dspmap_create(const dspmap_config *cfg, dspmap **out) {
     CKM(cudaMemcpyAsync(d_lut, m->lut.data(), sizeof(float) * DSP_LUT_HALF, cudaMemcpyHostToDevice, m->stream));
     CKM(cudaMemcpyAsync(d_planes0, m->planes0.data(), sizeof(float) * m->planes0.size(), cudaMemcpyHostToDevice, m->stream));
     CKM(cudaMemcpyAsync(d_nbr, m->nbr.data(), sizeof(int) * m->nbr.size(), cudaMemcpyHostToDevice, m->stream));
+    CKM(cudaMemcpyAsync(d_nbrev, nbrev.data(), sizeof(int) * nbrev.size(), cudaMemcpyHostToDevice, m->stream));
+    CKM(cudaStreamSynchronize(m->stream));  // nbrev is a local
     CKM(cudaFuncSetAttribute(k_pyr_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PYR_SORT_CAP * sizeof(u64))));
     CKM(cudaFuncSetAttribute(k_ck, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CKM(cudaFuncSetAttribute(k_pair_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
@@ -1060,15 +1070,14 @@ int dspmap_shard_phase(dspmap *m, int phase, int n, const float *d_pts, float px
         LAUNCH(m, FAM_PYRAMID, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{dp.pcount, dp.poff, nullptr, 0, mc.P}, ScanJob{}, ScanJob{}}});
         LAUNCH(m, FAM_PYRAMID, k_shard_fov_gathered, kSMs * 8, B, 0, mc, dp, 1);
         LAUNCH(m, FAM_PYRAMID, k_pyr_sort, std::min(mc.P, kSMs * 3), 512, PYR_SORT_CAP * sizeof(u64), mc, dp, fc.Pd);
-        LAUNCH(m, FAM_CK, k_pair_prep, grid_for(mc.P, B), B, 0, mc, dp);
-        LAUNCH(m, FAM_CK, k_scan_small, 2, 1024, 0, ScanJobs{{ScanJob{dp.pairs, dp.rowbase, nullptr, 0, mc.P}, ScanJob{dp.chunks, dp.chunk_off, nullptr, 0, mc.P}, ScanJob{}}});
+        LAUNCH(m, FAM_CK, k_pair_prep, 1, 1024, 0, mc, dp);
         LAUNCH(m, FAM_CK, k_shard_zero, kSMs * 2, B, 0, mc, fc, dp, 0);
-        LAUNCH(m, FAM_CK, k_pair_eval, kSMs * 2, EVAL_THREADS, sizeof(float) * (DSP_LUT_HALF + 3 + (EVAL_THREADS / 32) * 32 * TILE_LD), mc, fc, dp, 1);
+        LAUNCH(m, FAM_CK, k_pair_eval, kSMs * 2, EVAL_THREADS, EVAL_SMEM_BYTES, mc, fc, dp, 1);
         LAUNCH(m, FAM_CK, k_cz_wide, std::min(mc.P, kSMs * 3), 256, sizeof(float) * (2 * (8192 + 8) + 2 * 128), mc, fc, dp);
     } else if (phase == 3) {
         dp.tagged = d_tagged;
         LAUNCH(m, FAM_WEIGHT, k_shard_zero, kSMs * 2, B, 0, mc, fc, dp, 1);
-        LAUNCH(m, FAM_WEIGHT, k_pair_eval, kSMs * 2, EVAL_THREADS, sizeof(float) * (DSP_LUT_HALF + 3 + (EVAL_THREADS / 32) * 32 * TILE_LD), mc, fc, dp, 2);
+        LAUNCH(m, FAM_WEIGHT, k_pair_eval, kSMs * 2, EVAL_THREADS, EVAL_SMEM_BYTES, mc, fc, dp, 2);
         LAUNCH(m, FAM_WEIGHT, k_weight2, kSMs * 8, W2_THREADS, 0, mc, fc, dp);
         LAUNCH(m, FAM_WEIGHT, k_weight2w, kSMs * 6, W2W_THREADS, 0, mc, fc, dp);
     } else if (phase == 4) {  // owners take their new weights; the newborn split reads them (dsp_dynamic.h:829-866)
@@ -1096,7 +1105,7 @@ int dspmap_shard_phase(dspmap *m, int phase, int n, const float *d_pts, float px
             newborn_ran = 1;
         }
         LAUNCH(m, FAM_RESAMPLE, k_voxel_list, grid_for(mc.V, B), B, 0, mc, dp);
-        LAUNCH(m, FAM_RESAMPLE, k_resample, kSMs * 4, 32 * RS_WARPS, RS_WARPS * rs_warp_bytes(mc.S), mc, fc, dp);
+        LAUNCH(m, FAM_RESAMPLE, k_resample, kSMs * (RS_VPW >= 4 ? 4 : 16), 32 * RS_WARPS, RS_WARPS * rs_warp_bytes(mc.S), mc, fc, dp);
         LAUNCH(m, FAM_CLEANUP, k_cleanup, kSMs * 2, B, 0, mc, fc, dp, newborn_ran, 0);
         CK(cudaMemcpyAsync(m->h_state, m->dp.st, sizeof(DevState), cudaMemcpyDeviceToHost, m->stream));
         CK(cudaEventRecord(m->ev_state, m->stream));

@@ -864,10 +864,47 @@ __global__ void __launch_bounds__(K5_THREADS) k_weight(MapConst mc, FrameConst f
 //           particle in the concatenation of i's neighbour lists (neighbour-table order, list order)
 //   k_cz_chain reads a row sequentially (j); k_weight2 reads it with consecutive lanes = consecutive particles.
 // ------------------------------------------------------------------------------------------------------------
-__global__ void k_pair_prep(MapConst mc, DevPtrs dp) {
+// One block: per point pyramid i the offsets of its neighbours' lists in the concatenation (cum), the block's size in G and
+// the number of 32-particle chunks of its own list; then the two exclusive scans (rowbase, chunk_off) and the chunk -> pyramid
+// table the pair-buffer kernels index with their queue tickets.  (Round 1 ran this as k_pair_prep + a scan launch and let
+// every work item find its pyramid by binary search over chunk_off.)
+__device__ __forceinline__ void block_exclusive_scan(const int *in, int *out, int n, int *wsum) {
+    const int T = blockDim.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = T >> 5;
+    const int per = (n + T - 1) / T;
+    const int b0 = min(n, (int)threadIdx.x * per), b1 = min(n, b0 + per);
+    int s = 0;
+    for (int i = b0; i < b1; ++i) s += in[i];
+    int incl = s;
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(FULLMASK, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) wsum[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        const int y0 = lane < nw ? wsum[lane] : 0;
+        int y = y0;
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(FULLMASK, y, d);
+            if (lane >= d) y += t;
+        }
+        wsum[lane] = y - y0;  // exclusive prefix of the warp totals
+    }
+    __syncthreads();
+    int run = wsum[wid] + incl - s;
+    for (int i = b0; i < b1; ++i) {
+        const int x = in[i];
+        out[i] = run;
+        run += x;
+    }
+    if ((int)threadIdx.x == T - 1) out[n] = run;
+    __syncthreads();  // the warp totals may be reused by a following scan; out[] is visible to the whole block
+}
+__global__ void __launch_bounds__(1024) k_pair_prep(MapConst mc, DevPtrs dp) {
     pdl_enter();
+    __shared__ int wsum[32];
     unsigned long long local = 0ull;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < mc.P; i += gridDim.x * blockDim.x) {
+    for (int i = threadIdx.x; i < mc.P; i += blockDim.x) {
         const int np = min(dp.obs_cnt[i], mc.OBS - 1), nn = dp.nbr[i * mc.NBW];
         int c = 0;
         for (int ns = 0; ns < nn; ++ns) {
@@ -881,6 +918,13 @@ __global__ void k_pair_prep(MapConst mc, DevPtrs dp) {
         dp.chunks[i] = (dp.plen[i] + 31) >> 5;
     }
     if (local) atomicAdd(&dp.st->total_pairs, local);
+    __syncthreads();
+    block_exclusive_scan(dp.pairs, dp.rowbase, mc.P, wsum);
+    block_exclusive_scan(dp.chunks, dp.chunk_off, mc.P, wsum);
+    for (int i = threadIdx.x; i < mc.P; i += blockDim.x) {
+        const int c0 = dp.chunk_off[i], c1 = c0 + dp.chunks[i];
+        for (int c = c0; c < c1; ++c) dp.chunk_pyr[c] = i;
+    }
 }
 // position of pyramid a inside pyramid b's neighbour list (the relation is symmetric)
 __device__ __forceinline__ int nb_index_of(const MapConst &mc, const DevPtrs &dp, int b, int a) {
@@ -898,53 +942,94 @@ __device__ __forceinline__ int chunk_to_pyramid(const int *chunk_off, int P, int
     return lo;
 }
 #define EVAL_THREADS 512
-#define TILE_LD 33  // per-warp 32 x 32 staging tile, padded
+#define TILE_LD 33  // per-warp 32 x 32 staging tile of k_weight2w, padded
+#define EVAL_GROUP 3     // neighbour pyramids per work item
+#define EVAL_PTS 112     // float4 slots for a pyramid's points (OBS <= 128 is checked at create time; the default is 100)
+#define EVAL_WARP_F4 (128 + 32)  // shared memory of one warp in float4: points, then the chunk's 32 particles
+#define EVAL_SMEM_BYTES (((DSP_LUT_HALF + 3 + 31) & ~31) * 4 + (EVAL_THREADS / 32) * EVAL_WARP_F4 * 16 + (EVAL_THREADS / 32) * 8)
+// queryNormalPDF's table index (dsp_dynamic.h:1294-1300) with the clamp moved behind the conversion:
+//     |trunc(clamp(cx, -9.9, 9.9) * 1000 + 10000) - 10000|  ==  min(|trunc(cx * 1000 + 10000) - 10000|, 9900)
+// for EVERY finite float cx (the conversion saturates; checked exhaustively over all 2^32 bit patterns by
+// tests/test_host.py::test_pdf_index_clamp_can_move_behind_the_conversion), which turns three float compare / select
+// instructions and a three-instruction absolute value into IABS + IMNMX.
+__device__ __forceinline__ float dsp_pdf_i(const float *lut, float x, float mu, const FrameConst &fc) {
+    const float cx = fc.fast_sigma ? dsp_div_known(x - mu, fc.sigma, fc.sigma_r) : (x - mu) / fc.sigma;
+    const int i = __float2int_rz(cx * 1000 + 10000);
+    const int j = (int)((unsigned)i - 10000u);
+    return lut[min(abs(j), 9900)];
+}
+// The pair evaluation.  A work item is one chunk of 32 particles of pyramid a x up to EVAL_GROUP of the point pyramids i that
+// see it; the (particle, point) tile of one (chunk, i) is nrows x np values that lie CONTIGUOUSLY in G (row-major rows of
+// np), so the warp walks it flat: lane l takes pairs l, l + 32, ... and every store is a full coalesced line — no
+// transposing tile.  The pyramid's observation points and the chunk's particles are staged in the warp's shared memory by
+// 1-D bulk copies (cp.async.bulk, completion on an mbarrier): "per-pyramid observation points staged in shared memory via
+// TMA" (BASELINE.json north_star).  Round 1's kernel read every point with a global load in front of its first use (23 % of
+// all stall samples) and spent 20 % of its instructions on the transposed store.
 // mode 0: all items; sharded: mode 1 = rows of the point pyramids this rank computes C_z for (i % nranks == rank),
 // mode 2 = rows of the particle chunks this rank computes weights for (chunk % nranks == rank)
 __global__ void __launch_bounds__(EVAL_THREADS) k_pair_eval(MapConst mc, FrameConst fc, DevPtrs dp, int mode) {
-    extern __shared__ float sm[];
+    extern __shared__ __align__(128) float sm[];
     float *lut = sm;
-    float *tile = sm + (DSP_LUT_HALF + 3) + (threadIdx.x >> 5) * (32 * TILE_LD);
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+    float4 *s_pts = reinterpret_cast<float4 *>(sm + ((DSP_LUT_HALF + 3 + 31) & ~31)) + wl * EVAL_WARP_F4;
+    float4 *s_par = s_pts + 128;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<float4 *>(sm + ((DSP_LUT_HALF + 3 + 31) & ~31)) + (EVAL_THREADS / 32) * EVAL_WARP_F4);
+    uint64_t *bar = bars + wl;
     pdl_trigger();
     for (int i = threadIdx.x; i < DSP_LUT_HALF; i += blockDim.x) lut[i] = dp.lut[i];  // constant after create: staged before the wait
+    if (lane == 0) {
+        cuda::ptx::mbarrier_init(bar, 1);  // one arrival (the issuing lane's expect_tx) + the bytes
+        cuda::ptx::fence_mbarrier_init(cuda::ptx::sem_release, cuda::ptx::scope_cluster);
+    }
     pdl_wait();
     if (!use_pair_buffer(mc, dp)) return;
     __syncthreads();
-    const int lane = threadIdx.x & 31;
+    unsigned phase = 0u;
     const int nchunks = dp.chunk_off[mc.P];
-    const int items = nchunks * mc.NB;
+    // (one queue ticket per (chunk, neighbour) would be ~21 000 same-address atomics per frame at cfg2)
+    const int groups = (mc.NB + EVAL_GROUP - 1) / EVAL_GROUP;
+    const int items = nchunks * groups;
     for (;;) {
         int it = 0;
         if (lane == 0) it = atomicAdd(mode == 2 ? &dp.st->work_eval2 : &dp.st->work_eval, 1);
         it = __shfl_sync(FULLMASK, it, 0);
         if (it >= items) break;
-        const int c = it / mc.NB, ns = it - c * mc.NB;
+        const int c = it / groups, g0 = (it - c * groups) * EVAL_GROUP;
         if (mode == 2 && c % mc.nranks != mc.rank) continue;
-        const int a = chunk_to_pyramid(dp.chunk_off, mc.P, c);
-        if (ns >= dp.nbr[a * mc.NBW]) continue;
-        const int i = dp.nbr[a * mc.NBW + 1 + ns];  // a point pyramid that sees pyramid a
-        if (mode == 1 && i % mc.nranks != mc.rank) continue;
-        const int np = min(dp.obs_cnt[i], mc.OBS - 1);
-        if (np == 0) continue;
+        const int a = dp.chunk_pyr[c];
+        const int nn = dp.nbr[a * mc.NBW];
+        if (g0 >= nn) continue;
         const int k0 = (c - dp.chunk_off[a]) << 5;
-        const int ln = dp.plen[a];
-        const int nrows = min(32, ln - k0);
-        const float4 p = lane < nrows ? dp.LP[dp.poff[a] + k0 + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
-        float *gb = dp.G + (size_t)dp.rowbase[i] + (size_t)(dp.cum[i * mc.NBW + nb_index_of(mc, dp, i, a)] + k0) * np;
-        const float4 *zs = dp.OBSP + (size_t)i * mc.OBS;
-        for (int z0 = 0; z0 < np; z0 += 32) {
-            const int nsub = min(32, np - z0);
-            for (int zl = 0; zl < nsub; ++zl) {
-                const float4 o = zs[z0 + zl];
-                tile[lane * TILE_LD + zl] = dsp_pdf_f(lut, p.x, o.x, fc) * dsp_pdf_f(lut, p.y, o.y, fc) * dsp_pdf_f(lut, p.z, o.z, fc);
+        const int nrows = min(32, dp.plen[a] - k0);
+        bool have_particles = false;
+        for (int ns = g0; ns < min(nn, g0 + EVAL_GROUP); ++ns) {
+            const int i = dp.nbr[a * mc.NBW + 1 + ns];  // a point pyramid that sees pyramid a
+            if (mode == 1 && i % mc.nranks != mc.rank) continue;
+            const int np = min(dp.obs_cnt[i], mc.OBS - 1);
+            if (np == 0) continue;
+            __syncwarp();  // every lane is done with the previous tile's points
+            if (lane == 0) {
+                cuda::ptx::fence_proxy_async(cuda::ptx::space_shared);  // earlier generic reads of the buffers before the async writes
+                const unsigned bytes = (unsigned)np * 16u + (have_particles ? 0u : (unsigned)nrows * 16u);
+                cuda::ptx::mbarrier_arrive_expect_tx(cuda::ptx::sem_release, cuda::ptx::scope_cta, cuda::ptx::space_shared, bar, bytes);
+                cuda::ptx::cp_async_bulk(cuda::ptx::space_cluster, cuda::ptx::space_global, s_pts, dp.OBSP + (size_t)i * mc.OBS, (unsigned)np * 16u, bar);
+                if (!have_particles)
+                    cuda::ptx::cp_async_bulk(cuda::ptx::space_cluster, cuda::ptx::space_global, s_par, dp.LP + dp.poff[a] + k0, (unsigned)nrows * 16u, bar);
             }
-            __syncwarp();
-            if (lane < nsub) {
-                float *dst = gb + z0 + lane;
-#pragma unroll 8
-                for (int r = 0; r < nrows; ++r) dst[(size_t)r * np] = tile[r * TILE_LD + lane];
+            have_particles = true;
+            // the tile's place in G while the copies fly
+            float *gb = dp.G + (size_t)dp.rowbase[i] + (size_t)(dp.cum[i * mc.NBW + dp.nbrev[a * mc.NBW + 1 + ns]] + k0) * np;
+            const int total = nrows * np;
+            const unsigned magic = np > 1 ? 0xffffffffu / (unsigned)np + 1u : 0u;  // exact f / np for f < 65536
+            while (!cuda::ptx::mbarrier_try_wait_parity(bar, phase)) {}
+            phase ^= 1u;
+#pragma unroll 2
+            for (int f = lane; f < total; f += 32) {
+                const int r = np > 1 ? (int)__umulhi((unsigned)f, magic) : f;
+                const int z = f - r * np;
+                const float4 p = s_par[r], o = s_pts[z];
+                gb[f] = dsp_pdf_i(lut, p.x, o.x, fc) * dsp_pdf_i(lut, p.y, o.y, fc) * dsp_pdf_i(lut, p.z, o.z, fc);
             }
-            __syncwarp();
         }
     }
 }
@@ -1610,8 +1695,12 @@ __global__ void k_voxel_list(MapConst mc, DevPtrs dp) {
 //     (Round 1's kernel gave a whole warp to one voxel and fetched every operand of the walk with find-first-set +
 //     shuffle: 2 450 warp instructions per voxel, 35 us at cfg2.)
 // ------------------------------------------------------------------------------------------------------------
+#ifndef RS_VPW
 #define RS_VPW 8     // voxels per warp
+#endif
+#ifndef RS_WARPS
 #define RS_WARPS 4   // warps per block
+#endif
 // shared memory of one warp: tile[RS_VPW][S + 1] float4 | verd[RS_VPW][S] float | tagb, dsrc, ddst [RS_VPW][S] u8 | wafter[RS_VPW] float
 __host__ __device__ __forceinline__ size_t rs_warp_bytes(int S) {
     return ((size_t)RS_VPW * (S + 1) * 16 + (size_t)RS_VPW * S * 4 + (size_t)RS_VPW * S * 3 + (size_t)RS_VPW * 4 + 15) & ~(size_t)15;
@@ -1788,11 +1877,29 @@ __global__ void __launch_bounds__(32 * RS_WARPS) k_resample(MapConst mc, FrameCo
             }
         }
     }
-    if (c_pre | c_low) {  // (lanes that walked voxels hold the counts)
-        atomicAdd(&dp.st->n_pre, c_pre);
-        atomicAdd(&dp.st->n_old, c_old);
-        atomicAdd(&dp.st->n_out, c_out);
-        if (c_low) atomicAdd(&dp.st->n_low_weight, c_low);
+    // the walking lanes hold the counts: one atomic per counter and BLOCK (same-address atomics serialise in L2; a few
+    // thousand of them per counter were the longest part of this kernel)
+    __shared__ int s_cnt[4];
+    if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    for (int d = 16; d > 0; d >>= 1) {
+        c_pre += __shfl_down_sync(FULLMASK, c_pre, d);
+        c_old += __shfl_down_sync(FULLMASK, c_old, d);
+        c_out += __shfl_down_sync(FULLMASK, c_out, d);
+        c_low += __shfl_down_sync(FULLMASK, c_low, d);
+    }
+    if (lane == 0 && (c_pre | c_low)) {
+        atomicAdd(&s_cnt[0], c_pre);
+        atomicAdd(&s_cnt[1], c_old);
+        atomicAdd(&s_cnt[2], c_out);
+        atomicAdd(&s_cnt[3], c_low);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && (s_cnt[0] | s_cnt[3])) {
+        atomicAdd(&dp.st->n_pre, s_cnt[0]);
+        atomicAdd(&dp.st->n_old, s_cnt[1]);
+        atomicAdd(&dp.st->n_out, s_cnt[2]);
+        if (s_cnt[3]) atomicAdd(&dp.st->n_low_weight, s_cnt[3]);
     }
 }
 

@@ -73,6 +73,8 @@ struct DevPtrs {
     // pair buffer: G[rowbase[i] + z * totlen[i] + j] = g(particle j of pyramid i's concatenated neighbour lists; point z of i)
     float *G;
     int *cum, *totlen, *pairs, *rowbase, *chunks, *chunk_off;
+    int *chunk_pyr;     // chunk -> pyramid (k_pair_prep)
+    const int *nbrev;   // [P][NBW]: nbrev[a][1 + ns] = position of a in the neighbour list of nbr[a][1 + ns] (host-built)
     // newborn
     const float *tagged;  // n_tagged x 7, world frame
     float4 *NPC;          // corrected point + voxel id

@@ -48,9 +48,10 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise DSPMapError("%s is missing: build it with `python dsp-map_b200/build.py` (there is no CPU fallback)" % LIB_PATH)
-    L = C.CDLL(LIB_PATH)
+    path = os.environ.get("DSPMAP_B200_LIB") or LIB_PATH   # (the override serves A/B runs of compile-time variants: tests/ab_variants.sh)
+    if not os.path.exists(path):
+        raise DSPMapError("%s is missing: build it with `python dsp-map_b200/build.py` (there is no CPU fallback)" % path)
+    L = C.CDLL(path)
     vp, f, i, fp, ip = C.c_void_p, C.c_float, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int32)
     sig = {
         "dspmap_default_config": (None, [C.POINTER(Config)]),
