@@ -40,8 +40,11 @@ struct ProfSlot {
 
 }  // namespace
 
+struct dspmap_shard;  // shard_host.inc
+
 struct dspmap {
     dspmap_config cfg;
+    dspmap_shard *shard = nullptr;  // part of a sharded map orchestrated by the library (dspmap_shard_init / _init_local)
     MapConst mc;
     DevPtrs dp;
     cudaStream_t stream = nullptr, own_stream = nullptr, side = nullptr, nb = nullptr;  // frame; observation binning + normaliser; early newborn placement
@@ -106,6 +109,7 @@ struct dspmap {
     bool vz_mode = false;
     int vz_blocks = 0;
     // the recompute kernels (k_ck / k_weight) are launched only while the pair buffer may overflow
+    bool pyr_scan_fused = true;   // the pyramid table fits the scatter kernel's shared memory
     bool fallback_armed = true;
     bool fallback_forced = false;  // a frame overran the pair buffer without the recompute kernels: keep them armed from now on
     int overflow_latched = 0;      // capacity overruns seen on the device and not yet reported to the caller (codes OR-ed)
@@ -441,14 +445,22 @@ int enqueue_frame_a(dspmap *m, const FrameConst &fc, const float *d_pts, const f
     // With a device-resident newborn input the early newborn kernels (they need the cloud, the noise table and these masks)
     // run beside the observation passes; with a host cloud they are enqueued by enqueue_frame_b, once the cloud is there
     if (d_tagged_early && (rc_nb = enqueue_newborn_early(m, fc, d_tagged_early)) != DSPMAP_OK) return rc_nb;
-    LAUNCH(m, FAM_PYRAMID, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{dp.pcount, dp.poff, nullptr, 0, mc.P}, ScanJob{}, ScanJob{}}});
-    LAUNCH(m, FAM_PYRAMID, k_pyr_scatter, kSMs * 8, B, 0, dp);
+    if (m->pyr_scan_fused) {  // every block of the scatter kernel scans the pyramid counts itself (shared memory)
+        LAUNCH(m, FAM_PYRAMID, k_pyr_scatter, kSMs * 2, B, sizeof(int) * (mc.P + 1), mc, dp, 1);
+    } else {
+        LAUNCH(m, FAM_PYRAMID, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{dp.pcount, dp.poff, nullptr, 0, mc.P}, ScanJob{}, ScanJob{}}});
+        LAUNCH(m, FAM_PYRAMID, k_pyr_scatter, kSMs * 8, B, 0, mc, dp, 0);
+    }
     LAUNCH(m, FAM_PYRAMID, k_pyr_sort, std::min(mc.P, kSMs * 3), 512, PYR_SORT_CAP * sizeof(u64), mc, dp, fc.Pd);
     CK(cudaStreamWaitEvent(m->stream, m->ev_join_obs, 0));
     if (fc.stage_limit >= 2) {
         LAUNCH(m, FAM_CK, k_pair_prep, 1, 1024, 0, mc, dp);
         LAUNCH(m, FAM_CK, k_pair_eval, kSMs * 2, EVAL_THREADS, EVAL_SMEM_BYTES, mc, fc, dp, 0);
+#ifdef CZ_TMA
+        LAUNCH(m, FAM_CK, k_cz_chain_tma, std::min(mc.P, kSMs * 2), CZT_THREADS, CZT_SMEM_BYTES, mc, fc, dp);
+#else
         LAUNCH(m, FAM_CK, k_cz_wide, std::min(mc.P, kSMs * 3), 256, sizeof(float) * (2 * (8192 + 8) + 2 * 128), mc, fc, dp);
+#endif
         size_t smem4 = sizeof(float) * (DSP_LUT_HALF + 3 + K4_TERMS) + sizeof(float4) * (256 + mc.OBS);
         if (m->fallback_armed) LAUNCH(m, FAM_CK, k_ck, std::min(mc.P, kSMs * 2), K4_THREADS, smem4, mc, fc, dp);  // returns at once when the pair buffer is used
         if (fc.stage_limit >= 3) {  // the newborn normaliser is one long serial chain: run it beside the weight pass
@@ -459,8 +471,12 @@ int enqueue_frame_a(dspmap *m, const FrameConst &fc, const float *d_pts, const f
             ++m->launches_frame;
             CK(cudaEventRecord(m->ev_join, m->side));
         }
+#ifdef W3
+        LAUNCH(m, FAM_WEIGHT, k_weight3, kSMs * 2, 32 * W3_WARPS, w3_smem_bytes(mc.OBS), mc, fc, dp);
+#else
         LAUNCH(m, FAM_WEIGHT, k_weight2, kSMs * 8, W2_THREADS, 0, mc, fc, dp);
         LAUNCH(m, FAM_WEIGHT, k_weight2w, kSMs * 6, W2W_THREADS, 0, mc, fc, dp);
+#endif
         size_t smem5 = sizeof(float) * (DSP_LUT_HALF + 3) + sizeof(float4) * (size_t)mc.NB * (mc.OBS - 1);
         int chunks = (mc.L + K5_THREADS - 1) / K5_THREADS;
         if (m->fallback_armed) LAUNCH(m, FAM_WEIGHT, k_weight, kSMs * 2, K5_THREADS, smem5, mc, fc, dp, chunks);
@@ -799,14 +815,18 @@ int dspmap_create(const dspmap_config *cfg, dspmap **out) {
     CKM(cudaMemcpyAsync(d_nbrev, nbrev.data(), sizeof(int) * nbrev.size(), cudaMemcpyHostToDevice, m->stream));
     CKM(cudaStreamSynchronize(m->stream));  // nbrev is a local
     CKM(cudaFuncSetAttribute(k_pyr_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PYR_SORT_CAP * sizeof(u64))));
+    m->pyr_scan_fused = sizeof(int) * (size_t)(mc.P + 1) <= 200 * 1024;
+    if (m->pyr_scan_fused) CKM(cudaFuncSetAttribute(k_pyr_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(int) * (mc.P + 1))));
     CKM(cudaFuncSetAttribute(k_ck, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CKM(cudaFuncSetAttribute(k_pair_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     CKM(cudaFuncSetAttribute(k_cz_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    CKM(cudaFuncSetAttribute(k_cz_chain_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, CZT_SMEM_BYTES));
     // the three defaults that can be turned off for A/B measurements (profiles/r02_ab_switches.jsonl)
     m->pdl = !env_off("DSPMAP_PDL");
     m->est_thread = !env_off("DSPMAP_EST_THREAD");
     m->async_update = !env_off("DSPMAP_ASYNC_UPDATE");
     CKM(cudaFuncSetAttribute(k_weight, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CKM(cudaFuncSetAttribute(k_weight3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w3_smem_bytes(128)));
     CKM(cudaFuncSetAttribute(k_resample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RS_WARPS * rs_warp_bytes(DSP_MAX_SLOTS))));
     CKM(cudaStreamSynchronize(m->stream));
     if (gen_tables(m) != DSPMAP_OK) { dspmap_destroy(m); return DSPMAP_E_CUDA; }
@@ -831,11 +851,14 @@ int dspmap_create(const dspmap_config *cfg, dspmap **out) {
     return DSPMAP_OK;
 }
 
+void dspmap_shard_release(dspmap *m);
+
 void dspmap_destroy(dspmap *m) {
     if (!m) return;
     m->worker.stop();
     cudaSetDevice(m->cfg.device);
     cudaDeviceSynchronize();
+    dspmap_shard_release(m);
     if (m->pinned_user) cudaHostUnregister(m->pinned_user);
     for (void *p : m->allocs) cudaFree(p);
     if (m->h_pts) cudaFreeHost(m->h_pts);
@@ -1073,13 +1096,21 @@ int dspmap_shard_phase(dspmap *m, int phase, int n, const float *d_pts, float px
         LAUNCH(m, FAM_CK, k_pair_prep, 1, 1024, 0, mc, dp);
         LAUNCH(m, FAM_CK, k_shard_zero, kSMs * 2, B, 0, mc, fc, dp, 0);
         LAUNCH(m, FAM_CK, k_pair_eval, kSMs * 2, EVAL_THREADS, EVAL_SMEM_BYTES, mc, fc, dp, 1);
+#ifdef CZ_TMA
+        LAUNCH(m, FAM_CK, k_cz_chain_tma, std::min(mc.P, kSMs * 2), CZT_THREADS, CZT_SMEM_BYTES, mc, fc, dp);
+#else
         LAUNCH(m, FAM_CK, k_cz_wide, std::min(mc.P, kSMs * 3), 256, sizeof(float) * (2 * (8192 + 8) + 2 * 128), mc, fc, dp);
+#endif
     } else if (phase == 3) {
         dp.tagged = d_tagged;
         LAUNCH(m, FAM_WEIGHT, k_shard_zero, kSMs * 2, B, 0, mc, fc, dp, 1);
         LAUNCH(m, FAM_WEIGHT, k_pair_eval, kSMs * 2, EVAL_THREADS, EVAL_SMEM_BYTES, mc, fc, dp, 2);
+#ifdef W3
+        LAUNCH(m, FAM_WEIGHT, k_weight3, kSMs * 2, 32 * W3_WARPS, w3_smem_bytes(mc.OBS), mc, fc, dp);
+#else
         LAUNCH(m, FAM_WEIGHT, k_weight2, kSMs * 8, W2_THREADS, 0, mc, fc, dp);
         LAUNCH(m, FAM_WEIGHT, k_weight2w, kSMs * 6, W2W_THREADS, 0, mc, fc, dp);
+#endif
     } else if (phase == 4) {  // owners take their new weights; the newborn split reads them (dsp_dynamic.h:829-866)
         dp.tagged = d_tagged;
         LAUNCH(m, FAM_WEIGHT, k_shard_apply_weights, kSMs * 4, B, 0, mc, dp);
@@ -1152,8 +1183,7 @@ int dspmap_get_occupancy_device(dspmap *m, float thr, float *d_xyz, int cap, int
     CK(cudaSetDevice(m->cfg.device));
     const MapConst &mc = m->mc;
     LAUNCH(m, FAM_READER, k_occ_count, m->occ_blocks, 256, 0, mc, m->dp, thr, m->d_blockcnt, d_future);
-    LAUNCH(m, FAM_READER, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{m->d_blockcnt, m->d_blockoff, nullptr, 0, m->occ_blocks}, ScanJob{}, ScanJob{}}});
-    LAUNCH(m, FAM_READER, k_occ_write, m->occ_blocks, 256, 0, mc, m->dp, thr, m->d_blockoff, d_xyz, cap, d_count, m->occ_blocks);
+    LAUNCH(m, FAM_READER, k_occ_write, m->occ_blocks, 256, 0, mc, m->dp, thr, m->d_blockcnt, d_xyz, cap, d_count, m->occ_blocks);
     CK(cudaGetLastError());
     return DSPMAP_OK;
 }
@@ -1590,6 +1620,8 @@ int dspmap_euclidean_clusters(const float *xyz, int n, float tolerance, int min_
 }
 
 }  // extern "C"
+
+#include "shard_host.inc"
 
 namespace {
 // the reference's particle CSV (dsp_dynamic.h:328-350): flag,vx,vy,vz,px,py,pz,weight,voxel per live particle

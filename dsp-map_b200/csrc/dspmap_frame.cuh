@@ -130,6 +130,40 @@ __global__ void __launch_bounds__(1024) k_scan_small(ScanJobs jobs) {
 }
 
 
+// exclusive scan of n ints by one block (any block size that is a multiple of 32); out may be shared or global memory,
+// out[n] receives the total; wsum: 32 ints of shared memory
+__device__ __forceinline__ void block_exclusive_scan(const int *in, int *out, int n, int *wsum) {
+    const int T = blockDim.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = T >> 5;
+    const int per = (n + T - 1) / T;
+    const int b0 = min(n, (int)threadIdx.x * per), b1 = min(n, b0 + per);
+    int s = 0;
+    for (int i = b0; i < b1; ++i) s += in[i];
+    int incl = s;
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(FULLMASK, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) wsum[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        const int y0 = lane < nw ? wsum[lane] : 0;
+        int y = y0;
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(FULLMASK, y, d);
+            if (lane >= d) y += t;
+        }
+        wsum[lane] = y - y0;  // exclusive prefix of the warp totals
+    }
+    __syncthreads();
+    int run = wsum[wid] + incl - s;
+    for (int i = b0; i < b1; ++i) {
+        const int x = in[i];
+        out[i] = run;
+        run += x;
+    }
+    if ((int)threadIdx.x == T - 1) out[n] = run;
+    __syncthreads();  // the warp totals may be reused by a following scan; out[] is visible to the whole block
+}
 __global__ void k_obs_scatter(MapConst mc, FrameConst fc, DevPtrs dp) {
     pdl_enter();
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < fc.n_points; i += gridDim.x * blockDim.x) {
@@ -634,8 +668,19 @@ __global__ void k_shard_apply_weights(MapConst mc, DevPtrs dp) {
 //      segment by sweep key, keep the first L (the rest vanish, :1256-1259), and materialise a compact per-pyramid
 //      copy of (px, py, pz, w) for the two observation passes.
 // ------------------------------------------------------------------------------------------------------------
-__global__ void k_pyr_scatter(DevPtrs dp) {
+// fused != 0: every block first scans the pyramid counts into shared memory itself (P + 1 ints; block 0 also publishes the
+// offsets for the kernels that follow) instead of waiting for a scan launch of its own on the critical path
+__global__ void __launch_bounds__(256) k_pyr_scatter(MapConst mc, DevPtrs dp, int fused) {
     pdl_enter();
+    extern __shared__ int s_poff[];
+    __shared__ int wsum[32];
+    const int *poff = dp.poff;
+    if (fused) {
+        block_exclusive_scan(dp.pcount, s_poff, mc.P, wsum);
+        if (blockIdx.x == 0)
+            for (int q = threadIdx.x; q <= mc.P; q += blockDim.x) dp.poff[q] = s_poff[q];
+        poff = s_poff;
+    }
     const int n = dp.st->n_fov;
     // neighbouring particles mostly fall in the same pyramid: lanes that share one are counted together and their
     // leader reserves the block of slots with a single atomic (the order inside a segment is fixed by k_pyr_sort)
@@ -650,7 +695,7 @@ __global__ void k_pyr_scatter(DevPtrs dp) {
         if (lane == leader && q >= 0) base = atomicAdd(&dp.pfill[q], __popc(peers));
         base = __shfl_sync(FULLMASK, base, leader);
         if (q >= 0) {
-            const int pos = dp.poff[q] + base + __popc(peers & ((1u << lane) - 1u));
+            const int pos = poff[q] + base + __popc(peers & ((1u << lane) - 1u));
             dp.PSkey[pos] = dp.Fkey[i];
             dp.PSaddr[pos] = dp.Faddr[i];
         }
@@ -658,6 +703,9 @@ __global__ void k_pyr_scatter(DevPtrs dp) {
 }
 
 #define PYR_SORT_CAP 8192
+#ifndef PYR_RANK_MAX
+#define PYR_RANK_MAX 1024  // segments up to this length are ranked by counting instead of sorted
+#endif
 // Bitonic sort in shared memory, one thread per compare-exchange pair: the stages that exchange keys less than 32 apart (40 of
 // the 55 stages of a 1024-key network) stay inside one warp's 64-element block and need a warp barrier only.
 // (Measured on B200, cfg2: 27.3 -> 20.2 us against one thread per key with block-wide barriers; profiles/r02_ab_switches.jsonl.)
@@ -669,7 +717,32 @@ __global__ void __launch_bounds__(512) k_pyr_sort(MapConst mc, DevPtrs dp, float
         const int keep = min(n, mc.L);
         if (threadIdx.x == 0) dp.plen[q] = keep;
         if (n == 0) continue;
-        if (n <= PYR_SORT_CAP) {
+        if (n <= PYR_RANK_MAX) {
+            // short segment (every segment of the BASELINE configurations): no sorting network — each thread counts the keys
+            // below its own (keys are unique; the segment sits in shared memory and is read by broadcast) and writes its
+            // particle straight to that rank.  One barrier instead of ~45; the gather of the particle is issued before the count.
+            int *ikey = reinterpret_cast<int *>(skey);
+            for (int i = threadIdx.x; i < n; i += blockDim.x) ikey[i] = dp.PSkey[b + i];
+            __syncthreads();
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                int a = dp.PSaddr[b + i];
+                const float4 pa = mc.sharded ? dp.PSpay[b + i] : dp.PA[a];
+                const int ki = ikey[i];
+                int r = 0;
+#pragma unroll 8
+                for (int j = 0; j < n; ++j) r += ikey[j] < ki;
+                if (r < keep) {
+                    dp.LA[b + r] = a;
+                    dp.LP[b + r] = pa;
+                    dp.PW[b + r] = Pd * pa.w;
+                } else if (a >= 0) {  // pyramid full (sharded maps only, see below)
+                    mask_atomic_clear(dp.M, a / mc.S, a % mc.S);
+                    atomicAdd(&dp.st->n_pyramid_full, 1);
+                    atomicOr(&dp.st->overflow, 32);
+                }
+            }
+            __syncthreads();
+        } else if (n <= PYR_SORT_CAP) {
             int m = 1;
             while (m < n) m <<= 1;
             for (int i = threadIdx.x; i < m; i += blockDim.x)
@@ -868,38 +941,6 @@ __global__ void __launch_bounds__(K5_THREADS) k_weight(MapConst mc, FrameConst f
 // the number of 32-particle chunks of its own list; then the two exclusive scans (rowbase, chunk_off) and the chunk -> pyramid
 // table the pair-buffer kernels index with their queue tickets.  (Round 1 ran this as k_pair_prep + a scan launch and let
 // every work item find its pyramid by binary search over chunk_off.)
-__device__ __forceinline__ void block_exclusive_scan(const int *in, int *out, int n, int *wsum) {
-    const int T = blockDim.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = T >> 5;
-    const int per = (n + T - 1) / T;
-    const int b0 = min(n, (int)threadIdx.x * per), b1 = min(n, b0 + per);
-    int s = 0;
-    for (int i = b0; i < b1; ++i) s += in[i];
-    int incl = s;
-    for (int d = 1; d < 32; d <<= 1) {
-        const int t = __shfl_up_sync(FULLMASK, incl, d);
-        if (lane >= d) incl += t;
-    }
-    if (lane == 31) wsum[wid] = incl;
-    __syncthreads();
-    if (wid == 0) {
-        const int y0 = lane < nw ? wsum[lane] : 0;
-        int y = y0;
-        for (int d = 1; d < 32; d <<= 1) {
-            const int t = __shfl_up_sync(FULLMASK, y, d);
-            if (lane >= d) y += t;
-        }
-        wsum[lane] = y - y0;  // exclusive prefix of the warp totals
-    }
-    __syncthreads();
-    int run = wsum[wid] + incl - s;
-    for (int i = b0; i < b1; ++i) {
-        const int x = in[i];
-        out[i] = run;
-        run += x;
-    }
-    if ((int)threadIdx.x == T - 1) out[n] = run;
-    __syncthreads();  // the warp totals may be reused by a following scan; out[] is visible to the whole block
-}
 __global__ void __launch_bounds__(1024) k_pair_prep(MapConst mc, DevPtrs dp) {
     pdl_enter();
     __shared__ int wsum[32];
@@ -1033,6 +1074,27 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_pair_eval(MapConst mc, FrameCo
         }
     }
 }
+// One point's chain over `cur` rows of a staged tile: acc += w[j] * t[j * np] for j = 0 .. cur-1, IN THAT ORDER (one dependent
+// fp32 add per row, 4 cycles each: the floor of the whole C_z pass is the longest chain).  The products of the next eight rows
+// are formed while the current eight are added, so the shared-memory latency (~30 cycles) never sits in front of the adds.
+__device__ __forceinline__ float cz_chain_rows(float acc, const float *t, const float *w, int np, int cur) {
+    int jj = 0;
+    if (cur >= 8) {
+        float a0 = w[0] * t[0], a1 = w[1] * t[np], a2 = w[2] * t[2 * np], a3 = w[3] * t[3 * np];
+        float a4 = w[4] * t[4 * np], a5 = w[5] * t[5 * np], a6 = w[6] * t[6 * np], a7 = w[7] * t[7 * np];
+        for (jj = 8; jj + 8 <= cur; jj += 8) {
+            const float *tn = t + jj * np;
+            const float *wn = w + jj;
+            const float b0 = wn[0] * tn[0], b1 = wn[1] * tn[np], b2 = wn[2] * tn[2 * np], b3 = wn[3] * tn[3 * np];
+            const float b4 = wn[4] * tn[4 * np], b5 = wn[5] * tn[5 * np], b6 = wn[6] * tn[6 * np], b7 = wn[7] * tn[7 * np];
+            acc += a0; acc += a1; acc += a2; acc += a3; acc += a4; acc += a5; acc += a6; acc += a7;
+            a0 = b0; a1 = b1; a2 = b2; a3 = b3; a4 = b4; a5 = b5; a6 = b6; a7 = b7;
+        }
+        acc += a0; acc += a1; acc += a2; acc += a3; acc += a4; acc += a5; acc += a6; acc += a7;
+    }
+    for (; jj < cur; ++jj) acc += w[jj] * t[jj * np];
+    return acc;
+}
 // C_z (dsp_dynamic.h:709-739): a CTA per point pyramid streams the pyramid's contiguous block of G through shared
 // memory (double-buffered cp.async); thread z < np adds its column in list order: one fp32 chain per point.
 // Measured on B200 (cfg2): 256 threads with 2 x 32 KB tiles (3 CTAs / SM) 54 us, 128 threads with 2 x 16 KB tiles
@@ -1096,17 +1158,7 @@ __global__ void __launch_bounds__(CZ_THREADS) k_cz_chain(MapConst mc, FrameConst
             __pipeline_wait_prior(1);
             __syncthreads();
             if (tid < np) {  // the chain: (P_d * w) * g added in list order, one fp32 add per term
-                const float *t = (buf ? tile1 : tile0) + (buf ? ph1 : ph0) + tid;
-                const float *w = buf ? pws1 : pws0;
-                int jj = 0;
-                for (; jj + 8 <= cur; jj += 8) {
-                    float g0 = t[jj * np], g1 = t[(jj + 1) * np], g2 = t[(jj + 2) * np], g3 = t[(jj + 3) * np];
-                    float g4 = t[(jj + 4) * np], g5 = t[(jj + 5) * np], g6 = t[(jj + 6) * np], g7 = t[(jj + 7) * np];
-                    const float4 wa = *reinterpret_cast<const float4 *>(w + jj), wb = *reinterpret_cast<const float4 *>(w + jj + 4);
-                    g0 *= wa.x; g1 *= wa.y; g2 *= wa.z; g3 *= wa.w; g4 *= wb.x; g5 *= wb.y; g6 *= wb.z; g7 *= wb.w;
-                    acc += g0; acc += g1; acc += g2; acc += g3; acc += g4; acc += g5; acc += g6; acc += g7;
-                }
-                for (; jj < cur; ++jj) acc += w[jj] * t[jj * np];
+                acc = cz_chain_rows(acc, (buf ? tile1 : tile0) + (buf ? ph1 : ph0) + tid, buf ? pws1 : pws0, np, cur);
             }
             __syncthreads();
             cur = nxt;
@@ -1120,12 +1172,122 @@ __global__ void __launch_bounds__(CZ_THREADS) k_cz_chain(MapConst mc, FrameConst
         }
     }
 }
+// C_z with a bulk-copy ring (compile-time variant -DCZ_TMA=1, A/B-measured with tests/ab_variants.sh).  A producer thread
+// streams the pyramid's contiguous block of G (and the matching P_d * w values) through a ring of CZT_STAGES shared-memory
+// stages with cp.async.bulk (TMA, 1-D) completing on per-stage mbarriers; the chain warps wait on "full", add their column in
+// list order, and release the stage on "empty": no block-wide barrier inside a pyramid.  Same terms, same order as k_cz_chain.
+#ifndef CZT_STAGES
+#define CZT_STAGES 3
+#endif
+#ifndef CZT_TILE
+#define CZT_TILE 8448   // floats per stage
+#endif
+#ifndef CZT_JT
+#define CZT_JT 256      // particle rows per stage at most
+#endif
+#define CZT_CHAIN_WARPS 4
+#define CZT_MAXNB 128    // neighbour tables staged in shared memory up to this many neighbours (== chain threads)
+#define CZT_THREADS (32 * (CZT_CHAIN_WARPS + 1))
+#define CZT_SMEM_BYTES (CZT_STAGES * (CZT_TILE + 4 + CZT_JT + 4) * 4 + 2 * CZT_STAGES * 8)
+__global__ void __launch_bounds__(CZT_THREADS) k_cz_chain_tma(MapConst mc, FrameConst fc, DevPtrs dp) {
+    pdl_enter();
+    extern __shared__ __align__(128) float cztsm[];
+    float *tiles = cztsm;                                       // CZT_STAGES x (CZT_TILE + 4): + room for the alignment phase
+    float *pws = tiles + CZT_STAGES * (CZT_TILE + 4);           // CZT_STAGES x (CZT_JT + 4)
+    uint64_t *full = reinterpret_cast<uint64_t *>(pws + CZT_STAGES * (CZT_JT + 4));
+    uint64_t *empty = full + CZT_STAGES;
+    __shared__ int s_item;
+    __shared__ int s_len[CZT_MAXNB], s_off[CZT_MAXNB];  // this pyramid's neighbour lists (length, offset into PW): read once, walked per tile
+    if (!use_pair_buffer(mc, dp)) return;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) {
+        for (int s = 0; s < CZT_STAGES; ++s) {
+            cuda::ptx::mbarrier_init(&full[s], 1);                  // the producer's arrive.expect_tx; completes with the bytes
+            cuda::ptx::mbarrier_init(&empty[s], CZT_CHAIN_WARPS);   // one arrival per chain warp
+        }
+        cuda::ptx::fence_mbarrier_init(cuda::ptx::sem_release, cuda::ptx::scope_cluster);
+        cuda::ptx::fence_proxy_async(cuda::ptx::space_shared);
+    }
+    __syncthreads();
+    const float enb = fc.nb_weight * (float)dp.st->n_valid * (float)fc.nb_num;  // :292
+    const float add_k = enb + fc.kappa;
+    unsigned it = 0;  // tiles this CTA has been through: the producer and the chain warps walk the same sequence
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_item = atomicAdd(&dp.st->work_k4, 1);
+        __syncthreads();
+        const int wi = s_item;
+        if (wi >= mc.P) break;
+        const int i = wi;
+        const int np = min(dp.obs_cnt[i], mc.OBS - 1);
+        if (np == 0) continue;
+        if (mc.sharded && i % mc.nranks != mc.rank) continue;  // another rank computes this pyramid's C_z
+        const int nn = dp.nbr[i * mc.NBW];
+        const bool staged = nn <= CZT_MAXNB;  // larger neighbourhoods (PYRAMID_NEIGHBOR_N >= 6) read the tables per tile
+        if (staged && tid < nn) {
+            const int b = dp.nbr[i * mc.NBW + 1 + tid];
+            s_len[tid] = dp.plen[b];
+            s_off[tid] = dp.poff[b];
+        }
+        __syncthreads();  // (the barrier at the top of the loop keeps the previous pyramid's readers ahead of these writes)
+        auto len_of = [&](int k) { return staged ? s_len[k] : dp.plen[dp.nbr[i * mc.NBW + 1 + k]]; };
+        auto off_of = [&](int k) { return staged ? s_off[k] : dp.poff[dp.nbr[i * mc.NBW + 1 + k]]; };
+        const int JT = min(CZT_JT, CZT_TILE / np);
+        const float *g = dp.G + (size_t)dp.rowbase[i];
+        int ns = 0, k0 = 0, ln = nn > 0 ? len_of(0) : 0;
+        float acc = 0.f;
+        for (;;) {
+            while (ns < nn && k0 >= ln) {
+                ++ns;
+                k0 = 0;
+                ln = ns < nn ? len_of(ns) : 0;
+            }
+            if (ns >= nn) break;
+            const int cur = min(JT, ln - k0), nfl = cur * np;
+            const float *wsrc = dp.PW + off_of(ns) + k0;
+            // bulk copies move 16-byte units between 16-byte aligned addresses: start at the boundary below and keep the phase
+            const int phg = (int)((reinterpret_cast<size_t>(g) >> 2) & 3), phw = (int)((reinterpret_cast<size_t>(wsrc) >> 2) & 3);
+            const int s = (int)(it % CZT_STAGES);
+            const unsigned par = (it / CZT_STAGES) & 1u;
+            float *ts = tiles + s * (CZT_TILE + 4), *ws = pws + s * (CZT_JT + 4);
+            if (wid == CZT_CHAIN_WARPS) {  // producer warp: one thread feeds the ring
+                if (lane == 0) {
+                    while (!cuda::ptx::mbarrier_try_wait_parity(&empty[s], par ^ 1u)) {}  // a fresh barrier passes at once
+                    const unsigned bg = (unsigned)((phg + nfl + 3) >> 2) * 16u, bw = (unsigned)((phw + cur + 3) >> 2) * 16u;
+                    cuda::ptx::mbarrier_arrive_expect_tx(cuda::ptx::sem_release, cuda::ptx::scope_cta, cuda::ptx::space_shared, &full[s], bg + bw);
+                    cuda::ptx::cp_async_bulk(cuda::ptx::space_cluster, cuda::ptx::space_global, ts, g - phg, bg, &full[s]);
+                    cuda::ptx::cp_async_bulk(cuda::ptx::space_cluster, cuda::ptx::space_global, ws, wsrc - phw, bw, &full[s]);
+                }
+                __syncwarp();
+            } else {
+                while (!cuda::ptx::mbarrier_try_wait_parity(&full[s], par)) {}
+                if (tid < np) {  // the chain: (P_d * w) * g added in list order, one fp32 add per term
+                    acc = cz_chain_rows(acc, ts + phg + tid, ws + phw, np, cur);
+                }
+                __syncwarp();
+                if (lane == 0) cuda::ptx::mbarrier_arrive(&empty[s]);
+            }
+            g += nfl;
+            k0 += cur;
+            ++it;
+        }
+        if (tid < np) {
+            acc += add_k;
+            dp.CZ[i * mc.OBS + tid] = acc;
+            dp.INV[dp.obs_capoff[i] + tid] = 1.f / acc;  // for the newborn normaliser (:802)
+        }
+    }
+}
 // weights (dsp_dynamic.h:743-790): a CTA per 32 particles of a pyramid.  For one neighbour pyramid at a time, ALL threads
 // turn the chunk's contiguous 32 x np tile of G into quotient terms (P_d * g) / C_z (flat, coalesced loads); then warp 0,
 // lane = particle, adds its row in bin order.  Neighbours are visited in table order, so each particle's sum is one fp32
 // chain in the reference's order.  Two term buffers let the next neighbour's divisions overlap the current chain.
+#ifndef W2_SWITCH
 #define W2_SWITCH 4096  // chunks of 32 particles: below, CTA-per-chunk (k_weight2); from here on, warp-per-chunk (k_weight2w)
-#define W2_THREADS 128
+#endif
+#ifndef W2_THREADS
+#define W2_THREADS 128   // warp 0 adds the chains, the other warps turn tiles into quotient terms
+#endif
 #define W2_NP 100  // padded row length (np <= 99; odd stride: no bank conflicts in the chain)
 __global__ void __launch_bounds__(W2_THREADS) k_weight2(MapConst mc, FrameConst fc, DevPtrs dp) {
     pdl_enter();
@@ -1200,7 +1362,7 @@ __global__ void __launch_bounds__(W2_THREADS) k_weight2(MapConst mc, FrameConst 
                     if (t96 + PSTR < np) czs[buf][t96 + PSTR] = czpre1;
                     const float *gb = gb_n;
                     const int nfl = nfl_n;
-                    asm volatile("bar.sync 1, 96;" ::: "memory");  // only the three producer warps
+                    asm volatile("bar.sync 1, %0;" ::"n"(W2_THREADS - 32) : "memory");  // only the producer warps
                     const unsigned magic = np > 1 ? 0xffffffffu / (unsigned)np + 1u : 0u;  // exact f / np for f < 65536
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
@@ -1328,6 +1490,85 @@ __global__ void __launch_bounds__(W2W_THREADS, 3) k_weight2w(MapConst mc, FrameC
         }
         if (lane < nrows) {
             const float w_new = act ? p.w * (fc.one_minus_Pd + sum) : p.w;
+            if (mc.sharded) dp.NW[lb + k0 + lane] = w_new;  // merged over ranks, applied by the particle's owner
+            else if (act) dp.PA[dp.LA[lb + k0 + lane]].w = w_new;
+        }
+    }
+}
+
+// weights (dsp_dynamic.h:743-790), one WARP per 32 particles of a pyramid, no block-wide barrier.  For one neighbour pyramid
+// at a time the chunk's tile of G — nrows x np values, contiguous — is walked flat (lane l takes values l, l + 32, ...:
+// coalesced loads, several in flight), every value becomes its quotient term (P_d * g) / C_z and lands in the warp's padded
+// shared tile; then lane = particle adds its row in bin order.  Neighbours are visited in table order, so each particle's sum
+// is one fp32 chain in the reference's order.  (The CTA-per-chunk kernel k_weight2 spent more instructions on distributing a
+// tile over its producer warps and on the hand-over than on the terms themselves.)
+#define W3_WARPS 8
+// (P_d * g) / C_z rounded exactly like the IEEE division of the reference (:776) without the division's slow path: nvcc's a / b
+// sends zero and subnormal dividends to a 30-80 instruction subroutine, and the warp pays for it as soon as one lane needs it
+// (g, a product of three table values down to 3e-22, is zero / subnormal / below 2^-100 in 0.3 / 3.2 / 3.9 % of the pairs).
+//   a == 0     ->  +0 (C_z is positive and finite)
+//   a < 2^-96  ->  divided in double and rounded to float once more: innocuous for the quotient of two floats (53 >= 2 * 24 + 2
+//                  bits, subnormal results included; tests/test_host.py checks it against IEEE fp32 division)
+__device__ __forceinline__ float dsp_quot(float a, float b) {
+    if (a == 0.f) return 0.f;
+    if (a < 1.262177448e-29f) return (float)((double)a / (double)b);  // 2^-96
+    return a / b;
+}
+__host__ __device__ __forceinline__ size_t w3_smem_bytes(int OBS) { return (size_t)W3_WARPS * (32 * (size_t)((OBS - 1) | 1) + 128) * sizeof(float); }
+__global__ void __launch_bounds__(32 * W3_WARPS) k_weight3(MapConst mc, FrameConst fc, DevPtrs dp) {
+    pdl_enter();
+    extern __shared__ float w3sm[];
+    if (!use_pair_buffer(mc, dp)) return;
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+    const int ldmax = (mc.OBS - 1) | 1;
+    float *tile = w3sm + (size_t)wl * (32 * ldmax + 128);
+    float *czs = tile + 32 * ldmax;
+    const int nchunks = dp.chunk_off[mc.P];
+    for (;;) {
+        int c = 0;
+        if (lane == 0) c = atomicAdd(&dp.st->work_w2, 1);
+        c = __shfl_sync(FULLMASK, c, 0);
+        if (c >= nchunks) break;
+        if (mc.sharded && c % mc.nranks != mc.rank) continue;  // chunks are dealt round-robin over the ranks
+        const int a = dp.chunk_pyr[c];
+        const int k0 = (c - dp.chunk_off[a]) << 5;
+        const int lb = dp.poff[a];
+        const int nrows = min(32, dp.plen[a] - k0);
+        bool act = false;
+        float pw = 0.f, sum = 0.f;
+        if (lane < nrows) {
+            const float4 p = dp.LP[lb + k0 + lane];
+            pw = p.w;
+            const float dist = sqrtf(p.x * p.x + p.y * p.y + p.z * p.z);
+            const float maxlen = __int_as_float(dp.obs_maxbits[a]);
+            act = !(maxlen > 0.f && dist > maxlen + mc.occl);  // occluded particles keep their weight (:761)
+        }
+        const int nn = dp.nbr[a * mc.NBW];
+        for (int ns = 0; ns < nn; ++ns) {
+            const int b = dp.nbr[a * mc.NBW + 1 + ns];
+            const int np = min(dp.obs_cnt[b], mc.OBS - 1);
+            if (np == 0) continue;
+            const float *gb = dp.G + (size_t)dp.rowbase[b] + (size_t)(dp.cum[b * mc.NBW + dp.nbrev[a * mc.NBW + 1 + ns]] + k0) * np;
+            const int total = nrows * np, ld = np | 1;
+            __syncwarp();  // the previous neighbour's rows have been added
+            for (int z = lane; z < np; z += 32) czs[z] = dp.CZ[(size_t)b * mc.OBS + z];
+            __syncwarp();
+            const unsigned magic = np > 1 ? 0xffffffffu / (unsigned)np + 1u : 0u;  // exact f / np for f < 65536
+#pragma unroll 4
+            for (int f = lane; f < total; f += 32) {
+                const int r = np > 1 ? (int)__umulhi((unsigned)f, magic) : f;
+                const int z = f - r * np;
+                tile[r * ld + z] = dsp_quot(fc.Pd * __ldg(gb + f), czs[z]);
+            }
+            __syncwarp();
+            if (act) {
+                const float *row = tile + lane * ld;
+#pragma unroll 4
+                for (int z = 0; z < np; ++z) sum += row[z];
+            }
+        }
+        if (lane < nrows) {
+            const float w_new = act ? pw * (fc.one_minus_Pd + sum) : pw;
             if (mc.sharded) dp.NW[lb + k0 + lane] = w_new;  // merged over ranks, applied by the particle's owner
             else if (act) dp.PA[dp.LA[lb + k0 + lane]].w = w_new;
         }
@@ -1696,16 +1937,19 @@ __global__ void k_voxel_list(MapConst mc, DevPtrs dp) {
 //     shuffle: 2 450 warp instructions per voxel, 35 us at cfg2.)
 // ------------------------------------------------------------------------------------------------------------
 #ifndef RS_VPW
-#define RS_VPW 8     // voxels per warp
+#define RS_VPW 2     // voxels per warp (measured on B200, cfg2: 8 -> 83 us, 4 -> 53, 2 -> 38, 1 -> 40; profiles/r02_variants.jsonl)
 #endif
 #ifndef RS_WARPS
-#define RS_WARPS 4   // warps per block
+#define RS_WARPS 8   // warps per block
 #endif
 // shared memory of one warp: tile[RS_VPW][S + 1] float4 | verd[RS_VPW][S] float | tagb, dsrc, ddst [RS_VPW][S] u8 | wafter[RS_VPW] float
 __host__ __device__ __forceinline__ size_t rs_warp_bytes(int S) {
     return ((size_t)RS_VPW * (S + 1) * 16 + (size_t)RS_VPW * S * 4 + (size_t)RS_VPW * S * 3 + (size_t)RS_VPW * 4 + 15) & ~(size_t)15;
 }
-__global__ void __launch_bounds__(32 * RS_WARPS) k_resample(MapConst mc, FrameConst fc, DevPtrs dp) {
+#ifndef RS_MINB
+#define RS_MINB 1
+#endif
+__global__ void __launch_bounds__(32 * RS_WARPS, RS_MINB) k_resample(MapConst mc, FrameConst fc, DevPtrs dp) {
     pdl_enter();
     extern __shared__ __align__(16) float4 rs_smem4[];
     unsigned char *rs_smem = reinterpret_cast<unsigned char *>(rs_smem4);
@@ -1953,13 +2197,31 @@ __global__ void __launch_bounds__(256) k_occ_count(MapConst mc, DevPtrs dp, floa
         dp.FUT[i] = 0.f;
     }
 }
-__global__ void __launch_bounds__(256) k_occ_write(MapConst mc, DevPtrs dp, float thr, const int *blockoff, float *xyz, int cap, int *d_count, int nblocks) {
+__global__ void __launch_bounds__(256) k_occ_write(MapConst mc, DevPtrs dp, float thr, const int *blockcnt, float *xyz, int cap, int *d_count, int nblocks) {
     pdl_enter();
-    __shared__ int wsum[8];
-    int b = blockIdx.x * OCC_BLOCK;
-    int run = blockoff[blockIdx.x];
-    if (blockIdx.x == 0 && threadIdx.x == 0 && d_count) *d_count = blockoff[nblocks];
+    __shared__ int wsum[8], s_before, s_total;
+    // this block's offset = the occupied voxels of all blocks before it (k_occ_count's per-block counts): summed here instead
+    // of by a scan launch between the two reader kernels
     int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    {
+        int before = 0, total = 0;
+        for (int b = threadIdx.x; b < nblocks; b += blockDim.x) {
+            const int c = blockcnt[b];
+            total += c;
+            if (b < (int)blockIdx.x) before += c;
+        }
+        for (int d = 16; d > 0; d >>= 1) {
+            before += __shfl_down_sync(FULLMASK, before, d);
+            total += __shfl_down_sync(FULLMASK, total, d);
+        }
+        if (threadIdx.x == 0) { s_before = 0; s_total = 0; }
+        __syncthreads();
+        if (lane == 0) { atomicAdd(&s_before, before); atomicAdd(&s_total, total); }
+        __syncthreads();
+    }
+    int b = blockIdx.x * OCC_BLOCK;
+    int run = s_before;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && d_count) *d_count = s_total;
     for (int i0 = 0; i0 < OCC_BLOCK; i0 += 256) {
         int v = b + i0 + threadIdx.x;
         bool occ = v < mc.V && dp.OCCV[v].x > thr;

@@ -97,6 +97,14 @@ def load_library():
         "dspmap_shard_config": (i, [vp, i, i, vp, vp, i, vp, vp, i, vp, vp]),
         "dspmap_shard_gather_records": (i, [vp, i]),
         "dspmap_shard_phase": (i, [vp, i, i, vp, f, f, f, C.c_double, f, f, f, f, vp, i]),
+        "dspmap_shard_unique_id": (i, [vp]),
+        "dspmap_shard_init": (i, [vp, i, i, vp, i, i]),
+        "dspmap_shard_init_local": (i, [C.POINTER(vp), i, i, i]),
+        "dspmap_shard_update": (i, [vp, i, vp, f, f, f, C.c_double, f, f, f, f, vp, i]),
+        "dspmap_shard_update_local": (i, [C.POINTER(vp), i, i, vp, f, f, f, C.c_double, f, f, f, f, vp, i]),
+        "dspmap_shard_get_occupancy": (i, [vp, f, vp, i, vp, vp]),
+        "dspmap_shard_get_occupancy_local": (i, [C.POINTER(vp), i, f, C.POINTER(vp), i, C.POINTER(vp), C.POINTER(vp)]),
+        "dspmap_shard_info": (i, [vp, ip]),
         "dspmap_estimator_create": (vp, [C.POINTER(Config), f]),
         "dspmap_estimator_destroy": (None, [vp]),
         "dspmap_estimator_estimate": (i, [vp, i, fp, f, f, f, f, f, f, f, f, fp, i]),
@@ -133,7 +141,9 @@ EXPORTED_SYMBOLS = [
     "dspmap_euclidean_clusters",
     "dspmap_prefilter_create", "dspmap_prefilter_destroy", "dspmap_prefilter_set_stream", "dspmap_prefilter_last_error",
     "dspmap_prefilter_launches", "dspmap_prefilter_run", "dspmap_prefilter_run_device", "dspmap_update_raw",
-    "dspmap_shard_config", "dspmap_shard_gather_records", "dspmap_shard_phase",
+    "dspmap_shard_config", "dspmap_shard_gather_records", "dspmap_shard_phase", "dspmap_shard_unique_id", "dspmap_shard_init",
+    "dspmap_shard_init_local", "dspmap_shard_update", "dspmap_shard_update_local", "dspmap_shard_get_occupancy",
+    "dspmap_shard_get_occupancy_local", "dspmap_shard_info",
 ]
 
 
@@ -395,6 +405,26 @@ class DSPMap:
                                                        float(pos[2]), float(t), float(quat[0]), float(quat[1]), float(quat[2]),
                                                        float(quat[3]), C.c_void_p(d_tagged), n_tagged))
 
+    # ---- one map over several GPUs, orchestrated by the library (include/dspmap_b200.h: dspmap_shard_init / _update) ------
+    def shard_init(self, rank, nranks, nccl_id, cap_x=0, cap_g=0):
+        """nccl_id: the 128 bytes of shard_unique_id() from rank 0."""
+        buf = (C.c_char * 128).from_buffer_copy(bytes(nccl_id))
+        return self._check(self.lib.dspmap_shard_init(self.h, rank, nranks, C.cast(buf, C.c_void_p), cap_x, cap_g))
+
+    def shard_update(self, n, d_pts, pos, t, quat, d_tagged, n_tagged):
+        return self._check(self.lib.dspmap_shard_update(self.h, n, C.c_void_p(d_pts), float(pos[0]), float(pos[1]), float(pos[2]),
+                                                        float(t), float(quat[0]), float(quat[1]), float(quat[2]), float(quat[3]),
+                                                        C.c_void_p(d_tagged), n_tagged))
+
+    def shard_get_occupancy(self, threshold, d_xyz, cap, d_count, d_future):
+        return self._check(self.lib.dspmap_shard_get_occupancy(self.h, threshold, C.c_void_p(d_xyz), cap, C.c_void_p(d_count),
+                                                               C.c_void_p(d_future)))
+
+    def shard_info(self):
+        o = np.zeros(4, np.int32)
+        self._check(self.lib.dspmap_shard_info(self.h, _ip(o)))
+        return dict(cap_x=int(o[0]), cap_g=int(o[1]), gather_records=int(o[2]), frames=int(o[3]))
+
     def get_occupancy_device(self, threshold, d_xyz, cap, d_count, d_future):
         return self._check(self.lib.dspmap_get_occupancy_device(self.h, threshold, C.c_void_p(d_xyz), cap,
                                                                 C.c_void_p(d_count), C.c_void_p(d_future)))
@@ -527,3 +557,95 @@ def bytes_per_update(counters, V, T, M):
     c = counters
     return (64 * c["n_in"] + 36 * c["n_fov"] + 32 * c["n_born"] + 32 * c["n_pre"] + 32 * c["n_out"] +
             4 * T * c["n_old"] + V * (20 + 12 * T) + 20 * M)
+
+
+def shard_unique_id():
+    """ncclGetUniqueId through the library (rank 0 calls it and hands the 128 bytes to every rank)."""
+    lib = load_library()
+    buf = (C.c_char * 128)()
+    rc = lib.dspmap_shard_unique_id(C.cast(buf, C.c_void_p))
+    if rc != OK:
+        raise DSPMapError("dspmap_shard_unique_id failed (%d): %s" % (rc, lib.dspmap_last_error().decode()))
+    return bytes(buf)
+
+
+class LocalShardedMap:
+    """All shards of one map in ONE process on ONE device, driven by the library's own C++ orchestrator
+    (dspmap_shard_init_local / _update_local / _get_occupancy_local): the code path of the NCCL build with the collectives
+    done as device-to-device copies.  For tests on a single-GPU box."""
+
+    def __init__(self, cfg, nranks, seed=1, device=0, max_points=0, setters=None, cap_x=0, cap_g=0, **kw):
+        import torch
+        self.torch = torch
+        self.cfg, self.nranks = cfg, nranks
+        self.maps = [DSPMap(cfg, seed=seed, device=device, max_points=max_points or 65536, **kw) for _ in range(nranks)]
+        self.lib = self.maps[0].lib
+        for m in self.maps:
+            if setters:
+                setters(m)
+        self.hs = (C.c_void_p * nranks)(*[m.h for m in self.maps])
+        rc = self.lib.dspmap_shard_init_local(self.hs, nranks, cap_x, cap_g)
+        if rc != OK:
+            raise DSPMapError("dspmap_shard_init_local failed (%d): %s" % (rc, self.lib.dspmap_last_error().decode()))
+        self.dev = torch.device("cuda", device)
+        m = self.maps[0]
+        self.V, self.T = m.V, m.T
+        self.d_xyz = [torch.zeros((m.V, 3), dtype=torch.float32, device=self.dev) for _ in range(nranks)]
+        self.d_cnt = [torch.zeros(1, dtype=torch.int32, device=self.dev) for _ in range(nranks)]
+        self.d_fut = [torch.zeros((m.V, max(m.T, 1)), dtype=torch.float32, device=self.dev) for _ in range(nranks)]
+        zpr = (cfg["nz"] + nranks - 1) // nranks
+        self.v_lo = [min(cfg["nz"], r * zpr) * cfg["nx"] * cfg["ny"] for r in range(nranks)]
+        self.v_hi = [min(cfg["nz"], (r + 1) * zpr) * cfg["nx"] * cfg["ny"] for r in range(nranks)]
+
+    def update(self, pts, pos, t, quat, tagged):
+        torch = self.torch
+        d_pts = torch.from_numpy(np.ascontiguousarray(pts, np.float32)).to(self.dev)
+        tg = np.ascontiguousarray(tagged, np.float32).reshape(-1, 7)
+        d_tag = torch.from_numpy(tg if len(tg) else np.zeros((1, 7), np.float32)).to(self.dev)
+        torch.cuda.synchronize()
+        rc = self.lib.dspmap_shard_update_local(self.hs, self.nranks, len(pts), C.c_void_p(d_pts.data_ptr()), float(pos[0]), float(pos[1]),
+                                                float(pos[2]), float(t), float(quat[0]), float(quat[1]), float(quat[2]), float(quat[3]),
+                                                C.c_void_p(d_tag.data_ptr()), len(tg))
+        if rc < 0:
+            raise DSPMapError("dspmap_shard_update_local failed (%d): %s" % (rc, self.lib.dspmap_last_error().decode()))
+        for m in self.maps:
+            m.synchronize()
+        return rc
+
+    def occupancy(self, threshold):
+        """Every rank's copy of the whole map's results (they must all be equal): list of (n, xyz, future)."""
+        n = self.nranks
+        xs = (C.c_void_p * n)(*[x.data_ptr() for x in self.d_xyz])
+        cs = (C.c_void_p * n)(*[x.data_ptr() for x in self.d_cnt])
+        fs = (C.c_void_p * n)(*[x.data_ptr() for x in self.d_fut])
+        rc = self.lib.dspmap_shard_get_occupancy_local(self.hs, n, threshold, xs, self.V, cs, fs)
+        if rc < 0:
+            raise DSPMapError("dspmap_shard_get_occupancy_local failed (%d): %s" % (rc, self.lib.dspmap_last_error().decode()))
+        for m in self.maps:
+            m.synchronize()
+        out = []
+        for r in range(n):
+            k = int(self.d_cnt[r].item())
+            out.append((k, self.d_xyz[r][:k].cpu().numpy(), self.d_fut[r].cpu().numpy()))
+        return out
+
+    def particles(self):
+        parts = [m.particles() for m in self.maps]
+        ids = np.concatenate([p[0] for p in parts])
+        vals = np.concatenate([p[1] for p in parts])
+        order = np.argsort(ids[:, 0].astype(np.int64) * 128 + ids[:, 1], kind="stable")
+        return ids[order], vals[order]
+
+    def voxel_objects(self):
+        out = None
+        for r, m in enumerate(self.maps):
+            vo = m.voxel_objects()
+            if out is None:
+                out = np.zeros_like(vo)
+            out[self.v_lo[r]:self.v_hi[r], :4] = vo[self.v_lo[r]:self.v_hi[r], :4]
+            out[:, 4:] += vo[:, 4:]
+        return out
+
+    def close(self):
+        for m in self.maps:
+            m.close()

@@ -207,6 +207,32 @@ int dspmap_shard_gather_records(dspmap *m, int records);
 int dspmap_shard_phase(dspmap *m, int phase, int n, const float *d_pts, float px, float py, float pz, double t, float qw,
                        float qx, float qy, float qz, const float *d_tagged, int n_tagged);
 
+/* ---- the same, orchestrated by the library (C++ host): one call per frame, collectives inside -------------------------------
+ * One process + one handle per GPU; the six phases and their collectives are issued from C++ on the handle's stream with
+ * NCCL (libnccl.so.2 is opened with dlopen by dspmap_shard_init: no link-time dependency), with no host synchronisation
+ * inside a frame: the all-gather of frame k is sized from the largest per-rank count of frame k-2, which every rank read
+ * from the same gathered headers (a frame that outgrows it is flagged: capacity code 16).  Exchange buffers belong to the
+ * library.  cap_x / cap_g <= 0 pick defaults (4096 crossers per rank pair; live-list capacity / nranks).
+ *   rank 0:      dspmap_shard_unique_id(id)  ->  hand the DSPMAP_NCCL_ID_BYTES bytes to every rank (MPI, a file, a socket, ...)
+ *   every rank:  dspmap_create(...); dspmap_shard_init(m, rank, nranks, id, 0, 0);
+ *   per frame:   dspmap_shard_update(m, ...)       cloud, pose and newborn input replicated, device memory
+ *                dspmap_shard_get_occupancy(m, ...) every rank receives the whole map's occupied list and future grid
+ * The *_local variants drive all handles of one map in ONE process on ONE device (shared stream; the collectives are
+ * device-to-device copies): the same orchestration code, testable on a single GPU. */
+#define DSPMAP_NCCL_ID_BYTES 128
+int dspmap_shard_unique_id(void *id128);
+int dspmap_shard_init(dspmap *m, int rank, int nranks, const void *id128, int cap_x, int cap_g);
+int dspmap_shard_init_local(dspmap **handles, int n, int cap_x, int cap_g);
+int dspmap_shard_update(dspmap *m, int n, const float *d_pts, float px, float py, float pz, double t, float qw, float qx,
+                        float qy, float qz, const float *d_tagged, int n_tagged);
+int dspmap_shard_update_local(dspmap **handles, int n_handles, int n, const float *d_pts, float px, float py, float pz, double t,
+                              float qw, float qx, float qy, float qz, const float *d_tagged, int n_tagged);
+int dspmap_shard_get_occupancy(dspmap *m, float threshold, float *d_xyz, int cap, int *d_count, float *d_future);
+int dspmap_shard_get_occupancy_local(dspmap **handles, int n_handles, float threshold, float *const *d_xyz, int cap,
+                                     int *const *d_count, float *const *d_future);
+/* out4: cap_x, cap_g, records per rank moved by the last frame's all-gather, frames so far. */
+int dspmap_shard_info(dspmap *m, int32_t *out4);
+
 /* Host-only access to the velocity-estimation step (the reference's side thread, dsp_dynamic.h:1377-1544; static variant
  * dsp_static.h:1285-1309) without a map or a GPU: used to pre-compute newborn inputs for device-resident streams and
  * by the CPU tests.  `estimate` consumes one frame (n x 3 points, sensor frame) and writes the tagged cloud (7 floats

@@ -53,3 +53,35 @@ def test_sharded_equals_single_gpu(name, nranks, frames):
             assert same(xyz, sxyz) and np.allclose(fut, sfut, rtol=4e-6, atol=0)
     one.close()
     cl.close()
+
+
+@pytest.mark.parametrize("name,nranks,frames", [("tiny_dyn", 2, 8), ("tiny_dyn", 3, 6), ("cfg2", 4, 5), ("cfg2", 8, 3)])
+def test_library_orchestrated_sharded_map_equals_single_gpu(name, nranks, frames):
+    """The C++ orchestrator (dspmap_shard_update_local: six phases + collectives issued by the library, no host synchronisation
+    inside a frame, the gather of frame k sized from frame k-2) against an unsharded map: particle state after every frame,
+    and the sharded reader's occupied list / future grid on EVERY rank."""
+    cfg = dm.CONFIGS[name]
+    st = make_stream(cfg, seed=8, frames=frames)
+    est = dm.VelocityEstimator(cfg, seed=4, filter_res=0.1)
+    one = gpu_map(name, seed=4, max_points=cfg["points"])
+    cl = dm.LocalShardedMap(cfg, nranks, seed=4, max_points=cfg["points"], setters=setters)
+    for f in range(frames):
+        pts, pos, t, q = st["points"][f], st["pos"][f], st["t"][f], st["quat"][f]
+        tc = est.estimate(pts, pos, t, q)
+        assert gpu_update(one, pts, pos, t, q, tagged=tc) == 1
+        assert cl.update(pts, pos, t, q, tc) == 1
+        ids, vals = one.particles()
+        sids, svals = cl.particles()
+        assert same(ids, sids), "frame %d: particle (voxel, slot) sets" % f
+        assert same(vals, svals), "frame %d: particle fields" % f
+        vo, svo = one.voxel_objects(), cl.voxel_objects()
+        assert same(vo[:, :4], svo[:, :4]), "frame %d: occupancy / mean velocity" % f
+        assert all(m.counters()["overflow"] == 0 for m in cl.maps)
+        n, xyz, fut = one.getOccupancyMapWithFutureStatus(0.2)
+        for r, (k, sxyz, sfut) in enumerate(cl.occupancy(0.2)):
+            assert k == n and same(xyz, sxyz), "frame %d rank %d: occupied-voxel list" % (f, r)
+            assert np.array_equal(fut != 0, sfut != 0) and np.allclose(fut, sfut, rtol=4e-6, atol=0), "frame %d rank %d: future grid" % (f, r)
+    info = cl.maps[0].shard_info()
+    assert info["frames"] == frames and (frames < 3 or info["gather_records"] < info["cap_g"])   # the gather shrank to the predicted size
+    one.close()
+    cl.close()
