@@ -27,10 +27,11 @@ thread_local std::string g_err;
 
 enum Family {
     FAM_SETUP = 0, FAM_OBS, FAM_ENUM, FAM_PREDICT, FAM_ARRIVE, FAM_PYRAMID, FAM_CK, FAM_WEIGHT, FAM_NORM, FAM_NEWBORN,
-    FAM_RESAMPLE, FAM_CLEANUP, FAM_READER, FAM_MISC, FAM_COUNT
+    FAM_RESAMPLE, FAM_CLEANUP, FAM_READER, FAM_MISC, FAM_COLL, FAM_COUNT
 };
 const char *kFamilyNames[FAM_COUNT] = {"setup", "obs_bin", "enumerate", "predict", "arrive", "pyramid_lists", "ck_pass",
-                                       "weight_pass", "newborn_norm", "newborn", "resample_future", "cleanup", "reader", "misc"};
+                                       "weight_pass", "newborn_norm", "newborn", "resample_future", "cleanup", "reader", "misc",
+                                       "collectives"};
 
 struct ProfSlot {
     cudaEvent_t a, b;
@@ -124,6 +125,7 @@ struct dspmap {
     bool est_thread = true;       // velocity estimation on the helper thread, beside the enqueueing of the frame (DSPMAP_EST_THREAD=0: calling thread)
     HostWorker worker;
     FrameConst shard_fc;  // frame scalars carried across the phases of a sharded frame
+    const float *shard_pts = nullptr;  // this frame's cloud (device), for the binning kernels of phase 1
     int shard_cap_g = 0;
     long long host_u_cur = 0;  // uniform draws consumed on the host while seeding
     VelocityEstimator estimator;
@@ -1066,13 +1068,8 @@ int dspmap_shard_phase(dspmap *m, int phase, int n, const float *d_pts, float px
     if (phase == 0) {
         dp.pts = d_pts;
         m->launches_frame = 0;
+        m->shard_pts = d_pts;
         LAUNCH(m, FAM_SETUP, k_frame_setup, 1, 256, 0, mc, fc, dp);
-        if (fc.n_points > 0) LAUNCH(m, FAM_OBS, k_obs_classify, grid_for(fc.n_points, B), B, 0, mc, fc, dp);
-        LAUNCH(m, FAM_OBS, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{dp.obs_cnt, dp.obs_off, dp.obs_capoff, mc.OBS - 1, mc.P}, ScanJob{}, ScanJob{}}});
-        if (fc.n_points > 0) {
-            LAUNCH(m, FAM_OBS, k_obs_scatter, grid_for(fc.n_points, B), B, 0, mc, fc, dp);
-            LAUNCH(m, FAM_OBS, k_obs_rank, grid_for(fc.n_points, B), B, 0, mc, fc, dp);
-        }
         if (fc.vz_mode) {
             LAUNCH(m, FAM_PREDICT, k_vz_count, grid_for(mc.V, B), B, 0, mc, dp);
             LAUNCH(m, FAM_PREDICT, k_scan_blocksum, m->vz_blocks, 256, 0, dp.vzcnt, mc.V, dp.vzblk);
@@ -1082,12 +1079,22 @@ int dspmap_shard_phase(dspmap *m, int phase, int n, const float *d_pts, float px
         LAUNCH(m, FAM_ENUM, k_enumerate, grid_for(mc.V, B), B, 0, mc, dp, 1);
         LAUNCH(m, FAM_PREDICT, k_predict, kSMs * 8, B, 0, mc, fc, dp);
         if (fc.vz_mode) LAUNCH(m, FAM_PREDICT, k_vz_advance, 1, 32, 0, mc, dp);
+        LAUNCH(m, FAM_PREDICT, k_shard_headers, 1, 32, 0, mc, dp);  // the slab headers now bound every rank's registered particles
     } else if (phase == 1) {
+        dp.pts = m->shard_pts;
         LAUNCH(m, FAM_ARRIVE, k_shard_import, grid_for((long long)mc.nranks * mc.cap_x, B), B, 0, mc, dp);
         LAUNCH(m, FAM_ARRIVE, k_group_owner, kSMs * 2, B, 0, dp, &dp.st->n_mov_owner, dp.mowner, dp.mcnt, dp.mbase, &dp.st->mov_top);
         LAUNCH(m, FAM_ARRIVE, k_group_scatter, kSMs * 4, B, 0, &dp.st->n_mov, dp.MBdst, dp.MBkey, dp.mbase, dp.mfill, dp.mseg, (int *)nullptr);
         LAUNCH(m, FAM_ARRIVE, k_arrive, kSMs * 4, B, 0, mc, fc, dp);
         LAUNCH(m, FAM_PYRAMID, k_shard_pack_fov, kSMs * 4, B, 0, mc, dp);
+        // observation binning (replicated on every rank) sits here so that the device has work while the host waits for the
+        // size of the all-gather (shard_host.inc: shard_frame)
+        if (fc.n_points > 0) LAUNCH(m, FAM_OBS, k_obs_classify, grid_for(fc.n_points, B), B, 0, mc, fc, dp);
+        LAUNCH(m, FAM_OBS, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{dp.obs_cnt, dp.obs_off, dp.obs_capoff, mc.OBS - 1, mc.P}, ScanJob{}, ScanJob{}}});
+        if (fc.n_points > 0) {
+            LAUNCH(m, FAM_OBS, k_obs_scatter, grid_for(fc.n_points, B), B, 0, mc, fc, dp);
+            LAUNCH(m, FAM_OBS, k_obs_rank, grid_for(fc.n_points, B), B, 0, mc, fc, dp);
+        }
     } else if (phase == 2) {
         LAUNCH(m, FAM_PYRAMID, k_shard_fov_gathered, kSMs * 8, B, 0, mc, dp, 0);
         LAUNCH(m, FAM_PYRAMID, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{dp.pcount, dp.poff, nullptr, 0, mc.P}, ScanJob{}, ScanJob{}}});

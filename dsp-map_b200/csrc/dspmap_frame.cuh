@@ -34,6 +34,7 @@ __global__ void k_frame_setup(MapConst mc, FrameConst fc, DevPtrs dp) {
         s->n_vz = s->n_skipped = 0;
         s->n_occ_voxels = 0;
         s->ticket = 0;
+        s->n_mov_fov = 0;
         s->work_eval = s->work_eval2 = s->work_w2 = 0;
         s->total_pairs = 0ull;
         s->use_store = 0;
@@ -365,6 +366,7 @@ __global__ void k_predict(MapConst mc, FrameConst fc, DevPtrs dp) {
                 continue;
             }
             if (q >= 0 && !mc.sharded) atomicAdd(&dp.pub[q], 1);  // upper bound of the pyramid's list length (arrive_needs_replay)
+            if (q >= 0 && mc.sharded) agg_inc(&dp.st->n_mov_fov);
             int k = agg_inc(&dp.st->n_mov);
             dp.MBA[k] = A;
             dp.MBB[k] = B;
@@ -602,6 +604,38 @@ __global__ void k_shard_import(MapConst mc, DevPtrs dp) {
         dp.MBdst[k] = d;
         dp.MBq[k] = reinterpret_cast<const int *>(rec)[10];
         if (atomicAdd(&dp.mcnt[d], 1) == 0) dp.mowner[agg_inc(&dp.st->n_mov_owner)] = d;
+    }
+}
+// end of phase 0: every exchange slab's header carries, besides its own count of boundary crossers, what the receiver needs
+// to bound ANY rank's number of registered particles without another exchange: this rank's own candidates (particles that
+// stayed in the field of view + local movers heading for a pyramid) and the crossers it sends in total
+__global__ void k_shard_headers(MapConst mc, DevPtrs dp) {
+    pdl_enter();
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const int slab = SLAB_HDR + mc.cap_x * XREC;
+        int total = 0;
+        for (int r = 0; r < mc.nranks; ++r) total += min(reinterpret_cast<int *>(dp.xsend + (size_t)r * slab)[0], mc.cap_x);
+        for (int r = 0; r < mc.nranks; ++r) {
+            int *h = reinterpret_cast<int *>(dp.xsend + (size_t)r * slab);
+            h[1] = dp.st->n_fov + dp.st->n_mov_fov;
+            h[2] = total;
+        }
+    }
+}
+// after the all-to-all: max over the ranks of (own candidates) + all crossers of the frame >= any rank's registered particles;
+// the same number on every rank (every rank holds every sender's header)
+__global__ void k_shard_bound(MapConst mc, DevPtrs dp, int *out) {
+    pdl_enter();
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const int slab = SLAB_HDR + mc.cap_x * XREC;
+        int own = 0, cross = 0;
+        for (int r = 0; r < mc.nranks; ++r) {
+            const int *h = reinterpret_cast<const int *>((r == mc.rank ? dp.xsend : dp.xrecv) + (size_t)r * slab);
+            own = max(own, h[1]);
+            cross += h[2];
+        }
+        dp.st->gather_max = own + cross;
+        *out = own + cross;
     }
 }
 __global__ void k_shard_pack_fov(MapConst mc, DevPtrs dp) {

@@ -209,9 +209,9 @@ int dspmap_shard_phase(dspmap *m, int phase, int n, const float *d_pts, float px
 
 /* ---- the same, orchestrated by the library (C++ host): one call per frame, collectives inside -------------------------------
  * One process + one handle per GPU; the six phases and their collectives are issued from C++ on the handle's stream with
- * NCCL (libnccl.so.2 is opened with dlopen by dspmap_shard_init: no link-time dependency), with no host synchronisation
- * inside a frame: the all-gather of frame k is sized from the largest per-rank count of frame k-2, which every rank read
- * from the same gathered headers (a frame that outgrows it is flagged: capacity code 16).  Exchange buffers belong to the
+ * NCCL (libnccl.so.2 is opened with dlopen by dspmap_shard_init: no link-time dependency).  One host synchronisation per
+ * frame, with device work queued behind it: the headers of the boundary exchange let every rank compute the same upper
+ * bound of any rank's registered particles, which sizes the all-gather exactly.  Exchange buffers belong to the
  * library.  cap_x / cap_g <= 0 pick defaults (4096 crossers per rank pair; live-list capacity / nranks).
  *   rank 0:      dspmap_shard_unique_id(id)  ->  hand the DSPMAP_NCCL_ID_BYTES bytes to every rank (MPI, a file, a socket, ...)
  *   every rank:  dspmap_create(...); dspmap_shard_init(m, rank, nranks, id, 0, 0);

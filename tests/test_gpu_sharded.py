@@ -82,6 +82,25 @@ def test_library_orchestrated_sharded_map_equals_single_gpu(name, nranks, frames
             assert k == n and same(xyz, sxyz), "frame %d rank %d: occupied-voxel list" % (f, r)
             assert np.array_equal(fut != 0, sfut != 0) and np.allclose(fut, sfut, rtol=4e-6, atol=0), "frame %d rank %d: future grid" % (f, r)
     info = cl.maps[0].shard_info()
-    assert info["frames"] == frames and (frames < 3 or info["gather_records"] < info["cap_g"])   # the gather shrank to the predicted size
+    assert info["frames"] == frames and (frames < 3 or info["gather_records"] < info["cap_g"])   # the gather moves what the exchange headers bound, not the slab capacity
     one.close()
     cl.close()
+
+
+def test_library_orchestrated_sharded_map_over_nccl():
+    """The same orchestrator over NCCL, one process per GPU (tests/shard_nccl_cpp_check.py under torchrun): needs a box with at
+    least two GPUs, skipped otherwise."""
+    import json
+    import os
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("one GPU visible: the NCCL back end needs two (the local back end above runs the same orchestration code)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(min(n, 4)), "--master-addr", "127.0.0.1",
+                        "--master-port", "29513", os.path.join(root, "tests", "shard_nccl_cpp_check.py"), "cfg2", "5"],
+                       capture_output=True, text=True, timeout=600)
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert r.returncode == 0 and line and json.loads(line[-1])["bit_identical"], r.stdout[-2000:] + r.stderr[-2000:]

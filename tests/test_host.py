@@ -166,3 +166,49 @@ def test_estimator_on_the_helper_thread_equals_the_calling_thread():
         b.estimate(pts, (0, 0, 0), 100.0 + 0.1 * k, (1, 0, 0, 0))
         if k % 500 == 499:
             time.sleep(0.005)
+
+
+def test_double_division_rounds_like_float_division_for_tiny_dividends():
+    """dsp_quot (dspmap_frame.cuh: the weight pass's quotient (P_d * g) / C_z) replaces the IEEE fp32 division of a tiny
+    dividend by a division in double rounded to float once more.  For the quotient of two floats that double rounding is
+    innocuous (53 >= 2*24 + 2 bits), subnormal results included; here it is checked against the host's IEEE fp32 division on
+    the dividends the kernel sends down that path (0 < a < 2^-90) and both C_z-like and arbitrary normal divisors."""
+    rng = np.random.default_rng(1)
+    n = 2_000_000
+    a = rng.integers(1, (127 - 90) << 23, n, dtype=np.uint32).view(np.float32)
+    for b in (np.exp(rng.uniform(np.log(1e-3), np.log(1e6), n)).astype(np.float32),
+              rng.integers(1 << 23, 0x7f000000, n, dtype=np.uint32).view(np.float32)):
+        with np.errstate(all="ignore"):
+            q32 = a / b
+            q64 = (a.astype(np.float64) / b.astype(np.float64)).astype(np.float32)
+        assert np.float32(1e-40) / np.float32(3) != 0          # the host honours subnormals
+        assert np.array_equal(q32.view(np.uint32), q64.view(np.uint32))
+
+
+def test_pdf_index_clamp_can_move_behind_the_conversion():
+    """dsp_pdf_i (dspmap_frame.cuh) computes queryNormalPDF's table index (dsp_dynamic.h:1294-1300) as
+    min(|trunc(cx*1000 + 10000) - 10000|, 9900) with a saturating conversion instead of clamping cx to +-9.9 first.  The two
+    agree for every finite float; the full sweep over all 2^32 bit patterns takes five minutes in numpy (it was run once,
+    0 mismatches), here every float with 9 <= |cx| <= 11 (where the clamp acts), every 4099th bit pattern elsewhere and the
+    extremes are checked."""
+    f32 = np.float32
+
+    def both(cx):
+        c = np.where(cx > f32(9.9), f32(9.9), np.where(cx < f32(-9.9), f32(-9.9), cx)).astype(f32)
+        with np.errstate(all="ignore"):
+            i1 = np.abs(np.trunc((c * f32(1000) + f32(10000)).astype(f32)).astype(np.int64) - 10000)
+            t2 = (cx * f32(1000) + f32(10000)).astype(f32)
+        i = np.clip(np.trunc(np.clip(np.nan_to_num(t2, nan=0.0, posinf=3e9, neginf=-3e9), -2147483648.0, 2147483647.0)).astype(np.int64),
+                    -2147483648, 2147483647)
+        j = ((i - 10000 + 2 ** 31) % 2 ** 32) - 2 ** 31   # 32-bit wrap-around of the subtraction
+        return i1, np.minimum(np.abs(j), 9900)
+
+    lo, hi = np.array([9.0, 11.0], f32).view(np.uint32)
+    near = np.arange(lo, hi + 1, dtype=np.uint32)
+    sparse = np.arange(0, 0x7f800000, 4099, dtype=np.uint32)
+    extremes = np.array([0, 1, 0x007fffff, 0x00800000, 0x7f7fffff, 0x4f000000, 0x4effffff, 0x5f000000], np.uint32)
+    for bits in (near, sparse, extremes):
+        for sign in (0, 0x80000000):
+            cx = (bits | np.uint32(sign)).view(f32)
+            a, b = both(cx)
+            assert np.array_equal(a, b)
