@@ -89,6 +89,7 @@ struct dspmap {
     float *d_xyz = nullptr, *d_future = nullptr;
     int occ_blocks = 0;
     int occ_guess = 4096;  // occupied voxels copied along with the count (twice the last count): one round trip, not two
+    long long last_d2h_bytes = 0;  // what the last blocking reader call moved over PCIe (count, list, future grid or its rows)
     // sparse copy-out of the future grid into a registered (page-locked) caller buffer (DSPMAP_SPARSE_FUTURE=1)
     int *d_fcnt = nullptr, *d_foff = nullptr, *d_fidx = nullptr, *d_nf = nullptr, *h_fidx = nullptr, *h_nf = nullptr;
     float *d_fval = nullptr, *h_fval = nullptr;
@@ -1245,11 +1246,15 @@ int dspmap_get_occupancy(dspmap *m, float thr, float *xyz_out, int cap, int *n_o
         }
         m->fut_guess = std::max(8192, 2 * nf);
         m->sparse_rows.apply(future, mc.V, mc.T, m->h_fidx, m->h_fval, nf);
+        m->last_d2h_bytes = 4 + (long long)std::max(nf, fguess) * (4 + 4 * mc.T);
+    } else {
+        m->last_d2h_bytes = future ? (long long)fbytes : 0;
     }
     if (m->update_counter > 0 && m->state_event_recorded) absorb_state(m);  // the frame's state copy has landed by now
     int n = *m->h_count;
     if (n_out) *n_out = n;
     int ncopy = std::min(n, cap);
+    m->last_d2h_bytes += 4 + 12ll * std::max(ncopy, guess);
     m->occ_guess = std::max(4096, 2 * n);
     if (xyz_out && ncopy > 0) {
         if (ncopy > guess) {
@@ -1320,6 +1325,7 @@ int dspmap_wait_occupancy(dspmap *m, int ticket, const float **xyz, int *n_out, 
     if (m->profile) prof_collect(m);
     return DSPMAP_OK;
 }
+long long dspmap_last_reader_bytes(dspmap *m) { return m ? m->last_d2h_bytes : 0; }
 int dspmap_pin_host_buffer(dspmap *m, void *ptr, size_t bytes) {
     if (!m) return DSPMAP_E_BAD_ARG;
     if (m->pinned_user) {

@@ -72,6 +72,7 @@ def load_library():
         "dspmap_get_occupancy_async": (i, [vp, f, i, ip]),
         "dspmap_wait_occupancy": (i, [vp, i, C.POINTER(fp), ip, C.POINTER(fp)]),
         "dspmap_clear_prediction": (i, [vp]),
+        "dspmap_last_reader_bytes": (C.c_longlong, [vp]),
         "dspmap_pin_host_buffer": (i, [vp, vp, C.c_size_t]),
         "dspmap_get_tagged_cloud": (i, [vp, fp, i]),
         "dspmap_voxel_center": (None, [vp, i, fp]),
@@ -133,7 +134,7 @@ EXPORTED_SYMBOLS = [
     "dspmap_set_newborn_weight", "dspmap_set_newborn_number", "dspmap_set_particle_record_flag",
     "dspmap_set_voxel_filter_resolution", "dspmap_get_occupancy", "dspmap_get_occupancy_device",
     "dspmap_get_occupancy_async", "dspmap_wait_occupancy",
-    "dspmap_clear_prediction", "dspmap_pin_host_buffer", "dspmap_get_tagged_cloud", "dspmap_voxel_center", "dspmap_voxel_index", "dspmap_uniform",
+    "dspmap_clear_prediction", "dspmap_last_reader_bytes", "dspmap_pin_host_buffer", "dspmap_get_tagged_cloud", "dspmap_voxel_center", "dspmap_voxel_index", "dspmap_uniform",
     "dspmap_dims", "dspmap_dump_particles", "dspmap_load_particles", "dspmap_dump_voxel_objects",
     "dspmap_dump_observations", "dspmap_dump_pyramid_lists", "dspmap_dump_plane_normals", "dspmap_cursors", "dspmap_set_cursors", "dspmap_counters",
     "dspmap_set_stage_limit", "dspmap_set_last_pose", "dspmap_set_stream", "dspmap_synchronize", "dspmap_profile_enable", "dspmap_profile_read", "dspmap_profile_read_kernels",
@@ -349,6 +350,10 @@ class DSPMap:
         c = np.zeros(16, np.int64)
         self._check(self.lib.dspmap_counters(self.h, c.ctypes.data_as(C.POINTER(C.c_int64))))
         return dict(zip(COUNTER_NAMES, [int(x) for x in c]))
+
+    def last_future_bytes(self):
+        """Device-to-host bytes of the last blocking reader call (dspmap_last_reader_bytes)."""
+        return int(self.lib.dspmap_last_reader_bytes(self.h))
 
     def fast_paths(self):
         """(fast_res, fast_sigma): whether the exhaustively verified exact fast divisions are enabled (sigma: after the next update)."""

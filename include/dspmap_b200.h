@@ -131,6 +131,9 @@ int dspmap_wait_occupancy(dspmap *m, int ticket, const float **xyz, int *n, cons
  * buffer as read-only between calls (the reference application only reads it, map_sim_example.cpp:371-437). */
 int dspmap_pin_host_buffer(dspmap *m, void *ptr, size_t bytes);
 /* clearOccupancyMapPrediction (:431-438). */
+/* Bytes the last dspmap_get_occupancy call moved from the device to the host (count, occupied list incl. its speculative
+ * prefix, and the future grid: dense, or only its non-zero rows when the caller's array is registered). */
+long long dspmap_last_reader_bytes(dspmap *m);
 int dspmap_clear_prediction(dspmap *m);
 /* getKMClusterResult (:441-445): copies the last newborn input; returns the number of points. */
 int dspmap_get_tagged_cloud(dspmap *m, float *out, int cap);
