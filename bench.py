@@ -390,8 +390,11 @@ def main_single(args, cfg_name, dm, make_stream):
         "prefilter": prefilter,
     }
     bm = os.path.join(ROOT, "profiles", "build_manifest.json")
-    if os.path.exists(bm):
-        line["build"] = json.load(open(bm))
+    if os.path.exists(bm):  # flags / compiler of the last build, and the hash of the library this process actually loaded
+        import hashlib
+        man = json.load(open(bm))
+        line["build"] = {"nvcc": man["nvcc"], "flags": " ".join(man["flags"]), "sha256_manifest": man["sha256"],
+                         "sha256_loaded": hashlib.sha256(open(dm.LIB_PATH, "rb").read()).hexdigest()}
     if not args.no_cpu_baseline:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import refmap

@@ -39,7 +39,24 @@ def build(force=False, verbose=False, defines=(), out=None):
     target = out or SO
     cmd = [NVCC] + FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + sources() + ["-o", target]
     subprocess.check_call(cmd)
+    if out is None:
+        write_manifest()
     return target
+
+
+def write_manifest():
+    """profiles/build_manifest.json: what exactly was compiled (bench.py copies it into its JSON line)."""
+    import hashlib
+    import json
+    ver = subprocess.run([NVCC, "--version"], capture_output=True, text=True).stdout.strip().splitlines()[-2:]
+    h = hashlib.sha256(open(SO, "rb").read()).hexdigest()
+    srcs = {os.path.basename(f): hashlib.sha256(open(os.path.join(SRC, f), "rb").read()).hexdigest()[:16] for f in sorted(os.listdir(SRC))}
+    man = {"library": "dsp-map_b200/lib/libdspmap_b200.so", "sha256": h, "nvcc": " / ".join(ver), "flags": FLAGS, "sources_sha256_16": srcs}
+    path = os.path.join(HERE, "..", "profiles", "build_manifest.json")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    with open(path, "w") as f:
+        json.dump(man, f, indent=1)
+        f.write("\n")
 
 
 if __name__ == "__main__":

@@ -1848,87 +1848,36 @@ __global__ void k_nb_fill(MapConst mc, FrameConst fc, DevPtrs dp, u64 useed) {
     }
 }
 // addAParticle (:1183-1201) in serial order: the k-th candidate of a voxel (in (point, candidate) order) takes its k-th free
-// slot.  One warp per destination voxel; at cfg2 a voxel has ~100 candidates and ~20 free slots.  Keys are unique 32-bit
-// integers, so the minimum key alone identifies the next winner: __reduce_min_sync (REDUX) gives it to every lane at once and
-// the lane that holds it keeps the slot for its own candidate.  Voxels without a free slot are left before their keys are loaded.
+// slot.  One thread per candidate, walking the grouped segments: it counts the keys of its voxel's segment below its own
+// (keys are unique; neighbouring threads share the segment, so the reads are broadcasts from L1), and if that rank is below
+// the number of free slots of the voxel's mask — the snapshot MS the grouping pass took, i.e. the mask after the arrival pass
+// — it takes the rank-th free slot.  No rounds, no shuffles: every candidate decides for itself.
+// (Round 1 gave a warp to each destination voxel and extracted the minimum key once per free slot: 38 us at cfg2.)
 __global__ void __launch_bounds__(256) k_nb_place(MapConst mc, FrameConst fc, DevPtrs dp) {
     pdl_enter();
-    const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-    const int nown = dp.st->n_cand_owner;
+    const int n = min(dp.st->cand_top, dp.cap_cand);
     int born = 0;
-    for (int o = warp; o < nown; o += nwarps) {
-        const int d = dp.cowner[o];
-        const int b = dp.cbase[d], c = dp.ccnt[d];
-        ulonglong2 msk = dp.M[d];
-        const int nfree = min(mask_free(mc, msk), c);
+    for (int pos = blockIdx.x * blockDim.x + threadIdx.x; pos < n; pos += gridDim.x * blockDim.x) {
+        const int cand = dp.csegi[pos];
+        const int d = dp.Cdst[cand];
+        const ulonglong2 msk = dp.MS[d];
+        const int nfree = mask_free(mc, msk);
         if (nfree == 0) continue;
-        if (c <= 256) {  // the usual case: the segment's keys live in registers for all rounds
-            unsigned K[8];
-            int slot_q[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int j = q * 32 + lane;
-                K[q] = j < c ? (unsigned)dp.cseg[b + j] : 0xffffffffu;
-                slot_q[q] = -1;
-            }
-            for (int r = 0; r < nfree; ++r) {
-                unsigned loc = K[0];
-#pragma unroll
-                for (int q = 1; q < 8; ++q) loc = min(loc, K[q]);
-                const unsigned best = __reduce_min_sync(FULLMASK, loc);  // r < nfree <= c: a valid key is left
-                const int slot = mask_nth_free(mc, msk, 0);
-                if (slot < 64) msk.x |= 1ull << slot; else msk.y |= 1ull << (slot - 64);
-#pragma unroll
-                for (int q = 0; q < 8; ++q)
-                    if (K[q] == best) { slot_q[q] = slot; K[q] = 0xffffffffu; }
-            }
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-                if (slot_q[q] >= 0) {
-                    const int cand = dp.csegi[b + q * 32 + lane];
-                    const int a = d * mc.S + slot_q[q];
-                    dp.PA[a] = dp.CA[cand];                        // position; the weight follows in k_nb_fill
-                    dp.PB[a] = make_float4(0.f, 0.f, 0.f, 15.f);   // newborn flag now, velocity in k_nb_fill
-                    dp.Caddr[cand] = a;
-                }
-        } else {  // oversized segment: every round rescans it in global memory (rare)
-            long long last = -1;
-            int my_slot[4] = {-1, -1, -1, -1}, my_cand[4] = {0, 0, 0, 0};
-            for (int r = 0; r < nfree; ++r) {
-                u64 best = ~0ull;  // (key << 32) | position
-                for (int j = lane; j < c; j += 32) {
-                    const long long kj = dp.cseg[b + j];
-                    if (kj > last) best = min(best, ((u64)kj << 32) | (unsigned)j);
-                }
-                for (int sft = 16; sft > 0; sft >>= 1) best = min(best, __shfl_xor_sync(FULLMASK, best, sft));
-                last = (long long)(best >> 32);
-                const int slot = mask_nth_free(mc, msk, 0);
-                if (slot < 64) msk.x |= 1ull << slot; else msk.y |= 1ull << (slot - 64);
-                if (lane == (r & 31)) {
-                    const int q = r >> 5;
-                    const int cand = dp.csegi[b + (int)(best & 0xffffffffull)];
-                    if (q == 0) { my_slot[0] = slot; my_cand[0] = cand; }
-                    else if (q == 1) { my_slot[1] = slot; my_cand[1] = cand; }
-                    else if (q == 2) { my_slot[2] = slot; my_cand[2] = cand; }
-                    else { my_slot[3] = slot; my_cand[3] = cand; }
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (my_slot[q] >= 0) {
-                    const int a = d * mc.S + my_slot[q];
-                    dp.PA[a] = dp.CA[my_cand[q]];
-                    dp.PB[a] = make_float4(0.f, 0.f, 0.f, 15.f);
-                    dp.Caddr[my_cand[q]] = a;
-                }
-        }
-        if (lane == 0) {
-            dp.M[d] = msk;
-            born += nfree;
-        }
+        const int b = dp.cbase[d], c = dp.ccnt[d], key = dp.cseg[pos];
+        int rank = 0;
+#pragma unroll 4
+        for (int j = 0; j < c; ++j) rank += dp.cseg[b + j] < key;
+        if (rank >= nfree) continue;
+        const int slot = mask_nth_free(mc, msk, rank);
+        const int a = d * mc.S + slot;
+        dp.PA[a] = dp.CA[cand];                        // position; the weight follows in k_nb_fill
+        dp.PB[a] = make_float4(0.f, 0.f, 0.f, 15.f);   // newborn flag now, velocity in k_nb_fill
+        dp.Caddr[cand] = a;
+        mask_atomic_set(dp.M, d, slot);
+        ++born;
     }
-    if (lane == 0 && born) atomicAdd(&dp.st->n_born, born);
+    for (int sft = 16; sft > 0; sft >>= 1) born += __shfl_down_sync(FULLMASK, born, sft);
+    if ((threadIdx.x & 31) == 0 && born) atomicAdd(&dp.st->n_born, born);
 }
 // ------------------------------------------------------------------------------------------------------------
 // K7a list of occupied voxels (balances K7: occupied voxels are x-adjacent, so a strided sweep would hand one warp up
