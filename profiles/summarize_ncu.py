@@ -33,7 +33,7 @@ def main():
             for m, label in METRICS:
                 if m in h:
                     print("- %s: %s %s" % (label, r[h.index(m)], units[h.index(m)]))
-            hot = subprocess.run([sys.executable, __file__.replace("summarize_ncu.py", "hot_lines.py"), rep, short.split("<")[0] + "[(<]", "8"],
+            hot = subprocess.run([sys.executable, __file__.replace("summarize_ncu.py", "hot_lines.py"), rep, "^" + short.split("<")[0] + "$", "8"],
                                  capture_output=True, text=True).stdout.splitlines()
             print("\n```")
             for line in hot[1:]:
