@@ -17,6 +17,7 @@
 
 #include "../../include/dspmap_b200.h"
 #include "dspmap_frame.cuh"
+#include "dspmap_estimator.cuh"
 #include "velocity_estimator.h"
 #include "host_worker.h"
 #include "sparse_rows.h"
@@ -27,11 +28,11 @@ thread_local std::string g_err;
 
 enum Family {
     FAM_SETUP = 0, FAM_OBS, FAM_ENUM, FAM_PREDICT, FAM_ARRIVE, FAM_PYRAMID, FAM_CK, FAM_WEIGHT, FAM_NORM, FAM_NEWBORN,
-    FAM_RESAMPLE, FAM_CLEANUP, FAM_READER, FAM_MISC, FAM_COLL, FAM_COUNT
+    FAM_RESAMPLE, FAM_CLEANUP, FAM_READER, FAM_MISC, FAM_COLL, FAM_EST, FAM_COUNT
 };
 const char *kFamilyNames[FAM_COUNT] = {"setup", "obs_bin", "enumerate", "predict", "arrive", "pyramid_lists", "ck_pass",
                                        "weight_pass", "newborn_norm", "newborn", "resample_future", "cleanup", "reader", "misc",
-                                       "collectives"};
+                                       "collectives", "velocity_estimation"};
 
 struct ProfSlot {
     cudaEvent_t a, b;
@@ -89,6 +90,7 @@ struct dspmap {
     float *d_xyz = nullptr, *d_future = nullptr;
     int occ_blocks = 0;
     int occ_guess = 4096;  // occupied voxels copied along with the count (twice the last count): one round trip, not two
+    long long upd_h2d_bytes = 0, upd_d2h_bytes = 0;  // what the last dspmap_update call moved over PCIe (cloud, newborn input or cluster velocities; cluster features)
     long long last_d2h_bytes = 0;  // what the last blocking reader call moved over PCIe (count, list, future grid or its rows)
     // sparse copy-out of the future grid into a registered (page-locked) caller buffer (DSPMAP_SPARSE_FUTURE=1)
     int *d_fcnt = nullptr, *d_foff = nullptr, *d_fidx = nullptr, *d_nf = nullptr, *h_fidx = nullptr, *h_nf = nullptr;
@@ -123,6 +125,9 @@ struct dspmap {
     bool async_update = true;     // dspmap_update returns once the frame is enqueued; the next call that needs results waits (DSPMAP_ASYNC_UPDATE=0: wait in update)
     bool staged_pending = false;  // the page-locked staging buffers are still being read by the previous frame's copies
     cudaEvent_t ev_staged = nullptr;
+    int nb_pos = 0;               // where frame_a enqueues the early newborn kernels (DSPMAP_NB_POS: 0 behind the estimator, 1 before the weight pass, 2 last)
+    bool norm_poll = true;        // k_norm beside the C_z pass, waiting for each 1 / C_z (DSPMAP_NORM_POLL=0: behind it)
+    bool timeline = false;        // DSPMAP_TIMELINE=1: the frame's events carry timestamps (dspmap_timeline; diagnosis only)
     bool est_thread = true;       // velocity estimation on the helper thread, beside the enqueueing of the frame (DSPMAP_EST_THREAD=0: calling thread)
     HostWorker worker;
     FrameConst shard_fc;  // frame scalars carried across the phases of a sharded frame
@@ -130,6 +135,22 @@ struct dspmap {
     int shard_cap_g = 0;
     long long host_u_cur = 0;  // uniform draws consumed on the host while seeding
     VelocityEstimator estimator;
+    // front half of the velocity estimation on the device (dspmap_estimator.cuh; DSPMAP_EST_GPU=0: host implementation)
+    bool est_gpu = true;
+    EstPtrs est;
+    EstConst est_ec;              // this frame's constants (prepare_estimator)
+    bool est_cluster = false;
+    unsigned est_hash_mask = 0;
+    size_t est_hash_bytes = 0;
+    int est_n_pad = 0;            // entries of the device tagged cloud that are initialised (real ones + padding)
+    int est_nt_explicit = -1;     // >= 0: the tagged cloud on the device was supplied by the caller and has this many entries
+    int est_n_real = 0;           // real entries of the device tagged cloud
+    bool tagged_host_stale = false;  // tagged_host has to be fetched from the device (getKMClusterResult)
+    int *est_h_hdr = nullptr;
+    EstFeature *est_h_feat = nullptr;
+    float *est_h_cvel = nullptr;
+    float4 *est_d_cvel = nullptr;
+    cudaEvent_t ev_feat = nullptr;
     // statistics
     long long launches_total = 0, launches_frame = 0;
     DevState last_state;
@@ -221,7 +242,7 @@ int report_overflow(dspmap *m) {
     if (!m->overflow_latched) return DSPMAP_OK;
     char buf[256];
     snprintf(buf, sizeof(buf), "device capacity exceeded: code %d (1 live list, 2 newborn candidates, 4 pair buffer without fallback, "
-             "8 shard crossers, 16 shard gather, 32 pyramid-list overflow on a sharded map); pairs last frame %llu, capacity %lld", m->overflow_latched,
+             "8 shard crossers, 16 shard gather, 32 pyramid-list overflow on a sharded map, 64 normaliser never saw the C_z pass); pairs last frame %llu, capacity %lld", m->overflow_latched,
              m->last_state.total_pairs, m->mc.cap_pairs);
     g_err = buf;
     m->overflow_latched = 0;
@@ -384,6 +405,90 @@ int ensure_cand_capacity(dspmap *m) {
     return DSPMAP_OK;
 }
 
+// The tagged cloud was laid out on the device (dspmap_estimator.cuh): bring the host copy up to date.
+int fetch_tagged(dspmap *m) {
+    if (!m->tagged_host_stale) return DSPMAP_OK;
+    CK(cudaSetDevice(m->cfg.device));
+    CK(cudaStreamSynchronize(m->nb));
+    CK(cudaStreamSynchronize(m->stream));
+    m->tagged_host.resize((size_t)7 * m->est_n_real);
+    if (m->est_n_real > 0) CK(cudaMemcpy(m->tagged_host.data(), m->dp.tagged, sizeof(float) * 7 * (size_t)m->est_n_real, cudaMemcpyDeviceToHost));
+    m->tagged_host_stale = false;
+    return DSPMAP_OK;
+}
+// Front half of the velocity estimation (the reference's side thread, dsp_dynamic.h:1377-1447) on the newborn branch: it
+// starts with the frame, beside the prediction chain on the main stream; the early newborn kernels follow it on the same
+// stream.  fc->n_tagged becomes the padded size of the tagged cloud (dspmap_estimator.cuh).
+void prepare_estimator(dspmap *m, FrameConst *fc, int n) {
+    EstConst &ec = m->est_ec;
+    memset(&ec, 0, sizeof(ec));
+    const MapConst &mc = m->mc;
+    const float *planes0 = m->planes0.data();
+    dsp_rotate(planes0, fc->q, fc->qi, ec.nrm);
+    dsp_rotate(planes0 + 3 * mc.Nh, fc->q, fc->qi, ec.nrm + 3);
+    dsp_rotate(planes0 + 3 * (mc.Nh + 1), fc->q, fc->qi, ec.nrm + 6);
+    dsp_rotate(planes0 + 3 * (mc.Nh + 1 + mc.Nv), fc->q, fc->qi, ec.nrm + 9);
+    for (int k = 0; k < 4; ++k) { ec.q[k] = fc->q[k]; ec.qi[k] = fc->qi[k]; }
+    for (int k = 0; k < 3; ++k) ec.cur[k] = fc->cur[k];
+    ec.filter_res = m->estimator.filter_res;
+    const float tol = 2 * m->estimator.filter_res;  // :1411
+    const bool cluster = mc.model != 1 && tol > 0.f && n > 0;
+    ec.tol2 = tol * tol;
+    ec.inv_cell = cluster ? 1.f / (tol * 0.57f) : 1.f;  // cell edge below tolerance / sqrt(3): a cell's points are mutually linked
+    ec.n = n;
+    ec.model = mc.model;
+    ec.hash_mask = m->est_hash_mask;
+    ec.n_pad_prev = m->est_nt_explicit >= 0 ? m->est_nt_explicit : m->est_n_pad;
+    ec.nt_override = m->est_nt_explicit;
+    ec.n_pad = std::max(ec.n_pad_prev, n);
+    m->est_nt_explicit = -1;
+    m->est_n_pad = ec.n_pad;
+    m->est_cluster = cluster;
+    fc->n_tagged = ec.n_pad;
+    fc->tagged_padded = 1;
+}
+int enqueue_estimator(dspmap *m, const float *d_pts) {
+    const EstConst &ec = m->est_ec;
+    const bool cluster = m->est_cluster;
+    const int n = ec.n;
+    EstPtrs ep = m->est;
+    ep.pts = d_pts;
+    cudaStream_t nb = m->nb;
+    const int B = 256;
+    CK(cudaMemsetAsync(ep.hkey, 0xFF, m->est_hash_bytes, nb));
+    CK(cudaMemsetAsync(ep.cnt, 0, sizeof(int) * EC_PER_FRAME, nb));
+    LAUNCH_ON(m, FAM_EST, nb, k_est_classify, grid_for(n, B), B, 0, ec, ep);
+    if (cluster) {
+        LAUNCH_ON(m, FAM_EST, nb, k_est_scatter, grid_for(n, B), B, 0, ec, ep);
+        LAUNCH_ON(m, FAM_EST, nb, k_est_link, grid_for(62ll * n, B, kSMs * 16), B, 0, ec, ep);
+    }
+    LAUNCH_ON(m, FAM_EST, nb, k_est_label, grid_for(n, B), B, 0, ec, ep);
+    LAUNCH_ON(m, FAM_EST, nb, k_est_clusters, 1, 1024, 0, ec, ep);
+    LAUNCH_ON(m, FAM_EST, nb, k_est_features, cluster ? kSMs * 8 : 1, B, 0, ec, ep);
+    CK(cudaEventRecord(m->ev_feat, nb));
+    LAUNCH_ON(m, FAM_EST, nb, k_est_write, grid_for(ec.n_pad, B), B, 0, ec, ep);
+    CK(cudaGetLastError());
+    return DSPMAP_OK;
+}
+// Second half: waits for the cluster centroids, matches them against the previous frame's on the host (Hungarian, :1449-1499)
+// and sends the velocities back; k_est_apply runs on the main stream in front of the kernels that read them.
+int finish_estimator(dspmap *m, const FrameConst &fc) {
+    CK(cudaEventSynchronize(m->ev_feat));
+    const int *hdr = m->est_h_hdr;
+    m->est_n_real = hdr[EC_NTAGGED];
+    m->tagged_host_stale = true;
+    if (hdr[EC_NV] == 0) return DSPMAP_OK;  // nothing in view: the previous cloud, clusters and colours stay (:1379)
+    const int ndyn = hdr[EC_NDYN];
+    m->upd_d2h_bytes = (long long)sizeof(int) * EC_COUNT + (long long)sizeof(EstFeature) * ndyn;  // written by the device into mapped memory
+    m->upd_h2d_bytes += (long long)sizeof(float) * 4 * ndyn;
+    m->estimator.finish_device(m->est_h_feat, ndyn, hdr[EC_NC], fc.dt, m->est_h_cvel);
+    if (ndyn > 0) {
+        CK(cudaMemcpyAsync(m->est_d_cvel, m->est_h_cvel, sizeof(float) * 4 * (size_t)ndyn, cudaMemcpyHostToDevice, m->stream));
+        LAUNCH(m, FAM_EST, k_est_apply, grid_for(hdr[EC_NDYNPTS], 256), 256, 0, m->est);
+    }
+    return DSPMAP_OK;
+}
+
 // The early half of the newborn step on its own branch (see k_nb_cand): in-map test and position-noise cursors of the points,
 // candidate positions, grouping by destination voxel, slot assignment.  Needs the masks after the arrival pass (ev_arrived).
 int enqueue_newborn_early(dspmap *m, const FrameConst &fc, const float *d_tagged) {
@@ -407,7 +512,7 @@ int enqueue_newborn_early(dspmap *m, const FrameConst &fc, const float *d_tagged
 }
 
 // Enqueue the first half of a frame: binning, prediction, reassignment, pyramid lists, C_z pass, weight pass.
-int enqueue_frame_a(dspmap *m, const FrameConst &fc, const float *d_pts, const float *d_tagged_early = nullptr) {
+int enqueue_frame_a(dspmap *m, const FrameConst &fc, const float *d_pts, const float *d_tagged_early = nullptr, bool device_estimator = false) {
     const MapConst &mc = m->mc;
     DevPtrs dp = m->dp;
     dp.pts = d_pts;
@@ -415,22 +520,9 @@ int enqueue_frame_a(dspmap *m, const FrameConst &fc, const float *d_pts, const f
     const int B = 256;
     int rc_nb = DSPMAP_OK;
     LAUNCH(m, FAM_SETUP, k_frame_setup, 1, 256, 0, mc, fc, dp);
-    // observations: binning touches nothing the prediction / reassignment chain reads, and both are chains of small
-    // latency-bound kernels, so they run side by side (joined before the pair preparation, the first consumer of the bins)
     CK(cudaEventRecord(m->ev_fork_obs, m->stream));
-    CK(cudaStreamWaitEvent(m->side, m->ev_fork_obs, 0));
-    if (fc.n_points > 0) {
-        LAUNCH_ON(m, FAM_OBS, m->side, k_obs_classify, grid_for(fc.n_points, B), B, 0, mc, fc, dp);
-    }
-    LAUNCH_ON(m, FAM_OBS, m->side, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{dp.obs_cnt, dp.obs_off, dp.obs_capoff, mc.OBS - 1, mc.P}, ScanJob{}, ScanJob{}}});
-    if (fc.n_points > 0) {
-        LAUNCH_ON(m, FAM_OBS, m->side, k_obs_scatter, grid_for(fc.n_points, B), B, 0, mc, fc, dp);
-        LAUNCH_ON(m, FAM_OBS, m->side, k_obs_rank, grid_for(fc.n_points, B), B, 0, mc, fc, dp);
-    }
-    CK(cudaEventRecord(m->ev_join_obs, m->side));
-    // the newborn branch starts behind this frame's setup (i.e. behind everything of the previous frame)
-    CK(cudaStreamWaitEvent(m->nb, m->ev_fork_obs, 0));
-    m->nb_early_done = false;
+    // (Order of the calls below: when a frame starts on an idle device — the host-pointer API — kernels run as soon as they are
+    // enqueued, so the host feeds the critical chain first: prediction and reassignment, then the two side branches, then the rest.)
     // prediction and reassignment
     if (fc.vz_mode) {
         LAUNCH(m, FAM_PREDICT, k_vz_count, grid_for(mc.V, B), B, 0, mc, dp);
@@ -445,9 +537,23 @@ int enqueue_frame_a(dspmap *m, const FrameConst &fc, const float *d_pts, const f
     LAUNCH(m, FAM_ARRIVE, k_group_scatter, kSMs * 4, B, 0, &dp.st->n_mov, dp.MBdst, dp.MBkey, dp.mbase, dp.mfill, dp.mseg, (int *)nullptr);
     LAUNCH(m, FAM_ARRIVE, k_arrive, kSMs * 4, B, 0, mc, fc, dp);
     CK(cudaEventRecord(m->ev_arrived, m->stream));  // the occupancy masks are final until the newborn placement
-    // With a device-resident newborn input the early newborn kernels (they need the cloud, the noise table and these masks)
-    // run beside the observation passes; with a host cloud they are enqueued by enqueue_frame_b, once the cloud is there
-    if (d_tagged_early && (rc_nb = enqueue_newborn_early(m, fc, d_tagged_early)) != DSPMAP_OK) return rc_nb;
+    // the newborn branch starts behind this frame's setup (i.e. behind everything of the previous frame)
+    CK(cudaStreamWaitEvent(m->nb, m->ev_fork_obs, 0));
+    m->nb_early_done = false;
+    if (device_estimator && (rc_nb = enqueue_estimator(m, d_pts)) != DSPMAP_OK) return rc_nb;  // its tagged cloud feeds the early newborn kernels
+    if (m->nb_pos == 0) { if (d_tagged_early && (rc_nb = enqueue_newborn_early(m, fc, d_tagged_early)) != DSPMAP_OK) return rc_nb; }
+    // observations: binning touches nothing the prediction / reassignment chain reads, and both are chains of small
+    // latency-bound kernels, so they run side by side (joined before the pair preparation, the first consumer of the bins)
+    CK(cudaStreamWaitEvent(m->side, m->ev_fork_obs, 0));
+    if (fc.n_points > 0) {
+        LAUNCH_ON(m, FAM_OBS, m->side, k_obs_classify, grid_for(fc.n_points, B), B, 0, mc, fc, dp);
+    }
+    LAUNCH_ON(m, FAM_OBS, m->side, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{dp.obs_cnt, dp.obs_off, dp.obs_capoff, mc.OBS - 1, mc.P}, ScanJob{}, ScanJob{}}});
+    if (fc.n_points > 0) {
+        LAUNCH_ON(m, FAM_OBS, m->side, k_obs_scatter, grid_for(fc.n_points, B), B, 0, mc, fc, dp);
+        LAUNCH_ON(m, FAM_OBS, m->side, k_obs_rank, grid_for(fc.n_points, B), B, 0, mc, fc, dp);
+    }
+    CK(cudaEventRecord(m->ev_join_obs, m->side));
     if (m->pyr_scan_fused) {  // every block of the scatter kernel scans the pyramid counts itself (shared memory)
         LAUNCH(m, FAM_PYRAMID, k_pyr_scatter, kSMs * 2, B, sizeof(int) * (mc.P + 1), mc, dp, 1);
     } else {
@@ -458,6 +564,14 @@ int enqueue_frame_a(dspmap *m, const FrameConst &fc, const float *d_pts, const f
     CK(cudaStreamWaitEvent(m->stream, m->ev_join_obs, 0));
     if (fc.stage_limit >= 2) {
         LAUNCH(m, FAM_CK, k_pair_prep, 1, 1024, 0, mc, dp);
+        if (fc.stage_limit >= 3 && m->norm_poll) {  // the newborn normaliser is one long serial chain: it runs beside the C_z pass and takes each 1 / C_z as it appears
+            CK(cudaEventRecord(m->ev_fork, m->stream));
+            CK(cudaStreamWaitEvent(m->side, m->ev_fork, 0));
+            launch_kernel(m->pdl, m->side, k_norm, 1, 128, 0, mc, fc, dp, 1);
+            ++m->launches_total;
+            ++m->launches_frame;
+            CK(cudaEventRecord(m->ev_join, m->side));
+        }
         LAUNCH(m, FAM_CK, k_pair_eval, kSMs * 2, EVAL_THREADS, EVAL_SMEM_BYTES, mc, fc, dp, 0);
 #ifdef CZ_TMA
         LAUNCH(m, FAM_CK, k_cz_chain_tma, std::min(mc.P, kSMs * 2), CZT_THREADS, CZT_SMEM_BYTES, mc, fc, dp);
@@ -466,14 +580,15 @@ int enqueue_frame_a(dspmap *m, const FrameConst &fc, const float *d_pts, const f
 #endif
         size_t smem4 = sizeof(float) * (DSP_LUT_HALF + 3 + K4_TERMS) + sizeof(float4) * (256 + mc.OBS);
         if (m->fallback_armed) LAUNCH(m, FAM_CK, k_ck, std::min(mc.P, kSMs * 2), K4_THREADS, smem4, mc, fc, dp);  // returns at once when the pair buffer is used
-        if (fc.stage_limit >= 3) {  // the newborn normaliser is one long serial chain: run it beside the weight pass
+        if (fc.stage_limit >= 3 && !m->norm_poll) {  // DSPMAP_NORM_POLL=0: behind the C_z pass, beside the weight pass
             CK(cudaEventRecord(m->ev_fork, m->stream));
             CK(cudaStreamWaitEvent(m->side, m->ev_fork, 0));
-            launch_kernel(m->pdl, m->side, k_norm, 1, 128, 0, mc, fc, dp);
+            launch_kernel(m->pdl, m->side, k_norm, 1, 128, 0, mc, fc, dp, 0);
             ++m->launches_total;
             ++m->launches_frame;
             CK(cudaEventRecord(m->ev_join, m->side));
         }
+        if (m->nb_pos == 1) { if (d_tagged_early && (rc_nb = enqueue_newborn_early(m, fc, d_tagged_early)) != DSPMAP_OK) return rc_nb; }
 #ifdef W3
         LAUNCH(m, FAM_WEIGHT, k_weight3, kSMs * 2, 32 * W3_WARPS, w3_smem_bytes(mc.OBS), mc, fc, dp);
 #else
@@ -486,6 +601,9 @@ int enqueue_frame_a(dspmap *m, const FrameConst &fc, const float *d_pts, const f
         // the normaliser is first read by k_nb_cand (w_new): it is joined behind the newborn kernels that do not need it
         m->norm_join_pending = fc.stage_limit >= 3;
     }
+    // With a device-resident newborn input the early newborn kernels (they need the cloud, the noise table and the masks after
+    // the arrival pass) run beside the observation passes; with a host cloud they are enqueued by enqueue_frame_b, once the cloud is there
+    if (m->nb_pos >= 2 || (m->nb_pos == 1 && fc.stage_limit < 2)) { if (d_tagged_early && (rc_nb = enqueue_newborn_early(m, fc, d_tagged_early)) != DSPMAP_OK) return rc_nb; }
     CK(cudaGetLastError());
     return DSPMAP_OK;
 }
@@ -715,17 +833,21 @@ int dspmap_create(const dspmap_config *cfg, dspmap **out) {
     mc.vlo = mc.S >= 64 ? ~0ull : ((1ull << mc.S) - 1ull);
     mc.vhi = mc.S <= 64 ? 0ull : (mc.S >= 128 ? ~0ull : ((1ull << (mc.S - 64)) - 1ull));
     m->max_points = cfg->max_points > 0 ? cfg->max_points : 65536;
+    // (Stream priorities were tried — main chain high, newborn branch low — and starved the newborn branch: its early kernels
+    // ended 0.15 ms later and with them the frame; profiles/r02_variants.jsonl.)
     CKM(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
     CKM(cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking));
     CKM(cudaStreamCreateWithFlags(&m->nb, cudaStreamNonBlocking));
-    CKM(cudaEventCreateWithFlags(&m->ev_arrived, cudaEventDisableTiming));
-    CKM(cudaEventCreateWithFlags(&m->ev_nb_early, cudaEventDisableTiming));
+    { const char *tl = getenv("DSPMAP_TIMELINE"); m->timeline = tl && strcmp(tl, "1") == 0; }
+    const unsigned evflags = m->timeline ? cudaEventDefault : cudaEventDisableTiming;
+    CKM(cudaEventCreateWithFlags(&m->ev_arrived, evflags));
+    CKM(cudaEventCreateWithFlags(&m->ev_nb_early, evflags));
     CKM(cudaEventCreateWithFlags(&m->ev_staged_t, cudaEventDisableTiming));
-    CKM(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
-    CKM(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
-    CKM(cudaEventCreateWithFlags(&m->ev_fork_obs, cudaEventDisableTiming));
-    CKM(cudaEventCreateWithFlags(&m->ev_join_obs, cudaEventDisableTiming));
-    CKM(cudaEventCreateWithFlags(&m->ev_state, cudaEventDisableTiming));
+    CKM(cudaEventCreateWithFlags(&m->ev_fork, evflags));
+    CKM(cudaEventCreateWithFlags(&m->ev_join, evflags));
+    CKM(cudaEventCreateWithFlags(&m->ev_fork_obs, evflags));
+    CKM(cudaEventCreateWithFlags(&m->ev_join_obs, evflags));
+    CKM(cudaEventCreateWithFlags(&m->ev_state, evflags));
     CKM(cudaEventCreateWithFlags(&m->ev_staged, cudaEventDisableTiming));
     m->stream = m->own_stream;
 
@@ -773,6 +895,38 @@ int dspmap_create(const dspmap_config *cfg, dspmap **out) {
     CKM(cudaMallocHost(&m->h_xyz, sizeof(float) * V * 3));
     CKM(cudaMallocHost(&m->h_state, sizeof(DevState)));
     CKM(cudaMallocHost(&m->h_count, sizeof(int)));
+    m->est_gpu = !env_off("DSPMAP_EST_GPU");
+    m->norm_poll = !env_off("DSPMAP_NORM_POLL");
+    { const char *e = getenv("DSPMAP_NB_POS"); if (e && e[0] >= '0' && e[0] <= '2') m->nb_pos = e[0] - '0'; }
+    if (m->est_gpu) {
+        int rc2 = DSPMAP_OK;
+        EstPtrs &e = m->est;
+        memset(&e, 0, sizeof(e));
+        const size_t NP = (size_t)MP + 1, NCL = (size_t)MP / EST_MIN_CLUSTER + 2;
+        size_t H = 1024;
+        while (H < 4 * (size_t)MP) H <<= 1;
+        m->est_hash_mask = (unsigned)(H - 1);
+        m->est_hash_bytes = H * (sizeof(u64) + sizeof(int));
+        unsigned char *hash = nullptr;
+#define AE(ptr, count) if (rc2 == DSPMAP_OK) rc2 = dalloc(m, &ptr, (size_t)(count))
+        AE(e.W, NP); AE(e.parent, NP); AE(e.csize, NP); AE(e.label, NP); AE(e.pos, NP); AE(e.grank, NP); AE(e.mrank, NP);
+        AE(e.kidx, NP); AE(e.flag_g, NP); AE(e.flag_r, NP); AE(e.cells, NP); AE(e.cbase, NP); AE(e.ccells, NP); AE(e.bbox, 6 * NP); AE(e.SW, NP); AE(e.cellof, NP); AE(e.cmin, NP); AE(e.ccount, NP); AE(e.rootc, NP); AE(e.cellid, H); AE(hash, m->est_hash_bytes);
+        AE(e.croot, NCL); AE(e.csz, NCL); AE(e.spos, NCL); AE(e.cdyn, NCL); AE(e.coff, NCL); AE(e.dseq, NCL); AE(e.order, NCL);
+        AE(e.a_dyn, NCL); AE(e.a_dsz, NCL); AE(e.a_ssz, NCL); AE(e.p_dyn, NCL); AE(e.p_dsz, NCL); AE(e.p_ssz, NCL); AE(e.cfeat, NCL);
+        AE(e.cnt, EC_COUNT); AE(e.tcid, NP); AE(m->est_d_cvel, NCL);
+#undef AE
+        if (rc2 != DSPMAP_OK) { dspmap_destroy(m); return rc2; }
+        e.hkey = (u64 *)hash;
+        e.hcnt = (int *)(hash + H * sizeof(u64));
+        e.cvel = m->est_d_cvel;
+        e.tagged = d_tagged;
+        CKM(cudaHostAlloc(&m->est_h_hdr, sizeof(int) * EC_COUNT, cudaHostAllocMapped));
+        CKM(cudaHostAlloc(&m->est_h_feat, sizeof(EstFeature) * NCL, cudaHostAllocMapped));
+        CKM(cudaMallocHost(&m->est_h_cvel, sizeof(float) * 4 * NCL));
+        CKM(cudaHostGetDevicePointer((void **)&e.h_hdr, m->est_h_hdr, 0));
+        CKM(cudaHostGetDevicePointer((void **)&e.h_feat, m->est_h_feat, 0));
+        CKM(cudaEventCreateWithFlags(&m->ev_feat, evflags));
+    }
 
     make_planes0(cfg, mc.Nh, mc.Nv, m->planes0);  // boundary-plane normals in the sensor frame (:563-578)
     // neighbour table (:1128-1147; mn:1135-1136)
@@ -894,6 +1048,10 @@ void dspmap_destroy(dspmap *m) {
     if (m->ev_arrived) cudaEventDestroy(m->ev_arrived);
     if (m->ev_nb_early) cudaEventDestroy(m->ev_nb_early);
     if (m->ev_staged_t) cudaEventDestroy(m->ev_staged_t);
+    if (m->est_h_hdr) cudaFreeHost(m->est_h_hdr);
+    if (m->est_h_feat) cudaFreeHost(m->est_h_feat);
+    if (m->est_h_cvel) cudaFreeHost(m->est_h_cvel);
+    if (m->ev_feat) cudaEventDestroy(m->ev_feat);
     delete m;
 }
 
@@ -923,16 +1081,29 @@ static int update_common(dspmap *m, int n, int stride, const float *pts, float p
         m->h_pts[3 * i + 2] = pts[(size_t)i * stride + 2];
     }
     if (n > 0) CK(cudaMemcpyAsync((void *)m->dp.pts, m->h_pts, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, m->stream));
+    m->upd_h2d_bytes = (long long)sizeof(float) * 3 * n;
+    m->upd_d2h_bytes = 0;
     if (m->async_update) CK(cudaEventRecord(m->ev_staged, m->stream));  // behind the staging copy of the cloud
-    const bool on_helper = use_estimator && m->est_thread;
+    const bool on_device = use_estimator && m->est_gpu;
+    const bool on_helper = use_estimator && !on_device && m->est_thread;
+    if (on_device) prepare_estimator(m, &fc, n);
     if (on_helper) {  // the estimation starts now, on the helper thread, while this thread enqueues the frame (host_worker.h)
         m->worker.start();
         dspmap *mm = m;
         m->worker.submit([mm, fc, n] { mm->estimator.estimate(mm->mc, fc, mm->planes0.data(), mm->h_pts, n, mm->cfg.model, mm->tagged_host); });
     }
-    rc = enqueue_frame_a(m, fc, m->dp.pts);
+    rc = enqueue_frame_a(m, fc, m->dp.pts, on_device ? m->dp.tagged : nullptr, on_device);
     if (on_helper) m->worker.wait();  // joined before the newborn step, like the reference's thread (:311)
     if (rc != DSPMAP_OK) return rc;
+    if (on_device) {
+        if (m->async_update) {
+            CK(cudaEventRecord(m->ev_staged_t, m->nb));
+            m->staged_pending = true;
+        }
+        if ((rc = finish_estimator(m, fc)) != DSPMAP_OK) return rc;
+        if ((rc = enqueue_frame_b(m, fc, m->dp.tagged)) != DSPMAP_OK) return rc;
+    } else {
+    if (!use_estimator && (rc = fetch_tagged(m)) != DSPMAP_OK) return rc;  // (frames of the device estimator came before)
     if (use_estimator && !on_helper) {
         // the reference's side thread (dsp_dynamic.h:297, 1377-1544), overlapped with the kernels enqueued above exactly
         // as the reference overlaps it with prediction + update (:297-311)
@@ -950,13 +1121,18 @@ static int update_common(dspmap *m, int n, int stride, const float *pts, float p
         // follow it there do not queue up behind this frame's observation passes
         memcpy(m->h_tagged, m->tagged_host.data(), sizeof(float) * 7 * (size_t)nt);
         CK(cudaMemcpyAsync((void *)m->dp.tagged, m->h_tagged, sizeof(float) * 7 * (size_t)nt, cudaMemcpyHostToDevice, m->nb));
+        m->upd_h2d_bytes += (long long)sizeof(float) * 7 * nt;
     }
     fc.n_tagged = nt;
+    m->est_nt_explicit = nt;  // (a later frame of the device estimator starts from this cloud)
+    m->est_n_real = nt;
+    m->tagged_host_stale = false;
     if (m->async_update) {
         CK(cudaEventRecord(m->ev_staged_t, m->nb));  // behind the staging copy of the newborn input
         m->staged_pending = true;
     }
     if ((rc = enqueue_frame_b(m, fc, m->dp.tagged)) != DSPMAP_OK) return rc;
+    }
     // Asynchronous update: like dspmap_update_device, return with the frame enqueued; readers and dumps are stream-ordered or
     // synchronise themselves, dspmap_counters / dspmap_synchronize pick up the frame's state copy.  A capacity overrun of an
     // earlier frame (latched by frame_prologue from that frame's state copy) is reported here; this frame's own by the next
@@ -1122,7 +1298,7 @@ int dspmap_shard_phase(dspmap *m, int phase, int n, const float *d_pts, float px
     } else if (phase == 4) {  // owners take their new weights; the newborn split reads them (dsp_dynamic.h:829-866)
         dp.tagged = d_tagged;
         LAUNCH(m, FAM_WEIGHT, k_shard_apply_weights, kSMs * 4, B, 0, mc, dp);
-        LAUNCH(m, FAM_NORM, k_norm, 1, 128, 0, mc, fc, dp);
+        LAUNCH(m, FAM_NORM, k_norm, 1, 128, 0, mc, fc, dp, 0);
         if (fc.n_tagged > 0 && fc.nb_num > 0) {
             LAUNCH(m, FAM_NEWBORN, k_shard_zero, kSMs, B, 0, mc, fc, dp, 2);
             LAUNCH(m, FAM_NEWBORN, k_nb_point0, grid_for(fc.n_tagged, B), B, 0, mc, fc, dp);
@@ -1326,6 +1502,28 @@ int dspmap_wait_occupancy(dspmap *m, int ticket, const float **xyz, int *n_out, 
     return DSPMAP_OK;
 }
 long long dspmap_last_reader_bytes(dspmap *m) { return m ? m->last_d2h_bytes : 0; }
+int dspmap_timeline(dspmap *m, float *out8) {
+    if (!m || !out8 || !m->timeline) return DSPMAP_E_BAD_ARG;
+    CK(cudaSetDevice(m->cfg.device));
+    CK(cudaDeviceSynchronize());
+    cudaEvent_t evs[7] = {m->ev_feat, m->ev_arrived, m->ev_join_obs, m->ev_nb_early, m->ev_fork, m->ev_join, m->ev_state};
+    for (int k = 0; k < 7; ++k) {
+        out8[k] = -1.f;
+        if (evs[k] && cudaEventElapsedTime(&out8[k], m->ev_fork_obs, evs[k]) != cudaSuccess) { out8[k] = -1.f; cudaGetLastError(); }
+    }
+    out8[7] = 0.f;
+    return DSPMAP_OK;
+}
+int dspmap_estimator_stats(dspmap *m, int32_t *out8) {
+    if (!m || !out8) return DSPMAP_E_BAD_ARG;
+    for (int c = 0; c < 7; ++c) out8[c] = m->est_h_hdr ? m->est_h_hdr[c] : 0;
+    out8[7] = m->est_h_hdr ? m->est_h_hdr[EC_NTAGGED] : 0;
+    return m->est_gpu ? 1 : 0;
+}
+void dspmap_last_update_bytes(dspmap *m, long long *h2d, long long *d2h) {
+    if (h2d) *h2d = m ? m->upd_h2d_bytes : 0;
+    if (d2h) *d2h = m ? m->upd_d2h_bytes : 0;
+}
 int dspmap_pin_host_buffer(dspmap *m, void *ptr, size_t bytes) {
     if (!m) return DSPMAP_E_BAD_ARG;
     if (m->pinned_user) {
@@ -1352,6 +1550,8 @@ int dspmap_clear_prediction(dspmap *m) {
 }
 int dspmap_get_tagged_cloud(dspmap *m, float *out, int cap) {
     if (!m) return DSPMAP_E_BAD_ARG;
+    int rc = fetch_tagged(m);
+    if (rc != DSPMAP_OK) return rc;
     int n = (int)(m->tagged_host.size() / 7);
     if (out) memcpy(out, m->tagged_host.data(), sizeof(float) * 7 * (size_t)std::min(n, cap));
     return n;

@@ -1000,6 +1000,11 @@ __global__ void __launch_bounds__(1024) k_pair_prep(MapConst mc, DevPtrs dp) {
         const int c0 = dp.chunk_off[i], c1 = c0 + dp.chunks[i];
         for (int c = c0; c < c1; ++c) dp.chunk_pyr[c] = i;
     }
+    // the newborn normaliser (k_norm) runs BESIDE the C_z pass and takes each 1 / C_z as soon as it is there: "not there yet" is 0
+    if (!mc.sharded) {
+        const int n = dp.obs_capoff[mc.P];
+        for (int t = threadIdx.x; t < n; t += blockDim.x) dp.INV[t] = 0.f;
+    }
 }
 // position of pyramid a inside pyramid b's neighbour list (the relation is symmetric)
 __device__ __forceinline__ int nb_index_of(const MapConst &mc, const DevPtrs &dp, int b, int a) {
@@ -1632,20 +1637,38 @@ __global__ void k_verify_div(float b, float r, unsigned max_bits, int mode, int 
 
 
 // K6a  newborn normaliser (dsp_dynamic.h:799-805): sum of 1/C_z over (pyramid, bin) order, one fp32 chain.
-__global__ void k_norm(MapConst mc, FrameConst fc, DevPtrs dp) {
+// poll: the kernel was launched beside the C_z pass (k_pair_prep zeroed INV): a value of 0 has not been written yet (1 / C_z is
+// never 0), so every load waits for its value; the serial chain of thread 0 then ends a few microseconds behind the C_z pass
+// instead of starting there (beside the weight pass it ran three times slower than alone and ended 30 - 80 us after it).
+// (The wait is bounded, about 1 ms per value: if the C_z pass never runs beside this kernel — a profiler that serialises
+// kernels, DSPMAP_NORM_POLL=0 is for that — the frame ends with capacity code 64 instead of a hung device.)
+__device__ __forceinline__ float norm_take(const float *p, int poll, int *overflow) {
+    if (!poll) return *p;
+    float v = 0.f;
+    for (int it = 0; it < 5000; ++it) {
+        v = *(const volatile float *)p;
+        if (v != 0.f) return v;
+#ifdef __CUDA_ARCH__
+        __nanosleep(200);
+#endif
+    }
+    atomicOr(overflow, 64);
+    return v;
+}
+__global__ void k_norm(MapConst mc, FrameConst fc, DevPtrs dp, int poll) {
     pdl_enter();
     __shared__ __align__(16) float buf[2][1024];
     const int n = dp.obs_capoff[mc.P];
     float acc = 0.f;
     int nchunk = (n + 1023) / 1024;
     if (nchunk > 0)
-        for (int t = threadIdx.x; t < 1024; t += blockDim.x) buf[0][t] = t < n ? dp.INV[t] : 0.f;
+        for (int t = threadIdx.x; t < 1024; t += blockDim.x) buf[0][t] = t < n ? norm_take(dp.INV + t, poll, &dp.st->overflow) : 0.f;
     __syncthreads();
     for (int c = 0; c < nchunk; ++c) {
         int nb = (c + 1) & 1, b0 = (c + 1) * 1024;
         if (threadIdx.x >= 32) {  // warps 1.. prefetch the next chunk while warp 0 adds the current one
             if (c + 1 < nchunk)
-                for (int t = threadIdx.x - 32; t < 1024; t += blockDim.x - 32) buf[nb][t] = b0 + t < n ? dp.INV[b0 + t] : 0.f;
+                for (int t = threadIdx.x - 32; t < 1024; t += blockDim.x - 32) buf[nb][t] = b0 + t < n ? norm_take(dp.INV + b0 + t, poll, &dp.st->overflow) : 0.f;
         } else if (threadIdx.x == 0) {
             int cnt = min(1024, n - c * 1024);
             const float4 *s4 = reinterpret_cast<const float4 *>(buf[c & 1]);
@@ -1676,7 +1699,7 @@ __global__ void k_nb_point0(MapConst mc, FrameConst fc, DevPtrs dp) {
         float cx = pt[0] - fc.cur[0], cy = pt[1] - fc.cur[1], cz = pt[2] - fc.cur[2];
         int pv = dsp_voxel_index(mc, cx, cy, cz);
         dp.NPC[m] = make_float4(cx, cy, cz, __int_as_float(pv));
-        dp.ninmap[m] = (mc.model == 1) ? 1 : (pv >= 0);
+        dp.ninmap[m] = (mc.model == 1) ? !(fc.tagged_padded && !(pt[0] < 1e29f)) : (pv >= 0);
         dp.nimask[m] = 0ull;
     }
 }
@@ -1864,9 +1887,11 @@ __global__ void __launch_bounds__(256) k_nb_place(MapConst mc, FrameConst fc, De
         const int nfree = mask_free(mc, msk);
         if (nfree == 0) continue;
         const int b = dp.cbase[d], c = dp.ccnt[d], key = dp.cseg[pos];
-        int rank = 0;
-#pragma unroll 4
-        for (int j = 0; j < c; ++j) rank += dp.cseg[b + j] < key;
+        int rank = 0;  // (a candidate whose rank reaches the number of free slots is not born: no need to finish the count)
+        for (int j0 = 0; j0 < c && rank < nfree; j0 += 8) {
+            const int j1 = min(c, j0 + 8);
+            for (int j = j0; j < j1; ++j) rank += dp.cseg[b + j] < key;
+        }
         if (rank >= nfree) continue;
         const int slot = mask_nth_free(mc, msk, rank);
         const int a = d * mc.S + slot;

@@ -40,6 +40,7 @@ struct FrameConst {
     float sigma_r;  // RN(1/sigma), used only when fast_sigma (exhaustively verified, see k_verify_div)
     int fast_sigma;
     int vz_mode;  // some particle may still carry vz != 0 (constructor-seeded): ordered prediction noise is active
+    int tagged_padded;  // the tagged cloud ends in padding entries (x >= 1e29) that are not points (dspmap_estimator.cuh)
 };
 
 // Device-resident counters and scalars of one frame (one instance in global memory).
@@ -64,3 +65,6 @@ struct DevState {
     float w_new;     // newborn particle weight    (dsp_dynamic.h:805)
     long long p_cur, v_cur, u_cur;  // noise-table cursors and uniform-stream counter (dsp_dynamic.h:483-484)
 };
+
+// One dynamic cluster of the device-side velocity estimation front end (dspmap_estimator.cuh), as handed to the host.
+struct EstFeature { float cx, cy, cz; int size; int sorted_pos; };

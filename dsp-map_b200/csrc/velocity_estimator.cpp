@@ -486,6 +486,59 @@ int rotate_split(const float *pts, int n, const float *q, const float *qi, const
 }
 }  // namespace
 
+// Hungarian matching of this frame's dynamic clusters to the previous frame's and the velocities that follow (:1449-1499)
+void VelocityEstimator::match(std::vector<ClusterFeature> &cur, float dt) {
+    const float distance_gate = 1.5f, maximum_velocity = 5.f;  // :1449-1451
+    const int point_num_gate = 100;
+    if (!last.empty() && !cur.empty() && dt > 0.00001 && dt < 10.0) {  // :1454-1455
+        const int R = (int)cur.size(), C = (int)last.size();
+        std::vector<float> cost((size_t)R * C), gate((size_t)R * C);
+        for (int r = 0; r < R; ++r)
+            for (int c = 0; c < C; ++c) {
+                float dx = cur[r].cx - last[c].cx, dy = cur[r].cy - last[c].cy, dz = cur[r].cz - last[c].cz;
+                float d = sqrtf(dx * dx + dy * dy + dz * dz);
+                if (std::abs(cur[r].point_num - last[c].point_num) > point_num_gate || d >= distance_gate) {
+                    gate[(size_t)r * C + c] = 0.f;
+                    cost[(size_t)r * C + c] = distance_gate * 5000.f;
+                } else {
+                    gate[(size_t)r * C + c] = 1.f;
+                    cost[(size_t)r * C + c] = d / distance_gate * 1000.f;
+                }
+            }
+        std::vector<int> assign;
+        hungarian(cost, R, C, assign);
+        for (int r = 0; r < R; ++r) {  // :1477-1499
+            int c = assign[r];
+            if (c < 0 || !(gate[(size_t)r * C + c] > 0.01f)) continue;
+            ClusterFeature &f = cur[r];
+            f.vx = (f.cx - last[c].cx) / dt;
+            f.vy = (f.cy - last[c].cy) / dt;
+            f.vz = (f.cz - last[c].cz) / dt;
+            f.v = sqrtf(f.vx * f.vx + f.vy * f.vy + f.vz * f.vz);
+            f.intensity = last[c].intensity;
+            if (f.v > maximum_velocity) { f.v = 0.f; f.vx = f.vy = f.vz = 0.f; }
+        }
+    }
+}
+
+// Second half of a frame whose front end ran on the device (dspmap_estimator.cuh): feat = the dynamic clusters in output
+// order, n_clusters = all clusters of admissible size (each drew a colour, :1422).  cvel: 4 floats per dynamic cluster.
+void VelocityEstimator::finish_device(const EstFeature *feat, int n_dynamic, int n_clusters, float dt, float *cvel) {
+    std::vector<ClusterFeature> cur((size_t)n_dynamic);
+    for (int r = 0; r < n_dynamic; ++r) {
+        ClusterFeature &f = cur[r];
+        f.cx = feat[r].cx; f.cy = feat[r].cy; f.cz = feat[r].cz;
+        f.point_num = feat[r].size;
+        f.intensity = dsp_uniform(seed, draws + (u64)feat[r].sorted_pos, 0.1f, 1.f);
+    }
+    draws += (u64)n_clusters;
+    if (n_dynamic > 0) match(cur, dt);
+    for (int r = 0; r < n_dynamic; ++r) {
+        cvel[4 * r] = cur[r].vx; cvel[4 * r + 1] = cur[r].vy; cvel[4 * r + 2] = cur[r].vz; cvel[4 * r + 3] = cur[r].intensity;
+    }
+    last = cur;
+}
+
 void VelocityEstimator::estimate(const MapConst &mc, const FrameConst &fc, const float *planes0, const float *pts, int n,
                                  int model, std::vector<float> &out) {
     // rotated outer boundary planes and the in-view rotated cloud, same arithmetic as the device (dsp_dynamic.h:226-257)
@@ -543,37 +596,7 @@ void VelocityEstimator::estimate(const MapConst &mc, const FrameConst &fc, const
                 dynamic_flag.push_back(1);
             }
         }
-        const float distance_gate = 1.5f, maximum_velocity = 5.f;  // :1449-1451
-        const int point_num_gate = 100;
-        if (!last.empty() && !cur.empty() && fc.dt > 0.00001 && fc.dt < 10.0) {  // :1454-1455
-            const int R = (int)cur.size(), C = (int)last.size();
-            std::vector<float> cost((size_t)R * C), gate((size_t)R * C);
-            for (int r = 0; r < R; ++r)
-                for (int c = 0; c < C; ++c) {
-                    float dx = cur[r].cx - last[c].cx, dy = cur[r].cy - last[c].cy, dz = cur[r].cz - last[c].cz;
-                    float d = sqrtf(dx * dx + dy * dy + dz * dz);
-                    if (std::abs(cur[r].point_num - last[c].point_num) > point_num_gate || d >= distance_gate) {
-                        gate[(size_t)r * C + c] = 0.f;
-                        cost[(size_t)r * C + c] = distance_gate * 5000.f;
-                    } else {
-                        gate[(size_t)r * C + c] = 1.f;
-                        cost[(size_t)r * C + c] = d / distance_gate * 1000.f;
-                    }
-                }
-            std::vector<int> assign;
-            hungarian(cost, R, C, assign);
-            for (int r = 0; r < R; ++r) {  // :1477-1499
-                int c = assign[r];
-                if (c < 0 || !(gate[(size_t)r * C + c] > 0.01f)) continue;
-                ClusterFeature &f = cur[r];
-                f.vx = (f.cx - last[c].cx) / fc.dt;
-                f.vy = (f.cy - last[c].cy) / fc.dt;
-                f.vz = (f.cz - last[c].cz) / fc.dt;
-                f.v = sqrtf(f.vx * f.vx + f.vy * f.vy + f.vz * f.vz);
-                f.intensity = last[c].intensity;
-                if (f.v > maximum_velocity) { f.v = 0.f; f.vx = f.vy = f.vz = 0.f; }
-            }
-        }
+        match(cur, fc.dt);
         int seq = 0, dseq = 0;  // :1503-1524
         for (const auto &cl : clusters) {
             if (dynamic_flag[seq]) {

@@ -26,6 +26,8 @@ struct VelocityEstimator {
     void reset(u64 s) { seed = s ^ 0xA5A5A5A5DEADBEEFull; draws = 0; last.clear(); }
     float uniform(float lo, float hi);
     // pts: n x 3 points in the sensor frame. tagged_out is left untouched when no point is in view (:1379).
+    void match(std::vector<ClusterFeature> &cur, float dt);
+    void finish_device(const EstFeature *feat, int n_dynamic, int n_clusters, float dt, float *cvel);
     void estimate(const MapConst &mc, const FrameConst &fc, const float *planes0, const float *pts, int n, int model,
                   std::vector<float> &tagged_out);
 };

@@ -73,6 +73,9 @@ def load_library():
         "dspmap_wait_occupancy": (i, [vp, i, C.POINTER(fp), ip, C.POINTER(fp)]),
         "dspmap_clear_prediction": (i, [vp]),
         "dspmap_last_reader_bytes": (C.c_longlong, [vp]),
+        "dspmap_last_update_bytes": (None, [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
+        "dspmap_estimator_stats": (i, [vp, ip]),
+        "dspmap_timeline": (i, [vp, fp]),
         "dspmap_pin_host_buffer": (i, [vp, vp, C.c_size_t]),
         "dspmap_get_tagged_cloud": (i, [vp, fp, i]),
         "dspmap_voxel_center": (None, [vp, i, fp]),
@@ -134,7 +137,7 @@ EXPORTED_SYMBOLS = [
     "dspmap_set_newborn_weight", "dspmap_set_newborn_number", "dspmap_set_particle_record_flag",
     "dspmap_set_voxel_filter_resolution", "dspmap_get_occupancy", "dspmap_get_occupancy_device",
     "dspmap_get_occupancy_async", "dspmap_wait_occupancy",
-    "dspmap_clear_prediction", "dspmap_last_reader_bytes", "dspmap_pin_host_buffer", "dspmap_get_tagged_cloud", "dspmap_voxel_center", "dspmap_voxel_index", "dspmap_uniform",
+    "dspmap_clear_prediction", "dspmap_last_reader_bytes", "dspmap_last_update_bytes", "dspmap_estimator_stats", "dspmap_timeline", "dspmap_pin_host_buffer", "dspmap_get_tagged_cloud", "dspmap_voxel_center", "dspmap_voxel_index", "dspmap_uniform",
     "dspmap_dims", "dspmap_dump_particles", "dspmap_load_particles", "dspmap_dump_voxel_objects",
     "dspmap_dump_observations", "dspmap_dump_pyramid_lists", "dspmap_dump_plane_normals", "dspmap_cursors", "dspmap_set_cursors", "dspmap_counters",
     "dspmap_set_stage_limit", "dspmap_set_last_pose", "dspmap_set_stream", "dspmap_synchronize", "dspmap_profile_enable", "dspmap_profile_read", "dspmap_profile_read_kernels",
@@ -354,6 +357,27 @@ class DSPMap:
     def last_future_bytes(self):
         """Device-to-host bytes of the last blocking reader call (dspmap_last_reader_bytes)."""
         return int(self.lib.dspmap_last_reader_bytes(self.h))
+
+    def last_update_bytes(self):
+        """(host-to-device, device-to-host) bytes of the last update() call (dspmap_last_update_bytes)."""
+        a, b = C.c_longlong(0), C.c_longlong(0)
+        self.lib.dspmap_last_update_bytes(self.h, C.byref(a), C.byref(b))
+        return int(a.value), int(b.value)
+
+    def estimator_stats(self):
+        """(on_device, dict of the device front end's counters for the last frame) — dspmap_estimator_stats."""
+        d = np.zeros(8, np.int32)
+        on = int(self.lib.dspmap_estimator_stats(self.h, _ip(d)))
+        names = ("in_view", "clusters", "ground_points", "dynamic_clusters", "dynamic_points", "static_cluster_points", "cells", "tagged")
+        return on, {k: int(v) for k, v in zip(names, d)}
+
+    def timeline(self):
+        """ms from the start of the last frame to its milestones (dspmap_timeline; maps created with DSPMAP_TIMELINE=1)."""
+        d = np.zeros(8, np.float32)
+        if self.lib.dspmap_timeline(self.h, _fp(d)) != 1:
+            return None
+        names = ("features_on_host", "arrived", "obs_binned", "newborn_placed", "weights_start", "norm_done", "frame_end")
+        return {k: round(float(v), 4) for k, v in zip(names, d)}
 
     def fast_paths(self):
         """(fast_res, fast_sigma): whether the exhaustively verified exact fast divisions are enabled (sigma: after the next update)."""

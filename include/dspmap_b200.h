@@ -134,6 +134,18 @@ int dspmap_pin_host_buffer(dspmap *m, void *ptr, size_t bytes);
 /* Bytes the last dspmap_get_occupancy call moved from the device to the host (count, occupied list incl. its speculative
  * prefix, and the future grid: dense, or only its non-zero rows when the caller's array is registered). */
 long long dspmap_last_reader_bytes(dspmap *m);
+/* Bytes the last dspmap_update / dspmap_update_tagged call moved over PCIe: the cloud plus either the velocity-tagged newborn
+ * input (host estimator, explicit input) or the matched clusters' velocities (device estimator); the cluster features the
+ * device hands to the host matching. */
+void dspmap_last_update_bytes(dspmap *m, long long *h2d, long long *d2h);
+/* Counters of the last frame's velocity-estimation front end when it ran on the device (dspmap_estimator.cuh): points in view,
+ * clusters of admissible size, ground points, dynamic clusters, their points, points of static clusters, occupied grid cells,
+ * size of the tagged cloud.  Returns 1 if the map estimates on the device (default), 0 if on the host (DSPMAP_EST_GPU=0). */
+int dspmap_estimator_stats(dspmap *m, int32_t *out8);
+/* Diagnosis (maps created with DSPMAP_TIMELINE=1): milliseconds from the start of the last frame (behind k_frame_setup) to
+ * the cluster features reaching the host, the arrival pass, the end of the observation binning, the early newborn placement,
+ * the start of the weight pass, the newborn normaliser and the end of the frame; -1 for events the frame did not record. */
+int dspmap_timeline(dspmap *m, float *out8);
 int dspmap_clear_prediction(dspmap *m);
 /* getKMClusterResult (:441-445): copies the last newborn input; returns the number of points. */
 int dspmap_get_tagged_cloud(dspmap *m, float *out, int cap);

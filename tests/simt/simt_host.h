@@ -3,7 +3,7 @@
 // against another kernel on the same inputs without a GPU.  Supported: threadIdx / blockIdx / blockDim / gridDim,
 // __shared__ (static + one dynamic buffer; one block at a time), __syncthreads, one named barrier, the warp collectives
 // the kernels use (__ballot_sync, __shfl*_sync, __syncwarp, __reduce_min_sync; full masks, convergent call sites), integer
-// / float atomics, bit intrinsics, cp.async pipelines (copies complete at once), and the mbarrier / cp.async.bulk subset
+// / float atomics (add, or, and, compare-and-swap, exchange), bit intrinsics, cp.async pipelines (copies complete at once), and the mbarrier / cp.async.bulk subset
 // of cuda::ptx (copies complete at once and are checked for the 16-byte rules of the hardware).
 // Not modelled: memory ordering weaker than sequential consistency, divergent collectives, several blocks at once.
 #pragma once
@@ -120,6 +120,7 @@ inline unsigned __reduce_min_sync(unsigned, unsigned v) {
     simt::sync();
     return r;
 }
+inline bool __any_sync(unsigned m, bool p) { return __ballot_sync(m, p) != 0u; }
 inline unsigned __activemask() { return 0xffffffffu; }
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
 inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
@@ -146,6 +147,15 @@ inline float atomicAdd(float *p, float v) {
 inline unsigned long long atomicOr(unsigned long long *p, unsigned long long v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
 inline unsigned long long atomicAnd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_and(p, v, __ATOMIC_SEQ_CST); }
 inline int atomicOr(int *p, int v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+inline int atomicCAS(int *p, int cmp, int v) { __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST); return cmp; }
+inline unsigned long long atomicCAS(unsigned long long *p, unsigned long long cmp, unsigned long long v) {
+    __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
+    return cmp;
+}
+inline int atomicMin(int *p, int v) { int o = __atomic_load_n(p, __ATOMIC_SEQ_CST); while (v < o && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {} return o; }
+inline int atomicMax(int *p, int v) { int o = __atomic_load_n(p, __ATOMIC_SEQ_CST); while (v > o && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {} return o; }
+inline int atomicExch(int *p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
+inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 using std::max;
 using std::min;
 

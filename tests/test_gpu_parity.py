@@ -286,9 +286,10 @@ def test_full_size_properties(name, frames):
     g.close()
 
 
-@pytest.mark.parametrize("switch", ["DSPMAP_PDL", "DSPMAP_EST_THREAD", "DSPMAP_ASYNC_UPDATE"])
+@pytest.mark.parametrize("switch", ["DSPMAP_PDL", "DSPMAP_EST_THREAD", "DSPMAP_ASYNC_UPDATE", "DSPMAP_EST_GPU"])
 def test_library_defaults_that_can_be_switched_off_do_not_change_a_bit(switch, monkeypatch):
-    """Programmatic dependent launch, the helper-thread velocity estimation and the asynchronous update are library defaults
+    """Programmatic dependent launch, the helper-thread velocity estimation (of a map whose estimation front end is not on the
+    device), the asynchronous update and the device-side estimation front end are library defaults
     (adopted from the A/B of profiles/r02_ab_switches.jsonl); NAME=0, read by dspmap_create, turns one off.  A map created
     without one must stay bit-identical to a default map on the bench workload, through the explicit-newborn-input path and
     through the library's own estimator."""
@@ -315,3 +316,38 @@ def test_library_defaults_that_can_be_switched_off_do_not_change_a_bit(switch, m
     a.close()
     b.close()
     assert not bad, "\n".join(bad)
+
+
+@pytest.mark.parametrize("name,frames,seed", [("tiny_dyn", 10, 4), ("tiny_static", 6, 2), ("cfg2", 12, 1), ("cfg3", 4, 3)])
+def test_device_velocity_estimation_equals_host_estimation(name, frames, seed, monkeypatch):
+    """update() with the estimation front end on the device (dspmap_estimator.cuh: FOV filter, ground split, hash-grid
+    union-find clustering, centroids, layout of the tagged cloud; Hungarian matching on the host) against the same map with
+    the host implementation (DSPMAP_EST_GPU=0), which test_host.py pins against the reference's own side thread: the tagged
+    cloud (positions, velocities, colours, order) and the map state must be bit-identical after every frame — including a
+    frame with nothing in view (the previous cloud is kept) and an empty cloud."""
+    cfg = dm.CONFIGS[name]
+    st = make_stream(cfg, seed=seed, frames=frames)
+    monkeypatch.delenv("DSPMAP_EST_GPU", raising=False)
+    a = gpu_map(name, seed=7, max_points=cfg["points"])
+    monkeypatch.setenv("DSPMAP_EST_GPU", "0")
+    b = gpu_map(name, seed=7, max_points=cfg["points"])
+    monkeypatch.delenv("DSPMAP_EST_GPU", raising=False)
+    bad, moving = [], 0
+    for f in range(frames):
+        pts, pos, t, q = st["points"][f].copy(), st["pos"][f], st["t"][f], st["quat"][f]
+        if f == frames // 2:      # everything behind the sensor: nothing in view
+            pts[:, 0] = -np.abs(pts[:, 0]) - 1.0
+            pts[:, 1:] = 0.0
+        if f == frames // 2 + 1:  # an empty cloud
+            pts = pts[:0]
+        assert gpu_update(a, pts, pos, t, q) == gpu_update(b, pts, pos, t, q) == 1
+        ta, tb = a.getKMClusterResult(), b.getKMClusterResult()
+        if not same(ta, tb):
+            bad.append("%s frame %d: tagged clouds differ (%s vs %s)" % (name, f, ta.shape, tb.shape))
+        moving += int(((tb[:, 6] > 0.01) & (tb[:, 3] > -100)).sum()) if len(tb) else 0
+        bad += compare_state(b, a, label="%s frame %d:" % (name, f))
+    a.close()
+    b.close()
+    assert not bad, "\n".join(bad)
+    if name == "cfg2":
+        assert moving > 0  # the streams contain moving boxes: some points carried an estimated velocity

@@ -14,7 +14,7 @@ CUH = os.path.join(ROOT, "dsp-map_b200", "csrc", "dspmap_frame.cuh")
 LEGACY = os.path.join(SIMT, "legacy_frame_r01.cuh")
 
 
-def build_and_run(check, inc, kernels, legacy=(), timeout=600, defines=(), tag=""):
+def build_and_run(check, inc, kernels, legacy=(), timeout=600, defines=(), tag="", sources=(), flags=()):
     os.makedirs(BUILD, exist_ok=True)
     subprocess.check_call([sys.executable, os.path.join(SIMT, "extract.py"), CUH, os.path.join(BUILD, inc)] + list(kernels))
     if legacy:
@@ -23,7 +23,7 @@ def build_and_run(check, inc, kernels, legacy=(), timeout=600, defines=(), tag="
     exe = os.path.join(BUILD, check + tag)
     subprocess.check_call(["g++", "-std=c++20", "-O1", "-I/usr/local/cuda/include", "-I" + SIMT, "-I" + BUILD,
                            "-I" + os.path.join(ROOT, "dsp-map_b200", "csrc")] + ["-D" + d for d in defines] +
-                          [os.path.join(SIMT, check + ".cpp"), "-o", exe, "-lpthread"])
+                          list(flags) + [os.path.join(SIMT, check + ".cpp")] + list(sources) + ["-o", exe, "-lpthread"])
     r = subprocess.run([exe], capture_output=True, text=True, timeout=timeout)
     assert r.returncode == 0, r.stdout + r.stderr
     return r.stdout
@@ -43,3 +43,13 @@ def test_newborn_placement_kernel_equals_the_round1_kernel():
     count, on random voxels (full, nearly full, 1 .. 330 candidates per voxel)."""
     out = build_and_run("check_nb_place", "nb_place.inc", ["k_nb_place"], legacy=["k_nb_place"])
     assert out.count("identical") == 4 and "DIFFERENT" not in out
+
+
+def test_device_estimation_front_end_equals_the_host_estimator():
+    """dspmap_estimator.cuh (FOV filter, ground split, hash-grid union-find clustering, PCL's cluster order, centroids, layout
+    of the tagged cloud) + the host matching, against VelocityEstimator::estimate on the same random scenes (blobs of 1..600
+    points, some above 1.5 m, a wall, ground points around the threshold, points behind the sensor, a frame with nothing in
+    view), dynamic and static model: the tagged clouds — positions, velocities, colours, order — bit for bit, 14 frames."""
+    out = build_and_run("check_estimator", "est_scan.inc", ["block_exclusive_scan"], flags=("-ffp-contract=off",),
+                        sources=(os.path.join(ROOT, "dsp-map_b200", "csrc", "velocity_estimator.cpp"),))
+    assert out.count("identical") == 14 and "DIFFERENT" not in out
