@@ -389,7 +389,7 @@ def main_single(args, cfg_name, dm, make_stream):
         "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": workload_config(cfg_name, cfg),
         "run": {"where": "hbm-resident", "parallelism": "single", "l2_flush_between_steps": flush is not None, "preroll_frames": PREROLL,
-                "library_defaults": "PDL, velocity-estimation front end on the device, asynchronous update, sparse future copy-out"},
+                "library_defaults": "PDL, helper-thread velocity estimation, asynchronous update, sparse future copy-out"},
         "e2e": {"value": len(e2e_t) / float(np.sum(e2e_t)), "unit": "updates/s", "h2d_bytes_per_step": r["h2d"] // max(len(e2e_t), 1),
                 "d2h_bytes_per_step": r["d2h"] // max(len(e2e_t), 1), "ms_per_step": 1e3 * float(np.mean(e2e_t)),
                 "update_ms": 1e3 * float(np.mean(e2e_upd)), "reader_ms": 1e3 * float(np.mean(e2e_t) - np.mean(e2e_upd))},

@@ -135,8 +135,8 @@ struct dspmap {
     int shard_cap_g = 0;
     long long host_u_cur = 0;  // uniform draws consumed on the host while seeding
     VelocityEstimator estimator;
-    // front half of the velocity estimation on the device (dspmap_estimator.cuh; DSPMAP_EST_GPU=0: host implementation)
-    bool est_gpu = true;
+    // front half of the velocity estimation on the device (dspmap_estimator.cuh; DSPMAP_EST_GPU=1, default: host implementation)
+    bool est_gpu = false;
     EstPtrs est;
     EstConst est_ec;              // this frame's constants (prepare_estimator)
     bool est_cluster = false;
@@ -867,7 +867,7 @@ int dspmap_create(const dspmap_config *cfg, dspmap **out) {
     A(dp.obs_capoff, P + 1); A(dp.OSEG, MP); A(dp.OBSP, P * mc.OBS); A(dp.CZ, P * mc.OBS); A(dp.INV, MP + P * 0 + 1024);
     A(dp.MBA, CL); A(dp.MBB, CL); A(dp.MBkey, CL); A(dp.MBdst, CL); A(dp.MBq, CL);
     A(dp.mcnt, V); A(dp.mfill, V); A(dp.mbase, V); A(dp.mowner, V); A(dp.mseg, CL);
-    A(dp.Fkey, CL); A(dp.Faddr, CL); A(dp.Fq, CL); A(dp.FP, CL); A(dp.PSpay, CL); A(dp.pcount, P); A(dp.pfill, P); A(dp.pub, P); A(dp.poff, P + 1); A(dp.plen, P);
+    A(dp.Fkey, CL); A(dp.Faddr, CL); A(dp.Fq, CL); A(dp.FP, CL); A(dp.PSpay, CL); A(dp.pcount, P); A(dp.pfill, P); A(dp.pub, P); A(dp.rkey, CL); A(dp.poff, P + 1); A(dp.plen, P);
     A(dp.PSkey, CL); A(dp.PSaddr, CL); A(dp.LA, CL); A(dp.LP, CL); A(dp.PW, CL);
     mc.cap_pairs = 512ll << 20;  // 2 GB of fp32 pair terms (of 180 GB); larger frames fall back to the recompute kernels
     A(dp.G, (size_t)mc.cap_pairs + 64); A(dp.cum, P * mc.NBW); A(dp.totlen, P); A(dp.pairs, P + 1); A(dp.rowbase, P + 1);
@@ -895,7 +895,11 @@ int dspmap_create(const dspmap_config *cfg, dspmap **out) {
     CKM(cudaMallocHost(&m->h_xyz, sizeof(float) * V * 3));
     CKM(cudaMallocHost(&m->h_state, sizeof(DevState)));
     CKM(cudaMallocHost(&m->h_count, sizeof(int)));
-    m->est_gpu = !env_off("DSPMAP_EST_GPU");
+    {   // measured on B200 (profiles/r02_variants.jsonl): end to end the two are level at cfg2 (host 0.565 ms, device 0.565 - 0.58), the
+        // host estimator is ahead with the pipelined reader and at cfg3 (the device is left to the frame) — so it is the default
+        const char *e = getenv("DSPMAP_EST_GPU");
+        m->est_gpu = e && strcmp(e, "1") == 0;
+    }
     m->norm_poll = !env_off("DSPMAP_NORM_POLL");
     { const char *e = getenv("DSPMAP_NB_POS"); if (e && e[0] >= '0' && e[0] <= '2') m->nb_pos = e[0] - '0'; }
     if (m->est_gpu) {

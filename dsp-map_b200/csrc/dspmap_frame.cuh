@@ -34,6 +34,7 @@ __global__ void k_frame_setup(MapConst mc, FrameConst fc, DevPtrs dp) {
         s->n_vz = s->n_skipped = 0;
         s->n_occ_voxels = 0;
         s->ticket = 0;
+        s->n_rel = 0;
         s->n_mov_fov = 0;
         s->work_eval = s->work_eval2 = s->work_w2 = 0;
         s->total_pairs = 0ull;
@@ -497,20 +498,35 @@ __device__ __forceinline__ void replay_clear(const DevPtrs &dp, int v, int s) {
     if (s < 64) w.x &= ~(1ull << s); else w.y &= ~(1ull << (s - 64));
     dp.MS[v] = w;
 }
+__device__ __forceinline__ void replay_touch(const void *p) {  // bring the line into this SM's L1 (the walk below is one thread: latency is everything)
+#ifdef __CUDA_ARCH__
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#endif
+}
 __device__ void arrive_replay(const MapConst &mc, const DevPtrs &dp) {
     __shared__ bool s_last;
+    __shared__ __align__(16) int s_keys[1024];
+    __shared__ volatile int s_pos;
     DevState *st = dp.st;
     const int n_stay = st->n_fov, n_mov = st->n_mov, n_ev = n_stay + n_mov;  // (nobody changes them before phase B)
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-    int *ev = dp.PSkey;  // free until k_pyr_scatter
-    // phase A
+    int *ev = dp.PSkey, *evl = dp.PSaddr, *evk = dp.rkey;  // free until k_pyr_scatter
+    // phase A (whole grid): working masks; the events the walk has to see.  A registered stayer only matters if ITS pyramid can
+    // overflow (k_predict counted it into pcount already, and a list that cannot fill up never turns anyone away): the walk
+    // is as long as the movers plus the stayers of the few pyramids over the bound, not as long as the live list.
     for (int v = tid; v < mc.V; v += nth) { dp.MS[v] = dp.M0[v]; dp.vzcnt[v] = 0; }
     for (int e = tid; e < n_ev; e += nth) {
-        const int key = e < n_stay ? dp.Fkey[e] : dp.MBkey[e - n_stay];
-        int r = 0;
-        for (int j = 0; j < n_stay; ++j) r += dp.Fkey[j] < key;
-        for (int j = 0; j < n_mov; ++j) r += dp.MBkey[j] < key;
-        ev[r] = e;
+        int key;
+        if (e < n_stay) {
+            const int q = dp.Fq[e];
+            if (!(dp.pcount[q] + dp.pub[q] > mc.L)) continue;
+            key = dp.Fkey[e];
+        } else {
+            key = dp.MBkey[e - n_stay];
+        }
+        const int k = atomicAdd(&st->n_rel, 1);
+        evl[k] = e;
+        evk[k] = key;
     }
     __threadfence();
     __syncthreads();
@@ -518,13 +534,59 @@ __device__ void arrive_replay(const MapConst &mc, const DevPtrs &dp) {
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    // phase B
-    for (int q = threadIdx.x; q < mc.P; q += blockDim.x) dp.pcount[q] = 0;
+    // phase B (the block that finishes last): rank the events by sweep key (keys are unique), then walk them
+    const int n_rel = *(volatile int *)&st->n_rel;
+    {
+        const int per = (n_rel + blockDim.x - 1) / blockDim.x;
+        for (int it = 0; it < per; ++it) {
+            const int i = it * blockDim.x + threadIdx.x;
+            const int key = i < n_rel ? __ldcg(evk + i) : 0;
+            int r = 0;
+            for (int j0 = 0; j0 < n_rel; j0 += 1024) {
+                __syncthreads();
+                for (int j = threadIdx.x; j < 1024; j += blockDim.x) s_keys[j] = j0 + j < n_rel ? __ldcg(evk + j0 + j) : INT_MAX;
+                __syncthreads();
+                const int4 *k4 = reinterpret_cast<const int4 *>(s_keys);
+#pragma unroll 4
+                for (int j = 0; j < 256; ++j) {
+                    const int4 k = k4[j];
+                    r += (k.x < key) + (k.y < key) + (k.z < key) + (k.w < key);
+                }
+            }
+            if (i < n_rel) ev[r] = __ldcg(evl + i);
+        }
+    }
+    for (int q = threadIdx.x; q < mc.P; q += blockDim.x)
+        if (dp.pcount[q] + dp.pub[q] > mc.L) dp.pcount[q] = 0;  // recounted by the walk; the other lists keep k_predict's count of their stayers
+    if (threadIdx.x == 0) s_pos = 0;
     __syncthreads();
+    if (threadIdx.x >= 32) {
+        // the other warps run a little ahead of the walk and pull what it is going to read into L1
+        const int ahead = blockDim.x - 32;
+        for (int r = threadIdx.x - 32; r < n_rel; r += ahead) {
+            while (r > s_pos + 2 * ahead) {
+#ifdef __CUDA_ARCH__
+                __nanosleep(100);
+#endif
+            }
+            const int e = ev[r];
+            int v;
+            if (e < n_stay) {
+                replay_touch(dp.Fq + e);
+                v = dp.Fkey[e] >> DSP_KEY_SHIFT;
+            } else {
+                const int i = e - n_stay;
+                replay_touch(dp.MBkey + i); replay_touch(dp.MBq + i); replay_touch(dp.MBA + i); replay_touch(dp.MBB + i);
+                v = dp.MBdst[i];
+            }
+            replay_touch(dp.MS + v); replay_touch(dp.M0 + v); replay_touch(dp.M + v); replay_touch(dp.vzcnt + v);
+        }
+    }
     if (threadIdx.x == 0) {
         int n_fov = n_stay, n_moved = 0, n_vfull = 0, n_pfull = 0;
-        for (int r = 0; r < n_ev; ++r) {
-            const int e = __ldcg(ev + r);
+        for (int r = 0; r < n_rel; ++r) {
+            if ((r & 31) == 0) s_pos = r;
+            const int e = ev[r];
             if (e < n_stay) {  // stayed in its voxel, inside the field of view: joins its pyramid's list unless that is full
                 const int key = dp.Fkey[e], q = dp.Fq[e];
                 if (dp.pcount[q] < mc.L) {
@@ -560,6 +622,7 @@ __device__ void arrive_replay(const MapConst &mc, const DevPtrs &dp) {
                 ++n_fov;
             }
         }
+        s_pos = n_rel;
         st->n_fov = n_fov;
         st->n_moved = n_moved;
         st->n_voxel_full = n_vfull;

@@ -66,6 +66,7 @@ struct DevPtrs {
     float *NW;             // [nranks * cap_g] new weights by global list index, summed over ranks (one writer each)
     int *pcount, *pfill, *poff, *plen;
     int *pub;           // per pyramid: movers heading for it this frame (upper bound for the overflow test of k_arrive)
+    int *rkey;          // replay scratch: sweep keys of the events to walk
     int *PSkey, *PSaddr;
     int *LA;            // per-pyramid sorted list: slot address
     float4 *LP;         // per-pyramid sorted list: px py pz weight (post-prediction)

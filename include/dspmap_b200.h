@@ -140,7 +140,7 @@ long long dspmap_last_reader_bytes(dspmap *m);
 void dspmap_last_update_bytes(dspmap *m, long long *h2d, long long *d2h);
 /* Counters of the last frame's velocity-estimation front end when it ran on the device (dspmap_estimator.cuh): points in view,
  * clusters of admissible size, ground points, dynamic clusters, their points, points of static clusters, occupied grid cells,
- * size of the tagged cloud.  Returns 1 if the map estimates on the device (default), 0 if on the host (DSPMAP_EST_GPU=0). */
+ * size of the tagged cloud.  Returns 1 if the map estimates on the device (DSPMAP_EST_GPU=1), 0 if on the host (default). */
 int dspmap_estimator_stats(dspmap *m, int32_t *out8);
 /* Diagnosis (maps created with DSPMAP_TIMELINE=1): milliseconds from the start of the last frame (behind k_frame_setup) to
  * the cluster features reaching the host, the arrival pass, the end of the observation binning, the early newborn placement,

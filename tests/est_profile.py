@@ -6,6 +6,7 @@ sys.path.insert(0, os.path.join(ROOT, "dsp-map_b200"))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 os.environ.setdefault("DSPMAP_TIMELINE", "1")
+os.environ.setdefault("DSPMAP_EST_GPU", "1")
 import dspmap_b200 as dm
 from common import make_stream, gpu_map
 

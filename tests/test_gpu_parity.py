@@ -286,20 +286,21 @@ def test_full_size_properties(name, frames):
     g.close()
 
 
-@pytest.mark.parametrize("switch", ["DSPMAP_PDL", "DSPMAP_EST_THREAD", "DSPMAP_ASYNC_UPDATE", "DSPMAP_EST_GPU"])
-def test_library_defaults_that_can_be_switched_off_do_not_change_a_bit(switch, monkeypatch):
-    """Programmatic dependent launch, the helper-thread velocity estimation (of a map whose estimation front end is not on the
-    device), the asynchronous update and the device-side estimation front end are library defaults
-    (adopted from the A/B of profiles/r02_ab_switches.jsonl); NAME=0, read by dspmap_create, turns one off.  A map created
-    without one must stay bit-identical to a default map on the bench workload, through the explicit-newborn-input path and
-    through the library's own estimator."""
+@pytest.mark.parametrize("switch,value", [("DSPMAP_PDL", "0"), ("DSPMAP_EST_THREAD", "0"), ("DSPMAP_ASYNC_UPDATE", "0"), ("DSPMAP_EST_GPU", "1"),
+                                          ("DSPMAP_NORM_POLL", "0"), ("DSPMAP_NB_POS", "2")])
+def test_library_switches_do_not_change_a_bit(switch, value, monkeypatch):
+    """The library's run-time switches (read by dspmap_create) select HOW a frame is executed —
+    programmatic dependent launch, helper-thread / calling-thread host estimation, asynchronous update, the estimation front
+    end on the device, the newborn normaliser beside / behind the C_z pass, where the early newborn kernels are enqueued —
+    never what it computes: a map created with one switched must stay bit-identical to a default map on the bench workload,
+    through the explicit-newborn-input path and through the library's own estimator."""
     name, frames = "cfg2", 3
     cfg = dm.CONFIGS[name]
     st = make_stream(cfg, seed=3, frames=frames + 2)
     est = dm.VelocityEstimator(cfg, seed=7, filter_res=0.1)
     monkeypatch.delenv(switch, raising=False)
     a = gpu_map(name, seed=7, max_points=cfg["points"])
-    monkeypatch.setenv(switch, "0")
+    monkeypatch.setenv(switch, value)
     b = gpu_map(name, seed=7, max_points=cfg["points"])
     monkeypatch.delenv(switch, raising=False)
     bad = []
@@ -322,16 +323,16 @@ def test_library_defaults_that_can_be_switched_off_do_not_change_a_bit(switch, m
 def test_device_velocity_estimation_equals_host_estimation(name, frames, seed, monkeypatch):
     """update() with the estimation front end on the device (dspmap_estimator.cuh: FOV filter, ground split, hash-grid
     union-find clustering, centroids, layout of the tagged cloud; Hungarian matching on the host) against the same map with
-    the host implementation (DSPMAP_EST_GPU=0), which test_host.py pins against the reference's own side thread: the tagged
+    the host implementation (the default), which test_host.py pins against the reference's own side thread: the tagged
     cloud (positions, velocities, colours, order) and the map state must be bit-identical after every frame — including a
     frame with nothing in view (the previous cloud is kept) and an empty cloud."""
     cfg = dm.CONFIGS[name]
     st = make_stream(cfg, seed=seed, frames=frames)
-    monkeypatch.delenv("DSPMAP_EST_GPU", raising=False)
+    monkeypatch.setenv("DSPMAP_EST_GPU", "1")
     a = gpu_map(name, seed=7, max_points=cfg["points"])
-    monkeypatch.setenv("DSPMAP_EST_GPU", "0")
-    b = gpu_map(name, seed=7, max_points=cfg["points"])
     monkeypatch.delenv("DSPMAP_EST_GPU", raising=False)
+    b = gpu_map(name, seed=7, max_points=cfg["points"])
+    assert a.estimator_stats()[0] == 1 and b.estimator_stats()[0] == 0
     bad, moving = [], 0
     for f in range(frames):
         pts, pos, t, q = st["points"][f].copy(), st["pos"][f], st["t"][f], st["quat"][f]
