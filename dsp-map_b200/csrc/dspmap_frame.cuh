@@ -1201,6 +1201,8 @@ __device__ __forceinline__ float cz_chain_rows(float acc, const float *t, const 
 // memory (double-buffered cp.async); thread z < np adds its column in list order: one fp32 chain per point.
 // Measured on B200 (cfg2): 256 threads with 2 x 32 KB tiles (3 CTAs / SM) 54 us, 128 threads with 2 x 16 KB tiles
 // (6 CTAs / SM, every pyramid resident at once) 64 us — the longer tiles amortise the per-tile barrier better.
+// A three-stage variant in which the warps without a column multiplied the landed tile by its row weights in place, so that
+// the chain was one load and one add per term, was bit-identical and slower: 81 vs 66 us (profiles/r02_variants.jsonl).
 template <int CZ_THREADS, int CZ_TILE, int CZ_JT>
 __global__ void __launch_bounds__(CZ_THREADS) k_cz_chain(MapConst mc, FrameConst fc, DevPtrs dp) {
     pdl_enter();

@@ -11,6 +11,29 @@
 
 #include "dspmap_hostmath.h"
 
+#ifdef EST_TIMING  // build.py -DEST_TIMING: where a frame's estimation time goes, printed at exit (diagnosis)
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+namespace {
+double est_us[5];
+long est_frames;
+void est_report() {
+    fprintf(stderr, "estimator: front sweep %.1f  clustering %.1f  features + matching %.1f  tagged cloud %.1f  total %.1f us per frame (%ld frames)\n",
+            est_us[0] / est_frames, est_us[1] / est_frames, est_us[2] / est_frames, est_us[3] / est_frames, est_us[4] / est_frames, est_frames);
+}
+struct EstTimer {
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    int k;
+    explicit EstTimer(int k_) : k(k_) {}
+    ~EstTimer() { est_us[k] += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t).count(); }
+};
+}  // namespace
+#define EST_TIME(k) EstTimer est_timer_##k(k)
+#else
+#define EST_TIME(k)
+#endif
+
 float VelocityEstimator::uniform(float lo, float hi) { return dsp_uniform(seed, draws++, lo, hi); }
 
 namespace {
@@ -542,6 +565,10 @@ void VelocityEstimator::finish_device(const EstFeature *feat, int n_dynamic, int
 void VelocityEstimator::estimate(const MapConst &mc, const FrameConst &fc, const float *planes0, const float *pts, int n,
                                  int model, std::vector<float> &out) {
     // rotated outer boundary planes and the in-view rotated cloud, same arithmetic as the device (dsp_dynamic.h:226-257)
+#ifdef EST_TIMING
+    if (est_frames++ == 0) atexit(est_report);
+#endif
+    EST_TIME(4);
     float nrm[12];
     dsp_rotate(planes0, fc.q, fc.qi, nrm);
     dsp_rotate(planes0 + 3 * mc.Nh, fc.q, fc.qi, nrm + 3);
@@ -556,6 +583,7 @@ void VelocityEstimator::estimate(const MapConst &mc, const FrameConst &fc, const
     } else {  // rotation, FOV test, world shift, ground split and the clustering grid's bounding box in one sweep
         statics.resize(3 * (size_t)n + 3);
         nonground.resize(3 * (size_t)n + 3);
+        EST_TIME(0);
         nv = rotate_split(pts, n, fc.q, fc.qi, nrm, fc.cur, filter_res, statics.data(), nonground.data(), split_counts, ng_box);
     }
     if (nv == 0) return;  // :1379 — the previous cloud is kept
@@ -578,7 +606,11 @@ void VelocityEstimator::estimate(const MapConst &mc, const FrameConst &fc, const
     std::vector<ClusterFeature> cur;
     if (!nonground.empty()) {
         std::vector<std::vector<int>> clusters;
-        clusters_impl(nonground.data(), (int)nonground.size() / 3, 2 * filter_res, 5, 10000, 0, clusters, ng_box);  // :1410-1417
+        {
+            EST_TIME(1);
+            clusters_impl(nonground.data(), (int)nonground.size() / 3, 2 * filter_res, 5, 10000, 0, clusters, ng_box);  // :1410-1417
+        }
+        EST_TIME(2);
         std::vector<char> dynamic_flag;
         for (const auto &cl : clusters) {  // :1419-1447
             ClusterFeature f;
