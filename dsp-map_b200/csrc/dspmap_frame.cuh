@@ -1864,6 +1864,8 @@ __device__ __forceinline__ void nb_point1_body(const MapConst &mc, const FrameCo
         }
     }
 }
+// (Fusing the two scans of the draw counts into this kernel's last block — 256 threads, 40 elements each, one scan after the
+// other — cost 24 us per frame against the separate 2 x 1024-thread launch: profiles/r02_variants.jsonl.)
 __global__ void __launch_bounds__(256) k_nb_point1(MapConst mc, FrameConst fc, DevPtrs dp, int phase) {
     pdl_enter();
     nb_point1_body(mc, fc, dp, phase);
