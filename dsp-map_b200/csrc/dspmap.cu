@@ -573,11 +573,7 @@ int enqueue_frame_a(dspmap *m, const FrameConst &fc, const float *d_pts, const f
             CK(cudaEventRecord(m->ev_join, m->side));
         }
         LAUNCH(m, FAM_CK, k_pair_eval, kSMs * 2, EVAL_THREADS, EVAL_SMEM_BYTES, mc, fc, dp, 0);
-#ifdef CZ_TMA
-        LAUNCH(m, FAM_CK, k_cz_chain_tma, std::min(mc.P, kSMs * 2), CZT_THREADS, CZT_SMEM_BYTES, mc, fc, dp);
-#else
         LAUNCH(m, FAM_CK, k_cz_wide, std::min(mc.P, kSMs * 3), 256, sizeof(float) * (2 * (8192 + 8) + 2 * 128), mc, fc, dp);
-#endif
         size_t smem4 = sizeof(float) * (DSP_LUT_HALF + 3 + K4_TERMS) + sizeof(float4) * (256 + mc.OBS);
         if (m->fallback_armed) LAUNCH(m, FAM_CK, k_ck, std::min(mc.P, kSMs * 2), K4_THREADS, smem4, mc, fc, dp);  // returns at once when the pair buffer is used
         if (fc.stage_limit >= 3 && !m->norm_poll) {  // DSPMAP_NORM_POLL=0: behind the C_z pass, beside the weight pass
@@ -589,12 +585,8 @@ int enqueue_frame_a(dspmap *m, const FrameConst &fc, const float *d_pts, const f
             CK(cudaEventRecord(m->ev_join, m->side));
         }
         if (m->nb_pos == 1) { if (d_tagged_early && (rc_nb = enqueue_newborn_early(m, fc, d_tagged_early)) != DSPMAP_OK) return rc_nb; }
-#ifdef W3
-        LAUNCH(m, FAM_WEIGHT, k_weight3, kSMs * 2, 32 * W3_WARPS, w3_smem_bytes(mc.OBS), mc, fc, dp);
-#else
         LAUNCH(m, FAM_WEIGHT, k_weight2, kSMs * 8, W2_THREADS, 0, mc, fc, dp);
         LAUNCH(m, FAM_WEIGHT, k_weight2w, kSMs * 6, W2W_THREADS, 0, mc, fc, dp);
-#endif
         size_t smem5 = sizeof(float) * (DSP_LUT_HALF + 3) + sizeof(float4) * (size_t)mc.NB * (mc.OBS - 1);
         int chunks = (mc.L + K5_THREADS - 1) / K5_THREADS;
         if (m->fallback_armed) LAUNCH(m, FAM_WEIGHT, k_weight, kSMs * 2, K5_THREADS, smem5, mc, fc, dp, chunks);
@@ -981,13 +973,11 @@ int dspmap_create(const dspmap_config *cfg, dspmap **out) {
     CKM(cudaFuncSetAttribute(k_ck, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CKM(cudaFuncSetAttribute(k_pair_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     CKM(cudaFuncSetAttribute(k_cz_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
-    CKM(cudaFuncSetAttribute(k_cz_chain_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, CZT_SMEM_BYTES));
     // the three defaults that can be turned off for A/B measurements (profiles/r02_ab_switches.jsonl)
     m->pdl = !env_off("DSPMAP_PDL");
     m->est_thread = !env_off("DSPMAP_EST_THREAD");
     m->async_update = !env_off("DSPMAP_ASYNC_UPDATE");
     CKM(cudaFuncSetAttribute(k_weight, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CKM(cudaFuncSetAttribute(k_weight3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w3_smem_bytes(128)));
     CKM(cudaFuncSetAttribute(k_resample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RS_WARPS * rs_warp_bytes(DSP_MAX_SLOTS))));
     CKM(cudaStreamSynchronize(m->stream));
     if (gen_tables(m) != DSPMAP_OK) { dspmap_destroy(m); return DSPMAP_E_CUDA; }
@@ -1284,21 +1274,13 @@ int dspmap_shard_phase(dspmap *m, int phase, int n, const float *d_pts, float px
         LAUNCH(m, FAM_CK, k_pair_prep, 1, 1024, 0, mc, dp);
         LAUNCH(m, FAM_CK, k_shard_zero, kSMs * 2, B, 0, mc, fc, dp, 0);
         LAUNCH(m, FAM_CK, k_pair_eval, kSMs * 2, EVAL_THREADS, EVAL_SMEM_BYTES, mc, fc, dp, 1);
-#ifdef CZ_TMA
-        LAUNCH(m, FAM_CK, k_cz_chain_tma, std::min(mc.P, kSMs * 2), CZT_THREADS, CZT_SMEM_BYTES, mc, fc, dp);
-#else
         LAUNCH(m, FAM_CK, k_cz_wide, std::min(mc.P, kSMs * 3), 256, sizeof(float) * (2 * (8192 + 8) + 2 * 128), mc, fc, dp);
-#endif
     } else if (phase == 3) {
         dp.tagged = d_tagged;
         LAUNCH(m, FAM_WEIGHT, k_shard_zero, kSMs * 2, B, 0, mc, fc, dp, 1);
         LAUNCH(m, FAM_WEIGHT, k_pair_eval, kSMs * 2, EVAL_THREADS, EVAL_SMEM_BYTES, mc, fc, dp, 2);
-#ifdef W3
-        LAUNCH(m, FAM_WEIGHT, k_weight3, kSMs * 2, 32 * W3_WARPS, w3_smem_bytes(mc.OBS), mc, fc, dp);
-#else
         LAUNCH(m, FAM_WEIGHT, k_weight2, kSMs * 8, W2_THREADS, 0, mc, fc, dp);
         LAUNCH(m, FAM_WEIGHT, k_weight2w, kSMs * 6, W2W_THREADS, 0, mc, fc, dp);
-#endif
     } else if (phase == 4) {  // owners take their new weights; the newborn split reads them (dsp_dynamic.h:829-866)
         dp.tagged = d_tagged;
         LAUNCH(m, FAM_WEIGHT, k_shard_apply_weights, kSMs * 4, B, 0, mc, dp);

@@ -1276,112 +1276,9 @@ __global__ void __launch_bounds__(CZ_THREADS) k_cz_chain(MapConst mc, FrameConst
         }
     }
 }
-// C_z with a bulk-copy ring (compile-time variant -DCZ_TMA=1, A/B-measured with tests/ab_variants.sh).  A producer thread
-// streams the pyramid's contiguous block of G (and the matching P_d * w values) through a ring of CZT_STAGES shared-memory
-// stages with cp.async.bulk (TMA, 1-D) completing on per-stage mbarriers; the chain warps wait on "full", add their column in
-// list order, and release the stage on "empty": no block-wide barrier inside a pyramid.  Same terms, same order as k_cz_chain.
-#ifndef CZT_STAGES
-#define CZT_STAGES 3
-#endif
-#ifndef CZT_TILE
-#define CZT_TILE 8448   // floats per stage
-#endif
-#ifndef CZT_JT
-#define CZT_JT 256      // particle rows per stage at most
-#endif
-#define CZT_CHAIN_WARPS 4
-#define CZT_MAXNB 128    // neighbour tables staged in shared memory up to this many neighbours (== chain threads)
-#define CZT_THREADS (32 * (CZT_CHAIN_WARPS + 1))
-#define CZT_SMEM_BYTES (CZT_STAGES * (CZT_TILE + 4 + CZT_JT + 4) * 4 + 2 * CZT_STAGES * 8)
-__global__ void __launch_bounds__(CZT_THREADS) k_cz_chain_tma(MapConst mc, FrameConst fc, DevPtrs dp) {
-    pdl_enter();
-    extern __shared__ __align__(128) float cztsm[];
-    float *tiles = cztsm;                                       // CZT_STAGES x (CZT_TILE + 4): + room for the alignment phase
-    float *pws = tiles + CZT_STAGES * (CZT_TILE + 4);           // CZT_STAGES x (CZT_JT + 4)
-    uint64_t *full = reinterpret_cast<uint64_t *>(pws + CZT_STAGES * (CZT_JT + 4));
-    uint64_t *empty = full + CZT_STAGES;
-    __shared__ int s_item;
-    __shared__ int s_len[CZT_MAXNB], s_off[CZT_MAXNB];  // this pyramid's neighbour lists (length, offset into PW): read once, walked per tile
-    if (!use_pair_buffer(mc, dp)) return;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) {
-        for (int s = 0; s < CZT_STAGES; ++s) {
-            cuda::ptx::mbarrier_init(&full[s], 1);                  // the producer's arrive.expect_tx; completes with the bytes
-            cuda::ptx::mbarrier_init(&empty[s], CZT_CHAIN_WARPS);   // one arrival per chain warp
-        }
-        cuda::ptx::fence_mbarrier_init(cuda::ptx::sem_release, cuda::ptx::scope_cluster);
-        cuda::ptx::fence_proxy_async(cuda::ptx::space_shared);
-    }
-    __syncthreads();
-    const float enb = fc.nb_weight * (float)dp.st->n_valid * (float)fc.nb_num;  // :292
-    const float add_k = enb + fc.kappa;
-    unsigned it = 0;  // tiles this CTA has been through: the producer and the chain warps walk the same sequence
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) s_item = atomicAdd(&dp.st->work_k4, 1);
-        __syncthreads();
-        const int wi = s_item;
-        if (wi >= mc.P) break;
-        const int i = wi;
-        const int np = min(dp.obs_cnt[i], mc.OBS - 1);
-        if (np == 0) continue;
-        if (mc.sharded && i % mc.nranks != mc.rank) continue;  // another rank computes this pyramid's C_z
-        const int nn = dp.nbr[i * mc.NBW];
-        const bool staged = nn <= CZT_MAXNB;  // larger neighbourhoods (PYRAMID_NEIGHBOR_N >= 6) read the tables per tile
-        if (staged && tid < nn) {
-            const int b = dp.nbr[i * mc.NBW + 1 + tid];
-            s_len[tid] = dp.plen[b];
-            s_off[tid] = dp.poff[b];
-        }
-        __syncthreads();  // (the barrier at the top of the loop keeps the previous pyramid's readers ahead of these writes)
-        auto len_of = [&](int k) { return staged ? s_len[k] : dp.plen[dp.nbr[i * mc.NBW + 1 + k]]; };
-        auto off_of = [&](int k) { return staged ? s_off[k] : dp.poff[dp.nbr[i * mc.NBW + 1 + k]]; };
-        const int JT = min(CZT_JT, CZT_TILE / np);
-        const float *g = dp.G + (size_t)dp.rowbase[i];
-        int ns = 0, k0 = 0, ln = nn > 0 ? len_of(0) : 0;
-        float acc = 0.f;
-        for (;;) {
-            while (ns < nn && k0 >= ln) {
-                ++ns;
-                k0 = 0;
-                ln = ns < nn ? len_of(ns) : 0;
-            }
-            if (ns >= nn) break;
-            const int cur = min(JT, ln - k0), nfl = cur * np;
-            const float *wsrc = dp.PW + off_of(ns) + k0;
-            // bulk copies move 16-byte units between 16-byte aligned addresses: start at the boundary below and keep the phase
-            const int phg = (int)((reinterpret_cast<size_t>(g) >> 2) & 3), phw = (int)((reinterpret_cast<size_t>(wsrc) >> 2) & 3);
-            const int s = (int)(it % CZT_STAGES);
-            const unsigned par = (it / CZT_STAGES) & 1u;
-            float *ts = tiles + s * (CZT_TILE + 4), *ws = pws + s * (CZT_JT + 4);
-            if (wid == CZT_CHAIN_WARPS) {  // producer warp: one thread feeds the ring
-                if (lane == 0) {
-                    while (!cuda::ptx::mbarrier_try_wait_parity(&empty[s], par ^ 1u)) {}  // a fresh barrier passes at once
-                    const unsigned bg = (unsigned)((phg + nfl + 3) >> 2) * 16u, bw = (unsigned)((phw + cur + 3) >> 2) * 16u;
-                    cuda::ptx::mbarrier_arrive_expect_tx(cuda::ptx::sem_release, cuda::ptx::scope_cta, cuda::ptx::space_shared, &full[s], bg + bw);
-                    cuda::ptx::cp_async_bulk(cuda::ptx::space_cluster, cuda::ptx::space_global, ts, g - phg, bg, &full[s]);
-                    cuda::ptx::cp_async_bulk(cuda::ptx::space_cluster, cuda::ptx::space_global, ws, wsrc - phw, bw, &full[s]);
-                }
-                __syncwarp();
-            } else {
-                while (!cuda::ptx::mbarrier_try_wait_parity(&full[s], par)) {}
-                if (tid < np) {  // the chain: (P_d * w) * g added in list order, one fp32 add per term
-                    acc = cz_chain_rows(acc, ts + phg + tid, ws + phw, np, cur);
-                }
-                __syncwarp();
-                if (lane == 0) cuda::ptx::mbarrier_arrive(&empty[s]);
-            }
-            g += nfl;
-            k0 += cur;
-            ++it;
-        }
-        if (tid < np) {
-            acc += add_k;
-            dp.CZ[i * mc.OBS + tid] = acc;
-            dp.INV[dp.obs_capoff[i] + tid] = 1.f / acc;  // for the newborn normaliser (:802)
-        }
-    }
-}
+// (A bulk-copy ring for this pass — a producer thread streaming stages with cp.async.bulk on mbarriers, chain warps releasing
+// them — was measured twice: 92.5 us with 16 KB stages in round 1, 56.8 - 63.5 us with 33 KB stages in round 2, against 54.6 -
+// 59.6 us for the kernel above; deleted.  profiles/r02_variants.jsonl.)
 // weights (dsp_dynamic.h:743-790): a CTA per 32 particles of a pyramid.  For one neighbour pyramid at a time, ALL threads
 // turn the chunk's contiguous 32 x np tile of G into quotient terms (P_d * g) / C_z (flat, coalesced loads); then warp 0,
 // lane = particle, adds its row in bin order.  Neighbours are visited in table order, so each particle's sum is one fp32
@@ -1600,84 +1497,9 @@ __global__ void __launch_bounds__(W2W_THREADS, 3) k_weight2w(MapConst mc, FrameC
     }
 }
 
-// weights (dsp_dynamic.h:743-790), one WARP per 32 particles of a pyramid, no block-wide barrier.  For one neighbour pyramid
-// at a time the chunk's tile of G — nrows x np values, contiguous — is walked flat (lane l takes values l, l + 32, ...:
-// coalesced loads, several in flight), every value becomes its quotient term (P_d * g) / C_z and lands in the warp's padded
-// shared tile; then lane = particle adds its row in bin order.  Neighbours are visited in table order, so each particle's sum
-// is one fp32 chain in the reference's order.  (The CTA-per-chunk kernel k_weight2 spent more instructions on distributing a
-// tile over its producer warps and on the hand-over than on the terms themselves.)
-#define W3_WARPS 8
-// (P_d * g) / C_z rounded exactly like the IEEE division of the reference (:776) without the division's slow path: nvcc's a / b
-// sends zero and subnormal dividends to a 30-80 instruction subroutine, and the warp pays for it as soon as one lane needs it
-// (g, a product of three table values down to 3e-22, is zero / subnormal / below 2^-100 in 0.3 / 3.2 / 3.9 % of the pairs).
-//   a == 0     ->  +0 (C_z is positive and finite)
-//   a < 2^-96  ->  divided in double and rounded to float once more: innocuous for the quotient of two floats (53 >= 2 * 24 + 2
-//                  bits, subnormal results included; tests/test_host.py checks it against IEEE fp32 division)
-__device__ __forceinline__ float dsp_quot(float a, float b) {
-    if (a == 0.f) return 0.f;
-    if (a < 1.262177448e-29f) return (float)((double)a / (double)b);  // 2^-96
-    return a / b;
-}
-__host__ __device__ __forceinline__ size_t w3_smem_bytes(int OBS) { return (size_t)W3_WARPS * (32 * (size_t)((OBS - 1) | 1) + 128) * sizeof(float); }
-__global__ void __launch_bounds__(32 * W3_WARPS) k_weight3(MapConst mc, FrameConst fc, DevPtrs dp) {
-    pdl_enter();
-    extern __shared__ float w3sm[];
-    if (!use_pair_buffer(mc, dp)) return;
-    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
-    const int ldmax = (mc.OBS - 1) | 1;
-    float *tile = w3sm + (size_t)wl * (32 * ldmax + 128);
-    float *czs = tile + 32 * ldmax;
-    const int nchunks = dp.chunk_off[mc.P];
-    for (;;) {
-        int c = 0;
-        if (lane == 0) c = atomicAdd(&dp.st->work_w2, 1);
-        c = __shfl_sync(FULLMASK, c, 0);
-        if (c >= nchunks) break;
-        if (mc.sharded && c % mc.nranks != mc.rank) continue;  // chunks are dealt round-robin over the ranks
-        const int a = dp.chunk_pyr[c];
-        const int k0 = (c - dp.chunk_off[a]) << 5;
-        const int lb = dp.poff[a];
-        const int nrows = min(32, dp.plen[a] - k0);
-        bool act = false;
-        float pw = 0.f, sum = 0.f;
-        if (lane < nrows) {
-            const float4 p = dp.LP[lb + k0 + lane];
-            pw = p.w;
-            const float dist = sqrtf(p.x * p.x + p.y * p.y + p.z * p.z);
-            const float maxlen = __int_as_float(dp.obs_maxbits[a]);
-            act = !(maxlen > 0.f && dist > maxlen + mc.occl);  // occluded particles keep their weight (:761)
-        }
-        const int nn = dp.nbr[a * mc.NBW];
-        for (int ns = 0; ns < nn; ++ns) {
-            const int b = dp.nbr[a * mc.NBW + 1 + ns];
-            const int np = min(dp.obs_cnt[b], mc.OBS - 1);
-            if (np == 0) continue;
-            const float *gb = dp.G + (size_t)dp.rowbase[b] + (size_t)(dp.cum[b * mc.NBW + dp.nbrev[a * mc.NBW + 1 + ns]] + k0) * np;
-            const int total = nrows * np, ld = np | 1;
-            __syncwarp();  // the previous neighbour's rows have been added
-            for (int z = lane; z < np; z += 32) czs[z] = dp.CZ[(size_t)b * mc.OBS + z];
-            __syncwarp();
-            const unsigned magic = np > 1 ? 0xffffffffu / (unsigned)np + 1u : 0u;  // exact f / np for f < 65536
-#pragma unroll 4
-            for (int f = lane; f < total; f += 32) {
-                const int r = np > 1 ? (int)__umulhi((unsigned)f, magic) : f;
-                const int z = f - r * np;
-                tile[r * ld + z] = dsp_quot(fc.Pd * __ldg(gb + f), czs[z]);
-            }
-            __syncwarp();
-            if (act) {
-                const float *row = tile + lane * ld;
-#pragma unroll 4
-                for (int z = 0; z < np; ++z) sum += row[z];
-            }
-        }
-        if (lane < nrows) {
-            const float w_new = act ? pw * (fc.one_minus_Pd + sum) : pw;
-            if (mc.sharded) dp.NW[lb + k0 + lane] = w_new;  // merged over ranks, applied by the particle's owner
-            else if (act) dp.PA[dp.LA[lb + k0 + lane]].w = w_new;
-        }
-    }
-}
+// (A warp-per-chunk weight kernel without block-wide barriers — the chunk's tile walked flat by the 32 lanes, quotients through
+// an exact fast path for zero / subnormal dividends — took 207 us against 86 us for k_weight2: nine tiles in sequence per warp
+// is too long a chain.  Deleted; profiles/r02_variants.jsonl.)
 
 // Exhaustive check of dsp_div_known for ONE divisor over every float a with |a| <= max (both signs).  What has to be
 // identical to IEEE division is the integer the quotient is turned into, so that is what is compared:
@@ -1943,30 +1765,83 @@ __global__ void k_nb_fill(MapConst mc, FrameConst fc, DevPtrs dp, u64 useed) {
 // the number of free slots of the voxel's mask — the snapshot MS the grouping pass took, i.e. the mask after the arrival pass
 // — it takes the rank-th free slot.  No rounds, no shuffles: every candidate decides for itself.
 // (Round 1 gave a warp to each destination voxel and extracted the minimum key once per free slot: 38 us at cfg2.)
+// Voxels with MANY candidates (a few hundred to a few thousand: voxels near the sensor, where the rays are dense) used to set
+// the kernel's duration — every one of their candidates counted the whole segment, 85 us at cfg2 once the map is populated.
+// Above NBP_HEAVY candidates a thread first counts only against the segment's first NBP_SAMPLE keys (the order inside a
+// segment is arbitrary, so they are a sample): if that many of those alone are smaller than its key as the voxel has free
+// slots, the candidate is not born — exactly, no estimate involved.  The few survivors of a block (those whose key is small
+// enough to have a chance) are then ranked one after the other by whole warps, 32 keys of the segment per step.
+#define NBP_HEAVY 96
+#define NBP_SAMPLE 96
+__device__ __forceinline__ void nb_place_born(const MapConst &mc, const DevPtrs &dp, int cand, int d, ulonglong2 msk, int rank) {
+    const int slot = mask_nth_free(mc, msk, rank);
+    const int a = d * mc.S + slot;
+    dp.PA[a] = dp.CA[cand];                        // position; the weight follows in k_nb_fill
+    dp.PB[a] = make_float4(0.f, 0.f, 0.f, 15.f);   // newborn flag now, velocity in k_nb_fill
+    dp.Caddr[cand] = a;
+    mask_atomic_set(dp.M, d, slot);
+}
 __global__ void __launch_bounds__(256) k_nb_place(MapConst mc, FrameConst fc, DevPtrs dp) {
     pdl_enter();
+    __shared__ int s_surv[256];
+    __shared__ int s_nsurv;
     const int n = min(dp.st->cand_top, dp.cap_cand);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     int born = 0;
-    for (int pos = blockIdx.x * blockDim.x + threadIdx.x; pos < n; pos += gridDim.x * blockDim.x) {
-        const int cand = dp.csegi[pos];
-        const int d = dp.Cdst[cand];
-        const ulonglong2 msk = dp.MS[d];
-        const int nfree = mask_free(mc, msk);
-        if (nfree == 0) continue;
-        const int b = dp.cbase[d], c = dp.ccnt[d], key = dp.cseg[pos];
-        int rank = 0;  // (a candidate whose rank reaches the number of free slots is not born: no need to finish the count)
-        for (int j0 = 0; j0 < c && rank < nfree; j0 += 8) {
-            const int j1 = min(c, j0 + 8);
-            for (int j = j0; j < j1; ++j) rank += dp.cseg[b + j] < key;
+    for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {  // (uniform per block: barriers inside)
+        if (threadIdx.x == 0) s_nsurv = 0;
+        __syncthreads();
+        const int pos = base + threadIdx.x;
+        if (pos < n) {
+            const int cand = dp.csegi[pos];
+            const int d = dp.Cdst[cand];
+            const ulonglong2 msk = dp.MS[d];
+            const int nfree = mask_free(mc, msk);
+            if (nfree > 0) {
+                const int b = dp.cbase[d], c = dp.ccnt[d], key = dp.cseg[pos];
+                const int first = c > NBP_HEAVY ? NBP_SAMPLE : c;
+                int rank = 0;  // (a candidate whose rank reaches the number of free slots is not born: no need to finish the count)
+                for (int j0 = 0; j0 < first && rank < nfree; j0 += 8) {
+                    const int j1 = min(first, j0 + 8);
+                    for (int j = j0; j < j1; ++j) rank += dp.cseg[b + j] < key;
+                }
+                if (rank < nfree) {
+                    if (first == c) {
+                        nb_place_born(mc, dp, cand, d, msk, rank);
+                        ++born;
+                    } else {
+                        s_surv[atomicAdd(&s_nsurv, 1)] = pos;  // still in the race: ranked against the whole segment below
+                    }
+                }
+            }
         }
-        if (rank >= nfree) continue;
-        const int slot = mask_nth_free(mc, msk, rank);
-        const int a = d * mc.S + slot;
-        dp.PA[a] = dp.CA[cand];                        // position; the weight follows in k_nb_fill
-        dp.PB[a] = make_float4(0.f, 0.f, 0.f, 15.f);   // newborn flag now, velocity in k_nb_fill
-        dp.Caddr[cand] = a;
-        mask_atomic_set(dp.M, d, slot);
-        ++born;
+        __syncthreads();
+        const int ns = s_nsurv;
+        for (int k = wid; k < ns; k += 8) {
+            const int p2 = s_surv[k];
+            const int cand = dp.csegi[p2];
+            const int d = dp.Cdst[cand];
+            const ulonglong2 msk = dp.MS[d];
+            const int nfree = mask_free(mc, msk);
+            const int b = dp.cbase[d], c = dp.ccnt[d], key = dp.cseg[p2];
+            int rank = 0;
+            for (int j0 = 0; j0 < c; j0 += 128) {  // four coalesced loads in flight per lane; the race is over once nfree keys are smaller
+                int r4 = 0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = j0 + 32 * u + lane;
+                    r4 += j < c && dp.cseg[b + j] < key;
+                }
+                for (int sft = 16; sft > 0; sft >>= 1) r4 += __shfl_xor_sync(FULLMASK, r4, sft);
+                rank += r4;
+                if (rank >= nfree) break;
+            }
+            if (rank < nfree && lane == 0) {
+                nb_place_born(mc, dp, cand, d, msk, rank);
+                ++born;
+            }
+        }
+        __syncthreads();
     }
     for (int sft = 16; sft > 0; sft >>= 1) born += __shfl_down_sync(FULLMASK, born, sft);
     if ((threadIdx.x & 31) == 0 && born) atomicAdd(&dp.st->n_born, born);

@@ -168,23 +168,6 @@ def test_estimator_on_the_helper_thread_equals_the_calling_thread():
             time.sleep(0.005)
 
 
-def test_double_division_rounds_like_float_division_for_tiny_dividends():
-    """dsp_quot (dspmap_frame.cuh: the weight pass's quotient (P_d * g) / C_z) replaces the IEEE fp32 division of a tiny
-    dividend by a division in double rounded to float once more.  For the quotient of two floats that double rounding is
-    innocuous (53 >= 2*24 + 2 bits), subnormal results included; here it is checked against the host's IEEE fp32 division on
-    the dividends the kernel sends down that path (0 < a < 2^-90) and both C_z-like and arbitrary normal divisors."""
-    rng = np.random.default_rng(1)
-    n = 2_000_000
-    a = rng.integers(1, (127 - 90) << 23, n, dtype=np.uint32).view(np.float32)
-    for b in (np.exp(rng.uniform(np.log(1e-3), np.log(1e6), n)).astype(np.float32),
-              rng.integers(1 << 23, 0x7f000000, n, dtype=np.uint32).view(np.float32)):
-        with np.errstate(all="ignore"):
-            q32 = a / b
-            q64 = (a.astype(np.float64) / b.astype(np.float64)).astype(np.float32)
-        assert np.float32(1e-40) / np.float32(3) != 0          # the host honours subnormals
-        assert np.array_equal(q32.view(np.uint32), q64.view(np.uint32))
-
-
 def test_pdf_index_clamp_can_move_behind_the_conversion():
     """dsp_pdf_i (dspmap_frame.cuh) computes queryNormalPDF's table index (dsp_dynamic.h:1294-1300) as
     min(|trunc(cx*1000 + 10000) - 10000|, 9900) with a saturating conversion instead of clamping cx to +-9.9 first.  The two

@@ -41,7 +41,7 @@ def test_newborn_placement_kernel_equals_the_round1_kernel():
     """k_nb_place (one thread per candidate: rank by counting inside the voxel's grouped segment, rank-th free slot of the
     mask snapshot) against round 1's warp-per-voxel minimum extraction: same candidates in the same slots, same masks, same
     count, on random voxels (full, nearly full, 1 .. 330 candidates per voxel)."""
-    out = build_and_run("check_nb_place", "nb_place.inc", ["k_nb_place"], legacy=["k_nb_place"])
+    out = build_and_run("check_nb_place", "nb_place.inc", ["nb_place_born", "k_nb_place"], legacy=["k_nb_place"])
     assert out.count("identical") == 4 and "DIFFERENT" not in out
 
 
