@@ -1241,6 +1241,18 @@ int dspmap_shard_phase(dspmap *m, int phase, int n, const float *d_pts, float px
         m->launches_frame = 0;
         m->shard_pts = d_pts;
         LAUNCH(m, FAM_SETUP, k_frame_setup, 1, 256, 0, mc, fc, dp);
+        // observation binning (replicated on every rank) on the side branch, beside prediction, exchange and arrival; joined in phase 2
+        CK(cudaEventRecord(m->ev_fork_obs, m->stream));
+        CK(cudaStreamWaitEvent(m->side, m->ev_fork_obs, 0));
+        if (fc.n_points > 0) LAUNCH_ON(m, FAM_OBS, m->side, k_obs_classify, grid_for(fc.n_points, B), B, 0, mc, fc, dp);
+        LAUNCH_ON(m, FAM_OBS, m->side, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{dp.obs_cnt, dp.obs_off, dp.obs_capoff, mc.OBS - 1, mc.P}, ScanJob{}, ScanJob{}}});
+        if (fc.n_points > 0) {
+            LAUNCH_ON(m, FAM_OBS, m->side, k_obs_scatter, grid_for(fc.n_points, B), B, 0, mc, fc, dp);
+            LAUNCH_ON(m, FAM_OBS, m->side, k_obs_rank, grid_for(fc.n_points, B), B, 0, mc, fc, dp);
+        }
+        CK(cudaEventRecord(m->ev_join_obs, m->side));
+        CK(cudaStreamWaitEvent(m->nb, m->ev_fork_obs, 0));  // the newborn branch starts behind this frame's setup
+        m->nb_early_done = false;
         if (fc.vz_mode) {
             LAUNCH(m, FAM_PREDICT, k_vz_count, grid_for(mc.V, B), B, 0, mc, dp);
             LAUNCH(m, FAM_PREDICT, k_scan_blocksum, m->vz_blocks, 256, 0, dp.vzcnt, mc.V, dp.vzblk);
@@ -1257,26 +1269,30 @@ int dspmap_shard_phase(dspmap *m, int phase, int n, const float *d_pts, float px
         LAUNCH(m, FAM_ARRIVE, k_group_owner, kSMs * 2, B, 0, dp, &dp.st->n_mov_owner, dp.mowner, dp.mcnt, dp.mbase, &dp.st->mov_top);
         LAUNCH(m, FAM_ARRIVE, k_group_scatter, kSMs * 4, B, 0, &dp.st->n_mov, dp.MBdst, dp.MBkey, dp.mbase, dp.mfill, dp.mseg, (int *)nullptr);
         LAUNCH(m, FAM_ARRIVE, k_arrive, kSMs * 4, B, 0, mc, fc, dp);
+        CK(cudaEventRecord(m->ev_arrived, m->stream));  // the occupancy masks are final until the newborn placement
         LAUNCH(m, FAM_PYRAMID, k_shard_pack_fov, kSMs * 4, B, 0, mc, dp);
-        // observation binning (replicated on every rank) sits here so that the device has work while the host waits for the
-        // size of the all-gather (shard_host.inc: shard_frame)
-        if (fc.n_points > 0) LAUNCH(m, FAM_OBS, k_obs_classify, grid_for(fc.n_points, B), B, 0, mc, fc, dp);
-        LAUNCH(m, FAM_OBS, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{dp.obs_cnt, dp.obs_off, dp.obs_capoff, mc.OBS - 1, mc.P}, ScanJob{}, ScanJob{}}});
-        if (fc.n_points > 0) {
-            LAUNCH(m, FAM_OBS, k_obs_scatter, grid_for(fc.n_points, B), B, 0, mc, fc, dp);
-            LAUNCH(m, FAM_OBS, k_obs_rank, grid_for(fc.n_points, B), B, 0, mc, fc, dp);
-        }
+        // WHERE this rank's newborn particles land depends only on the cloud, the noise table and the masks after the arrival pass:
+        // candidates, grouping and placement run on the newborn branch, beside the gather and the observation passes (like on one GPU)
+        if ((rc = enqueue_newborn_early(m, fc, d_tagged)) != DSPMAP_OK) return rc;
     } else if (phase == 2) {
         LAUNCH(m, FAM_PYRAMID, k_shard_fov_gathered, kSMs * 8, B, 0, mc, dp, 0);
         LAUNCH(m, FAM_PYRAMID, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{dp.pcount, dp.poff, nullptr, 0, mc.P}, ScanJob{}, ScanJob{}}});
         LAUNCH(m, FAM_PYRAMID, k_shard_fov_gathered, kSMs * 8, B, 0, mc, dp, 1);
         LAUNCH(m, FAM_PYRAMID, k_pyr_sort, std::min(mc.P, kSMs * 3), 512, PYR_SORT_CAP * sizeof(u64), mc, dp, fc.Pd);
+        CK(cudaStreamWaitEvent(m->stream, m->ev_join_obs, 0));
         LAUNCH(m, FAM_CK, k_pair_prep, 1, 1024, 0, mc, dp);
         LAUNCH(m, FAM_CK, k_shard_zero, kSMs * 2, B, 0, mc, fc, dp, 0);
         LAUNCH(m, FAM_CK, k_pair_eval, kSMs * 2, EVAL_THREADS, EVAL_SMEM_BYTES, mc, fc, dp, 1);
         LAUNCH(m, FAM_CK, k_cz_wide, std::min(mc.P, kSMs * 3), 256, sizeof(float) * (2 * (8192 + 8) + 2 * 128), mc, fc, dp);
     } else if (phase == 3) {
         dp.tagged = d_tagged;
+        if (fc.stage_limit >= 3) {  // 1 / C_z is complete on every rank (merged behind phase 2): the normaliser's serial chain runs beside the weight pass
+            CK(cudaEventRecord(m->ev_fork, m->stream));
+            CK(cudaStreamWaitEvent(m->side, m->ev_fork, 0));
+            LAUNCH_ON(m, FAM_NORM, m->side, k_norm, 1, 128, 0, mc, fc, dp, 0);
+            CK(cudaEventRecord(m->ev_join, m->side));
+            m->norm_join_pending = true;
+        }
         LAUNCH(m, FAM_WEIGHT, k_shard_zero, kSMs * 2, B, 0, mc, fc, dp, 1);
         LAUNCH(m, FAM_WEIGHT, k_pair_eval, kSMs * 2, EVAL_THREADS, EVAL_SMEM_BYTES, mc, fc, dp, 2);
         LAUNCH(m, FAM_WEIGHT, k_weight2, kSMs * 8, W2_THREADS, 0, mc, fc, dp);
@@ -1284,12 +1300,10 @@ int dspmap_shard_phase(dspmap *m, int phase, int n, const float *d_pts, float px
     } else if (phase == 4) {  // owners take their new weights; the newborn split reads them (dsp_dynamic.h:829-866)
         dp.tagged = d_tagged;
         LAUNCH(m, FAM_WEIGHT, k_shard_apply_weights, kSMs * 4, B, 0, mc, dp);
-        LAUNCH(m, FAM_NORM, k_norm, 1, 128, 0, mc, fc, dp, 0);
         if (fc.n_tagged > 0 && fc.nb_num > 0) {
             LAUNCH(m, FAM_NEWBORN, k_shard_zero, kSMs, B, 0, mc, fc, dp, 2);
-            LAUNCH(m, FAM_NEWBORN, k_nb_point0, grid_for(fc.n_tagged, B), B, 0, mc, fc, dp);
-            LAUNCH(m, FAM_NEWBORN, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{dp.ninmap, dp.nrank, nullptr, 0, fc.n_tagged}, ScanJob{}, ScanJob{}}});
-            LAUNCH(m, FAM_NEWBORN, k_nb_mask, grid_for((long long)fc.n_tagged * fc.nb_num, B), B, 0, mc, fc, dp);
+            if (!m->nb_early_done && (rc = enqueue_newborn_early(m, fc, d_tagged)) != DSPMAP_OK) return rc;  // (a driver that skipped phase 1's early half)
+            CK(cudaStreamWaitEvent(m->stream, m->ev_nb_early, 0));  // point pass 0 ran there; the slots born early carry flag 15: the split skips them
             LAUNCH(m, FAM_NEWBORN, k_nb_point1, grid_for((long long)fc.n_tagged * 32, B), B, 0, mc, fc, dp, 1);
         }
     } else if (phase == 5) {
@@ -1298,12 +1312,16 @@ int dspmap_shard_phase(dspmap *m, int phase, int n, const float *d_pts, float px
         if (fc.n_tagged > 0 && fc.nb_num > 0) {
             LAUNCH(m, FAM_NEWBORN, k_nb_point1, grid_for((long long)fc.n_tagged * 32, B), B, 0, mc, fc, dp, 2);
             LAUNCH(m, FAM_NEWBORN, k_scan_small, 2, 1024, 0, ScanJobs{{ScanJob{dp.nvcnt, dp.nvoff, nullptr, 0, fc.n_tagged}, ScanJob{dp.nrcnt, dp.nroff, nullptr, 0, fc.n_tagged}, ScanJob{}}});
-            LAUNCH(m, FAM_NEWBORN, k_nb_cand, grid_for((long long)fc.n_tagged * fc.nb_num, B), B, 0, mc, fc, dp);
-            LAUNCH(m, FAM_NEWBORN, k_group_owner, kSMs * 2, B, 0, dp, &dp.st->n_cand_owner, dp.cowner, dp.ccnt, dp.cbase, &dp.st->cand_top);
-            LAUNCH(m, FAM_NEWBORN, k_group_scatter, kSMs * 4, B, 0, &dp.st->n_cand, dp.Cdst, dp.Ckey, dp.cbase, dp.cfill, dp.cseg, dp.csegi);
-            LAUNCH(m, FAM_NEWBORN, k_nb_place, kSMs * 8, B, 0, mc, fc, dp);
+            if (m->norm_join_pending) {  // k_norm (side branch) wrote w_new, which k_nb_fill reads
+                CK(cudaStreamWaitEvent(m->stream, m->ev_join, 0));
+                m->norm_join_pending = false;
+            }
             LAUNCH(m, FAM_NEWBORN, k_nb_fill, kSMs * 8, B, 0, mc, fc, dp, (u64)m->cfg.uniform_seed);
             newborn_ran = 1;
+        }
+        if (m->norm_join_pending) {
+            CK(cudaStreamWaitEvent(m->stream, m->ev_join, 0));
+            m->norm_join_pending = false;
         }
         LAUNCH(m, FAM_RESAMPLE, k_voxel_list, grid_for(mc.V, B), B, 0, mc, dp);
         LAUNCH(m, FAM_RESAMPLE, k_resample, kSMs * (RS_VPW >= 4 ? 4 : 16), 32 * RS_WARPS, RS_WARPS * rs_warp_bytes(mc.S), mc, fc, dp);

@@ -16,11 +16,18 @@
 #include <cstdio>
 #include <cstdlib>
 namespace {
-double est_us[5];
+double est_us[10];
 long est_frames;
 void est_report() {
     fprintf(stderr, "estimator: front sweep %.1f  clustering %.1f  features + matching %.1f  tagged cloud %.1f  total %.1f us per frame (%ld frames)\n",
             est_us[0] / est_frames, est_us[1] / est_frames, est_us[2] / est_frames, est_us[3] / est_frames, est_us[4] / est_frames, est_frames);
+    fprintf(stderr, "clustering: cells %.1f  links (2 passes) %.1f  components %.1f us per frame\n", est_us[5] / est_frames, est_us[6] / est_frames, est_us[7] / est_frames);
+}
+std::chrono::steady_clock::time_point est_last;
+void est_mark(int k) {  // k < 0: start; else: charge the time since the last mark to slot k
+    const auto now = std::chrono::steady_clock::now();
+    if (k >= 0) est_us[k] += std::chrono::duration<double, std::micro>(now - est_last).count();
+    est_last = now;
 }
 struct EstTimer {
     std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
@@ -30,8 +37,10 @@ struct EstTimer {
 };
 }  // namespace
 #define EST_TIME(k) EstTimer est_timer_##k(k)
+#define EST_MARK(k) est_mark(k)
 #else
 #define EST_TIME(k)
+#define EST_MARK(k)
 #endif
 
 float VelocityEstimator::uniform(float lo, float hi) { return dsp_uniform(seed, draws++, lo, hi); }
@@ -192,6 +201,7 @@ bool dense_clusters(const float *xyz, int n, float tol, int min_size, int max_si
     unsigned char *bits = S.bits.data();  // one occupancy bit per cell: the neighbour scan below stays in L1
     S.cell_of.resize(n); S.next.resize(n);
     S.rep.clear(); S.tail.clear(); S.cell_lin.clear(); S.box.clear();
+    EST_MARK(-1);
     // cells numbered in order of first appearance; each cell's point list ascends by index, its head is rep[c]
     const int ox = 2 - lo[0], oy = 2 - lo[1], oz = 2 - lo[2];
     for (int i = 0; i < n; ++i) {
@@ -220,6 +230,7 @@ bool dense_clusters(const float *xyz, int n, float tol, int min_size, int max_si
         S.next[i] = -1;
         S.cell_of[i] = c;
     }
+    EST_MARK(5);
     const int nc = (int)S.rep.size();
     const float *box = S.box.data();
     auto apart = [&](int ca, int cb) {  // no pair of the two cells can be within tol
@@ -295,6 +306,7 @@ bool dense_clusters(const float *xyz, int n, float tol, int min_size, int max_si
                 }
             }
         }
+    EST_MARK(6);
     for (int c = 0; c < nc; ++c) { grid[S.cell_lin[c]] = -1; bits[S.cell_lin[c] >> 3] = 0; }  // leave the grid clean for the next call
     // gather components; a component is discovered at its smallest point index, like a seeded flood fill would
     S.croot.resize(nc);
@@ -318,6 +330,7 @@ bool dense_clusters(const float *xyz, int n, float tol, int min_size, int max_si
         const int s = slot[S.comp_of_root[S.croot[S.cell_of[i]]]];
         if (s >= 0) out[s].push_back(i);  // ascending indices by construction
     }
+    EST_MARK(7);
     return true;
 }
 }  // namespace
