@@ -859,7 +859,7 @@ int dspmap_create(const dspmap_config *cfg, dspmap **out) {
     A(dp.obs_capoff, P + 1); A(dp.OSEG, MP); A(dp.OBSP, P * mc.OBS); A(dp.CZ, P * mc.OBS); A(dp.INV, MP + P * 0 + 1024);
     A(dp.MBA, CL); A(dp.MBB, CL); A(dp.MBkey, CL); A(dp.MBdst, CL); A(dp.MBq, CL);
     A(dp.mcnt, V); A(dp.mfill, V); A(dp.mbase, V); A(dp.mowner, V); A(dp.mseg, CL);
-    A(dp.Fkey, CL); A(dp.Faddr, CL); A(dp.Fq, CL); A(dp.FP, CL); A(dp.PSpay, CL); A(dp.pcount, P); A(dp.pfill, P); A(dp.pub, P); A(dp.rkey, CL); A(dp.poff, P + 1); A(dp.plen, P);
+    A(dp.Fkey, CL); A(dp.Faddr, CL); A(dp.Fq, CL); A(dp.FP, CL); A(dp.PSpay, CL); A(dp.pcount, P); A(dp.pfill, P); A(dp.pub, P); A(dp.rkey, CL); A(dp.rkey2, CL); A(dp.rpos, CL); A(dp.rcount, V + 1); A(dp.poff, P + 1); A(dp.plen, P);
     A(dp.PSkey, CL); A(dp.PSaddr, CL); A(dp.LA, CL); A(dp.LP, CL); A(dp.PW, CL);
     mc.cap_pairs = 512ll << 20;  // 2 GB of fp32 pair terms (of 180 GB); larger frames fall back to the recompute kernels
     A(dp.G, (size_t)mc.cap_pairs + 64); A(dp.cum, P * mc.NBW); A(dp.totlen, P); A(dp.pairs, P + 1); A(dp.rowbase, P + 1);

@@ -67,6 +67,8 @@ struct DevPtrs {
     int *pcount, *pfill, *poff, *plen;
     int *pub;           // per pyramid: movers heading for it this frame (upper bound for the overflow test of k_arrive)
     int *rkey;          // replay scratch: sweep keys of the events to walk
+    int *rkey2, *rpos;  // replay scratch: keys in sweep order; an event's place among the events of its voxel
+    int *rcount;        // replay scratch: events per voxel (V + 1, zero between uses)
     int *PSkey, *PSaddr;
     int *LA;            // per-pyramid sorted list: slot address
     float4 *LP;         // per-pyramid sorted list: px py pz weight (post-prediction)
