@@ -73,6 +73,16 @@ class ShardedDSPMap:
         self.v_lo, self.v_hi = self.z0 * cfg["nx"] * cfg["ny"], self.z1 * cfg["nx"] * cfg["ny"]
         self.P_obs = m.P * m.obs_max
 
+    def bind_current_stream(self):
+        """Run the map's frames on torch's current stream of its device (where torch.distributed enqueues the collectives)."""
+        dev = int(self.map.config.device)
+        h = torch.cuda.current_stream(dev).cuda_stream
+        if h != getattr(self, "_bound_stream", None):
+            if h != 0:
+                self.map.set_stream(h)
+            # (0 = torch's legacy default stream: the library keeps its own stream; sharded_update then synchronises around every collective)
+            self._bound_stream = h
+
     def phase(self, k, n, d_pts, pos, t, quat, d_tagged, n_tagged):
         return self.map.shard_phase(k, n, d_pts, pos, t, quat, d_tagged, n_tagged)
 
@@ -117,26 +127,41 @@ class NcclComm:
 
 
 def sharded_update(sm, comm, n, d_pts, pos, t, quat, d_tagged, n_tagged):
-    """One frame on this rank (all ranks call it with the same cloud, pose and newborn input)."""
+    """One frame on this rank (all ranks call it with the same cloud, pose and newborn input).
+
+    The phases only enqueue kernels, and torch.distributed orders its collectives against torch's CURRENT stream: the map is
+    (re)bound to that stream here, so a collective never reads a slab the phase in front of it has not written yet (the
+    library's side branches are joined into that stream by events).  On torch's legacy default stream, which the library
+    cannot adopt, every hand-over between a phase and a collective is a full synchronisation instead."""
+    sm.bind_current_stream()
+    legacy = sm._bound_stream == 0
+
+    def coll(fn, *a):
+        if legacy:
+            sm.map.synchronize()
+        fn(*a)
+        if legacy:
+            torch.cuda.current_stream(int(sm.map.config.device)).synchronize()
+
     b, N = sm.buf, sm.nranks
     rc = sm.phase(0, n, d_pts, pos, t, quat, d_tagged, n_tagged)
     if rc != 1:
         return rc
-    comm.all_to_all(b.xrecv, b.xsend, N)
+    coll(comm.all_to_all, b.xrecv, b.xsend, N)
     sm.phase(1, n, d_pts, pos, t, quat, d_tagged, n_tagged)
-    comm.all_gather(b.hdr, b.gsend[:HDR], N)                      # counts of registered particles per rank
+    coll(comm.all_gather, b.hdr, b.gsend[:HDR], N)                # counts of registered particles per rank
     counts = b.hdr.view(torch.int32)[::HDR].tolist()              # the one host synchronisation of a sharded frame
     g = gather_size(counts, sm.cap_g)
     sm.map.shard_gather_records(g)
     gs = HDR + g * GREC
-    comm.all_gather(b.grecv[:N * gs], b.gsend[:gs], N)
+    coll(comm.all_gather, b.grecv[:N * gs], b.gsend[:gs], N)
     sm.phase(2, n, d_pts, pos, t, quat, d_tagged, n_tagged)
-    comm.all_reduce_sum(b.czinv[:sm.P_obs + n])
+    coll(comm.all_reduce_sum, b.czinv[:sm.P_obs + n])
     sm.phase(3, n, d_pts, pos, t, quat, d_tagged, n_tagged)
-    comm.all_reduce_sum(b.shared[sm.max_points:sm.max_points + sum(counts)])   # new weights
+    coll(comm.all_reduce_sum, b.shared[sm.max_points:sm.max_points + sum(counts)])   # new weights
     sm.phase(4, n, d_pts, pos, t, quat, d_tagged, n_tagged)
     if n_tagged > 0:
-        comm.all_reduce_sum(b.shared[:n_tagged])                               # newborn split
+        coll(comm.all_reduce_sum, b.shared[:n_tagged])                               # newborn split
     sm.phase(5, n, d_pts, pos, t, quat, d_tagged, n_tagged)
     return 1
 
