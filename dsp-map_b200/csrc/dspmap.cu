@@ -93,7 +93,7 @@ struct dspmap {
     long long upd_h2d_bytes = 0, upd_d2h_bytes = 0;  // what the last dspmap_update call moved over PCIe (cloud, newborn input or cluster velocities; cluster features)
     long long last_d2h_bytes = 0;  // what the last blocking reader call moved over PCIe (count, list, future grid or its rows)
     // sparse copy-out of the future grid into a registered (page-locked) caller buffer (DSPMAP_SPARSE_FUTURE=1)
-    int *d_fcnt = nullptr, *d_foff = nullptr, *d_fidx = nullptr, *d_nf = nullptr, *h_fidx = nullptr, *h_nf = nullptr;
+    int *d_fidx = nullptr, *d_nf = nullptr, *h_fidx = nullptr, *h_nf = nullptr;
     float *d_fval = nullptr, *h_fval = nullptr;
     int fut_guess = 8192;                 // rows copied along with their count
     SparseRows sparse_rows;               // which caller buffer holds the previous call's result, and its non-zero rows
@@ -1370,7 +1370,7 @@ int dspmap_get_occupancy_device(dspmap *m, float thr, float *d_xyz, int cap, int
     if (!m) return DSPMAP_E_BAD_ARG;
     CK(cudaSetDevice(m->cfg.device));
     const MapConst &mc = m->mc;
-    LAUNCH(m, FAM_READER, k_occ_count, m->occ_blocks, 256, 0, mc, m->dp, thr, m->d_blockcnt, d_future);
+    LAUNCH(m, FAM_READER, k_occ_count, m->occ_blocks, 256, 0, mc, m->dp, thr, m->d_blockcnt, d_future, (int *)nullptr, (float *)nullptr, (int *)nullptr);
     LAUNCH(m, FAM_READER, k_occ_write, m->occ_blocks, 256, 0, mc, m->dp, thr, m->d_blockcnt, d_xyz, cap, d_count, m->occ_blocks);
     CK(cudaGetLastError());
     return DSPMAP_OK;
@@ -1379,12 +1379,6 @@ int dspmap_get_occupancy(dspmap *m, float thr, float *xyz_out, int cap, int *n_o
     if (!m) return DSPMAP_E_BAD_ARG;
     CK(cudaSetDevice(m->cfg.device));
     const MapConst &mc = m->mc;
-    int rc = dspmap_get_occupancy_device(m, thr, m->d_xyz, mc.V, m->d_count, future ? m->d_future : nullptr);
-    if (rc != DSPMAP_OK) return rc;
-    CK(cudaMemcpyAsync(m->h_count, m->d_count, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
-    // the occupied-voxel list travels with its count: as many records as the last frames suggest, the rest (rare) after
-    const int guess = xyz_out ? std::min(std::min(m->occ_guess, cap), mc.V) : 0;
-    if (guess > 0) CK(cudaMemcpyAsync(m->h_xyz, m->d_xyz, sizeof(float) * 3 * (size_t)guess, cudaMemcpyDeviceToHost, m->stream));
     const size_t fbytes = sizeof(float) * (size_t)mc.V * mc.T;
     const bool direct = future && m->pinned_user && (char *)future >= (char *)m->pinned_user &&
                         (char *)future + fbytes <= (char *)m->pinned_user + m->pinned_bytes;
@@ -1394,19 +1388,28 @@ int dspmap_get_occupancy(dspmap *m, float thr, float *xyz_out, int cap, int *n_o
     const bool sparse = direct && mc.T > 0;
     int fguess = 0;
     if (sparse) {
-        if (!m->d_fcnt) {
-            if (dalloc(m, &m->d_fcnt, m->occ_blocks + 1) != DSPMAP_OK || dalloc(m, &m->d_foff, m->occ_blocks + 1) != DSPMAP_OK ||
-                dalloc(m, &m->d_fidx, (size_t)mc.V, false) != DSPMAP_OK || dalloc(m, &m->d_fval, (size_t)mc.V * mc.T, false) != DSPMAP_OK ||
+        if (!m->d_fidx) {
+            if (dalloc(m, &m->d_fidx, (size_t)mc.V, false) != DSPMAP_OK || dalloc(m, &m->d_fval, (size_t)mc.V * mc.T, false) != DSPMAP_OK ||
                 dalloc(m, &m->d_nf, 1) != DSPMAP_OK)
                 return DSPMAP_E_CUDA;
             CK(cudaMallocHost(&m->h_fidx, sizeof(int) * (size_t)mc.V));
             CK(cudaMallocHost(&m->h_fval, sizeof(float) * (size_t)mc.V * mc.T));
             CK(cudaMallocHost(&m->h_nf, sizeof(int)));
         }
-        LAUNCH(m, FAM_READER, k_fut_count, m->occ_blocks, 256, 0, mc, m->d_future, m->d_fcnt);
-        LAUNCH(m, FAM_READER, k_scan_small, 1, 1024, 0, ScanJobs{{ScanJob{m->d_fcnt, m->d_foff, nullptr, 0, m->occ_blocks}, ScanJob{}, ScanJob{}}});
-        LAUNCH(m, FAM_READER, k_fut_compact, m->occ_blocks, 256, 0, mc, m->d_future, m->d_foff, m->d_fidx, m->d_fval, m->d_nf, m->occ_blocks);
+        // the reader's first kernel packs the non-zero rows while it reads and clears the grid (no dense device copy, no extra kernels)
+        CK(cudaMemsetAsync(m->d_nf, 0, sizeof(int), m->stream));
+        LAUNCH(m, FAM_READER, k_occ_count, m->occ_blocks, 256, 0, mc, m->dp, thr, m->d_blockcnt, (float *)nullptr, m->d_fidx, m->d_fval, m->d_nf);
+        LAUNCH(m, FAM_READER, k_occ_write, m->occ_blocks, 256, 0, mc, m->dp, thr, m->d_blockcnt, m->d_xyz, mc.V, m->d_count, m->occ_blocks);
         CK(cudaGetLastError());
+    } else {
+        int rc = dspmap_get_occupancy_device(m, thr, m->d_xyz, mc.V, m->d_count, future ? m->d_future : nullptr);
+        if (rc != DSPMAP_OK) return rc;
+    }
+    CK(cudaMemcpyAsync(m->h_count, m->d_count, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    // the occupied-voxel list travels with its count: as many records as the last frames suggest, the rest (rare) after
+    const int guess = xyz_out ? std::min(std::min(m->occ_guess, cap), mc.V) : 0;
+    if (guess > 0) CK(cudaMemcpyAsync(m->h_xyz, m->d_xyz, sizeof(float) * 3 * (size_t)guess, cudaMemcpyDeviceToHost, m->stream));
+    if (sparse) {
         fguess = std::min(m->fut_guess, mc.V);
         CK(cudaMemcpyAsync(m->h_nf, m->d_nf, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
         CK(cudaMemcpyAsync(m->h_fidx, m->d_fidx, sizeof(int) * (size_t)fguess, cudaMemcpyDeviceToHost, m->stream));

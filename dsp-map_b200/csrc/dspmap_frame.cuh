@@ -2143,7 +2143,10 @@ __global__ void k_cleanup(MapConst mc, FrameConst fc, DevPtrs dp, int newborn_ra
 // K8  readers (dsp_dynamic.h:385-438): ordered compaction of occupied voxel centres, future copy-out + zeroing
 // ------------------------------------------------------------------------------------------------------------
 #define OCC_BLOCK 512  // voxels per block
-__global__ void __launch_bounds__(256) k_occ_count(MapConst mc, DevPtrs dp, float thr, int *blockcnt, float *d_future) {
+// fidx != nullptr: the non-zero voxel rows of the future grid are packed into (fidx, fval) as they are read — rows in no
+// particular order, *d_nf counts them (zeroed by the caller) — instead of the dense copy into d_future: the sparse copy-out
+// of the host reader without its three extra kernels.
+__global__ void __launch_bounds__(256) k_occ_count(MapConst mc, DevPtrs dp, float thr, int *blockcnt, float *d_future, int *fidx, float *fval, int *d_nf) {
     pdl_enter();
     __shared__ int s;
     if (threadIdx.x == 0) s = 0;
@@ -2158,6 +2161,33 @@ __global__ void __launch_bounds__(256) k_occ_count(MapConst mc, DevPtrs dp, floa
     __syncthreads();
     if (threadIdx.x == 0) blockcnt[blockIdx.x] = s;
     // future status: copy out (if asked) and clear (:416-424)
+    if (fidx) {
+        const int lane = threadIdx.x & 31;
+        for (int i0 = 0; i0 < OCC_BLOCK; i0 += blockDim.x) {  // (uniform trip count: warp collectives inside)
+            const int v = b + i0 + threadIdx.x;
+            float row[DSP_MAX_T];
+            bool nz = false;
+            if (v < mc.V)
+                for (int t = 0; t < mc.T; ++t) {
+                    row[t] = dp.FUT[(size_t)v * mc.T + t];
+                    nz |= row[t] != 0.f;
+                }
+            const unsigned bal = __ballot_sync(FULLMASK, nz);
+            if (bal == 0u) continue;
+            int base = 0;
+            if (lane == 0) base = atomicAdd(d_nf, __popc(bal));
+            base = __shfl_sync(FULLMASK, base, 0);
+            if (nz) {
+                const int pos = base + __popc(bal & ((1u << lane) - 1u));
+                fidx[pos] = v;
+                for (int t = 0; t < mc.T; ++t) {
+                    fval[(size_t)pos * mc.T + t] = row[t];
+                    dp.FUT[(size_t)v * mc.T + t] = 0.f;
+                }
+            }
+        }
+        return;
+    }
     size_t fb = (size_t)b * mc.T, fe = min((size_t)mc.V, (size_t)b + OCC_BLOCK) * mc.T;
     for (size_t i = fb + threadIdx.x; i < fe; i += blockDim.x) {
         if (d_future) d_future[i] = dp.FUT[i];
@@ -2213,52 +2243,6 @@ __global__ void __launch_bounds__(256) k_occ_write(MapConst mc, DevPtrs dp, floa
 // V x T floats per call (dsp_dynamic.h:416-418), 4.2 MB at cfg2, of which 2.4 % of the voxel rows are non-zero (measured on
 // the reference's state): over PCIe only those rows travel, as (voxel id, T values) records in ascending voxel order, and the
 // host patches the application's array (dspmap_get_occupancy).  Both kernels read the dense device copy k_occ_count made.
-__global__ void __launch_bounds__(256) k_fut_count(MapConst mc, const float *d_future, int *blockcnt) {
-    pdl_enter();
-    __shared__ int s;
-    if (threadIdx.x == 0) s = 0;
-    __syncthreads();
-    const int b = blockIdx.x * OCC_BLOCK;
-    int c = 0;
-    for (int i = threadIdx.x; i < OCC_BLOCK; i += blockDim.x) {
-        const int v = b + i;
-        if (v < mc.V) {
-            bool nz = false;
-            for (int t = 0; t < mc.T; ++t) nz |= d_future[(size_t)v * mc.T + t] != 0.f;
-            c += nz ? 1 : 0;
-        }
-    }
-    for (int d = 16; d > 0; d >>= 1) c += __shfl_down_sync(FULLMASK, c, d);
-    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s, c);
-    __syncthreads();
-    if (threadIdx.x == 0) blockcnt[blockIdx.x] = s;
-}
-__global__ void __launch_bounds__(256) k_fut_compact(MapConst mc, const float *d_future, const int *blockoff, int *fidx, float *fval, int *d_nf, int nblocks) {
-    pdl_enter();
-    __shared__ int wsum[8];
-    const int b = blockIdx.x * OCC_BLOCK;
-    int run = blockoff[blockIdx.x];
-    if (blockIdx.x == 0 && threadIdx.x == 0) *d_nf = blockoff[nblocks];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int i0 = 0; i0 < OCC_BLOCK; i0 += 256) {
-        const int v = b + i0 + threadIdx.x;
-        bool nz = false;
-        if (v < mc.V)
-            for (int t = 0; t < mc.T; ++t) nz |= d_future[(size_t)v * mc.T + t] != 0.f;
-        const unsigned bal = __ballot_sync(FULLMASK, nz);
-        if (lane == 0) wsum[w] = __popc(bal);
-        __syncthreads();
-        int before = 0, tot = 0;
-        for (int k = 0; k < 8; ++k) { const int x = wsum[k]; if (k < w) before += x; tot += x; }
-        if (nz) {
-            const int pos = run + before + __popc(bal & ((1u << lane) - 1u));
-            fidx[pos] = v;
-            for (int t = 0; t < mc.T; ++t) fval[(size_t)pos * mc.T + t] = d_future[(size_t)v * mc.T + t];
-        }
-        run += tot;
-        __syncthreads();
-    }
-}
 __global__ void k_future_clear(MapConst mc, DevPtrs dp) {
     pdl_enter();
     size_t n = (size_t)mc.V * mc.T;
