@@ -89,7 +89,7 @@ struct dspmap {
     int *d_blockcnt = nullptr, *d_blockoff = nullptr, *d_count = nullptr;
     float *d_xyz = nullptr, *d_future = nullptr;
     int occ_blocks = 0;
-    int occ_guess = 4096;  // occupied voxels copied along with the count (twice the last count): one round trip, not two
+    int occ_guess = 4096;  // occupied voxels copied along with the count (the last count + 25 %): one round trip, not two
     long long upd_h2d_bytes = 0, upd_d2h_bytes = 0;  // what the last dspmap_update call moved over PCIe (cloud, newborn input or cluster velocities; cluster features)
     long long last_d2h_bytes = 0;  // what the last blocking reader call moved over PCIe (count, list, future grid or its rows)
     // sparse copy-out of the future grid into a registered (page-locked) caller buffer (DSPMAP_SPARSE_FUTURE=1)
@@ -1390,28 +1390,28 @@ int dspmap_get_occupancy(dspmap *m, float thr, float *xyz_out, int cap, int *n_o
     if (sparse) {
         if (!m->d_fidx) {
             if (dalloc(m, &m->d_fidx, (size_t)mc.V, false) != DSPMAP_OK || dalloc(m, &m->d_fval, (size_t)mc.V * mc.T, false) != DSPMAP_OK ||
-                dalloc(m, &m->d_nf, 1) != DSPMAP_OK)
+                dalloc(m, &m->d_nf, 2) != DSPMAP_OK)  // d_nf[0]: rows, d_nf[1]: occupied voxels (one copy brings both)
                 return DSPMAP_E_CUDA;
             CK(cudaMallocHost(&m->h_fidx, sizeof(int) * (size_t)mc.V));
             CK(cudaMallocHost(&m->h_fval, sizeof(float) * (size_t)mc.V * mc.T));
-            CK(cudaMallocHost(&m->h_nf, sizeof(int)));
+            CK(cudaMallocHost(&m->h_nf, 2 * sizeof(int)));
         }
         // the reader's first kernel packs the non-zero rows while it reads and clears the grid (no dense device copy, no extra kernels)
         CK(cudaMemsetAsync(m->d_nf, 0, sizeof(int), m->stream));
         LAUNCH(m, FAM_READER, k_occ_count, m->occ_blocks, 256, 0, mc, m->dp, thr, m->d_blockcnt, (float *)nullptr, m->d_fidx, m->d_fval, m->d_nf);
-        LAUNCH(m, FAM_READER, k_occ_write, m->occ_blocks, 256, 0, mc, m->dp, thr, m->d_blockcnt, m->d_xyz, mc.V, m->d_count, m->occ_blocks);
+        LAUNCH(m, FAM_READER, k_occ_write, m->occ_blocks, 256, 0, mc, m->dp, thr, m->d_blockcnt, m->d_xyz, mc.V, m->d_nf + 1, m->occ_blocks);
         CK(cudaGetLastError());
     } else {
         int rc = dspmap_get_occupancy_device(m, thr, m->d_xyz, mc.V, m->d_count, future ? m->d_future : nullptr);
         if (rc != DSPMAP_OK) return rc;
     }
-    CK(cudaMemcpyAsync(m->h_count, m->d_count, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    if (!sparse) CK(cudaMemcpyAsync(m->h_count, m->d_count, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
     // the occupied-voxel list travels with its count: as many records as the last frames suggest, the rest (rare) after
     const int guess = xyz_out ? std::min(std::min(m->occ_guess, cap), mc.V) : 0;
     if (guess > 0) CK(cudaMemcpyAsync(m->h_xyz, m->d_xyz, sizeof(float) * 3 * (size_t)guess, cudaMemcpyDeviceToHost, m->stream));
     if (sparse) {
         fguess = std::min(m->fut_guess, mc.V);
-        CK(cudaMemcpyAsync(m->h_nf, m->d_nf, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+        CK(cudaMemcpyAsync(m->h_nf, m->d_nf, 2 * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
         CK(cudaMemcpyAsync(m->h_fidx, m->d_fidx, sizeof(int) * (size_t)fguess, cudaMemcpyDeviceToHost, m->stream));
         CK(cudaMemcpyAsync(m->h_fval, m->d_fval, sizeof(float) * (size_t)fguess * mc.T, cudaMemcpyDeviceToHost, m->stream));
     } else if (future) {
@@ -1427,18 +1427,18 @@ int dspmap_get_occupancy(dspmap *m, float thr, float *xyz_out, int cap, int *n_o
                                cudaMemcpyDeviceToHost, m->stream));
             CK(cudaStreamSynchronize(m->stream));
         }
-        m->fut_guess = std::max(8192, 2 * nf);
+        m->fut_guess = nf + nf / 4 + 1024;  // the row count moves by a few per cent from frame to frame; twice the count doubled the copy
         m->sparse_rows.apply(future, mc.V, mc.T, m->h_fidx, m->h_fval, nf);
         m->last_d2h_bytes = 4 + (long long)std::max(nf, fguess) * (4 + 4 * mc.T);
     } else {
         m->last_d2h_bytes = future ? (long long)fbytes : 0;
     }
     if (m->update_counter > 0 && m->state_event_recorded) absorb_state(m);  // the frame's state copy has landed by now
-    int n = *m->h_count;
+    int n = sparse ? m->h_nf[1] : *m->h_count;
     if (n_out) *n_out = n;
     int ncopy = std::min(n, cap);
     m->last_d2h_bytes += 4 + 12ll * std::max(ncopy, guess);
-    m->occ_guess = std::max(4096, 2 * n);
+    m->occ_guess = n + n / 4 + 512;
     if (xyz_out && ncopy > 0) {
         if (ncopy > guess) {
             CK(cudaMemcpyAsync(m->h_xyz + 3 * (size_t)guess, m->d_xyz + 3 * (size_t)guess, sizeof(float) * 3 * (size_t)(ncopy - guess),
@@ -1501,7 +1501,7 @@ int dspmap_wait_occupancy(dspmap *m, int ticket, const float **xyz, int *n_out, 
         CK(cudaStreamSynchronize(m->copy_stream));
         s.copied = n;
     }
-    m->occ_guess = std::max(4096, 2 * n);
+    m->occ_guess = n + n / 4 + 512;
     if (n_out) *n_out = n;
     if (xyz) *xyz = s.h_xyz;
     if (future) *future = s.with_future ? s.h_future : nullptr;
