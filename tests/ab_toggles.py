@@ -27,7 +27,7 @@ for p in (os.path.join(ROOT, "dsp-map_b200"), os.path.join(ROOT, "tests")):
 
 import numpy as np  # noqa: E402
 
-SWITCHES = ("DSPMAP_PDL", "DSPMAP_EST_THREAD", "DSPMAP_ASYNC_UPDATE")  # defaults that NAME=0 turns off
+SWITCHES = ("DSPMAP_PDL", "DSPMAP_EST_THREAD", "DSPMAP_ASYNC_UPDATE", "DSPMAP_NORM_POLL", "DSPMAP_EST_GPU", "DSPMAP_NB_POS")  # run-time switches
 
 
 def make_map(dm, gpu_map, name, env, **kw):
