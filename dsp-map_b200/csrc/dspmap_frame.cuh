@@ -505,7 +505,7 @@ __device__ __forceinline__ void replay_touch(const void *p) {  // bring the line
 }
 __device__ void arrive_replay(const MapConst &mc, const DevPtrs &dp) {
     __shared__ bool s_last;
-    __shared__ volatile int s_pos;
+    __shared__ int s_pos;  // how far the walk has come (a hint for the prefetching warps: exchanged with shared-memory atomics)
     DevState *st = dp.st;
     const int n_stay = st->n_fov, n_mov = st->n_mov, n_ev = n_stay + n_mov;  // (nobody changes them before phase B)
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
@@ -572,7 +572,7 @@ __device__ void arrive_replay(const MapConst &mc, const DevPtrs &dp) {
         // the other warps run a little ahead of the walk and pull what it is going to read into L1
         const int ahead = blockDim.x - 32;
         for (int r = threadIdx.x - 32; r < n_rel; r += ahead) {
-            while (r > s_pos + 96) {  // (close ahead: an event touches ~1 KB of lines, and they have to still be in L1 when the walk arrives)
+            while (r > atomicOr(&s_pos, 0) + 96) {  // (close ahead: an event touches ~1 KB of lines, and they have to still be in L1 when the walk arrives)
 #ifdef __CUDA_ARCH__
                 __nanosleep(100);
 #endif
@@ -599,7 +599,7 @@ __device__ void arrive_replay(const MapConst &mc, const DevPtrs &dp) {
             else { key_nx = dp.MBkey[e_nx - n_stay]; d_nx = dp.MBdst[e_nx - n_stay]; q_nx = dp.MBq[e_nx - n_stay]; }
         }
         for (int r = 0; r < n_rel; ++r) {
-            if ((r & 15) == 0) s_pos = r;
+            if ((r & 15) == 0) atomicExch(&s_pos, r);
             const int e = e_nx, key = key_nx, q = q_nx, d = d_nx;
             if (r + 1 < n_rel) {
                 e_nx = ev[r + 1];
@@ -639,7 +639,7 @@ __device__ void arrive_replay(const MapConst &mc, const DevPtrs &dp) {
                 ++n_fov;
             }
         }
-        s_pos = n_rel;
+        atomicExch(&s_pos, n_rel);
         st->n_fov = n_fov;
         st->n_moved = n_moved;
         st->n_voxel_full = n_vfull;
