@@ -563,7 +563,7 @@ int enqueue_frame_a(dspmap *m, const FrameConst &fc, const float *d_pts, const f
     LAUNCH(m, FAM_PYRAMID, k_pyr_sort, std::min(mc.P, kSMs * 3), 512, PYR_SORT_CAP * sizeof(u64), mc, dp, fc.Pd);
     CK(cudaStreamWaitEvent(m->stream, m->ev_join_obs, 0));
     if (fc.stage_limit >= 2) {
-        LAUNCH(m, FAM_CK, k_pair_prep, 1, 1024, 0, mc, dp);
+        LAUNCH(m, FAM_CK, k_pair_prep, mc.P > 2048 ? std::min((mc.P + 1023) / 1024, 32) : 1, 1024, 0, mc, dp);
         if (fc.stage_limit >= 3 && m->norm_poll) {  // the newborn normaliser is one long serial chain: it runs beside the C_z pass and takes each 1 / C_z as it appears
             CK(cudaEventRecord(m->ev_fork, m->stream));
             CK(cudaStreamWaitEvent(m->side, m->ev_fork, 0));
@@ -1280,7 +1280,7 @@ int dspmap_shard_phase(dspmap *m, int phase, int n, const float *d_pts, float px
         LAUNCH(m, FAM_PYRAMID, k_shard_fov_gathered, kSMs * 8, B, 0, mc, dp, 1);
         LAUNCH(m, FAM_PYRAMID, k_pyr_sort, std::min(mc.P, kSMs * 3), 512, PYR_SORT_CAP * sizeof(u64), mc, dp, fc.Pd);
         CK(cudaStreamWaitEvent(m->stream, m->ev_join_obs, 0));
-        LAUNCH(m, FAM_CK, k_pair_prep, 1, 1024, 0, mc, dp);
+        LAUNCH(m, FAM_CK, k_pair_prep, mc.P > 2048 ? std::min((mc.P + 1023) / 1024, 32) : 1, 1024, 0, mc, dp);
         LAUNCH(m, FAM_CK, k_shard_zero, kSMs * 2, B, 0, mc, fc, dp, 0);
         LAUNCH(m, FAM_CK, k_pair_eval, kSMs * 2, EVAL_THREADS, EVAL_SMEM_BYTES, mc, fc, dp, 1);
         LAUNCH(m, FAM_CK, k_cz_wide, std::min(mc.P, kSMs * 3), 256, sizeof(float) * (2 * (8192 + 8) + 2 * 128), mc, fc, dp);

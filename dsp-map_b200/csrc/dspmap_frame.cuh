@@ -34,6 +34,7 @@ __global__ void k_frame_setup(MapConst mc, FrameConst fc, DevPtrs dp) {
         s->n_vz = s->n_skipped = 0;
         s->n_occ_voxels = 0;
         s->ticket = 0;
+        s->ticket_prep = 0;
         s->n_rel = 0;
         s->n_mov_fov = 0;
         s->work_eval = s->work_eval2 = s->work_w2 = 0;
@@ -1055,11 +1056,14 @@ __global__ void __launch_bounds__(K5_THREADS) k_weight(MapConst mc, FrameConst f
 // the number of 32-particle chunks of its own list; then the two exclusive scans (rowbase, chunk_off) and the chunk -> pyramid
 // table the pair-buffer kernels index with their queue tickets.  (Round 1 ran this as k_pair_prep + a scan launch and let
 // every work item find its pyramid by binary search over chunk_off.)
+// (With many pyramids — cfg3: 21 600 at 1 degree, 25 neighbours each — the per-pyramid part is spread over several blocks and
+// the block that finishes last does the scans: 0.11 ms of a 0.76 ms frame as a single block.)
 __global__ void __launch_bounds__(1024) k_pair_prep(MapConst mc, DevPtrs dp) {
     pdl_enter();
     __shared__ int wsum[32];
+    __shared__ int s_last;
     unsigned long long local = 0ull;
-    for (int i = threadIdx.x; i < mc.P; i += blockDim.x) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < mc.P; i += gridDim.x * blockDim.x) {
         const int np = min(dp.obs_cnt[i], mc.OBS - 1), nn = dp.nbr[i * mc.NBW];
         int c = 0;
         for (int ns = 0; ns < nn; ++ns) {
@@ -1073,6 +1077,14 @@ __global__ void __launch_bounds__(1024) k_pair_prep(MapConst mc, DevPtrs dp) {
         dp.chunks[i] = (dp.plen[i] + 31) >> 5;
     }
     if (local) atomicAdd(&dp.st->total_pairs, local);
+    if (gridDim.x > 1) {
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = atomicAdd(&dp.st->ticket_prep, 1) == (int)gridDim.x - 1;
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+    }
     __syncthreads();
     block_exclusive_scan(dp.pairs, dp.rowbase, mc.P, wsum);
     block_exclusive_scan(dp.chunks, dp.chunk_off, mc.P, wsum);

@@ -56,6 +56,7 @@ struct DevState {
     int work_k4, work_k5;  // dynamic work queues
     int n_occ_voxels;      // occupied-voxel work list of the resampling kernel
     int ticket;            // "last block done" counter of k_arrive's serial replay
+    int ticket_prep;       // "last block done" counter of k_pair_prep (maps with many pyramids)
     int n_rel;             // events the replay has to walk (movers + registered stayers of the pyramids that can overflow)
     int gather_max;        // sharded maps: upper bound of any rank's registered particles this frame (sizes the all-gather)
     int n_mov_fov;         // local movers heading for a pyramid (part of that bound)
