@@ -1429,6 +1429,7 @@ int dspmap_get_occupancy(dspmap *m, float thr, float *xyz_out, int cap, int *n_o
         CK(cudaMemcpyAsync(direct ? future : m->h_future, m->d_future, fbytes, cudaMemcpyDeviceToHost, m->stream));
         if (direct) m->sparse_rows.invalidate();  // a dense copy went into the buffer: the row list no longer describes it
     }
+    if (sparse) m->sparse_rows.clear_previous(future, mc.V, mc.T);  // host work that needs no new data: done while the device finishes the frame
     CK(cudaStreamSynchronize(m->stream));
     if (sparse) {
         const int nf = *m->h_nf;

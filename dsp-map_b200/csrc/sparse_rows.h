@@ -14,8 +14,10 @@ struct SparseRows {
         owner = nullptr;
         prev.clear();
     }
-    // future: V x T floats; idx[k] / val[k * T .. k * T + T): the nf non-zero rows of the new grid
-    void apply(float *future, int V, int T, const int *idx, const float *val, int nf) {
+    // First half, independent of the new data: the rows that were non-zero last time are cleared.  The reader calls it while it
+    // waits for the device (the patching is bound by cache misses on rows scattered over a few MB, ~5 ns each: 10 k rows cleared
+    // and 10 k written took 0.1 ms behind the synchronisation; the clearing now hides in the wait and leaves the lines warm).
+    void clear_previous(float *future, int V, int T) {
         const size_t row = sizeof(float) * (size_t)T;
         if (owner != future) {  // first use of this array (or something else wrote it in between): clear all of it once
             memset(future, 0, row * (size_t)V);
@@ -23,6 +25,12 @@ struct SparseRows {
         } else {
             for (int v : prev) memset(future + (size_t)v * T, 0, row);
         }
+        prev.clear();
+    }
+    // future: V x T floats; idx[k] / val[k * T .. k * T + T): the nf non-zero rows of the new grid
+    void apply(float *future, int V, int T, const int *idx, const float *val, int nf) {
+        const size_t row = sizeof(float) * (size_t)T;
+        clear_previous(future, V, T);  // (nothing left to do when the reader has called it already)
         for (int k = 0; k < nf; ++k) memcpy(future + (size_t)idx[k] * T, val + (size_t)k * T, row);
         prev.assign(idx, idx + nf);
     }
